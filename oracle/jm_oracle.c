@@ -1,0 +1,401 @@
+/*
+ * oracle/jm_oracle.c -- TEST INFRASTRUCTURE ONLY.  See jm_oracle.h.
+ * Plain-C restatement of JM 19.0's ME + transform/quant leaf algorithms (file:line cited per
+ * function, relative to /root/reference).  Written as clamped-index arithmetic rather than JM's
+ * pointer walking; checked bit-for-bit against the real JM functions (oracle/_ref/libjmref.so).
+ */
+#include "jm_oracle.h"
+#include <stdlib.h>
+#include <string.h>
+
+static inline int iclip(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
+static inline int iabs_(int v) { return v < 0 ? -v : v; }
+
+/* ------------------------------------------------------------------------------------------
+ * Quarter-pel reference planes.  lencod/src/img_luma.c:611-680 (getSubImagesLuma) and helpers
+ * :40-596.  All taps index the PADDED buffer with the index clamped to the padded extent
+ * (img_luma.c:170-237 horizontal, :272-331 vertical); the centre plane [2][2] is filtered
+ * vertically from the un-rounded horizontal intermediates (:347-423).
+ * ---------------------------------------------------------------------------------------- */
+jmo_ref *jmo_ref_create(const uint16_t *luma, int w, int h, int stride, int max_value)
+{
+  jmo_ref *r = (jmo_ref *)calloc(1, sizeof(*r));
+  int W = w + 2 * JMO_PAD_X, H = h + 2 * JMO_PAD_Y;
+  r->w = w; r->h = h; r->W = W; r->H = H;
+  for (int a = 0; a < 4; a++)
+    for (int b = 0; b < 4; b++)
+      r->plane[a][b] = (uint16_t *)malloc((size_t)W * H * sizeof(uint16_t));
+  int *tmp = (int *)malloc((size_t)W * H * sizeof(int));
+  uint16_t *G = r->plane[0][0], *B = r->plane[0][2], *Hh = r->plane[2][0], *J = r->plane[2][2];
+
+  /* integer plane: edge replication, img_luma.c:40-85 */
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++)
+      G[y * W + x] = luma[(size_t)iclip(0, h - 1, y - JMO_PAD_Y) * stride + iclip(0, w - 1, x - JMO_PAD_X)];
+
+#define CX(x) iclip(0, W - 1, (x))
+#define CY(y) iclip(0, H - 1, (y))
+  /* horizontal six-tap (20,-5,1), img_luma.c:151-245; un-rounded copy kept in tmp (:168) */
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++) {
+      const uint16_t *g = G + y * W;
+      int is = 20 * (g[x] + g[CX(x + 1)]) - 5 * (g[CX(x - 1)] + g[CX(x + 2)]) + (g[CX(x - 2)] + g[CX(x + 3)]);
+      tmp[y * W + x] = is;
+      B[y * W + x] = (uint16_t)iclip(0, max_value, (is + 16) >> 5);
+    }
+  /* vertical six-tap, img_luma.c:257-339, and vertical over tmp for [2][2], :347-431 */
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++) {
+      int ya = y, yd = CY(y + 1), yb = CY(y - 1), ye = CY(y + 2), yc = CY(y - 2), yf = CY(y + 3);
+      int is = 20 * (G[ya * W + x] + G[yd * W + x]) - 5 * (G[yb * W + x] + G[ye * W + x]) + (G[yc * W + x] + G[yf * W + x]);
+      Hh[y * W + x] = (uint16_t)iclip(0, max_value, (is + 16) >> 5);
+      int it = 20 * (tmp[ya * W + x] + tmp[yd * W + x]) - 5 * (tmp[yb * W + x] + tmp[ye * W + x]) + (tmp[yc * W + x] + tmp[yf * W + x]);
+      J[y * W + x] = (uint16_t)iclip(0, max_value, (it + 512) >> 10);
+    }
+  /* bilinear quarter-pel planes, img_luma.c:440-596 and the source pairs at :647-678 */
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++) {
+      int i = y * W + x, xr = y * W + CX(x + 1), yd = CY(y + 1) * W + x;
+#define AVG(a, b) (uint16_t)(((a) + (b) + 1) >> 1)
+      r->plane[0][1][i] = AVG(G[i], B[i]);
+      r->plane[1][0][i] = AVG(G[i], Hh[i]);
+      r->plane[1][1][i] = AVG(B[i], Hh[i]);
+      r->plane[1][2][i] = AVG(B[i], J[i]);
+      r->plane[2][1][i] = AVG(Hh[i], J[i]);
+      r->plane[0][3][i] = AVG(B[i], G[xr]);
+      r->plane[1][3][i] = AVG(B[i], Hh[xr]);
+      r->plane[2][3][i] = AVG(J[i], Hh[xr]);
+      r->plane[3][0][i] = AVG(Hh[i], G[yd]);
+      r->plane[3][1][i] = AVG(Hh[i], B[yd]);
+      r->plane[3][2][i] = AVG(J[i], B[yd]);
+      r->plane[3][3][i] = AVG(B[yd], Hh[xr]);
+#undef AVG
+    }
+#undef CX
+#undef CY
+  free(tmp);
+  return r;
+}
+
+void jmo_ref_destroy(jmo_ref *r)
+{
+  if (!r) return;
+  for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) free(r->plane[a][b]);
+  free(r);
+}
+
+void jmo_ref_get_plane(const jmo_ref *r, int fy, int fx, uint16_t *out)
+{
+  memcpy(out, r->plane[fy][fx], (size_t)r->W * r->H * sizeof(uint16_t));
+}
+
+/* UMVLine4X, lencod/inc/refbuf.h:22-26: only the block ORIGIN is clamped, to
+ * [-PAD, size_pad] with size_x_pad = w + PAD_X - 1 - 16 (mbuffer.c:564-565); rows then run linearly. */
+static inline const uint16_t *umv_line(const jmo_ref *r, int qy, int qx)
+{
+  int iy = iclip(-JMO_PAD_Y, r->h + JMO_PAD_Y - 1 - 16, qy >> 2);
+  int ix = iclip(-JMO_PAD_X, r->w + JMO_PAD_X - 1 - 16, qx >> 2);
+  return r->plane[qy & 3][qx & 3] + (size_t)(iy + JMO_PAD_Y) * r->W + (ix + JMO_PAD_X);
+}
+
+/* square spiral, lencod/src/mv_search.c:406-442 */
+void jmo_spiral(int R, int16_t *xy)
+{
+  int k = 1;
+  xy[0] = xy[1] = 0;
+  for (int l = 1; l <= (R > 1 ? R : 1); l++) {
+    for (int i = -l + 1; i < l; i++) {
+      xy[2 * k] = (int16_t)i; xy[2 * k + 1] = (int16_t)-l; k++;
+      xy[2 * k] = (int16_t)i; xy[2 * k + 1] = (int16_t)l;  k++;
+    }
+    for (int i = -l; i <= l; i++) {
+      xy[2 * k] = (int16_t)-l; xy[2 * k + 1] = (int16_t)i; k++;
+      xy[2 * k] = (int16_t)l;  xy[2 * k + 1] = (int16_t)i; k++;
+    }
+  }
+}
+
+/* mvbits[], lencod/src/mv_search.c:366-374: 1 for 0, else 2*floor(log2|v|)+3 */
+int jmo_mvbits(int v)
+{
+  int a = iabs_(v), n = 0;
+  if (!a) return 1;
+  while (a >> (n + 1)) n++;
+  return 2 * n + 3;
+}
+
+/* HadamardSAD4x4, lencod/src/me_distortion.c:175-258: 2-D 4x4 Hadamard, (sum|.| + 1) >> 1 */
+int jmo_hadamard_sad4x4(const int16_t *d)
+{
+  int m[16], t[16], s = 0;
+  for (int c = 0; c < 4; c++) {           /* columns */
+    int a0 = d[c] + d[12 + c], a1 = d[4 + c] + d[8 + c], a2 = d[4 + c] - d[8 + c], a3 = d[c] - d[12 + c];
+    m[c] = a0 + a1; m[8 + c] = a0 - a1; m[4 + c] = a3 + a2; m[12 + c] = a3 - a2;
+  }
+  for (int r = 0; r < 4; r++) {           /* rows */
+    const int *p = m + 4 * r;
+    int a0 = p[0] + p[3], a1 = p[1] + p[2], a2 = p[1] - p[2], a3 = p[0] - p[3];
+    t[4 * r] = a0 + a1; t[4 * r + 1] = a0 - a1; t[4 * r + 2] = a2 + a3; t[4 * r + 3] = a3 - a2;
+  }
+  for (int k = 0; k < 16; k++) s += iabs_(t[k]);
+  return (s + 1) >> 1;
+}
+
+/* HadamardSAD8x8, lencod/src/me_distortion.c:266-341: (sum|.| + 2) >> 2 */
+int jmo_hadamard_sad8x8(const int16_t *d)
+{
+  int a[64], s = 0;
+  for (int i = 0; i < 64; i++) a[i] = d[i];
+  for (int pass = 0; pass < 2; pass++) {
+    int step = pass ? 8 : 1, line = pass ? 1 : 8;
+    for (int l = 0; l < 8; l++) {
+      int *p = a + l * line;
+      for (int len = 4; len >= 1; len >>= 1)     /* butterflies of span 4, 2, 1 */
+        for (int b = 0; b < 8; b += 2 * len)
+          for (int k = 0; k < len; k++) {
+            int u = p[(b + k) * step], v = p[(b + k + len) * step];
+            p[(b + k) * step] = u + v; p[(b + k + len) * step] = u - v;
+          }
+    }
+  }
+  for (int i = 0; i < 64; i++) s += iabs_(a[i]);
+  return (s + 2) >> 2;
+}
+
+/* computeSAD  lencod/src/me_distortion.c:349-426  (partition origin clamped once)
+ * computeSSE  lencod/src/me_distortion.c:1190+     (same addressing, squared differences)
+ * computeSATD lencod/src/me_distortion.c:745-825   (EVERY 4x4 / 8x8 sub-block origin clamped)
+ * Early termination in JM only ever turns a losing candidate into "min_mcost" (mv_search.h:19),
+ * which the strict '<' tests reject, so the complete sum decides identically. */
+int jmo_dist(const jmo_ref *r, const uint16_t *src, int bsx, int bsy, int cx, int cy, int metric, int test8x8)
+{
+  int acc = 0;
+  if (metric != JMO_SATD) {
+    const uint16_t *ref = umv_line(r, cy, cx);
+    for (int y = 0; y < bsy; y++)
+      for (int x = 0; x < bsx; x++) {
+        int d = src[y * bsx + x] - ref[(size_t)y * r->W + x];
+        acc += (metric == JMO_SAD) ? iabs_(d) : d * d;
+      }
+    return acc;
+  }
+  int n = test8x8 ? 8 : 4;
+  int16_t diff[64];
+  for (int by = 0; by < bsy; by += n)
+    for (int bx = 0; bx < bsx; bx += n) {
+      const uint16_t *ref = umv_line(r, cy + (by << 2), cx + (bx << 2));
+      for (int y = 0; y < n; y++)
+        for (int x = 0; x < n; x++)
+          diff[y * n + x] = (int16_t)(src[(by + y) * bsx + bx + x] - ref[(size_t)y * r->W + x]);
+      acc += test8x8 ? jmo_hadamard_sad8x8(diff) : jmo_hadamard_sad4x4(diff);
+    }
+  return acc;
+}
+
+static const int k_bs[8][2] = {{16,16},{16,16},{16,8},{8,16},{8,8},{8,4},{4,8},{4,4}}; /* macroblock.h:58-68 */
+
+static void get_block(const uint16_t *cur, int stride, int px, int py, int bsx, int bsy, uint16_t *out)
+{
+  for (int y = 0; y < bsy; y++)
+    memcpy(out + y * bsx, cur + (size_t)(py + y) * stride + px, bsx * sizeof(uint16_t));
+}
+
+static inline int64_t mvcost(int lambda, int cx, int cy, int px, int py)   /* mv_search.h:100-112 */
+{
+  return (int64_t)lambda * (jmo_mvbits(cx - px) + jmo_mvbits(cy - py));
+}
+
+/* full_search_motion_estimation, lencod/src/me_fullsearch.c:39-103 (rdopt on: no (0,0) bonus) */
+int64_t jmo_full_search(const jmo_ref *r, const uint16_t *cur, int cur_stride, int blocktype,
+                        int pos_x, int pos_y, int pred_x, int pred_y, int center_x, int center_y,
+                        int lambda, int64_t min_mcost, int R, int16_t *mv_out)
+{
+  int bsx = k_bs[blocktype][0], bsy = k_bs[blocktype][1];
+  int max_pos = (2 * R + 1) * (2 * R + 1), best = 0;
+  uint16_t src[256];
+  int16_t *sp = (int16_t *)malloc(sizeof(int16_t) * 2 * max_pos);
+  jmo_spiral(R, sp);
+  get_block(cur, cur_stride, pos_x, pos_y, bsx, bsy, src);
+  int ccx = (pos_x << 2) + center_x, ccy = (pos_y << 2) + center_y;
+  int ppx = (pos_x << 2) + pred_x, ppy = (pos_y << 2) + pred_y;
+  for (int pos = 0; pos < max_pos; pos++) {
+    int cx = ccx + 4 * sp[2 * pos], cy = ccy + 4 * sp[2 * pos + 1];
+    int64_t mc = mvcost(lambda, cx, cy, ppx, ppy);
+    if (mc >= min_mcost) continue;
+    mc += (int64_t)jmo_dist(r, src, bsx, bsy, cx, cy, JMO_SAD, 0) << 5;
+    if (mc < min_mcost) { min_mcost = mc; best = pos; }
+  }
+  mv_out[0] = (int16_t)(center_x + 4 * sp[2 * best]);
+  mv_out[1] = (int16_t)(center_y + 4 * sp[2 * best + 1]);
+  free(sp);
+  return min_mcost;
+}
+
+/* sub_pel_motion_estimation, lencod/src/me_fullsearch.c:186-289 (rdopt on) */
+int64_t jmo_sub_pel(const jmo_ref *r, const uint16_t *cur, int cur_stride, int blocktype,
+                    int pos_x, int pos_y, int pred_x, int pred_y, int mv_x, int mv_y,
+                    const int *lambda3, int64_t min_mcost, int metric_h, int metric_q,
+                    int start_hp, int start_qp, int test8x8, int16_t *mv_out)
+{
+  int bsx = k_bs[blocktype][0], bsy = k_bs[blocktype][1];
+  uint16_t src[256];
+  int16_t sp[18];
+  jmo_spiral(1, sp);
+  get_block(cur, cur_stride, pos_x, pos_y, bsx, bsy, src);
+  int best = 0;
+  for (int pos = start_hp; pos < 9; pos++) {
+    int cx = mv_x + 2 * sp[2 * pos], cy = mv_y + 2 * sp[2 * pos + 1];
+    int64_t mc = mvcost(lambda3[1], cx, cy, pred_x, pred_y);
+    if (mc >= min_mcost) continue;
+    mc += (int64_t)jmo_dist(r, src, bsx, bsy, cx + (pos_x << 2), cy + (pos_y << 2), metric_h, test8x8) << 5;
+    if (mc < min_mcost) { min_mcost = mc; best = pos; }
+  }
+  if (best) { mv_x += 2 * sp[2 * best]; mv_y += 2 * sp[2 * best + 1]; }
+  if (!start_qp) min_mcost = (int64_t)0x7fffffff << 5;   /* DISTBLK_MAX, defines.h:136 */
+  best = 0;
+  for (int pos = start_qp; pos < 9; pos++) {
+    int cx = mv_x + sp[2 * pos], cy = mv_y + sp[2 * pos + 1];
+    int64_t mc = mvcost(lambda3[2], cx, cy, pred_x, pred_y);
+    if (mc >= min_mcost) continue;
+    mc += (int64_t)jmo_dist(r, src, bsx, bsy, cx + (pos_x << 2), cy + (pos_y << 2), metric_q, test8x8) << 5;
+    if (mc < min_mcost) { min_mcost = mc; best = pos; }
+  }
+  if (best) { mv_x += sp[2 * best]; mv_y += sp[2 * best + 1]; }
+  mv_out[0] = (int16_t)mv_x; mv_out[1] = (int16_t)mv_y;
+  return min_mcost;
+}
+
+/* search centre of the fast full search, lencod/src/me_fullfast.c:309-327 (rdopt on) */
+void jmo_ffs_center(int pmv_x, int pmv_y, int R, const int *hq, const int *vq, int16_t *c)
+{
+  int sr = R << 2;
+  c[0] = (int16_t)iclip(hq[0] + sr, hq[1] - sr, ((pmv_x + 2) >> 2) * 4);
+  c[1] = (int16_t)iclip(vq[0] + sr, vq[1] - sr, ((pmv_y + 2) >> 2) * 4);
+}
+
+/* setup_fast_full_search, lencod/src/me_fullfast.c:492-556 (the MACROBLOCK origin is clamped once
+ * per position, :498) + update_full_search_large_blocks :196-260.
+ * block_sad layout [blocktype 0..7][16][max_pos]; slot numbering of each type as JM's. */
+void jmo_ffs_setup(const jmo_ref *r, const uint16_t *cur, int cur_stride, int mb_x, int mb_y,
+                   int center_x, int center_y, int R, uint32_t *bs)
+{
+  int max_pos = (2 * R + 1) * (2 * R + 1);
+  int16_t *sp = (int16_t *)malloc(sizeof(int16_t) * 2 * max_pos);
+  jmo_spiral(R, sp);
+#define BS(t, i) (bs + ((size_t)(t) * 16 + (i)) * max_pos)
+  for (int pos = 0; pos < max_pos; pos++) {
+    int cx = (mb_x << 2) + center_x + 4 * sp[2 * pos], cy = (mb_y << 2) + center_y + 4 * sp[2 * pos + 1];
+    const uint16_t *ref = umv_line(r, cy, cx);
+    for (int b = 0; b < 16; b++) {
+      int bx = (b & 3) * 4, by = (b >> 2) * 4, s = 0;
+      for (int y = 0; y < 4; y++)
+        for (int x = 0; x < 4; x++)
+          s += iabs_((int)ref[(size_t)(by + y) * r->W + bx + x] - (int)cur[(size_t)(mb_y + by + y) * cur_stride + mb_x + bx + x]);
+      BS(7, b)[pos] = (uint32_t)s;
+    }
+  }
+  /* larger blocks: the exact slot arithmetic of me_fullfast.c:207-259 */
+  for (int pos = 0; pos < max_pos; pos++) {
+    for (int i = 0; i < 4; i++) { BS(6, i)[pos] = BS(7, i)[pos] + BS(7, i + 4)[pos]; BS(6, 8 + i)[pos] = BS(7, 8 + i)[pos] + BS(7, 12 + i)[pos]; }
+    for (int i = 0; i < 16; i += 2) BS(5, i)[pos] = BS(7, i)[pos] + BS(7, i + 1)[pos];
+    BS(4, 0)[pos] = BS(6, 0)[pos] + BS(6, 1)[pos];   BS(4, 2)[pos]  = BS(6, 2)[pos] + BS(6, 3)[pos];
+    BS(4, 8)[pos] = BS(6, 8)[pos] + BS(6, 9)[pos];   BS(4, 10)[pos] = BS(6, 10)[pos] + BS(6, 11)[pos];
+    BS(3, 0)[pos] = BS(4, 0)[pos] + BS(4, 8)[pos];   BS(3, 2)[pos]  = BS(4, 2)[pos] + BS(4, 10)[pos];
+    BS(2, 0)[pos] = BS(4, 0)[pos] + BS(4, 2)[pos];   BS(2, 8)[pos]  = BS(4, 8)[pos] + BS(4, 10)[pos];
+    BS(1, 0)[pos] = BS(3, 0)[pos] + BS(3, 2)[pos];
+  }
+#undef BS
+  free(sp);
+}
+
+/* fast_full_search_motion_estimation, lencod/src/me_fullfast.c:618-689 (rdopt on) */
+int64_t jmo_ffs_search(const uint32_t *bs, int R, int blocktype, int block_index, int center_x, int center_y,
+                       int pred_x, int pred_y, int lambda, int64_t min_mcost, int max_mvd, int16_t *mv_out)
+{
+  int max_pos = (2 * R + 1) * (2 * R + 1), best = 0;
+  int16_t *sp = (int16_t *)malloc(sizeof(int16_t) * 2 * max_pos);
+  jmo_spiral(R, sp);
+  const uint32_t *s = bs + ((size_t)blocktype * 16 + block_index) * max_pos;
+  max_mvd -= 1;
+  for (int pos = 0; pos < max_pos; pos++) {
+    int64_t mc = (int64_t)s[pos] << 5;
+    int cx = center_x + 4 * sp[2 * pos], cy = center_y + 4 * sp[2 * pos + 1];
+    int mvd = iabs_(cx - pred_x) > iabs_(cy - pred_y) ? iabs_(cx - pred_x) : iabs_(cy - pred_y);
+    if (mc < min_mcost && mvd < max_mvd) {
+      mc += mvcost(lambda, cx, cy, pred_x, pred_y);
+      if (mc < min_mcost) { min_mcost = mc; best = pos; }
+    }
+  }
+  mv_out[0] = (int16_t)(center_x + 4 * sp[2 * best]);
+  mv_out[1] = (int16_t)(center_y + 4 * sp[2 * best + 1]);
+  free(sp);
+  return min_mcost;
+}
+
+/* forward4x4, lcommon/src/transform.c:20-68 */
+void jmo_forward4x4(int *b)
+{
+  int t[16];
+  for (int i = 0; i < 4; i++) {
+    int *p = b + 4 * i;
+    int t0 = p[0] + p[3], t1 = p[1] + p[2], t2 = p[1] - p[2], t3 = p[0] - p[3];
+    t[4 * i] = t0 + t1; t[4 * i + 1] = (t3 << 1) + t2; t[4 * i + 2] = t0 - t1; t[4 * i + 3] = t3 - (t2 << 1);
+  }
+  for (int i = 0; i < 4; i++) {
+    int t0 = t[i] + t[12 + i], t1 = t[4 + i] + t[8 + i], t2 = t[4 + i] - t[8 + i], t3 = t[i] - t[12 + i];
+    b[i] = t0 + t1; b[4 + i] = t2 + (t3 << 1); b[8 + i] = t0 - t1; b[12 + i] = t3 - (t2 << 1);
+  }
+}
+
+static void fwd8_1d(const int *p, int s, int *o, int os)   /* lcommon/src/transform.c:365-402 */
+{
+  int a0 = p[0] + p[7 * s], a1 = p[s] + p[6 * s], a2 = p[2 * s] + p[5 * s], a3 = p[3 * s] + p[4 * s];
+  int b0 = a0 + a3, b1 = a1 + a2, b2 = a0 - a3, b3 = a1 - a2;
+  a0 = p[0] - p[7 * s]; a1 = p[s] - p[6 * s]; a2 = p[2 * s] - p[5 * s]; a3 = p[3 * s] - p[4 * s];
+  int b4 = a1 + a2 + ((a0 >> 1) + a0), b5 = a0 - a3 - ((a2 >> 1) + a2);
+  int b6 = a0 + a3 - ((a1 >> 1) + a1), b7 = a1 - a2 + ((a3 >> 1) + a3);
+  o[0] = b0 + b1; o[os] = b4 + (b7 >> 2); o[2 * os] = b2 + (b3 >> 1); o[3 * os] = b5 + (b6 >> 2);
+  o[4 * os] = b0 - b1; o[5 * os] = b6 - (b5 >> 2); o[6 * os] = (b2 >> 1) - b3; o[7 * os] = (b4 >> 2) - b7;
+}
+
+/* forward8x8, lcommon/src/transform.c:353-448 */
+void jmo_forward8x8(int *b)
+{
+  int t[64];
+  for (int i = 0; i < 8; i++) fwd8_1d(b + 8 * i, 1, t + 8 * i, 1);
+  for (int i = 0; i < 8; i++) fwd8_1d(t + i, 8, b + i, 8);
+}
+
+/* quant_4x4_normal  lencod/src/quant4x4_normal.c:39-115,  quant_4x4_around  quant4x4_around.c:40-130,
+ * quant_8x8_normal  quant8x8_normal.c:43-107, quant_8x8_around quant8x8_around.c:40-115,
+ * quant_8x8cavlc_normal quant8x8_normal.c:123-202, quant_8x8cavlc_around quant8x8_around.c:133-223 */
+int jmo_quant(int variant, int *coef, int qp, const int *qparams, const uint8_t *scan,
+              const uint8_t *c_cost, int is_cavlc, int arw, int *levels, int *runs, int *fadjust, int *coeff_cost)
+{
+  int n = variant < 2 ? 4 : 8, nn = n * n;
+  int around = variant & 1, cavlc8 = variant >= 4;
+  int qp_per = qp / 6, q_bits = (n == 4 ? 15 : 16) + qp_per, dq = n == 4 ? 4 : 6;
+  int nonzero = 0, nl[4] = {0, 0, 0, 0}, run[4] = {0, 0, 0, 0};
+  int clip = (n == 4) ? is_cavlc : cavlc8;
+  for (int k = 0; k < nn; k++) {
+    int i = scan[2 * k], j = scan[2 * k + 1], idx = j * n + i;
+    int s = cavlc8 ? k / 16 : 0;
+    int *m7 = coef + idx;
+    const int *q = qparams + 3 * idx;
+    if (around && fadjust) fadjust[idx] = 0;
+    if (*m7 == 0) { run[s]++; continue; }
+    int scaled = iabs_(*m7) * q[1];
+    int level = (scaled + q[0]) >> q_bits;
+    if (level == 0) { *m7 = 0; run[s]++; continue; }
+    if (clip && level > 2063) level = 2063;
+    if (around && fadjust) fadjust[idx] = (arw * (scaled - (level << q_bits)) + (1 << q_bits)) >> (q_bits + 1);
+    *coeff_cost += (level > 1) ? 999999 : c_cost[run[s]];
+    if (*m7 < 0) level = -level;
+    *m7 = (((level * q[2]) << qp_per) + (1 << (dq - 1))) >> dq;
+    levels[17 * s * cavlc8 + nl[s]] = level;
+    runs[17 * s * cavlc8 + nl[s]] = run[s];
+    nl[s]++; run[s] = 0; nonzero = 1;
+  }
+  for (int s = 0; s < (cavlc8 ? 4 : 1); s++) levels[17 * s * cavlc8 + nl[s]] = 0;
+  return nonzero;
+}

@@ -1,0 +1,74 @@
+/*
+ * oracle/jm_oracle.h -- TEST INFRASTRUCTURE ONLY (checker, never shipped, never on the product path).
+ *
+ * CPU restatement, in plain C, of the JM 19.0 lencod algorithms on the motion-estimation +
+ * transform/quantisation hot path.  Every function cites the reference file:line it follows
+ * (paths relative to /root/reference).  Parity is PINNED: tests/test_oracle_vs_ref.py checks every
+ * function here against the real JM leaf functions (oracle/_ref/libjmref.so, built from the
+ * reference's own sources by oracle/Makefile) and against tests/golden/ fixtures that were generated
+ * from those same JM functions by tests/golden/make_golden.py.
+ */
+#ifndef JM_ORACLE_H
+#define JM_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JMO_PAD_X 32   /* IMG_PAD_SIZE_X  lencod/inc/defines.h:121 */
+#define JMO_PAD_Y 20   /* IMG_PAD_SIZE_Y  lencod/inc/defines.h:122 */
+
+enum { JMO_SAD = 0, JMO_SSE = 1, JMO_SATD = 2 };   /* ERROR_SAD/SSE/SATD */
+
+/* A reference picture: 16 quarter-pel planes [fy][fx], each (h+40) x (w+64) uint16 samples. */
+typedef struct jmo_ref {
+  int w, h, W, H;          /* picture and padded sizes */
+  uint16_t *plane[4][4];   /* plane[fy][fx][ (y+PAD_Y)*W + (x+PAD_X) ] */
+} jmo_ref;
+
+jmo_ref *jmo_ref_create(const uint16_t *luma, int w, int h, int stride, int max_value);
+void     jmo_ref_destroy(jmo_ref *r);
+void     jmo_ref_get_plane(const jmo_ref *r, int fy, int fx, uint16_t *out);
+
+void jmo_spiral(int search_range, int16_t *xy /* 2*(2R+1)^2 */);
+int  jmo_mvbits(int v);
+
+/* raw (unscaled, never early-terminated) distortion of a bsx x bsy source block against the
+ * reference at absolute quarter-pel position (cand_x, cand_y) */
+int jmo_dist(const jmo_ref *r, const uint16_t *src, int bsx, int bsy, int cand_x, int cand_y,
+             int metric, int test8x8);
+
+int64_t jmo_full_search(const jmo_ref *r, const uint16_t *cur, int cur_stride, int blocktype,
+                        int pos_x, int pos_y, int pred_x, int pred_y, int center_x, int center_y,
+                        int lambda, int64_t min_mcost, int search_range, int16_t *mv_out);
+
+int64_t jmo_sub_pel(const jmo_ref *r, const uint16_t *cur, int cur_stride, int blocktype,
+                    int pos_x, int pos_y, int pred_x, int pred_y, int mv_x, int mv_y,
+                    const int *lambda3, int64_t min_mcost, int metric_h, int metric_q,
+                    int start_hp, int start_qp, int test8x8, int16_t *mv_out);
+
+/* fast full search: 16 4x4 SAD surfaces with the macroblock-origin clamp, 41 partition surfaces */
+void jmo_ffs_center(int pmv_x, int pmv_y, int search_range, const int *max_hmv_q, const int *max_vmv_q,
+                    int16_t *center);
+void jmo_ffs_setup(const jmo_ref *r, const uint16_t *cur, int cur_stride, int mb_x, int mb_y,
+                   int center_x, int center_y, int search_range,
+                   uint32_t *block_sad /* [8][16][max_pos], types 1..7 filled */);
+int64_t jmo_ffs_search(const uint32_t *block_sad, int search_range, int blocktype, int block_index,
+                       int center_x, int center_y, int pred_x, int pred_y, int lambda,
+                       int64_t min_mcost, int max_mvd, int16_t *mv_out);
+
+void jmo_forward4x4(int *blk /* 16, in place */);
+void jmo_forward8x8(int *blk /* 64, in place */);
+int  jmo_hadamard_sad4x4(const int16_t *diff);
+int  jmo_hadamard_sad8x8(const int16_t *diff);
+
+/* variants as in oracle/ref_harness.c::jmref_quant */
+int jmo_quant(int variant, int *coef, int qp, const int *qparams, const uint8_t *scan,
+              const uint8_t *c_cost, int is_cavlc, int adapt_rnd_weight,
+              int *levels, int *runs, int *fadjust, int *coeff_cost);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

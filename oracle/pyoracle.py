@@ -1,0 +1,273 @@
+"""ctypes bindings for the CPU checker libraries.  TEST INFRASTRUCTURE ONLY.
+
+Two libraries live behind this module:
+  * ``oracle/libjmoracle.so``   -- our plain-C restatement (oracle/jm_oracle.c), class ``Oracle``.
+  * ``oracle/_ref/libjmref.so`` -- the REAL JM 19.0 leaf functions, compiled from the reference's own
+    sources by oracle/Makefile and reached through oracle/ref_harness.c, class ``JMRef``.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+The product (jm_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "libjmoracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libjmref.so")
+PAD_X, PAD_Y = 32, 20
+SAD, SSE, SATD = 0, 1, 2
+DISTBLK_MAX = 0x7FFFFFFF << 5   # lencod/inc/defines.h:136
+BLOCK_SIZE = [(16, 16), (16, 16), (16, 8), (8, 16), (8, 8), (8, 4), (4, 8), (4, 4)]
+
+_u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
+_i16p = np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+
+
+def build_oracle():
+    """Compile the restatement (gcc, < 1 s).  Building the checker is not using it."""
+    subprocess.check_call(["make", "-s", "-C", HERE, "all"])
+
+
+def ref_available():
+    return os.path.exists(REF_SO)
+
+
+class Oracle:
+    def __init__(self):
+        if not os.path.exists(ORACLE_SO):
+            build_oracle()
+        L = C.CDLL(ORACLE_SO)
+        self.L = L
+        L.jmo_ref_create.restype = C.c_void_p
+        L.jmo_ref_create.argtypes = [_u16p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.jmo_ref_destroy.argtypes = [C.c_void_p]
+        L.jmo_ref_get_plane.argtypes = [C.c_void_p, C.c_int, C.c_int, _u16p]
+        L.jmo_spiral.argtypes = [C.c_int, _i16p]
+        L.jmo_dist.argtypes = [C.c_void_p, _u16p] + [C.c_int] * 6
+        L.jmo_full_search.restype = C.c_int64
+        L.jmo_full_search.argtypes = [C.c_void_p, _u16p] + [C.c_int] * 9 + [C.c_int64, C.c_int, _i16p]
+        L.jmo_sub_pel.restype = C.c_int64
+        L.jmo_sub_pel.argtypes = [C.c_void_p, _u16p] + [C.c_int] * 8 + [_i32p, C.c_int64] + [C.c_int] * 5 + [_i16p]
+        L.jmo_ffs_center.argtypes = [C.c_int, C.c_int, C.c_int, _i32p, _i32p, _i16p]
+        L.jmo_ffs_setup.argtypes = [C.c_void_p, _u16p] + [C.c_int] * 6 + [_u32p]
+        L.jmo_ffs_search.restype = C.c_int64
+        L.jmo_ffs_search.argtypes = [_u32p] + [C.c_int] * 8 + [C.c_int64, C.c_int, _i16p]
+        L.jmo_forward4x4.argtypes = [_i32p]
+        L.jmo_forward8x8.argtypes = [_i32p]
+        L.jmo_hadamard_sad4x4.argtypes = [_i16p]
+        L.jmo_hadamard_sad8x8.argtypes = [_i16p]
+        L.jmo_quant.argtypes = [C.c_int, _i32p, C.c_int, _i32p, _u8p, _u8p, C.c_int, C.c_int,
+                                _i32p, _i32p, _i32p, _i32p]
+
+    # -- reference planes ---------------------------------------------------------------
+    def ref_create(self, luma, max_value=255):
+        luma = np.ascontiguousarray(luma, np.uint16)
+        h, w = luma.shape
+        return self.L.jmo_ref_create(luma, w, h, w, max_value), (w, h)
+
+    def ref_destroy(self, r):
+        self.L.jmo_ref_destroy(r[0])
+
+    def planes(self, r):
+        w, h = r[1]
+        out = np.empty((4, 4, h + 2 * PAD_Y, w + 2 * PAD_X), np.uint16)
+        for fy in range(4):
+            for fx in range(4):
+                self.L.jmo_ref_get_plane(r[0], fy, fx, out[fy, fx])
+        return out
+
+    def spiral(self, R):
+        out = np.empty(((2 * R + 1) ** 2, 2), np.int16)
+        self.L.jmo_spiral(R, out)
+        return out
+
+    def mvbits(self, v):
+        return self.L.jmo_mvbits(int(v))
+
+    def dist(self, r, cur, blocktype, pos, cand, metric, test8x8=0):
+        bsx, bsy = BLOCK_SIZE[blocktype]
+        src = np.ascontiguousarray(cur[pos[1]:pos[1] + bsy, pos[0]:pos[0] + bsx], np.uint16)
+        return self.L.jmo_dist(r[0], src, bsx, bsy, cand[0], cand[1], metric, test8x8)
+
+    def full_search(self, r, cur, blocktype, pos, pred, center, lam, min_mcost, R):
+        cur = np.ascontiguousarray(cur, np.uint16)
+        mv = np.zeros(2, np.int16)
+        c = self.L.jmo_full_search(r[0], cur, cur.shape[1], blocktype, pos[0], pos[1], pred[0], pred[1],
+                                   center[0], center[1], lam, min_mcost, R, mv)
+        return (int(mv[0]), int(mv[1])), c
+
+    def sub_pel(self, r, cur, blocktype, pos, pred, mv_in, lam3, min_mcost, metric_h, metric_q,
+                start_hp, start_qp, test8x8=0):
+        cur = np.ascontiguousarray(cur, np.uint16)
+        mv = np.zeros(2, np.int16)
+        c = self.L.jmo_sub_pel(r[0], cur, cur.shape[1], blocktype, pos[0], pos[1], pred[0], pred[1],
+                               mv_in[0], mv_in[1], np.asarray(lam3, np.int32), min_mcost, metric_h, metric_q,
+                               start_hp, start_qp, test8x8, mv)
+        return (int(mv[0]), int(mv[1])), c
+
+    def ffs_center(self, pmv, R, hq=(-8192, 8191), vq=(-2048, 2047)):
+        c = np.zeros(2, np.int16)
+        self.L.jmo_ffs_center(pmv[0], pmv[1], R, np.asarray(hq, np.int32), np.asarray(vq, np.int32), c)
+        return int(c[0]), int(c[1])
+
+    def ffs_setup(self, r, cur, mb, center, R):
+        cur = np.ascontiguousarray(cur, np.uint16)
+        bs = np.zeros((8, 16, (2 * R + 1) ** 2), np.uint32)
+        self.L.jmo_ffs_setup(r[0], cur, cur.shape[1], mb[0], mb[1], center[0], center[1], R, bs)
+        return bs
+
+    def ffs_search(self, bs, R, blocktype, block_index, center, pred, lam, min_mcost, max_mvd):
+        mv = np.zeros(2, np.int16)
+        c = self.L.jmo_ffs_search(bs, R, blocktype, block_index, center[0], center[1], pred[0], pred[1],
+                                  lam, min_mcost, max_mvd, mv)
+        return (int(mv[0]), int(mv[1])), c
+
+    # -- transforms / quant ---------------------------------------------------------------
+    def forward4x4(self, blk):
+        b = np.ascontiguousarray(blk, np.int32).copy()
+        self.L.jmo_forward4x4(b.reshape(-1))
+        return b
+
+    def forward8x8(self, blk):
+        b = np.ascontiguousarray(blk, np.int32).copy()
+        self.L.jmo_forward8x8(b.reshape(-1))
+        return b
+
+    def hadamard4x4(self, d):
+        return self.L.jmo_hadamard_sad4x4(np.ascontiguousarray(d, np.int16).reshape(-1))
+
+    def hadamard8x8(self, d):
+        return self.L.jmo_hadamard_sad8x8(np.ascontiguousarray(d, np.int16).reshape(-1))
+
+    def quant(self, variant, coef, qp, qparams, scan, c_cost, is_cavlc, arw=0, cost0=0):
+        return _quant_call(self.L.jmo_quant, None, variant, coef, qp, qparams, scan, c_cost, is_cavlc, arw, cost0)
+
+
+def _quant_call(fn, handle, variant, coef, qp, qparams, scan, c_cost, is_cavlc, arw, cost0):
+    n = 4 if variant < 2 else 8
+    coef = np.ascontiguousarray(coef, np.int32).reshape(n * n).copy()
+    nl = 68 if variant >= 4 else n * n + 1
+    levels = np.zeros(nl, np.int32)
+    runs = np.zeros(nl, np.int32)
+    fadj = np.zeros(n * n, np.int32)
+    cost = np.array([cost0], np.int32)
+    args = [variant, coef, qp, np.ascontiguousarray(qparams, np.int32).reshape(-1),
+            np.ascontiguousarray(scan, np.uint8).reshape(-1), np.ascontiguousarray(c_cost, np.uint8),
+            int(is_cavlc), int(arw), levels, runs, fadj, cost]
+    nz = fn(*( [handle] + args if handle is not None else args))
+    return dict(nonzero=int(nz), coef=coef.reshape(n, n), levels=levels, runs=runs,
+                fadjust=fadj.reshape(n, n), coeff_cost=int(cost[0]))
+
+
+class JMRef:
+    """The real JM leaf functions (oracle/_ref/libjmref.so)."""
+
+    def __init__(self, w, h, search_range=32, metrics=(SAD, SATD, SATD), fast_full=0, rdopt=1,
+                 bitdepth=8, vmv_qpel=2048):
+        L = C.CDLL(REF_SO)
+        self.L = L
+        self.w, self.h, self.R = w, h, search_range
+        L.jmref_open.restype = C.c_void_p
+        L.jmref_open.argtypes = [C.c_int] * 10
+        L.jmref_set_ref.argtypes = [C.c_void_p, _u16p, C.c_int]
+        L.jmref_set_cur.argtypes = [C.c_void_p, _u16p, C.c_int]
+        L.jmref_get_subplane.argtypes = [C.c_void_p, C.c_int, C.c_int, _u16p]
+        L.jmref_full_search.restype = C.c_int64
+        L.jmref_full_search.argtypes = [C.c_void_p] + [C.c_int] * 8 + [C.c_int64, _i16p]
+        L.jmref_sub_pel.restype = C.c_int64
+        L.jmref_sub_pel.argtypes = [C.c_void_p] + [C.c_int] * 7 + [_i32p, C.c_int64, C.c_int, _i16p]
+        L.jmref_dist.restype = C.c_int64
+        L.jmref_dist.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_int64]
+        L.jmref_ffs_setup.argtypes = [C.c_void_p] + [C.c_int] * 4 + [_i16p]
+        L.jmref_ffs_get_sad.argtypes = [C.c_void_p, C.c_int, C.c_int, _u32p, C.c_int]
+        L.jmref_ffs_search.restype = C.c_int64
+        L.jmref_ffs_search.argtypes = [C.c_void_p] + [C.c_int] * 6 + [C.c_int64, _i16p]
+        L.jmref_spiral.argtypes = [C.c_void_p, _i16p, C.c_int]
+        L.jmref_mvbits.argtypes = [C.c_void_p, C.c_int]
+        L.jmref_forward4x4.argtypes = [_i32p]
+        L.jmref_forward8x8.argtypes = [_i32p]
+        L.jmref_hadamard_sad4x4.argtypes = [_i16p]
+        L.jmref_hadamard_sad8x8.argtypes = [_i16p]
+        L.jmref_quant.argtypes = [C.c_void_p, C.c_int, _i32p, C.c_int, _i32p, _u8p, _u8p, C.c_int, C.c_int,
+                                  _i32p, _i32p, _i32p, _i32p]
+        self.h_ = L.jmref_open(w, h, search_range, metrics[0], metrics[1], metrics[2], int(fast_full),
+                               int(rdopt), bitdepth, vmv_qpel)
+
+    def set_ref(self, luma):
+        luma = np.ascontiguousarray(luma, np.uint16)
+        self.L.jmref_set_ref(self.h_, luma, luma.shape[1])
+
+    def set_cur(self, luma):
+        luma = np.ascontiguousarray(luma, np.uint16)
+        self.L.jmref_set_cur(self.h_, luma, luma.shape[1])
+
+    def planes(self):
+        out = np.empty((4, 4, self.h + 2 * PAD_Y, self.w + 2 * PAD_X), np.uint16)
+        for fy in range(4):
+            for fx in range(4):
+                self.L.jmref_get_subplane(self.h_, fy, fx, out[fy, fx])
+        return out
+
+    def spiral(self):
+        n = max(9, (2 * self.R + 1) ** 2)
+        out = np.empty((n, 2), np.int16)
+        self.max_mvd = self.L.jmref_spiral(self.h_, out, n)
+        return out
+
+    def mvbits(self, v):
+        return self.L.jmref_mvbits(self.h_, int(v))
+
+    def full_search(self, blocktype, pos, pred, center, lam, min_mcost):
+        mv = np.zeros(2, np.int16)
+        c = self.L.jmref_full_search(self.h_, blocktype, pos[0], pos[1], pred[0], pred[1], center[0], center[1],
+                                     lam, min_mcost, mv)
+        return (int(mv[0]), int(mv[1])), c
+
+    def sub_pel(self, blocktype, pos, pred, mv_in, lam3, min_mcost, test8x8=0):
+        mv = np.zeros(2, np.int16)
+        c = self.L.jmref_sub_pel(self.h_, blocktype, pos[0], pos[1], pred[0], pred[1], mv_in[0], mv_in[1],
+                                 np.asarray(lam3, np.int32), min_mcost, test8x8, mv)
+        return (int(mv[0]), int(mv[1])), c
+
+    def dist(self, metric, blocktype, pos, cand, test8x8=0, min_mcost=DISTBLK_MAX):
+        return self.L.jmref_dist(self.h_, metric, blocktype, pos[0], pos[1], cand[0], cand[1], test8x8, min_mcost)
+
+    def ffs_setup(self, mb, pmv):
+        c = np.zeros(2, np.int16)
+        self.L.jmref_ffs_setup(self.h_, mb[0], mb[1], pmv[0], pmv[1], c)
+        return int(c[0]), int(c[1])
+
+    def ffs_sad(self, blocktype, block_index):
+        n = (2 * self.R + 1) ** 2
+        out = np.empty(n, np.uint32)
+        self.L.jmref_ffs_get_sad(self.h_, blocktype, block_index, out, n)
+        return out
+
+    def ffs_search(self, blocktype, pos, pred, lam, min_mcost):
+        mv = np.zeros(2, np.int16)
+        c = self.L.jmref_ffs_search(self.h_, blocktype, pos[0], pos[1], pred[0], pred[1], lam, min_mcost, mv)
+        return (int(mv[0]), int(mv[1])), c
+
+    def forward4x4(self, blk):
+        b = np.ascontiguousarray(blk, np.int32).copy()
+        self.L.jmref_forward4x4(b.reshape(-1))
+        return b
+
+    def forward8x8(self, blk):
+        b = np.ascontiguousarray(blk, np.int32).copy()
+        self.L.jmref_forward8x8(b.reshape(-1))
+        return b
+
+    def hadamard4x4(self, d):
+        return self.L.jmref_hadamard_sad4x4(np.ascontiguousarray(d, np.int16).reshape(-1).copy())
+
+    def hadamard8x8(self, d):
+        return self.L.jmref_hadamard_sad8x8(np.ascontiguousarray(d, np.int16).reshape(-1).copy())
+
+    def quant(self, variant, coef, qp, qparams, scan, c_cost, is_cavlc, arw=0, cost0=0):
+        return _quant_call(self.L.jmref_quant, self.h_, variant, coef, qp, qparams, scan, c_cost, is_cavlc, arw, cost0)

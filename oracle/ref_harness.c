@@ -1,0 +1,357 @@
+/*
+ * oracle/ref_harness.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Flat C entry points around the REAL JM 19.0 leaf functions of the ME + transform/quant hot
+ * path.  It is compiled against JM's own headers and linked with JM's own (unmodified) objects
+ * into oracle/_ref/libjmref.so by oracle/Makefile ("make -C oracle ref").  Nothing of JM is
+ * re-implemented here: this file only builds the minimal VideoParameters / InputParameters /
+ * Slice / Macroblock / MEBlock / StorablePicture state each leaf dereferences, then calls it.
+ *
+ * Leaves called (all in /root/reference):
+ *   getSubImagesLuma                     lencod/src/img_luma.c:611
+ *   init_motion_search_module            lencod/src/mv_search.c:315   (spiral + mvbits tables)
+ *   full_search_motion_estimation        lencod/src/me_fullsearch.c:39
+ *   sub_pel_motion_estimation            lencod/src/me_fullsearch.c:186
+ *   setup_fast_full_search               lencod/src/me_fullfast.c:269
+ *   fast_full_search_motion_estimation   lencod/src/me_fullfast.c:618
+ *   computeSAD / computeSATD / computeSSE  lencod/src/me_distortion.c:349,745,1190
+ *   forward4x4 / forward8x8              lcommon/src/transform.c:20,353
+ *   quant_4x4_normal/_around             lencod/src/quant4x4_normal.c:39, quant4x4_around.c:40
+ *   quant_8x8_normal/_around, quant_8x8cavlc_normal/_around   lencod/src/quant8x8_*.c
+ */
+#include <stdint.h>
+#include <string.h>
+#include <stdlib.h>
+
+#include "global.h"
+#include "mbuffer.h"
+#include "memalloc.h"
+#include "img_luma.h"
+#include "mv_search.h"
+#include "me_fullsearch.h"
+#include "me_fullfast.h"
+#include "me_distortion.h"
+#include "transform.h"
+#include "quant4x4.h"
+#include "quant8x8.h"
+#include "refbuf.h"
+
+typedef struct jmref_ctx
+{
+  VideoParameters *p_Vid;
+  InputParameters *p_Inp;
+  Slice           *slice;
+  Macroblock      *mb;
+  StorablePicture *ref;
+  StorablePicture *ref_list[2];
+  imgpel         **cur;        /* current (source) luma, row pointers */
+  int              w, h;
+  MotionVector     stub_pmv;   /* what the stubbed GetMVPredictor returns */
+  QuantParameters *quant;
+  int             *qp_per, *qp_rem;
+} jmref_ctx;
+
+static jmref_ctx *g_ctx; /* the stubs below need it; single-threaded like JM */
+
+static void stub_getNeighbour(Macroblock *currMB, int xN, int yN, int mb_size[2], PixelPos *pix)
+{
+  (void)currMB; (void)xN; (void)yN; (void)mb_size;
+  memset(pix, 0, sizeof(*pix));
+}
+
+static void stub_GetMVPredictor(Macroblock *currMB, PixelPos *block, MotionVector *pmv, short ref_frame,
+                                struct pic_motion_params **mv_info, int list, int mb_x, int mb_y, int bsx, int bsy)
+{
+  (void)currMB; (void)block; (void)ref_frame; (void)mv_info; (void)list; (void)mb_x; (void)mb_y; (void)bsx; (void)bsy;
+  *pmv = g_ctx->stub_pmv;
+}
+
+/* metric codes as JM's: 0 = SAD, 1 = SSE, 2 = SATD (lencod/inc/defines.h ERROR_*) */
+void *jmref_open(int width, int height, int search_range, int metric_f, int metric_h, int metric_q,
+                 int fast_full, int rdopt, int bitdepth, int level_vmv_qpel /* e.g. 2048 for level >= 3.1 */)
+{
+  jmref_ctx *c = (jmref_ctx *)calloc(1, sizeof(*c));
+  VideoParameters *p_Vid = (VideoParameters *)calloc(1, sizeof(VideoParameters));
+  InputParameters *p_Inp = (InputParameters *)calloc(1, sizeof(InputParameters));
+  c->p_Vid = p_Vid; c->p_Inp = p_Inp; c->w = width; c->h = height;
+  p_Vid->p_Inp = p_Inp;
+
+  p_Inp->search_range[0] = p_Inp->search_range[1] = search_range;
+  p_Inp->MEErrorMetric[F_PEL] = metric_f;
+  p_Inp->MEErrorMetric[H_PEL] = metric_h;
+  p_Inp->MEErrorMetric[Q_PEL] = metric_q;
+  p_Inp->ModeDecisionMetric = ERROR_SATD;
+  p_Inp->SearchMode[0] = p_Inp->SearchMode[1] = fast_full ? FAST_FULL_SEARCH : FULL_SEARCH;
+  p_Inp->full_search = 2;              /* RestrictSearchRange = 2: no restriction (all bundled cfgs) */
+  p_Inp->rdopt = rdopt;
+  p_Inp->ChromaMEEnable = 0;
+  p_Inp->OnTheFlyFractMCP = 0;
+
+  p_Vid->max_num_references = 1;
+  p_Vid->bitdepth_luma = (short)bitdepth;
+  p_Vid->max_pel_value_comp[0] = p_Vid->max_pel_value_comp[1] = p_Vid->max_pel_value_comp[2] = (1 << bitdepth) - 1;
+  p_Vid->max_imgpel_value = (short)((1 << bitdepth) - 1);
+  p_Vid->width = width; p_Vid->height = height;
+  p_Vid->padded_size_x      = width + 2 * IMG_PAD_SIZE_X;
+  p_Vid->padded_size_x_m8x8 = p_Vid->padded_size_x - BLOCK_SIZE_8x8;
+  p_Vid->padded_size_x_m4x4 = p_Vid->padded_size_x - BLOCK_SIZE;
+  p_Vid->mb_size[0][0] = p_Vid->mb_size[0][1] = MB_BLOCK_SIZE;
+  p_Vid->getNeighbour = stub_getNeighbour;
+  p_Vid->searchRange.min_x = p_Vid->searchRange.min_y = -(search_range << 2);
+  p_Vid->searchRange.max_x = p_Vid->searchRange.max_y =  (search_range << 2);
+  p_Vid->MaxHmvR[0] = -2047; p_Vid->MaxHmvR[1] = 2047; p_Vid->MaxHmvR[2] = -4096;
+  p_Vid->MaxHmvR[3] = 4095;  p_Vid->MaxHmvR[4] = -8192; p_Vid->MaxHmvR[5] = 8191;
+  p_Vid->MaxVmvR[4] = -level_vmv_qpel;       p_Vid->MaxVmvR[5] = level_vmv_qpel - 1;
+  p_Vid->MaxVmvR[2] = -(level_vmv_qpel / 2); p_Vid->MaxVmvR[3] = level_vmv_qpel / 2 - 1;
+  p_Vid->MaxVmvR[0] = -(level_vmv_qpel / 4) + 1; p_Vid->MaxVmvR[1] = level_vmv_qpel / 4 - 1;
+  p_Vid->active_pps = (pic_parameter_set_rbsp_t *)calloc(1, sizeof(pic_parameter_set_rbsp_t));
+  p_Vid->mb_data = (Macroblock *)calloc(1, sizeof(Macroblock));
+  p_Vid->enc_picture = (StorablePicture *)calloc(1, sizeof(StorablePicture)); /* only ->mv_info is read, by the stub */
+  get_mem2Dint_pad(&p_Vid->imgY_sub_tmp, height, width, IMG_PAD_SIZE_Y, IMG_PAD_SIZE_X);
+
+  init_motion_search_module(p_Vid, p_Inp);
+
+  /* reference picture with its 16 quarter-pel planes (layout of mbuffer.c:438,562-565) */
+  StorablePicture *s = (StorablePicture *)calloc(1, sizeof(StorablePicture));
+  s->size_x = width; s->size_y = height;
+  s->size_x_padded = width + 2 * IMG_PAD_SIZE_X;
+  s->size_y_padded = height + 2 * IMG_PAD_SIZE_Y;
+  s->size_x_pad = width + 2 * IMG_PAD_SIZE_X - 1 - MB_BLOCK_SIZE - IMG_PAD_SIZE_X;
+  s->size_y_pad = height + 2 * IMG_PAD_SIZE_Y - 1 - MB_BLOCK_SIZE - IMG_PAD_SIZE_Y;
+  get_mem2Dpel(&s->imgY, height, width);
+  get_mem4Dpel_pad(&s->imgY_sub, 4, 4, height, width, IMG_PAD_SIZE_Y, IMG_PAD_SIZE_X);
+  s->p_img_sub[0] = s->imgY_sub;
+  s->p_curr_img = s->imgY;
+  s->p_curr_img_sub = s->imgY_sub;
+  c->ref = s;
+  c->ref_list[0] = s; c->ref_list[1] = NULL;
+
+  get_mem2Dpel(&c->cur, height, width);
+  p_Vid->pCurImg = c->cur;
+
+  c->slice = (Slice *)calloc(1, sizeof(Slice));
+  c->slice->p_Vid = p_Vid; c->slice->p_Inp = p_Inp;
+  c->slice->slice_type = P_SLICE;
+  c->slice->listX[0] = c->ref_list;
+  c->slice->listXsize[0] = 1;
+  c->slice->symbol_mode = CAVLC;
+
+  c->mb = (Macroblock *)calloc(1, sizeof(Macroblock));
+  c->mb->p_Vid = p_Vid; c->mb->p_Inp = p_Inp; c->mb->p_Slice = c->slice;
+  c->mb->GetMVPredictor = stub_GetMVPredictor;
+  c->mb->p_SetupFastFullPelSearch = setup_fast_full_search;
+
+  /* quantiser state dereferenced by quant_*: p_Vid->p_Quant->qp_per_matrix */
+  c->quant = (QuantParameters *)calloc(1, sizeof(QuantParameters));
+  c->qp_per = (int *)calloc(128, sizeof(int));
+  c->qp_rem = (int *)calloc(128, sizeof(int));
+  for (int i = 0; i < 128; i++) { c->qp_per[i] = i / 6; c->qp_rem[i] = i % 6; }
+  c->quant->qp_per_matrix = c->qp_per; c->quant->qp_rem_matrix = c->qp_rem;
+  p_Vid->p_Quant = c->quant;
+
+  g_ctx = c;
+  return c;
+}
+
+void jmref_set_ref(void *h, const uint16_t *luma, int stride)
+{
+  jmref_ctx *c = (jmref_ctx *)h;
+  for (int y = 0; y < c->h; y++)
+    memcpy(c->ref->imgY[y], luma + (size_t)y * stride, c->w * sizeof(imgpel));
+  getSubImagesLuma(c->p_Vid, c->ref);
+}
+
+/* out: (h+2*PADY) x (w+2*PADX) samples, row-major, origin = padded top-left */
+void jmref_get_subplane(void *h, int fy, int fx, uint16_t *out)
+{
+  jmref_ctx *c = (jmref_ctx *)h;
+  int W = c->w + 2 * IMG_PAD_SIZE_X, H = c->h + 2 * IMG_PAD_SIZE_Y;
+  for (int y = 0; y < H; y++)
+    memcpy(out + (size_t)y * W, c->ref->imgY_sub[fy][fx][y - IMG_PAD_SIZE_Y] - IMG_PAD_SIZE_X, W * sizeof(imgpel));
+}
+
+void jmref_set_cur(void *h, const uint16_t *luma, int stride)
+{
+  jmref_ctx *c = (jmref_ctx *)h;
+  for (int y = 0; y < c->h; y++)
+    memcpy(c->cur[y], luma + (size_t)y * stride, c->w * sizeof(imgpel));
+}
+
+static const short k_bsize[8][2] = {{16,16},{16,16},{16,8},{8,16},{8,8},{8,4},{4,8},{4,4}};
+
+static void fill_mv_block(jmref_ctx *c, MEBlock *b, int blocktype, int pos_x, int pos_y, int test8x8)
+{
+  VideoParameters *p_Vid = c->p_Vid;
+  memset(b, 0, sizeof(*b));
+  b->p_Vid = p_Vid; b->p_Slice = c->slice;
+  b->blocktype = (short)blocktype;
+  b->blocksize_x = k_bsize[blocktype][0];
+  b->blocksize_y = k_bsize[blocktype][1];
+  b->pos_x = (short)pos_x; b->pos_y = (short)pos_y;
+  b->pos_x2 = (short)(pos_x >> 2); b->pos_y2 = (short)(pos_y >> 2);
+  b->pos_x_padded = (short)(pos_x << 2); b->pos_y_padded = (short)(pos_y << 2);
+  b->block_x = (short)((pos_x & 15) >> 2); b->block_y = (short)((pos_y & 15) >> 2);
+  b->list = 0; b->ref_idx = 0;
+  b->searchRange = p_Vid->searchRange;
+  b->search_pos2 = 9; b->search_pos4 = 9;
+  b->test8x8 = test8x8;
+  b->computePredFPel = p_Vid->computeUniPred[F_PEL];
+  b->computePredHPel = p_Vid->computeUniPred[H_PEL];
+  b->computePredQPel = p_Vid->computeUniPred[Q_PEL];
+  get_mem2Dpel(&b->orig_pic, 1, b->blocksize_x * b->blocksize_y);
+  get_original_block(p_Vid, b);
+  c->mb->pix_x = (short)(pos_x & ~15); c->mb->pix_y = (short)(pos_y & ~15);
+  c->mb->opix_y = (short)(pos_y & ~15);
+}
+
+int64_t jmref_full_search(void *h, int blocktype, int pos_x, int pos_y, int pred_x, int pred_y,
+                          int center_x, int center_y, int lambda, int64_t min_mcost, int16_t *mv_out)
+{
+  jmref_ctx *c = (jmref_ctx *)h; g_ctx = c;
+  MEBlock b; MotionVector pred;
+  fill_mv_block(c, &b, blocktype, pos_x, pos_y, 0);
+  pred.mv_x = (short)pred_x; pred.mv_y = (short)pred_y;
+  b.mv[0].mv_x = (short)center_x; b.mv[0].mv_y = (short)center_y;
+  distblk r = full_search_motion_estimation(c->mb, &pred, &b, (distblk)min_mcost, lambda);
+  mv_out[0] = b.mv[0].mv_x; mv_out[1] = b.mv[0].mv_y;
+  free_mem2Dpel(b.orig_pic);
+  return (int64_t)r;
+}
+
+int64_t jmref_sub_pel(void *h, int blocktype, int pos_x, int pos_y, int pred_x, int pred_y,
+                      int mv_x, int mv_y, const int *lambda3, int64_t min_mcost, int test8x8, int16_t *mv_out)
+{
+  jmref_ctx *c = (jmref_ctx *)h; g_ctx = c;
+  MEBlock b; MotionVector pred; int lam[3] = { lambda3[0], lambda3[1], lambda3[2] };
+  fill_mv_block(c, &b, blocktype, pos_x, pos_y, test8x8);
+  pred.mv_x = (short)pred_x; pred.mv_y = (short)pred_y;
+  b.mv[0].mv_x = (short)mv_x; b.mv[0].mv_y = (short)mv_y;
+  distblk r = sub_pel_motion_estimation(c->mb, &pred, &b, (distblk)min_mcost, lam);
+  mv_out[0] = b.mv[0].mv_x; mv_out[1] = b.mv[0].mv_y;
+  free_mem2Dpel(b.orig_pic);
+  return (int64_t)r;
+}
+
+/* metric: 0 SAD, 1 SSE, 2 SATD; cand = absolute quarter-pel position (pos<<2 + mv) */
+int64_t jmref_dist(void *h, int metric, int blocktype, int pos_x, int pos_y, int cand_x, int cand_y,
+                   int test8x8, int64_t min_mcost)
+{
+  jmref_ctx *c = (jmref_ctx *)h; g_ctx = c;
+  MEBlock b; MotionVector cand;
+  fill_mv_block(c, &b, blocktype, pos_x, pos_y, test8x8);
+  cand.mv_x = (short)cand_x; cand.mv_y = (short)cand_y;
+  distblk r;
+  if (metric == 0)      r = computeSAD (c->ref, &b, (distblk)min_mcost, &cand);
+  else if (metric == 1) r = computeSSE (c->ref, &b, (distblk)min_mcost, &cand);
+  else                  r = computeSATD(c->ref, &b, (distblk)min_mcost, &cand);
+  free_mem2Dpel(b.orig_pic);
+  return (int64_t)r;
+}
+
+/* Fast full search: one setup per macroblock (pmv = 16x16 predictor), then per-partition arg-min. */
+void jmref_ffs_setup(void *h, int mb_pix_x, int mb_pix_y, int pmv_x, int pmv_y, int16_t *center_out)
+{
+  jmref_ctx *c = (jmref_ctx *)h; g_ctx = c;
+  MEBlock b;
+  fill_mv_block(c, &b, 1, mb_pix_x, mb_pix_y, 0);
+  c->stub_pmv.mv_x = (short)pmv_x; c->stub_pmv.mv_y = (short)pmv_y;
+  reset_fast_full_search(c->p_Vid);
+  setup_fast_full_search(c->mb, &b, 0);
+  center_out[0] = c->p_Vid->p_ffast_me->search_center[0][0].mv_x;
+  center_out[1] = c->p_Vid->p_ffast_me->search_center[0][0].mv_y;
+  free_mem2Dpel(b.orig_pic);
+}
+
+void jmref_ffs_get_sad(void *h, int blocktype, int block_index, uint32_t *out, int max_pos)
+{
+  jmref_ctx *c = (jmref_ctx *)h;
+  distpel *s = c->p_Vid->p_ffast_me->BlockSAD[0][0][blocktype][block_index];
+  for (int i = 0; i < max_pos; i++) out[i] = (uint32_t)s[i];
+}
+
+int64_t jmref_ffs_search(void *h, int blocktype, int pos_x, int pos_y, int pred_x, int pred_y,
+                         int lambda, int64_t min_mcost, int16_t *mv_out)
+{
+  jmref_ctx *c = (jmref_ctx *)h; g_ctx = c;
+  MEBlock b; MotionVector pred;
+  fill_mv_block(c, &b, blocktype, pos_x, pos_y, 0);
+  pred.mv_x = (short)pred_x; pred.mv_y = (short)pred_y;
+  distblk r = fast_full_search_motion_estimation(c->mb, &pred, &b, (distblk)min_mcost, lambda);
+  mv_out[0] = b.mv[0].mv_x; mv_out[1] = b.mv[0].mv_y;
+  free_mem2Dpel(b.orig_pic);
+  return (int64_t)r;
+}
+
+int jmref_spiral(void *h, int16_t *out_xy, int max_pos)
+{
+  jmref_ctx *c = (jmref_ctx *)h;
+  for (int i = 0; i < max_pos; i++) {
+    out_xy[2 * i] = c->p_Vid->spiral_search[i].mv_x;
+    out_xy[2 * i + 1] = c->p_Vid->spiral_search[i].mv_y;
+  }
+  return c->p_Vid->max_mvd;
+}
+
+int jmref_mvbits(void *h, int v) { return ((jmref_ctx *)h)->p_Vid->mvbits[v]; }
+
+/* ---- transforms (stateless) ---- */
+static void call_fwd(void (*f)(int **, int **, int, int), int *blk, int n)
+{
+  int *rows[8];
+  for (int i = 0; i < n; i++) rows[i] = blk + i * n;
+  f(rows, rows, 0, 0);
+}
+void jmref_forward4x4(int *blk16) { call_fwd(forward4x4, blk16, 4); }
+void jmref_forward8x8(int *blk64) { call_fwd(forward8x8, blk64, 8); }
+int  jmref_hadamard_sad4x4(short *d) { return HadamardSAD4x4(d); }
+int  jmref_hadamard_sad8x8(short *d) { return HadamardSAD8x8(d); }
+
+/* ---- quantisation ----
+ * variant: 0 quant_4x4_normal, 1 quant_4x4_around, 2 quant_8x8_normal, 3 quant_8x8_around,
+ *          4 quant_8x8cavlc_normal, 5 quant_8x8cavlc_around
+ * coef   : n*n transformed coefficients, row-major (in) -> dequantised coefficients (out)
+ * qparams: n*n triples {OffsetComp, ScaleComp, InvScaleComp}, row-major [j][i]
+ * scan   : n*n pairs {i (horizontal), j (vertical)}
+ * levels/runs: 4x4: [17]; 8x8: [65]; 8x8cavlc: [4][17] each
+ * fadjust: n*n (around variants only)
+ * returns nonzero; *coeff_cost is accumulated into.
+ */
+int jmref_quant(void *h, int variant, int *coef, int qp, const int *qparams, const uint8_t *scan,
+                const uint8_t *c_cost, int is_cavlc, int adapt_rnd_weight,
+                int *levels, int *runs, int *fadjust, int *coeff_cost)
+{
+  jmref_ctx *c = (jmref_ctx *)h; g_ctx = c;
+  int n = (variant < 2) ? 4 : 8;
+  int *rows[8], *frow[8];
+  LevelQuantParams qp_store[64], *qrows[8];
+  int fadj_dummy[64];
+  for (int i = 0; i < n; i++) {
+    rows[i] = coef + i * n;
+    frow[i] = (fadjust ? fadjust : fadj_dummy) + i * n;
+    qrows[i] = qp_store + i * n;
+  }
+  for (int i = 0; i < n * n; i++) {
+    qp_store[i].OffsetComp = qparams[3 * i];
+    qp_store[i].ScaleComp = qparams[3 * i + 1];
+    qp_store[i].InvScaleComp = qparams[3 * i + 2];
+  }
+  c->slice->symbol_mode = is_cavlc ? CAVLC : CABAC;
+  c->p_Vid->AdaptRndWeight = adapt_rnd_weight;
+  QuantMethods q; memset(&q, 0, sizeof(q));
+  q.block_x = 0; q.block_y = 0; q.qp = qp;
+  q.ACLevel = levels; q.ACRun = runs; q.fadjust = frow;
+  q.q_params = qrows; q.coeff_cost = coeff_cost;
+  q.pos_scan = (const byte (*)[2])scan; q.c_cost = c_cost;
+  if (variant >= 4) {
+    /* cofAC[k][0|1][..] for the four interleaved CAVLC sub-blocks */
+    int *lv[4][2]; int **cof[4];
+    for (int k = 0; k < 4; k++) { lv[k][0] = levels + 17 * k; lv[k][1] = runs + 17 * k; cof[k] = lv[k]; }
+    return (variant == 4) ? quant_8x8cavlc_normal(c->mb, rows, &q, cof) : quant_8x8cavlc_around(c->mb, rows, &q, cof);
+  }
+  switch (variant) {
+    case 0: return quant_4x4_normal(c->mb, rows, &q);
+    case 1: return quant_4x4_around(c->mb, rows, &q);
+    case 2: return quant_8x8_normal(c->mb, rows, &q);
+    default: return quant_8x8_around(c->mb, rows, &q);
+  }
+}

@@ -1,0 +1,153 @@
+"""Pins the oracle (oracle/jm_oracle.c) to the REAL JM 19.0 leaf functions (oracle/_ref/libjmref.so,
+compiled from the reference's own sources).  CPU only.  Skipped when the reference build is absent."""
+import numpy as np
+import pytest
+
+from jm_b200 import h264_tables as T
+from jm_b200 import synth
+from oracle import pyoracle as po
+
+W, H, R = 96, 64, 8
+
+
+@pytest.fixture(scope="module")
+def pair(oracle, have_ref):
+    f = synth.luma_frames(W, H, 2, seed=7, motion=(3, -2))
+    ref = po.JMRef(W, H, search_range=R)
+    ref.set_ref(f[0]); ref.set_cur(f[1])
+    r = oracle.ref_create(f[0])
+    yield oracle, ref, r, f
+    oracle.ref_destroy(r)
+
+
+def test_subpel_planes(pair):
+    o, ref, r, f = pair
+    a, b = o.planes(r), ref.planes()
+    for fy in range(4):
+        for fx in range(4):
+            assert np.array_equal(a[fy, fx], b[fy, fx]), (fy, fx)
+
+
+def test_subpel_planes_extreme_values(oracle, have_ref):
+    rng = np.random.default_rng(3)
+    img = rng.choice([0, 255], size=(H, W)).astype(np.uint16)      # forces the iClip1 clamps
+    ref = po.JMRef(W, H, search_range=R); ref.set_ref(img)
+    r = oracle.ref_create(img)
+    assert np.array_equal(oracle.planes(r), ref.planes())
+    oracle.ref_destroy(r)
+
+
+def test_spiral_and_mvbits(pair):
+    o, ref, r, f = pair
+    assert np.array_equal(o.spiral(R), ref.spiral()[:(2 * R + 1) ** 2])
+    for v in list(range(-130, 131)) + [255, -255, ref.max_mvd, -ref.max_mvd]:   # table spans +-max_mvd
+        assert o.mvbits(v) == ref.mvbits(v), v
+    big = po.JMRef(64, 64, search_range=32); big.spiral()
+    assert big.max_mvd == 1023
+    for v in [256, 511, 512, 1023, -1023]:
+        assert o.mvbits(v) == big.mvbits(v), v
+
+
+@pytest.mark.parametrize("metric", [po.SAD, po.SSE, po.SATD])
+def test_distortion(pair, metric):
+    o, ref, r, f = pair
+    rng = np.random.default_rng(metric)
+    for _ in range(300):
+        bt = int(rng.integers(1, 8))
+        bsx, bsy = po.BLOCK_SIZE[bt]
+        pos = (int(rng.integers(0, (W - bsx) // 4 + 1)) * 4, int(rng.integers(0, (H - bsy) // 4 + 1)) * 4)
+        # include candidates far outside the picture so every clamp rule is hit
+        cand = (pos[0] * 4 + int(rng.integers(-200, 200)), pos[1] * 4 + int(rng.integers(-160, 160)))
+        t8 = int(metric == po.SATD and bt <= 4 and rng.integers(0, 2))
+        assert o.dist(r, f[1], bt, pos, cand, metric, t8) << 5 == ref.dist(metric, bt, pos, cand, t8)
+
+
+def test_full_search(pair):
+    o, ref, r, f = pair
+    rng = np.random.default_rng(11)
+    for _ in range(40):
+        bt = int(rng.integers(1, 8))
+        bsx, bsy = po.BLOCK_SIZE[bt]
+        pos = (int(rng.integers(0, (W - bsx) // 4 + 1)) * 4, int(rng.integers(0, (H - bsy) // 4 + 1)) * 4)
+        pred = (int(rng.integers(-40, 40)), int(rng.integers(-40, 40)))
+        center = (((pred[0] + 2) >> 2) * 4, ((pred[1] + 2) >> 2) * 4)
+        lam = int(rng.integers(1, 400))
+        big = po.DISTBLK_MAX
+        assert o.full_search(r, f[1], bt, pos, pred, center, lam, big, R) == ref.full_search(bt, pos, pred, center, lam, big)
+
+
+def test_sub_pel(pair):
+    o, ref, r, f = pair
+    rng = np.random.default_rng(12)
+    for _ in range(60):
+        bt = int(rng.integers(1, 8))
+        bsx, bsy = po.BLOCK_SIZE[bt]
+        pos = (int(rng.integers(0, (W - bsx) // 4 + 1)) * 4, int(rng.integers(0, (H - bsy) // 4 + 1)) * 4)
+        pred = (int(rng.integers(-40, 40)), int(rng.integers(-40, 40)))
+        mv = (int(rng.integers(-12, 12)) * 4, int(rng.integers(-12, 12)) * 4)
+        lam = [int(rng.integers(1, 400))] * 3
+        t8 = int(bt <= 4 and rng.integers(0, 2))
+        big = po.DISTBLK_MAX
+        got = o.sub_pel(r, f[1], bt, pos, pred, mv, lam, big, po.SATD, po.SATD, 0, 1, t8)
+        assert got == ref.sub_pel(bt, pos, pred, mv, lam, big, t8)
+
+
+def test_fast_full_search(oracle, have_ref):
+    f = synth.luma_frames(W, H, 2, seed=9, motion=(-4, 3))
+    ref = po.JMRef(W, H, search_range=R, fast_full=1)
+    ref.set_ref(f[0]); ref.set_cur(f[1]); ref.spiral()
+    r = oracle.ref_create(f[0])
+    rng = np.random.default_rng(5)
+    for mb in [(0, 0), (80, 48), (32, 16), (80, 0), (0, 48)]:
+        pmv = (int(rng.integers(-30, 30)), int(rng.integers(-30, 30)))
+        c_ref = ref.ffs_setup(mb, pmv)
+        c = oracle.ffs_center(pmv, R)
+        assert c == c_ref
+        bs = oracle.ffs_setup(r, f[1], mb, c, R)
+        for bt, idxs in [(7, range(16)), (6, [0, 1, 2, 3, 8, 9, 10, 11]), (5, range(0, 16, 2)), (4, [0, 2, 8, 10]),
+                         (3, [0, 2]), (2, [0, 8]), (1, [0])]:
+            for i in idxs:
+                assert np.array_equal(bs[bt, i], ref.ffs_sad(bt, i)), (mb, bt, i)
+                pos = (mb[0] + (i & 3) * 4, mb[1] + (i >> 2) * 4)
+                pred = (pmv[0] + int(rng.integers(-6, 6)), pmv[1] + int(rng.integers(-6, 6)))
+                lam = int(rng.integers(1, 300))
+                assert oracle.ffs_search(bs, R, bt, i, c, pred, lam, po.DISTBLK_MAX, ref.max_mvd) == \
+                    ref.ffs_search(bt, pos, pred, lam, po.DISTBLK_MAX)
+    oracle.ref_destroy(r)
+
+
+def test_transforms_and_hadamard(oracle, have_ref):
+    ref = po.JMRef(32, 32, search_range=4)
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        b4 = rng.integers(-255, 256, size=(4, 4)); b8 = rng.integers(-255, 256, size=(8, 8))
+        assert np.array_equal(oracle.forward4x4(b4), ref.forward4x4(b4))
+        assert np.array_equal(oracle.forward8x8(b8), ref.forward8x8(b8))
+        assert oracle.hadamard4x4(b4) == ref.hadamard4x4(b4)
+        assert oracle.hadamard8x8(b8) == ref.hadamard8x8(b8)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+def test_quant(oracle, have_ref, variant):
+    ref = po.JMRef(32, 32, search_range=4)
+    rng = np.random.default_rng(variant)
+    n = 4 if variant < 2 else 8
+    scan = T.SNGL_SCAN if n == 4 else (T.SNGL_SCAN8x8_CAVLC if variant >= 4 else T.SNGL_SCAN8x8)
+    cc = T.COEFF_COST4x4[0] if n == 4 else T.COEFF_COST8x8[0]
+    for it in range(300):
+        qp = int(rng.integers(0, 52))
+        amp = int(rng.choice([3, 40, 255, 1023]))   # residual range of 8- and 10-bit video (JM itself overflows int32 beyond)
+        res = rng.integers(-amp, amp + 1, size=(n, n))
+        coef = oracle.forward4x4(res) if n == 4 else oracle.forward8x8(res)
+        if it % 7 == 0:
+            coef[rng.integers(0, n), rng.integers(0, n)] = 0
+        qpar = T.q_params(qp, intra=int(rng.integers(0, 2)), n=n)
+        cav = int(rng.integers(0, 2))
+        arw = 1 + (it % 8)
+        a = oracle.quant(variant, coef, qp, qpar, scan, cc, cav, arw=arw, cost0=5)
+        b = ref.quant(variant, coef, qp, qpar, scan, cc, cav, arw=arw, cost0=5)
+        assert a["nonzero"] == b["nonzero"] and a["coeff_cost"] == b["coeff_cost"]
+        assert np.array_equal(a["coef"], b["coef"])
+        assert np.array_equal(a["levels"], b["levels"]) and np.array_equal(a["runs"], b["runs"])
+        if variant % 2 == 1:
+            assert np.array_equal(a["fadjust"], b["fadjust"])
