@@ -1,0 +1,193 @@
+/*
+ * jmb200.h -- C ABI of libjmb200.so: B200 (sm_100a) kernels for the JM 19.0 lencod motion-estimation
+ * and integer transform/quantisation hot path.
+ *
+ * Plain C, plain pointers and sizes; no CUDA or torch types.  Every entry point names the JM
+ * interface it stands behind (paths relative to the JM 19.0 tree, shihuade/JM).  The reference-side
+ * binding (GNU ld --wrap stubs compiled against JM's own headers) is jm_b200/shim/jm_wrap.c and is
+ * described in INTEGRATION.md.
+ *
+ * Conventions (all JM's):
+ *   - samples are uint16_t (imgpel, lcommon/inc/typedefs.h:36) holding bit-depth-8 values;
+ *   - motion vectors and predictors are in quarter-pel units (MotionVector, 2 x short);
+ *   - costs are J = (D << 5) + lambda * bits  (LAMBDA_ACCURACY_BITS 5, lencod/inc/defines.h:130);
+ *   - block types 1..7 = 16x16,16x8,8x16,8x8,8x4,4x8,4x4 (lencod/inc/macroblock.h:58-68);
+ *   - reference planes are padded by 32 x 20 samples (IMG_PAD_SIZE_X/Y, lencod/inc/defines.h:121-122)
+ *     and addressed with JM's UMVLine4X origin clamp (lencod/inc/refbuf.h:22-26).
+ *
+ * Memory location of every data pointer is given by a `loc` argument: JMB_HOST (pageable or pinned
+ * host memory; the call copies in/out and returns when the results are in the caller's buffers) or
+ * JMB_DEVICE (device memory of the context's GPU; the call only enqueues work on the context's
+ * stream -- use jmb_sync()).  There is NO CPU implementation behind this ABI: without a CUDA device
+ * jmb_create() fails with JMB_ERR_NO_DEVICE and nothing else can be called.
+ *
+ * Return value: 0 on success, a negative JMB_ERR_* otherwise; jmb_last_error() gives the text.
+ * JM's own convention for fatal conditions is error(text, code) -> exit (lencod/src/filehandle.c:37);
+ * the shim forwards every non-zero return to it.
+ */
+#ifndef JMB200_H
+#define JMB200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JMB_ABI_VERSION 1
+
+enum { JMB_HOST = 0, JMB_DEVICE = 1 };
+enum { JMB_SAD = 0, JMB_SSE = 1, JMB_SATD = 2 };            /* ERROR_SAD/SSE/SATD, lencod/inc/defines.h */
+enum { JMB_SEARCH_FULL = 0,                                 /* full_search_motion_estimation  */
+       JMB_SEARCH_FAST_FULL = 1 };                          /* fast_full_search_motion_estimation */
+enum {
+  JMB_OK = 0,
+  JMB_ERR_NO_DEVICE = -1,
+  JMB_ERR_CUDA = -2,
+  JMB_ERR_ARG = -3,
+  JMB_ERR_UNSUPPORTED = -4,
+  JMB_ERR_STATE = -5
+};
+
+#define JMB_MAX_REFS 16
+#define JMB_REQ_SUBPEL   1   /* run the half-/quarter-pel refinement after the integer search */
+#define JMB_REQ_TEST8X8  2   /* SATD on 8x8 sub-blocks (MEBlock.test8x8, set when Transform8x8Mode) */
+#define JMB_REQ_SKIP_INT 4   /* no integer search: refine (center_x, center_y) only (SubPelME call) */
+
+typedef struct jmb_ctx jmb_ctx;
+
+/* Search-engine configuration = the fields of InputParameters / VideoParameters the searches read
+ * (init_motion_search_module, lencod/src/mv_search.c:315-515). */
+typedef struct jmb_me_config {
+  int32_t search_range;      /* SearchRange, integer pels (positions per search = (2R+1)^2) */
+  int32_t max_mvd;           /* p_Vid->max_mvd (mv_search.c:325-329); FAST_FULL guard uses max_mvd-1 */
+  int32_t metric[3];         /* MEDistortionFPel/HPel/QPel */
+  int32_t start_hp;          /* p_Vid->start_me_refinement_hp (mv_search.c:445) */
+  int32_t start_qp;          /* p_Vid->start_me_refinement_qp (mv_search.c:446) */
+  int32_t search_pos2;       /* MEBlock.search_pos2 (9) */
+  int32_t search_pos4;       /* MEBlock.search_pos4 (9) */
+} jmb_me_config;
+
+/* One motion search = one BlockMotionSearch leaf call (lencod/src/mv_search.c:858-1024):
+ * currMB->IntPelME (:960) followed, when JMB_REQ_SUBPEL, by currMB->SubPelME (:975). 40 bytes. */
+typedef struct jmb_me_req {
+  int16_t pos_x, pos_y;        /* MEBlock.pos_x/pos_y: block origin in the picture, pels */
+  int16_t pred_x, pred_y;      /* pred_mv, quarter-pel */
+  int16_t center_x, center_y;  /* search centre as an mv, quarter-pel, multiple of 4
+                                  (FULL: MEBlock.mv[list] on entry, mv_search.c:931-957;
+                                   FAST_FULL: p_ffast_me->search_center, me_fullfast.c:309-327) */
+  uint8_t blocktype;           /* 1..7 */
+  uint8_t ref;                 /* index into the reference list given to jmb_pic_begin */
+  uint8_t mode;                /* JMB_SEARCH_* */
+  uint8_t flags;               /* JMB_REQ_* */
+  int32_t lambda[3];           /* lambda_factor[F_PEL,H_PEL,Q_PEL] */
+  int32_t reserved_;           /* keeps min_mcost 8-byte aligned; set to 0 */
+  int64_t min_mcost;           /* incoming minimum cost (DISTBLK_MAX from BlockMotionSearch) */
+} jmb_me_req;
+
+/* 24 bytes */
+typedef struct jmb_me_res {
+  int16_t mv_x, mv_y;          /* final mv (after sub-pel when requested), quarter-pel */
+  int16_t imv_x, imv_y;        /* mv after the integer search */
+  int64_t cost;                /* value SubPelME (or IntPelME) returns */
+  int64_t icost;               /* value IntPelME returns */
+} jmb_me_res;
+
+/* Per-macroblock inter prediction description for jmb_mc_tq: mirrors what luma_residual_coding
+ * (lencod/src/macroblock.c:1182) reads from currMB->b8x8[] and currSlice->all_mv. 72 bytes. */
+typedef struct jmb_mb_pred {
+  int16_t mv[16][2];           /* mv of each 4x4 block, raster order inside the MB, quarter-pel */
+  uint8_t b8mode[4];           /* partition mode of each 8x8 quadrant, 1..7 (1..3 = whole-MB modes) */
+  uint8_t ref[4];              /* reference index of each 8x8 quadrant */
+} jmb_mb_pred;
+
+/* Quantiser description = struct quant_methods + LevelQuantParams (lcommon/inc/quant_params.h:17-51). */
+typedef struct jmb_quant_desc {
+  int32_t n;                   /* 4 or 8 (transform size) */
+  int32_t qp;                  /* qp_scaled; qp_per = qp/6 (p_Quant->qp_per_matrix) */
+  int32_t is_cavlc;            /* currSlice->symbol_mode == CAVLC: clip levels to 2063; for n=8 use the
+                                  4-way interleaved CAVLC level/run lists (quant_8x8cavlc_*) */
+  int32_t around;              /* 0: *_normal, 1: *_around (adaptive rounding: also writes fadjust) */
+  int32_t adapt_rnd_weight;    /* p_Vid->AdaptRndWeight */
+  int32_t qparams[64][3];      /* [j*n+i] = {OffsetComp, ScaleComp, InvScaleComp} */
+  uint8_t scan[64][2];         /* pos_scan: {i, j} per scan position */
+  uint8_t c_cost[64];          /* COEFF_COST4x4 / COEFF_COST8x8 row in use */
+} jmb_quant_desc;
+
+/* ---- context --------------------------------------------------------------------------------- */
+int         jmb_abi_version(void);
+int         jmb_create(int device, jmb_ctx **out);
+void        jmb_destroy(jmb_ctx *ctx);
+const char *jmb_last_error(const jmb_ctx *ctx);     /* ctx may be NULL for jmb_create failures */
+int         jmb_sync(jmb_ctx *ctx);
+void       *jmb_stream(jmb_ctx *ctx);               /* the cudaStream_t all work is enqueued on */
+uint64_t    jmb_launch_count(const jmb_ctx *ctx);   /* kernels launched by this context so far */
+int         jmb_host_alloc(jmb_ctx *ctx, size_t bytes, void **out);   /* pinned host memory */
+int         jmb_host_free(jmb_ctx *ctx, void *p);
+
+/* ---- reference pictures: stands behind getSubImagesLuma (lencod/src/img_luma.c:611), called from
+ * UnifiedOneForthPix (lencod/src/image.c:2187) when a picture enters the DPB --------------------- */
+int jmb_ref_put(jmb_ctx *ctx, int slot, const uint16_t *luma, int width, int height, int stride,
+                int bitdepth, int loc);
+int jmb_ref_drop(jmb_ctx *ctx, int slot);           /* free_storable_picture, lencod/src/mbuffer.c:729 */
+/* copy one quarter-pel plane [fy][fx] back as JM lays it out: (height+40) x (width+64) uint16_t */
+int jmb_ref_get_plane(jmb_ctx *ctx, int slot, int fy, int fx, uint16_t *out, int loc);
+
+/* ---- current picture: p_Vid->pCurImg, read by get_original_block (lencod/src/mv_search.c:786) and
+ * setup_fast_full_search (lencod/src/me_fullfast.c:333-337) ------------------------------------- */
+int jmb_pic_begin(jmb_ctx *ctx, const uint16_t *cur, int width, int height, int stride, int loc,
+                  const int *ref_slots, int nref);
+
+/* ---- motion search --------------------------------------------------------------------------- */
+int jmb_me_configure(jmb_ctx *ctx, const jmb_me_config *cfg);
+/* n searches; requests of one macroblock and reference that sit next to each other in `reqs`
+ * share their 4x4 SAD evaluations (what setup_fast_full_search + update_full_search_large_blocks
+ * do for one macroblock, lencod/src/me_fullfast.c:196-608). */
+int jmb_me_search(jmb_ctx *ctx, const jmb_me_req *reqs, int n, jmb_me_res *res, int loc);
+/* Whole-picture form: exactly 41 requests per macroblock, macroblocks in any order, the 41 in
+ * canonical partition order (type 1..7, partitions of a type in raster order inside the
+ * macroblock: slot = base[type] + (by4/h4)*(4/w4) + bx4/w4 with base = {0,1,3,5,9,17,25}).
+ * No grouping pass is needed, so with JMB_DEVICE nothing touches the host. */
+int jmb_me_search_frame(jmb_ctx *ctx, const jmb_me_req *reqs, int n_mb, jmb_me_res *res, int loc);
+
+/* BlockSAD surfaces of one macroblock exactly as setup_fast_full_search leaves them:
+ * out[(blocktype*16 + slot) * max_pos + pos], blocktype 1..7, uint32 (distpel), spiral order.
+ * (lencod/src/me_fullfast.c:59-81 allocation, :492-556, :196-260) */
+int jmb_ffs_surfaces(jmb_ctx *ctx, int ref, int mb_x, int mb_y, int center_x, int center_y,
+                     uint32_t *out, int loc);
+
+/* distortion of n candidates of one block: computeSAD / computeSSE / computeSATD
+ * (lencod/src/me_distortion.c:349,1190,745).  cand = absolute quarter-pel positions (x,y pairs);
+ * out[i] = full (never early-terminated) distortion, not scaled by 32. */
+int jmb_dist(jmb_ctx *ctx, int ref, int metric, int blocktype, int pos_x, int pos_y,
+             const int16_t *cand_xy, int n, int test8x8, int32_t *out, int loc);
+
+/* ---- transform + quantisation ---------------------------------------------------------------- */
+/* forward4x4 / forward8x8 (lcommon/src/transform.c:20,353) on nblk blocks of n*n int32, in place */
+int jmb_forward_transform(jmb_ctx *ctx, int32_t *blocks, int nblk, int n, int loc);
+
+/* forward transform (optional) + quant_{4x4,8x8,8x8cavlc}_{normal,around} on nblk blocks.
+ *   coef   [nblk][n*n] int32: residual (do_transform=1) or transformed coefficients (0), row-major;
+ *                             on return the dequantised coefficients, as JM leaves them in tblock
+ *   levels/runs [nblk][lr_stride] int32 with lr_stride = 17 (n=4), 65 (n=8), 68 (n=8 cavlc: 4 x 17)
+ *   fadjust [nblk][n*n] (around only, may be NULL), coeff_cost[nblk] (added to, like *coeff_cost),
+ *   nonzero [nblk] */
+int jmb_quant_blocks(jmb_ctx *ctx, const jmb_quant_desc *q, int do_transform, int32_t *coef, int nblk,
+                     int32_t *levels, int32_t *runs, int32_t *fadjust, int32_t *coeff_cost,
+                     int32_t *nonzero, int loc);
+
+/* whole-picture inter residual coding: luma_prediction (lencod/src/mc_prediction.c:144) ->
+ * compute_residue -> forward4x4|8x8 -> quant, for every macroblock of the current picture.
+ *   pred   [n_mb] macroblocks in raster order
+ *   levels [n_mb][256] int16: quantised levels, per 4x4 (or 8x8) block in scan order
+ *                              (4x4: block b = by*4+bx at [b*16 + k]; 8x8: block b8 at [b8*64 + k])
+ *   coeff_cost [n_mb][4] int32 per 8x8 quadrant, cbp_blk [n_mb] uint32: bit b set if 4x4 block b has a
+ *   nonzero level (8x8 transform: bits of the quadrant set together, macroblock.c:1004) */
+int jmb_mc_tq(jmb_ctx *ctx, const jmb_mb_pred *pred, int n_mb, const jmb_quant_desc *q,
+              int16_t *levels, int32_t *coeff_cost, uint32_t *cbp_blk, int loc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JMB200_H */

@@ -1,0 +1,241 @@
+"""ctypes mirror of the libjmb200 C ABI (include/jmb200.h) -- harness side only.
+
+No CPU fallback lives here: if the shared library is missing, or no B200 is present, construction
+raises.  Arrays cross the boundary as numpy buffers (JMB_HOST) or raw device pointers (JMB_DEVICE,
+e.g. ``tensor.data_ptr()`` of a torch CUDA tensor).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libjmb200.so")
+HOST, DEVICE = 0, 1
+SAD, SSE, SATD = 0, 1, 2
+SEARCH_FULL, SEARCH_FAST_FULL = 0, 1
+REQ_SUBPEL, REQ_TEST8X8, REQ_SKIP_INT = 1, 2, 4
+DISTBLK_MAX = 0x7FFFFFFF << 5
+NPART = 41
+BLOCK_SIZE = [(16, 16), (16, 16), (16, 8), (8, 16), (8, 8), (8, 4), (4, 8), (4, 4)]
+
+ME_REQ = np.dtype([("pos_x", "<i2"), ("pos_y", "<i2"), ("pred_x", "<i2"), ("pred_y", "<i2"),
+                   ("center_x", "<i2"), ("center_y", "<i2"), ("blocktype", "u1"), ("ref", "u1"),
+                   ("mode", "u1"), ("flags", "u1"), ("lambda", "<i4", (3,)), ("pad_", "<i4"), ("min_mcost", "<i8")])
+ME_RES = np.dtype([("mv_x", "<i2"), ("mv_y", "<i2"), ("imv_x", "<i2"), ("imv_y", "<i2"), ("cost", "<i8"), ("icost", "<i8")])
+MB_PRED = np.dtype([("mv", "<i2", (16, 2)), ("b8mode", "u1", (4,)), ("ref", "u1", (4,))])
+QUANT_DESC = np.dtype([("n", "<i4"), ("qp", "<i4"), ("is_cavlc", "<i4"), ("around", "<i4"), ("adapt_rnd_weight", "<i4"),
+                       ("qparams", "<i4", (64, 3)), ("scan", "u1", (64, 2)), ("c_cost", "u1", (64,))])
+assert ME_REQ.itemsize == 40 and ME_RES.itemsize == 24 and MB_PRED.itemsize == 72 and QUANT_DESC.itemsize == 980
+
+
+class MEConfig(C.Structure):
+    _fields_ = [("search_range", C.c_int32), ("max_mvd", C.c_int32), ("metric", C.c_int32 * 3),
+                ("start_hp", C.c_int32), ("start_qp", C.c_int32), ("search_pos2", C.c_int32), ("search_pos4", C.c_int32)]
+
+
+class JMBError(RuntimeError):
+    pass
+
+
+def load_library():
+    if not os.path.exists(LIB_PATH):
+        raise JMBError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(make -C jm_b200/csrc).  There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i = C.c_void_p, C.c_int
+    L.jmb_abi_version.restype = i
+    L.jmb_create.argtypes = [i, C.POINTER(vp)]
+    L.jmb_destroy.argtypes = [vp]
+    L.jmb_last_error.restype = C.c_char_p; L.jmb_last_error.argtypes = [vp]
+    L.jmb_sync.argtypes = [vp]
+    L.jmb_stream.restype = vp; L.jmb_stream.argtypes = [vp]
+    L.jmb_launch_count.restype = C.c_uint64; L.jmb_launch_count.argtypes = [vp]
+    L.jmb_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    L.jmb_host_free.argtypes = [vp, vp]
+    L.jmb_ref_put.argtypes = [vp, i, vp, i, i, i, i, i]
+    L.jmb_ref_drop.argtypes = [vp, i]
+    L.jmb_ref_get_plane.argtypes = [vp, i, i, i, vp, i]
+    L.jmb_pic_begin.argtypes = [vp, vp, i, i, i, i, C.POINTER(i), i]
+    L.jmb_me_configure.argtypes = [vp, C.POINTER(MEConfig)]
+    L.jmb_me_search.argtypes = [vp, vp, i, vp, i]
+    L.jmb_me_search_frame.argtypes = [vp, vp, i, vp, i]
+    L.jmb_ffs_surfaces.argtypes = [vp, i, i, i, i, i, vp, i]
+    L.jmb_dist.argtypes = [vp, i, i, i, i, i, vp, i, i, vp, i]
+    L.jmb_forward_transform.argtypes = [vp, vp, i, i, i]
+    L.jmb_quant_blocks.argtypes = [vp, vp, i, vp, i, vp, vp, vp, vp, vp, i]
+    L.jmb_mc_tq.argtypes = [vp, vp, i, vp, vp, vp, vp, i]
+    return L
+
+
+def _ptr(a):
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    return int(a)      # raw device / pinned pointer
+
+
+def part_slot(blocktype, bx4, by4):
+    base = [0, 0, 1, 3, 5, 9, 17, 25][blocktype]
+    w4 = [4, 4, 4, 2, 2, 2, 1, 1][blocktype]; h4 = [4, 4, 2, 4, 2, 1, 2, 1][blocktype]
+    return base + (by4 // h4) * (4 // w4) + bx4 // w4
+
+
+def mb_partitions():
+    """(blocktype, x offset, y offset) of the 41 partitions of a macroblock in canonical order."""
+    out = []
+    for t in range(1, 8):
+        bsx, bsy = BLOCK_SIZE[t]
+        for y in range(0, 16, bsy):
+            for x in range(0, 16, bsx):
+                out.append((t, x, y))
+    assert all(part_slot(t, x // 4, y // 4) == k for k, (t, x, y) in enumerate(out))
+    return out
+
+
+def quant_desc(n, qp, qparams, scan, c_cost, is_cavlc, around=0, arw=0):
+    q = np.zeros(1, QUANT_DESC)
+    q["n"], q["qp"], q["is_cavlc"], q["around"], q["adapt_rnd_weight"] = n, qp, int(is_cavlc), int(around), int(arw)
+    q["qparams"][0, :n * n] = np.asarray(qparams, np.int32).reshape(n * n, 3)
+    q["scan"][0, :n * n] = np.asarray(scan, np.uint8).reshape(n * n, 2)
+    m = min(len(c_cost), 64)
+    q["c_cost"][0, :m] = np.asarray(c_cost, np.uint8)[:m]
+    return q
+
+
+class Context:
+    """One libjmb200 context = one GPU, one stream."""
+
+    def __init__(self, device=0):
+        self.L = load_library()
+        h = C.c_void_p()
+        rc = self.L.jmb_create(device, C.byref(h))
+        if rc:
+            raise JMBError(f"jmb_create({device}) = {rc}: {self.L.jmb_last_error(None).decode()}")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.jmb_destroy(self.h); self.h = None
+
+    __del__ = close
+
+    def _ck(self, rc):
+        if rc:
+            raise JMBError(f"libjmb200 error {rc}: {self.L.jmb_last_error(self.h).decode()}")
+
+    def sync(self):
+        self._ck(self.L.jmb_sync(self.h))
+
+    @property
+    def stream(self):
+        return self.L.jmb_stream(self.h)
+
+    @property
+    def launches(self):
+        return int(self.L.jmb_launch_count(self.h))
+
+    def pinned(self, shape, dtype):
+        """numpy array over cudaHostAlloc'd memory (freed with the context's process)."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        self._ck(self.L.jmb_host_alloc(self.h, max(n, 1), C.byref(p)))
+        buf = (C.c_char * n).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def configure(self, search_range=32, max_mvd=None, metric=(SAD, SATD, SATD), start_hp=None, start_qp=None,
+                  search_pos2=9, search_pos4=9):
+        if max_mvd is None:   # lencod/src/mv_search.c:325-329
+            import math
+            bits = 3 + 2 * int(math.ceil(math.log(4 * (2 * search_range + 3) + 1) / math.log(2) + 1e-10))
+            max_mvd = (1 << (bits >> 1)) - 1
+        if start_hp is None:
+            start_hp = 0 if metric[0] != metric[1] else 1
+        if start_qp is None:
+            start_qp = 0 if metric[1] != metric[2] else 1
+        cfg = MEConfig(search_range, max_mvd, (C.c_int32 * 3)(*metric), start_hp, start_qp, search_pos2, search_pos4)
+        self._ck(self.L.jmb_me_configure(self.h, C.byref(cfg)))
+        self.search_range, self.max_mvd = search_range, max_mvd
+
+    def ref_put(self, slot, luma, loc=HOST, shape=None, stride=None, bitdepth=8):
+        if loc == HOST:
+            luma = np.ascontiguousarray(luma, np.uint16)
+            h, w = luma.shape
+            stride = w
+        else:
+            h, w = shape
+            stride = stride or w
+        self._ck(self.L.jmb_ref_put(self.h, slot, _ptr(luma), w, h, stride, bitdepth, loc))
+
+    def ref_drop(self, slot):
+        self._ck(self.L.jmb_ref_drop(self.h, slot))
+
+    def ref_plane(self, slot, fy, fx, shape):
+        h, w = shape
+        out = np.empty((h + 40, w + 64), np.uint16)
+        self._ck(self.L.jmb_ref_get_plane(self.h, slot, fy, fx, _ptr(out), HOST))
+        return out
+
+    def pic_begin(self, cur, ref_slots, loc=HOST, shape=None, stride=None):
+        if loc == HOST:
+            cur = np.ascontiguousarray(cur, np.uint16)
+            h, w = cur.shape
+            stride = w
+        else:
+            h, w = shape
+            stride = stride or w
+        arr = (C.c_int * len(ref_slots))(*ref_slots)
+        self._ck(self.L.jmb_pic_begin(self.h, _ptr(cur), w, h, stride, loc, arr, len(ref_slots)))
+
+    def me_search(self, reqs, res=None, loc=HOST, n=None, frame=False):
+        if loc == HOST:
+            reqs = np.ascontiguousarray(reqs, ME_REQ)
+            n = len(reqs)
+            if res is None:
+                res = np.zeros(n, ME_RES)
+        if frame:
+            assert n % NPART == 0
+            self._ck(self.L.jmb_me_search_frame(self.h, _ptr(reqs), n // NPART, _ptr(res), loc))
+        else:
+            self._ck(self.L.jmb_me_search(self.h, _ptr(reqs), n, _ptr(res), loc))
+        return res
+
+    def ffs_surfaces(self, ref, mb, center):
+        n = (2 * self.search_range + 1) ** 2
+        out = np.zeros((8, 16, n), np.uint32)
+        self._ck(self.L.jmb_ffs_surfaces(self.h, ref, mb[0], mb[1], center[0], center[1], _ptr(out), HOST))
+        return out
+
+    def dist(self, ref, metric, blocktype, pos, cands, test8x8=0):
+        cands = np.ascontiguousarray(cands, np.int16).reshape(-1, 2)
+        out = np.zeros(len(cands), np.int32)
+        self._ck(self.L.jmb_dist(self.h, ref, metric, blocktype, pos[0], pos[1], _ptr(cands), len(cands), test8x8, _ptr(out), HOST))
+        return out
+
+    def forward_transform(self, blocks, n):
+        b = np.ascontiguousarray(blocks, np.int32).reshape(-1, n * n).copy()
+        self._ck(self.L.jmb_forward_transform(self.h, _ptr(b), len(b), n, HOST))
+        return b.reshape(-1, n, n)
+
+    def quant_blocks(self, qdesc, coef, do_transform=0, cost0=0):
+        n = int(qdesc["n"][0]); nn = n * n
+        coef = np.ascontiguousarray(coef, np.int32).reshape(-1, nn).copy()
+        nblk = len(coef)
+        lr = 17 if n == 4 else (68 if int(qdesc["is_cavlc"][0]) else 65)
+        levels = np.zeros((nblk, lr), np.int32); runs = np.zeros((nblk, lr), np.int32)
+        fadj = np.zeros((nblk, nn), np.int32)
+        cost = np.full(nblk, cost0, np.int32); nz = np.zeros(nblk, np.int32)
+        self._ck(self.L.jmb_quant_blocks(self.h, _ptr(qdesc), int(do_transform), _ptr(coef), nblk, _ptr(levels), _ptr(runs),
+                                         _ptr(fadj), _ptr(cost), _ptr(nz), HOST))
+        return dict(coef=coef.reshape(-1, n, n), levels=levels, runs=runs, fadjust=fadj.reshape(-1, n, n), coeff_cost=cost, nonzero=nz)
+
+    def mc_tq(self, pred, qdesc, loc=HOST, n_mb=None, out=None):
+        if loc == HOST:
+            pred = np.ascontiguousarray(pred, MB_PRED)
+            n_mb = len(pred)
+            levels = np.zeros((n_mb, 256), np.int16); cost = np.zeros((n_mb, 4), np.int32); cbp = np.zeros(n_mb, np.uint32)
+        else:
+            levels, cost, cbp = out
+        self._ck(self.L.jmb_mc_tq(self.h, _ptr(pred), n_mb, _ptr(qdesc), _ptr(levels), _ptr(cost), _ptr(cbp), loc))
+        return levels, cost, cbp

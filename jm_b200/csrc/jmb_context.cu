@@ -1,0 +1,243 @@
+// jmb_context.cu -- context, memory and picture management of libjmb200 (host side, C++).
+#include <stdarg.h>
+#include <stdlib.h>
+#include "jmb_internal.h"
+
+static char g_create_err[512] = "";
+
+int jmb_fail(jmb_ctx *ctx, int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(ctx ? ctx->err : g_create_err, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int jmb_reserve_host(jmb_ctx *ctx, void **p, size_t *cap, size_t bytes) {
+  if (bytes <= *cap) return 0;
+  if (*p) JMB_CUDA(ctx, cudaFreeHost(*p));
+  *p = nullptr; *cap = 0;
+  size_t want = bytes + bytes / 4 + 4096;
+  JMB_CUDA(ctx, cudaHostAlloc(p, want, cudaHostAllocDefault));
+  *cap = want;
+  return 0;
+}
+
+int jmb_reserve_dev(jmb_ctx *ctx, void **p, size_t *cap, size_t bytes) {
+  if (bytes <= *cap) return 0;
+  if (*p) { JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); JMB_CUDA(ctx, cudaFree(*p)); }
+  *p = nullptr; *cap = 0;
+  size_t want = bytes + bytes / 4 + 4096;
+  JMB_CUDA(ctx, cudaMalloc(p, want));
+  *cap = want;
+  return 0;
+}
+
+extern "C" {
+
+int jmb_abi_version(void) { return JMB_ABI_VERSION; }
+
+const char *jmb_last_error(const jmb_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
+
+int jmb_create(int device, jmb_ctx **out) {
+  if (!out) return jmb_fail(nullptr, JMB_ERR_ARG, "jmb_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return jmb_fail(nullptr, JMB_ERR_NO_DEVICE,
+                    "jmb_create: no CUDA device (%s); libjmb200 has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (device < 0 || device >= count)
+    return jmb_fail(nullptr, JMB_ERR_ARG, "jmb_create: device %d out of range (0..%d)", device, count - 1);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10)
+    return jmb_fail(nullptr, JMB_ERR_UNSUPPORTED,
+                    "jmb_create: device %d is sm_%d%d; libjmb200 is built for sm_100a only", device,
+                    prop.major, prop.minor);
+  jmb_ctx *ctx = new jmb_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    jmb_fail(nullptr, JMB_ERR_CUDA, "jmb_create: cannot create a stream on device %d: %s", device,
+             cudaGetErrorString(cudaGetLastError()));
+    delete ctx;
+    return JMB_ERR_CUDA;
+  }
+  // defaults = the bundled encoder cfgs: SearchRange 32, SAD / SATD / SATD
+  ctx->me.search_range = 32; ctx->me.max_mvd = 1023;
+  ctx->me.metric[0] = JMB_SAD; ctx->me.metric[1] = JMB_SATD; ctx->me.metric[2] = JMB_SATD;
+  ctx->me.start_hp = 0; ctx->me.start_qp = 1; ctx->me.search_pos2 = 9; ctx->me.search_pos4 = 9;
+  *out = ctx;
+  return JMB_OK;
+}
+
+void jmb_destroy(jmb_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < JMB_MAX_REFS; i++) if (ctx->refs[i].planes) cudaFree(ctx->refs[i].planes);
+  if (ctx->cur) cudaFree(ctx->cur);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->h_groups) cudaFreeHost(ctx->h_groups);
+  if (ctx->d_stage) cudaFree(ctx->d_stage);
+  if (ctx->d_stage2) cudaFree(ctx->d_stage2);
+  if (ctx->d_groups) cudaFree(ctx->d_groups);
+  if (ctx->d_reftab) cudaFree(ctx->d_reftab);
+  if (ctx->d_qdesc) cudaFree(ctx->d_qdesc);
+  if (ctx->d_stage3) cudaFree(ctx->d_stage3);
+  if (ctx->d_stage4) cudaFree(ctx->d_stage4);
+  if (ctx->d_stage5) cudaFree(ctx->d_stage5);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int jmb_sync(jmb_ctx *ctx) {
+  JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return JMB_OK;
+}
+
+void *jmb_stream(jmb_ctx *ctx) { return (void *)ctx->stream; }
+uint64_t jmb_launch_count(const jmb_ctx *ctx) { return ctx->launches; }
+
+int jmb_host_alloc(jmb_ctx *ctx, size_t bytes, void **out) {
+  JMB_CUDA(ctx, cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return JMB_OK;
+}
+int jmb_host_free(jmb_ctx *ctx, void *p) {
+  JMB_CUDA(ctx, cudaFreeHost(p));
+  return JMB_OK;
+}
+
+int jmb_me_configure(jmb_ctx *ctx, const jmb_me_config *cfg) {
+  if (!cfg) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_me_configure: cfg is NULL");
+  if (cfg->search_range < 1 || cfg->search_range > 64)
+    return jmb_fail(ctx, JMB_ERR_UNSUPPORTED, "jmb_me_configure: search_range %d not in 1..64", cfg->search_range);
+  for (int i = 0; i < 3; i++)
+    if (cfg->metric[i] < 0 || cfg->metric[i] > 2)
+      return jmb_fail(ctx, JMB_ERR_ARG, "jmb_me_configure: metric[%d]=%d", i, cfg->metric[i]);
+  if (cfg->metric[0] != JMB_SAD)
+    return jmb_fail(ctx, JMB_ERR_UNSUPPORTED, "jmb_me_configure: integer search supports MEDistortionFPel=SAD only");
+  if (cfg->search_pos2 < 1 || cfg->search_pos2 > 9 || cfg->search_pos4 < 1 || cfg->search_pos4 > 9)
+    return jmb_fail(ctx, JMB_ERR_ARG, "jmb_me_configure: search_pos2/4 must be 1..9");
+  ctx->me = *cfg;
+  ctx->me_configured = true;
+  return JMB_OK;
+}
+
+// Bring `bytes` of caller data (host or device) to the device; returns the device pointer to read.
+static int to_device(jmb_ctx *ctx, const void *src, size_t bytes, int loc, void **dptr, void **scratch, size_t *cap) {
+  if (loc == JMB_DEVICE) { *dptr = (void *)src; return 0; }
+  int rc = jmb_reserve_dev(ctx, scratch, cap, bytes);
+  if (rc) return rc;
+  JMB_CUDA(ctx, cudaMemcpyAsync(*scratch, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  *dptr = *scratch;
+  return 0;
+}
+
+int jmb_ref_put(jmb_ctx *ctx, int slot, const uint16_t *luma, int width, int height, int stride,
+                int bitdepth, int loc) {
+  if (slot < 0 || slot >= JMB_MAX_REFS) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_ref_put: slot %d", slot);
+  if (bitdepth != 8)
+    return jmb_fail(ctx, JMB_ERR_UNSUPPORTED, "jmb_ref_put: bit depth %d (this build packs samples to 8 bits)", bitdepth);
+  if (width < 16 || height < 16 || (width & 15) || (height & 15) || stride < width)
+    return jmb_fail(ctx, JMB_ERR_ARG, "jmb_ref_put: %dx%d stride %d (need multiples of 16)", width, height, stride);
+  JMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  jmb_ref *r = &ctx->refs[slot];
+  int W = width + 2 * JMB_PAD_X, H = height + 2 * JMB_PAD_Y;
+  int pitch = (W + 127) & ~127;
+  size_t plane_bytes = (size_t)pitch * H;
+  if (!r->planes || r->w != width || r->h != height) {
+    if (r->planes) { JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); JMB_CUDA(ctx, cudaFree(r->planes)); r->planes = nullptr; }
+    JMB_CUDA(ctx, cudaMalloc(&r->planes, plane_bytes * 16));
+    r->w = width; r->h = height; r->W = W; r->H = H; r->pitch = pitch; r->plane_bytes = plane_bytes;
+  }
+  void *d_src = nullptr;
+  int rc = to_device(ctx, luma, (size_t)stride * height * sizeof(uint16_t), loc, &d_src, &ctx->d_stage, &ctx->d_stage_cap);
+  if (rc) return rc;
+  rc = jmb_launch_subpel(ctx, (const uint16_t *)d_src, stride, r);
+  if (rc) return rc;
+  r->valid = true;
+  if (loc == JMB_HOST) JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return JMB_OK;
+}
+
+int jmb_ref_drop(jmb_ctx *ctx, int slot) {
+  if (slot < 0 || slot >= JMB_MAX_REFS) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_ref_drop: slot %d", slot);
+  jmb_ref *r = &ctx->refs[slot];
+  if (r->planes) { JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); JMB_CUDA(ctx, cudaFree(r->planes)); }
+  *r = jmb_ref();
+  return JMB_OK;
+}
+
+__global__ void k_plane_to_u16(const uint8_t *__restrict__ plane, int pitch, int W, int H, uint16_t *__restrict__ out) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x < W && y < H) out[(size_t)y * W + x] = plane[(size_t)y * pitch + x];
+}
+
+int jmb_ref_get_plane(jmb_ctx *ctx, int slot, int fy, int fx, uint16_t *out, int loc) {
+  if (slot < 0 || slot >= JMB_MAX_REFS || !ctx->refs[slot].valid)
+    return jmb_fail(ctx, JMB_ERR_STATE, "jmb_ref_get_plane: slot %d holds no picture", slot);
+  if ((fy | fx) & ~3) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_ref_get_plane: plane [%d][%d]", fy, fx);
+  jmb_ref *r = &ctx->refs[slot];
+  size_t bytes = (size_t)r->W * r->H * sizeof(uint16_t);
+  uint16_t *d_out = out;
+  if (loc == JMB_HOST) {
+    int rc = jmb_reserve_dev(ctx, &ctx->d_stage2, &ctx->d_stage2_cap, bytes);
+    if (rc) return rc;
+    d_out = (uint16_t *)ctx->d_stage2;
+  }
+  dim3 grid((r->W + 255) / 256, r->H);
+  k_plane_to_u16<<<grid, 256, 0, ctx->stream>>>(r->planes + (size_t)(fy * 4 + fx) * r->plane_bytes, r->pitch, r->W, r->H, d_out);
+  JMB_LAUNCH_CHECK(ctx);
+  if (loc == JMB_HOST) {
+    JMB_CUDA(ctx, cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return JMB_OK;
+}
+
+// u16 samples -> u8 plane with a 128-byte-aligned pitch (the layout every search kernel reads)
+__global__ void k_pack_cur(const uint16_t *__restrict__ src, int stride, int w, int h, uint8_t *__restrict__ dst, int pitch) {
+  int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+  if (x4 >= w || y >= h) return;
+  const uint16_t *s = src + (size_t)y * stride + x4;
+  uint32_t v = (uint32_t)(s[0] & 255) | ((uint32_t)(s[1] & 255) << 8) | ((uint32_t)(s[2] & 255) << 16) | ((uint32_t)(s[3] & 255) << 24);
+  *(uint32_t *)(dst + (size_t)y * pitch + x4) = v;
+}
+
+int jmb_pic_begin(jmb_ctx *ctx, const uint16_t *cur, int width, int height, int stride, int loc,
+                  const int *ref_slots, int nref) {
+  if (width < 16 || height < 16 || (width & 15) || (height & 15) || stride < width)
+    return jmb_fail(ctx, JMB_ERR_ARG, "jmb_pic_begin: %dx%d stride %d", width, height, stride);
+  if (nref < 0 || nref > JMB_MAX_REFS) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_pic_begin: nref %d", nref);
+  for (int i = 0; i < nref; i++) {
+    int s = ref_slots[i];
+    if (s < 0 || s >= JMB_MAX_REFS || !ctx->refs[s].valid)
+      return jmb_fail(ctx, JMB_ERR_STATE, "jmb_pic_begin: reference slot %d holds no picture", s);
+    if (ctx->refs[s].w != width || ctx->refs[s].h != height)
+      return jmb_fail(ctx, JMB_ERR_ARG, "jmb_pic_begin: reference slot %d is %dx%d, picture is %dx%d", s,
+                      ctx->refs[s].w, ctx->refs[s].h, width, height);
+    ctx->ref_list[i] = s;
+  }
+  ctx->nref = nref;
+  JMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  int pitch = (width + 127) & ~127;
+  size_t bytes = (size_t)pitch * height;
+  if (bytes > ctx->cur_cap) {
+    if (ctx->cur) { JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); JMB_CUDA(ctx, cudaFree(ctx->cur)); ctx->cur = nullptr; }
+    JMB_CUDA(ctx, cudaMalloc(&ctx->cur, bytes));
+    ctx->cur_cap = bytes;
+  }
+  ctx->cur_w = width; ctx->cur_h = height; ctx->cur_pitch = pitch;
+  void *d_src = nullptr;
+  int rc = to_device(ctx, cur, (size_t)stride * height * sizeof(uint16_t), loc, &d_src, &ctx->d_stage, &ctx->d_stage_cap);
+  if (rc) return rc;
+  dim3 grid((width / 4 + 127) / 128, height);
+  k_pack_cur<<<grid, 128, 0, ctx->stream>>>((const uint16_t *)d_src, stride, width, height, ctx->cur, pitch);
+  JMB_LAUNCH_CHECK(ctx);
+  if (loc == JMB_HOST) JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return JMB_OK;
+}
+
+}  // extern "C"

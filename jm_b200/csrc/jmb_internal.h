@@ -1,0 +1,83 @@
+// jmb_internal.h -- shared declarations of libjmb200 (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "jmb200.h"
+
+#define JMB_PAD_X 32   // IMG_PAD_SIZE_X, lencod/inc/defines.h:121
+#define JMB_PAD_Y 20   // IMG_PAD_SIZE_Y, lencod/inc/defines.h:122
+
+// One reference picture in HBM: 16 quarter-pel planes of u8 samples (bit depth 8), plane-major,
+// each (h+40) rows of `pitch` bytes (pitch = (w+64) rounded up to 128 B so every row starts on a
+// 128-byte line).  plane(fy,fx) = base + (fy*4+fx)*plane_bytes.
+struct jmb_ref {
+  uint8_t *planes = nullptr;
+  int w = 0, h = 0, W = 0, H = 0, pitch = 0;
+  size_t plane_bytes = 0;
+  bool valid = false;
+};
+
+struct jmb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  char err[512] = {0};
+  uint64_t launches = 0;
+  jmb_ref refs[JMB_MAX_REFS];
+  // current picture (u8) and the reference list of this picture
+  uint8_t *cur = nullptr; int cur_w = 0, cur_h = 0, cur_pitch = 0; size_t cur_cap = 0;
+  int ref_list[JMB_MAX_REFS]; int nref = 0;
+  jmb_me_config me;
+  bool me_configured = false;
+  // staging: pinned host buffer + device scratch, grown on demand
+  void *h_stage = nullptr; size_t h_stage_cap = 0;
+  void *d_stage = nullptr; size_t d_stage_cap = 0;
+  void *d_stage2 = nullptr; size_t d_stage2_cap = 0;
+  void *d_groups = nullptr; size_t d_groups_cap = 0;
+  void *h_groups = nullptr; size_t h_groups_cap = 0;
+  void *d_reftab = nullptr; size_t d_reftab_cap = 0;
+  void *d_qdesc = nullptr; size_t d_qdesc_cap = 0;
+  void *d_stage3 = nullptr; size_t d_stage3_cap = 0;
+  void *d_stage4 = nullptr; size_t d_stage4_cap = 0;
+  void *d_stage5 = nullptr; size_t d_stage5_cap = 0;
+};
+
+int jmb_fail(jmb_ctx *ctx, int code, const char *fmt, ...);
+int jmb_reserve_host(jmb_ctx *ctx, void **p, size_t *cap, size_t bytes);
+int jmb_reserve_dev(jmb_ctx *ctx, void **p, size_t *cap, size_t bytes);
+
+#define JMB_CUDA(ctx, call)                                                                     \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess)                                                                      \
+      return jmb_fail((ctx), JMB_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #call,        \
+                      cudaGetErrorString(e_));                                                  \
+  } while (0)
+
+#define JMB_LAUNCH_CHECK(ctx)                                                                   \
+  do {                                                                                          \
+    (ctx)->launches++;                                                                          \
+    JMB_CUDA((ctx), cudaGetLastError());                                                        \
+  } while (0)
+
+// ---- device helpers shared by the kernels -----------------------------------------------------
+__device__ __forceinline__ int jmb_clip(int lo, int hi, int v) { return min(max(v, lo), hi); }
+
+// mvbits[] of lencod/src/mv_search.c:366-374: 1 for 0, else 2*floor(log2|v|)+3
+__device__ __forceinline__ int jmb_mvbits(int v) {
+  int a = abs(v);
+  return a ? (2 * (31 - __clz(a)) + 3) : 1;
+}
+
+// index of displacement (dx,dy) in JM's square spiral (lencod/src/mv_search.c:406-442)
+__device__ __forceinline__ int jmb_spiral_index(int dx, int dy) {
+  int l = max(abs(dx), abs(dy));
+  if (l == 0) return 0;
+  int base = (2 * l - 1) * (2 * l - 1);
+  if (abs(dy) == l && abs(dx) < l) return base + 2 * (dx + l - 1) + (dy > 0);
+  return base + 2 * (2 * l - 1) + 2 * (dy + l) + (dx > 0);
+}
+
+// kernels (defined in k_*.cu), launched through these host wrappers
+int jmb_launch_subpel(jmb_ctx *ctx, const uint16_t *d_src, int src_stride, jmb_ref *r);

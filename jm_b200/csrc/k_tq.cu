@@ -1,0 +1,289 @@
+// k_tq.cu -- K7 + K8: H.264 forward integer transforms and quantisation, and the fused
+// motion-compensation -> residual -> transform -> quantisation pass over a whole picture.
+//
+//  forward4x4 / forward8x8          lcommon/src/transform.c:20-68, :353-448
+//  quant_4x4_normal / _around       lencod/src/quant4x4_normal.c:39-115, quant4x4_around.c:40-130
+//  quant_8x8_normal / _around       lencod/src/quant8x8_normal.c:43-107, quant8x8_around.c:40-115
+//  quant_8x8cavlc_normal / _around  lencod/src/quant8x8_normal.c:123-202, quant8x8_around.c:133-223
+//  luma_prediction                  lencod/src/mc_prediction.c:117-236 (copy out of the quarter-pel
+//                                   plane the mv selects, UMVLine4X origin clamp per predicted block)
+//  luma_residual_coding_8x8         lencod/src/macroblock.c:919-1022 (8x8 prediction units for modes
+//                                   1..4, 4x4 units for modes 5..7; per-quadrant coeff_cost)
+//
+// All arithmetic is int32 exactly as in JM.  One thread owns one transform block; the work is a
+// pure stream (residual in, levels out), i.e. HBM-bound.
+#include "jmb_internal.h"
+
+namespace {
+
+__device__ __forceinline__ void fwd4(int *b) {
+  int t[16];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    int *p = b + 4 * i;
+    int t0 = p[0] + p[3], t1 = p[1] + p[2], t2 = p[1] - p[2], t3 = p[0] - p[3];
+    t[4 * i] = t0 + t1; t[4 * i + 1] = (t3 << 1) + t2; t[4 * i + 2] = t0 - t1; t[4 * i + 3] = t3 - (t2 << 1);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    int t0 = t[i] + t[12 + i], t1 = t[4 + i] + t[8 + i], t2 = t[4 + i] - t[8 + i], t3 = t[i] - t[12 + i];
+    b[i] = t0 + t1; b[4 + i] = t2 + (t3 << 1); b[8 + i] = t0 - t1; b[12 + i] = t3 - (t2 << 1);
+  }
+}
+
+__device__ __forceinline__ void fwd8_1d(const int *p, int s, int *o, int os) {
+  int a0 = p[0] + p[7 * s], a1 = p[s] + p[6 * s], a2 = p[2 * s] + p[5 * s], a3 = p[3 * s] + p[4 * s];
+  int b0 = a0 + a3, b1 = a1 + a2, b2 = a0 - a3, b3 = a1 - a2;
+  a0 = p[0] - p[7 * s]; a1 = p[s] - p[6 * s]; a2 = p[2 * s] - p[5 * s]; a3 = p[3 * s] - p[4 * s];
+  int b4 = a1 + a2 + ((a0 >> 1) + a0), b5 = a0 - a3 - ((a2 >> 1) + a2);
+  int b6 = a0 + a3 - ((a1 >> 1) + a1), b7 = a1 - a2 + ((a3 >> 1) + a3);
+  o[0] = b0 + b1; o[os] = b4 + (b7 >> 2); o[2 * os] = b2 + (b3 >> 1); o[3 * os] = b5 + (b6 >> 2);
+  o[4 * os] = b0 - b1; o[5 * os] = b6 - (b5 >> 2); o[6 * os] = (b2 >> 1) - b3; o[7 * os] = (b4 >> 2) - b7;
+}
+
+__device__ void fwd8(int *b) {
+  int t[64];
+#pragma unroll
+  for (int i = 0; i < 8; i++) fwd8_1d(b + 8 * i, 1, t + 8 * i, 1);
+#pragma unroll
+  for (int i = 0; i < 8; i++) fwd8_1d(t + i, 8, b + i, 8);
+}
+
+struct QOut { int nonzero; int cost; };
+
+// quantise one block in scan order.  coef: in = transformed, out = dequantised (JM leaves it in tblock).
+// LISTS: write JM's (level, run) lists; otherwise write the level of every scan position to lv16.
+template <int N, bool LISTS>
+__device__ QOut quant_block(const jmb_quant_desc &q, int *coef, int *levels, int *runs, int *fadj, int16_t *lv16) {
+  constexpr int NN = N * N;
+  const int qp_per = q.qp / 6, q_bits = (N == 4 ? 15 : 16) + qp_per, dq = (N == 4) ? 4 : 6;
+  const bool cavlc8 = (N == 8) && q.is_cavlc;
+  const bool clip = (N == 4) ? (q.is_cavlc != 0) : cavlc8;
+  int nl[4] = {0, 0, 0, 0}, run[4] = {0, 0, 0, 0};
+  QOut o{0, 0};
+  for (int k = 0; k < NN; k++) {
+    const int i = q.scan[k][0], j = q.scan[k][1], idx = j * N + i;
+    const int s = cavlc8 ? (k >> 4) : 0;
+    const int c = coef[idx];
+    int level = 0, adj = 0;
+    if (c != 0) {
+      const int scaled = abs(c) * q.qparams[idx][1];
+      level = (scaled + q.qparams[idx][0]) >> q_bits;
+      if (level != 0) {
+        if (clip) level = min(level, 2063);                      // CAVLC_LEVEL_LIMIT
+        adj = (q.adapt_rnd_weight * (scaled - (level << q_bits)) + (1 << q_bits)) >> (q_bits + 1);
+        o.cost += (level > 1) ? 999999 : q.c_cost[run[s]];        // MAX_VALUE
+        if (c < 0) level = -level;
+        coef[idx] = (((level * q.qparams[idx][2]) << qp_per) + (1 << (dq - 1))) >> dq;
+        o.nonzero = 1;
+      } else coef[idx] = 0;
+    }
+    if (fadj) fadj[idx] = adj;
+    if (LISTS) {
+      if (level != 0) {
+        const int base = cavlc8 ? 17 * s : 0;
+        levels[base + nl[s]] = level; runs[base + nl[s]] = run[s];
+        nl[s]++; run[s] = 0;
+      } else run[s]++;
+    } else {
+      lv16[k] = (int16_t)level;
+      if (level != 0) run[s] = 0; else run[s]++;
+    }
+  }
+  if (LISTS) {
+    if (cavlc8) { for (int s = 0; s < 4; s++) levels[17 * s + nl[s]] = 0; }
+    else levels[nl[0]] = 0;
+  }
+  return o;
+}
+
+template <int N>
+__global__ void k_forward(int *blocks, int nblk) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nblk) return;
+  int b[N * N];
+  int *g = blocks + (size_t)i * N * N;
+#pragma unroll
+  for (int k = 0; k < N * N; k++) b[k] = g[k];
+  if (N == 4) fwd4(b); else fwd8(b);
+#pragma unroll
+  for (int k = 0; k < N * N; k++) g[k] = b[k];
+}
+
+template <int N>
+__global__ void k_quant_blocks(const jmb_quant_desc *__restrict__ qd, int do_transform, int *coef, int nblk, int lr_stride,
+                               int *levels, int *runs, int *fadjust, int *coeff_cost, int *nonzero) {
+  __shared__ jmb_quant_desc q;
+  for (int i = threadIdx.x; i < (int)(sizeof(q) / 4); i += blockDim.x) ((int *)&q)[i] = ((const int *)qd)[i];
+  __syncthreads();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nblk) return;
+  int b[N * N];
+  int *g = coef + (size_t)i * N * N;
+  for (int k = 0; k < N * N; k++) b[k] = g[k];
+  if (do_transform) { if (N == 4) fwd4(b); else fwd8(b); }
+  QOut o = quant_block<N, true>(q, b, levels + (size_t)i * lr_stride, runs + (size_t)i * lr_stride,
+                                (q.around && fadjust) ? fadjust + (size_t)i * N * N : nullptr, nullptr);
+  for (int k = 0; k < N * N; k++) g[k] = b[k];
+  coeff_cost[i] += o.cost;
+  nonzero[i] = o.nonzero;
+}
+
+// one thread per transform block of the picture
+template <int N>
+__global__ void k_mc_tq(const jmb_mb_pred *__restrict__ pred, int n_mb, int mb_w, const jmb_quant_desc *__restrict__ qd,
+                        const uint8_t *__restrict__ cur, int cur_pitch, const uint8_t *const *__restrict__ ref_planes,
+                        size_t plane_bytes, int ref_pitch, int w, int h,
+                        int16_t *__restrict__ levels, int *__restrict__ coeff_cost, unsigned *__restrict__ cbp_blk) {
+  __shared__ jmb_quant_desc q;
+  for (int i = threadIdx.x; i < (int)(sizeof(q) / 4); i += blockDim.x) ((int *)&q)[i] = ((const int *)qd)[i];
+  __syncthreads();
+  constexpr int PER_MB = (N == 4) ? 16 : 4;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_mb * PER_MB) return;
+  const int mb = t / PER_MB, b = t - mb * PER_MB;
+  const int mbx = (mb % mb_w) * 16, mby = (mb / mb_w) * 16;
+  const int bx4 = (N == 4) ? (b & 3) : (b & 1) * 2, by4 = (N == 4) ? (b >> 2) : (b >> 1) * 2;   // 4x4 units in the MB
+  const int b8 = (by4 >> 1) * 2 + (bx4 >> 1);
+  const jmb_mb_pred *mp = pred + mb;
+  const int mode = mp->b8mode[b8];
+  // prediction unit: the 8x8 quadrant for modes 1..4, the 4x4 block for modes 5..7 (macroblock.c:946-971)
+  int ux4 = bx4, uy4 = by4;
+  if (mode < 5 || N == 8) { ux4 &= ~1; uy4 &= ~1; }
+  const int mvx = mp->mv[uy4 * 4 + ux4][0], mvy = mp->mv[uy4 * 4 + ux4][1];
+  const int qx = ((mbx + ux4 * 4) << 2) + mvx, qy = ((mby + uy4 * 4) << 2) + mvy;
+  const int iy = jmb_clip(-JMB_PAD_Y, h + JMB_PAD_Y - 1 - 16, qy >> 2), ix = jmb_clip(-JMB_PAD_X, w + JMB_PAD_X - 1 - 16, qx >> 2);
+  const uint8_t *rp = ref_planes[mp->ref[b8]] + (size_t)((qy & 3) * 4 + (qx & 3)) * plane_bytes +
+                      (size_t)(iy + JMB_PAD_Y + (by4 - uy4) * 4) * ref_pitch + (ix + JMB_PAD_X + (bx4 - ux4) * 4);
+  const uint8_t *sp = cur + (size_t)(mby + by4 * 4) * cur_pitch + mbx + bx4 * 4;
+  int r[N * N];
+#pragma unroll
+  for (int y = 0; y < N; y++)
+#pragma unroll
+    for (int x = 0; x < N; x++) r[y * N + x] = (int)sp[(size_t)y * cur_pitch + x] - (int)rp[(size_t)y * ref_pitch + x];
+  if (N == 4) fwd4(r); else fwd8(r);
+  QOut o = quant_block<N, false>(q, r, nullptr, nullptr, nullptr, levels + (size_t)mb * 256 + b * N * N);
+  if (o.cost) atomicAdd(&coeff_cost[mb * 4 + b8], o.cost);
+  if (o.nonzero) {
+    unsigned bits = (N == 4) ? (1u << (by4 * 4 + bx4)) : (51u << (4 * b8 - 2 * (b8 & 1)));   // macroblock.c:1004
+    atomicOr(&cbp_blk[mb], bits);
+  }
+}
+
+}  // namespace
+
+static int check_qdesc(jmb_ctx *ctx, const jmb_quant_desc *q) {
+  if (!q || (q->n != 4 && q->n != 8)) return jmb_fail(ctx, JMB_ERR_ARG, "quant desc: n must be 4 or 8");
+  if (q->qp < 0 || q->qp > 87) return jmb_fail(ctx, JMB_ERR_ARG, "quant desc: qp %d", q->qp);
+  for (int k = 0; k < q->n * q->n; k++)
+    if (q->scan[k][0] >= q->n || q->scan[k][1] >= q->n) return jmb_fail(ctx, JMB_ERR_ARG, "quant desc: scan[%d] outside the block", k);
+  return 0;
+}
+
+static int upload_qdesc(jmb_ctx *ctx, const jmb_quant_desc *q, const jmb_quant_desc **d_q) {
+  int rc = jmb_reserve_dev(ctx, &ctx->d_qdesc, &ctx->d_qdesc_cap, sizeof(*q)); if (rc) return rc;
+  JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_qdesc, q, sizeof(*q), cudaMemcpyHostToDevice, ctx->stream));
+  *d_q = (const jmb_quant_desc *)ctx->d_qdesc;
+  return 0;
+}
+
+extern "C" {
+
+int jmb_forward_transform(jmb_ctx *ctx, int32_t *blocks, int nblk, int n, int loc) {
+  if (n != 4 && n != 8) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_forward_transform: n=%d", n);
+  if (nblk <= 0) return JMB_OK;
+  JMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  size_t bytes = (size_t)nblk * n * n * 4;
+  int *d = blocks;
+  if (loc == JMB_HOST) {
+    int rc = jmb_reserve_dev(ctx, &ctx->d_stage, &ctx->d_stage_cap, bytes); if (rc) return rc;
+    JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage, blocks, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    d = (int *)ctx->d_stage;
+  }
+  if (n == 4) k_forward<4><<<(nblk + 127) / 128, 128, 0, ctx->stream>>>(d, nblk);
+  else k_forward<8><<<(nblk + 63) / 64, 64, 0, ctx->stream>>>(d, nblk);
+  JMB_LAUNCH_CHECK(ctx);
+  if (loc == JMB_HOST) {
+    JMB_CUDA(ctx, cudaMemcpyAsync(blocks, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return JMB_OK;
+}
+
+int jmb_quant_blocks(jmb_ctx *ctx, const jmb_quant_desc *q, int do_transform, int32_t *coef, int nblk,
+                     int32_t *levels, int32_t *runs, int32_t *fadjust, int32_t *coeff_cost, int32_t *nonzero, int loc) {
+  int rc = check_qdesc(ctx, q); if (rc) return rc;
+  if (nblk <= 0) return JMB_OK;
+  if (!coef || !levels || !runs || !coeff_cost || !nonzero) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_quant_blocks: NULL buffer");
+  JMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int nn = q->n * q->n, lr = (q->n == 4) ? 17 : (q->is_cavlc ? 68 : 65);
+  const jmb_quant_desc *d_q; rc = upload_qdesc(ctx, q, &d_q); if (rc) return rc;
+  int *d_coef = coef, *d_lv = levels, *d_rn = runs, *d_fa = fadjust, *d_cc = coeff_cost, *d_nz = nonzero;
+  if (loc == JMB_HOST) {
+    // one device arena: coef | levels | runs | fadjust | cost | nonzero
+    size_t o_lv = (size_t)nblk * nn, o_rn = o_lv + (size_t)nblk * lr, o_fa = o_rn + (size_t)nblk * lr, o_cc = o_fa + (size_t)nblk * nn,
+           o_nz = o_cc + nblk, total = o_nz + nblk;
+    rc = jmb_reserve_dev(ctx, &ctx->d_stage, &ctx->d_stage_cap, total * 4); if (rc) return rc;
+    int *base = (int *)ctx->d_stage;
+    d_coef = base; d_lv = base + o_lv; d_rn = base + o_rn; d_fa = base + o_fa; d_cc = base + o_cc; d_nz = base + o_nz;
+    JMB_CUDA(ctx, cudaMemcpyAsync(d_coef, coef, (size_t)nblk * nn * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JMB_CUDA(ctx, cudaMemcpyAsync(d_cc, coeff_cost, (size_t)nblk * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JMB_CUDA(ctx, cudaMemsetAsync(d_lv, 0, (size_t)nblk * lr * 2 * 4, ctx->stream));
+  }
+  if (q->n == 4) k_quant_blocks<4><<<(nblk + 127) / 128, 128, 0, ctx->stream>>>(d_q, do_transform, d_coef, nblk, lr, d_lv, d_rn, d_fa, d_cc, d_nz);
+  else k_quant_blocks<8><<<(nblk + 63) / 64, 64, 0, ctx->stream>>>(d_q, do_transform, d_coef, nblk, lr, d_lv, d_rn, d_fa, d_cc, d_nz);
+  JMB_LAUNCH_CHECK(ctx);
+  if (loc == JMB_HOST) {
+    JMB_CUDA(ctx, cudaMemcpyAsync(coef, d_coef, (size_t)nblk * nn * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaMemcpyAsync(levels, d_lv, (size_t)nblk * lr * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaMemcpyAsync(runs, d_rn, (size_t)nblk * lr * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (fadjust && q->around) JMB_CUDA(ctx, cudaMemcpyAsync(fadjust, d_fa, (size_t)nblk * nn * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaMemcpyAsync(coeff_cost, d_cc, (size_t)nblk * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaMemcpyAsync(nonzero, d_nz, (size_t)nblk * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return JMB_OK;
+}
+
+int jmb_mc_tq(jmb_ctx *ctx, const jmb_mb_pred *pred, int n_mb, const jmb_quant_desc *q,
+              int16_t *levels, int32_t *coeff_cost, uint32_t *cbp_blk, int loc) {
+  int rc = check_qdesc(ctx, q); if (rc) return rc;
+  if (!ctx->cur || ctx->nref == 0) return jmb_fail(ctx, JMB_ERR_STATE, "jmb_mc_tq: call jmb_pic_begin first");
+  const int mb_w = ctx->cur_w / 16, mb_total = mb_w * (ctx->cur_h / 16);
+  if (n_mb <= 0 || n_mb > mb_total) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_mc_tq: n_mb %d (picture has %d)", n_mb, mb_total);
+  JMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const jmb_ref &r0 = ctx->refs[ctx->ref_list[0]];
+  const uint8_t *tab[JMB_MAX_REFS];
+  for (int i = 0; i < JMB_MAX_REFS; i++) tab[i] = i < ctx->nref ? ctx->refs[ctx->ref_list[i]].planes : nullptr;
+  rc = jmb_reserve_dev(ctx, &ctx->d_reftab, &ctx->d_reftab_cap, sizeof(tab)); if (rc) return rc;
+  JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_reftab, tab, sizeof(tab), cudaMemcpyHostToDevice, ctx->stream));
+  const jmb_quant_desc *d_q; rc = upload_qdesc(ctx, q, &d_q); if (rc) return rc;
+  const jmb_mb_pred *d_pred = pred; int16_t *d_lv = levels; int *d_cc = coeff_cost; unsigned *d_cbp = cbp_blk;
+  if (loc == JMB_HOST) {
+    for (int i = 0; i < n_mb; i++)
+      for (int k = 0; k < 4; k++)
+        if (pred[i].b8mode[k] < 1 || pred[i].b8mode[k] > 7 || pred[i].ref[k] >= ctx->nref)
+          return jmb_fail(ctx, JMB_ERR_ARG, "jmb_mc_tq: macroblock %d quadrant %d: mode %d ref %d", i, k, pred[i].b8mode[k], pred[i].ref[k]);
+    rc = jmb_reserve_dev(ctx, &ctx->d_stage, &ctx->d_stage_cap, (size_t)n_mb * sizeof(jmb_mb_pred)); if (rc) return rc;
+    rc = jmb_reserve_dev(ctx, &ctx->d_stage3, &ctx->d_stage3_cap, (size_t)n_mb * (512 + 16 + 4)); if (rc) return rc;
+    JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage, pred, (size_t)n_mb * sizeof(jmb_mb_pred), cudaMemcpyHostToDevice, ctx->stream));
+    d_pred = (const jmb_mb_pred *)ctx->d_stage;
+    d_lv = (int16_t *)ctx->d_stage3; d_cc = (int *)((char *)ctx->d_stage3 + (size_t)n_mb * 512); d_cbp = (unsigned *)(d_cc + (size_t)n_mb * 4);
+  }
+  JMB_CUDA(ctx, cudaMemsetAsync(d_cc, 0, (size_t)n_mb * 16, ctx->stream));
+  JMB_CUDA(ctx, cudaMemsetAsync(d_cbp, 0, (size_t)n_mb * 4, ctx->stream));
+  if (q->n == 4) k_mc_tq<4><<<(n_mb * 16 + 127) / 128, 128, 0, ctx->stream>>>(d_pred, n_mb, mb_w, d_q, ctx->cur, ctx->cur_pitch,
+        (const uint8_t *const *)ctx->d_reftab, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_cc, d_cbp);
+  else k_mc_tq<8><<<(n_mb * 4 + 63) / 64, 64, 0, ctx->stream>>>(d_pred, n_mb, mb_w, d_q, ctx->cur, ctx->cur_pitch,
+        (const uint8_t *const *)ctx->d_reftab, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_cc, d_cbp);
+  JMB_LAUNCH_CHECK(ctx);
+  if (loc == JMB_HOST) {
+    JMB_CUDA(ctx, cudaMemcpyAsync(levels, d_lv, (size_t)n_mb * 512, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaMemcpyAsync(coeff_cost, d_cc, (size_t)n_mb * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaMemcpyAsync(cbp_blk, d_cbp, (size_t)n_mb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return JMB_OK;
+}
+
+}  // extern "C"

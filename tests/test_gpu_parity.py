@@ -1,0 +1,325 @@
+"""GPU parity tests proper: every libjmb200 entry point, called through the C ABI, against the CPU
+oracle (oracle/jm_oracle.c, itself pinned to the real JM functions by test_oracle_vs_ref.py) on the
+same seeded inputs.  Bit-exact: this is integer work."""
+import numpy as np
+import pytest
+
+from jm_b200 import api, synth
+from jm_b200 import h264_tables as T
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+BIG = po.DISTBLK_MAX
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+def _frames(w, h, seed, motion=(3, -2), n=2):
+    return synth.luma_frames(w, h, n, seed=seed, motion=motion)
+
+
+@pytest.mark.parametrize("w,h,seed", [(96, 64, 1), (176, 144, 2), (16, 16, 3), (400, 48, 4)])
+def test_subpel_planes(ctx, oracle, w, h, seed):
+    f = _frames(w, h, seed)[0]
+    if seed == 3:
+        f = np.random.default_rng(3).choice([0, 255], size=(h, w)).astype(np.uint16)   # exercises the clips
+    ctx.ref_put(0, f)
+    r = oracle.ref_create(f)
+    want = oracle.planes(r)
+    for fy in range(4):
+        for fx in range(4):
+            got = ctx.ref_plane(0, fy, fx, (h, w))
+            assert np.array_equal(got, want[fy, fx]), (fy, fx)
+    oracle.ref_destroy(r)
+
+
+def _random_reqs(rng, w, h, n, R, mode, flags, pred_span=40, lam_max=400):
+    reqs = np.zeros(n, api.ME_REQ)
+    for q in reqs:
+        bt = int(rng.integers(1, 8))
+        bsx, bsy = api.BLOCK_SIZE[bt]
+        q["blocktype"] = bt
+        q["pos_x"] = int(rng.integers(0, (w - bsx) // bsx + 1)) * bsx
+        q["pos_y"] = int(rng.integers(0, (h - bsy) // bsy + 1)) * bsy
+        q["pred_x"], q["pred_y"] = rng.integers(-pred_span, pred_span + 1, 2)
+        q["center_x"] = ((int(q["pred_x"]) + 2) >> 2) * 4
+        q["center_y"] = ((int(q["pred_y"]) + 2) >> 2) * 4
+        q["mode"], q["flags"] = mode, flags
+        q["lambda"] = int(rng.integers(1, lam_max))
+        q["min_mcost"] = BIG
+    return reqs
+
+
+def _check_full(ctx, oracle, r, cur, reqs, res, R, sub=None):
+    for q, o in zip(reqs, res):
+        pos = (int(q["pos_x"]), int(q["pos_y"])); pred = (int(q["pred_x"]), int(q["pred_y"]))
+        center = (int(q["center_x"]), int(q["center_y"]))
+        mv, cost = oracle.full_search(r, cur, int(q["blocktype"]), pos, pred, center, int(q["lambda"][0]), int(q["min_mcost"]), R)
+        assert (int(o["imv_x"]), int(o["imv_y"])) == mv and int(o["icost"]) == cost, (q, o, mv, cost)
+        if sub:
+            mh, mq, shp, sqp = sub
+            mc = cost if shp else BIG
+            t8 = int(bool(q["flags"] & api.REQ_TEST8X8))
+            mv2, c2 = oracle.sub_pel(r, cur, int(q["blocktype"]), pos, pred, mv, [int(x) for x in q["lambda"]], mc, mh, mq, shp, sqp, t8)
+            assert (int(o["mv_x"]), int(o["mv_y"])) == mv2 and int(o["cost"]) == c2, (q, o, mv2, c2)
+
+
+@pytest.mark.parametrize("w,h,R,seed,span", [(96, 64, 8, 5, 40), (64, 48, 12, 6, 200), (176, 144, 32, 7, 60)])
+def test_full_search_random_requests(ctx, oracle, w, h, R, seed, span):
+    """Ungrouped random requests; large predictors push whole windows outside the picture so the
+    partition-origin clamp (me_distortion.c:367) and the border path are exercised."""
+    f = _frames(w, h, seed)
+    ctx.configure(search_range=R)
+    ctx.ref_put(0, f[0]); ctx.pic_begin(f[1], [0])
+    r = oracle.ref_create(f[0])
+    rng = np.random.default_rng(seed)
+    reqs = _random_reqs(rng, w, h, 24 if R == 32 else 60, R, api.SEARCH_FULL, 0, pred_span=span)
+    res = ctx.me_search(reqs)
+    _check_full(ctx, oracle, r, f[1], reqs, res, R)
+    oracle.ref_destroy(r)
+
+
+def test_full_search_min_mcost_gate(ctx, oracle):
+    """Incoming min_mcost below every candidate: JM keeps the centre and returns min_mcost."""
+    w, h, R = 64, 48, 6
+    f = _frames(w, h, 8)
+    ctx.configure(search_range=R); ctx.ref_put(0, f[0]); ctx.pic_begin(f[1], [0])
+    r = oracle.ref_create(f[0])
+    reqs = _random_reqs(np.random.default_rng(8), w, h, 30, R, api.SEARCH_FULL, 0)
+    reqs["min_mcost"][::2] = 40
+    reqs["min_mcost"][1::4] = 3000
+    res = ctx.me_search(reqs)
+    _check_full(ctx, oracle, r, f[1], reqs, res, R)
+    oracle.ref_destroy(r)
+
+
+def _frame_reqs(w, h, rng, mode, flags, lam=None, jitter=6, base=(0, 0)):
+    parts = api.mb_partitions()
+    n_mb = (w // 16) * (h // 16)
+    reqs = np.zeros(n_mb * api.NPART, api.ME_REQ)
+    i = 0
+    for mb in range(n_mb):
+        mbx, mby = (mb % (w // 16)) * 16, (mb // (w // 16)) * 16
+        mbpred = rng.integers(-jitter, jitter + 1, 2) + np.array(base)
+        for (t, x, y) in parts:
+            q = reqs[i]; i += 1
+            q["blocktype"], q["pos_x"], q["pos_y"] = t, mbx + x, mby + y
+            p = mbpred + rng.integers(-3, 4, 2)
+            q["pred_x"], q["pred_y"] = p
+            c = p if mode == api.SEARCH_FULL else mbpred
+            q["center_x"], q["center_y"] = ((int(c[0]) + 2) >> 2) * 4, ((int(c[1]) + 2) >> 2) * 4
+            q["mode"], q["flags"] = mode, flags
+            q["lambda"] = lam if lam is not None else int(rng.integers(1, 300))
+            q["min_mcost"] = BIG
+    return reqs
+
+
+@pytest.mark.parametrize("flags,metrics", [(api.REQ_SUBPEL, (api.SAD, api.SATD, api.SATD)),
+                                           (api.REQ_SUBPEL, (api.SAD, api.SAD, api.SAD)),
+                                           (api.REQ_SUBPEL, (api.SAD, api.SATD, api.SAD)),
+                                           (api.REQ_SUBPEL | api.REQ_TEST8X8, (api.SAD, api.SATD, api.SATD))])
+def test_frame_search_with_subpel(ctx, oracle, flags, metrics):
+    """All 41 partitions of every macroblock in one call (shared 4x4 SADs), then the half-/quarter-pel
+    refinement, with each sub-pel metric combination JM's start_me_refinement_hp/qp rules produce."""
+    w, h, R = 80, 48, 8
+    f = _frames(w, h, 9, motion=(-3, 2))
+    ctx.configure(search_range=R, metric=metrics)
+    ctx.ref_put(0, f[0]); ctx.pic_begin(f[1], [0])
+    r = oracle.ref_create(f[0])
+    rng = np.random.default_rng(10)
+    reqs = _frame_reqs(w, h, rng, api.SEARCH_FULL, flags, base=(12, -8))
+    if flags & api.REQ_TEST8X8:
+        reqs["flags"][reqs["blocktype"] > 4] = api.REQ_SUBPEL      # JM only sets test8x8 for block types <= 4
+    res = ctx.me_search(reqs, frame=True)
+    shp = 0 if metrics[0] != metrics[1] else 1
+    sqp = 0 if metrics[1] != metrics[2] else 1
+    _check_full(ctx, oracle, r, f[1], reqs, res, R, sub=(metrics[1], metrics[2], shp, sqp))
+    # the ungrouped entry point must give the same answers
+    sel = rng.permutation(len(reqs))[:50]
+    res2 = ctx.me_search(reqs[sel])
+    assert np.array_equal(res2, res[sel])
+    oracle.ref_destroy(r)
+
+
+def test_fast_full_search(ctx, oracle):
+    """FAST_FULL: one centre per macroblock, macroblock-origin clamp, max_mvd guard; also the BlockSAD
+    surfaces JM's setup_fast_full_search would have produced."""
+    w, h, R = 64, 48, 8
+    f = _frames(w, h, 11, motion=(2, 3))
+    ctx.configure(search_range=R)
+    ctx.ref_put(0, f[0]); ctx.pic_begin(f[1], [0])
+    r = oracle.ref_create(f[0])
+    rng = np.random.default_rng(12)
+    reqs = _frame_reqs(w, h, rng, api.SEARCH_FAST_FULL, 0, jitter=30)
+    res = ctx.me_search(reqs, frame=True)
+    for g in range(len(reqs) // api.NPART):
+        q0 = reqs[g * api.NPART]
+        mb = (int(q0["pos_x"]), int(q0["pos_y"])); c = (int(q0["center_x"]), int(q0["center_y"]))
+        bs = oracle.ffs_setup(r, f[1], mb, c, R)
+        if g % 5 == 0:
+            got = ctx.ffs_surfaces(0, mb, c)
+            for bt, idxs in [(7, range(16)), (6, [0, 1, 2, 3, 8, 9, 10, 11]), (5, range(0, 16, 2)), (4, [0, 2, 8, 10]),
+                             (3, [0, 2]), (2, [0, 8]), (1, [0])]:
+                for i in idxs:
+                    assert np.array_equal(got[bt, i], bs[bt, i]), (mb, bt, i)
+        for k in range(api.NPART):
+            q, o = reqs[g * api.NPART + k], res[g * api.NPART + k]
+            bi = ((int(q["pos_y"]) & 15) >> 2) * 4 + ((int(q["pos_x"]) & 15) >> 2)
+            mv, cost = oracle.ffs_search(bs, R, int(q["blocktype"]), bi, c, (int(q["pred_x"]), int(q["pred_y"])),
+                                         int(q["lambda"][0]), BIG, ctx.max_mvd)
+            assert (int(o["imv_x"]), int(o["imv_y"])) == mv and int(o["icost"]) == cost, (g, k, q, o, mv, cost)
+    oracle.ref_destroy(r)
+
+
+def test_subpel_only_requests(ctx, oracle):
+    """JMB_REQ_SKIP_INT: the SubPelME call site alone (mv_search.c:975)."""
+    w, h = 64, 48
+    f = _frames(w, h, 13)
+    ctx.configure(search_range=8); ctx.ref_put(0, f[0]); ctx.pic_begin(f[1], [0])
+    r = oracle.ref_create(f[0])
+    rng = np.random.default_rng(13)
+    reqs = _random_reqs(rng, w, h, 80, 8, api.SEARCH_FULL, api.REQ_SUBPEL | api.REQ_SKIP_INT)
+    reqs["center_x"] = rng.integers(-12, 12, len(reqs)) * 4
+    reqs["center_y"] = rng.integers(-12, 12, len(reqs)) * 4
+    reqs["min_mcost"][::3] = 20000
+    res = ctx.me_search(reqs)
+    for q, o in zip(reqs, res):
+        mv, c = oracle.sub_pel(r, f[1], int(q["blocktype"]), (int(q["pos_x"]), int(q["pos_y"])), (int(q["pred_x"]), int(q["pred_y"])),
+                               (int(q["center_x"]), int(q["center_y"])), [int(x) for x in q["lambda"]], int(q["min_mcost"]),
+                               po.SATD, po.SATD, 0, 1, 0)
+        assert (int(o["mv_x"]), int(o["mv_y"])) == mv and int(o["cost"]) == c
+    oracle.ref_destroy(r)
+
+
+@pytest.mark.parametrize("metric", [api.SAD, api.SSE, api.SATD])
+def test_dist(ctx, oracle, metric):
+    w, h = 96, 64
+    f = _frames(w, h, 14)
+    ctx.ref_put(0, f[0]); ctx.pic_begin(f[1], [0])
+    r = oracle.ref_create(f[0])
+    rng = np.random.default_rng(metric)
+    for _ in range(12):
+        bt = int(rng.integers(1, 8)); bsx, bsy = api.BLOCK_SIZE[bt]
+        pos = (int(rng.integers(0, (w - bsx) // 4 + 1)) * 4, int(rng.integers(0, (h - bsy) // 4 + 1)) * 4)
+        t8 = int(metric == api.SATD and bt <= 4 and rng.integers(0, 2))
+        cands = np.stack([pos[0] * 4 + rng.integers(-220, 220, 40), pos[1] * 4 + rng.integers(-170, 170, 40)], 1).astype(np.int16)
+        got = ctx.dist(0, metric, bt, pos, cands, t8)
+        want = [oracle.dist(r, f[1], bt, pos, (int(c[0]), int(c[1])), metric, t8) for c in cands]
+        assert got.tolist() == want
+    oracle.ref_destroy(r)
+
+
+def test_forward_transforms(ctx, oracle):
+    rng = np.random.default_rng(20)
+    b4 = rng.integers(-255, 256, size=(500, 4, 4)); b8 = rng.integers(-255, 256, size=(300, 8, 8))
+    g4 = ctx.forward_transform(b4, 4); g8 = ctx.forward_transform(b8, 8)
+    for i in range(len(b4)):
+        assert np.array_equal(g4[i], oracle.forward4x4(b4[i]))
+    for i in range(len(b8)):
+        assert np.array_equal(g8[i], oracle.forward8x8(b8[i]))
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("do_transform", [0, 1])
+def test_quant_blocks(ctx, oracle, variant, do_transform):
+    n = 4 if variant < 2 else 8
+    around, cavlc8 = variant & 1, variant >= 4
+    scan = T.SNGL_SCAN if n == 4 else (T.SNGL_SCAN8x8_CAVLC if cavlc8 else T.SNGL_SCAN8x8)
+    cc = T.COEFF_COST4x4[0] if n == 4 else T.COEFF_COST8x8[0]
+    rng = np.random.default_rng(100 + variant)
+    for qp in [0, 7, 22, 28, 37, 51]:
+        for cav in ([1] if cavlc8 else [0, 1]):
+            if variant in (2, 3) and cav:
+                continue        # n=8 with is_cavlc selects the cavlc variants
+            intra = int(rng.integers(0, 2)); arw = int(rng.integers(1, 9))
+            qpar = T.q_params(qp, intra, n)
+            qd = api.quant_desc(n, qp, qpar, scan, cc, cav, around, arw)
+            res = np.concatenate([rng.integers(-a, a + 1, size=(40, n, n)) for a in (2, 30, 255, 1023)])
+            res[::9, 0, 0] = 0
+            coef = res if do_transform else np.stack([(oracle.forward4x4 if n == 4 else oracle.forward8x8)(b) for b in res])
+            got = ctx.quant_blocks(qd, coef, do_transform=do_transform, cost0=3)
+            for i in range(len(res)):
+                tc = (oracle.forward4x4 if n == 4 else oracle.forward8x8)(res[i])
+                want = oracle.quant(variant, tc, qp, qpar, scan, cc, cav, arw=arw, cost0=3)
+                assert got["nonzero"][i] == want["nonzero"] and got["coeff_cost"][i] == want["coeff_cost"], (qp, i)
+                assert np.array_equal(got["coef"][i], want["coef"])
+                assert np.array_equal(got["levels"][i], want["levels"]) and np.array_equal(got["runs"][i], want["runs"])
+                if around:
+                    assert np.array_equal(got["fadjust"][i], want["fadjust"])
+
+
+def _mc_tq_reference(oracle, planes, cur, pred, w, h, n, qp, qpar, scan, cc, cav):
+    """luma_prediction + compute_residue + forward + quant, composed from oracle pieces."""
+    n_mb = len(pred); mb_w = w // 16
+    levels = np.zeros((n_mb, 256), np.int16); cost = np.zeros((n_mb, 4), np.int32); cbp = np.zeros(n_mb, np.uint32)
+    variant = 0 if n == 4 else (4 if cav else 2)
+    for mb in range(n_mb):
+        mbx, mby = (mb % mb_w) * 16, (mb // mb_w) * 16
+        step = n // 4
+        for by4 in range(0, 4, step):
+            for bx4 in range(0, 4, step):
+                b8 = (by4 >> 1) * 2 + (bx4 >> 1)
+                mode = int(pred[mb]["b8mode"][b8])
+                ux4, uy4 = (bx4 & ~1, by4 & ~1) if (mode < 5 or n == 8) else (bx4, by4)
+                mvx, mvy = [int(v) for v in pred[mb]["mv"][uy4 * 4 + ux4]]
+                qx, qy = ((mbx + ux4 * 4) << 2) + mvx, ((mby + uy4 * 4) << 2) + mvy
+                iy = min(max(qy >> 2, -20), h + 20 - 1 - 16); ix = min(max(qx >> 2, -32), w + 32 - 1 - 16)
+                y0 = iy + 20 + (by4 - uy4) * 4; x0 = ix + 32 + (bx4 - ux4) * 4
+                p = planes[qy & 3, qx & 3, y0:y0 + n, x0:x0 + n].astype(np.int32)
+                s = cur[mby + by4 * 4: mby + by4 * 4 + n, mbx + bx4 * 4: mbx + bx4 * 4 + n].astype(np.int32)
+                tc = (oracle.forward4x4 if n == 4 else oracle.forward8x8)(s - p)
+                o = oracle.quant(variant, tc, qp, qpar, scan, cc, cav)
+                # (level, run) lists -> level per scan position
+                lv = np.zeros(n * n, np.int16)
+                for sgrp in range(4 if variant == 4 else 1):
+                    k = sgrp * 16 if variant == 4 else 0
+                    for L, Rn in zip(o["levels"][17 * sgrp:], o["runs"][17 * sgrp:]):
+                        if L == 0:
+                            break
+                        k += Rn; lv[k] = L; k += 1
+                b = by4 * 4 + bx4 if n == 4 else b8
+                levels[mb, b * n * n:(b + 1) * n * n] = lv
+                cost[mb, b8] += o["coeff_cost"]
+                if o["nonzero"]:
+                    cbp[mb] |= (1 << (by4 * 4 + bx4)) if n == 4 else (51 << (4 * b8 - 2 * (b8 & 1)))
+    return levels, cost, cbp
+
+
+@pytest.mark.parametrize("n,cav", [(4, 1), (4, 0), (8, 0), (8, 1)])
+def test_mc_tq(ctx, oracle, n, cav):
+    w, h = 64, 48
+    f = _frames(w, h, 15)
+    ctx.ref_put(0, f[0]); ctx.pic_begin(f[1], [0])
+    r = oracle.ref_create(f[0]); planes = oracle.planes(r)
+    rng = np.random.default_rng(15 + n)
+    n_mb = (w // 16) * (h // 16)
+    pred = np.zeros(n_mb, api.MB_PRED)
+    pred["mv"] = rng.integers(-60, 60, size=(n_mb, 16, 2))
+    pred["mv"][0] = rng.integers(-400, 400, size=(16, 2))       # far outside: origin clamps
+    pred["b8mode"] = rng.integers(1, 5 if n == 8 else 8, size=(n_mb, 4))
+    for qp in (20, 28, 40):
+        qpar = T.q_params(qp, 0, n)
+        scan = T.SNGL_SCAN if n == 4 else (T.SNGL_SCAN8x8_CAVLC if cav else T.SNGL_SCAN8x8)
+        cc = T.COEFF_COST4x4[0] if n == 4 else T.COEFF_COST8x8[0]
+        qd = api.quant_desc(n, qp, qpar, scan, cc, cav)
+        got = ctx.mc_tq(pred, qd)
+        want = _mc_tq_reference(oracle, planes, f[1], pred, w, h, n, qp, qpar, scan, cc, cav)
+        for a, b, name in zip(got, want, ("levels", "coeff_cost", "cbp_blk")):
+            assert np.array_equal(a, b), (name, qp)
+    oracle.ref_destroy(r)
+
+
+def test_errors_are_loud(ctx):
+    with pytest.raises(api.JMBError):
+        ctx.ref_put(0, np.zeros((30, 30), np.uint16))           # not a multiple of 16
+    with pytest.raises(api.JMBError):
+        ctx.ref_put(99, np.zeros((32, 32), np.uint16))
+    bad = np.zeros(1, api.ME_REQ); bad["blocktype"] = 9
+    ctx.ref_put(0, np.zeros((32, 32), np.uint16)); ctx.pic_begin(np.zeros((32, 32), np.uint16), [0])
+    with pytest.raises(api.JMBError):
+        ctx.me_search(bad)
