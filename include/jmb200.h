@@ -187,6 +187,17 @@ int jmb_quant_blocks(jmb_ctx *ctx, const jmb_quant_desc *q, int do_transform, in
 int jmb_mc_tq(jmb_ctx *ctx, const jmb_mb_pred *pred, int n_mb, const jmb_quant_desc *q,
               int16_t *levels, int32_t *coeff_cost, uint32_t *cbp_blk, int loc);
 
+/* all_mv fill of BlockMotionSearch (lencod/src/mv_search.c:1005-1014): turn the results of a
+ * jmb_me_search_frame call (41 per macroblock, canonical order) into the jmb_mb_pred of partition
+ * mode `mode` (1..7) for every macroblock, reference 0. */
+int jmb_pred_from_results(jmb_ctx *ctx, const jmb_me_res *res, int n_mb, int mode, jmb_mb_pred *pred, int loc);
+
+/* ---- measurement: CUDA events recorded on the context's stream around every kernel launch ----- */
+/* kernel names: subpel_planes, pack_cur, int_search, subpel_refine, dist, ffs_surfaces, forward,
+ * quant_blocks, mc_tq, pred_from_results */
+int jmb_timing_enable(jmb_ctx *ctx, int on);      /* also clears the accumulated samples */
+int jmb_timing_get(jmb_ctx *ctx, const char *kernel, double *total_ms, int *launches);
+
 #ifdef __cplusplus
 }
 #endif

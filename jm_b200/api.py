@@ -65,6 +65,9 @@ def load_library():
     L.jmb_forward_transform.argtypes = [vp, vp, i, i, i]
     L.jmb_quant_blocks.argtypes = [vp, vp, i, vp, i, vp, vp, vp, vp, vp, i]
     L.jmb_mc_tq.argtypes = [vp, vp, i, vp, vp, vp, vp, i]
+    L.jmb_pred_from_results.argtypes = [vp, vp, i, i, vp, i]
+    L.jmb_timing_enable.argtypes = [vp, i]
+    L.jmb_timing_get.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(i)]
     return L
 
 
@@ -239,3 +242,19 @@ class Context:
             levels, cost, cbp = out
         self._ck(self.L.jmb_mc_tq(self.h, _ptr(pred), n_mb, _ptr(qdesc), _ptr(levels), _ptr(cost), _ptr(cbp), loc))
         return levels, cost, cbp
+
+    def pred_from_results(self, res, mode, loc=HOST, n_mb=None, out=None):
+        if loc == HOST:
+            res = np.ascontiguousarray(res, ME_RES)
+            n_mb = len(res) // NPART
+            out = np.zeros(n_mb, MB_PRED)
+        self._ck(self.L.jmb_pred_from_results(self.h, _ptr(res), n_mb, mode, _ptr(out), loc))
+        return out
+
+    def timing(self, on):
+        self._ck(self.L.jmb_timing_enable(self.h, int(on)))
+
+    def timing_get(self, kernel):
+        ms, n = C.c_double(), C.c_int()
+        self._ck(self.L.jmb_timing_get(self.h, kernel.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value

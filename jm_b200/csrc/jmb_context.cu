@@ -33,7 +33,45 @@ int jmb_reserve_dev(jmb_ctx *ctx, void **p, size_t *cap, size_t bytes) {
   return 0;
 }
 
+void jmb_time_begin(jmb_ctx *ctx, int kid) {
+  if (!ctx->timing) return;
+  if (ctx->ev_n[kid] == ctx->ev_cap[kid]) {
+    int cap = ctx->ev_cap[kid] ? ctx->ev_cap[kid] * 2 : 64;
+    ctx->ev[kid] = (jmb_ctx::EvPair *)realloc(ctx->ev[kid], cap * sizeof(jmb_ctx::EvPair));
+    for (int i = ctx->ev_cap[kid]; i < cap; i++) { cudaEventCreate(&ctx->ev[kid][i].a); cudaEventCreate(&ctx->ev[kid][i].b); }
+    ctx->ev_cap[kid] = cap;
+  }
+  cudaEventRecord(ctx->ev[kid][ctx->ev_n[kid]].a, ctx->stream);
+}
+void jmb_time_end(jmb_ctx *ctx, int kid) {
+  if (!ctx->timing) return;
+  cudaEventRecord(ctx->ev[kid][ctx->ev_n[kid]].b, ctx->stream);
+  ctx->ev_n[kid]++;
+}
+
 extern "C" {
+
+static const char *k_names[JMB_K_COUNT] = {"subpel_planes", "pack_cur", "int_search", "subpel_refine", "dist", "ffs_surfaces",
+                                           "forward", "quant_blocks", "mc_tq", "pred_from_results"};
+
+int jmb_timing_enable(jmb_ctx *ctx, int on) {
+  JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->timing = on != 0;
+  for (int k = 0; k < JMB_K_COUNT; k++) ctx->ev_n[k] = 0;
+  return JMB_OK;
+}
+
+int jmb_timing_get(jmb_ctx *ctx, const char *kernel, double *total_ms, int *launches) {
+  JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < JMB_K_COUNT; k++)
+    if (!strcmp(kernel, k_names[k])) {
+      double t = 0;
+      for (int i = 0; i < ctx->ev_n[k]; i++) { float ms = 0; JMB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[k][i].a, ctx->ev[k][i].b)); t += ms; }
+      *total_ms = t; *launches = ctx->ev_n[k];
+      return JMB_OK;
+    }
+  return jmb_fail(ctx, JMB_ERR_ARG, "jmb_timing_get: unknown kernel '%s'", kernel);
+}
 
 int jmb_abi_version(void) { return JMB_ABI_VERSION; }
 
@@ -234,7 +272,9 @@ int jmb_pic_begin(jmb_ctx *ctx, const uint16_t *cur, int width, int height, int 
   int rc = to_device(ctx, cur, (size_t)stride * height * sizeof(uint16_t), loc, &d_src, &ctx->d_stage, &ctx->d_stage_cap);
   if (rc) return rc;
   dim3 grid((width / 4 + 127) / 128, height);
+  jmb_time_begin(ctx, JMB_K_PACK);
   k_pack_cur<<<grid, 128, 0, ctx->stream>>>((const uint16_t *)d_src, stride, width, height, ctx->cur, pitch);
+  jmb_time_end(ctx, JMB_K_PACK);
   JMB_LAUNCH_CHECK(ctx);
   if (loc == JMB_HOST) JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return JMB_OK;

@@ -36,6 +36,10 @@ struct jmb_ctx {
   void *d_stage2 = nullptr; size_t d_stage2_cap = 0;
   void *d_groups = nullptr; size_t d_groups_cap = 0;
   void *h_groups = nullptr; size_t h_groups_cap = 0;
+  // per-kernel event timing
+  bool timing = false;
+  struct EvPair { cudaEvent_t a, b; };
+  EvPair *ev[16] = {nullptr}; int ev_n[16] = {0}; int ev_cap[16] = {0};
   void *d_reftab = nullptr; size_t d_reftab_cap = 0;
   void *d_qdesc = nullptr; size_t d_qdesc_cap = 0;
   void *d_stage3 = nullptr; size_t d_stage3_cap = 0;
@@ -60,6 +64,12 @@ int jmb_reserve_dev(jmb_ctx *ctx, void **p, size_t *cap, size_t bytes);
     (ctx)->launches++;                                                                          \
     JMB_CUDA((ctx), cudaGetLastError());                                                        \
   } while (0)
+
+// kernel classes for the optional per-kernel CUDA-event timing (jmb_timing_enable / jmb_timing_get)
+enum { JMB_K_SUBPEL = 0, JMB_K_PACK, JMB_K_INT_SEARCH, JMB_K_REFINE, JMB_K_DIST, JMB_K_FFS_SURF, JMB_K_FORWARD,
+       JMB_K_QUANT, JMB_K_MC_TQ, JMB_K_PRED, JMB_K_COUNT };
+void jmb_time_begin(jmb_ctx *ctx, int kid);
+void jmb_time_end(jmb_ctx *ctx, int kid);
 
 // ---- device helpers shared by the kernels -----------------------------------------------------
 __device__ __forceinline__ int jmb_clip(int lo, int hi, int v) { return min(max(v, lo), hi); }

@@ -172,8 +172,10 @@ __global__ void k_dist(const uint8_t *__restrict__ cur, int cur_pitch, RefView r
 
 int jmb_launch_refine(jmb_ctx *ctx, const jmb_me_req *d_reqs, jmb_me_res *d_res, int n, const uint8_t *const *d_ref_planes) {
   const jmb_ref &r0 = ctx->refs[ctx->ref_list[0]];
+  jmb_time_begin(ctx, JMB_K_REFINE);
   k_subpel_refine<<<(n + 7) / 8, 256, 0, ctx->stream>>>(d_reqs, d_res, n, ctx->cur, ctx->cur_pitch, d_ref_planes, r0.plane_bytes,
                                                         r0.pitch, ctx->cur_w, ctx->cur_h, ctx->me);
+  jmb_time_end(ctx, JMB_K_REFINE);
   JMB_LAUNCH_CHECK(ctx);
   return JMB_OK;
 }
@@ -200,7 +202,9 @@ extern "C" int jmb_dist(jmb_ctx *ctx, int ref, int metric, int blocktype, int po
   const int nn = (metric == JMB_SATD && test8x8) ? 8 : 4;
   const int items = n * (bsx[blocktype] / nn) * (bsy[blocktype] / nn);
   RefView rv{r.planes, r.plane_bytes, r.pitch, r.w, r.h};
+  jmb_time_begin(ctx, JMB_K_DIST);
   k_dist<<<(items + 127) / 128, 128, 0, ctx->stream>>>(ctx->cur, ctx->cur_pitch, rv, blocktype, pos_x, pos_y, d_c, n, metric, test8x8, d_o);
+  jmb_time_end(ctx, JMB_K_DIST);
   JMB_LAUNCH_CHECK(ctx);
   if (loc == JMB_HOST) {
     JMB_CUDA(ctx, cudaMemcpyAsync(out, d_o, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));

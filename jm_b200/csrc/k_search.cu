@@ -399,8 +399,10 @@ static int me_search_impl(jmb_ctx *ctx, const jmb_me_req *reqs, int n, jmb_me_re
     JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage, reqs, (size_t)n * sizeof(jmb_me_req), cudaMemcpyHostToDevice, ctx->stream));
     d_reqs = (const jmb_me_req *)ctx->d_stage; d_res = (jmb_me_res *)ctx->d_stage2;
   }
+  jmb_time_begin(ctx, JMB_K_INT_SEARCH);
   k_int_search<<<n_groups, 256, 0, ctx->stream>>>(d_reqs, d_groups, d_res, ctx->cur, ctx->cur_pitch, d_tab, r0.pitch,
                                                   ctx->cur_w, ctx->cur_h, ctx->me.search_range, ctx->me.max_mvd - 1);
+  jmb_time_end(ctx, JMB_K_INT_SEARCH);
   JMB_LAUNCH_CHECK(ctx);
   if (any_subpel) { rc = jmb_launch_refine(ctx, d_reqs, d_res, n, d_tab); if (rc) return rc; }
   if (loc == JMB_HOST) {
@@ -433,8 +435,10 @@ int jmb_ffs_surfaces(jmb_ctx *ctx, int ref, int mb_x, int mb_y, int center_x, in
     int rc = jmb_reserve_dev(ctx, &ctx->d_stage2, &ctx->d_stage2_cap, bytes); if (rc) return rc;
     d_out = (uint32_t *)ctx->d_stage2;
   }
+  jmb_time_begin(ctx, JMB_K_FFS_SURF);
   k_ffs_surfaces<<<(max_pos + 127) / 128, 128, 0, ctx->stream>>>(ctx->cur, ctx->cur_pitch, r.planes, r.pitch, r.w, r.h, mb_x, mb_y,
                                                                  center_x >> 2, center_y >> 2, R, d_out);
+  jmb_time_end(ctx, JMB_K_FFS_SURF);
   JMB_LAUNCH_CHECK(ctx);
   if (loc == JMB_HOST) {
     JMB_CUDA(ctx, cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, ctx->stream));

@@ -87,7 +87,9 @@ k_subpel_planes(const uint16_t *__restrict__ src, int src_stride, int w, int h, 
 
 int jmb_launch_subpel(jmb_ctx *ctx, const uint16_t *d_src, int src_stride, jmb_ref *r) {
   dim3 grid((r->W + TW - 1) / TW, (r->H + TH - 1) / TH);
+  jmb_time_begin(ctx, JMB_K_SUBPEL);
   k_subpel_planes<<<grid, 256, 0, ctx->stream>>>(d_src, src_stride, r->w, r->h, r->W, r->H, r->planes, r->pitch, r->plane_bytes);
+  jmb_time_end(ctx, JMB_K_SUBPEL);
   JMB_LAUNCH_CHECK(ctx);
   return JMB_OK;
 }

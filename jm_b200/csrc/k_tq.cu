@@ -170,6 +170,19 @@ __global__ void k_mc_tq(const jmb_mb_pred *__restrict__ pred, int n_mb, int mb_w
   }
 }
 
+// all_mv fill of BlockMotionSearch (lencod/src/mv_search.c:1005-1014) for one partition mode of every
+// macroblock: the mv of each partition is replicated over the 4x4 blocks it covers.
+__global__ void k_pred_from_results(const jmb_me_res *__restrict__ res, int n_mb, int mode, jmb_mb_pred *__restrict__ pred) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_mb * 16) return;
+  const int mb = t >> 4, b = t & 15, bx4 = b & 3, by4 = b >> 2;
+  const int base[8] = {0, 0, 1, 3, 5, 9, 17, 25}, w4[8] = {4, 4, 4, 2, 2, 2, 1, 1}, h4[8] = {4, 4, 2, 4, 2, 1, 2, 1};
+  const int slot = base[mode] + (by4 / h4[mode]) * (4 / w4[mode]) + bx4 / w4[mode];
+  const jmb_me_res r = res[mb * 41 + slot];
+  pred[mb].mv[b][0] = r.mv_x; pred[mb].mv[b][1] = r.mv_y;
+  if (b < 4) { pred[mb].b8mode[b] = (uint8_t)mode; pred[mb].ref[b] = 0; }
+}
+
 }  // namespace
 
 static int check_qdesc(jmb_ctx *ctx, const jmb_quant_desc *q) {
@@ -200,8 +213,10 @@ int jmb_forward_transform(jmb_ctx *ctx, int32_t *blocks, int nblk, int n, int lo
     JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage, blocks, bytes, cudaMemcpyHostToDevice, ctx->stream));
     d = (int *)ctx->d_stage;
   }
+  jmb_time_begin(ctx, JMB_K_FORWARD);
   if (n == 4) k_forward<4><<<(nblk + 127) / 128, 128, 0, ctx->stream>>>(d, nblk);
   else k_forward<8><<<(nblk + 63) / 64, 64, 0, ctx->stream>>>(d, nblk);
+  jmb_time_end(ctx, JMB_K_FORWARD);
   JMB_LAUNCH_CHECK(ctx);
   if (loc == JMB_HOST) {
     JMB_CUDA(ctx, cudaMemcpyAsync(blocks, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -230,8 +245,10 @@ int jmb_quant_blocks(jmb_ctx *ctx, const jmb_quant_desc *q, int do_transform, in
     JMB_CUDA(ctx, cudaMemcpyAsync(d_cc, coeff_cost, (size_t)nblk * 4, cudaMemcpyHostToDevice, ctx->stream));
     JMB_CUDA(ctx, cudaMemsetAsync(d_lv, 0, (size_t)nblk * lr * 2 * 4, ctx->stream));
   }
+  jmb_time_begin(ctx, JMB_K_QUANT);
   if (q->n == 4) k_quant_blocks<4><<<(nblk + 127) / 128, 128, 0, ctx->stream>>>(d_q, do_transform, d_coef, nblk, lr, d_lv, d_rn, d_fa, d_cc, d_nz);
   else k_quant_blocks<8><<<(nblk + 63) / 64, 64, 0, ctx->stream>>>(d_q, do_transform, d_coef, nblk, lr, d_lv, d_rn, d_fa, d_cc, d_nz);
+  jmb_time_end(ctx, JMB_K_QUANT);
   JMB_LAUNCH_CHECK(ctx);
   if (loc == JMB_HOST) {
     JMB_CUDA(ctx, cudaMemcpyAsync(coef, d_coef, (size_t)nblk * nn * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -240,6 +257,27 @@ int jmb_quant_blocks(jmb_ctx *ctx, const jmb_quant_desc *q, int do_transform, in
     if (fadjust && q->around) JMB_CUDA(ctx, cudaMemcpyAsync(fadjust, d_fa, (size_t)nblk * nn * 4, cudaMemcpyDeviceToHost, ctx->stream));
     JMB_CUDA(ctx, cudaMemcpyAsync(coeff_cost, d_cc, (size_t)nblk * 4, cudaMemcpyDeviceToHost, ctx->stream));
     JMB_CUDA(ctx, cudaMemcpyAsync(nonzero, d_nz, (size_t)nblk * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return JMB_OK;
+}
+
+int jmb_pred_from_results(jmb_ctx *ctx, const jmb_me_res *res, int n_mb, int mode, jmb_mb_pred *pred, int loc) {
+  if (mode < 1 || mode > 7 || n_mb <= 0) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_pred_from_results: mode %d n_mb %d", mode, n_mb);
+  JMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const jmb_me_res *d_res = res; jmb_mb_pred *d_pred = pred;
+  if (loc == JMB_HOST) {
+    int rc = jmb_reserve_dev(ctx, &ctx->d_stage4, &ctx->d_stage4_cap, (size_t)n_mb * 41 * sizeof(jmb_me_res)); if (rc) return rc;
+    rc = jmb_reserve_dev(ctx, &ctx->d_stage5, &ctx->d_stage5_cap, (size_t)n_mb * sizeof(jmb_mb_pred)); if (rc) return rc;
+    JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage4, res, (size_t)n_mb * 41 * sizeof(jmb_me_res), cudaMemcpyHostToDevice, ctx->stream));
+    d_res = (const jmb_me_res *)ctx->d_stage4; d_pred = (jmb_mb_pred *)ctx->d_stage5;
+  }
+  jmb_time_begin(ctx, JMB_K_PRED);
+  k_pred_from_results<<<(n_mb * 16 + 255) / 256, 256, 0, ctx->stream>>>(d_res, n_mb, mode, d_pred);
+  jmb_time_end(ctx, JMB_K_PRED);
+  JMB_LAUNCH_CHECK(ctx);
+  if (loc == JMB_HOST) {
+    JMB_CUDA(ctx, cudaMemcpyAsync(pred, d_pred, (size_t)n_mb * sizeof(jmb_mb_pred), cudaMemcpyDeviceToHost, ctx->stream));
     JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return JMB_OK;
@@ -272,10 +310,12 @@ int jmb_mc_tq(jmb_ctx *ctx, const jmb_mb_pred *pred, int n_mb, const jmb_quant_d
   }
   JMB_CUDA(ctx, cudaMemsetAsync(d_cc, 0, (size_t)n_mb * 16, ctx->stream));
   JMB_CUDA(ctx, cudaMemsetAsync(d_cbp, 0, (size_t)n_mb * 4, ctx->stream));
+  jmb_time_begin(ctx, JMB_K_MC_TQ);
   if (q->n == 4) k_mc_tq<4><<<(n_mb * 16 + 127) / 128, 128, 0, ctx->stream>>>(d_pred, n_mb, mb_w, d_q, ctx->cur, ctx->cur_pitch,
         (const uint8_t *const *)ctx->d_reftab, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_cc, d_cbp);
   else k_mc_tq<8><<<(n_mb * 4 + 63) / 64, 64, 0, ctx->stream>>>(d_pred, n_mb, mb_w, d_q, ctx->cur, ctx->cur_pitch,
         (const uint8_t *const *)ctx->d_reftab, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_cc, d_cbp);
+  jmb_time_end(ctx, JMB_K_MC_TQ);
   JMB_LAUNCH_CHECK(ctx);
   if (loc == JMB_HOST) {
     JMB_CUDA(ctx, cudaMemcpyAsync(levels, d_lv, (size_t)n_mb * 512, cudaMemcpyDeviceToHost, ctx->stream));

@@ -271,3 +271,22 @@ class JMRef:
 
     def quant(self, variant, coef, qp, qparams, scan, c_cost, is_cavlc, arw=0, cost0=0):
         return _quant_call(self.L.jmref_quant, self.h_, variant, coef, qp, qparams, scan, c_cost, is_cavlc, arw, cost0)
+
+
+def jmref_run_mbs(ref, mb_xy, preds, lam3, qp, qparams, scan, c_cost, do_tq=True, want_levels=True):
+    """CPU baseline leg: JM's own functions on the GPU step's per-macroblock work (see ref_harness.c)."""
+    L = ref.L
+    L.jmref_run_mbs.argtypes = [C.c_void_p, C.c_int, _i16p, _i16p, _i32p, C.c_int, _i32p, _u8p, _u8p, C.c_int,
+                                _i16p, np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS"), C.c_void_p,
+                                np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")]
+    mb_xy = np.ascontiguousarray(mb_xy, np.int16).reshape(-1, 2)
+    n = len(mb_xy)
+    preds = np.ascontiguousarray(preds, np.int16).reshape(n, 41, 2)
+    mv = np.zeros((n, 41, 2), np.int16); cost = np.zeros((n, 41), np.int64)
+    lev = np.zeros((n, 7, 256), np.int16) if (do_tq and want_levels) else None
+    secs = np.zeros(2)
+    L.jmref_run_mbs(ref.h_, n, mb_xy, preds, np.asarray(lam3, np.int32), qp,
+                    np.ascontiguousarray(qparams, np.int32).reshape(-1), np.ascontiguousarray(scan, np.uint8).reshape(-1),
+                    np.ascontiguousarray(c_cost, np.uint8), int(do_tq), mv, cost,
+                    lev.ctypes.data if lev is not None else None, secs)
+    return mv, cost, lev, secs

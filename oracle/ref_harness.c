@@ -355,3 +355,83 @@ int jmref_quant(void *h, int variant, int *coef, int qp, const int *qparams, con
     default: return quant_8x8_around(c->mb, rows, &q);
   }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * CPU baseline leg of bench.py: the same per-macroblock work the GPU step does, executed by JM's own
+ * functions: 41 x (full_search_motion_estimation + sub_pel_motion_estimation) and, for each of the 7
+ * partition modes, prediction (UMVLine4X copy, as OneComponentLumaPrediction mc_prediction.c:117) ->
+ * residual -> forward4x4 -> quant_4x4_normal for the 16 luma blocks.
+ *   preds  [n_mb][41][2] predictors (qpel), canonical partition order (include/jmb200.h)
+ *   out_mv [n_mb][41][2], out_cost [n_mb][41], out_levels [n_mb][7][256] (scan order per 4x4 block)
+ *   secs[0] = motion-estimation seconds, secs[1] = transform/quant seconds
+ * ---------------------------------------------------------------------------------------------- */
+#include <time.h>
+static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+
+static const unsigned char k_pt[41][3] = { /* type, x, y */
+  {1,0,0},{2,0,0},{2,0,8},{3,0,0},{3,8,0},{4,0,0},{4,8,0},{4,0,8},{4,8,8},
+  {5,0,0},{5,8,0},{5,0,4},{5,8,4},{5,0,8},{5,8,8},{5,0,12},{5,8,12},
+  {6,0,0},{6,4,0},{6,8,0},{6,12,0},{6,0,8},{6,4,8},{6,8,8},{6,12,8},
+  {7,0,0},{7,4,0},{7,8,0},{7,12,0},{7,0,4},{7,4,4},{7,8,4},{7,12,4},{7,0,8},{7,4,8},{7,8,8},{7,12,8},{7,0,12},{7,4,12},{7,8,12},{7,12,12}};
+static const int k_base[8] = {0, 0, 1, 3, 5, 9, 17, 25};
+
+void jmref_run_mbs(void *h, int n_mb, const int16_t *mb_xy, const int16_t *preds, const int *lambda3, int qp,
+                   const int *qparams, const uint8_t *scan, const uint8_t *c_cost, int do_tq,
+                   int16_t *out_mv, int64_t *out_cost, int16_t *out_levels, double *secs)
+{
+  jmref_ctx *c = (jmref_ctx *)h; g_ctx = c;
+  int lam[3] = { lambda3[0], lambda3[1], lambda3[2] };
+  double t_me = 0, t_tq = 0;
+  for (int m = 0; m < n_mb; m++) {
+    int mbx = mb_xy[2 * m], mby = mb_xy[2 * m + 1];
+    double t0 = now_s();
+    for (int p = 0; p < 41; p++) {
+      MEBlock b; MotionVector pred;
+      fill_mv_block(c, &b, k_pt[p][0], mbx + k_pt[p][1], mby + k_pt[p][2], 0);
+      pred.mv_x = preds[(m * 41 + p) * 2]; pred.mv_y = preds[(m * 41 + p) * 2 + 1];
+      b.mv[0].mv_x = (short)(((pred.mv_x + 2) >> 2) * 4);          /* mv_search.c:931-932 */
+      b.mv[0].mv_y = (short)(((pred.mv_y + 2) >> 2) * 4);
+      distblk mc = full_search_motion_estimation(c->mb, &pred, &b, DISTBLK_MAX, lam[F_PEL]);
+      if (!c->p_Vid->start_me_refinement_hp) mc = DISTBLK_MAX;      /* mv_search.c:971-974 */
+      mc = sub_pel_motion_estimation(c->mb, &pred, &b, mc, lam);
+      out_mv[(m * 41 + p) * 2] = b.mv[0].mv_x; out_mv[(m * 41 + p) * 2 + 1] = b.mv[0].mv_y;
+      out_cost[m * 41 + p] = (int64_t)mc;
+      free_mem2Dpel(b.orig_pic);
+    }
+    double t1 = now_s();
+    t_me += t1 - t0;
+    if (do_tq) {
+      static const int w4[8] = {4, 4, 4, 2, 2, 2, 1, 1}, h4[8] = {4, 4, 2, 4, 2, 1, 2, 1};
+      for (int mode = 1; mode <= 7; mode++)
+        for (int blk = 0; blk < 16; blk++) {
+          int bx4 = blk & 3, by4 = blk >> 2;
+          int ux4 = bx4, uy4 = by4;
+          if (mode < 5) { ux4 &= ~1; uy4 &= ~1; }                  /* macroblock.c:946-971 */
+          int slot = k_base[mode] + (uy4 / h4[mode]) * (4 / w4[mode]) + ux4 / w4[mode];
+          int mvx = out_mv[(m * 41 + slot) * 2], mvy = out_mv[(m * 41 + slot) * 2 + 1];
+          imgpel *rl = UMVLine4X(c->ref, ((mby + uy4 * 4) << 2) + mvy, ((mbx + ux4 * 4) << 2) + mvx);
+          rl += (by4 - uy4) * 4 * c->p_Vid->padded_size_x + (bx4 - ux4) * 4;
+          int blk16[16], *rows[4], lev[17], run[17], cost = 0;
+          LevelQuantParams qs[16], *qrows[4];
+          for (int y = 0; y < 4; y++) {
+            rows[y] = blk16 + 4 * y; qrows[y] = qs + 4 * y;
+            for (int x = 0; x < 4; x++)
+              blk16[4 * y + x] = (int)c->cur[mby + by4 * 4 + y][mbx + bx4 * 4 + x] - (int)rl[y * c->p_Vid->padded_size_x + x];
+          }
+          for (int i = 0; i < 16; i++) { qs[i].OffsetComp = qparams[3 * i]; qs[i].ScaleComp = qparams[3 * i + 1]; qs[i].InvScaleComp = qparams[3 * i + 2]; }
+          forward4x4(rows, rows, 0, 0);
+          QuantMethods q; memset(&q, 0, sizeof(q));
+          q.qp = qp; q.ACLevel = lev; q.ACRun = run; q.q_params = qrows; q.coeff_cost = &cost;
+          q.pos_scan = (const byte (*)[2])scan; q.c_cost = c_cost;
+          quant_4x4_normal(c->mb, rows, &q);
+          if (out_levels) {
+            int16_t *o = out_levels + ((size_t)(m * 7 + mode - 1) * 16 + blk) * 16;
+            memset(o, 0, 32);
+            for (int i = 0, k = 0; lev[i]; i++) { k += run[i]; o[k++] = (int16_t)lev[i]; }
+          }
+        }
+      t_tq += now_s() - t1;
+    }
+  }
+  secs[0] = t_me; secs[1] = t_tq;
+}
