@@ -23,10 +23,12 @@
 namespace {
 
 constexpr int NPART = 41;
+constexpr int NT = 192;            // threads per CTA
 constexpr int CW = 128;            // chunk of displacements handled per staging pass
-constexpr int CH = 72;
-constexpr int WIN_PITCH = CW + 16 + 4;
+constexpr int CH = 72;             // multiple of 4 (a thread owns 4 vertically adjacent displacements)
+constexpr int WIN_PITCH = 152;     // bytes: <=3 alignment + CW + 15, rounded up to a word, + the fifth word
 constexpr int WIN_ROWS = CH + 15;
+constexpr int S1_COLS = 10, S1_RGS = 3, S1_ITEMS = S1_COLS * S1_RGS, S1_PITCH = 43;   // stage-1 neighbourhood
 constexpr int IDX_BITS = 13;       // (2*64+1)^2 = 16641 > 8192: search_range <= 45 keeps idx < 8192
 
 struct PartGeom { unsigned char type, bx, by, w4, h4; };
@@ -52,15 +54,39 @@ struct ReqS {
   unsigned long long init; // min_mcost << IDX_BITS
 };
 
+// everything the slow path needs, in shared memory
+struct Grp {
+  ReqS rq[NPART];
+  unsigned long long best[NPART];      // (cost << IDX_BITS) | spiral index of the current winner
+  __align__(16) unsigned thr[NPART + 3];   // gate: a SAD can only win if sad < thr (see bound_of)
+  __align__(16) int4 inner[NPART];     // displacements that stand for exactly one candidate: x0, x1, y0, y1 (inclusive)
+  int R, max_mvd_m1;
+};
+
+// Largest SAD that can still win against the key `k`: a winner needs (sad << 5) + lambda * bits <= cost(k),
+// and every candidate pays at least 2 bits (mvbits >= 1 per component).  The gate is sad < bound.
+__device__ __forceinline__ unsigned bound_of(unsigned long long k, int lam) {
+  const unsigned long long cost = k >> IDX_BITS, floor_ = 2ull * (unsigned)lam;
+  if (cost < floor_) return 0u;
+  return (unsigned)min(((cost - floor_) >> 5) + 1, 0xffffffffull);
+}
+
 __device__ __forceinline__ unsigned sad4(unsigned a, unsigned b, unsigned c) {
   unsigned d;
   asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
 }
 
-// all candidates d that clamp onto displacement (Dx,Dy); rare (picture borders only)
-__device__ __noinline__ void eval_border(const ReqS *q, unsigned sad, int Dx, int Dy, int R, int max_mvd_m1,
-                                         unsigned long long *best) {
+__device__ __forceinline__ void publish(Grp *g, int p, unsigned long long k) {
+  if (k < atomicMin(&g->best[p], k)) atomicMin(&g->thr[p], bound_of(k, g->rq[p].lam));
+}
+
+// Exact cost evaluation of the candidates that read the block(s) at displacement (Dx,Dy).  Reached only
+// when the SAD passed the gate (rare), so it is kept out of line.  Interior displacements stand for
+// exactly one candidate; a displacement ON the clamp boundary stands for every candidate beyond it.
+__device__ __noinline__ void eval_slow(Grp *g, int p, unsigned sad, int Dx, int Dy) {
+  const ReqS *q = &g->rq[p];
+  const int R = g->R, max_mvd_m1 = g->max_mvd_m1;
   if (Dx < q->dlo_x || Dx > q->dhi_x || Dy < q->dlo_y || Dy > q->dhi_y) return;
   int x0 = Dx, x1 = Dx, y0 = Dy, y1 = Dy;
   if (Dx == q->dlo_x) x0 = q->cx - R;     // every d <= Dlo clamps to Dlo
@@ -77,26 +103,22 @@ __device__ __noinline__ void eval_border(const ReqS *q, unsigned sad, int Dx, in
       unsigned long long cost = ((unsigned long long)sad << 5) + (unsigned long long)((long long)q->lam * (jmb_mvbits(mx) + jmb_mvbits(my)));
       k = min(k, (cost << IDX_BITS) | (unsigned)jmb_spiral_index(dx - q->cx, dy - q->cy));
     }
-  if (k < *best) atomicMin(best, k);
+  if (k < *(volatile unsigned long long *)&g->best[p]) publish(g, p, k);
 }
 
-__device__ __forceinline__ void eval(const ReqS *q, unsigned sad, int Dx, int Dy, int R, int max_mvd_m1,
-                                     unsigned long long *best) {
-  if (!q->active) return;
-  unsigned long long cur = *(volatile unsigned long long *)best;
-  if (((unsigned long long)sad << (5 + IDX_BITS)) > cur) return;     // cost >= SAD<<5 cannot win
-  int ex = Dx - q->cx, ey = Dy - q->cy;
-  bool interior = Dx > q->dlo_x && Dx < q->dhi_x && Dy > q->dlo_y && Dy < q->dhi_y;
-  if (interior) {
-    if (abs(ex) > R || abs(ey) > R) return;
-    int mx = 4 * Dx - q->px, my = 4 * Dy - q->py;
-    if (q->ffs && max(abs(mx), abs(my)) >= max_mvd_m1) return;
-    unsigned long long cost = ((unsigned long long)sad << 5) + (unsigned long long)((long long)q->lam * (jmb_mvbits(mx) + jmb_mvbits(my)));
-    unsigned long long k = (cost << IDX_BITS) | (unsigned)jmb_spiral_index(ex, ey);
-    if (k < cur) atomicMin(best, k);
-  } else {
-    eval_border(q, sad, Dx, Dy, R, max_mvd_m1, best);
-  }
+// A SAD passed the gate: exact cost of the one candidate an interior displacement stands for; everything on a
+// clamp boundary or outside the partition's own window goes to eval_slow.
+__device__ __noinline__ void level2(Grp *g, int p, unsigned sad, int Dx, int Dy) {
+  const int4 in = g->inner[p];
+  if (Dx < in.x || Dx > in.y || Dy < in.z || Dy > in.w) { eval_slow(g, p, sad, Dx, Dy); return; }
+  const ReqS *q = &g->rq[p];
+  const int mx = 4 * Dx - q->px, my = 4 * Dy - q->py;
+  if (q->ffs && max(abs(mx), abs(my)) >= g->max_mvd_m1) return;
+  const unsigned long long cost = ((unsigned long long)sad << 5) + (unsigned long long)((long long)q->lam * (jmb_mvbits(mx) + jmb_mvbits(my)));
+  const unsigned long long cur = *(volatile unsigned long long *)&g->best[p];
+  if (cost > (cur >> IDX_BITS)) return;
+  const unsigned long long k = (cost << IDX_BITS) | (unsigned)jmb_spiral_index(Dx - q->cx, Dy - q->cy);
+  if (k < cur) publish(g, p, k);
 }
 
 // inverse of jmb_spiral_index
@@ -110,16 +132,81 @@ __device__ void spiral_xy(int idx, int *dx, int *dy) {
   else { off -= 2 * (2 * l - 1); *dy = (off >> 1) - l; *dx = (off & 1) ? l : -l; }
 }
 
+// the 41 partition SADs of one displacement from its sixteen 4x4 SADs (update_full_search_large_blocks,
+// lencod/src/me_fullfast.c:207-259), handed to F(partition, sad) in canonical order
+template <typename F>
+__device__ __forceinline__ void for_each_partition(const unsigned *a, F &&f) {
+  unsigned s6[8], s5[8], s4[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) { s6[i] = a[i] + a[4 + i]; s6[4 + i] = a[8 + i] + a[12 + i]; }
+#pragma unroll
+  for (int i = 0; i < 8; i++) s5[i] = a[2 * i] + a[2 * i + 1];
+  s4[0] = s6[0] + s6[1]; s4[1] = s6[2] + s6[3]; s4[2] = s6[4] + s6[5]; s4[3] = s6[6] + s6[7];
+  const unsigned s3a = s4[0] + s4[2], s3b = s4[1] + s4[3], s2a = s4[0] + s4[1], s2b = s4[2] + s4[3];
+  f(0, s2a + s2b);
+  f(1, s2a); f(2, s2b);
+  f(3, s3a); f(4, s3b);
+#pragma unroll
+  for (int i = 0; i < 4; i++) f(5 + i, s4[i]);
+#pragma unroll
+  for (int i = 0; i < 8; i++) f(9 + i, s5[i]);      // 8x4: (bx 0|2, by 0..3) raster = pairs (2i, 2i+1)
+#pragma unroll
+  for (int i = 0; i < 8; i++) f(17 + i, s6[i]);     // 4x8: (bx 0..3, by 0|2)
+#pragma unroll
+  for (int i = 0; i < 16; i++) f(25 + i, a[i]);
+}
+
+// Sixty-four 4x4 SADs of one thread item: window column xo (bytes from the staged row start), displacement
+// rows row0 .. row0+3.  Window row row0+wr is byte-aligned once (4 PRMT) and meets source row wr-dy for each dy.
+__device__ __forceinline__ void sad_item(const uint8_t *win, const unsigned *ssrc, int row0, int xo, unsigned (&acc)[4][16]) {
+  const unsigned sel = 0x3210u + 0x1111u * (xo & 3);
+  const unsigned *wrow = (const unsigned *)(win + row0 * WIN_PITCH + (xo & ~3));
+#pragma unroll
+  for (int s = 0; s < 4; s++)
+#pragma unroll
+    for (int b = 0; b < 16; b++) acc[s][b] = 0;
+  unsigned srow[4][4];
+#pragma unroll
+  for (int wr = 0; wr < 19; wr++) {
+    if (wr < 16) {
+      const uint4 v = *(const uint4 *)&ssrc[wr * 4];
+      srow[wr & 3][0] = v.x; srow[wr & 3][1] = v.y; srow[wr & 3][2] = v.z; srow[wr & 3][3] = v.w;
+    }
+    const unsigned *wp = wrow + wr * (WIN_PITCH / 4);
+    const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
+    unsigned al[4];
+    al[0] = __byte_perm(w0, w1, sel); al[1] = __byte_perm(w1, w2, sel);
+    al[2] = __byte_perm(w2, w3, sel); al[3] = __byte_perm(w3, w4, sel);
+#pragma unroll
+    for (int dy = 0; dy < 4; dy++) {
+      const int r = wr - dy;                 // source row matched with this window row at displacement row0+dy
+      if (r >= 0 && r < 16) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[dy][(r >> 2) * 4 + c] = sad4(al[c], srow[r & 3][c], acc[dy][(r >> 2) * 4 + c]);
+      }
+    }
+  }
+}
+
 // groups == nullptr: frame layout, group g = requests [41g, 41g+41) in canonical partition order.
-__global__ void __launch_bounds__(256)
+//
+// Work decomposition: a thread owns ONE column of displacements and FOUR vertically adjacent rows, so the
+// byte alignment (PRMT) of a window row is done once and feeds four displacements; its sixty-four 4x4 SADs
+// live in registers.  Winners are tracked per partition in shared memory; a thread only leaves the
+// arithmetic loop when one of its SADs beats the current bound (sad < thr), which after the seeding step
+// below is rare.  ALU-pipe work per displacement: 64 VABSDIFF4 + 19 PRMT + 41 ISETP.
+#ifndef JMB_IS_MINB
+#define JMB_IS_MINB 2
+#endif
+__global__ void __launch_bounds__(NT, JMB_IS_MINB)
 k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups, jmb_me_res *__restrict__ res,
              const uint8_t *__restrict__ cur, int cur_pitch,
              const uint8_t *const *__restrict__ ref_planes, int ref_pitch, int w, int h, int R, int max_mvd_m1) {
-  __shared__ ReqS rq[NPART];
-  __shared__ unsigned long long best[NPART];
+  __shared__ Grp G;
   __shared__ __align__(16) uint8_t win[WIN_ROWS * WIN_PITCH];
-  __shared__ unsigned ssrc[16 * 4];
-  __shared__ int sbox[8];
+  __shared__ __align__(16) unsigned ssrc[16 * 4];
+  __shared__ int sbox[10];
+  __shared__ unsigned short S1[S1_ITEMS * 4 * S1_PITCH];
 
   const int tid = threadIdx.x, g = blockIdx.x;
   const int W = w + 2 * JMB_PAD_X, H = h + 2 * JMB_PAD_Y;
@@ -140,18 +227,25 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
         q.init = (unsigned long long)r.min_mcost << IDX_BITS;
       }
     }
-    rq[tid] = q;
-    best[tid] = q.active ? q.init : 0ull;
+    G.rq[tid] = q;
+    G.best[tid] = q.active ? q.init : 0ull;
+    G.thr[tid] = q.active ? bound_of(q.init, q.lam) : 0u;
+    int4 in = make_int4(1, 0, 1, 0);
+    if (q.active) in = make_int4(max(q.dlo_x + 1, q.cx - R), min(q.dhi_x - 1, q.cx + R), max(q.dlo_y + 1, q.cy - R), min(q.dhi_y - 1, q.cy + R));
+    G.inner[tid] = in;
   }
+  if (tid == 0) { G.R = R; G.max_mvd_m1 = max_mvd_m1; G.thr[NPART] = G.thr[NPART + 1] = G.thr[NPART + 2] = 0; }
   __syncthreads();
   if (tid == 0) {
     int x0 = 1 << 30, x1 = -(1 << 30), y0 = 1 << 30, y1 = -(1 << 30), mbx = 0, mby = 0, rf = 0, any = 0;
-    for (int p = 0; p < NPART; p++) if (rq[p].active) {
-      const ReqS &q = rq[p];
+    for (int p = 0; p < NPART; p++) if (G.rq[p].active) {
+      const ReqS &q = G.rq[p];
       x0 = min(x0, jmb_clip(q.dlo_x, q.dhi_x, q.cx - R)); x1 = max(x1, jmb_clip(q.dlo_x, q.dhi_x, q.cx + R));
       y0 = min(y0, jmb_clip(q.dlo_y, q.dhi_y, q.cy - R)); y1 = max(y1, jmb_clip(q.dlo_y, q.dhi_y, q.cy + R));
       jmb_me_req r = reqs[q.req];
-      mbx = r.pos_x & ~15; mby = r.pos_y & ~15; rf = r.ref; any = 1;
+      mbx = r.pos_x & ~15; mby = r.pos_y & ~15; rf = r.ref;
+      if (!any) { sbox[8] = q.cx; sbox[9] = q.cy; }
+      any = 1;
     }
     sbox[0] = x0; sbox[1] = x1; sbox[2] = y0; sbox[3] = y1; sbox[4] = mbx; sbox[5] = mby; sbox[6] = rf; sbox[7] = any;
   }
@@ -165,85 +259,111 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
     ssrc[tid] = *(const unsigned *)(cur + (size_t)(mby + r) * cur_pitch + mbx + 4 * c);
   }
 
+  bool seeded = false;
   for (int cy0 = by0; cy0 <= by1; cy0 += CH) {
     const int ch = min(CH, by1 - cy0 + 1);
     for (int cx0 = bx0; cx0 <= bx1; cx0 += CW) {
       const int cw = min(CW, bx1 - cx0 + 1);
       __syncthreads();
-      // stage the window: rows cy0 .. cy0+ch+14, columns cx0 .. cx0+cw+14 (+3), relative to the MB origin;
-      // coordinates outside the padded plane are clamped (such samples are never used by a valid candidate)
-      const int wcols = ((cw + 3) & ~3) + 16, wrows = ch + 15;
-      for (int i = tid; i < wrows * (wcols >> 2); i += 256) {
-        int r = i / (wcols >> 2), c4 = (i - r * (wcols >> 2)) * 4;
-        int py = jmb_clip(0, H - 1, mby + cy0 + r + JMB_PAD_Y);
-        unsigned v = 0;
+      // stage the window with its left edge aligned down to a 4-sample boundary of the plane: staged byte
+      // (r, c) = plane sample (mby + cy0 + r + PAD_Y, sx0 + c).  Rows 0 .. ch+14; samples outside the padded
+      // plane are clamped (no valid candidate reads them).
+      const int ax = mbx + cx0 + JMB_PAD_X, sx0 = ax & ~3, xoff0 = ax - sx0;
+      const int nwords = ((xoff0 + cw + 15) >> 2) + 1, wrows = ch + 15;
+      for (int i = tid; i < wrows * nwords; i += NT) {
+        const int r = i / nwords, wi = i - r * nwords;
+        const int py = jmb_clip(0, H - 1, mby + cy0 + r + JMB_PAD_Y), px = sx0 + 4 * wi;
+        const uint8_t *rowp = ref + (size_t)py * ref_pitch;
+        unsigned v;
+        if (px >= 0 && px + 3 < W) v = __ldg((const unsigned *)(rowp + px));
+        else {
+          v = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          int px = jmb_clip(0, W - 1, mbx + cx0 + c4 + k + JMB_PAD_X);
-          v |= (unsigned)ref[(size_t)py * ref_pitch + px] << (8 * k);
+          for (int k = 0; k < 4; k++) v |= (unsigned)rowp[jmb_clip(0, W - 1, px + k)] << (8 * k);
         }
-        *(unsigned *)(win + r * WIN_PITCH + c4) = v;
+        *(unsigned *)(win + r * WIN_PITCH + 4 * wi) = v;
       }
       __syncthreads();
 
-      const int nx4 = (cw + 3) >> 2, mid = ch >> 1;
-      for (int it = tid; it < nx4 * ch; it += 256) {
-        const int k = it / nx4, ix4 = it - k * nx4;
-        const int row = (k & 1) ? mid - ((k + 1) >> 1) : mid + (k >> 1);   // centre rows first: tight bounds early
-        unsigned acc[4][16];
+      const int nrg = (ch + 3) >> 2, mid = nrg >> 1;
+      if (!seeded) {
+        // Stage 1: exact, gate-free evaluation of a small neighbourhood of the search centre (S1_COLS columns x
+        // 4*S1_RGS rows) so that the bounds are tight before the sweep starts.  Phase a: one thread per item
+        // computes the SADs and leaves the 41 partition sums of its 4 displacements in shared memory; phase b:
+        // four threads per partition scan them with the exact cost and publish the winner.
+        seeded = true;
+        const int ncol = min(S1_COLS, cw), nrgs = min(S1_RGS, nrg);
+        const int col0 = jmb_clip(0, cw - ncol, sbox[8] - cx0 - ncol / 2);
+        const int rg0 = jmb_clip(0, nrg - nrgs, ((sbox[9] - cy0) >> 2) - nrgs / 2);
+        if (tid < ncol * nrgs) {
+          const int ic = col0 + tid % ncol, rg = rg0 + tid / ncol;
+          unsigned acc[4][16];
+          sad_item(win, ssrc, rg * 4, ic + xoff0, acc);
 #pragma unroll
-        for (int s = 0; s < 4; s++)
-#pragma unroll
-          for (int b = 0; b < 16; b++) acc[s][b] = 0;
-#pragma unroll
-        for (int r = 0; r < 16; r++) {
-          const unsigned *wp = (const unsigned *)(win + (row + r) * WIN_PITCH + ix4 * 4);
-          unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
-          unsigned wv[5] = {w0, w1, w2, w3, w4};
-#pragma unroll
-          for (int c = 0; c < 4; c++) {
-            const unsigned sv = ssrc[r * 4 + c];
-            const int b = (r >> 2) * 4 + c;
-            acc[0][b] = sad4(wv[c], sv, acc[0][b]);
-            acc[1][b] = sad4(__byte_perm(wv[c], wv[c + 1], 0x4321), sv, acc[1][b]);
-            acc[2][b] = sad4(__byte_perm(wv[c], wv[c + 1], 0x5432), sv, acc[2][b]);
-            acc[3][b] = sad4(__byte_perm(wv[c], wv[c + 1], 0x6543), sv, acc[3][b]);
+          for (int s = 0; s < 4; s++) {
+            unsigned short *o = S1 + (tid * 4 + s) * S1_PITCH;
+            for_each_partition(acc[s], [&](int p, unsigned v) { o[p] = (unsigned short)v; });
           }
         }
-        const int Dy = cy0 + row;
+        __syncthreads();
+        {
+          const int p = tid >> 2, j = tid & 3;
+          unsigned long long k = ~0ull;
+          if (p < NPART && G.rq[p].active) {
+            const ReqS &q = G.rq[p];
+            const int4 in = G.inner[p];
+            for (int i = j; i < ncol * nrgs * 4; i += 4) {
+              const int item = i >> 2, s = i & 3;
+              const int Dx = cx0 + col0 + item % ncol, Dy = cy0 + (rg0 + item / ncol) * 4 + s;
+              if (Dx < in.x || Dx > in.y || Dy < in.z || Dy > in.w || Dy >= cy0 + ch) continue;
+              const int mx = 4 * Dx - q.px, my = 4 * Dy - q.py;
+              if (q.ffs && max(abs(mx), abs(my)) >= max_mvd_m1) continue;
+              const unsigned long long cost = ((unsigned long long)S1[i * S1_PITCH + p] << 5) +
+                                              (unsigned long long)((long long)q.lam * (jmb_mvbits(mx) + jmb_mvbits(my)));
+              k = min(k, (cost << IDX_BITS) | (unsigned)jmb_spiral_index(Dx - q.cx, Dy - q.cy));
+            }
+          }
+          k = min(k, __shfl_xor_sync(0xffffffffu, k, 1));
+          k = min(k, __shfl_xor_sync(0xffffffffu, k, 2));
+          if (p < NPART && j == 0 && k != ~0ull && k < G.best[p]) publish(&G, p, k);
+        }
+        __syncthreads();
+      }
+
+      for (int it = tid; it < nrg * cw; it += NT) {
+        const int k = it / cw, ic = it - k * cw;
+        const int rg = (k & 1) ? mid - ((k + 1) >> 1) : mid + (k >> 1);   // centre rows first: tight bounds early
+        const int row0 = rg * 4, xo = ic + xoff0;
+        unsigned acc[4][16];
+        sad_item(win, ssrc, row0, xo, acc);
+        // gate: does any of the 4 x 41 partition SADs beat its current bound?
+        unsigned t[NPART + 3];
 #pragma unroll
-        for (int s = 0; s < 4; s++) {
-          const int Dx = cx0 + ix4 * 4 + s;
-          if (Dx > bx1) break;
-          const unsigned *a = acc[s];
-          // partition sums, lencod/src/me_fullfast.c:207-259
-          unsigned s6[8], s5[8], s4[4];
+        for (int i = 0; i < (NPART + 3) / 4; i++) {
+          asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(t[4 * i]), "=r"(t[4 * i + 1]), "=r"(t[4 * i + 2]), "=r"(t[4 * i + 3])
+                       : "r"((unsigned)__cvta_generic_to_shared(&G.thr[4 * i])));
+        }
+        bool any = false;
 #pragma unroll
-          for (int i = 0; i < 4; i++) { s6[i] = a[i] + a[4 + i]; s6[4 + i] = a[8 + i] + a[12 + i]; }
+        for (int s = 0; s < 4; s++)
+          if (row0 + s < ch) for_each_partition(acc[s], [&](int p, unsigned v) { any |= v < t[p]; });
+        if (any) {
+          const int Dx = cx0 + ic;
 #pragma unroll
-          for (int i = 0; i < 8; i++) s5[i] = a[2 * i] + a[2 * i + 1];
-          s4[0] = s6[0] + s6[1]; s4[1] = s6[2] + s6[3]; s4[2] = s6[4] + s6[5]; s4[3] = s6[6] + s6[7];
-          const unsigned s3a = s4[0] + s4[2], s3b = s4[1] + s4[3], s2a = s4[0] + s4[1], s2b = s4[2] + s4[3];
-#define EV(p, v) eval(&rq[p], (v), Dx, Dy, R, max_mvd_m1, &best[p])
-          EV(0, s2a + s2b);
-          EV(1, s2a); EV(2, s2b);
-          EV(3, s3a); EV(4, s3b);
-          EV(5, s4[0]); EV(6, s4[1]); EV(7, s4[2]); EV(8, s4[3]);
-#pragma unroll
-          for (int i = 0; i < 8; i++) EV(9 + i, s5[i]);     // 8x4: (bx 0|2, by 0..3) raster = pairs (2i, 2i+1)
-#pragma unroll
-          for (int i = 0; i < 8; i++) EV(17 + i, s6[i]);    // 4x8: (bx 0..3, by 0|2)
-#pragma unroll
-          for (int i = 0; i < 16; i++) EV(25 + i, a[i]);
-#undef EV
+          for (int s = 0; s < 4; s++)
+            if (row0 + s < ch) {
+              const int Dy = cy0 + row0 + s;
+              for_each_partition(acc[s], [&](int p, unsigned v) { if (v < t[p]) level2(&G, p, v, Dx, Dy); });
+            }
         }
       }
     }
   }
   __syncthreads();
-  if (tid < NPART && rq[tid].active) {
-    const ReqS &q = rq[tid];
-    unsigned long long k = best[tid];
+  if (tid < NPART && G.rq[tid].active) {
+    const ReqS &q = G.rq[tid];
+    unsigned long long k = G.best[tid];
     int dx = 0, dy = 0;
     long long cost = (long long)(k >> IDX_BITS);
     if (k != q.init) spiral_xy((int)(k & ((1u << IDX_BITS) - 1)), &dx, &dy);
@@ -400,7 +520,7 @@ static int me_search_impl(jmb_ctx *ctx, const jmb_me_req *reqs, int n, jmb_me_re
     d_reqs = (const jmb_me_req *)ctx->d_stage; d_res = (jmb_me_res *)ctx->d_stage2;
   }
   jmb_time_begin(ctx, JMB_K_INT_SEARCH);
-  k_int_search<<<n_groups, 256, 0, ctx->stream>>>(d_reqs, d_groups, d_res, ctx->cur, ctx->cur_pitch, d_tab, r0.pitch,
+  k_int_search<<<n_groups, NT, 0, ctx->stream>>>(d_reqs, d_groups, d_res, ctx->cur, ctx->cur_pitch, d_tab, r0.pitch,
                                                   ctx->cur_w, ctx->cur_h, ctx->me.search_range, ctx->me.max_mvd - 1);
   jmb_time_end(ctx, JMB_K_INT_SEARCH);
   JMB_LAUNCH_CHECK(ctx);

@@ -24,6 +24,30 @@ template <int MODE> __global__ void k(unsigned *out, int iters, unsigned seed) {
         asm volatile("prmt.b32 %0,%0,%1,0x5432;" : "+r"(c6) : "r"(a2)); asm volatile("prmt.b32 %0,%0,%1,0x5432;" : "+r"(c7) : "r"(a3));
       } else if (MODE == 2) {  // iadd3 reference
         c0 += a0 + c1; c1 += a1 + c2; c2 += a2 + c3; c3 += a3 + c4; c4 += a0 + c5; c5 += a1 + c6; c6 += a2 + c7; c7 += a3 + c0;
+      } else if (MODE == 4) {  // dp4a
+        asm volatile("dp4a.u32.u32 %0,%1,%2,%0;" : "+r"(c0) : "r"(a0), "r"(a1)); asm volatile("dp4a.u32.u32 %0,%1,%2,%0;" : "+r"(c1) : "r"(a1), "r"(a2));
+        asm volatile("dp4a.u32.u32 %0,%1,%2,%0;" : "+r"(c2) : "r"(a2), "r"(a3)); asm volatile("dp4a.u32.u32 %0,%1,%2,%0;" : "+r"(c3) : "r"(a3), "r"(a0));
+        asm volatile("dp4a.u32.u32 %0,%1,%2,%0;" : "+r"(c4) : "r"(a0), "r"(a2)); asm volatile("dp4a.u32.u32 %0,%1,%2,%0;" : "+r"(c5) : "r"(a1), "r"(a3));
+        asm volatile("dp4a.u32.u32 %0,%1,%2,%0;" : "+r"(c6) : "r"(a2), "r"(a0)); asm volatile("dp4a.u32.u32 %0,%1,%2,%0;" : "+r"(c7) : "r"(a3), "r"(a1));
+      } else if (MODE == 5) {  // funnel shift
+        asm volatile("shf.r.wrap.b32 %0,%0,%1,8;" : "+r"(c0) : "r"(a0)); asm volatile("shf.r.wrap.b32 %0,%0,%1,8;" : "+r"(c1) : "r"(a1));
+        asm volatile("shf.r.wrap.b32 %0,%0,%1,8;" : "+r"(c2) : "r"(a2)); asm volatile("shf.r.wrap.b32 %0,%0,%1,8;" : "+r"(c3) : "r"(a3));
+        asm volatile("shf.r.wrap.b32 %0,%0,%1,16;" : "+r"(c4) : "r"(a0)); asm volatile("shf.r.wrap.b32 %0,%0,%1,16;" : "+r"(c5) : "r"(a1));
+        asm volatile("shf.r.wrap.b32 %0,%0,%1,16;" : "+r"(c6) : "r"(a2)); asm volatile("shf.r.wrap.b32 %0,%0,%1,16;" : "+r"(c7) : "r"(a3));
+      } else if (MODE == 6) {  // vabsdiff4 (no add) + imad accumulate via dp4a
+        unsigned t0, t1, t2, t3;
+        asm volatile("vabsdiff4.u32.u32.u32 %0,%1,%2,%3;" : "=r"(t0) : "r"(a0), "r"(c4), "r"(0u));
+        asm volatile("dp4a.u32.u32 %0,%1,%2,%0;" : "+r"(c0) : "r"(t0), "r"(0x01010101u));
+        asm volatile("vabsdiff4.u32.u32.u32 %0,%1,%2,%3;" : "=r"(t1) : "r"(a1), "r"(c5), "r"(0u));
+        asm volatile("dp4a.u32.u32 %0,%1,%2,%0;" : "+r"(c1) : "r"(t1), "r"(0x01010101u));
+        asm volatile("vabsdiff4.u32.u32.u32 %0,%1,%2,%3;" : "=r"(t2) : "r"(a2), "r"(c6), "r"(0u));
+        asm volatile("dp4a.u32.u32 %0,%1,%2,%0;" : "+r"(c2) : "r"(t2), "r"(0x01010101u));
+        asm volatile("vabsdiff4.u32.u32.u32 %0,%1,%2,%3;" : "=r"(t3) : "r"(a3), "r"(c7), "r"(0u));
+        asm volatile("dp4a.u32.u32 %0,%1,%2,%0;" : "+r"(c3) : "r"(t3), "r"(0x01010101u));
+        c4 ^= c0; c5 ^= c1; c6 ^= c2; c7 ^= c3;
+      } else if (MODE == 7) {  // isetp with predicate accumulation + select
+        bool p = (c0 < a0) | (c1 < a1) | (c2 < a2) | (c3 < a3) | (c4 < a0) | (c5 < a1) | (c6 < a2) | (c7 < a3);
+        c0 += p; c1 ^= c0; c2 ^= c1; c3 ^= c2; c4 ^= c3; c5 ^= c4; c6 ^= c5; c7 ^= c6;
       } else {  // mix: 4 vabsdiff4 + 3 prmt (the SAD inner loop ratio)
         asm volatile("vabsdiff4.u32.u32.u32.add %0,%1,%2,%0;" : "+r"(c0) : "r"(a0), "r"(c4));
         asm volatile("prmt.b32 %0,%1,%2,0x4321;" : "=r"(c4) : "r"(a1), "r"(c0));
@@ -51,5 +75,6 @@ template <int MODE> void run(const char *name, int per_iter) {
 }
 int main() {
   run<0>("vabsdiff4.add", 8); run<1>("prmt", 8); run<2>("iadd3", 8); run<3>("4 vabsdiff4 + 3 prmt + 1 lop", 8);
+  run<4>("dp4a", 8); run<5>("shf.r.wrap", 8); run<6>("4x(vabsdiff4 + dp4a) + 4 lop", 12); run<7>("8 isetp.or + 8 alu", 16);
   return 0;
 }
