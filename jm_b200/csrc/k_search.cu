@@ -29,6 +29,7 @@ constexpr int CH = 72;             // multiple of 4 (a thread owns 4 vertically 
 constexpr int WIN_PITCH = 152;     // bytes: <=3 alignment + CW + 15, rounded up to a word, + the fifth word
 constexpr int WIN_ROWS = CH + 15;
 constexpr int S1_COLS = 10, S1_RGS = 3, S1_ITEMS = S1_COLS * S1_RGS, S1_PITCH = 43;   // stage-1 neighbourhood
+constexpr int ADJ_PITCH = 56;      // u16 per column (>= NPART; 112 B keeps the 128-bit row reads conflict-free)
 constexpr int IDX_BITS = 13;       // (2*64+1)^2 = 16641 > 8192: search_range <= 45 keeps idx < 8192
 
 struct PartGeom { unsigned char type, bx, by, w4, h4; };
@@ -68,7 +69,7 @@ struct Grp {
 __device__ __forceinline__ unsigned bound_of(unsigned long long k, int lam) {
   const unsigned long long cost = k >> IDX_BITS, floor_ = 2ull * (unsigned)lam;
   if (cost < floor_) return 0u;
-  return (unsigned)min(((cost - floor_) >> 5) + 1, 0xffffffffull);
+  return (unsigned)min(((cost - floor_) >> 5) + 1, 0x7fffffffull);   // compared as signed int after the column adjustment
 }
 
 __device__ __forceinline__ unsigned sad4(unsigned a, unsigned b, unsigned c) {
@@ -205,12 +206,18 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
   __shared__ Grp G;
   __shared__ __align__(16) uint8_t win[WIN_ROWS * WIN_PITCH];
   __shared__ __align__(16) unsigned ssrc[16 * 4];
-  __shared__ int sbox[10];
+  __shared__ int sbox[12];
+  __shared__ __align__(16) unsigned short adjx[CW * ADJ_PITCH];   // per column and partition: floor(lambda * (bits_x - 1) / 32)
   __shared__ unsigned short S1[S1_ITEMS * 4 * S1_PITCH];
 
   const int tid = threadIdx.x, g = blockIdx.x;
   const int W = w + 2 * JMB_PAD_X, H = h + 2 * JMB_PAD_Y;
 
+  if (tid == 0) {
+    sbox[0] = sbox[2] = 1 << 30; sbox[1] = sbox[3] = -(1 << 30); sbox[7] = 0; sbox[10] = NPART;
+    G.R = R; G.max_mvd_m1 = max_mvd_m1; G.thr[NPART] = G.thr[NPART + 1] = G.thr[NPART + 2] = 0;
+  }
+  __syncthreads();
   if (tid < NPART) {
     int ri = groups ? groups[g * NPART + tid] : g * NPART + tid;
     ReqS q; q.active = 0; q.req = ri;
@@ -225,6 +232,11 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
         q.cx = r.center_x >> 2; q.cy = r.center_y >> 2;
         q.px = r.pred_x; q.py = r.pred_y; q.lam = r.lambda[0];
         q.init = (unsigned long long)r.min_mcost << IDX_BITS;
+        // union of the (clamped) displacement ranges of the group's requests
+        atomicMin(&sbox[0], jmb_clip(q.dlo_x, q.dhi_x, q.cx - R)); atomicMax(&sbox[1], jmb_clip(q.dlo_x, q.dhi_x, q.cx + R));
+        atomicMin(&sbox[2], jmb_clip(q.dlo_y, q.dhi_y, q.cy - R)); atomicMax(&sbox[3], jmb_clip(q.dlo_y, q.dhi_y, q.cy + R));
+        atomicMin(&sbox[10], tid);
+        sbox[4] = r.pos_x & ~15; sbox[5] = r.pos_y & ~15; sbox[6] = r.ref; sbox[7] = 1;   // same for every request of a group
       }
     }
     G.rq[tid] = q;
@@ -233,21 +245,6 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
     int4 in = make_int4(1, 0, 1, 0);
     if (q.active) in = make_int4(max(q.dlo_x + 1, q.cx - R), min(q.dhi_x - 1, q.cx + R), max(q.dlo_y + 1, q.cy - R), min(q.dhi_y - 1, q.cy + R));
     G.inner[tid] = in;
-  }
-  if (tid == 0) { G.R = R; G.max_mvd_m1 = max_mvd_m1; G.thr[NPART] = G.thr[NPART + 1] = G.thr[NPART + 2] = 0; }
-  __syncthreads();
-  if (tid == 0) {
-    int x0 = 1 << 30, x1 = -(1 << 30), y0 = 1 << 30, y1 = -(1 << 30), mbx = 0, mby = 0, rf = 0, any = 0;
-    for (int p = 0; p < NPART; p++) if (G.rq[p].active) {
-      const ReqS &q = G.rq[p];
-      x0 = min(x0, jmb_clip(q.dlo_x, q.dhi_x, q.cx - R)); x1 = max(x1, jmb_clip(q.dlo_x, q.dhi_x, q.cx + R));
-      y0 = min(y0, jmb_clip(q.dlo_y, q.dhi_y, q.cy - R)); y1 = max(y1, jmb_clip(q.dlo_y, q.dhi_y, q.cy + R));
-      jmb_me_req r = reqs[q.req];
-      mbx = r.pos_x & ~15; mby = r.pos_y & ~15; rf = r.ref;
-      if (!any) { sbox[8] = q.cx; sbox[9] = q.cy; }
-      any = 1;
-    }
-    sbox[0] = x0; sbox[1] = x1; sbox[2] = y0; sbox[3] = y1; sbox[4] = mbx; sbox[5] = mby; sbox[6] = rf; sbox[7] = any;
   }
   __syncthreads();
   if (!sbox[7]) return;   // nothing but sub-pel-only requests in this group
@@ -284,17 +281,18 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
         *(unsigned *)(win + r * WIN_PITCH + 4 * wi) = v;
       }
       __syncthreads();
-
       const int nrg = (ch + 3) >> 2, mid = nrg >> 1;
-      if (!seeded) {
-        // Stage 1: exact, gate-free evaluation of a small neighbourhood of the search centre (S1_COLS columns x
-        // 4*S1_RGS rows) so that the bounds are tight before the sweep starts.  Phase a: one thread per item
-        // computes the SADs and leaves the 41 partition sums of its 4 displacements in shared memory; phase b:
-        // four threads per partition scan them with the exact cost and publish the winner.
-        seeded = true;
-        const int ncol = min(S1_COLS, cw), nrgs = min(S1_RGS, nrg);
-        const int col0 = jmb_clip(0, cw - ncol, sbox[8] - cx0 - ncol / 2);
-        const int rg0 = jmb_clip(0, nrg - nrgs, ((sbox[9] - cy0) >> 2) - nrgs / 2);
+      const bool s1 = !seeded;
+      seeded = true;
+      // Stage 1 (first chunk only): exact, gate-free evaluation of a small neighbourhood of the search centre
+      // (S1_COLS columns x 4*S1_RGS rows) so that the bounds are tight before the sweep starts.  Phase a: warp 0,
+      // one thread per item, computes the SADs and leaves the 41 partition sums of its 4 displacements in shared
+      // memory -- while the other warps build the column table of the gate.  Phase b: four threads per partition
+      // scan the sums with the exact cost and publish the winner.
+      const int ncol = min(S1_COLS, cw), nrgs = min(S1_RGS, nrg);
+      const int col0 = jmb_clip(0, cw - ncol, G.rq[sbox[10]].cx - cx0 - ncol / 2);
+      const int rg0 = jmb_clip(0, nrg - nrgs, ((G.rq[sbox[10]].cy - cy0) >> 2) - nrgs / 2);
+      if (s1 && tid < 32) {
         if (tid < ncol * nrgs) {
           const int ic = col0 + tid % ncol, rg = rg0 + tid / ncol;
           unsigned acc[4][16];
@@ -305,32 +303,54 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
             for_each_partition(acc[s], [&](int p, unsigned v) { o[p] = (unsigned short)v; });
           }
         }
-        __syncthreads();
-        {
-          const int p = tid >> 2, j = tid & 3;
-          unsigned long long k = ~0ull;
-          if (p < NPART && G.rq[p].active) {
-            const ReqS &q = G.rq[p];
-            const int4 in = G.inner[p];
-            for (int i = j; i < ncol * nrgs * 4; i += 4) {
-              const int item = i >> 2, s = i & 3;
-              const int Dx = cx0 + col0 + item % ncol, Dy = cy0 + (rg0 + item / ncol) * 4 + s;
-              if (Dx < in.x || Dx > in.y || Dy < in.z || Dy > in.w || Dy >= cy0 + ch) continue;
-              const int mx = 4 * Dx - q.px, my = 4 * Dy - q.py;
-              if (q.ffs && max(abs(mx), abs(my)) >= max_mvd_m1) continue;
-              const unsigned long long cost = ((unsigned long long)S1[i * S1_PITCH + p] << 5) +
-                                              (unsigned long long)((long long)q.lam * (jmb_mvbits(mx) + jmb_mvbits(my)));
-              k = min(k, (cost << IDX_BITS) | (unsigned)jmb_spiral_index(Dx - q.cx, Dy - q.cy));
-            }
-          }
-          k = min(k, __shfl_xor_sync(0xffffffffu, k, 1));
-          k = min(k, __shfl_xor_sync(0xffffffffu, k, 2));
-          if (p < NPART && j == 0 && k != ~0ull && k < G.best[p]) publish(&G, p, k);
+      } else {
+        // column part of the gate: every candidate in column Dx pays at least lambda * (bits_x(Dx) + 1), i.e.
+        // lambda * (bits_x - 1) more than the constant folded into thr
+        for (int i = s1 ? tid - 32 : tid; i < cw * NPART; i += s1 ? NT - 32 : NT) {
+          const int ic = i / NPART, p = i - ic * NPART;
+          const ReqS &q = G.rq[p];
+          unsigned a = 0;
+          if (q.active) a = min(65535u, ((unsigned)q.lam * (unsigned)(jmb_mvbits(4 * (cx0 + ic) - q.px) - 1)) >> 5);
+          adjx[ic * ADJ_PITCH + p] = (unsigned short)a;
         }
+      }
+      if (tid == 0) sbox[11] = 0;      // next warp item of the sweep
+      __syncthreads();
+      if (s1) {
+        const int p = tid >> 2, j = tid & 3;
+        unsigned long long k = ~0ull;
+        if (p < NPART && G.rq[p].active) {
+          const ReqS &q = G.rq[p];
+          const int4 in = G.inner[p];
+          int item = 0, c = 0;     // item = c + ncol * row group
+          for (int i = j; i < ncol * nrgs * 4; i += 4, item++) {
+            const int rgi = item / ncol; c = item - rgi * ncol;
+            const int Dx = cx0 + col0 + c, Dy = cy0 + (rg0 + rgi) * 4 + j;      // i = 4 * item + j: displacement row j of the item
+            if (Dx < in.x || Dx > in.y || Dy < in.z || Dy > in.w || Dy >= cy0 + ch) continue;
+            const int mx = 4 * Dx - q.px, my = 4 * Dy - q.py;
+            if (q.ffs && max(abs(mx), abs(my)) >= max_mvd_m1) continue;
+            const unsigned long long cost = ((unsigned long long)S1[i * S1_PITCH + p] << 5) +
+                                            (unsigned long long)((long long)q.lam * (jmb_mvbits(mx) + jmb_mvbits(my)));
+            if (cost > (k >> IDX_BITS)) continue;
+            k = min(k, (cost << IDX_BITS) | (unsigned)jmb_spiral_index(Dx - q.cx, Dy - q.cy));
+          }
+        }
+        k = min(k, __shfl_xor_sync(0xffffffffu, k, 1));
+        k = min(k, __shfl_xor_sync(0xffffffffu, k, 2));
+        if (p < NPART && j == 0 && k != ~0ull && k < G.best[p]) publish(&G, p, k);
         __syncthreads();
       }
 
-      for (int it = tid; it < nrg * cw; it += NT) {
+      // the sweep: warps draw batches of 32 items from a shared counter (a batch that meets the gate runs much
+      // longer than one that does not, so a static split would leave warps waiting at the final barrier)
+      const int nitems = nrg * cw, lane = tid & 31;
+      for (;;) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&sbox[11], 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= nitems) break;
+        const int it = base + lane;
+        if (it >= nitems) continue;
         const int k = it / cw, ic = it - k * cw;
         const int rg = (k & 1) ? mid - ((k + 1) >> 1) : mid + (k >> 1);   // centre rows first: tight bounds early
         const int row0 = rg * 4, xo = ic + xoff0;
@@ -344,18 +364,32 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
                        : "=r"(t[4 * i]), "=r"(t[4 * i + 1]), "=r"(t[4 * i + 2]), "=r"(t[4 * i + 3])
                        : "r"((unsigned)__cvta_generic_to_shared(&G.thr[4 * i])));
         }
-        bool any = false;
+        {
+          const uint4 *ap = (const uint4 *)&adjx[ic * ADJ_PITCH];
 #pragma unroll
-        for (int s = 0; s < 4; s++)
-          if (row0 + s < ch) for_each_partition(acc[s], [&](int p, unsigned v) { any |= v < t[p]; });
-        if (any) {
-          const int Dx = cx0 + ic;
+          for (int i = 0; i < (NPART + 7) / 8; i++) {
+            const uint4 v = ap[i];
+            const unsigned w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-          for (int s = 0; s < 4; s++)
-            if (row0 + s < ch) {
-              const int Dy = cy0 + row0 + s;
-              for_each_partition(acc[s], [&](int p, unsigned v) { if (v < t[p]) level2(&G, p, v, Dx, Dy); });
-            }
+            for (int k = 0; k < 8; k++)
+              if (8 * i + k < NPART) t[8 * i + k] -= (w[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+          }
+        }
+        // one flag per displacement and partition class (larger partitions / the sixteen 4x4s) keeps the
+        // re-visit below short
+        bool hitA[4], hitB[4];
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+          hitA[s] = hitB[s] = false;
+          if (row0 + s < ch)
+            for_each_partition(acc[s], [&](int p, unsigned v) { if (p < 25) hitA[s] |= (int)v < (int)t[p]; else hitB[s] |= (int)v < (int)t[p]; });
+        }
+        const int Dx = cx0 + ic;
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+          const int Dy = cy0 + row0 + s;
+          if (hitA[s]) for_each_partition(acc[s], [&](int p, unsigned v) { if (p < 25 && (int)v < (int)t[p]) level2(&G, p, v, Dx, Dy); });
+          if (hitB[s]) for_each_partition(acc[s], [&](int p, unsigned v) { if (p >= 25 && (int)v < (int)t[p]) level2(&G, p, v, Dx, Dy); });
         }
       }
     }
