@@ -81,7 +81,7 @@ typedef struct jmb_me_req {
   uint8_t ref;                 /* index into the reference list given to jmb_pic_begin */
   uint8_t mode;                /* JMB_SEARCH_* */
   uint8_t flags;               /* JMB_REQ_* */
-  int32_t lambda[3];           /* lambda_factor[F_PEL,H_PEL,Q_PEL] */
+  int32_t lambda[3];           /* lambda_factor[F_PEL,H_PEL,Q_PEL], each 0..65535 (JM's largest is < 6000) */
   int32_t reserved_;           /* keeps min_mcost 8-byte aligned; set to 0 */
   int64_t min_mcost;           /* incoming minimum cost (DISTBLK_MAX from BlockMotionSearch) */
 } jmb_me_req;

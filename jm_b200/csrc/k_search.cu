@@ -24,12 +24,12 @@ namespace {
 
 constexpr int NPART = 41;
 constexpr int NT = 192;            // threads per CTA
-constexpr int CW = 128;            // chunk of displacements handled per staging pass
+constexpr int CW = 96;             // chunk of displacements handled per staging pass
 constexpr int CH = 72;             // multiple of 4 (a thread owns 4 vertically adjacent displacements)
-constexpr int WIN_PITCH = 152;     // bytes: <=3 alignment + CW + 15, rounded up to a word, + the fifth word
+constexpr int WIN_PITCH = 120;     // bytes: <=3 alignment + CW + 15, rounded up to a word, + the fifth word
 constexpr int WIN_ROWS = CH + 15;
 constexpr int S1_COLS = 10, S1_RGS = 3, S1_ITEMS = S1_COLS * S1_RGS, S1_PITCH = 43;   // stage-1 neighbourhood
-constexpr int ADJ_PITCH = 56;      // u16 per column (>= NPART; 112 B keeps the 128-bit row reads conflict-free)
+constexpr int ADJ_PITCH = 44;      // words per column (>= NPART; 176 B keeps the 128-bit row reads conflict-free)
 constexpr int IDX_BITS = 13;       // (2*64+1)^2 = 16641 > 8192: search_range <= 45 keeps idx < 8192
 
 struct PartGeom { unsigned char type, bx, by, w4, h4; };
@@ -207,7 +207,7 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
   __shared__ __align__(16) uint8_t win[WIN_ROWS * WIN_PITCH];
   __shared__ __align__(16) unsigned ssrc[16 * 4];
   __shared__ int sbox[12];
-  __shared__ __align__(16) unsigned short adjx[CW * ADJ_PITCH];   // per column and partition: floor(lambda * (bits_x - 1) / 32)
+  __shared__ __align__(16) unsigned adjx[CW * ADJ_PITCH];   // per column and partition: floor(lambda * (bits_x - 1) / 32)
   __shared__ unsigned short S1[S1_ITEMS * 4 * S1_PITCH];
 
   const int tid = threadIdx.x, g = blockIdx.x;
@@ -311,7 +311,7 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
           const ReqS &q = G.rq[p];
           unsigned a = 0;
           if (q.active) a = min(65535u, ((unsigned)q.lam * (unsigned)(jmb_mvbits(4 * (cx0 + ic) - q.px) - 1)) >> 5);
-          adjx[ic * ADJ_PITCH + p] = (unsigned short)a;
+          adjx[ic * ADJ_PITCH + p] = a;
         }
       }
       if (tid == 0) sbox[11] = 0;      // next warp item of the sweep
@@ -322,18 +322,25 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
         if (p < NPART && G.rq[p].active) {
           const ReqS &q = G.rq[p];
           const int4 in = G.inner[p];
-          int item = 0, c = 0;     // item = c + ncol * row group
-          for (int i = j; i < ncol * nrgs * 4; i += 4, item++) {
-            const int rgi = item / ncol; c = item - rgi * ncol;
-            const int Dx = cx0 + col0 + c, Dy = cy0 + (rg0 + rgi) * 4 + j;      // i = 4 * item + j: displacement row j of the item
-            if (Dx < in.x || Dx > in.y || Dy < in.z || Dy > in.w || Dy >= cy0 + ch) continue;
-            const int mx = 4 * Dx - q.px, my = 4 * Dy - q.py;
-            if (q.ffs && max(abs(mx), abs(my)) >= max_mvd_m1) continue;
-            const unsigned long long cost = ((unsigned long long)S1[i * S1_PITCH + p] << 5) +
-                                            (unsigned long long)((long long)q.lam * (jmb_mvbits(mx) + jmb_mvbits(my)));
-            if (cost > (k >> IDX_BITS)) continue;
-            k = min(k, (cost << IDX_BITS) | (unsigned)jmb_spiral_index(Dx - q.cx, Dy - q.cy));
+          const unsigned lam = (unsigned)q.lam;
+          unsigned bcost = 0xffffffffu; int bDx = 0, bDy = 0, bidx = 0;   // thread j looks at displacement row j of every item
+          for (int rgi = 0; rgi < nrgs; rgi++) {
+            const int Dy = cy0 + (rg0 + rgi) * 4 + j, my = 4 * Dy - q.py;
+            if (Dy < in.z || Dy > in.w || Dy >= cy0 + ch) continue;
+            const unsigned ycost = lam * (unsigned)jmb_mvbits(my);
+            const unsigned short *sp = S1 + ((rgi * ncol) * 4 + j) * S1_PITCH + p;
+            for (int c = 0; c < ncol; c++) {
+              const int Dx = cx0 + col0 + c, mx = 4 * Dx - q.px;
+              if (Dx < in.x || Dx > in.y) continue;
+              if (q.ffs && max(abs(mx), abs(my)) >= max_mvd_m1) continue;
+              const unsigned cost = ((unsigned)sp[c * 4 * S1_PITCH] << 5) + ycost + lam * (unsigned)jmb_mvbits(mx);
+              if (cost > bcost) continue;
+              const int idx = jmb_spiral_index(Dx - q.cx, Dy - q.cy);
+              if (cost < bcost || idx < bidx) { bcost = cost; bidx = idx; bDx = Dx; bDy = Dy; }
+            }
           }
+          if (bcost != 0xffffffffu) k = ((unsigned long long)bcost << IDX_BITS) | (unsigned)bidx;
+          (void)bDx; (void)bDy;
         }
         k = min(k, __shfl_xor_sync(0xffffffffu, k, 1));
         k = min(k, __shfl_xor_sync(0xffffffffu, k, 2));
@@ -367,12 +374,9 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
         {
           const uint4 *ap = (const uint4 *)&adjx[ic * ADJ_PITCH];
 #pragma unroll
-          for (int i = 0; i < (NPART + 7) / 8; i++) {
+          for (int i = 0; i < (NPART + 3) / 4; i++) {
             const uint4 v = ap[i];
-            const unsigned w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-              if (8 * i + k < NPART) t[8 * i + k] -= (w[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+            t[4 * i] -= v.x; t[4 * i + 1] -= v.y; t[4 * i + 2] -= v.z; t[4 * i + 3] -= v.w;
           }
         }
         // one flag per displacement and partition class (larger partitions / the sixteen 4x4s) keeps the
@@ -476,6 +480,8 @@ static int validate_req(jmb_ctx *ctx, const jmb_me_req &r, int i) {
   if (!(r.flags & JMB_REQ_SKIP_INT) && ((r.center_x | r.center_y) & 3))
     return jmb_fail(ctx, JMB_ERR_ARG, "request %d: search centre (%d,%d) is not integer-pel", i, r.center_x, r.center_y);
   if (r.mode > JMB_SEARCH_FAST_FULL) return jmb_fail(ctx, JMB_ERR_ARG, "request %d: mode %d", i, r.mode);
+  for (int k = 0; k < 3; k++)
+    if (r.lambda[k] < 0 || r.lambda[k] > 65535) return jmb_fail(ctx, JMB_ERR_ARG, "request %d: lambda[%d]=%d not in 0..65535", i, k, r.lambda[k]);
   if (r.min_mcost < 0 || r.min_mcost > ((int64_t)1 << 48)) return jmb_fail(ctx, JMB_ERR_ARG, "request %d: min_mcost out of range", i);
   return 0;
 }
