@@ -187,7 +187,7 @@ int jmb_ref_put(jmb_ctx *ctx, int slot, const uint16_t *luma, int width, int hei
   size_t plane_bytes = (size_t)pitch * H;
   if (!r->planes || r->w != width || r->h != height) {
     if (r->planes) { JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); JMB_CUDA(ctx, cudaFree(r->planes)); r->planes = nullptr; }
-    JMB_CUDA(ctx, cudaMalloc(&r->planes, plane_bytes * 16));
+    JMB_CUDA(ctx, cudaMalloc(&r->planes, plane_bytes * 16 + 64));   // + slack: unaligned 4-sample reads fetch the next word
     r->w = width; r->h = height; r->W = W; r->H = H; r->pitch = pitch; r->plane_bytes = plane_bytes;
   }
   void *d_src = nullptr;

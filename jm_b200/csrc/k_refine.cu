@@ -69,11 +69,36 @@ __device__ int hadamard8(int *a) {   // a[64] row-major, destroyed
   return (s + 2) >> 2;
 }
 
+// four (or eight) consecutive samples starting at an arbitrary byte address: aligned word loads + PRMT
+__device__ __forceinline__ unsigned ld4(const uint8_t *p) {
+  const unsigned sh = (unsigned)(size_t)p & 3u;
+  const unsigned *a = (const unsigned *)(p - sh);
+  return __byte_perm(__ldg(a), __ldg(a + 1), 0x3210u + 0x1111u * sh);
+}
+__device__ __forceinline__ void ld8(const uint8_t *p, unsigned &lo, unsigned &hi) {
+  const unsigned sh = (unsigned)(size_t)p & 3u, sel = 0x3210u + 0x1111u * sh;
+  const unsigned *a = (const unsigned *)(p - sh);
+  const unsigned w0 = __ldg(a), w1 = __ldg(a + 1), w2 = __ldg(a + 2);
+  lo = __byte_perm(w0, w1, sel); hi = __byte_perm(w1, w2, sel);
+}
+
+// One sub-block of the source, kept in registers while the candidates of a refinement stage go by.
+struct SrcBlk { unsigned w[16]; };   // n = 4: w[0..3] = rows; n = 8: w[2y], w[2y+1] = row y
+
+__device__ __forceinline__ void load_src(SrcBlk &s, const uint8_t *cur, int cur_pitch, int x, int y, int n) {
+  const uint8_t *p = cur + (size_t)y * cur_pitch + x;      // x is a multiple of 4: aligned
+  if (n == 4) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) s.w[r] = *(const unsigned *)(p + (size_t)r * cur_pitch);
+  } else {
+#pragma unroll
+    for (int r = 0; r < 8; r++) { const unsigned *v = (const unsigned *)(p + (size_t)r * cur_pitch); s.w[2 * r] = v[0]; s.w[2 * r + 1] = v[1]; }
+  }
+}
+
 // distortion contribution of sub-block (sbx, sby) [units of n pels] of a block at (pos_x,pos_y)
 // against the candidate at absolute quarter-pel (cqx, cqy)
-__device__ int subblock_dist(const RefView &rv, const uint8_t *cur, int cur_pitch, int pos_x, int pos_y,
-                             int cqx, int cqy, int sbx, int sby, int n, int metric) {
-  const uint8_t *src = cur + (size_t)(pos_y + sby * n) * cur_pitch + pos_x + sbx * n;
+__device__ __forceinline__ int subblock_dist(const RefView &rv, const SrcBlk &src, int cqx, int cqy, int sbx, int sby, int n, int metric) {
   const uint8_t *ref;
   if (metric == JMB_SATD) ref = umv(rv, cqy + ((sby * n) << 2), cqx + ((sbx * n) << 2));   // per-sub-block clamp
   else ref = umv(rv, cqy, cqx) + (size_t)(sby * n) * rv.pitch + sbx * n;                     // partition clamp
@@ -81,10 +106,9 @@ __device__ int subblock_dist(const RefView &rv, const uint8_t *cur, int cur_pitc
     int d[16];
 #pragma unroll
     for (int y = 0; y < 4; y++) {
-      unsigned sv = *(const unsigned *)(src + (size_t)y * cur_pitch);
-      const uint8_t *rp = ref + (size_t)y * rv.pitch;
+      const unsigned sv = src.w[y], rw = ld4(ref + (size_t)y * rv.pitch);
 #pragma unroll
-      for (int x = 0; x < 4; x++) d[y * 4 + x] = (int)((sv >> (8 * x)) & 255) - (int)rp[x];
+      for (int x = 0; x < 4; x++) d[y * 4 + x] = (int)((sv >> (8 * x)) & 255) - (int)((rw >> (8 * x)) & 255);
     }
     if (metric == JMB_SATD) return hadamard4(d);
     int s = 0;
@@ -95,65 +119,117 @@ __device__ int subblock_dist(const RefView &rv, const uint8_t *cur, int cur_pitc
   int a[64];
 #pragma unroll
   for (int y = 0; y < 8; y++) {
-    const uint8_t *sp = src + (size_t)y * cur_pitch, *rp = ref + (size_t)y * rv.pitch;
+    unsigned lo, hi;
+    ld8(ref + (size_t)y * rv.pitch, lo, hi);
 #pragma unroll
-    for (int x = 0; x < 8; x++) a[y * 8 + x] = (int)sp[x] - (int)rp[x];
+    for (int x = 0; x < 4; x++) {
+      a[y * 8 + x] = (int)((src.w[2 * y] >> (8 * x)) & 255) - (int)((lo >> (8 * x)) & 255);
+      a[y * 8 + 4 + x] = (int)((src.w[2 * y + 1] >> (8 * x)) & 255) - (int)((hi >> (8 * x)) & 255);
+    }
   }
   return hadamard8(a);
 }
 
-// one refinement stage of sub_pel_motion_estimation: candidates mv + step*spiral[pos], pos0 <= pos < pos1
-__device__ void refine_stage(const RefView &rv, const uint8_t *cur, int cur_pitch, const jmb_me_req &r, int lane,
-                             int *sums /* shared, >= 9 per warp */, int step, int pos0, int pos1, int metric, int lam,
-                             int &mvx, int &mvy, long long &min_mcost) {
-  const int bsx = c_bsx[r.blocktype], bsy = c_bsy[r.blocktype];
-  const int n = (metric == JMB_SATD && (r.flags & JMB_REQ_TEST8X8)) ? 8 : 4;
-  const int nsx = bsx / n, nsub = nsx * (bsy / n);
-  if (lane < 9) sums[lane] = 0;
-  __syncwarp();
-  const int ncand = pos1 - pos0;
-  for (int it = lane; it < ncand * nsub; it += 32) {
-    int c = it / nsub, sb = it - c * nsub;
-    int pos = pos0 + c;
-    int cqx = (r.pos_x << 2) + mvx + step * c_spiral9[pos][0], cqy = (r.pos_y << 2) + mvy + step * c_spiral9[pos][1];
-    int d = subblock_dist(rv, cur, cur_pitch, r.pos_x, r.pos_y, cqx, cqy, sb % nsx, sb / nsx, n, metric);
-    atomicAdd(&sums[pos], d);
-  }
-  __syncwarp();
-  int best = 0;
-  for (int pos = pos0; pos < pos1; pos++) {      // every lane replays JM's loop (uniform, tiny)
-    int cx = mvx + step * c_spiral9[pos][0], cy = mvy + step * c_spiral9[pos][1];
-    long long mc = (long long)lam * (jmb_mvbits(cx - r.pred_x) + jmb_mvbits(cy - r.pred_y));
-    if (mc >= min_mcost) continue;
-    mc += (long long)sums[pos] << 5;
-    if (mc < min_mcost) { min_mcost = mc; best = pos; }
-  }
-  mvx += step * c_spiral9[best][0]; mvy += step * c_spiral9[best][1];
-  __syncwarp();
-}
+// Refinement of up to RQ consecutive requests per CTA (one macroblock's 41 searches in the frame layout).
+// Work item = one sub-block of one request; the thread keeps the source sub-block in registers and walks
+// the candidates of the stage, adding its share of every candidate's distortion to sums[request][candidate].
+// One thread per request then replays JM's sequential strict-'<' selection (me_fullsearch.c:221-289).
+constexpr int RT = 128, RQ = 41;
 
-__global__ void __launch_bounds__(256)
+struct RefineS {
+  short pos_x, pos_y, pred_x, pred_y;
+  int mvx, mvy;
+  long long min_mcost;
+  int lam_h, lam_q;
+  unsigned char blocktype, ref, flags, nsub, n, nsx;
+  int first;                  // index of the request's first work item
+};
+
+__global__ void __launch_bounds__(RT)
 k_subpel_refine(const jmb_me_req *__restrict__ reqs, jmb_me_res *__restrict__ res, int n, const uint8_t *__restrict__ cur, int cur_pitch,
                 const uint8_t *const *__restrict__ ref_planes, size_t plane_bytes, int ref_pitch, int w, int h, jmb_me_config me) {
-  __shared__ int s_sums[8][12];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = blockIdx.x * 8 + warp;
-  if (i >= n) return;
-  const jmb_me_req r = reqs[i];
-  if (!(r.flags & JMB_REQ_SUBPEL)) return;
-  RefView rv{ref_planes[r.ref], plane_bytes, ref_pitch, w, h};
-  int mvx, mvy; long long min_mcost;
+  __shared__ RefineS sr[RQ];
+  __shared__ int sums[RQ][9];
+  __shared__ int s_total;
+  const int tid = threadIdx.x, base = blockIdx.x * RQ, cnt = min(RQ, n - base);
   const long long DISTBLK_MAX = (long long)0x7fffffff << 5;     // lencod/inc/defines.h:136
-  if (r.flags & JMB_REQ_SKIP_INT) { mvx = r.center_x; mvy = r.center_y; min_mcost = r.min_mcost; }
-  else {
-    mvx = res[i].imv_x; mvy = res[i].imv_y; min_mcost = res[i].icost;
-    if (!me.start_hp) min_mcost = DISTBLK_MAX;                  // BlockMotionSearch, mv_search.c:971-974
+
+  if (tid < cnt) {
+    const jmb_me_req r = reqs[base + tid];
+    RefineS q;
+    q.pos_x = r.pos_x; q.pos_y = r.pos_y; q.pred_x = r.pred_x; q.pred_y = r.pred_y;
+    q.lam_h = r.lambda[1]; q.lam_q = r.lambda[2];
+    q.blocktype = r.blocktype; q.ref = r.ref; q.flags = r.flags;
+    q.nsub = 0; q.n = 4; q.nsx = 1; q.first = 0; q.mvx = q.mvy = 0; q.min_mcost = 0;
+    if (r.flags & JMB_REQ_SUBPEL) {
+      if (r.flags & JMB_REQ_SKIP_INT) { q.mvx = r.center_x; q.mvy = r.center_y; q.min_mcost = r.min_mcost; }
+      else {
+        const jmb_me_res o = res[base + tid];
+        q.mvx = o.imv_x; q.mvy = o.imv_y; q.min_mcost = o.icost;
+        if (!me.start_hp) q.min_mcost = DISTBLK_MAX;                  // BlockMotionSearch, mv_search.c:971-974
+      }
+    }
+    sr[tid] = q;
   }
-  const int max_pos2 = !me.start_hp ? max(1, me.search_pos2) : me.search_pos2;
-  refine_stage(rv, cur, cur_pitch, r, lane, s_sums[warp], 2, me.start_hp, max_pos2, me.metric[1], r.lambda[1], mvx, mvy, min_mcost);
-  if (!me.start_qp) min_mcost = DISTBLK_MAX;
-  refine_stage(rv, cur, cur_pitch, r, lane, s_sums[warp], 1, me.start_qp, me.search_pos4, me.metric[2], r.lambda[2], mvx, mvy, min_mcost);
-  if (lane == 0) { res[i].mv_x = (int16_t)mvx; res[i].mv_y = (int16_t)mvy; res[i].cost = min_mcost; }
+  __syncthreads();
+
+#pragma unroll 1
+  for (int stage = 0; stage < 2; stage++) {
+    const int metric = me.metric[1 + stage], step = stage ? 1 : 2;
+    const int pos0 = stage ? me.start_qp : me.start_hp;
+    const int pos1 = stage ? me.search_pos4 : (!me.start_hp ? max(1, me.search_pos2) : me.search_pos2);
+    if (tid == 0) {       // work items of this stage (the sub-block size depends on the stage's metric)
+      int tot = 0;
+      for (int i = 0; i < cnt; i++) {
+        RefineS &q = sr[i];
+        q.first = tot;
+        if (q.flags & JMB_REQ_SUBPEL) {
+          const int nn = (metric == JMB_SATD && (q.flags & JMB_REQ_TEST8X8)) ? 8 : 4;
+          q.n = (unsigned char)nn; q.nsx = (unsigned char)(c_bsx[q.blocktype] / nn);
+          q.nsub = (unsigned char)(q.nsx * (c_bsy[q.blocktype] / nn));
+          tot += q.nsub;
+        } else q.nsub = 0;
+      }
+      s_total = tot;
+    }
+    for (int i = tid; i < cnt * 9; i += RT) (&sums[0][0])[i] = 0;
+    __syncthreads();
+    const int total = s_total;
+    for (int item = tid; item < total; item += RT) {
+      int lo = 0, hi = cnt - 1;                        // last request whose first item is <= item
+      while (lo < hi) { const int m = (lo + hi + 1) >> 1; if (sr[m].first <= item) lo = m; else hi = m - 1; }
+      while (sr[lo].nsub == 0) lo--;                   // skip inactive requests that share the same first index
+      const RefineS &q = sr[lo];
+      const int sb = item - q.first, nn = q.n, sbx = sb % q.nsx, sby = sb / q.nsx;
+      RefView rv{ref_planes[q.ref], plane_bytes, ref_pitch, w, h};
+      SrcBlk src;
+      load_src(src, cur, cur_pitch, q.pos_x + sbx * nn, q.pos_y + sby * nn, nn);
+      for (int pos = pos0; pos < pos1; pos++) {
+        const int cqx = (q.pos_x << 2) + q.mvx + step * c_spiral9[pos][0], cqy = (q.pos_y << 2) + q.mvy + step * c_spiral9[pos][1];
+        const int d = (nn == 4) ? subblock_dist(rv, src, cqx, cqy, sbx, sby, 4, metric) : subblock_dist(rv, src, cqx, cqy, sbx, sby, 8, metric);
+        atomicAdd(&sums[lo][pos], d);
+      }
+    }
+    __syncthreads();
+    if (tid < cnt && (sr[tid].flags & JMB_REQ_SUBPEL)) {
+      RefineS &q = sr[tid];
+      if (stage == 1 && !me.start_qp) q.min_mcost = DISTBLK_MAX;
+      const int lam = stage ? q.lam_q : q.lam_h;
+      int best = 0;
+      for (int pos = pos0; pos < pos1; pos++) {
+        const int cx = q.mvx + step * c_spiral9[pos][0], cy = q.mvy + step * c_spiral9[pos][1];
+        long long mc = (long long)lam * (jmb_mvbits(cx - q.pred_x) + jmb_mvbits(cy - q.pred_y));
+        if (mc >= q.min_mcost) continue;
+        mc += (long long)sums[tid][pos] << 5;
+        if (mc < q.min_mcost) { q.min_mcost = mc; best = pos; }
+      }
+      q.mvx += step * c_spiral9[best][0]; q.mvy += step * c_spiral9[best][1];
+    }
+    __syncthreads();
+  }
+  if (tid < cnt && (sr[tid].flags & JMB_REQ_SUBPEL)) {
+    res[base + tid].mv_x = (int16_t)sr[tid].mvx; res[base + tid].mv_y = (int16_t)sr[tid].mvy; res[base + tid].cost = sr[tid].min_mcost;
+  }
 }
 
 __global__ void k_dist(const uint8_t *__restrict__ cur, int cur_pitch, RefView rv, int blocktype, int pos_x, int pos_y,
@@ -164,16 +240,18 @@ __global__ void k_dist(const uint8_t *__restrict__ cur, int cur_pitch, RefView r
   const int it = blockIdx.x * blockDim.x + threadIdx.x;
   if (it >= ncand * nsub) return;
   const int c = it / nsub, sb = it - c * nsub;
-  int d = subblock_dist(rv, cur, cur_pitch, pos_x, pos_y, cand[2 * c], cand[2 * c + 1], sb % nsx, sb / nsx, n, metric);
+  SrcBlk src;
+  load_src(src, cur, cur_pitch, pos_x + (sb % nsx) * n, pos_y + (sb / nsx) * n, n);
+  const int d = (n == 4) ? subblock_dist(rv, src, cand[2 * c], cand[2 * c + 1], sb % nsx, sb / nsx, 4, metric)
+                         : subblock_dist(rv, src, cand[2 * c], cand[2 * c + 1], sb % nsx, sb / nsx, 8, metric);
   atomicAdd(&out[c], d);
 }
-
 }  // namespace
 
 int jmb_launch_refine(jmb_ctx *ctx, const jmb_me_req *d_reqs, jmb_me_res *d_res, int n, const uint8_t *const *d_ref_planes) {
   const jmb_ref &r0 = ctx->refs[ctx->ref_list[0]];
   jmb_time_begin(ctx, JMB_K_REFINE);
-  k_subpel_refine<<<(n + 7) / 8, 256, 0, ctx->stream>>>(d_reqs, d_res, n, ctx->cur, ctx->cur_pitch, d_ref_planes, r0.plane_bytes,
+  k_subpel_refine<<<(n + RQ - 1) / RQ, RT, 0, ctx->stream>>>(d_reqs, d_res, n, ctx->cur, ctx->cur_pitch, d_ref_planes, r0.plane_bytes,
                                                         r0.pitch, ctx->cur_w, ctx->cur_h, ctx->me);
   jmb_time_end(ctx, JMB_K_REFINE);
   JMB_LAUNCH_CHECK(ctx);
