@@ -183,13 +183,17 @@ int jmb_quant_blocks(jmb_ctx *ctx, const jmb_quant_desc *q, int do_transform, in
  *   levels [n_mb][256] int16: quantised levels, per 4x4 (or 8x8) block in scan order
  *                              (4x4: block b = by*4+bx at [b*16 + k]; 8x8: block b8 at [b8*64 + k])
  *   coeff_cost [n_mb][4] int32 per 8x8 quadrant, cbp_blk [n_mb] uint32: bit b set if 4x4 block b has a
- *   nonzero level (8x8 transform: bits of the quadrant set together, macroblock.c:1004) */
+ *   nonzero level (8x8 transform: bits of the quadrant set together, macroblock.c:1004)
+ *   pred == NULL: use the prediction table the last jmb_pred_from_results(..., pred = NULL, ...) call left
+ *   on the device (no host round trip of an intermediate JM itself only keeps in all_mv). */
 int jmb_mc_tq(jmb_ctx *ctx, const jmb_mb_pred *pred, int n_mb, const jmb_quant_desc *q,
               int16_t *levels, int32_t *coeff_cost, uint32_t *cbp_blk, int loc);
 
 /* all_mv fill of BlockMotionSearch (lencod/src/mv_search.c:1005-1014): turn the results of a
  * jmb_me_search_frame call (41 per macroblock, canonical order) into the jmb_mb_pred of partition
- * mode `mode` (1..7) for every macroblock, reference 0. */
+ * mode `mode` (1..7) for every macroblock, reference 0.
+ *   res == NULL : use the results of the last jmb_me_search / jmb_me_search_frame call, still resident on the device;
+ *   pred == NULL: keep the table on the device for jmb_mc_tq(pred = NULL). */
 int jmb_pred_from_results(jmb_ctx *ctx, const jmb_me_res *res, int n_mb, int mode, jmb_mb_pred *pred, int loc);
 
 /* ---- measurement: CUDA events recorded on the context's stream around every kernel launch ----- */

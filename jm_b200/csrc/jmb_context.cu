@@ -49,6 +49,21 @@ void jmb_time_end(jmb_ctx *ctx, int kid) {
   ctx->ev_n[kid]++;
 }
 
+// Reads the device-side validation word (and clears it).  Called by every entry point that synchronises.
+int jmb_check_device_errors(jmb_ctx *ctx) {
+  JMB_CUDA(ctx, cudaMemcpyAsync(ctx->h_err, ctx->d_err, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->h_err[0]) {
+    const int code = ctx->h_err[0], idx = ctx->h_err[1];
+    JMB_CUDA(ctx, cudaMemsetAsync(ctx->d_err, 0, 2 * sizeof(int), ctx->stream));
+    return jmb_fail(ctx, JMB_ERR_ARG, "motion-search request %d rejected on the device (code 0x%x:%s%s%s%s%s%s%s%s); its result was not written", idx, code,
+                    code & JMB_REQERR_BLOCKTYPE ? " blocktype" : "", code & JMB_REQERR_REF ? " ref" : "", code & JMB_REQERR_POS ? " position/alignment" : "",
+                    code & JMB_REQERR_CENTER ? " centre-not-integer-pel" : "", code & JMB_REQERR_MODE ? " mode" : "", code & JMB_REQERR_LAMBDA ? " lambda" : "",
+                    code & JMB_REQERR_MINCOST ? " min_mcost" : "", code & JMB_REQERR_LAYOUT ? " frame-layout" : "");
+  }
+  return JMB_OK;
+}
+
 extern "C" {
 
 static const char *k_names[JMB_K_COUNT] = {"subpel_planes", "pack_cur", "int_search", "subpel_refine", "dist", "ffs_surfaces",
@@ -106,6 +121,13 @@ int jmb_create(int device, jmb_ctx **out) {
   ctx->me.search_range = 32; ctx->me.max_mvd = 1023;
   ctx->me.metric[0] = JMB_SAD; ctx->me.metric[1] = JMB_SATD; ctx->me.metric[2] = JMB_SATD;
   ctx->me.start_hp = 0; ctx->me.start_qp = 1; ctx->me.search_pos2 = 9; ctx->me.search_pos4 = 9;
+  if (cudaMalloc(&ctx->d_err, 2 * sizeof(int)) != cudaSuccess || cudaMemset(ctx->d_err, 0, 2 * sizeof(int)) != cudaSuccess ||
+      cudaHostAlloc(&ctx->h_err, 2 * sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
+    jmb_fail(nullptr, JMB_ERR_CUDA, "jmb_create: cannot allocate the error word: %s", cudaGetErrorString(cudaGetLastError()));
+    jmb_destroy(ctx);
+    return JMB_ERR_CUDA;
+  }
+  ctx->h_err[0] = ctx->h_err[1] = 0;
   *out = ctx;
   return JMB_OK;
 }
@@ -126,13 +148,16 @@ void jmb_destroy(jmb_ctx *ctx) {
   if (ctx->d_stage3) cudaFree(ctx->d_stage3);
   if (ctx->d_stage4) cudaFree(ctx->d_stage4);
   if (ctx->d_stage5) cudaFree(ctx->d_stage5);
+  if (ctx->d_res_keep) cudaFree(ctx->d_res_keep);
+  if (ctx->d_pred_keep) cudaFree(ctx->d_pred_keep);
+  if (ctx->d_err) cudaFree(ctx->d_err);
+  if (ctx->h_err) cudaFreeHost(ctx->h_err);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
 
 int jmb_sync(jmb_ctx *ctx) {
-  JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return JMB_OK;
+  return jmb_check_device_errors(ctx);
 }
 
 void *jmb_stream(jmb_ctx *ctx) { return (void *)ctx->stream; }

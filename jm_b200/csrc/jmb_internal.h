@@ -45,7 +45,14 @@ struct jmb_ctx {
   void *d_stage3 = nullptr; size_t d_stage3_cap = 0;
   void *d_stage4 = nullptr; size_t d_stage4_cap = 0;
   void *d_stage5 = nullptr; size_t d_stage5_cap = 0;
+  // context-resident intermediates (NULL arguments of jmb_pred_from_results / jmb_mc_tq refer to them)
+  void *d_res_keep = nullptr; size_t d_res_keep_cap = 0; const jmb_me_res *last_res = nullptr; int last_res_n = 0;
+  void *d_pred_keep = nullptr; size_t d_pred_keep_cap = 0; int pred_keep_n = 0;
+  // request validation happens on the device (the requests may live there); the kernels OR a JMB_REQERR_* code and the
+  // index of one offending request into d_err[0..1], which every synchronising call reads back
+  int *d_err = nullptr; int *h_err = nullptr;
 };
+int jmb_check_device_errors(jmb_ctx *ctx);   // after a stream synchronisation
 
 int jmb_fail(jmb_ctx *ctx, int code, const char *fmt, ...);
 int jmb_reserve_host(jmb_ctx *ctx, void **p, size_t *cap, size_t bytes);
@@ -87,6 +94,26 @@ __device__ __forceinline__ int jmb_spiral_index(int dx, int dy) {
   int base = (2 * l - 1) * (2 * l - 1);
   if (abs(dy) == l && abs(dx) < l) return base + 2 * (dx + l - 1) + (dy > 0);
   return base + 2 * (2 * l - 1) + 2 * (dy + l) + (dx > 0);
+}
+
+// request validation shared by the search and refinement kernels; 0 = fine
+enum { JMB_REQERR_BLOCKTYPE = 1, JMB_REQERR_REF = 2, JMB_REQERR_POS = 4, JMB_REQERR_CENTER = 8, JMB_REQERR_MODE = 16,
+       JMB_REQERR_LAMBDA = 32, JMB_REQERR_MINCOST = 64, JMB_REQERR_LAYOUT = 128 };
+__device__ __forceinline__ int jmb_req_check(const jmb_me_req &r, int w, int h, int nref) {
+  if (r.blocktype < 1 || r.blocktype > 7) return JMB_REQERR_BLOCKTYPE;
+  const int bsx = (r.blocktype <= 2) ? 16 : (r.blocktype <= 5 ? 8 : 4);
+  const int bsy = (r.blocktype == 1 || r.blocktype == 3) ? 16 : ((r.blocktype == 2 || r.blocktype == 4 || r.blocktype == 6) ? 8 : 4);
+  int e = 0;
+  if (r.ref >= nref) e |= JMB_REQERR_REF;
+  if (r.pos_x < 0 || r.pos_y < 0 || r.pos_x + bsx > w || r.pos_y + bsy > h || (r.pos_x % bsx) || (r.pos_y % bsy)) e |= JMB_REQERR_POS;
+  if (!(r.flags & JMB_REQ_SKIP_INT) && ((r.center_x | r.center_y) & 3)) e |= JMB_REQERR_CENTER;
+  if (r.mode > JMB_SEARCH_FAST_FULL) e |= JMB_REQERR_MODE;
+  if ((unsigned)r.lambda[0] > 65535u || (unsigned)r.lambda[1] > 65535u || (unsigned)r.lambda[2] > 65535u) e |= JMB_REQERR_LAMBDA;
+  if (r.min_mcost < 0 || r.min_mcost > ((long long)1 << 48)) e |= JMB_REQERR_MINCOST;
+  return e;
+}
+__device__ __forceinline__ void jmb_req_report(int *err, int code, int index) {
+  if (code) { atomicOr(&err[0], code); err[1] = index; }
 }
 
 // kernels (defined in k_*.cu), launched through these host wrappers

@@ -147,7 +147,7 @@ struct RefineS {
 
 __global__ void __launch_bounds__(RT)
 k_subpel_refine(const jmb_me_req *__restrict__ reqs, jmb_me_res *__restrict__ res, int n, const uint8_t *__restrict__ cur, int cur_pitch,
-                const uint8_t *const *__restrict__ ref_planes, size_t plane_bytes, int ref_pitch, int w, int h, jmb_me_config me) {
+                const uint8_t *const *__restrict__ ref_planes, size_t plane_bytes, int ref_pitch, int w, int h, jmb_me_config me, int nref, int *__restrict__ err) {
   __shared__ RefineS sr[RQ];
   __shared__ int sums[RQ][9];
   __shared__ int s_total;
@@ -161,7 +161,10 @@ k_subpel_refine(const jmb_me_req *__restrict__ reqs, jmb_me_res *__restrict__ re
     q.lam_h = r.lambda[1]; q.lam_q = r.lambda[2];
     q.blocktype = r.blocktype; q.ref = r.ref; q.flags = r.flags;
     q.nsub = 0; q.n = 4; q.nsx = 1; q.first = 0; q.mvx = q.mvy = 0; q.min_mcost = 0;
-    if (r.flags & JMB_REQ_SUBPEL) {
+    const int bad = jmb_req_check(r, w, h, nref);
+    jmb_req_report(err, bad, base + tid);
+    if (bad) q.flags = 0;
+    else if (r.flags & JMB_REQ_SUBPEL) {
       if (r.flags & JMB_REQ_SKIP_INT) { q.mvx = r.center_x; q.mvy = r.center_y; q.min_mcost = r.min_mcost; }
       else {
         const jmb_me_res o = res[base + tid];
@@ -252,7 +255,7 @@ int jmb_launch_refine(jmb_ctx *ctx, const jmb_me_req *d_reqs, jmb_me_res *d_res,
   const jmb_ref &r0 = ctx->refs[ctx->ref_list[0]];
   jmb_time_begin(ctx, JMB_K_REFINE);
   k_subpel_refine<<<(n + RQ - 1) / RQ, RT, 0, ctx->stream>>>(d_reqs, d_res, n, ctx->cur, ctx->cur_pitch, d_ref_planes, r0.plane_bytes,
-                                                        r0.pitch, ctx->cur_w, ctx->cur_h, ctx->me);
+                                                        r0.pitch, ctx->cur_w, ctx->cur_h, ctx->me, ctx->nref, ctx->d_err);
   jmb_time_end(ctx, JMB_K_REFINE);
   JMB_LAUNCH_CHECK(ctx);
   return JMB_OK;

@@ -202,7 +202,7 @@ __device__ __forceinline__ void sad_item(const uint8_t *win, const unsigned *ssr
 __global__ void __launch_bounds__(NT, JMB_IS_MINB)
 k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups, jmb_me_res *__restrict__ res,
              const uint8_t *__restrict__ cur, int cur_pitch,
-             const uint8_t *const *__restrict__ ref_planes, int ref_pitch, int w, int h, int R, int max_mvd_m1) {
+             const uint8_t *const *__restrict__ ref_planes, int ref_pitch, int w, int h, int R, int max_mvd_m1, int nref, int *__restrict__ err) {
   __shared__ Grp G;
   __shared__ __align__(16) uint8_t win[WIN_ROWS * WIN_PITCH];
   __shared__ __align__(16) unsigned ssrc[16 * 4];
@@ -223,7 +223,15 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
     ReqS q; q.active = 0; q.req = ri;
     if (ri >= 0) {
       jmb_me_req r = reqs[ri];
-      if (!(r.flags & JMB_REQ_SKIP_INT)) {
+      int bad = jmb_req_check(r, w, h, nref);
+      if (!bad && !groups) {      // frame layout: request k of a group must be partition k of one macroblock and reference
+        const PartGeom pg = c_part[tid];
+        const jmb_me_req r0 = reqs[g * NPART];
+        if (r.blocktype != pg.type || (r.pos_x & 15) != pg.bx * 4 || (r.pos_y & 15) != pg.by * 4 || ((r.pos_x ^ r0.pos_x) & ~15) ||
+            ((r.pos_y ^ r0.pos_y) & ~15) || r.ref != r0.ref) bad = JMB_REQERR_LAYOUT;
+      }
+      jmb_req_report(err, bad, ri);
+      if (!bad && !(r.flags & JMB_REQ_SKIP_INT)) {
         q.active = 1;
         q.ffs = (r.mode == JMB_SEARCH_FAST_FULL);
         int ox = q.ffs ? (r.pos_x & ~15) : r.pos_x, oy = q.ffs ? (r.pos_y & ~15) : r.pos_y;   // clamped origin
@@ -522,18 +530,14 @@ static int me_search_impl(jmb_ctx *ctx, const jmb_me_req *reqs, int n, jmb_me_re
     JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     h_reqs = (const jmb_me_req *)ctx->h_stage;
   }
-  if (h_reqs) {
+  // the frame layout is validated on the device (jmb_req_check); ungrouped requests are walked here anyway
+  if (h_reqs && !frame_layout) {
     for (int i = 0; i < n; i++) { rc = validate_req(ctx, h_reqs[i], i); if (rc) return rc; any_subpel |= (h_reqs[i].flags & JMB_REQ_SUBPEL) != 0; }
   } else any_subpel = true;
 
   if (frame_layout) {
     if (n % NPART) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_me_search_frame: n=%d is not a multiple of 41", n);
     n_groups = n / NPART;
-    if (h_reqs)
-      for (int i = 0; i < n; i++)
-        if (part_slot(h_reqs[i]) != i % NPART || (h_reqs[i].pos_x & ~15) != (h_reqs[i - i % NPART].pos_x & ~15) ||
-            (h_reqs[i].pos_y & ~15) != (h_reqs[i - i % NPART].pos_y & ~15) || h_reqs[i].ref != h_reqs[i - i % NPART].ref)
-          return jmb_fail(ctx, JMB_ERR_ARG, "jmb_me_search_frame: request %d is not partition %d of its macroblock", i, i % NPART);
   } else {
     // consecutive requests of one (macroblock, ref) form a group; a repeated partition starts a new one
     rc = jmb_reserve_host(ctx, &ctx->h_groups, &ctx->h_groups_cap, (size_t)n * NPART * sizeof(int)); if (rc) return rc;
@@ -555,19 +559,20 @@ static int me_search_impl(jmb_ctx *ctx, const jmb_me_req *reqs, int n, jmb_me_re
   }
   if (loc == JMB_HOST) {
     rc = jmb_reserve_dev(ctx, &ctx->d_stage, &ctx->d_stage_cap, (size_t)n * sizeof(jmb_me_req)); if (rc) return rc;
-    rc = jmb_reserve_dev(ctx, &ctx->d_stage2, &ctx->d_stage2_cap, (size_t)n * sizeof(jmb_me_res)); if (rc) return rc;
+    rc = jmb_reserve_dev(ctx, &ctx->d_res_keep, &ctx->d_res_keep_cap, (size_t)n * sizeof(jmb_me_res)); if (rc) return rc;
     JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage, reqs, (size_t)n * sizeof(jmb_me_req), cudaMemcpyHostToDevice, ctx->stream));
-    d_reqs = (const jmb_me_req *)ctx->d_stage; d_res = (jmb_me_res *)ctx->d_stage2;
+    d_reqs = (const jmb_me_req *)ctx->d_stage; d_res = (jmb_me_res *)ctx->d_res_keep;
   }
   jmb_time_begin(ctx, JMB_K_INT_SEARCH);
   k_int_search<<<n_groups, NT, 0, ctx->stream>>>(d_reqs, d_groups, d_res, ctx->cur, ctx->cur_pitch, d_tab, r0.pitch,
-                                                  ctx->cur_w, ctx->cur_h, ctx->me.search_range, ctx->me.max_mvd - 1);
+                                                  ctx->cur_w, ctx->cur_h, ctx->me.search_range, ctx->me.max_mvd - 1, ctx->nref, ctx->d_err);
   jmb_time_end(ctx, JMB_K_INT_SEARCH);
   JMB_LAUNCH_CHECK(ctx);
   if (any_subpel) { rc = jmb_launch_refine(ctx, d_reqs, d_res, n, d_tab); if (rc) return rc; }
+  ctx->last_res = d_res; ctx->last_res_n = n;
   if (loc == JMB_HOST) {
     JMB_CUDA(ctx, cudaMemcpyAsync(res, d_res, (size_t)n * sizeof(jmb_me_res), cudaMemcpyDeviceToHost, ctx->stream));
-    JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return jmb_check_device_errors(ctx);
   }
   return JMB_OK;
 }

@@ -266,17 +266,23 @@ int jmb_pred_from_results(jmb_ctx *ctx, const jmb_me_res *res, int n_mb, int mod
   if (mode < 1 || mode > 7 || n_mb <= 0) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_pred_from_results: mode %d n_mb %d", mode, n_mb);
   JMB_CUDA(ctx, cudaSetDevice(ctx->device));
   const jmb_me_res *d_res = res; jmb_mb_pred *d_pred = pred;
-  if (loc == JMB_HOST) {
+  if (!res) {          // the results of the last search call, still on the device
+    if (!ctx->last_res || ctx->last_res_n < n_mb * 41) return jmb_fail(ctx, JMB_ERR_STATE, "jmb_pred_from_results: no resident search results for %d macroblocks", n_mb);
+    d_res = ctx->last_res;
+  } else if (loc == JMB_HOST) {
     int rc = jmb_reserve_dev(ctx, &ctx->d_stage4, &ctx->d_stage4_cap, (size_t)n_mb * 41 * sizeof(jmb_me_res)); if (rc) return rc;
-    rc = jmb_reserve_dev(ctx, &ctx->d_stage5, &ctx->d_stage5_cap, (size_t)n_mb * sizeof(jmb_mb_pred)); if (rc) return rc;
     JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage4, res, (size_t)n_mb * 41 * sizeof(jmb_me_res), cudaMemcpyHostToDevice, ctx->stream));
-    d_res = (const jmb_me_res *)ctx->d_stage4; d_pred = (jmb_mb_pred *)ctx->d_stage5;
+    d_res = (const jmb_me_res *)ctx->d_stage4;
+  }
+  if (!pred || loc == JMB_HOST) {   // keep the prediction table in the context (jmb_mc_tq(pred = NULL) reads it)
+    int rc = jmb_reserve_dev(ctx, &ctx->d_pred_keep, &ctx->d_pred_keep_cap, (size_t)n_mb * sizeof(jmb_mb_pred)); if (rc) return rc;
+    d_pred = (jmb_mb_pred *)ctx->d_pred_keep; ctx->pred_keep_n = n_mb;
   }
   jmb_time_begin(ctx, JMB_K_PRED);
   k_pred_from_results<<<(n_mb * 16 + 255) / 256, 256, 0, ctx->stream>>>(d_res, n_mb, mode, d_pred);
   jmb_time_end(ctx, JMB_K_PRED);
   JMB_LAUNCH_CHECK(ctx);
-  if (loc == JMB_HOST) {
+  if (pred && loc == JMB_HOST) {
     JMB_CUDA(ctx, cudaMemcpyAsync(pred, d_pred, (size_t)n_mb * sizeof(jmb_mb_pred), cudaMemcpyDeviceToHost, ctx->stream));
     JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
@@ -297,15 +303,21 @@ int jmb_mc_tq(jmb_ctx *ctx, const jmb_mb_pred *pred, int n_mb, const jmb_quant_d
   JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_reftab, tab, sizeof(tab), cudaMemcpyHostToDevice, ctx->stream));
   const jmb_quant_desc *d_q; rc = upload_qdesc(ctx, q, &d_q); if (rc) return rc;
   const jmb_mb_pred *d_pred = pred; int16_t *d_lv = levels; int *d_cc = coeff_cost; unsigned *d_cbp = cbp_blk;
+  if (!pred) {
+    if (!ctx->d_pred_keep || ctx->pred_keep_n < n_mb) return jmb_fail(ctx, JMB_ERR_STATE, "jmb_mc_tq: no resident prediction table for %d macroblocks", n_mb);
+    d_pred = (const jmb_mb_pred *)ctx->d_pred_keep;
+  }
   if (loc == JMB_HOST) {
-    for (int i = 0; i < n_mb; i++)
+    if (pred) for (int i = 0; i < n_mb; i++)
       for (int k = 0; k < 4; k++)
         if (pred[i].b8mode[k] < 1 || pred[i].b8mode[k] > 7 || pred[i].ref[k] >= ctx->nref)
           return jmb_fail(ctx, JMB_ERR_ARG, "jmb_mc_tq: macroblock %d quadrant %d: mode %d ref %d", i, k, pred[i].b8mode[k], pred[i].ref[k]);
-    rc = jmb_reserve_dev(ctx, &ctx->d_stage, &ctx->d_stage_cap, (size_t)n_mb * sizeof(jmb_mb_pred)); if (rc) return rc;
     rc = jmb_reserve_dev(ctx, &ctx->d_stage3, &ctx->d_stage3_cap, (size_t)n_mb * (512 + 16 + 4)); if (rc) return rc;
-    JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage, pred, (size_t)n_mb * sizeof(jmb_mb_pred), cudaMemcpyHostToDevice, ctx->stream));
-    d_pred = (const jmb_mb_pred *)ctx->d_stage;
+    if (pred) {
+      rc = jmb_reserve_dev(ctx, &ctx->d_stage, &ctx->d_stage_cap, (size_t)n_mb * sizeof(jmb_mb_pred)); if (rc) return rc;
+      JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage, pred, (size_t)n_mb * sizeof(jmb_mb_pred), cudaMemcpyHostToDevice, ctx->stream));
+      d_pred = (const jmb_mb_pred *)ctx->d_stage;
+    }
     d_lv = (int16_t *)ctx->d_stage3; d_cc = (int *)((char *)ctx->d_stage3 + (size_t)n_mb * 512); d_cbp = (unsigned *)(d_cc + (size_t)n_mb * 4);
   }
   JMB_CUDA(ctx, cudaMemsetAsync(d_cc, 0, (size_t)n_mb * 16, ctx->stream));

@@ -323,3 +323,40 @@ def test_errors_are_loud(ctx):
     ctx.ref_put(0, np.zeros((32, 32), np.uint16)); ctx.pic_begin(np.zeros((32, 32), np.uint16), [0])
     with pytest.raises(api.JMBError):
         ctx.me_search(bad)
+    # the frame layout is validated on the device: a wrong partition order / a bad field is reported, not computed
+    ctx.configure(search_range=4)
+    good = _frame_reqs(32, 32, np.random.default_rng(0), api.SEARCH_FULL, api.REQ_SUBPEL, lam=10)
+    ctx.me_search(good, frame=True)
+    swapped = good.copy(); swapped[[3, 4]] = swapped[[4, 3]]
+    with pytest.raises(api.JMBError, match="frame-layout"):
+        ctx.me_search(swapped, frame=True)
+    badlam = good.copy(); badlam["lambda"][50] = 1 << 20
+    with pytest.raises(api.JMBError, match="lambda"):
+        ctx.me_search(badlam, frame=True)
+    ctx.me_search(good, frame=True)        # the error word is cleared once reported
+
+
+def test_pred_from_results_and_resident_chain(ctx, oracle):
+    """all_mv fill (mv_search.c:1005-1014) on the device, and the host-buffer-free chain
+    me_search_frame -> pred_from_results(NULL, NULL) -> mc_tq(NULL) gives what the explicit chain gives."""
+    w, h, R = 64, 48, 8
+    f = _frames(w, h, 21, motion=(2, 1))
+    ctx.configure(search_range=R)
+    ctx.ref_put(0, f[0]); ctx.pic_begin(f[1], [0])
+    rng = np.random.default_rng(21)
+    reqs = _frame_reqs(w, h, rng, api.SEARCH_FULL, api.REQ_SUBPEL, lam=40)
+    res = ctx.me_search(reqs, frame=True)
+    n_mb = len(reqs) // api.NPART
+    qd = api.quant_desc(4, 30, T.q_params(30, 0, 4), T.SNGL_SCAN, T.COEFF_COST4x4[0], 1)
+    r = res.reshape(n_mb, api.NPART)
+    for mode in range(1, 8):
+        pred = ctx.pred_from_results(res, mode)
+        for b in range(16):
+            slot = api.part_slot(mode, b & 3, b >> 2)
+            assert np.array_equal(pred["mv"][:, b, 0], r["mv_x"][:, slot]) and np.array_equal(pred["mv"][:, b, 1], r["mv_y"][:, slot])
+        assert (pred["b8mode"] == mode).all() and (pred["ref"] == 0).all()
+        want = ctx.mc_tq(pred, qd)
+        ctx._ck(ctx.L.jmb_pred_from_results(ctx.h, None, n_mb, mode, None, api.HOST))
+        lv = np.zeros((n_mb, 256), np.int16); cc = np.zeros((n_mb, 4), np.int32); cbp = np.zeros(n_mb, np.uint32)
+        ctx._ck(ctx.L.jmb_mc_tq(ctx.h, None, n_mb, qd.ctypes.data, lv.ctypes.data, cc.ctypes.data, cbp.ctypes.data, api.HOST))
+        assert np.array_equal(lv, want[0]) and np.array_equal(cc, want[1]) and np.array_equal(cbp, want[2])
