@@ -1,0 +1,498 @@
+/*
+ * jm_wrap.c -- the reference-side binding of libjmb200: GNU ld --wrap stubs that sit behind JM 19.0
+ * lencod's own call sites and forward them to the C ABI in include/jmb200.h.
+ *
+ * Compiled with JM's own headers and flags (gcc -std=gnu99 -fsigned-char ...) and linked with JM's
+ * UNMODIFIED objects:
+ *
+ *   gcc -o lencod_jmb  <all lencod/lcommon objects>  jm_wrap.o  -ljmb200 -lm \
+ *       -Wl,--wrap=getSubImagesLuma -Wl,--wrap=encode_one_slice \
+ *       -Wl,--wrap=full_search_motion_estimation -Wl,--wrap=fast_full_search_motion_estimation \
+ *       -Wl,--wrap=setup_fast_full_search -Wl,--wrap=sub_pel_motion_estimation \
+ *       -Wl,--wrap=forward4x4 -Wl,--wrap=forward8x8 \
+ *       -Wl,--wrap=quant_4x4_normal -Wl,--wrap=quant_4x4_around \
+ *       -Wl,--wrap=quant_8x8_normal -Wl,--wrap=quant_8x8_around \
+ *       -Wl,--wrap=quant_8x8cavlc_normal -Wl,--wrap=quant_8x8cavlc_around
+ *
+ * No JM source file is edited: every symbol above is defined in one translation unit and referenced
+ * from another, so the linker redirects the reference to __wrap_<sym>.
+ *
+ * What runs where: the arithmetic of every wrapped function runs on the GPU; this file only converts
+ * JM's row-pointer arrays and structs to the flat arguments of the ABI and back.  There is no CPU
+ * path behind the ABI.  The ONLY use of __real_<sym> is the explicit plumbing switch
+ * JMB_SHIM=passthrough (config 0 of BASELINE.json: proves the re-link itself is neutral) and the
+ * per-family bisect switches JMB_SHIM_OFF=planes,me,subpel,tq -- both are debugging aids, off by default.
+ * Unsupported configurations (field/MBAFF pictures, weighted-prediction ME, RDOptimization=0's (0,0)
+ * bias, chroma ME, on-the-fly interpolation) stop the encoder the way JM's own error() does: message on stderr, exit.
+ *
+ * Granularity: JM decides one block at a time (each search's predictor depends on the previous
+ * decisions), so this drop-in issues one small launch per leaf call.  It is the
+ * bit-exactness proof on JM's real call sequence; the throughput path is the whole-picture form of the
+ * same entry points (jmb_me_search_frame, jmb_mc_tq) that bench.py drives.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "global.h"
+#include "mbuffer.h"
+#include "mv_search.h"
+#include "me_fullsearch.h"
+#include "me_fullfast.h"
+#include "img_luma.h"
+#include "transform.h"
+#include "quant4x4.h"
+#include "quant8x8.h"
+#include "mv_prediction.h"
+
+#include "jmb200.h"
+
+/* ---- the symbols the linker leaves reachable under their real names ------------------------------ */
+void    __real_getSubImagesLuma(VideoParameters *p_Vid, StorablePicture *s);
+int     __real_encode_one_slice(VideoParameters *p_Vid, int SliceGroupId, int TotalCodedMBs);
+distblk __real_full_search_motion_estimation(Macroblock *, MotionVector *, MEBlock *, distblk, int);
+distblk __real_fast_full_search_motion_estimation(Macroblock *, MotionVector *, MEBlock *, distblk, int);
+void    __real_setup_fast_full_search(Macroblock *, MEBlock *, int);
+distblk __real_sub_pel_motion_estimation(Macroblock *, MotionVector *, MEBlock *, distblk, int *);
+void    __real_forward4x4(int **block, int **tblock, int pos_y, int pos_x);
+void    __real_forward8x8(int **block, int **tblock, int pos_y, int pos_x);
+int     __real_quant_4x4_normal(Macroblock *, int **, struct quant_methods *);
+int     __real_quant_4x4_around(Macroblock *, int **, struct quant_methods *);
+int     __real_quant_8x8_normal(Macroblock *, int **, struct quant_methods *);
+int     __real_quant_8x8_around(Macroblock *, int **, struct quant_methods *);
+int     __real_quant_8x8cavlc_normal(Macroblock *, int **, struct quant_methods *, int ***);
+int     __real_quant_8x8cavlc_around(Macroblock *, int **, struct quant_methods *, int ***);
+
+enum { FAM_PLANES = 1, FAM_ME = 2, FAM_SUBPEL = 4, FAM_TQ = 8 };
+
+static struct
+{
+  int              init;              /* 0 = not yet, 1 = GPU, 2 = passthrough */
+  int              off;               /* FAM_* families handed back to JM (bisecting only) */
+  jmb_ctx         *ctx;
+  StorablePicture *slot_pic[JMB_MAX_REFS];
+  unsigned long    slot_stamp[JMB_MAX_REFS];
+  unsigned long    stamp;
+  int              pic_valid;         /* jmb_pic_begin done for the current slice and reference set */
+  int              list[JMB_MAX_REFS], nlist;
+  jmb_me_config    cfg;
+  int              cfg_valid;
+  unsigned long    calls[8];
+} S;
+
+/* JM's convention for fatal conditions is error(text, code) -> message on stderr, exit(code) (lencod/src/lencod.c).
+ * JM's error() also flushes the DPB first, which re-enters the wrapped functions; the shim therefore prints the same
+ * way and exits itself. */
+static void fatal(int code)
+{
+  fprintf(stderr, "%s\n", errortext);
+  exit(code);
+}
+
+static void jmb_die(const char *what, int rc)
+{
+  snprintf(errortext, ET_SIZE, "libjmb200 shim: %s failed (%d): %s", what, rc, jmb_last_error(S.ctx));
+  fatal(700);
+}
+
+static void unsupported(const char *what)
+{
+  snprintf(errortext, ET_SIZE, "libjmb200 shim: %s is not supported by the GPU path (and there is no CPU fallback)", what);
+  fatal(701);
+}
+
+static void report(void)
+{
+  if (S.init == 1 && getenv("JMB_SHIM_VERBOSE"))
+    fprintf(stderr, "[jmb shim] planes %lu  full %lu  fastfull %lu  subpel %lu  fwd4 %lu  fwd8 %lu  quant4 %lu  quant8 %lu  kernel launches %llu\n",
+            S.calls[0], S.calls[1], S.calls[2], S.calls[3], S.calls[4], S.calls[5], S.calls[6], S.calls[7],
+            (unsigned long long)jmb_launch_count(S.ctx));
+}
+
+static int shim_on(int family)
+{
+  if (!S.init)
+  {
+    const char *m = getenv("JMB_SHIM"), *off = getenv("JMB_SHIM_OFF");
+    if (m && !strcmp(m, "passthrough"))
+      S.init = 2;
+    else
+    {
+      int dev = getenv("JMB_DEVICE") ? atoi(getenv("JMB_DEVICE")) : 0;
+      int rc = jmb_create(dev, &S.ctx);
+      if (rc)
+      {
+        snprintf(errortext, ET_SIZE, "libjmb200 shim: jmb_create(%d) failed (%d): %s", dev, rc, jmb_last_error(NULL));
+        fatal(700);
+      }
+      S.init = 1;
+      if (off)
+      {
+        if (strstr(off, "planes")) S.off |= FAM_PLANES;
+        if (strstr(off, "me"))     S.off |= FAM_ME;
+        if (strstr(off, "subpel")) S.off |= FAM_SUBPEL;
+        if (strstr(off, "tq"))     S.off |= FAM_TQ;
+      }
+      atexit(report);
+    }
+  }
+  return S.init == 1 && !(S.off & family);
+}
+
+/* ---- reference pictures ------------------------------------------------------------------------------
+ * key = StorablePicture*; a slot is recycled least-recently-registered first, and a picture whose slot
+ * was recycled is simply uploaded again when a search names it (JM owns the samples, we only cache). */
+static int put_ref(VideoParameters *p_Vid, StorablePicture *s)
+{
+  int i, slot = -1;
+  for (i = 0; i < JMB_MAX_REFS; i++)
+    if (S.slot_pic[i] == s) { slot = i; break; }
+  if (slot < 0)
+    for (i = 0; i < JMB_MAX_REFS; i++)
+      if (!S.slot_pic[i]) { slot = i; break; }
+  if (slot < 0)
+  {
+    slot = 0;
+    for (i = 1; i < JMB_MAX_REFS; i++)
+      if (S.slot_stamp[i] < S.slot_stamp[slot]) slot = i;
+  }
+  {
+    imgpel **img = s->p_curr_img;
+    int stride = (int)(img[1] - img[0]);
+    int rc = jmb_ref_put(S.ctx, slot, (const uint16_t *)&img[0][0], s->size_x, s->size_y, stride, p_Vid->bitdepth_luma, JMB_HOST);
+    if (rc) jmb_die("jmb_ref_put", rc);
+  }
+  S.slot_pic[slot] = s;
+  S.slot_stamp[slot] = ++S.stamp;
+  S.pic_valid = 0;
+  return slot;
+}
+
+/* stands behind getSubImagesLuma (lencod/src/img_luma.c:611), called from UnifiedOneForthPix (image.c:2187):
+ * the 16 quarter-pel planes are built on the device, kept there for the searches, and copied into JM's own
+ * imgY_sub planes because JM's untouched host code (luma_prediction, mode decision) reads them. */
+void __wrap_getSubImagesLuma(VideoParameters *p_Vid, StorablePicture *s)
+{
+  int fy, fx, slot;
+  if (!shim_on(FAM_PLANES)) { __real_getSubImagesLuma(p_Vid, s); return; }
+  if (p_Vid->p_Inp->OnTheFlyFractMCP) unsupported("OnTheFlyFractMCP");
+  if (s->p_curr_img != s->imgY || s->p_curr_img_sub != s->imgY_sub)
+  { /* 4:4:4 joint coding interpolates U and V through this function too: not part of the luma ME path */
+    unsupported("getSubImagesLuma on a chroma plane (4:4:4 joint)");
+  }
+  S.calls[0]++;
+  slot = put_ref(p_Vid, s);
+  for (fy = 0; fy < 4; fy++)
+    for (fx = 0; fx < 4; fx++)
+    { /* each plane is one calloc of (h+40) x (w+64) imgpel with biased row pointers (memalloc.c:881-904) */
+      imgpel *flat = &s->imgY_sub[fy][fx][-IMG_PAD_SIZE_Y][-IMG_PAD_SIZE_X];
+      int rc = jmb_ref_get_plane(S.ctx, slot, fy, fx, (uint16_t *)flat, JMB_HOST);
+      if (rc) jmb_die("jmb_ref_get_plane", rc);
+    }
+}
+
+/* a new slice: the current picture must be (re)sent before its first search */
+int __wrap_encode_one_slice(VideoParameters *p_Vid, int SliceGroupId, int TotalCodedMBs)
+{
+  S.pic_valid = 0;
+  return __real_encode_one_slice(p_Vid, SliceGroupId, TotalCodedMBs);
+}
+
+static int ref_index(Macroblock *currMB, MEBlock *mv_block)
+{
+  VideoParameters *p_Vid = currMB->p_Vid;
+  Slice *currSlice = currMB->p_Slice;
+  StorablePicture *ref_picture = currSlice->listX[mv_block->list + currMB->list_offset][mv_block->ref_idx];
+  int i, slot = -1;
+
+  if (p_Vid->structure != FRAME || currSlice->mb_aff_frame_flag) unsupported("field / MBAFF picture");
+  if (mv_block->ChromaMEEnable) unsupported("ChromaMEEnable");
+  if (mv_block->apply_weights) unsupported("weighted-prediction motion estimation");
+
+  for (i = 0; i < JMB_MAX_REFS; i++)
+    if (S.slot_pic[i] == ref_picture) { slot = i; break; }
+  if (slot < 0) slot = put_ref(p_Vid, ref_picture);        /* its slot was recycled: upload again */
+  else S.slot_stamp[slot] = ++S.stamp;
+
+  if (!S.pic_valid)
+  {
+    imgpel **cur = p_Vid->pCurImg;
+    int rc;
+    S.nlist = 0;
+    for (i = 0; i < JMB_MAX_REFS; i++)
+      if (S.slot_pic[i]) S.list[S.nlist++] = i;
+    rc = jmb_pic_begin(S.ctx, (const uint16_t *)&cur[0][0], p_Vid->width, p_Vid->height, (int)(cur[1] - cur[0]), JMB_HOST, S.list, S.nlist);
+    if (rc) jmb_die("jmb_pic_begin", rc);
+    S.pic_valid = 1;
+  }
+  for (i = 0; i < S.nlist; i++)
+    if (S.list[i] == slot) return i;
+  snprintf(errortext, ET_SIZE, "libjmb200 shim: reference picture not in the device list");
+  fatal(702);
+  return -1;
+}
+
+static void configure(Macroblock *currMB, MEBlock *mv_block, int search_range)
+{
+  VideoParameters *p_Vid = currMB->p_Vid;
+  InputParameters *p_Inp = currMB->p_Inp;
+  jmb_me_config c;
+  memset(&c, 0, sizeof(c));
+  c.search_range = search_range > 0 ? search_range : (S.cfg_valid ? S.cfg.search_range : p_Inp->search_range[0]);
+  c.max_mvd = p_Vid->max_mvd;
+  c.metric[0] = p_Inp->MEErrorMetric[F_PEL];
+  c.metric[1] = p_Inp->MEErrorMetric[H_PEL];
+  c.metric[2] = p_Inp->MEErrorMetric[Q_PEL];
+  c.start_hp = p_Vid->start_me_refinement_hp;
+  c.start_qp = p_Vid->start_me_refinement_qp;
+  c.search_pos2 = mv_block->search_pos2;
+  c.search_pos4 = mv_block->search_pos4;
+  if (!S.cfg_valid || memcmp(&c, &S.cfg, sizeof(c)))
+  {
+    int rc = jmb_me_configure(S.ctx, &c);
+    if (rc) jmb_die("jmb_me_configure", rc);
+    S.cfg = c;
+    S.cfg_valid = 1;
+  }
+}
+
+static void fill_request(jmb_me_req *q, MEBlock *mv_block, MotionVector *pred_mv, int ref, distblk min_mcost)
+{
+  memset(q, 0, sizeof(*q));
+  q->pos_x = mv_block->pos_x;
+  q->pos_y = mv_block->pos_y;
+  q->pred_x = pred_mv->mv_x;
+  q->pred_y = pred_mv->mv_y;
+  q->blocktype = (uint8_t)mv_block->blocktype;
+  q->ref = (uint8_t)ref;
+  q->min_mcost = min_mcost;
+}
+
+/* stands behind full_search_motion_estimation (lencod/src/me_fullsearch.c:39) = currMB->IntPelME for SearchMode -1 */
+distblk __wrap_full_search_motion_estimation(Macroblock *currMB, MotionVector *pred_mv, MEBlock *mv_block, distblk min_mcost, int lambda_factor)
+{
+  jmb_me_req q;
+  jmb_me_res r;
+  MotionVector *mv = &mv_block->mv[(short)mv_block->list];
+  int rc;
+  if (!shim_on(FAM_ME)) return __real_full_search_motion_estimation(currMB, pred_mv, mv_block, min_mcost, lambda_factor);
+  if (!currMB->p_Inp->rdopt) unsupported("RDOptimization=0 (the (0,0) bias of full_search_motion_estimation)");
+  S.calls[1]++;
+  configure(currMB, mv_block, imin(mv_block->searchRange.max_x, mv_block->searchRange.max_y) >> 2);
+  fill_request(&q, mv_block, pred_mv, ref_index(currMB, mv_block), min_mcost);
+  q.center_x = mv->mv_x;           /* the search centre BlockMotionSearch left in mv (mv_search.c:931-957) */
+  q.center_y = mv->mv_y;
+  q.mode = JMB_SEARCH_FULL;
+  q.lambda[0] = lambda_factor;
+  rc = jmb_me_search(S.ctx, &q, 1, &r, JMB_HOST);
+  if (rc) jmb_die("jmb_me_search(full)", rc);
+  mv->mv_x = r.imv_x;
+  mv->mv_y = r.imv_y;
+  return (distblk)r.icost;
+}
+
+/* setup_fast_full_search (lencod/src/me_fullfast.c:269): only its search-centre rule (:305-329) survives --
+ * the BlockSAD surfaces it used to fill are evaluated inside the search kernel. */
+void __wrap_setup_fast_full_search(Macroblock *currMB, MEBlock *mv_block, int list)
+{
+  VideoParameters *p_Vid = currMB->p_Vid;
+  InputParameters *p_Inp = currMB->p_Inp;
+  MEFullFast *ff = p_Vid->p_ffast_me;
+  short ref = mv_block->ref_idx;
+  int search_range = ff->max_search_range[list][ref] << 2;
+  MotionVector pmv, *c = &ff->search_center[list][ref];
+  PixelPos block[4];
+  if (!shim_on(FAM_ME)) { __real_setup_fast_full_search(currMB, mv_block, list); return; }
+  if (!p_Inp->rdopt) unsupported("RDOptimization=0 with fast full search");
+  get_neighbors(currMB, block, 0, 0, 16);
+  currMB->GetMVPredictor(currMB, block, &pmv, ref, p_Vid->enc_picture->mv_info, list, 0, 0, 16, 16);
+#if (JM_INT_DIVIDE)
+  c->mv_x = ((pmv.mv_x + 2) >> 2) * 4;
+  c->mv_y = ((pmv.mv_y + 2) >> 2) * 4;
+#else
+  c->mv_x = (pmv.mv_x / 4) * 4;
+  c->mv_y = (pmv.mv_y / 4) * 4;
+#endif
+  c->mv_x = (short)iClip3(p_Vid->MaxHmvR[4] + search_range, p_Vid->MaxHmvR[5] - search_range, c->mv_x);
+  c->mv_y = (short)iClip3(p_Vid->MaxVmvR[4] + search_range, p_Vid->MaxVmvR[5] - search_range, c->mv_y);
+  ff->search_center_padded[list][ref] = pad_MVs(*c, mv_block);
+  ff->search_setup_done[list][ref] = 1;
+}
+
+/* stands behind fast_full_search_motion_estimation (lencod/src/me_fullfast.c:618) = currMB->IntPelME for SearchMode 0 */
+distblk __wrap_fast_full_search_motion_estimation(Macroblock *currMB, MotionVector *pred_mv, MEBlock *mv_block, distblk min_mcost, int lambda_factor)
+{
+  VideoParameters *p_Vid = currMB->p_Vid;
+  MEFullFast *ff = p_Vid->p_ffast_me;
+  int list = mv_block->list, rc;
+  short ref = mv_block->ref_idx;
+  jmb_me_req q;
+  jmb_me_res r;
+  if (!shim_on(FAM_ME)) return __real_fast_full_search_motion_estimation(currMB, pred_mv, mv_block, min_mcost, lambda_factor);
+  if (!currMB->p_Inp->rdopt) unsupported("RDOptimization=0 with fast full search");
+  S.calls[2]++;
+  if (!ff->search_setup_done[list][ref]) currMB->p_SetupFastFullPelSearch(currMB, mv_block, list);
+  configure(currMB, mv_block, imax(mv_block->searchRange.max_x, mv_block->searchRange.max_y) >> 2);
+  fill_request(&q, mv_block, pred_mv, ref_index(currMB, mv_block), min_mcost);
+  q.center_x = ff->search_center[list][ref].mv_x;
+  q.center_y = ff->search_center[list][ref].mv_y;
+  q.mode = JMB_SEARCH_FAST_FULL;
+  q.lambda[0] = lambda_factor;
+  rc = jmb_me_search(S.ctx, &q, 1, &r, JMB_HOST);
+  if (rc) jmb_die("jmb_me_search(fast full)", rc);
+  mv_block->mv[list].mv_x = r.imv_x;
+  mv_block->mv[list].mv_y = r.imv_y;
+  return (distblk)r.icost;
+}
+
+/* stands behind sub_pel_motion_estimation (lencod/src/me_fullsearch.c:186) = currMB->SubPelME */
+distblk __wrap_sub_pel_motion_estimation(Macroblock *currMB, MotionVector *pred, MEBlock *mv_block, distblk min_mcost, int *lambda)
+{
+  jmb_me_req q;
+  jmb_me_res r;
+  MotionVector *mv = &mv_block->mv[mv_block->list];
+  int rc;
+  if (!shim_on(FAM_SUBPEL)) return __real_sub_pel_motion_estimation(currMB, pred, mv_block, min_mcost, lambda);
+  if (!currMB->p_Inp->rdopt) unsupported("RDOptimization=0 (the (0,0) bias of sub_pel_motion_estimation)");
+  S.calls[3]++;
+  configure(currMB, mv_block, 0);
+  fill_request(&q, mv_block, pred, ref_index(currMB, mv_block), min_mcost);
+  q.center_x = mv->mv_x;
+  q.center_y = mv->mv_y;
+  q.mode = JMB_SEARCH_FULL;
+  q.flags = JMB_REQ_SUBPEL | JMB_REQ_SKIP_INT | (mv_block->test8x8 ? JMB_REQ_TEST8X8 : 0);
+  q.lambda[0] = lambda[F_PEL];
+  q.lambda[1] = lambda[H_PEL];
+  q.lambda[2] = lambda[Q_PEL];
+  rc = jmb_me_search(S.ctx, &q, 1, &r, JMB_HOST);
+  if (rc) jmb_die("jmb_me_search(sub-pel)", rc);
+  mv->mv_x = r.mv_x;
+  mv->mv_y = r.mv_y;
+  return (distblk)r.cost;
+}
+
+/* ---- transforms (lcommon/src/transform.c:20, :353) ---------------------------------------------------- */
+static void forward_nxn(int **block, int **tblock, int pos_y, int pos_x, int n)
+{
+  int32_t buf[64];
+  int i, j, rc;
+  for (j = 0; j < n; j++)
+    for (i = 0; i < n; i++) buf[j * n + i] = block[pos_y + j][pos_x + i];
+  rc = jmb_forward_transform(S.ctx, buf, 1, n, JMB_HOST);
+  if (rc) jmb_die("jmb_forward_transform", rc);
+  for (j = 0; j < n; j++)
+    for (i = 0; i < n; i++) tblock[pos_y + j][pos_x + i] = buf[j * n + i];
+}
+
+void __wrap_forward4x4(int **block, int **tblock, int pos_y, int pos_x)
+{
+  if (!shim_on(FAM_TQ)) { __real_forward4x4(block, tblock, pos_y, pos_x); return; }
+  S.calls[4]++;
+  forward_nxn(block, tblock, pos_y, pos_x, 4);
+}
+
+void __wrap_forward8x8(int **block, int **tblock, int pos_y, int pos_x)
+{
+  if (!shim_on(FAM_TQ)) { __real_forward8x8(block, tblock, pos_y, pos_x); return; }
+  S.calls[5]++;
+  forward_nxn(block, tblock, pos_y, pos_x, 8);
+}
+
+/* ---- quantisation (lencod/src/quant4x4_normal.c:39, quant4x4_around.c:40, quant8x8_normal.c:43,:123,
+ *      quant8x8_around.c) --------------------------------------------------------------------------------
+ * tblock is JM's row-pointer view of the coefficient block (rows already offset by the caller, columns by
+ * q_method->block_x); on return it holds the dequantised coefficients, ACLevel/ACRun (or cofAC for the 8x8
+ * CAVLC form) the level/run lists, *coeff_cost the running cost, fadjust the adaptive-rounding terms. */
+static int quant_nxn(Macroblock *currMB, int **tblock, struct quant_methods *qm, int n, int around, int cavlc8, int ***cofAC)
+{
+  VideoParameters *p_Vid = currMB->p_Vid;
+  Slice *currSlice = currMB->p_Slice;
+  jmb_quant_desc d;
+  int32_t coef[64], levels[68], runs[68], fadj[64], cost, nz;
+  int i, j, k, rc, bx = qm->block_x;
+  const int nn = n * n;
+
+  memset(&d, 0, sizeof(d));
+  d.n = n;
+  d.qp = qm->qp;
+  d.is_cavlc = (n == 4) ? (currSlice->symbol_mode == CAVLC) : cavlc8;
+  d.around = around;
+  d.adapt_rnd_weight = p_Vid->AdaptRndWeight;
+  for (j = 0; j < n; j++)
+    for (i = 0; i < n; i++)
+    {
+      d.qparams[j * n + i][0] = qm->q_params[j][i].OffsetComp;
+      d.qparams[j * n + i][1] = qm->q_params[j][i].ScaleComp;
+      d.qparams[j * n + i][2] = qm->q_params[j][i].InvScaleComp;
+      coef[j * n + i] = tblock[j][bx + i];
+    }
+  for (k = 0; k < nn; k++)
+  {
+    d.scan[k][0] = qm->pos_scan[k][0];
+    d.scan[k][1] = qm->pos_scan[k][1];
+  }
+  /* c_cost is indexed by the run (< 16 per list for 4x4 / 8x8 CAVLC, < 64 for 8x8); COEFF_COST rows are 16 / 64 long */
+  for (k = 0; k < ((n == 4 || cavlc8) ? 16 : 64); k++) d.c_cost[k] = qm->c_cost[k];
+  cost = *qm->coeff_cost;
+  rc = jmb_quant_blocks(S.ctx, &d, 0, coef, 1, levels, runs, around ? fadj : NULL, &cost, &nz, JMB_HOST);
+  if (rc) jmb_die("jmb_quant_blocks", rc);
+  *qm->coeff_cost = cost;
+  for (j = 0; j < n; j++)
+    for (i = 0; i < n; i++)
+    {
+      tblock[j][bx + i] = coef[j * n + i];
+      if (around) qm->fadjust[j][bx + i] = fadj[j * n + i];
+    }
+  if (cavlc8)
+  {
+    for (k = 0; k < 4; k++)
+    {
+      int *ACL = &cofAC[k][0][0], *ACR = &cofAC[k][1][0];
+      for (i = 0; levels[17 * k + i] != 0; i++) { ACL[i] = levels[17 * k + i]; ACR[i] = runs[17 * k + i]; }
+      ACL[i] = 0;
+    }
+  }
+  else
+  {
+    for (i = 0; levels[i] != 0; i++) { qm->ACLevel[i] = levels[i]; qm->ACRun[i] = runs[i]; }
+    qm->ACLevel[i] = 0;
+  }
+  return nz;
+}
+
+int __wrap_quant_4x4_normal(Macroblock *currMB, int **tblock, struct quant_methods *q_method)
+{
+  if (!shim_on(FAM_TQ)) return __real_quant_4x4_normal(currMB, tblock, q_method);
+  S.calls[6]++;
+  return quant_nxn(currMB, tblock, q_method, 4, 0, 0, NULL);
+}
+int __wrap_quant_4x4_around(Macroblock *currMB, int **tblock, struct quant_methods *q_method)
+{
+  if (!shim_on(FAM_TQ)) return __real_quant_4x4_around(currMB, tblock, q_method);
+  S.calls[6]++;
+  return quant_nxn(currMB, tblock, q_method, 4, 1, 0, NULL);
+}
+int __wrap_quant_8x8_normal(Macroblock *currMB, int **tblock, struct quant_methods *q_method)
+{
+  if (!shim_on(FAM_TQ)) return __real_quant_8x8_normal(currMB, tblock, q_method);
+  S.calls[7]++;
+  return quant_nxn(currMB, tblock, q_method, 8, 0, 0, NULL);
+}
+int __wrap_quant_8x8_around(Macroblock *currMB, int **tblock, struct quant_methods *q_method)
+{
+  if (!shim_on(FAM_TQ)) return __real_quant_8x8_around(currMB, tblock, q_method);
+  S.calls[7]++;
+  return quant_nxn(currMB, tblock, q_method, 8, 1, 0, NULL);
+}
+int __wrap_quant_8x8cavlc_normal(Macroblock *currMB, int **tblock, struct quant_methods *q_method, int ***cofAC)
+{
+  if (!shim_on(FAM_TQ)) return __real_quant_8x8cavlc_normal(currMB, tblock, q_method, cofAC);
+  S.calls[7]++;
+  return quant_nxn(currMB, tblock, q_method, 8, 0, 1, cofAC);
+}
+int __wrap_quant_8x8cavlc_around(Macroblock *currMB, int **tblock, struct quant_methods *q_method, int ***cofAC)
+{
+  if (!shim_on(FAM_TQ)) return __real_quant_8x8cavlc_around(currMB, tblock, q_method, cofAC);
+  S.calls[7]++;
+  return quant_nxn(currMB, tblock, q_method, 8, 1, 1, cofAC);
+}

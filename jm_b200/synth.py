@@ -28,12 +28,16 @@ def luma_frames(width, height, n_frames, seed=1234, motion=(5, 3), noise=2.0, bi
     return frames
 
 
-def write_yuv420(path, lumas, bitdepth=8):
-    """Planar I420 with flat chroma (all BASELINE cfgs have ChromaMEEnable=0)."""
+def write_yuv420(path, lumas, bitdepth=8, textured_chroma=False):
+    """Planar I420; chroma flat mid-grey (all BASELINE cfgs have ChromaMEEnable=0) or a 2x2-decimated copy of the luma
+    texture (so the chroma residual path codes something)."""
     with open(path, "wb") as f:
         for y in lumas:
             h, w = y.shape
             c = np.full((h // 2) * (w // 2) * 2, 1 << (bitdepth - 1))
+            if textured_chroma:
+                u = y[0::2, 0::2]; v = y[1::2, 1::2][::-1]
+                c = np.concatenate([u.reshape(-1), v.reshape(-1)])
             if bitdepth == 8:
                 f.write(y.astype(np.uint8).tobytes()); f.write(c.astype(np.uint8).tobytes())
             else:
