@@ -39,12 +39,14 @@ N_SETS = 4
 BYTES_PER_MB_REF = 13804           # 512 src + 12800 window + 492 results
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, anchor_bcast=False):
     return {"workload": "1080p 4:2:0 synthetic, FullSearch +-32 (SearchMode=-1) 41 partitions/MB + SATD sub-pel + "
                         "4x4 transform/quant of 7 partition modes, Baseline, 1 ref, QP28",
             "width": W, "height": H, "macroblocks_per_step": (W // 16) * (H // 16), "search_range": SEARCH_RANGE,
             "l2": f"rotating over {N_SETS} distinct input sets (> 126 MB in total)",
-            "parallelism": f"{n_gpus} x independent picture streams (closed-GOP shards), no data-path collective"}
+            "parallelism": (f"{n_gpus} x pictures sharing one anchor: ncclBroadcast of the reconstructed reference (4.2 MB u16 luma) per step"
+                            if anchor_bcast and n_gpus > 1 else
+                            f"{n_gpus} x independent picture streams (closed-GOP shards), no data-path collective")}
 
 
 def make_requests(api, seed, motion_q=(20, 12)):
@@ -147,8 +149,15 @@ def run_ours(args):
     h_lev = ctx.pinned((7, n_mb, 256), np.int16); h_cost = ctx.pinned((7, n_mb, 4), np.int32); h_cbp = ctx.pinned((7, n_mb), np.uint32)
     torch.cuda.synchronize()
 
+    from jm_b200 import shard
+
     def step_device(s):
         hs, ds = sets[s % N_SETS]
+        if args.anchor_bcast and world > 1:
+            # B-picture fan-out: rank 0 holds the reconstructed anchor; one NCCL broadcast of its u16 luma
+            # plane, then every rank builds its own quarter-pel planes and codes its own picture against it
+            with torch.cuda.stream(stream):
+                shard.broadcast_anchor(ds["ref"], src=0)
         ctx.ref_put(s % 2, ds["ref"].data_ptr(), api.DEVICE, shape=(H, W))
         ctx.pic_begin(ds["cur"].data_ptr(), [s % 2], api.DEVICE, shape=(H, W))
         ctx.me_search(ds["reqs"].data_ptr(), d_res.data_ptr(), api.DEVICE, n=n_mb * api.NPART, frame=True)
@@ -231,7 +240,7 @@ def run_ours(args):
     out = {"metric": "macroblocks/sec 1080p full-search ME+DCT/quant", "value": world * n_mb * args.steps / (ms / 1e3),
            "unit": "macroblocks/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-           "config": workload_config(world), "clocks": clocks, "gpu_launches": int(gpu_launches),
+           "config": workload_config(world, args.anchor_bcast), "clocks": clocks, "gpu_launches": int(gpu_launches),
            "e2e": {"value": world * n_mb * args.steps / e2e_s, "unit": "macroblocks/s", "h2d_bytes_per_step": int(h2d),
                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps,
                    "host_ms_per_step": {k: 1e3 * v / args.steps for k, v in e2e_t.items()}},
@@ -364,6 +373,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--anchor-bcast", action="store_true",
+                    help="N>1: broadcast rank 0's reference picture over NCCL every step (pictures sharing an anchor coded on different GPUs)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-mbs-per-core", type=int, default=24)
     args = ap.parse_args()
