@@ -132,10 +132,13 @@ def run_ours(args):
     # ---- inputs: N_SETS distinct (reference, current) pairs + request lists, on host (pinned) and in HBM
     sets = []
     for s in range(N_SETS):
-        f = synth.luma_frames(W, H, 2, seed=1234 + 97 * rank + s, motion=(5, 3))
+        # anchor-broadcast mode: every rank codes a picture of the SAME sequence against rank 0's anchor
+        f = synth.luma_frames(W, H, 2, seed=1234 + (0 if args.anchor_bcast else 97 * rank) + s, motion=(5, 3))
         reqs = make_requests(api, seed=50 + 13 * rank + s)
         reqs["lambda"] = lam
         hs = {"ref": ctx.pinned((H, W), np.uint16), "cur": ctx.pinned((H, W), np.uint16), "reqs": ctx.pinned(len(reqs), api.ME_REQ)}
+        if args.scene_cut:      # robustness probe: the reference is an unrelated picture (nothing matches)
+            f[0] = synth.luma_frames(W, H, 1, seed=999 + s)[0]
         hs["ref"][:] = f[0]; hs["cur"][:] = f[1]; hs["reqs"][:] = reqs
         ds = {k: torch.from_numpy(v.view(np.uint8).reshape(-1).copy()).cuda(local) for k, v in hs.items()}
         sets.append((hs, ds))
@@ -373,6 +376,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--scene-cut", action="store_true", help="probe: unrelated reference picture (worst case for the search gate)")
     ap.add_argument("--anchor-bcast", action="store_true",
                     help="N>1: broadcast rank 0's reference picture over NCCL every step (pictures sharing an anchor coded on different GPUs)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libjmb200.so")
+LIB_PATH = os.environ.get("JMB200_LIB") or os.path.join(HERE, "lib", "libjmb200.so")     # JMB200_LIB: tuning builds (tools/)
 HOST, DEVICE = 0, 1
 SAD, SSE, SATD = 0, 1, 2
 SEARCH_FULL, SEARCH_FAST_FULL = 0, 1

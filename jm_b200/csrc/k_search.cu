@@ -23,13 +23,19 @@
 namespace {
 
 constexpr int NPART = 41;
-constexpr int NT = 192;            // threads per CTA
+#ifndef JMB_IS_NT
+#define JMB_IS_NT 128
+#endif
+constexpr int NT = JMB_IS_NT;      // threads per CTA (multiple of 32, >= 64)
 constexpr int CW = 96;             // chunk of displacements handled per staging pass
 constexpr int CH = 72;             // multiple of 4 (a thread owns 4 vertically adjacent displacements)
 constexpr int WIN_PITCH = 120;     // bytes: <=3 alignment + CW + 15, rounded up to a word, + the fifth word
 constexpr int WIN_ROWS = CH + 15;
 constexpr int S1_COLS = 10, S1_RGS = 3, S1_ITEMS = S1_COLS * S1_RGS, S1_PITCH = 43;   // stage-1 neighbourhood
 constexpr int ADJ_PITCH = 44;      // words per column (>= NPART; 176 B keeps the 128-bit row reads conflict-free)
+constexpr int WQ_CAP = 192;          // per-warp queue of gate hits awaiting their exact evaluation
+constexpr int HS_PITCH = NPART + 1;   // u16 per thread: SADs of the partitions of a displacement that met the gate
+constexpr int INT_SEARCH_DYN_SMEM = (CW + CH + CH / 4) * ADJ_PITCH * 4 + (NT / 32) * WQ_CAP * 8 + NT * HS_PITCH * 2;
 constexpr int IDX_BITS = 13;       // (2*64+1)^2 = 16641 > 8192: search_range <= 45 keeps idx < 8192
 
 struct PartGeom { unsigned char type, bx, by, w4, h4; };
@@ -133,6 +139,23 @@ __device__ void spiral_xy(int idx, int *dx, int *dy) {
   else { off -= 2 * (2 * l - 1); *dy = (off >> 1) - l; *dx = (off & 1) ? l : -l; }
 }
 
+// compile-time copy of the partition geometry (bx, by, w4, h4 in 4x4 units) for part_sum<P>
+__host__ __device__ constexpr int pg_first(int t) { return t == 1 ? 0 : t == 2 ? 1 : t == 3 ? 3 : t == 4 ? 5 : t == 5 ? 9 : t == 6 ? 17 : 25; }
+__host__ __device__ constexpr int pg_type(int p) { return p < 1 ? 1 : p < 3 ? 2 : p < 5 ? 3 : p < 9 ? 4 : p < 17 ? 5 : p < 25 ? 6 : 7; }
+__host__ __device__ constexpr int pg_w4(int p) { return pg_type(p) <= 2 ? 4 : pg_type(p) <= 5 ? 2 : 1; }
+__host__ __device__ constexpr int pg_h4(int p) { return (pg_type(p) == 1 || pg_type(p) == 3) ? 4 : (pg_type(p) == 2 || pg_type(p) == 4 || pg_type(p) == 6) ? 2 : 1; }
+__host__ __device__ constexpr int pg_bx(int p) { return ((p - pg_first(pg_type(p))) % (4 / pg_w4(p))) * pg_w4(p); }
+__host__ __device__ constexpr int pg_by(int p) { return ((p - pg_first(pg_type(p))) / (4 / pg_w4(p))) * pg_h4(p); }
+template <int P>
+__device__ __forceinline__ unsigned part_sum(const unsigned *a) {
+  unsigned v = 0;
+#pragma unroll
+  for (int y = 0; y < pg_h4(P); y++)
+#pragma unroll
+    for (int x = 0; x < pg_w4(P); x++) v += a[(pg_by(P) + y) * 4 + pg_bx(P) + x];
+  return v;
+}
+
 // the 41 partition SADs of one displacement from its sixteen 4x4 SADs (update_full_search_large_blocks,
 // lencod/src/me_fullfast.c:207-259), handed to F(partition, sad) in canonical order
 template <typename F>
@@ -197,7 +220,7 @@ __device__ __forceinline__ void sad_item(const uint8_t *win, const unsigned *ssr
 // arithmetic loop when one of its SADs beats the current bound (sad < thr), which after the seeding step
 // below is rare.  ALU-pipe work per displacement: 64 VABSDIFF4 + 19 PRMT + 41 ISETP.
 #ifndef JMB_IS_MINB
-#define JMB_IS_MINB 2
+#define JMB_IS_MINB 3
 #endif
 __global__ void __launch_bounds__(NT, JMB_IS_MINB)
 k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups, jmb_me_res *__restrict__ res,
@@ -207,12 +230,19 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
   __shared__ __align__(16) uint8_t win[WIN_ROWS * WIN_PITCH];
   __shared__ __align__(16) unsigned ssrc[16 * 4];
   __shared__ int sbox[12];
-  __shared__ __align__(16) unsigned adjx[CW * ADJ_PITCH];   // per column and partition: floor(lambda * (bits_x - 1) / 32)
+  __shared__ int wq_n[NT / 32];
+  // gate tables (dynamic shared memory, INT_SEARCH_DYN_SMEM bytes): per column / per row and partition,
+  // floor(lambda * (bits_x - 1) / 32) and floor(lambda * (bits_y - 1) / 32)
+  extern __shared__ __align__(16) unsigned dyn_smem[];
+  unsigned *const adjx = dyn_smem, *const adjy = dyn_smem + CW * ADJ_PITCH, *const adjy4 = adjy + CH * ADJ_PITCH;   // adjy4: min over the 4 rows of an item
+  unsigned long long (*const wq)[WQ_CAP] = (unsigned long long (*)[WQ_CAP])(adjy4 + (CH / 4) * ADJ_PITCH);
+  unsigned short (*const hitsad)[HS_PITCH] = (unsigned short (*)[HS_PITCH])(wq + NT / 32);
   __shared__ unsigned short S1[S1_ITEMS * 4 * S1_PITCH];
 
   const int tid = threadIdx.x, g = blockIdx.x;
   const int W = w + 2 * JMB_PAD_X, H = h + 2 * JMB_PAD_Y;
 
+  if (tid < NT / 32) wq_n[tid] = 0;
   if (tid == 0) {
     sbox[0] = sbox[2] = 1 << 30; sbox[1] = sbox[3] = -(1 << 30); sbox[7] = 0; sbox[10] = NPART;
     G.R = R; G.max_mvd_m1 = max_mvd_m1; G.thr[NPART] = G.thr[NPART + 1] = G.thr[NPART + 2] = 0;
@@ -318,14 +348,37 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
           const int ic = i / NPART, p = i - ic * NPART;
           const ReqS &q = G.rq[p];
           unsigned a = 0;
-          if (q.active) a = min(65535u, ((unsigned)q.lam * (unsigned)(jmb_mvbits(4 * (cx0 + ic) - q.px) - 1)) >> 5);
+          // (a column ON the clamp boundary stands for every candidate beyond it: no column-specific term there)
+          if (q.active && cx0 + ic >= G.inner[p].x && cx0 + ic <= G.inner[p].y)
+            a = min(65535u, ((unsigned)q.lam * (unsigned)(jmb_mvbits(4 * (cx0 + ic) - q.px) - 1)) >> 5);
           adjx[ic * ADJ_PITCH + p] = a;
+        }
+        for (int i = s1 ? tid - 32 : tid; i < ch * NPART; i += s1 ? NT - 32 : NT) {
+          const int ir = i / NPART, p = i - ir * NPART;
+          const ReqS &q = G.rq[p];
+          unsigned a = 0;
+          if (q.active && cy0 + ir >= G.inner[p].z && cy0 + ir <= G.inner[p].w)
+            a = min(65535u, ((unsigned)q.lam * (unsigned)(jmb_mvbits(4 * (cy0 + ir) - q.py) - 1)) >> 5);
+          adjy[ir * ADJ_PITCH + p] = a;
+        }
+        for (int i = s1 ? tid - 32 : tid; i < ((ch + 3) >> 2) * NPART; i += s1 ? NT - 32 : NT) {
+          const int rg = i / NPART, p = i - rg * NPART;
+          const ReqS &q = G.rq[p];
+          unsigned a = 0xffffffffu;
+          for (int r = 4 * rg; r < min(4 * rg + 4, ch); r++) {
+            unsigned ar = 0;
+            if (q.active && cy0 + r >= G.inner[p].z && cy0 + r <= G.inner[p].w)
+              ar = min(65535u, ((unsigned)q.lam * (unsigned)(jmb_mvbits(4 * (cy0 + r) - q.py) - 1)) >> 5);
+            a = min(a, ar);
+          }
+          adjy4[rg * ADJ_PITCH + p] = a;
         }
       }
       if (tid == 0) sbox[11] = 0;      // next warp item of the sweep
       __syncthreads();
       if (s1) {
-        const int p = tid >> 2, j = tid & 3;
+        for (int pp = 0; pp < NPART; pp += NT / 4) {      // uniform trip count: the shuffles below need whole warps
+        const int p = pp + (tid >> 2), j = tid & 3;
         unsigned long long k = ~0ull;
         if (p < NPART && G.rq[p].active) {
           const ReqS &q = G.rq[p];
@@ -353,19 +406,25 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
         k = min(k, __shfl_xor_sync(0xffffffffu, k, 1));
         k = min(k, __shfl_xor_sync(0xffffffffu, k, 2));
         if (p < NPART && j == 0 && k != ~0ull && k < G.best[p]) publish(&G, p, k);
+        }
         __syncthreads();
       }
 
       // the sweep: warps draw batches of 32 items from a shared counter (a batch that meets the gate runs much
       // longer than one that does not, so a static split would leave warps waiting at the final barrier)
       const int nitems = nrg * cw, lane = tid & 31;
+      bool head = true, release = tid < 32;   // the most central batch goes first, alone (warp 0): every other batch then starts from its bounds
       for (;;) {
         int base = 0;
-        if (lane == 0) base = atomicAdd(&sbox[11], 32);
+        if (head) {
+          head = false;
+          if (tid >= 32) { __syncthreads(); continue; }
+          if (lane == 0) base = atomicAdd(&sbox[11], 32);
+        } else if (lane == 0) base = atomicAdd(&sbox[11], 32);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= nitems) break;
-        const int it = base + lane;
-        if (it >= nitems) continue;
+        const int it = base + lane, warp = tid >> 5;
+        if (it < nitems) {
         const int k = it / cw, ic = it - k * cw;
         const int rg = (k & 1) ? mid - ((k + 1) >> 1) : mid + (k >> 1);   // centre rows first: tight bounds early
         const int row0 = rg * 4, xo = ic + xoff0;
@@ -380,29 +439,60 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
                        : "r"((unsigned)__cvta_generic_to_shared(&G.thr[4 * i])));
         }
         {
-          const uint4 *ap = (const uint4 *)&adjx[ic * ADJ_PITCH];
+          const uint4 *ap = (const uint4 *)&adjx[ic * ADJ_PITCH], *bp = (const uint4 *)&adjy4[rg * ADJ_PITCH];
 #pragma unroll
           for (int i = 0; i < (NPART + 3) / 4; i++) {
-            const uint4 v = ap[i];
-            t[4 * i] -= v.x; t[4 * i + 1] -= v.y; t[4 * i + 2] -= v.z; t[4 * i + 3] -= v.w;
+            const uint4 v = ap[i], u = bp[i];
+            t[4 * i] -= v.x + u.x; t[4 * i + 1] -= v.y + u.y; t[4 * i + 2] -= v.z + u.z; t[4 * i + 3] -= v.w + u.w;
           }
         }
-        // one flag per displacement and partition class (larger partitions / the sixteen 4x4s) keeps the
-        // re-visit below short
-        bool hitA[4], hitB[4];
+        // one flag per displacement keeps the common case to 41 compares
+        bool hit[4];
 #pragma unroll
         for (int s = 0; s < 4; s++) {
-          hitA[s] = hitB[s] = false;
-          if (row0 + s < ch)
-            for_each_partition(acc[s], [&](int p, unsigned v) { if (p < 25) hitA[s] |= (int)v < (int)t[p]; else hitB[s] |= (int)v < (int)t[p]; });
+          hit[s] = false;
+          if (row0 + s < ch) for_each_partition(acc[s], [&](int p, unsigned v) { hit[s] |= (int)v < (int)t[p]; });
         }
+        // Re-visit of a displacement that met the gate: collect the partitions that did in a bit mask (straight-line,
+        // no calls), then walk the set bits: one jump per hit to the few adds that re-sum that partition's SAD, one more
+        // check with the row term of the mv cost, and only then the exact evaluation.  Cost is proportional to the number
+        // of hits, and only the code of partitions that hit is ever fetched (the flat-SAD regime lives here).
         const int Dx = cx0 + ic;
 #pragma unroll
         for (int s = 0; s < 4; s++) {
+          if (!hit[s]) continue;
+          unsigned mlo = 0, mhi = 0;
+          for_each_partition(acc[s], [&](int p, unsigned v) {
+            if ((int)v < (int)t[p]) { if (p < 32) mlo |= 1u << (p & 31); else mhi |= 1u << (p & 31); hitsad[tid][p] = (unsigned short)v; }
+          });
           const int Dy = cy0 + row0 + s;
-          if (hitA[s]) for_each_partition(acc[s], [&](int p, unsigned v) { if (p < 25 && (int)v < (int)t[p]) level2(&G, p, v, Dx, Dy); });
-          if (hitB[s]) for_each_partition(acc[s], [&](int p, unsigned v) { if (p >= 25 && (int)v < (int)t[p]) level2(&G, p, v, Dx, Dy); });
+          const unsigned *ay = adjy + (row0 + s) * ADJ_PITCH, *ax = adjx + ic * ADJ_PITCH;
+          while (mlo | mhi) {
+            int p;
+            if (mlo) { p = __ffs(mlo) - 1; mlo &= mlo - 1; } else { p = 32 + __ffs(mhi) - 1; mhi &= mhi - 1; }
+            const unsigned v = hitsad[tid][p];
+            const int bound = (int)(*(volatile unsigned *)&G.thr[p] - ax[p] - ay[p]);
+            if ((int)v < bound) {
+              // hits are parked in the warp's queue and evaluated below by all 32 lanes together (a lone lane walking
+              // its own hits would hold the other 31 idle); a full queue falls back to evaluating in place
+              const int slot = atomicAdd(&wq_n[warp], 1);
+              if (slot < WQ_CAP) wq[warp][slot] = ((unsigned long long)(unsigned)((p << 16) | ((Dy - cy0) << 8) | (Dx - cx0)) << 32) | v;
+              else level2(&G, p, v, Dx, Dy);
+            }
+          }
         }
+        }
+        __syncwarp();
+        const int nq = min(*(volatile int *)&wq_n[warp], WQ_CAP);
+        for (int e = lane; e < nq; e += 32) {
+          const unsigned long long ent = wq[warp][e];
+          const unsigned hi = (unsigned)(ent >> 32);
+          level2(&G, (int)(hi >> 16), (unsigned)ent, cx0 + (int)(hi & 255), cy0 + (int)((hi >> 8) & 255));
+        }
+        __syncwarp();
+        if (lane == 0) wq_n[warp] = 0;
+        __syncwarp();
+        if (release) { release = false; __syncthreads(); }
       }
     }
   }
@@ -564,7 +654,12 @@ static int me_search_impl(jmb_ctx *ctx, const jmb_me_req *reqs, int n, jmb_me_re
     d_reqs = (const jmb_me_req *)ctx->d_stage; d_res = (jmb_me_res *)ctx->d_res_keep;
   }
   jmb_time_begin(ctx, JMB_K_INT_SEARCH);
-  k_int_search<<<n_groups, NT, 0, ctx->stream>>>(d_reqs, d_groups, d_res, ctx->cur, ctx->cur_pitch, d_tab, r0.pitch,
+  static bool smem_opt_in = false;
+  if (!smem_opt_in) {
+    JMB_CUDA(ctx, cudaFuncSetAttribute(k_int_search, cudaFuncAttributeMaxDynamicSharedMemorySize, INT_SEARCH_DYN_SMEM));
+    smem_opt_in = true;
+  }
+  k_int_search<<<n_groups, NT, INT_SEARCH_DYN_SMEM, ctx->stream>>>(d_reqs, d_groups, d_res, ctx->cur, ctx->cur_pitch, d_tab, r0.pitch,
                                                   ctx->cur_w, ctx->cur_h, ctx->me.search_range, ctx->me.max_mvd - 1, ctx->nref, ctx->d_err);
   jmb_time_end(ctx, JMB_K_INT_SEARCH);
   JMB_LAUNCH_CHECK(ctx);
