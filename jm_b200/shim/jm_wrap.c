@@ -9,6 +9,7 @@
  *       -Wl,--wrap=getSubImagesLuma -Wl,--wrap=encode_one_slice \
  *       -Wl,--wrap=full_search_motion_estimation -Wl,--wrap=fast_full_search_motion_estimation \
  *       -Wl,--wrap=setup_fast_full_search -Wl,--wrap=sub_pel_motion_estimation \
+ *       -Wl,--wrap=computeSAD -Wl,--wrap=computeSSE -Wl,--wrap=computeSATD \
  *       -Wl,--wrap=forward4x4 -Wl,--wrap=forward8x8 \
  *       -Wl,--wrap=quant_4x4_normal -Wl,--wrap=quant_4x4_around \
  *       -Wl,--wrap=quant_8x8_normal -Wl,--wrap=quant_8x8_around \
@@ -43,6 +44,7 @@
 #include "transform.h"
 #include "quant4x4.h"
 #include "quant8x8.h"
+#include "me_distortion.h"
 #include "mv_prediction.h"
 
 #include "jmb200.h"
@@ -62,8 +64,11 @@ int     __real_quant_8x8_normal(Macroblock *, int **, struct quant_methods *);
 int     __real_quant_8x8_around(Macroblock *, int **, struct quant_methods *);
 int     __real_quant_8x8cavlc_normal(Macroblock *, int **, struct quant_methods *, int ***);
 int     __real_quant_8x8cavlc_around(Macroblock *, int **, struct quant_methods *, int ***);
+distblk __real_computeSAD(StorablePicture *, MEBlock *, distblk, MotionVector *);
+distblk __real_computeSSE(StorablePicture *, MEBlock *, distblk, MotionVector *);
+distblk __real_computeSATD(StorablePicture *, MEBlock *, distblk, MotionVector *);
 
-enum { FAM_PLANES = 1, FAM_ME = 2, FAM_SUBPEL = 4, FAM_TQ = 8 };
+enum { FAM_PLANES = 1, FAM_ME = 2, FAM_SUBPEL = 4, FAM_TQ = 8, FAM_DIST = 16 };
 
 static struct
 {
@@ -77,7 +82,7 @@ static struct
   int              list[JMB_MAX_REFS], nlist;
   jmb_me_config    cfg;
   int              cfg_valid;
-  unsigned long    calls[8];
+  unsigned long    calls[9];
 } S;
 
 /* JM's convention for fatal conditions is error(text, code) -> message on stderr, exit(code) (lencod/src/lencod.c).
@@ -104,8 +109,8 @@ static void unsupported(const char *what)
 static void report(void)
 {
   if (S.init == 1 && getenv("JMB_SHIM_VERBOSE"))
-    fprintf(stderr, "[jmb shim] planes %lu  full %lu  fastfull %lu  subpel %lu  fwd4 %lu  fwd8 %lu  quant4 %lu  quant8 %lu  kernel launches %llu\n",
-            S.calls[0], S.calls[1], S.calls[2], S.calls[3], S.calls[4], S.calls[5], S.calls[6], S.calls[7],
+    fprintf(stderr, "[jmb shim] planes %lu  full %lu  fastfull %lu  subpel %lu  fwd4 %lu  fwd8 %lu  quant4 %lu  quant8 %lu  dist %lu  kernel launches %llu\n",
+            S.calls[0], S.calls[1], S.calls[2], S.calls[3], S.calls[4], S.calls[5], S.calls[6], S.calls[7], S.calls[8],
             (unsigned long long)jmb_launch_count(S.ctx));
 }
 
@@ -132,6 +137,7 @@ static int shim_on(int family)
         if (strstr(off, "me"))     S.off |= FAM_ME;
         if (strstr(off, "subpel")) S.off |= FAM_SUBPEL;
         if (strstr(off, "tq"))     S.off |= FAM_TQ;
+        if (strstr(off, "dist"))   S.off |= FAM_DIST;
       }
       atexit(report);
     }
@@ -198,16 +204,14 @@ int __wrap_encode_one_slice(VideoParameters *p_Vid, int SliceGroupId, int TotalC
   return __real_encode_one_slice(p_Vid, SliceGroupId, TotalCodedMBs);
 }
 
-static int ref_index(Macroblock *currMB, MEBlock *mv_block)
+static int ref_index_of(VideoParameters *p_Vid, Slice *currSlice, MEBlock *mv_block, StorablePicture *ref_picture)
 {
-  VideoParameters *p_Vid = currMB->p_Vid;
-  Slice *currSlice = currMB->p_Slice;
-  StorablePicture *ref_picture = currSlice->listX[mv_block->list + currMB->list_offset][mv_block->ref_idx];
   int i, slot = -1;
 
   if (p_Vid->structure != FRAME || currSlice->mb_aff_frame_flag) unsupported("field / MBAFF picture");
   if (mv_block->ChromaMEEnable) unsupported("ChromaMEEnable");
   if (mv_block->apply_weights) unsupported("weighted-prediction motion estimation");
+  if (!ref_picture) unsupported("a search without a reference picture");
 
   for (i = 0; i < JMB_MAX_REFS; i++)
     if (S.slot_pic[i] == ref_picture) { slot = i; break; }
@@ -230,6 +234,12 @@ static int ref_index(Macroblock *currMB, MEBlock *mv_block)
   snprintf(errortext, ET_SIZE, "libjmb200 shim: reference picture not in the device list");
   fatal(702);
   return -1;
+}
+
+static int ref_index(Macroblock *currMB, MEBlock *mv_block)
+{
+  Slice *currSlice = currMB->p_Slice;
+  return ref_index_of(currMB->p_Vid, currSlice, mv_block, currSlice->listX[mv_block->list + currMB->list_offset][(int)mv_block->ref_idx]);
 }
 
 static void configure(Macroblock *currMB, MEBlock *mv_block, int search_range)
@@ -369,6 +379,43 @@ distblk __wrap_sub_pel_motion_estimation(Macroblock *currMB, MotionVector *pred,
   mv->mv_x = r.mv_x;
   mv->mv_y = r.mv_y;
   return (distblk)r.cost;
+}
+
+/* ---- block distortion (lencod/src/me_distortion.c:349 computeSAD, :1190 computeSSE, :745 computeSATD) --------------
+ * The finest-grain hook: p_Vid->computeUniPred[] (mv_search.c:486-500) -> mv_block->computePred{F,H,Q}Pel, i.e. every
+ * search engine that is NOT wrapped as a whole (EPZS, UMHex, the bi-predictive searches' single-list parts) becomes a
+ * client of the device distortion oracle.  JM's early exit returns dist_scale_f(x) = min_mcost (mv_search.h:19-23) as soon
+ * as a running sum exceeds min_mcost >> 5; the sums only grow and the check also follows the last row / sub-block, so the
+ * exit happens iff the TOTAL exceeds it -- the wrapper reproduces it from the full distortion. */
+static distblk block_dist(int metric, StorablePicture *ref1, MEBlock *mv_block, distblk min_mcost, MotionVector *cand)
+{
+  VideoParameters *p_Vid = mv_block->p_Vid;
+  int16_t xy[2];
+  int32_t d = 0;
+  int rc, ref = ref_index_of(p_Vid, mv_block->p_Slice, mv_block, ref1);
+  S.calls[8]++;
+  xy[0] = cand->mv_x;
+  xy[1] = cand->mv_y;
+  rc = jmb_dist(S.ctx, ref, metric, mv_block->blocktype, mv_block->pos_x, mv_block->pos_y, xy, 1,
+                metric == JMB_SATD && mv_block->test8x8, &d, JMB_HOST);
+  if (rc) jmb_die("jmb_dist", rc);
+  return d > dist_down(min_mcost) ? min_mcost : dist_scale((distblk)d);
+}
+
+distblk __wrap_computeSAD(StorablePicture *ref1, MEBlock *mv_block, distblk min_mcost, MotionVector *cand)
+{
+  if (!shim_on(FAM_DIST)) return __real_computeSAD(ref1, mv_block, min_mcost, cand);
+  return block_dist(JMB_SAD, ref1, mv_block, min_mcost, cand);
+}
+distblk __wrap_computeSSE(StorablePicture *ref1, MEBlock *mv_block, distblk min_mcost, MotionVector *cand)
+{
+  if (!shim_on(FAM_DIST)) return __real_computeSSE(ref1, mv_block, min_mcost, cand);
+  return block_dist(JMB_SSE, ref1, mv_block, min_mcost, cand);
+}
+distblk __wrap_computeSATD(StorablePicture *ref1, MEBlock *mv_block, distblk min_mcost, MotionVector *cand)
+{
+  if (!shim_on(FAM_DIST)) return __real_computeSATD(ref1, mv_block, min_mcost, cand);
+  return block_dist(JMB_SATD, ref1, mv_block, min_mcost, cand);
 }
 
 /* ---- transforms (lcommon/src/transform.c:20, :353) ---------------------------------------------------- */

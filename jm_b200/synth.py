@@ -42,3 +42,12 @@ def write_yuv420(path, lumas, bitdepth=8, textured_chroma=False):
                 f.write(y.astype(np.uint8).tobytes()); f.write(c.astype(np.uint8).tobytes())
             else:
                 f.write(y.astype("<u2").tobytes()); f.write(c.astype("<u2").tobytes())
+
+
+def write_yuv422(path, lumas, bitdepth=8):
+    """Planar 4:2:2 (chroma at half width, full height) with luma-derived chroma texture."""
+    with open(path, "wb") as f:
+        for y in lumas:
+            u = y[:, 0::2]; v = y[::-1, 1::2]
+            for p in (y, u, v):
+                f.write(p.astype(np.uint8 if bitdepth == 8 else "<u2").tobytes())

@@ -26,9 +26,13 @@ def _md5(path):
     return hashlib.md5(open(path, "rb").read()).hexdigest()
 
 
-def _make_yuv(path, w, h, n, seed):
+def _make_yuv(path, w, h, n, seed, fmt420=True):
     from jm_b200 import synth
-    synth.write_yuv420(path, synth.luma_frames(w, h, n, seed=seed, motion=(3, -2)), textured_chroma=True)
+    frames = synth.luma_frames(w, h, n, seed=seed, motion=(3, -2))
+    if fmt420:
+        synth.write_yuv420(path, frames, textured_chroma=True)
+    else:
+        synth.write_yuv422(path, frames)
 
 
 def _encode(exe, workdir, tag, w, h, frames, extra, env=None):
@@ -58,6 +62,14 @@ CONFIGS = {
                        "SearchMode=-1", "SearchRange=8", "NumberReferenceFrames=1", "AdaptiveRounding=1"],
     "high_8x8_cavlc_satd8x8": ["ProfileIDC=100", "SymbolMode=0", "RDOptimization=1", "Transform8x8Mode=1", "QPISlice=30", "QPPSlice=30",
                                "SearchMode=0", "SearchRange=8", "NumberReferenceFrames=2", "AdaptiveRounding=0"],
+    # BASELINE config 3 in small: EPZS (SearchMode 3) + 8x8 transform, High profile -- EPZS's predictor/threshold state machine
+    # stays JM's host code, every distortion it evaluates (computeSAD / computeSATD) comes from the device
+    "epzs_high_8x8": ["ProfileIDC=100", "SymbolMode=1", "RDOptimization=1", "Transform8x8Mode=1", "QPISlice=28", "QPPSlice=28",
+                      "SearchMode=3", "SearchRange=16", "NumberReferenceFrames=2", "AdaptiveRounding=1"],
+    # BASELINE config 4 in small: 4:2:2 input (High 4:2:2), SATD sub-pel refinement path
+    "yuv422_satd_subpel": ["ProfileIDC=122", "YUVFormat=2", "SymbolMode=1", "RDOptimization=1", "Transform8x8Mode=1", "QPISlice=28",
+                           "QPPSlice=28", "SearchMode=-1", "SearchRange=8", "NumberReferenceFrames=1", "AdaptiveRounding=1",
+                           "MEDistortionHPel=2", "MEDistortionQPel=2"],
 }
 
 
@@ -93,14 +105,17 @@ def test_no_gpu_is_a_loud_error(tmp_path):
 def test_bitstream_identical_to_stock_jm(tmp_path, name):
     """Motion vectors, quantised coefficients and the emitted bitstream, bit-exact against the JM CPU encoder."""
     w, h, frames = 96, 80, 4
-    _make_yuv(tmp_path / "input.yuv", w, h, frames, seed=11)
+    _make_yuv(tmp_path / "input.yuv", w, h, frames, seed=11, fmt420="YUVFormat=2" not in CONFIGS[name])
     r1 = _encode(REF, tmp_path, "ref", w, h, frames, CONFIGS[name])
     r2 = _encode(JMB, tmp_path, "gpu", w, h, frames, CONFIGS[name], env={"JMB_SHIM_VERBOSE": "1"})
     assert r1.returncode == 0, r1.stderr[-800:]
     assert r2.returncode == 0, r2.stderr[-800:]
     line = [l for l in r2.stderr.splitlines() if l.startswith("[jmb shim]")]
     assert line, "the shim did not report: was the GPU path used?"
-    counts = dict(zip(line[0].split()[2::2][:8], [int(x) for x in line[0].split()[3::2][:8]]))
-    assert counts["planes"] >= frames - 1 and counts["subpel"] > 0 and counts["quant4"] + counts["quant8"] > 0, line[0]
-    assert counts["full"] + counts["fastfull"] > 0, line[0]
+    counts = dict(zip(line[0].split()[2::2][:9], [int(x) for x in line[0].split()[3::2][:9]]))
+    assert counts["planes"] >= frames - 1 and counts["quant4"] + counts["quant8"] > 0, line[0]
+    if "SearchMode=3" in CONFIGS[name]:
+        assert counts["dist"] > 0, line[0]                       # EPZS: distortion oracle
+    else:
+        assert counts["full"] + counts["fastfull"] > 0 and counts["subpel"] > 0, line[0]
     _same_outputs(tmp_path, "ref", "gpu")
