@@ -32,7 +32,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H = 1920, 1088                  # coded size of 1080p (1920x1080 -> 68 MB rows)
+W, H = 1920, 1088                  # coded size of 1080p (1920x1080 -> 68 MB rows); --size 4k: 3840x2176
+SIZE_NAME = "1080p"
 SEARCH_RANGE = 32
 QP = 28
 N_SETS = 4
@@ -40,7 +41,7 @@ BYTES_PER_MB_REF = 13804           # 512 src + 12800 window + 49
 
 
 def workload_config(n_gpus, anchor_bcast=False):
-    return {"workload": "1080p 4:2:0 synthetic, FullSearch +-32 (SearchMode=-1) 41 partitions/MB + SATD sub-pel + "
+    return {"workload": f"{SIZE_NAME} 4:2:0 synthetic, FullSearch +-32 (SearchMode=-1) 41 partitions/MB + SATD sub-pel + "
                         "4x4 transform/quant of 7 partition modes, Baseline, 1 ref, QP28",
             "width": W, "height": H, "macroblocks_per_step": (W // 16) * (H // 16), "search_range": SEARCH_RANGE,
             "l2": f"rotating over {N_SETS} distinct input sets (> 126 MB in total)",
@@ -255,15 +256,17 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = BYTES_PER_MB_REF * n_mb / (k_ms / max(1, k_n) / 1e3) / 1e9
-    traffic = None
+    traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (tools/ncu_summary.py)
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "int_search_traffic.json")))["dram_bytes_per_launch"]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "int_search_traffic.json")))[args.size]["dram_bytes_per_launch"]
     except Exception:
         pass
     out["roofline"] = {"bound": "hbm", "kernel": "k_int_search", "achieved": achieved, "peak": peak, "unit": "GB/s",
                        "frac": achieved / peak, "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
                        "algorithmic_bytes_per_launch": BYTES_PER_MB_REF * n_mb, "launch_ms": k_ms / max(1, k_n),
-                       "note": "search-window model of SURVEY 8(d); the kernel is ALU(VABSDIFF4)-bound, not HBM-bound"}
+                       "note": "search-window model of SURVEY 8(d): 13804 B per macroblock*reference; the kernel is ALU-pipe "
+                               "(VABSDIFF4/PRMT/ISETP) bound, not HBM bound -- DESIGN.md 3; traffic < algorithmic bytes because "
+                               "neighbouring windows hit L2"}
 
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(sets[0][0], lam, ctx=ctx, api=api, budget_s=args.cpu_seconds)
@@ -381,7 +384,11 @@ def main():
                     help="N>1: broadcast rank 0's reference picture over NCCL every step (pictures sharing an anchor coded on different GPUs)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-mbs-per-core", type=int, default=24)
+    ap.add_argument("--size", default="1080p", choices=["1080p", "4k"], help="picture size (default = BASELINE configs[1])")
     args = ap.parse_args()
+    if args.size == "4k":
+        global W, H, SIZE_NAME
+        W, H, SIZE_NAME = 3840, 2176, "4K (3840x2160 coded 3840x2176)"
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -13,6 +13,25 @@ int jmb_fail(jmb_ctx *ctx, int code, const char *fmt, ...) {
   return code;
 }
 
+int jmb_make_tmap_u8(jmb_ctx *ctx, CUtensorMap *out, const void *base, int width, int height, int pitch, int box_w, int box_h) {
+  typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    JMB_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) return jmb_fail(ctx, JMB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    encode = (encode_fn)fn;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)width, (cuuint64_t)height}, gstride[1] = {(cuuint64_t)pitch};
+  const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h}, estride[2] = {1, 1};
+  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)base, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return jmb_fail(ctx, JMB_ERR_CUDA, "cuTensorMapEncodeTiled(%dx%d pitch %d box %dx%d) -> %d", width, height, pitch, box_w, box_h, (int)r);
+  return 0;
+}
+
 int jmb_reserve_host(jmb_ctx *ctx, void **p, size_t *cap, size_t bytes) {
   if (bytes <= *cap) return 0;
   if (*p) JMB_CUDA(ctx, cudaFreeHost(*p));
@@ -214,6 +233,8 @@ int jmb_ref_put(jmb_ctx *ctx, int slot, const uint16_t *luma, int width, int hei
     if (r->planes) { JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); JMB_CUDA(ctx, cudaFree(r->planes)); r->planes = nullptr; }
     JMB_CUDA(ctx, cudaMalloc(&r->planes, plane_bytes * 16 + 64));   // + slack: unaligned 4-sample reads fetch the next word
     r->w = width; r->h = height; r->W = W; r->H = H; r->pitch = pitch; r->plane_bytes = plane_bytes;
+    int rc = jmb_make_tmap_u8(ctx, &r->tmap_int, r->planes, W, H, pitch, JMB_WIN_BOX_W, JMB_WIN_BOX_H);
+    if (rc) return rc;
   }
   void *d_src = nullptr;
   int rc = to_device(ctx, luma, (size_t)stride * height * sizeof(uint16_t), loc, &d_src, &ctx->d_stage, &ctx->d_stage_cap);
@@ -291,6 +312,11 @@ int jmb_pic_begin(jmb_ctx *ctx, const uint16_t *cur, int width, int height, int 
     if (ctx->cur) { JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); JMB_CUDA(ctx, cudaFree(ctx->cur)); ctx->cur = nullptr; }
     JMB_CUDA(ctx, cudaMalloc(&ctx->cur, bytes));
     ctx->cur_cap = bytes;
+    ctx->cur_w = 0;
+  }
+  if (ctx->cur_w != width || ctx->cur_h != height) {
+    int rc = jmb_make_tmap_u8(ctx, &ctx->tmap_cur, ctx->cur, width, height, pitch, 16, 16);
+    if (rc) return rc;
   }
   ctx->cur_w = width; ctx->cur_h = height; ctx->cur_pitch = pitch;
   void *d_src = nullptr;

@@ -1,5 +1,6 @@
 // jmb_internal.h -- shared declarations of libjmb200 (not part of the C ABI).
 #pragma once
+#include <cuda.h>            // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -17,6 +18,7 @@ struct jmb_ref {
   int w = 0, h = 0, W = 0, H = 0, pitch = 0;
   size_t plane_bytes = 0;
   bool valid = false;
+  CUtensorMap tmap_int;      // TMA descriptor of the integer plane [0][0]: u8, W x H, box = search-window tile
 };
 
 struct jmb_ctx {
@@ -27,6 +29,7 @@ struct jmb_ctx {
   jmb_ref refs[JMB_MAX_REFS];
   // current picture (u8) and the reference list of this picture
   uint8_t *cur = nullptr; int cur_w = 0, cur_h = 0, cur_pitch = 0; size_t cur_cap = 0;
+  CUtensorMap tmap_cur;      // TMA descriptor of the current picture: box = one 16x16 macroblock
   int ref_list[JMB_MAX_REFS]; int nref = 0;
   jmb_me_config me;
   bool me_configured = false;
@@ -55,6 +58,10 @@ struct jmb_ctx {
 int jmb_check_device_errors(jmb_ctx *ctx);   // after a stream synchronisation
 
 int jmb_fail(jmb_ctx *ctx, int code, const char *fmt, ...);
+// 2-D u8 tensor map (width x height samples, `pitch` bytes per row, box_w x box_h tile, zero fill outside)
+int jmb_make_tmap_u8(jmb_ctx *ctx, CUtensorMap *out, const void *base, int width, int height, int pitch, int box_w, int box_h);
+#define JMB_WIN_BOX_W 128   // search-window tile staged by TMA in k_int_search: 128 x 87 samples
+#define JMB_WIN_BOX_H 87
 int jmb_reserve_host(jmb_ctx *ctx, void **p, size_t *cap, size_t bytes);
 int jmb_reserve_dev(jmb_ctx *ctx, void **p, size_t *cap, size_t bytes);
 

@@ -27,10 +27,11 @@ constexpr int NPART = 41;
 #define JMB_IS_NT 128
 #endif
 constexpr int NT = JMB_IS_NT;      // threads per CTA (multiple of 32, >= 64)
-constexpr int CW = 96;             // chunk of displacements handled per staging pass
+constexpr int CW = 92;             // chunk of displacements handled per staging pass (15 + CW + 15 + 4 <= the 128-byte TMA box)
 constexpr int CH = 72;             // multiple of 4 (a thread owns 4 vertically adjacent displacements)
-constexpr int WIN_PITCH = 120;     // bytes: <=3 alignment + CW + 15, rounded up to a word, + the fifth word
+constexpr int WIN_PITCH = JMB_WIN_BOX_W;   // bytes per staged window row = the TMA box width (>= CW + 15 + the fifth word)
 constexpr int WIN_ROWS = CH + 15;
+static_assert(WIN_ROWS == JMB_WIN_BOX_H && 15 + CW + 15 + 4 <= WIN_PITCH, "TMA box and window geometry disagree");
 constexpr int S1_COLS = 10, S1_RGS = 3, S1_ITEMS = S1_COLS * S1_RGS, S1_PITCH = 43;   // stage-1 neighbourhood
 constexpr int ADJ_PITCH = 44;      // words per column (>= NPART; 176 B keeps the 128-bit row reads conflict-free)
 constexpr int WQ_CAP = 192;          // per-warp queue of gate hits awaiting their exact evaluation
@@ -76,6 +77,29 @@ __device__ __forceinline__ unsigned bound_of(unsigned long long k, int lam) {
   const unsigned long long cost = k >> IDX_BITS, floor_ = 2ull * (unsigned)lam;
   if (cost < floor_) return 0u;
   return (unsigned)min(((cost - floor_) >> 5) + 1, 0x7fffffffull);   // compared as signed int after the column adjustment
+}
+
+// ---- TMA (cp.async.bulk.tensor) + mbarrier plumbing ---------------------------------------------------------------
+struct TMaps { CUtensorMap cur; CUtensorMap ref[JMB_MAX_REFS]; };   // kernel parameter (__grid_constant__)
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+  } while (!ok);
+}
+// one tile of a 2-D u8 tensor -> shared memory; coordinates may lie outside the tensor (zero fill)
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(dst)), "l"((unsigned long long)map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ unsigned sad4(unsigned a, unsigned b, unsigned c) {
@@ -224,11 +248,11 @@ __device__ __forceinline__ void sad_item(const uint8_t *win, const unsigned *ssr
 #endif
 __global__ void __launch_bounds__(NT, JMB_IS_MINB)
 k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups, jmb_me_res *__restrict__ res,
-             const uint8_t *__restrict__ cur, int cur_pitch,
-             const uint8_t *const *__restrict__ ref_planes, int ref_pitch, int w, int h, int R, int max_mvd_m1, int nref, int *__restrict__ err) {
+             const __grid_constant__ TMaps tm, int w, int h, int R, int max_mvd_m1, int nref, int *__restrict__ err) {
   __shared__ Grp G;
-  __shared__ __align__(16) uint8_t win[WIN_ROWS * WIN_PITCH];
-  __shared__ __align__(16) unsigned ssrc[16 * 4];
+  __shared__ __align__(128) uint8_t win[WIN_ROWS * WIN_PITCH];   // TMA destination: the search window tile
+  __shared__ __align__(128) unsigned ssrc[16 * 4];               // TMA destination: the 16x16 source macroblock
+  __shared__ __align__(8) unsigned long long mbar;
   __shared__ int sbox[12];
   __shared__ int wq_n[NT / 32];
   // gate tables (dynamic shared memory, INT_SEARCH_DYN_SMEM bytes): per column / per row and partition,
@@ -240,11 +264,10 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
   __shared__ unsigned short S1[S1_ITEMS * 4 * S1_PITCH];
 
   const int tid = threadIdx.x, g = blockIdx.x;
-  const int W = w + 2 * JMB_PAD_X, H = h + 2 * JMB_PAD_Y;
-
   if (tid < NT / 32) wq_n[tid] = 0;
   if (tid == 0) {
     sbox[0] = sbox[2] = 1 << 30; sbox[1] = sbox[3] = -(1 << 30); sbox[7] = 0; sbox[10] = NPART;
+    mbar_init(&mbar, 1);
     G.R = R; G.max_mvd_m1 = max_mvd_m1; G.thr[NPART] = G.thr[NPART + 1] = G.thr[NPART + 2] = 0;
   }
   __syncthreads();
@@ -287,38 +310,26 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
   __syncthreads();
   if (!sbox[7]) return;   // nothing but sub-pel-only requests in this group
   const int bx0 = sbox[0], bx1 = sbox[1], by0 = sbox[2], by1 = sbox[3], mbx = sbox[4], mby = sbox[5];
-  const uint8_t *ref = ref_planes[sbox[6]];
-
-  if (tid < 64) {   // source macroblock, one 32-bit word = 4 samples
-    int r = tid >> 2, c = tid & 3;
-    ssrc[tid] = *(const unsigned *)(cur + (size_t)(mby + r) * cur_pitch + mbx + 4 * c);
-  }
+  const CUtensorMap *ref_map = &tm.ref[sbox[6]];
 
   bool seeded = false;
+  unsigned phase = 0;
   for (int cy0 = by0; cy0 <= by1; cy0 += CH) {
     const int ch = min(CH, by1 - cy0 + 1);
     for (int cx0 = bx0; cx0 <= bx1; cx0 += CW) {
       const int cw = min(CW, bx1 - cx0 + 1);
       __syncthreads();
-      // stage the window with its left edge aligned down to a 4-sample boundary of the plane: staged byte
-      // (r, c) = plane sample (mby + cy0 + r + PAD_Y, sx0 + c).  Rows 0 .. ch+14; samples outside the padded
-      // plane are clamped (no valid candidate reads them).
-      const int ax = mbx + cx0 + JMB_PAD_X, sx0 = ax & ~3, xoff0 = ax - sx0;
-      const int nwords = ((xoff0 + cw + 15) >> 2) + 1, wrows = ch + 15;
-      for (int i = tid; i < wrows * nwords; i += NT) {
-        const int r = i / nwords, wi = i - r * nwords;
-        const int py = jmb_clip(0, H - 1, mby + cy0 + r + JMB_PAD_Y), px = sx0 + 4 * wi;
-        const uint8_t *rowp = ref + (size_t)py * ref_pitch;
-        unsigned v;
-        if (px >= 0 && px + 3 < W) v = __ldg((const unsigned *)(rowp + px));
-        else {
-          v = 0;
-#pragma unroll
-          for (int k = 0; k < 4; k++) v |= (unsigned)rowp[jmb_clip(0, W - 1, px + k)] << (8 * k);
-        }
-        *(unsigned *)(win + r * WIN_PITCH + 4 * wi) = v;
+      // Stage the search window with ONE 2-D TMA tile load.  TMA wants the innermost start coordinate on a 16-byte
+      // boundary, so the tile starts xoff0 (0..15) samples left of the window: staged byte (r, c) = plane sample
+      // (mby + cy0 + r + PAD_Y, mbx + cx0 + PAD_X - xoff0 + c); samples outside the padded plane arrive as zeros (no
+      // valid candidate reads them).  The first chunk also fetches the 16x16 source macroblock.  The copy runs while the
+      // threads build the gate tables below; everybody meets at the mbarrier before the first SAD.
+      const int ax = mbx + cx0 + JMB_PAD_X, xoff0 = ax & 15;
+      if (tid == 0) {
+        mbar_expect_tx(&mbar, WIN_ROWS * WIN_PITCH + (seeded ? 0 : 256));
+        tma_load_2d(win, ref_map, ax - xoff0, mby + cy0 + JMB_PAD_Y, &mbar);
+        if (!seeded) tma_load_2d(ssrc, &tm.cur, mbx, mby, &mbar);
       }
-      __syncthreads();
       const int nrg = (ch + 3) >> 2, mid = nrg >> 1;
       const bool s1 = !seeded;
       seeded = true;
@@ -331,6 +342,7 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
       const int col0 = jmb_clip(0, cw - ncol, G.rq[sbox[10]].cx - cx0 - ncol / 2);
       const int rg0 = jmb_clip(0, nrg - nrgs, ((G.rq[sbox[10]].cy - cy0) >> 2) - nrgs / 2);
       if (s1 && tid < 32) {
+        mbar_wait(&mbar, phase);
         if (tid < ncol * nrgs) {
           const int ic = col0 + tid % ncol, rg = rg0 + tid / ncol;
           unsigned acc[4][16];
@@ -375,6 +387,8 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
         }
       }
       if (tid == 0) sbox[11] = 0;      // next warp item of the sweep
+      mbar_wait(&mbar, phase);         // the window (and source) tiles have landed
+      phase ^= 1;
       __syncthreads();
       if (s1) {
         for (int pp = 0; pp < NPART; pp += NT / 4) {      // uniform trip count: the shuffles below need whole warps
@@ -384,7 +398,7 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
           const ReqS &q = G.rq[p];
           const int4 in = G.inner[p];
           const unsigned lam = (unsigned)q.lam;
-          unsigned bcost = 0xffffffffu; int bDx = 0, bDy = 0, bidx = 0;   // thread j looks at displacement row j of every item
+          unsigned bcost = 0xffffffffu; int bidx = 0;   // thread j looks at displacement row j of every item
           for (int rgi = 0; rgi < nrgs; rgi++) {
             const int Dy = cy0 + (rg0 + rgi) * 4 + j, my = 4 * Dy - q.py;
             if (Dy < in.z || Dy > in.w || Dy >= cy0 + ch) continue;
@@ -397,11 +411,11 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
               const unsigned cost = ((unsigned)sp[c * 4 * S1_PITCH] << 5) + ycost + lam * (unsigned)jmb_mvbits(mx);
               if (cost > bcost) continue;
               const int idx = jmb_spiral_index(Dx - q.cx, Dy - q.cy);
-              if (cost < bcost || idx < bidx) { bcost = cost; bidx = idx; bDx = Dx; bDy = Dy; }
+              if (cost < bcost || idx < bidx) { bcost = cost; bidx = idx; }
             }
           }
           if (bcost != 0xffffffffu) k = ((unsigned long long)bcost << IDX_BITS) | (unsigned)bidx;
-          (void)bDx; (void)bDy;
+
         }
         k = min(k, __shfl_xor_sync(0xffffffffu, k, 1));
         k = min(k, __shfl_xor_sync(0xffffffffu, k, 2));
@@ -659,8 +673,12 @@ static int me_search_impl(jmb_ctx *ctx, const jmb_me_req *reqs, int n, jmb_me_re
     JMB_CUDA(ctx, cudaFuncSetAttribute(k_int_search, cudaFuncAttributeMaxDynamicSharedMemorySize, INT_SEARCH_DYN_SMEM));
     smem_opt_in = true;
   }
-  k_int_search<<<n_groups, NT, INT_SEARCH_DYN_SMEM, ctx->stream>>>(d_reqs, d_groups, d_res, ctx->cur, ctx->cur_pitch, d_tab, r0.pitch,
-                                                  ctx->cur_w, ctx->cur_h, ctx->me.search_range, ctx->me.max_mvd - 1, ctx->nref, ctx->d_err);
+  TMaps tm;
+  memset(&tm, 0, sizeof(tm));
+  tm.cur = ctx->tmap_cur;
+  for (int i = 0; i < ctx->nref; i++) tm.ref[i] = ctx->refs[ctx->ref_list[i]].tmap_int;
+  k_int_search<<<n_groups, NT, INT_SEARCH_DYN_SMEM, ctx->stream>>>(d_reqs, d_groups, d_res, tm, ctx->cur_w, ctx->cur_h, ctx->me.search_range,
+                                                                  ctx->me.max_mvd - 1, ctx->nref, ctx->d_err);
   jmb_time_end(ctx, JMB_K_INT_SEARCH);
   JMB_LAUNCH_CHECK(ctx);
   if (any_subpel) { rc = jmb_launch_refine(ctx, d_reqs, d_res, n, d_tab); if (rc) return rc; }
