@@ -130,6 +130,27 @@ __device__ __forceinline__ int subblock_dist(const RefView &rv, const SrcBlk &sr
   return hadamard8(a);
 }
 
+// 4x4 sub-block, split in two so that the loads of several candidates can be in flight before the first Hadamard
+__device__ __forceinline__ void load_ref4(const RefView &rv, int cqx, int cqy, int sbx, int sby, int metric, unsigned (&rw)[4]) {
+  const uint8_t *ref;
+  if (metric == JMB_SATD) ref = umv(rv, cqy + ((sby * 4) << 2), cqx + ((sbx * 4) << 2));   // per-sub-block clamp
+  else ref = umv(rv, cqy, cqx) + (size_t)(sby * 4) * rv.pitch + sbx * 4;                     // partition clamp
+#pragma unroll
+  for (int y = 0; y < 4; y++) rw[y] = ld4(ref + (size_t)y * rv.pitch);
+}
+__device__ __forceinline__ int dist4(const SrcBlk &src, const unsigned (&rw)[4], int metric) {
+  int d[16];
+#pragma unroll
+  for (int y = 0; y < 4; y++)
+#pragma unroll
+    for (int x = 0; x < 4; x++) d[y * 4 + x] = (int)((src.w[y] >> (8 * x)) & 255) - (int)((rw[y] >> (8 * x)) & 255);
+  if (metric == JMB_SATD) return hadamard4(d);
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s += (metric == JMB_SAD) ? abs(d[i]) : d[i] * d[i];
+  return s;
+}
+
 // Refinement of up to RQ consecutive requests per CTA (one macroblock's 41 searches in the frame layout).
 // Work item = one sub-block of one request; the thread keeps the source sub-block in registers and walks
 // the candidates of the stage, adding its share of every candidate's distortion to sums[request][candidate].
@@ -145,7 +166,10 @@ struct RefineS {
   int first;                  // index of the request's first work item
 };
 
-__global__ void __launch_bounds__(RT)
+#ifndef JMB_RF_MINB
+#define JMB_RF_MINB 4
+#endif
+__global__ void __launch_bounds__(RT, JMB_RF_MINB)
 k_subpel_refine(const jmb_me_req *__restrict__ reqs, jmb_me_res *__restrict__ res, int n, const uint8_t *__restrict__ cur, int cur_pitch,
                 const uint8_t *const *__restrict__ ref_planes, size_t plane_bytes, int ref_pitch, int w, int h, jmb_me_config me, int nref, int *__restrict__ err) {
   __shared__ RefineS sr[RQ];
@@ -181,21 +205,23 @@ k_subpel_refine(const jmb_me_req *__restrict__ reqs, jmb_me_res *__restrict__ re
     const int metric = me.metric[1 + stage], step = stage ? 1 : 2;
     const int pos0 = stage ? me.start_qp : me.start_hp;
     const int pos1 = stage ? me.search_pos4 : (!me.start_hp ? max(1, me.search_pos2) : me.search_pos2);
-    if (tid == 0) {       // work items of this stage (the sub-block size depends on the stage's metric)
-      int tot = 0;
-      for (int i = 0; i < cnt; i++) {
-        RefineS &q = sr[i];
-        q.first = tot;
-        if (q.flags & JMB_REQ_SUBPEL) {
-          const int nn = (metric == JMB_SATD && (q.flags & JMB_REQ_TEST8X8)) ? 8 : 4;
-          q.n = (unsigned char)nn; q.nsx = (unsigned char)(c_bsx[q.blocktype] / nn);
-          q.nsub = (unsigned char)(q.nsx * (c_bsy[q.blocktype] / nn));
-          tot += q.nsub;
-        } else q.nsub = 0;
+    if (tid < cnt) {      // work items of this stage (the sub-block size depends on the stage's metric)
+      RefineS &q = sr[tid];
+      q.nsub = 0;
+      if (q.flags & JMB_REQ_SUBPEL) {
+        const int nn = (metric == JMB_SATD && (q.flags & JMB_REQ_TEST8X8)) ? 8 : 4;
+        q.n = (unsigned char)nn; q.nsx = (unsigned char)(c_bsx[q.blocktype] / nn);
+        q.nsub = (unsigned char)(q.nsx * (c_bsy[q.blocktype] / nn));
       }
-      s_total = tot;
     }
     for (int i = tid; i < cnt * 9; i += RT) (&sums[0][0])[i] = 0;
+    __syncthreads();
+    if (tid < cnt) {      // exclusive prefix sum of the item counts, one request per thread
+      int first = 0;
+      for (int i = 0; i < tid; i++) first += sr[i].nsub;
+      sr[tid].first = first;
+      if (tid == cnt - 1) s_total = first + sr[tid].nsub;
+    }
     __syncthreads();
     const int total = s_total;
     for (int item = tid; item < total; item += RT) {
@@ -207,10 +233,20 @@ k_subpel_refine(const jmb_me_req *__restrict__ reqs, jmb_me_res *__restrict__ re
       RefView rv{ref_planes[q.ref], plane_bytes, ref_pitch, w, h};
       SrcBlk src;
       load_src(src, cur, cur_pitch, q.pos_x + sbx * nn, q.pos_y + sby * nn, nn);
-      for (int pos = pos0; pos < pos1; pos++) {
-        const int cqx = (q.pos_x << 2) + q.mvx + step * c_spiral9[pos][0], cqy = (q.pos_y << 2) + q.mvy + step * c_spiral9[pos][1];
-        const int d = (nn == 4) ? subblock_dist(rv, src, cqx, cqy, sbx, sby, 4, metric) : subblock_dist(rv, src, cqx, cqy, sbx, sby, 8, metric);
-        atomicAdd(&sums[lo][pos], d);
+      const int bqx = (q.pos_x << 2) + q.mvx, bqy = (q.pos_y << 2) + q.mvy;
+      if (nn == 4) {
+        for (int pos = pos0; pos < pos1; pos += 3) {       // three candidates' reference rows in flight at a time
+          unsigned rw[3][4];
+#pragma unroll
+          for (int k = 0; k < 3; k++)
+            if (pos + k < pos1) load_ref4(rv, bqx + step * c_spiral9[pos + k][0], bqy + step * c_spiral9[pos + k][1], sbx, sby, metric, rw[k]);
+#pragma unroll
+          for (int k = 0; k < 3; k++)
+            if (pos + k < pos1) atomicAdd(&sums[lo][pos + k], dist4(src, rw[k], metric));
+        }
+      } else {
+        for (int pos = pos0; pos < pos1; pos++)
+          atomicAdd(&sums[lo][pos], subblock_dist(rv, src, bqx + step * c_spiral9[pos][0], bqy + step * c_spiral9[pos][1], sbx, sby, 8, metric));
       }
     }
     __syncthreads();
