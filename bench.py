@@ -83,7 +83,7 @@ class ClockSampler:
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
         except Exception:
@@ -93,14 +93,22 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def mark_begin(self):
+        self.i0 = len(self.rows)
+
+    def mark_end(self):
+        self.i1 = len(self.rows)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        i0, i1 = getattr(self, "i0", 0), getattr(self, "i1", len(self.rows)) + 1      # samples taken DURING the timed region
+        rows = self.rows[i0:i1] if i1 > i0 else self.rows
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for n, v in zip(names, r[3:7]):
@@ -201,12 +209,13 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing -------------------------------------------------------------------
+    sampler = ClockSampler(local); sampler.start()       # started early: nvidia-smi needs ~100 ms to deliver its first sample
     for s in range(args.warmup):
         step_device(s)
     ctx.sync()
     barrier()
     ctx.timing(True)
-    sampler = ClockSampler(local); sampler.start()
+    sampler.mark_begin()
     launches0 = ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -214,6 +223,7 @@ def run_ours(args):
         step_device(args.warmup + s)
     e1.record(stream)
     e1.synchronize()
+    sampler.mark_end()
     barrier()
     clocks = sampler.stop()
     gpu_launches = ctx.launches - launches0
@@ -375,15 +385,15 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--scene-cut", action="store_true", help="probe: unrelated reference picture (worst case for the search gate)")
     ap.add_argument("--anchor-bcast", action="store_true",
                     help="N>1: broadcast rank 0's reference picture over NCCL every step (pictures sharing an anchor coded on different GPUs)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--ref-mbs-per-core", type=int, default=24)
+    ap.add_argument("--ref-mbs-per-core", type=int, default=160)
     ap.add_argument("--size", default="1080p", choices=["1080p", "4k"], help="picture size (default = BASELINE configs[1])")
     args = ap.parse_args()
     if args.size == "4k":

@@ -10,7 +10,7 @@ timeout 900 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest_gpu.log 2>&1;
 tail -5 $O/${TAG}_pytest_gpu.log
 timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' > $O/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" | tee -a $O/${TAG}_smoke.log
 tail -3 $O/${TAG}_smoke.log
-timeout 600 python bench.py --steps 10 --warmup 3 > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; echo "bench rc=$?"
+timeout 600 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; echo "bench rc=$?"
 cat $O/${TAG}_bench.json; tail -5 $O/${TAG}_bench.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $O/${TAG}_bench_ref.json 2> $O/${TAG}_bench_ref.err; echo "ref rc=$?"
 cat $O/${TAG}_bench_ref.json; tail -5 $O/${TAG}_bench_ref.err
