@@ -36,7 +36,8 @@ constexpr int S1_COLS = 10, S1_RGS = 3, S1_ITEMS = S1_COLS * S1_RGS, S1_PITCH = 
 constexpr int ADJ_PITCH = 44;      // words per column (>= NPART; 176 B keeps the 128-bit row reads conflict-free)
 constexpr int WQ_CAP = 192;          // per-warp queue of gate hits awaiting their exact evaluation
 constexpr int HS_PITCH = NPART + 1;   // u16 per thread: SADs of the partitions of a displacement that met the gate
-constexpr int INT_SEARCH_DYN_SMEM = (CW + CH + CH / 4) * ADJ_PITCH * 4 + (NT / 32) * WQ_CAP * 8 + NT * HS_PITCH * 2;
+constexpr int S1_BYTES = S1_ITEMS * 4 * S1_PITCH * 2, SWEEP_BYTES = (NT / 32) * WQ_CAP * 8 + NT * HS_PITCH * 2;   // stage-1 sums and the sweep's queue / hit SADs share memory
+constexpr int INT_SEARCH_DYN_SMEM = (CW + CH / 4) * ADJ_PITCH * 4 + (S1_BYTES > SWEEP_BYTES ? S1_BYTES : SWEEP_BYTES);
 constexpr int IDX_BITS = 13;       // (2*64+1)^2 = 16641 > 8192: search_range <= 45 keeps idx < 8192
 
 struct PartGeom { unsigned char type, bx, by, w4, h4; };
@@ -244,7 +245,7 @@ __device__ __forceinline__ void sad_item(const uint8_t *win, const unsigned *ssr
 // arithmetic loop when one of its SADs beats the current bound (sad < thr), which after the seeding step
 // below is rare.  ALU-pipe work per displacement: 64 VABSDIFF4 + 19 PRMT + 41 ISETP.
 #ifndef JMB_IS_MINB
-#define JMB_IS_MINB 3
+#define JMB_IS_MINB 4
 #endif
 __global__ void __launch_bounds__(NT, JMB_IS_MINB)
 k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups, jmb_me_res *__restrict__ res,
@@ -258,10 +259,10 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
   // gate tables (dynamic shared memory, INT_SEARCH_DYN_SMEM bytes): per column / per row and partition,
   // floor(lambda * (bits_x - 1) / 32) and floor(lambda * (bits_y - 1) / 32)
   extern __shared__ __align__(16) unsigned dyn_smem[];
-  unsigned *const adjx = dyn_smem, *const adjy = dyn_smem + CW * ADJ_PITCH, *const adjy4 = adjy + CH * ADJ_PITCH;   // adjy4: min over the 4 rows of an item
+  unsigned *const adjx = dyn_smem, *const adjy4 = dyn_smem + CW * ADJ_PITCH;   // adjy4: min over the 4 rows of an item
   unsigned long long (*const wq)[WQ_CAP] = (unsigned long long (*)[WQ_CAP])(adjy4 + (CH / 4) * ADJ_PITCH);
+  unsigned short *const S1 = (unsigned short *)wq;      // stage 1 is over (barrier) before the sweep touches wq / hitsad
   unsigned short (*const hitsad)[HS_PITCH] = (unsigned short (*)[HS_PITCH])(wq + NT / 32);
-  __shared__ unsigned short S1[S1_ITEMS * 4 * S1_PITCH];
 
   const int tid = threadIdx.x, g = blockIdx.x;
   if (tid < NT / 32) wq_n[tid] = 0;
@@ -354,36 +355,30 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
           }
         }
       } else {
-        // column part of the gate: every candidate in column Dx pays at least lambda * (bits_x(Dx) + 1), i.e.
-        // lambda * (bits_x - 1) more than the constant folded into thr
-        for (int i = s1 ? tid - 32 : tid; i < cw * NPART; i += s1 ? NT - 32 : NT) {
-          const int ic = i / NPART, p = i - ic * NPART;
+        // Gate tables.  Column part: every candidate in column Dx pays at least lambda * (bits_x(Dx) + 1), i.e.
+        // lambda * (bits_x - 1) more than the constant folded into thr; row part likewise, minimised over the 4 rows
+        // of an item.  A column / row ON the clamp boundary stands for every candidate beyond it: no term there.
+        // A thread keeps one partition and strides over the columns / row groups.
+        const int t0 = s1 ? tid - 32 : tid, nthr = s1 ? NT - 32 : NT, lanes_per_p = nthr / NPART;   // nthr >= 41
+        const int p = t0 % NPART, sub = t0 / NPART;
+        if (sub < lanes_per_p) {
           const ReqS &q = G.rq[p];
-          unsigned a = 0;
-          // (a column ON the clamp boundary stands for every candidate beyond it: no column-specific term there)
-          if (q.active && cx0 + ic >= G.inner[p].x && cx0 + ic <= G.inner[p].y)
-            a = min(65535u, ((unsigned)q.lam * (unsigned)(jmb_mvbits(4 * (cx0 + ic) - q.px) - 1)) >> 5);
-          adjx[ic * ADJ_PITCH + p] = a;
-        }
-        for (int i = s1 ? tid - 32 : tid; i < ch * NPART; i += s1 ? NT - 32 : NT) {
-          const int ir = i / NPART, p = i - ir * NPART;
-          const ReqS &q = G.rq[p];
-          unsigned a = 0;
-          if (q.active && cy0 + ir >= G.inner[p].z && cy0 + ir <= G.inner[p].w)
-            a = min(65535u, ((unsigned)q.lam * (unsigned)(jmb_mvbits(4 * (cy0 + ir) - q.py) - 1)) >> 5);
-          adjy[ir * ADJ_PITCH + p] = a;
-        }
-        for (int i = s1 ? tid - 32 : tid; i < ((ch + 3) >> 2) * NPART; i += s1 ? NT - 32 : NT) {
-          const int rg = i / NPART, p = i - rg * NPART;
-          const ReqS &q = G.rq[p];
-          unsigned a = 0xffffffffu;
-          for (int r = 4 * rg; r < min(4 * rg + 4, ch); r++) {
-            unsigned ar = 0;
-            if (q.active && cy0 + r >= G.inner[p].z && cy0 + r <= G.inner[p].w)
-              ar = min(65535u, ((unsigned)q.lam * (unsigned)(jmb_mvbits(4 * (cy0 + r) - q.py) - 1)) >> 5);
-            a = min(a, ar);
+          const int4 in = G.inner[p];
+          const unsigned lam = (unsigned)q.lam;
+          for (int ic = sub; ic < cw; ic += lanes_per_p) {
+            unsigned a = 0;
+            if (q.active && cx0 + ic >= in.x && cx0 + ic <= in.y) a = min(65535u, (lam * (unsigned)(jmb_mvbits(4 * (cx0 + ic) - q.px) - 1)) >> 5);
+            adjx[ic * ADJ_PITCH + p] = a;
           }
-          adjy4[rg * ADJ_PITCH + p] = a;
+          for (int rg = sub; rg < ((ch + 3) >> 2); rg += lanes_per_p) {
+            unsigned a = 0xffffffffu;
+            for (int r = 4 * rg; r < min(4 * rg + 4, ch); r++) {
+              unsigned ar = 0;
+              if (q.active && cy0 + r >= in.z && cy0 + r <= in.w) ar = min(65535u, (lam * (unsigned)(jmb_mvbits(4 * (cy0 + r) - q.py) - 1)) >> 5);
+              a = min(a, ar);
+            }
+            adjy4[rg * ADJ_PITCH + p] = a;
+          }
         }
       }
       if (tid == 0) sbox[11] = 0;      // next warp item of the sweep
@@ -480,12 +475,16 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
             if ((int)v < (int)t[p]) { if (p < 32) mlo |= 1u << (p & 31); else mhi |= 1u << (p & 31); hitsad[tid][p] = (unsigned short)v; }
           });
           const int Dy = cy0 + row0 + s;
-          const unsigned *ay = adjy + (row0 + s) * ADJ_PITCH, *ax = adjx + ic * ADJ_PITCH;
+          const unsigned *ax = adjx + ic * ADJ_PITCH;
           while (mlo | mhi) {
             int p;
             if (mlo) { p = __ffs(mlo) - 1; mlo &= mlo - 1; } else { p = 32 + __ffs(mhi) - 1; mhi &= mhi - 1; }
             const unsigned v = hitsad[tid][p];
-            const int bound = (int)(*(volatile unsigned *)&G.thr[p] - ax[p] - ay[p]);
+            // second look with the exact row term of the mv cost (none on a clamp-boundary row)
+            const ReqS &q = G.rq[p];
+            unsigned ay = 0;
+            if (Dy >= G.inner[p].z && Dy <= G.inner[p].w) ay = min(65535u, ((unsigned)q.lam * (unsigned)(jmb_mvbits(4 * Dy - q.py) - 1)) >> 5);
+            const int bound = (int)(*(volatile unsigned *)&G.thr[p] - ax[p] - ay);
             if ((int)v < bound) {
               // hits are parked in the warp's queue and evaluated below by all 32 lanes together (a lone lane walking
               // its own hits would hold the other 31 idle); a full queue falls back to evaluating in place
