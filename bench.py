@@ -6,8 +6,8 @@ One "step" = the hot path over ONE 1080p P-picture (coded 1920x1088 = 8160 macro
   --  jmb_pic_begin          current picture to the device
   K1-K3 jmb_me_search_frame  full search +-32, all 41 partitions of every MB  (full_search_motion_estimation)
   K5  (same call)            half-/quarter-pel SATD refinement of every one   (sub_pel_motion_estimation)
-  K7/K8 7 x jmb_mc_tq        prediction -> residual -> forward4x4 -> quant for each of the 7 partition
-                             modes (what JM's RDO loop residual-codes per inter candidate)
+  K7/K8 jmb_mc_tq_modes      prediction -> residual -> forward4x4 -> quant for each of the 7 partition
+                             modes (what JM's RDO loop residual-codes per inter candidate), one launch
 Predictors are synthetic (true motion + per-MB / per-partition jitter), lambda from QP 28.
 
   value : device-timed (CUDA events on the library's stream), inputs resident in HBM, rotating over
@@ -152,12 +152,10 @@ def run_ours(args):
         ds = {k: torch.from_numpy(v.view(np.uint8).reshape(-1).copy()).cuda(local) for k, v in hs.items()}
         sets.append((hs, ds))
     d_res = torch.empty(n_mb * api.NPART * api.ME_RES.itemsize, dtype=torch.uint8, device=f"cuda:{local}")
-    d_pred = torch.empty(n_mb * api.MB_PRED.itemsize, dtype=torch.uint8, device=f"cuda:{local}")
     d_lev = torch.empty(7 * n_mb * 256, dtype=torch.int16, device=f"cuda:{local}")
     d_cost = torch.empty(7 * n_mb * 4, dtype=torch.int32, device=f"cuda:{local}")
     d_cbp = torch.empty(7 * n_mb, dtype=torch.int32, device=f"cuda:{local}")
     h_res = ctx.pinned(n_mb * api.NPART, api.ME_RES)
-    h_pred = ctx.pinned(n_mb, api.MB_PRED)
     h_lev = ctx.pinned((7, n_mb, 256), np.int16); h_cost = ctx.pinned((7, n_mb, 4), np.int32); h_cbp = ctx.pinned((7, n_mb), np.uint32)
     torch.cuda.synchronize()
 
@@ -173,18 +171,9 @@ def run_ours(args):
         ctx.ref_put(s % 2, ds["ref"].data_ptr(), api.DEVICE, shape=(H, W))
         ctx.pic_begin(ds["cur"].data_ptr(), [s % 2], api.DEVICE, shape=(H, W))
         ctx.me_search(ds["reqs"].data_ptr(), d_res.data_ptr(), api.DEVICE, n=n_mb * api.NPART, frame=True)
-        for m in range(7):
-            ctx.pred_from_results(d_res.data_ptr(), m + 1, api.DEVICE, n_mb=n_mb, out=d_pred.data_ptr())
-            ctx.mc_tq(d_pred.data_ptr(), qd, api.DEVICE, n_mb=n_mb,
-                      out=(d_lev[m * n_mb * 256:].data_ptr(), d_cost[m * n_mb * 4:].data_ptr(), d_cbp[m * n_mb:].data_ptr()))
+        ctx.mc_tq_modes(d_res.data_ptr(), qd, 0x7F, api.DEVICE, n_mb=n_mb, out=(d_lev.data_ptr(), d_cost.data_ptr(), d_cbp.data_ptr()))
 
-    parts = api.mb_partitions()
-    slot_of = np.zeros((8, 16), np.int64)
-    for mode in range(1, 8):
-        for b in range(16):
-            slot_of[mode, b] = api.part_slot(mode, b & 3, b >> 2)
-
-    e2e_t = {"ref_put": 0.0, "pic_begin": 0.0, "me_search": 0.0, "all_mv_fill": 0.0, "mc_tq": 0.0}
+    e2e_t = {"ref_put": 0.0, "pic_begin": 0.0, "me_search": 0.0, "mc_tq": 0.0}
 
     def step_host(s):
         hs, _ = sets[s % N_SETS]
@@ -193,14 +182,10 @@ def run_ours(args):
         ctx.pic_begin(hs["cur"], [s % 2]); t2 = time.perf_counter()
         ctx.me_search(hs["reqs"], h_res, frame=True); t3 = time.perf_counter()
         e2e_t["ref_put"] += t1 - t0; e2e_t["pic_begin"] += t2 - t1; e2e_t["me_search"] += t3 - t2
-        r = h_res.reshape(n_mb, api.NPART)
-        for m in range(7):     # all_mv fill (host scaffolding, mv_search.c:1005-1014), then residual coding on the device
-            t4 = time.perf_counter()
-            ctx._ck(ctx.L.jmb_pred_from_results(ctx.h, None, n_mb, m + 1, None, api.HOST))     # results + table stay in HBM
-            t5 = time.perf_counter()
-            ctx._ck(ctx.L.jmb_mc_tq(ctx.h, None, n_mb, qd.ctypes.data, h_lev[m].ctypes.data, h_cost[m].ctypes.data,
-                                    h_cbp[m].ctypes.data, api.HOST))
-            e2e_t["all_mv_fill"] += t5 - t4; e2e_t["mc_tq"] += time.perf_counter() - t5
+        # residual coding of all 7 partition modes from the results still resident in HBM; levels / costs / cbp come back
+        t5 = time.perf_counter()
+        ctx._ck(ctx.L.jmb_mc_tq_modes(ctx.h, None, n_mb, 0x7F, qd.ctypes.data, h_lev.ctypes.data, h_cost.ctypes.data, h_cbp.ctypes.data, api.HOST))
+        e2e_t["mc_tq"] += time.perf_counter() - t5
 
     def barrier():
         torch.cuda.synchronize()
@@ -229,8 +214,7 @@ def run_ours(args):
     gpu_launches = ctx.launches - launches0
     ms = e0.elapsed_time(e1)
     k_ms, k_n = ctx.timing_get("int_search")
-    kernel_break = {k: ctx.timing_get(k)[0] / max(1, args.steps) for k in ("subpel_planes", "pack_cur", "int_search", "subpel_refine",
-                                                                         "pred_from_results", "mc_tq")}
+    kernel_break = {k: ctx.timing_get(k)[0] / max(1, args.steps) for k in ("subpel_planes", "pack_cur", "int_search", "subpel_refine", "mc_tq")}
     ctx.timing(False)
     if world > 1:
         t = torch.tensor([ms], device=f"cuda:{local}"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
@@ -248,7 +232,7 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], device=f"cuda:{local}"); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
-    h2d = 2 * W * H * 2 + n_mb * api.NPART * api.ME_REQ.itemsize + 7 * api.QUANT_DESC.itemsize
+    h2d = 2 * W * H * 2 + n_mb * api.NPART * api.ME_REQ.itemsize + api.QUANT_DESC.itemsize
     d2h = n_mb * api.NPART * api.ME_RES.itemsize + 7 * n_mb * (512 + 16 + 4)
 
     out = {"metric": "macroblocks/sec 1080p full-search ME+DCT/quant", "value": world * n_mb * args.steps / (ms / 1e3),

@@ -189,6 +189,15 @@ int jmb_quant_blocks(jmb_ctx *ctx, const jmb_quant_desc *q, int do_transform, in
 int jmb_mc_tq(jmb_ctx *ctx, const jmb_mb_pred *pred, int n_mb, const jmb_quant_desc *q,
               int16_t *levels, int32_t *coeff_cost, uint32_t *cbp_blk, int loc);
 
+/* Residual coding of EVERY inter partition mode in one launch -- what JM's RDO loop does per inter candidate
+ * (luma_residual_coding called from RDCost_for_macroblocks, lencod/src/rdopt.c:1861, once per mode): for each mode m
+ * with bit m-1 set in mode_mask, prediction with the mode's motion vectors (taken from the 41 search results of the
+ * macroblock, reference 0) -> residual -> forward transform -> quantisation.  Outputs are mode-major and always sized
+ * for 7 modes: levels [7][n_mb][256], coeff_cost [7][n_mb][4], cbp_blk [7][n_mb] (layouts as jmb_mc_tq).
+ *   res == NULL: the results of the last jmb_me_search_frame call, still resident on the device. */
+int jmb_mc_tq_modes(jmb_ctx *ctx, const jmb_me_res *res, int n_mb, unsigned mode_mask, const jmb_quant_desc *q,
+                    int16_t *levels, int32_t *coeff_cost, uint32_t *cbp_blk, int loc);
+
 /* all_mv fill of BlockMotionSearch (lencod/src/mv_search.c:1005-1014): turn the results of a
  * jmb_me_search_frame call (41 per macroblock, canonical order) into the jmb_mb_pred of partition
  * mode `mode` (1..7) for every macroblock, reference 0.

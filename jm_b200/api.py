@@ -66,6 +66,7 @@ def load_library():
     L.jmb_quant_blocks.argtypes = [vp, vp, i, vp, i, vp, vp, vp, vp, vp, i]
     L.jmb_mc_tq.argtypes = [vp, vp, i, vp, vp, vp, vp, i]
     L.jmb_pred_from_results.argtypes = [vp, vp, i, i, vp, i]
+    L.jmb_mc_tq_modes.argtypes = [vp, vp, i, C.c_uint, vp, vp, vp, vp, i]
     L.jmb_timing_enable.argtypes = [vp, i]
     L.jmb_timing_get.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(i)]
     return L
@@ -241,6 +242,18 @@ class Context:
         else:
             levels, cost, cbp = out
         self._ck(self.L.jmb_mc_tq(self.h, _ptr(pred), n_mb, _ptr(qdesc), _ptr(levels), _ptr(cost), _ptr(cbp), loc))
+        return levels, cost, cbp
+
+    def mc_tq_modes(self, res, qdesc, mode_mask=0x7F, loc=HOST, n_mb=None, out=None):
+        """res=None: the search results still resident on the device.  Returns (levels[7][n_mb][256], cost[7][n_mb][4], cbp[7][n_mb])."""
+        if loc == HOST:
+            if res is not None:
+                res = np.ascontiguousarray(res, ME_RES)
+                n_mb = len(res) // NPART
+            levels = np.zeros((7, n_mb, 256), np.int16); cost = np.zeros((7, n_mb, 4), np.int32); cbp = np.zeros((7, n_mb), np.uint32)
+        else:
+            levels, cost, cbp = out
+        self._ck(self.L.jmb_mc_tq_modes(self.h, None if res is None else _ptr(res), n_mb, mode_mask, _ptr(qdesc), _ptr(levels), _ptr(cost), _ptr(cbp), loc))
         return levels, cost, cbp
 
     def pred_from_results(self, res, mode, loc=HOST, n_mb=None, out=None):

