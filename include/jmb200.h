@@ -198,6 +198,22 @@ int jmb_mc_tq(jmb_ctx *ctx, const jmb_mb_pred *pred, int n_mb, const jmb_quant_d
 int jmb_mc_tq_modes(jmb_ctx *ctx, const jmb_me_res *res, int n_mb, unsigned mode_mask, const jmb_quant_desc *q,
                     int16_t *levels, int32_t *coeff_cost, uint32_t *cbp_blk, int loc);
 
+/* inverse4x4 / inverse8x8 (lcommon/src/transform.c:70, :450) on nblk blocks of n*n int32 (dequantised coefficients), in place */
+int jmb_inverse_transform(jmb_ctx *ctx, int32_t *blocks, int nblk, int n, int loc);
+
+/* luma_residual_coding (lencod/src/macroblock.c:1182-1257) of a non-skipped inter macroblock of a P slice, for every
+ * partition mode with its bit set in mode_mask and every macroblock, in one launch: prediction from the macroblock's 41
+ * search results (reference 0) -> residual -> forward transform -> quant_{4x4,8x8,8x8cavlc}_normal -> per block inverse
+ * transform + sample_reconstruct (lcommon/src/blk_prediction.c:48) -> JM's coefficient thresholding (quadrant cost <=
+ * _LUMA_COEFF_COST_ -> reset_block, macroblock.c:806; macroblock cost <= _LUMA_MB_COEFF_COST_ -> luma cbp cleared,
+ * :1248-1255) -> distortion.  Outputs are mode-major, sized for 7 modes:
+ *   levels [7][n_mb][256] (as jmb_mc_tq, zeroed where reset_block applies), cost8 [7][n_mb][4] (after the resets),
+ *   cbp_blk [7][n_mb] (bits 0..15), cbp [7][n_mb] (bits 0..3), recon [7][n_mb][16][16] uint8 (may be NULL),
+ *   sse [7][n_mb] = sum (source - reconstruction)^2, the luma distortion RDCost_for_macroblocks charges (rdopt.c:1886).
+ * Adaptive rounding is not available here (its offsets are updated from macroblock to macroblock, q_around.c). */
+int jmb_luma_residual_coding_modes(jmb_ctx *ctx, const jmb_me_res *res, int n_mb, unsigned mode_mask, const jmb_quant_desc *q,
+                                   int16_t *levels, int32_t *cost8, uint32_t *cbp_blk, uint32_t *cbp, uint8_t *recon, int32_t *sse, int loc);
+
 /* all_mv fill of BlockMotionSearch (lencod/src/mv_search.c:1005-1014): turn the results of a
  * jmb_me_search_frame call (41 per macroblock, canonical order) into the jmb_mb_pred of partition
  * mode `mode` (1..7) for every macroblock, reference 0.

@@ -67,6 +67,8 @@ def load_library():
     L.jmb_mc_tq.argtypes = [vp, vp, i, vp, vp, vp, vp, i]
     L.jmb_pred_from_results.argtypes = [vp, vp, i, i, vp, i]
     L.jmb_mc_tq_modes.argtypes = [vp, vp, i, C.c_uint, vp, vp, vp, vp, i]
+    L.jmb_inverse_transform.argtypes = [vp, vp, i, i, i]
+    L.jmb_luma_residual_coding_modes.argtypes = [vp, vp, i, C.c_uint, vp, vp, vp, vp, vp, vp, vp, i]
     L.jmb_timing_enable.argtypes = [vp, i]
     L.jmb_timing_get.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(i)]
     return L
@@ -221,6 +223,24 @@ class Context:
         b = np.ascontiguousarray(blocks, np.int32).reshape(-1, n * n).copy()
         self._ck(self.L.jmb_forward_transform(self.h, _ptr(b), len(b), n, HOST))
         return b.reshape(-1, n, n)
+
+    def inverse_transform(self, blocks, n):
+        b = np.ascontiguousarray(blocks, np.int32).reshape(-1, n * n).copy()
+        self._ck(self.L.jmb_inverse_transform(self.h, _ptr(b), len(b), n, HOST))
+        return b.reshape(-1, n, n)
+
+    def luma_residual_coding_modes(self, res, qdesc, mode_mask=0x7F, n_mb=None, want_recon=True):
+        """res=None: resident search results.  Returns dict(levels, cost8, cbp_blk, cbp, recon, sse), all mode-major."""
+        if res is not None:
+            res = np.ascontiguousarray(res, ME_RES)
+            n_mb = len(res) // NPART
+        o = dict(levels=np.zeros((7, n_mb, 256), np.int16), cost8=np.zeros((7, n_mb, 4), np.int32), cbp_blk=np.zeros((7, n_mb), np.uint32),
+                 cbp=np.zeros((7, n_mb), np.uint32), recon=np.zeros((7, n_mb, 16, 16), np.uint8) if want_recon else None,
+                 sse=np.zeros((7, n_mb), np.int32))
+        self._ck(self.L.jmb_luma_residual_coding_modes(self.h, None if res is None else _ptr(res), n_mb, mode_mask, _ptr(qdesc), _ptr(o["levels"]),
+                                                       _ptr(o["cost8"]), _ptr(o["cbp_blk"]), _ptr(o["cbp"]),
+                                                       None if o["recon"] is None else _ptr(o["recon"]), _ptr(o["sse"]), HOST))
+        return o
 
     def quant_blocks(self, qdesc, coef, do_transform=0, cost0=0):
         n = int(qdesc["n"][0]); nn = n * n

@@ -49,6 +49,40 @@ __device__ void fwd8(int *b) {
   for (int i = 0; i < 8; i++) fwd8_1d(t + i, 8, b + i, 8);
 }
 
+// inverse4x4 / inverse8x8, lcommon/src/transform.c:70-119, :450-547
+__device__ __forceinline__ void inv4(int *b) {
+  int t[16];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int *p = b + 4 * i;
+    int p0 = p[0] + p[2], p1 = p[0] - p[2], p2 = (p[1] >> 1) - p[3], p3 = p[1] + (p[3] >> 1);
+    t[4 * i] = p0 + p3; t[4 * i + 1] = p1 + p2; t[4 * i + 2] = p1 - p2; t[4 * i + 3] = p0 - p3;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    int p0 = t[i] + t[8 + i], p1 = t[i] - t[8 + i], p2 = (t[4 + i] >> 1) - t[12 + i], p3 = t[4 + i] + (t[12 + i] >> 1);
+    b[i] = p0 + p3; b[4 + i] = p1 + p2; b[8 + i] = p1 - p2; b[12 + i] = p0 - p3;
+  }
+}
+__device__ __forceinline__ void inv8_1d(const int *p, int s, int *o, int os) {
+  int a0 = p[0] + p[4 * s], a1 = p[0] - p[4 * s], a2 = p[6 * s] - (p[2 * s] >> 1), a3 = p[2 * s] + (p[6 * s] >> 1);
+  int b0 = a0 + a3, b2 = a1 - a2, b4 = a1 + a2, b6 = a0 - a3;
+  a0 = -p[3 * s] + p[5 * s] - p[7 * s] - (p[7 * s] >> 1);
+  a1 = p[s] + p[7 * s] - p[3 * s] - (p[3 * s] >> 1);
+  a2 = -p[s] + p[7 * s] + p[5 * s] + (p[5 * s] >> 1);
+  a3 = p[3 * s] + p[5 * s] + p[s] + (p[s] >> 1);
+  int b1 = a0 + (a3 >> 2), b3 = a1 + (a2 >> 2), b5 = a2 - (a1 >> 2), b7 = a3 - (a0 >> 2);
+  o[0] = b0 + b7; o[os] = b2 - b5; o[2 * os] = b4 + b3; o[3 * os] = b6 + b1;
+  o[4 * os] = b6 - b1; o[5 * os] = b4 - b3; o[6 * os] = b2 + b5; o[7 * os] = b0 - b7;
+}
+__device__ void inv8(int *b) {
+  int t[64];
+#pragma unroll
+  for (int i = 0; i < 8; i++) inv8_1d(b + 8 * i, 1, t + 8 * i, 1);
+#pragma unroll
+  for (int i = 0; i < 8; i++) inv8_1d(t + i, 8, b + i, 8);
+}
+
 struct QOut { int nonzero; int cost; };
 
 // quantise one block in scan order.  coef: in = transformed, out = dequantised (JM leaves it in tblock).
@@ -209,6 +243,103 @@ __global__ void k_mc_tq_modes(const jmb_me_res *__restrict__ res, int n_mb, int 
   QOut o = quant_block<N, false>(q, rr, nullptr, nullptr, nullptr, levels + mo * 256 + b * N * N);
   if (o.cost) atomicAdd(&coeff_cost[mo * 4 + b8], o.cost);
   if (o.nonzero) atomicOr(&cbp_blk[mo], (N == 4) ? (1u << (by4 * 4 + bx4)) : (51u << (4 * b8 - 2 * (b8 & 1))));
+}
+
+template <int N>
+__global__ void k_inverse(int *blocks, int nblk) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nblk) return;
+  int b[N * N];
+  int *g = blocks + (size_t)i * N * N;
+#pragma unroll
+  for (int k = 0; k < N * N; k++) b[k] = g[k];
+  if (N == 4) inv4(b); else inv8(b);
+#pragma unroll
+  for (int k = 0; k < N * N; k++) g[k] = b[k];
+}
+
+// luma_residual_coding (lencod/src/macroblock.c:1182-1257) of a non-skipped inter macroblock of a P slice, for EVERY
+// partition mode of every macroblock in one launch: prediction (from the 41 search results) -> residual -> forward
+// transform -> quantisation -> per block inverse transform + sample_reconstruct (lcommon/src/blk_prediction.c:48) when a
+// level is nonzero, else the prediction -> coefficient thresholding: quadrants with cost <= _LUMA_COEFF_COST_ (4) are
+// reset (reset_block, macroblock.c:806), a macroblock whose summed cost is <= _LUMA_MB_COEFF_COST_ (5) drops its luma cbp
+// and takes the prediction (:1248-1255) -> SSE of the reconstruction against the source (what RDCost_for_macroblocks
+// charges as distortion).  Thread = one transform block; the 16 (4) threads of a macroblock exchange costs by shuffle.
+template <int N>
+__global__ void __launch_bounds__(128)
+k_luma_rc_modes(const jmb_me_res *__restrict__ res, int n_mb, int mb_w, unsigned mode_mask, const jmb_quant_desc *__restrict__ qd,
+                const uint8_t *__restrict__ cur, int cur_pitch, const uint8_t *__restrict__ ref_plane0,
+                size_t plane_bytes, int ref_pitch, int w, int h,
+                int16_t *__restrict__ levels, int *__restrict__ cost8, unsigned *__restrict__ cbp_blk, unsigned *__restrict__ cbp,
+                uint8_t *__restrict__ recon, int *__restrict__ sse) {
+  __shared__ jmb_quant_desc q;
+  for (int i = threadIdx.x; i < (int)(sizeof(q) / 4); i += blockDim.x) ((int *)&q)[i] = ((const int *)qd)[i];
+  __syncthreads();
+  constexpr int PER_MB = (N == 4) ? 16 : 4;
+  const int mode = blockIdx.y + 1;
+  if (!((mode_mask >> blockIdx.y) & 1)) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = t < n_mb * PER_MB;                         // dead threads still take part in the shuffles
+  const int mb = live ? t / PER_MB : 0, b = t % PER_MB;
+  const int mbx = (mb % mb_w) * 16, mby = (mb / mb_w) * 16;
+  const int bx4 = (N == 4) ? (b & 3) : (b & 1) * 2, by4 = (N == 4) ? (b >> 2) : (b >> 1) * 2;
+  const int b8 = (by4 >> 1) * 2 + (bx4 >> 1);
+  int ux4 = bx4, uy4 = by4;
+  if (mode < 5 || N == 8) { ux4 &= ~1; uy4 &= ~1; }
+  const int base[8] = {0, 0, 1, 3, 5, 9, 17, 25}, w4[8] = {4, 4, 4, 2, 2, 2, 1, 1}, h4[8] = {4, 4, 2, 4, 2, 1, 2, 1};
+  const jmb_me_res r = res[mb * 41 + base[mode] + (uy4 / h4[mode]) * (4 / w4[mode]) + ux4 / w4[mode]];
+  const int qx = ((mbx + ux4 * 4) << 2) + r.mv_x, qy = ((mby + uy4 * 4) << 2) + r.mv_y;
+  const int iy = jmb_clip(-JMB_PAD_Y, h + JMB_PAD_Y - 1 - 16, qy >> 2), ix = jmb_clip(-JMB_PAD_X, w + JMB_PAD_X - 1 - 16, qx >> 2);
+  const uint8_t *rp = ref_plane0 + (size_t)((qy & 3) * 4 + (qx & 3)) * plane_bytes +
+                      (size_t)(iy + JMB_PAD_Y + (by4 - uy4) * 4) * ref_pitch + (ix + JMB_PAD_X + (bx4 - ux4) * 4);
+  const uint8_t *sp = cur + (size_t)(mby + by4 * 4) * cur_pitch + mbx + bx4 * 4;
+  int rr[N * N];
+  uint8_t pr[N * N], sr[N * N];
+#pragma unroll
+  for (int y = 0; y < N; y++)
+#pragma unroll
+    for (int x = 0; x < N; x++) {
+      sr[y * N + x] = sp[(size_t)y * cur_pitch + x]; pr[y * N + x] = rp[(size_t)y * ref_pitch + x];
+      rr[y * N + x] = (int)sr[y * N + x] - (int)pr[y * N + x];
+    }
+  if (N == 4) fwd4(rr); else fwd8(rr);
+  const size_t mo = (size_t)blockIdx.y * n_mb + mb;          // mode-major output index
+  int16_t lv[N * N];
+  QOut o = quant_block<N, false>(q, rr, nullptr, nullptr, nullptr, lv);
+  // coefficient thresholding across the macroblock's threads
+  int c8 = o.cost;
+  if (N == 4) { c8 += __shfl_xor_sync(0xffffffffu, c8, 1); c8 += __shfl_xor_sync(0xffffffffu, c8, 4); }   // the quadrant's 4 blocks
+  const bool reset8 = c8 <= 4;                               // _LUMA_COEFF_COST_
+  if (reset8) c8 = 0;
+  int tot = c8;
+  if (N == 4) { tot += __shfl_xor_sync(0xffffffffu, tot, 2); tot += __shfl_xor_sync(0xffffffffu, tot, 8); }   // one lane per quadrant: b^2, b^8
+  else { tot += __shfl_xor_sync(0xffffffffu, tot, 1); tot += __shfl_xor_sync(0xffffffffu, tot, 2); }
+  const bool reset_mb = tot <= 5;                            // _LUMA_MB_COEFF_COST_
+  const bool coded = o.nonzero && !reset8 && !reset_mb;
+  int d2 = 0;
+  if (o.nonzero && !reset8 && !reset_mb) { if (N == 4) inv4(rr); else inv8(rr); }
+  uint8_t *rec = recon ? recon + mo * 256 + (by4 * 4) * 16 + bx4 * 4 : nullptr;
+#pragma unroll
+  for (int y = 0; y < N; y++)
+#pragma unroll
+    for (int x = 0; x < N; x++) {
+      const int v = coded ? min(max(((rr[y * N + x] + 32) >> 6) + (int)pr[y * N + x], 0), 255) : (int)pr[y * N + x];
+      const int d = (int)sr[y * N + x] - v;
+      d2 += d * d;
+      if (rec && live) rec[y * 16 + x] = (uint8_t)v;
+    }
+#pragma unroll
+  for (int sh = 1; sh < PER_MB; sh <<= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, sh);
+  unsigned bits = coded ? ((N == 4) ? (1u << (by4 * 4 + bx4)) : (51u << (4 * b8 - 2 * (b8 & 1)))) : 0u;
+  unsigned cb = coded ? (1u << b8) : 0u;
+#pragma unroll
+  for (int sh = 1; sh < PER_MB; sh <<= 1) { bits |= __shfl_xor_sync(0xffffffffu, bits, sh); cb |= __shfl_xor_sync(0xffffffffu, cb, sh); }
+  if (!live) return;
+  int16_t *lo = levels + mo * 256 + b * N * N;               // reset_block zeroes the quadrant's levels (cofAC memset)
+#pragma unroll
+  for (int k = 0; k < N * N; k++) lo[k] = reset8 ? (int16_t)0 : lv[k];
+  if (N == 8 || (b & 5) == 0) cost8[mo * 4 + b8] = c8;       // one lane per quadrant (4x4: bx4, by4 even)
+  if (b == 0) { cbp_blk[mo] = bits; cbp[mo] = cb; sse[mo] = d2; }
 }
 
 // all_mv fill of BlockMotionSearch (lencod/src/mv_search.c:1005-1014) for one partition mode of every
@@ -374,6 +505,78 @@ int jmb_mc_tq(jmb_ctx *ctx, const jmb_mb_pred *pred, int n_mb, const jmb_quant_d
     JMB_CUDA(ctx, cudaMemcpyAsync(levels, d_lv, (size_t)n_mb * 512, cudaMemcpyDeviceToHost, ctx->stream));
     JMB_CUDA(ctx, cudaMemcpyAsync(coeff_cost, d_cc, (size_t)n_mb * 16, cudaMemcpyDeviceToHost, ctx->stream));
     JMB_CUDA(ctx, cudaMemcpyAsync(cbp_blk, d_cbp, (size_t)n_mb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return JMB_OK;
+}
+
+int jmb_inverse_transform(jmb_ctx *ctx, int32_t *blocks, int nblk, int n, int loc) {
+  if (n != 4 && n != 8) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_inverse_transform: n=%d", n);
+  if (nblk <= 0) return JMB_OK;
+  JMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  size_t bytes = (size_t)nblk * n * n * 4;
+  int *d = blocks;
+  if (loc == JMB_HOST) {
+    int rc = jmb_reserve_dev(ctx, &ctx->d_stage, &ctx->d_stage_cap, bytes); if (rc) return rc;
+    JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage, blocks, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    d = (int *)ctx->d_stage;
+  }
+  jmb_time_begin(ctx, JMB_K_FORWARD);
+  if (n == 4) k_inverse<4><<<(nblk + 127) / 128, 128, 0, ctx->stream>>>(d, nblk);
+  else k_inverse<8><<<(nblk + 63) / 64, 64, 0, ctx->stream>>>(d, nblk);
+  jmb_time_end(ctx, JMB_K_FORWARD);
+  JMB_LAUNCH_CHECK(ctx);
+  if (loc == JMB_HOST) {
+    JMB_CUDA(ctx, cudaMemcpyAsync(blocks, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return JMB_OK;
+}
+
+int jmb_luma_residual_coding_modes(jmb_ctx *ctx, const jmb_me_res *res, int n_mb, unsigned mode_mask, const jmb_quant_desc *q,
+                                   int16_t *levels, int32_t *cost8, uint32_t *cbp_blk, uint32_t *cbp, uint8_t *recon, int32_t *sse, int loc) {
+  int rc = check_qdesc(ctx, q); if (rc) return rc;
+  if (!ctx->cur || ctx->nref == 0) return jmb_fail(ctx, JMB_ERR_STATE, "jmb_luma_residual_coding_modes: call jmb_pic_begin first");
+  const int mb_w = ctx->cur_w / 16, mb_total = mb_w * (ctx->cur_h / 16);
+  if (n_mb <= 0 || n_mb > mb_total) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_luma_residual_coding_modes: n_mb %d (picture has %d)", n_mb, mb_total);
+  if (!mode_mask || (mode_mask >> 7)) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_luma_residual_coding_modes: mode_mask 0x%x (bits 0..6 = modes 1..7)", mode_mask);
+  if (q->n == 8 && (mode_mask >> 4)) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_luma_residual_coding_modes: the 8x8 transform applies to modes 1..4 only");
+  if (q->around) return jmb_fail(ctx, JMB_ERR_UNSUPPORTED, "jmb_luma_residual_coding_modes: adaptive rounding carries state from macroblock to macroblock (q_around.c); use the leaf form");
+  if (!levels || !cost8 || !cbp_blk || !cbp || !sse) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_luma_residual_coding_modes: NULL output");
+  JMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const jmb_ref &r0 = ctx->refs[ctx->ref_list[0]];
+  const jmb_me_res *d_res = res;
+  if (!res) {
+    if (!ctx->last_res || ctx->last_res_n < n_mb * 41) return jmb_fail(ctx, JMB_ERR_STATE, "jmb_luma_residual_coding_modes: no resident search results for %d macroblocks", n_mb);
+    d_res = ctx->last_res;
+  } else if (loc == JMB_HOST) {
+    rc = jmb_reserve_dev(ctx, &ctx->d_stage4, &ctx->d_stage4_cap, (size_t)n_mb * 41 * sizeof(jmb_me_res)); if (rc) return rc;
+    JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage4, res, (size_t)n_mb * 41 * sizeof(jmb_me_res), cudaMemcpyHostToDevice, ctx->stream));
+    d_res = (const jmb_me_res *)ctx->d_stage4;
+  }
+  const jmb_quant_desc *d_q; rc = upload_qdesc(ctx, q, &d_q); if (rc) return rc;
+  const size_t n7 = (size_t)7 * n_mb;
+  int16_t *d_lv = levels; int *d_c8 = cost8; unsigned *d_cb = cbp_blk, *d_cbp = cbp; uint8_t *d_rec = recon; int *d_sse = sse;
+  if (loc == JMB_HOST) {     // one arena: levels | cost8 | cbp_blk | cbp | sse | recon
+    rc = jmb_reserve_dev(ctx, &ctx->d_stage3, &ctx->d_stage3_cap, n7 * (512 + 16 + 4 + 4 + 4 + 256)); if (rc) return rc;
+    char *a = (char *)ctx->d_stage3;
+    d_lv = (int16_t *)a; d_c8 = (int *)(a + n7 * 512); d_cb = (unsigned *)(a + n7 * 528); d_cbp = (unsigned *)(a + n7 * 532);
+    d_sse = (int *)(a + n7 * 536); d_rec = recon ? (uint8_t *)(a + n7 * 540) : nullptr;
+  }
+  jmb_time_begin(ctx, JMB_K_MC_TQ);
+  if (q->n == 4) k_luma_rc_modes<4><<<dim3((n_mb * 16 + 127) / 128, 7), 128, 0, ctx->stream>>>(d_res, n_mb, mb_w, mode_mask, d_q, ctx->cur, ctx->cur_pitch,
+        r0.planes, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_c8, d_cb, d_cbp, d_rec, d_sse);
+  else k_luma_rc_modes<8><<<dim3((n_mb * 4 + 127) / 128, 7), 128, 0, ctx->stream>>>(d_res, n_mb, mb_w, mode_mask, d_q, ctx->cur, ctx->cur_pitch,
+        r0.planes, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_c8, d_cb, d_cbp, d_rec, d_sse);
+  jmb_time_end(ctx, JMB_K_MC_TQ);
+  JMB_LAUNCH_CHECK(ctx);
+  if (loc == JMB_HOST) {
+    JMB_CUDA(ctx, cudaMemcpyAsync(levels, d_lv, n7 * 512, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaMemcpyAsync(cost8, d_c8, n7 * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaMemcpyAsync(cbp_blk, d_cb, n7 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaMemcpyAsync(cbp, d_cbp, n7 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaMemcpyAsync(sse, d_sse, n7 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (recon) JMB_CUDA(ctx, cudaMemcpyAsync(recon, d_rec, n7 * 256, cudaMemcpyDeviceToHost, ctx->stream));
     JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return JMB_OK;

@@ -10,7 +10,7 @@
  *       -Wl,--wrap=full_search_motion_estimation -Wl,--wrap=fast_full_search_motion_estimation \
  *       -Wl,--wrap=setup_fast_full_search -Wl,--wrap=sub_pel_motion_estimation \
  *       -Wl,--wrap=computeSAD -Wl,--wrap=computeSSE -Wl,--wrap=computeSATD \
- *       -Wl,--wrap=forward4x4 -Wl,--wrap=forward8x8 \
+ *       -Wl,--wrap=forward4x4 -Wl,--wrap=forward8x8 -Wl,--wrap=inverse4x4 -Wl,--wrap=inverse8x8 \
  *       -Wl,--wrap=quant_4x4_normal -Wl,--wrap=quant_4x4_around \
  *       -Wl,--wrap=quant_8x8_normal -Wl,--wrap=quant_8x8_around \
  *       -Wl,--wrap=quant_8x8cavlc_normal -Wl,--wrap=quant_8x8cavlc_around
@@ -58,6 +58,8 @@ void    __real_setup_fast_full_search(Macroblock *, MEBlock *, int);
 distblk __real_sub_pel_motion_estimation(Macroblock *, MotionVector *, MEBlock *, distblk, int *);
 void    __real_forward4x4(int **block, int **tblock, int pos_y, int pos_x);
 void    __real_forward8x8(int **block, int **tblock, int pos_y, int pos_x);
+void    __real_inverse4x4(int **tblock, int **block, int pos_y, int pos_x);
+void    __real_inverse8x8(int **tblock, int **block, int pos_x);
 int     __real_quant_4x4_normal(Macroblock *, int **, struct quant_methods *);
 int     __real_quant_4x4_around(Macroblock *, int **, struct quant_methods *);
 int     __real_quant_8x8_normal(Macroblock *, int **, struct quant_methods *);
@@ -443,6 +445,34 @@ void __wrap_forward8x8(int **block, int **tblock, int pos_y, int pos_x)
   if (!shim_on(FAM_TQ)) { __real_forward8x8(block, tblock, pos_y, pos_x); return; }
   S.calls[5]++;
   forward_nxn(block, tblock, pos_y, pos_x, 8);
+}
+
+/* inverse4x4 / inverse8x8 (lcommon/src/transform.c:70, :450): dequantised coefficients -> residual, used by the
+ * reconstruction half of residual_transform_quant_luma_* (block.c:708, transform8x8.c:572) and the chroma / intra paths */
+static void inverse_nxn(int **tblock, int **block, int pos_y, int pos_x, int n)
+{
+  int32_t buf[64];
+  int i, j, rc;
+  for (j = 0; j < n; j++)
+    for (i = 0; i < n; i++) buf[j * n + i] = tblock[pos_y + j][pos_x + i];
+  rc = jmb_inverse_transform(S.ctx, buf, 1, n, JMB_HOST);
+  if (rc) jmb_die("jmb_inverse_transform", rc);
+  for (j = 0; j < n; j++)
+    for (i = 0; i < n; i++) block[pos_y + j][pos_x + i] = buf[j * n + i];
+}
+
+void __wrap_inverse4x4(int **tblock, int **block, int pos_y, int pos_x)
+{
+  if (!shim_on(FAM_TQ)) { __real_inverse4x4(tblock, block, pos_y, pos_x); return; }
+  S.calls[4]++;
+  inverse_nxn(tblock, block, pos_y, pos_x, 4);
+}
+
+void __wrap_inverse8x8(int **tblock, int **block, int pos_x)
+{
+  if (!shim_on(FAM_TQ)) { __real_inverse8x8(tblock, block, pos_x); return; }
+  S.calls[5]++;
+  inverse_nxn(tblock, block, 0, pos_x, 8);
 }
 
 /* ---- quantisation (lencod/src/quant4x4_normal.c:39, quant4x4_around.c:40, quant8x8_normal.c:43,:123,

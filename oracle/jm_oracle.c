@@ -399,3 +399,104 @@ int jmo_quant(int variant, int *coef, int qp, const int *qparams, const uint8_t 
   for (int s = 0; s < (cavlc8 ? 4 : 1); s++) levels[17 * s * cavlc8 + nl[s]] = 0;
   return nonzero;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Inverse transforms.  lcommon/src/transform.c:70-119 (inverse4x4), :450-547 (inverse8x8).
+ * ---------------------------------------------------------------------------------------- */
+void jmo_inverse4x4(int *b)
+{
+  int t[16];
+  for (int i = 0; i < 4; i++) {                     /* horizontal */
+    const int *p = b + 4 * i;
+    int p0 = p[0] + p[2], p1 = p[0] - p[2], p2 = (p[1] >> 1) - p[3], p3 = p[1] + (p[3] >> 1);
+    t[4 * i] = p0 + p3; t[4 * i + 1] = p1 + p2; t[4 * i + 2] = p1 - p2; t[4 * i + 3] = p0 - p3;
+  }
+  for (int i = 0; i < 4; i++) {                     /* vertical */
+    int p0 = t[i] + t[8 + i], p1 = t[i] - t[8 + i], p2 = (t[4 + i] >> 1) - t[12 + i], p3 = t[4 + i] + (t[12 + i] >> 1);
+    b[i] = p0 + p3; b[4 + i] = p1 + p2; b[8 + i] = p1 - p2; b[12 + i] = p0 - p3;
+  }
+}
+
+static void inv8_1d(const int *p, int s, int *o, int os)
+{
+  int a0 = p[0] + p[4 * s], a1 = p[0] - p[4 * s], a2 = p[6 * s] - (p[2 * s] >> 1), a3 = p[2 * s] + (p[6 * s] >> 1);
+  int b0 = a0 + a3, b2 = a1 - a2, b4 = a1 + a2, b6 = a0 - a3;
+  a0 = -p[3 * s] + p[5 * s] - p[7 * s] - (p[7 * s] >> 1);
+  a1 =  p[s] + p[7 * s] - p[3 * s] - (p[3 * s] >> 1);
+  a2 = -p[s] + p[7 * s] + p[5 * s] + (p[5 * s] >> 1);
+  a3 =  p[3 * s] + p[5 * s] + p[s] + (p[s] >> 1);
+  int b1 = a0 + (a3 >> 2), b3 = a1 + (a2 >> 2), b5 = a2 - (a1 >> 2), b7 = a3 - (a0 >> 2);
+  o[0] = b0 + b7; o[os] = b2 - b5; o[2 * os] = b4 + b3; o[3 * os] = b6 + b1;
+  o[4 * os] = b6 - b1; o[5 * os] = b4 - b3; o[6 * os] = b2 + b5; o[7 * os] = b0 - b7;
+}
+
+void jmo_inverse8x8(int *b)
+{
+  int t[64];
+  for (int i = 0; i < 8; i++) inv8_1d(b + 8 * i, 1, t + 8 * i, 1);
+  for (int i = 0; i < 8; i++) inv8_1d(t + i, 8, b + i, 8);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Inter luma residual coding of one macroblock: luma_residual_coding (lencod/src/macroblock.c:1182-1257) for a
+ * non-skipped inter macroblock of a P slice, i.e. per 8x8 quadrant luma_residual_coding_8x8 / _16x16 (:832-1017):
+ * residual -> forward transform -> quantisation (quant_4x4_normal / quant_8x8_normal) -> per block inverse transform +
+ * sample_reconstruct (lcommon/src/blk_prediction.c:48, (r + 32) >> 6 + pred, clipped) when a level is nonzero, else the
+ * prediction; quadrants whose coefficient cost is <= _LUMA_COEFF_COST_ (4) are reset (reset_block :806: levels zeroed,
+ * cbp bits cleared, prediction copied); if the macroblock's summed cost is <= _LUMA_MB_COEFF_COST_ (5) the luma cbp is
+ * cleared and the whole prediction copied (levels are left as they are: JM's memset is commented out, :1254).
+ *   src, pred : 16x16 samples;  n = 4 | 8;  levels: 256 in scan order per block (4x4: block by*4+bx at [b*16], 8x8: b8 at [b8*64])
+ *   out: cost8[4] (after the resets), *cbp (bits 0..3), *cbp_blk (bits 0..15), recon 16x16, return SSE(src, recon)
+ * ---------------------------------------------------------------------------------------- */
+long long jmo_luma_residual_coding(const uint16_t *src, const uint16_t *pred, int n, int qp, const int *qparams,
+                                   const uint8_t *scan, const uint8_t *c_cost, int is_cavlc, int max_value,
+                                   short *levels, int *cost8, int *cbp, int *cbp_blk, uint16_t *recon)
+{
+  int sum = 0;
+  *cbp = 0; *cbp_blk = 0;
+  memset(levels, 0, 256 * sizeof(short));
+  for (int i = 0; i < 256; i++) recon[i] = pred[i];
+  for (int b8 = 0; b8 < 4; b8++) {
+    const int qy = (b8 >> 1) * 8, qx = (b8 & 1) * 8;
+    int cost = 0;
+    for (int sb = 0; sb < (n == 4 ? 4 : 1); sb++) {
+      const int by = qy + (n == 4 ? (sb >> 1) * 4 : 0), bx = qx + (n == 4 ? (sb & 1) * 4 : 0);
+      int blk[64], lv[68], rn[68];
+      for (int y = 0; y < n; y++)
+        for (int x = 0; x < n; x++) blk[y * n + x] = (int)src[(by + y) * 16 + bx + x] - (int)pred[(by + y) * 16 + bx + x];
+      if (n == 4) jmo_forward4x4(blk); else jmo_forward8x8(blk);
+      /* 8x8 + CAVLC: residual_transform_quant_luma_8x8_cavlc -> quant_8x8cavlc_normal, four interleaved lists (transform8x8.c:604) */
+      const int variant = n == 4 ? 0 : (is_cavlc ? 4 : 2);
+      int nz = jmo_quant(variant, blk, qp, qparams, scan, c_cost, is_cavlc, 0, lv, rn, NULL, &cost);
+      short *out = levels + (n == 4 ? ((by >> 2) * 4 + (bx >> 2)) * 16 : b8 * 64);
+      for (int s = 0; s < (variant == 4 ? 4 : 1); s++)
+        for (int k = 16 * s * (variant == 4), i = 17 * s * (variant == 4); lv[i] != 0; i++) { k += rn[i]; out[k++] = (short)lv[i]; }
+      if (nz) {
+        if (n == 4) { jmo_inverse4x4(blk); *cbp_blk |= 1 << ((by >> 2) * 4 + (bx >> 2)); }
+        else { jmo_inverse8x8(blk); *cbp_blk |= 51 << (4 * b8 - 2 * (b8 & 1)); }
+        *cbp |= 1 << b8;
+        for (int y = 0; y < n; y++)
+          for (int x = 0; x < n; x++)
+            recon[(by + y) * 16 + bx + x] = (uint16_t)iclip(0, max_value, ((blk[y * n + x] + 32) >> 6) + (int)pred[(by + y) * 16 + bx + x]);
+      }
+    }
+    if (cost <= 4) {                                  /* reset_block */
+      cost = 0;
+      *cbp &= 63 - (1 << b8);
+      *cbp_blk &= ~(51 << (4 * b8 - 2 * (b8 & 1)));
+      for (int y = 0; y < 8; y++)
+        for (int x = 0; x < 8; x++) recon[(qy + y) * 16 + qx + x] = pred[(qy + y) * 16 + qx + x];
+      if (n == 4) { for (int sb = 0; sb < 4; sb++) memset(levels + (((qy >> 2) + (sb >> 1)) * 4 + (qx >> 2) + (sb & 1)) * 16, 0, 16 * sizeof(short)); }
+      else memset(levels + b8 * 64, 0, 64 * sizeof(short));
+    }
+    cost8[b8] = cost;
+    sum += cost;
+  }
+  if (sum <= 5) {
+    *cbp &= 0xfffff0; *cbp_blk &= 0xff0000;
+    for (int i = 0; i < 256; i++) recon[i] = pred[i];
+  }
+  long long sse = 0;
+  for (int i = 0; i < 256; i++) { int d = (int)src[i] - (int)recon[i]; sse += d * d; }
+  return sse;
+}

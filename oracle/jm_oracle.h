@@ -64,6 +64,11 @@ int  jmo_hadamard_sad4x4(const int16_t *diff);
 int  jmo_hadamard_sad8x8(const int16_t *diff);
 
 /* variants as in oracle/ref_harness.c::jmref_quant */
+void jmo_inverse4x4(int *blk /* 16, in place */);
+void jmo_inverse8x8(int *blk /* 64, in place */);
+long long jmo_luma_residual_coding(const uint16_t *src, const uint16_t *pred, int n, int qp, const int *qparams,
+                                   const uint8_t *scan, const uint8_t *c_cost, int is_cavlc, int max_value,
+                                   short *levels, int *cost8, int *cbp, int *cbp_blk, uint16_t *recon);
 int jmo_quant(int variant, int *coef, int qp, const int *qparams, const uint8_t *scan,
               const uint8_t *c_cost, int is_cavlc, int adapt_rnd_weight,
               int *levels, int *runs, int *fadjust, int *coeff_cost);

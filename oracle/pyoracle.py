@@ -59,6 +59,10 @@ class Oracle:
         L.jmo_ffs_search.argtypes = [_u32p] + [C.c_int] * 8 + [C.c_int64, C.c_int, _i16p]
         L.jmo_forward4x4.argtypes = [_i32p]
         L.jmo_forward8x8.argtypes = [_i32p]
+        L.jmo_inverse4x4.argtypes = [_i32p]
+        L.jmo_inverse8x8.argtypes = [_i32p]
+        L.jmo_luma_residual_coding.restype = C.c_int64
+        L.jmo_luma_residual_coding.argtypes = [_u16p, _u16p, C.c_int, C.c_int, _i32p, _u8p, _u8p, C.c_int, C.c_int, _i16p, _i32p, _i32p, _i32p, _u16p]
         L.jmo_hadamard_sad4x4.argtypes = [_i16p]
         L.jmo_hadamard_sad8x8.argtypes = [_i16p]
         L.jmo_quant.argtypes = [C.c_int, _i32p, C.c_int, _i32p, _u8p, _u8p, C.c_int, C.c_int,
@@ -138,6 +142,25 @@ class Oracle:
         self.L.jmo_forward8x8(b.reshape(-1))
         return b
 
+    def inverse4x4(self, blk):
+        b = np.ascontiguousarray(blk, np.int32).copy()
+        self.L.jmo_inverse4x4(b.reshape(-1))
+        return b
+
+    def inverse8x8(self, blk):
+        b = np.ascontiguousarray(blk, np.int32).copy()
+        self.L.jmo_inverse8x8(b.reshape(-1))
+        return b
+
+    def luma_residual_coding(self, src, pred, n, qp, qparams, scan, c_cost, is_cavlc, max_value=255):
+        """One inter macroblock: (levels[256], cost8[4], cbp, cbp_blk, recon[16][16], sse)."""
+        levels = np.zeros(256, np.int16); cost8 = np.zeros(4, np.int32); cbp = np.zeros(1, np.int32); cbpb = np.zeros(1, np.int32)
+        recon = np.zeros((16, 16), np.uint16)
+        sse = self.L.jmo_luma_residual_coding(np.ascontiguousarray(src, np.uint16), np.ascontiguousarray(pred, np.uint16), n, qp,
+                                              np.ascontiguousarray(qparams, np.int32).reshape(-1), np.ascontiguousarray(scan, np.uint8).reshape(-1),
+                                              np.ascontiguousarray(c_cost, np.uint8), int(is_cavlc), max_value, levels, cost8, cbp, cbpb, recon)
+        return levels, cost8, int(cbp[0]), int(cbpb[0]), recon, int(sse)
+
     def hadamard4x4(self, d):
         return self.L.jmo_hadamard_sad4x4(np.ascontiguousarray(d, np.int16).reshape(-1))
 
@@ -191,6 +214,8 @@ class JMRef:
         L.jmref_mvbits.argtypes = [C.c_void_p, C.c_int]
         L.jmref_forward4x4.argtypes = [_i32p]
         L.jmref_forward8x8.argtypes = [_i32p]
+        L.jmref_inverse4x4.argtypes = [_i32p]
+        L.jmref_inverse8x8.argtypes = [_i32p]
         L.jmref_hadamard_sad4x4.argtypes = [_i16p]
         L.jmref_hadamard_sad8x8.argtypes = [_i16p]
         L.jmref_quant.argtypes = [C.c_void_p, C.c_int, _i32p, C.c_int, _i32p, _u8p, _u8p, C.c_int, C.c_int,
@@ -261,6 +286,16 @@ class JMRef:
     def forward8x8(self, blk):
         b = np.ascontiguousarray(blk, np.int32).copy()
         self.L.jmref_forward8x8(b.reshape(-1))
+        return b
+
+    def inverse4x4(self, blk):
+        b = np.ascontiguousarray(blk, np.int32).copy()
+        self.L.jmref_inverse4x4(b.reshape(-1))
+        return b
+
+    def inverse8x8(self, blk):
+        b = np.ascontiguousarray(blk, np.int32).copy()
+        self.L.jmref_inverse8x8(b.reshape(-1))
         return b
 
     def hadamard4x4(self, d):

@@ -303,6 +303,18 @@ static void call_fwd(void (*f)(int **, int **, int, int), int *blk, int n)
 }
 void jmref_forward4x4(int *blk16) { call_fwd(forward4x4, blk16, 4); }
 void jmref_forward8x8(int *blk64) { call_fwd(forward8x8, blk64, 8); }
+void jmref_inverse4x4(int *blk16)
+{
+  int *rows[4];
+  for (int i = 0; i < 4; i++) rows[i] = blk16 + i * 4;
+  inverse4x4(rows, rows, 0, 0);
+}
+void jmref_inverse8x8(int *blk64)
+{
+  int *rows[8];
+  for (int i = 0; i < 8; i++) rows[i] = blk64 + i * 8;
+  inverse8x8(rows, rows, 0);
+}
 int  jmref_hadamard_sad4x4(short *d) { return HadamardSAD4x4(d); }
 int  jmref_hadamard_sad8x8(short *d) { return HadamardSAD8x8(d); }
 

@@ -133,3 +133,21 @@ def test_gpu_transforms_and_quant(ctx):
             assert np.array_equal(o["levels"][0], g["levels"]) and np.array_equal(o["runs"][0], g["runs"])
             if variant & 1:
                 assert np.array_equal(o["fadjust"][0], g["fadjust"])
+
+
+def test_oracle_luma_residual_coding_consistency(oracle):
+    """The restated luma_residual_coding against its own pieces: a macroblock whose prediction equals the source codes
+    nothing and reconstructs the source; a strong residual is coded and reconstructs within the quantiser's error."""
+    src = G["cur_luma"][:16, :16]
+    qpar = T.q_params(28, 0, 4)
+    lv, c8, cbp, cbpb, rec, sse = oracle.luma_residual_coding(src, src, 4, 28, qpar, T.SNGL_SCAN, T.COEFF_COST4x4[0], 1)
+    assert not lv.any() and cbp == 0 and cbpb == 0 and sse == 0 and np.array_equal(rec, src)
+    pred = np.clip(src.astype(np.int32) + np.random.default_rng(1).integers(-40, 41, size=(16, 16)), 0, 255).astype(np.uint16)
+    lv, c8, cbp, cbpb, rec, sse = oracle.luma_residual_coding(src, pred, 4, 28, qpar, T.SNGL_SCAN, T.COEFF_COST4x4[0], 1)
+    assert cbp == 15 and cbpb == 0xFFFF and lv.any()
+    assert sse == int(((src.astype(np.int64) - rec.astype(np.int64)) ** 2).sum()) and sse < int(((src.astype(np.int64) - pred) ** 2).sum())
+    # inverse(dequant(quant(forward(x)))) ~ x: the pinned pieces compose
+    x = np.random.default_rng(2).integers(-60, 61, size=(4, 4))
+    q = oracle.quant(0, oracle.forward4x4(x), 20, T.q_params(20, 0, 4), T.SNGL_SCAN, T.COEFF_COST4x4[0], 1)
+    back = (oracle.inverse4x4(q["coef"]) + 32) >> 6
+    assert np.abs(back - x).max() <= 12          # QP 20: quantiser step 6.5

@@ -388,3 +388,61 @@ def test_mc_tq_modes_equals_per_mode_chain(ctx, n):
     if n == 8:
         with pytest.raises(api.JMBError):
             ctx.mc_tq_modes(res, qd, 0x7F)
+
+
+def test_inverse_transforms(ctx, oracle):
+    rng = np.random.default_rng(40)
+    b4 = rng.integers(-40000, 40001, size=(400, 4, 4)); b8 = rng.integers(-40000, 40001, size=(200, 8, 8))
+    g4 = ctx.inverse_transform(b4, 4); g8 = ctx.inverse_transform(b8, 8)
+    for i in range(len(b4)):
+        assert np.array_equal(g4[i], oracle.inverse4x4(b4[i]))
+    for i in range(len(b8)):
+        assert np.array_equal(g8[i], oracle.inverse8x8(b8[i]))
+
+
+@pytest.mark.parametrize("n,cav", [(4, 1), (4, 0), (8, 0), (8, 1)])
+@pytest.mark.parametrize("qp", [22, 30, 38])
+def test_luma_residual_coding_modes(ctx, oracle, n, cav, qp):
+    """Device luma_residual_coding (prediction .. thresholding .. reconstruction .. SSE) for every mode of every macroblock
+    against the oracle's restatement of macroblock.c:806-1257, fed with the same prediction (oracle planes + the mvs found)."""
+    w, h, R = 64, 48, 8
+    f = _frames(w, h, 41, motion=(2, -1))
+    ctx.configure(search_range=R)
+    ctx.ref_put(0, f[0]); ctx.pic_begin(f[1], [0])
+    reqs = _frame_reqs(w, h, np.random.default_rng(41), api.SEARCH_FULL, api.REQ_SUBPEL, lam=T.lambda_me(qp))
+    res = ctx.me_search(reqs, frame=True)
+    n_mb = len(reqs) // api.NPART
+    scan = T.SNGL_SCAN if n == 4 else (T.SNGL_SCAN8x8_CAVLC if cav else T.SNGL_SCAN8x8)
+    cc = (T.COEFF_COST4x4 if n == 4 else T.COEFF_COST8x8)[0]
+    qpar = T.q_params(qp, 0, n)
+    qd = api.quant_desc(n, qp, qpar, scan, cc, cav)
+    mask = 0x7F if n == 4 else 0x0F
+    got = ctx.luma_residual_coding_modes(res, qd, mask)
+    r = oracle.ref_create(f[0]); planes = oracle.planes(r); oracle.ref_destroy(r)
+    mbw = w // 16
+    seen_reset8 = seen_reset_mb = seen_coded = 0
+    for mode in range(1, 8):
+        if not (mask >> (mode - 1)) & 1:
+            continue
+        pred_tab = ctx.pred_from_results(res, mode)
+        for mb in range(n_mb):
+            mbx, mby = (mb % mbw) * 16, (mb // mbw) * 16
+            pred = np.zeros((16, 16), np.uint16)
+            for by4 in range(4):
+                for bx4 in range(4):
+                    ux4, uy4 = (bx4 & ~1, by4 & ~1) if (mode < 5 or n == 8) else (bx4, by4)
+                    mvx, mvy = [int(v) for v in pred_tab[mb]["mv"][uy4 * 4 + ux4]]
+                    qx, qy = ((mbx + ux4 * 4) << 2) + mvx, ((mby + uy4 * 4) << 2) + mvy
+                    iy = min(max(qy >> 2, -20), h + 20 - 1 - 16); ix = min(max(qx >> 2, -32), w + 32 - 1 - 16)
+                    y0 = iy + 20 + (by4 - uy4) * 4; x0 = ix + 32 + (bx4 - ux4) * 4
+                    pred[by4 * 4:by4 * 4 + 4, bx4 * 4:bx4 * 4 + 4] = planes[qy & 3, qx & 3, y0:y0 + 4, x0:x0 + 4]
+            src = f[1][mby:mby + 16, mbx:mbx + 16]
+            lv, c8, cbp, cbpb, rec, sse = oracle.luma_residual_coding(src, pred, n, qp, qpar, scan, cc, cav)
+            m = mode - 1
+            assert np.array_equal(got["levels"][m, mb], lv), (mode, mb)
+            assert np.array_equal(got["cost8"][m, mb], c8) and got["cbp"][m, mb] == cbp and got["cbp_blk"][m, mb] == cbpb, (mode, mb)
+            assert np.array_equal(got["recon"][m, mb], rec) and got["sse"][m, mb] == sse, (mode, mb)
+            seen_coded += cbp != 0; seen_reset_mb += (cbp == 0 and lv.any()); seen_reset8 += bool((c8 == 0).any() and cbp != 0)
+    assert seen_coded > 0 or qp > 30                        # coarse quantisers may threshold every macroblock away
+    no_recon = ctx.luma_residual_coding_modes(None, qd, mask, n_mb=n_mb, want_recon=False)        # resident results, no recon
+    assert np.array_equal(no_recon["sse"], got["sse"]) and np.array_equal(no_recon["levels"], got["levels"])

@@ -127,6 +127,17 @@ def test_transforms_and_hadamard(oracle, have_ref):
         assert oracle.hadamard8x8(b8) == ref.hadamard8x8(b8)
 
 
+def test_inverse_transforms(oracle, have_ref):
+    """inverse4x4 / inverse8x8 (lcommon/src/transform.c:70, :450) on dequantised-coefficient-like input."""
+    ref = po.JMRef(32, 32, search_range=4)
+    rng = np.random.default_rng(2)
+    for _ in range(300):
+        amp = int(rng.choice([64, 2000, 40000]))
+        b4 = rng.integers(-amp, amp + 1, size=(4, 4)); b8 = rng.integers(-amp, amp + 1, size=(8, 8))
+        assert np.array_equal(oracle.inverse4x4(b4), ref.inverse4x4(b4))
+        assert np.array_equal(oracle.inverse8x8(b8), ref.inverse8x8(b8))
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 def test_quant(oracle, have_ref, variant):
     ref = po.JMRef(32, 32, search_range=4)
