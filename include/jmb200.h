@@ -214,6 +214,12 @@ int jmb_inverse_transform(jmb_ctx *ctx, int32_t *blocks, int nblk, int n, int lo
 int jmb_luma_residual_coding_modes(jmb_ctx *ctx, const jmb_me_res *res, int n_mb, unsigned mode_mask, const jmb_quant_desc *q,
                                    int16_t *levels, int32_t *cost8, uint32_t *cbp_blk, uint32_t *cbp, uint8_t *recon, int32_t *sse, int loc);
 
+/* The same for n_mb macroblocks starting at picture address first_mb whose prediction is given explicitly
+ * (pred[i] describes macroblock first_mb + i: partition mode, reference and 4x4 mvs per quadrant, as in jmb_mc_tq) --
+ * what luma_residual_coding sees in currMB->b8x8[] / currSlice->all_mv.  Outputs are [n_mb]-sized. */
+int jmb_luma_residual_coding(jmb_ctx *ctx, const jmb_mb_pred *pred, int first_mb, int n_mb, const jmb_quant_desc *q,
+                             int16_t *levels, int32_t *cost8, uint32_t *cbp_blk, uint32_t *cbp, uint8_t *recon, int32_t *sse, int loc);
+
 /* all_mv fill of BlockMotionSearch (lencod/src/mv_search.c:1005-1014): turn the results of a
  * jmb_me_search_frame call (41 per macroblock, canonical order) into the jmb_mb_pred of partition
  * mode `mode` (1..7) for every macroblock, reference 0.

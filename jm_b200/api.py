@@ -68,6 +68,7 @@ def load_library():
     L.jmb_pred_from_results.argtypes = [vp, vp, i, i, vp, i]
     L.jmb_mc_tq_modes.argtypes = [vp, vp, i, C.c_uint, vp, vp, vp, vp, i]
     L.jmb_inverse_transform.argtypes = [vp, vp, i, i, i]
+    L.jmb_luma_residual_coding.argtypes = [vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, i]
     L.jmb_luma_residual_coding_modes.argtypes = [vp, vp, i, C.c_uint, vp, vp, vp, vp, vp, vp, vp, i]
     L.jmb_timing_enable.argtypes = [vp, i]
     L.jmb_timing_get.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(i)]
@@ -240,6 +241,14 @@ class Context:
         self._ck(self.L.jmb_luma_residual_coding_modes(self.h, None if res is None else _ptr(res), n_mb, mode_mask, _ptr(qdesc), _ptr(o["levels"]),
                                                        _ptr(o["cost8"]), _ptr(o["cbp_blk"]), _ptr(o["cbp"]),
                                                        None if o["recon"] is None else _ptr(o["recon"]), _ptr(o["sse"]), HOST))
+        return o
+
+    def luma_residual_coding(self, pred, qdesc, first_mb=0):
+        pred = np.ascontiguousarray(pred, MB_PRED); n_mb = len(pred)
+        o = dict(levels=np.zeros((n_mb, 256), np.int16), cost8=np.zeros((n_mb, 4), np.int32), cbp_blk=np.zeros(n_mb, np.uint32),
+                 cbp=np.zeros(n_mb, np.uint32), recon=np.zeros((n_mb, 16, 16), np.uint8), sse=np.zeros(n_mb, np.int32))
+        self._ck(self.L.jmb_luma_residual_coding(self.h, _ptr(pred), first_mb, n_mb, _ptr(qdesc), _ptr(o["levels"]), _ptr(o["cost8"]),
+                                                 _ptr(o["cbp_blk"]), _ptr(o["cbp"]), _ptr(o["recon"]), _ptr(o["sse"]), HOST))
         return o
 
     def quant_blocks(self, qdesc, coef, do_transform=0, cost0=0):

@@ -7,8 +7,8 @@
 //  quant_8x8cavlc_normal / _around  lencod/src/quant8x8_normal.c:123-202, quant8x8_around.c:133-223
 //  luma_prediction                  lencod/src/mc_prediction.c:117-236 (copy out of the quarter-pel
 //                                   plane the mv selects, UMVLine4X origin clamp per predicted block)
-//  luma_residual_coding_8x8         lencod/src/macroblock.c:919-1022 (8x8 prediction units for modes
-//                                   1..4, 4x4 units for modes 5..7; per-quadrant coeff_cost)
+//  luma_residual_coding(_8x8)       lencod/src/macroblock.c:919-1022, :1182-1257 (one 16x16 prediction unit for
+//                                   mode 1, 8x8 units for modes 2..4, 4x4 units for modes 5..7; per-quadrant coeff_cost)
 //
 // All arithmetic is int32 exactly as in JM.  One thread owns one transform block; the work is a
 // pure stream (residual in, levels out), i.e. HBM-bound.
@@ -184,6 +184,7 @@ __global__ void k_mc_tq(const jmb_mb_pred *__restrict__ pred, int n_mb, int mb_w
   // prediction unit: the 8x8 quadrant for modes 1..4, the 4x4 block for modes 5..7 (macroblock.c:946-971)
   int ux4 = bx4, uy4 = by4;
   if (mode < 5 || N == 8) { ux4 &= ~1; uy4 &= ~1; }
+  if (mode == 1) { ux4 = 0; uy4 = 0; }                       // P16x16: one 16x16 prediction, one origin clamp (macroblock.c:1225)
   const int mvx = mp->mv[uy4 * 4 + ux4][0], mvy = mp->mv[uy4 * 4 + ux4][1];
   const int qx = ((mbx + ux4 * 4) << 2) + mvx, qy = ((mby + uy4 * 4) << 2) + mvy;
   const int iy = jmb_clip(-JMB_PAD_Y, h + JMB_PAD_Y - 1 - 16, qy >> 2), ix = jmb_clip(-JMB_PAD_X, w + JMB_PAD_X - 1 - 16, qx >> 2);
@@ -226,6 +227,7 @@ __global__ void k_mc_tq_modes(const jmb_me_res *__restrict__ res, int n_mb, int 
   const int b8 = (by4 >> 1) * 2 + (bx4 >> 1);
   int ux4 = bx4, uy4 = by4;                                  // prediction unit (macroblock.c:946-971)
   if (mode < 5 || N == 8) { ux4 &= ~1; uy4 &= ~1; }
+  if (mode == 1) { ux4 = 0; uy4 = 0; }                       // P16x16: one 16x16 prediction, one origin clamp (macroblock.c:1225)
   const int base[8] = {0, 0, 1, 3, 5, 9, 17, 25}, w4[8] = {4, 4, 4, 2, 2, 2, 1, 1}, h4[8] = {4, 4, 2, 4, 2, 1, 2, 1};
   const jmb_me_res r = res[mb * 41 + base[mode] + (uy4 / h4[mode]) * (4 / w4[mode]) + ux4 / w4[mode]];
   const int qx = ((mbx + ux4 * 4) << 2) + r.mv_x, qy = ((mby + uy4 * 4) << 2) + r.mv_y;
@@ -267,8 +269,8 @@ __global__ void k_inverse(int *blocks, int nblk) {
 // charges as distortion).  Thread = one transform block; the 16 (4) threads of a macroblock exchange costs by shuffle.
 template <int N>
 __global__ void __launch_bounds__(128)
-k_luma_rc_modes(const jmb_me_res *__restrict__ res, int n_mb, int mb_w, unsigned mode_mask, const jmb_quant_desc *__restrict__ qd,
-                const uint8_t *__restrict__ cur, int cur_pitch, const uint8_t *__restrict__ ref_plane0,
+k_luma_rc_modes(const jmb_me_res *__restrict__ res, const jmb_mb_pred *__restrict__ pred, int first_mb, int n_mb, int mb_w, unsigned mode_mask,
+                const jmb_quant_desc *__restrict__ qd, const uint8_t *__restrict__ cur, int cur_pitch, const uint8_t *const *__restrict__ ref_planes,
                 size_t plane_bytes, int ref_pitch, int w, int h,
                 int16_t *__restrict__ levels, int *__restrict__ cost8, unsigned *__restrict__ cbp_blk, unsigned *__restrict__ cbp,
                 uint8_t *__restrict__ recon, int *__restrict__ sse) {
@@ -276,21 +278,28 @@ k_luma_rc_modes(const jmb_me_res *__restrict__ res, int n_mb, int mb_w, unsigned
   for (int i = threadIdx.x; i < (int)(sizeof(q) / 4); i += blockDim.x) ((int *)&q)[i] = ((const int *)qd)[i];
   __syncthreads();
   constexpr int PER_MB = (N == 4) ? 16 : 4;
-  const int mode = blockIdx.y + 1;
   if (!((mode_mask >> blockIdx.y) & 1)) return;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = t < n_mb * PER_MB;                         // dead threads still take part in the shuffles
-  const int mb = live ? t / PER_MB : 0, b = t % PER_MB;
-  const int mbx = (mb % mb_w) * 16, mby = (mb / mb_w) * 16;
+  const int mb = live ? t / PER_MB : 0, b = t % PER_MB;        // mb: index into the outputs / pred; picture address = first_mb + mb
+  const int mbx = ((first_mb + mb) % mb_w) * 16, mby = ((first_mb + mb) / mb_w) * 16;
   const int bx4 = (N == 4) ? (b & 3) : (b & 1) * 2, by4 = (N == 4) ? (b >> 2) : (b >> 1) * 2;
   const int b8 = (by4 >> 1) * 2 + (bx4 >> 1);
+  // prediction source: an explicit table (mode / mvs / reference per quadrant) or mode blockIdx.y+1 of the search results
+  const int mode = pred ? pred[mb].b8mode[b8] : blockIdx.y + 1;
   int ux4 = bx4, uy4 = by4;
   if (mode < 5 || N == 8) { ux4 &= ~1; uy4 &= ~1; }
-  const int base[8] = {0, 0, 1, 3, 5, 9, 17, 25}, w4[8] = {4, 4, 4, 2, 2, 2, 1, 1}, h4[8] = {4, 4, 2, 4, 2, 1, 2, 1};
-  const jmb_me_res r = res[mb * 41 + base[mode] + (uy4 / h4[mode]) * (4 / w4[mode]) + ux4 / w4[mode]];
-  const int qx = ((mbx + ux4 * 4) << 2) + r.mv_x, qy = ((mby + uy4 * 4) << 2) + r.mv_y;
+  if (mode == 1) { ux4 = 0; uy4 = 0; }                       // P16x16: one 16x16 prediction, one origin clamp (macroblock.c:1225)
+  int mvx, mvy, rf = 0;
+  if (pred) { mvx = pred[mb].mv[uy4 * 4 + ux4][0]; mvy = pred[mb].mv[uy4 * 4 + ux4][1]; rf = pred[mb].ref[b8]; }
+  else {
+    const int base[8] = {0, 0, 1, 3, 5, 9, 17, 25}, w4[8] = {4, 4, 4, 2, 2, 2, 1, 1}, h4[8] = {4, 4, 2, 4, 2, 1, 2, 1};
+    const jmb_me_res r = res[(first_mb + mb) * 41 + base[mode] + (uy4 / h4[mode]) * (4 / w4[mode]) + ux4 / w4[mode]];
+    mvx = r.mv_x; mvy = r.mv_y;
+  }
+  const int qx = ((mbx + ux4 * 4) << 2) + mvx, qy = ((mby + uy4 * 4) << 2) + mvy;
   const int iy = jmb_clip(-JMB_PAD_Y, h + JMB_PAD_Y - 1 - 16, qy >> 2), ix = jmb_clip(-JMB_PAD_X, w + JMB_PAD_X - 1 - 16, qx >> 2);
-  const uint8_t *rp = ref_plane0 + (size_t)((qy & 3) * 4 + (qx & 3)) * plane_bytes +
+  const uint8_t *rp = ref_planes[rf] + (size_t)((qy & 3) * 4 + (qx & 3)) * plane_bytes +
                       (size_t)(iy + JMB_PAD_Y + (by4 - uy4) * 4) * ref_pitch + (ix + JMB_PAD_X + (bx4 - ux4) * 4);
   const uint8_t *sp = cur + (size_t)(mby + by4 * 4) * cur_pitch + mbx + bx4 * 4;
   int rr[N * N];
@@ -362,6 +371,15 @@ static int check_qdesc(jmb_ctx *ctx, const jmb_quant_desc *q) {
   if (q->qp < 0 || q->qp > 87) return jmb_fail(ctx, JMB_ERR_ARG, "quant desc: qp %d", q->qp);
   for (int k = 0; k < q->n * q->n; k++)
     if (q->scan[k][0] >= q->n || q->scan[k][1] >= q->n) return jmb_fail(ctx, JMB_ERR_ARG, "quant desc: scan[%d] outside the block", k);
+  return 0;
+}
+
+static int upload_ref_table(jmb_ctx *ctx, const uint8_t *const **d_tab) {
+  const uint8_t *tab[JMB_MAX_REFS];
+  for (int i = 0; i < JMB_MAX_REFS; i++) tab[i] = i < ctx->nref ? ctx->refs[ctx->ref_list[i]].planes : nullptr;
+  int rc = jmb_reserve_dev(ctx, &ctx->d_reftab, &ctx->d_reftab_cap, sizeof(tab)); if (rc) return rc;
+  JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_reftab, tab, sizeof(tab), cudaMemcpyHostToDevice, ctx->stream));
+  *d_tab = (const uint8_t *const *)ctx->d_reftab;
   return 0;
 }
 
@@ -564,10 +582,11 @@ int jmb_luma_residual_coding_modes(jmb_ctx *ctx, const jmb_me_res *res, int n_mb
     d_sse = (int *)(a + n7 * 536); d_rec = recon ? (uint8_t *)(a + n7 * 540) : nullptr;
   }
   jmb_time_begin(ctx, JMB_K_MC_TQ);
-  if (q->n == 4) k_luma_rc_modes<4><<<dim3((n_mb * 16 + 127) / 128, 7), 128, 0, ctx->stream>>>(d_res, n_mb, mb_w, mode_mask, d_q, ctx->cur, ctx->cur_pitch,
-        r0.planes, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_c8, d_cb, d_cbp, d_rec, d_sse);
-  else k_luma_rc_modes<8><<<dim3((n_mb * 4 + 127) / 128, 7), 128, 0, ctx->stream>>>(d_res, n_mb, mb_w, mode_mask, d_q, ctx->cur, ctx->cur_pitch,
-        r0.planes, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_c8, d_cb, d_cbp, d_rec, d_sse);
+  const uint8_t *const *d_tab; rc = upload_ref_table(ctx, &d_tab); if (rc) return rc;
+  if (q->n == 4) k_luma_rc_modes<4><<<dim3((n_mb * 16 + 127) / 128, 7), 128, 0, ctx->stream>>>(d_res, nullptr, 0, n_mb, mb_w, mode_mask, d_q, ctx->cur, ctx->cur_pitch,
+        d_tab, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_c8, d_cb, d_cbp, d_rec, d_sse);
+  else k_luma_rc_modes<8><<<dim3((n_mb * 4 + 127) / 128, 7), 128, 0, ctx->stream>>>(d_res, nullptr, 0, n_mb, mb_w, mode_mask, d_q, ctx->cur, ctx->cur_pitch,
+        d_tab, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_c8, d_cb, d_cbp, d_rec, d_sse);
   jmb_time_end(ctx, JMB_K_MC_TQ);
   JMB_LAUNCH_CHECK(ctx);
   if (loc == JMB_HOST) {
@@ -577,6 +596,53 @@ int jmb_luma_residual_coding_modes(jmb_ctx *ctx, const jmb_me_res *res, int n_mb
     JMB_CUDA(ctx, cudaMemcpyAsync(cbp, d_cbp, n7 * 4, cudaMemcpyDeviceToHost, ctx->stream));
     JMB_CUDA(ctx, cudaMemcpyAsync(sse, d_sse, n7 * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (recon) JMB_CUDA(ctx, cudaMemcpyAsync(recon, d_rec, n7 * 256, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return JMB_OK;
+}
+
+int jmb_luma_residual_coding(jmb_ctx *ctx, const jmb_mb_pred *pred, int first_mb, int n_mb, const jmb_quant_desc *q,
+                             int16_t *levels, int32_t *cost8, uint32_t *cbp_blk, uint32_t *cbp, uint8_t *recon, int32_t *sse, int loc) {
+  int rc = check_qdesc(ctx, q); if (rc) return rc;
+  if (!ctx->cur || ctx->nref == 0) return jmb_fail(ctx, JMB_ERR_STATE, "jmb_luma_residual_coding: call jmb_pic_begin first");
+  const int mb_w = ctx->cur_w / 16, mb_total = mb_w * (ctx->cur_h / 16);
+  if (n_mb <= 0 || first_mb < 0 || first_mb + n_mb > mb_total) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_luma_residual_coding: macroblocks %d..%d (picture has %d)", first_mb, first_mb + n_mb - 1, mb_total);
+  if (q->around) return jmb_fail(ctx, JMB_ERR_UNSUPPORTED, "jmb_luma_residual_coding: adaptive rounding carries state from macroblock to macroblock (q_around.c); use the leaf form");
+  if (!pred || !levels || !cost8 || !cbp_blk || !cbp || !sse) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_luma_residual_coding: NULL argument");
+  JMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const jmb_ref &r0 = ctx->refs[ctx->ref_list[0]];
+  const jmb_mb_pred *d_pred = pred;
+  const size_t nn = (size_t)n_mb;
+  int16_t *d_lv = levels; int *d_c8 = cost8; unsigned *d_cb = cbp_blk, *d_cbp = cbp; uint8_t *d_rec = recon; int *d_sse = sse;
+  if (loc == JMB_HOST) {
+    for (int i = 0; i < n_mb; i++)
+      for (int k = 0; k < 4; k++)
+        if (pred[i].b8mode[k] < 1 || pred[i].b8mode[k] > 7 || pred[i].ref[k] >= ctx->nref || (q->n == 8 && pred[i].b8mode[k] > 4))
+          return jmb_fail(ctx, JMB_ERR_ARG, "jmb_luma_residual_coding: macroblock %d quadrant %d: mode %d ref %d", i, k, pred[i].b8mode[k], pred[i].ref[k]);
+    rc = jmb_reserve_dev(ctx, &ctx->d_stage, &ctx->d_stage_cap, nn * sizeof(jmb_mb_pred)); if (rc) return rc;
+    JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage, pred, nn * sizeof(jmb_mb_pred), cudaMemcpyHostToDevice, ctx->stream));
+    d_pred = (const jmb_mb_pred *)ctx->d_stage;
+    rc = jmb_reserve_dev(ctx, &ctx->d_stage3, &ctx->d_stage3_cap, nn * (512 + 16 + 4 + 4 + 4 + 256)); if (rc) return rc;
+    char *a = (char *)ctx->d_stage3;
+    d_lv = (int16_t *)a; d_c8 = (int *)(a + nn * 512); d_cb = (unsigned *)(a + nn * 528); d_cbp = (unsigned *)(a + nn * 532);
+    d_sse = (int *)(a + nn * 536); d_rec = recon ? (uint8_t *)(a + nn * 540) : nullptr;
+  }
+  const jmb_quant_desc *d_q; rc = upload_qdesc(ctx, q, &d_q); if (rc) return rc;
+  const uint8_t *const *d_tab; rc = upload_ref_table(ctx, &d_tab); if (rc) return rc;
+  jmb_time_begin(ctx, JMB_K_MC_TQ);
+  if (q->n == 4) k_luma_rc_modes<4><<<dim3((n_mb * 16 + 127) / 128, 1), 128, 0, ctx->stream>>>(nullptr, d_pred, first_mb, n_mb, mb_w, 1u, d_q, ctx->cur, ctx->cur_pitch,
+        d_tab, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_c8, d_cb, d_cbp, d_rec, d_sse);
+  else k_luma_rc_modes<8><<<dim3((n_mb * 4 + 127) / 128, 1), 128, 0, ctx->stream>>>(nullptr, d_pred, first_mb, n_mb, mb_w, 1u, d_q, ctx->cur, ctx->cur_pitch,
+        d_tab, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_c8, d_cb, d_cbp, d_rec, d_sse);
+  jmb_time_end(ctx, JMB_K_MC_TQ);
+  JMB_LAUNCH_CHECK(ctx);
+  if (loc == JMB_HOST) {
+    JMB_CUDA(ctx, cudaMemcpyAsync(levels, d_lv, nn * 512, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaMemcpyAsync(cost8, d_c8, nn * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaMemcpyAsync(cbp_blk, d_cb, nn * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaMemcpyAsync(cbp, d_cbp, nn * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaMemcpyAsync(sse, d_sse, nn * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (recon) JMB_CUDA(ctx, cudaMemcpyAsync(recon, d_rec, nn * 256, cudaMemcpyDeviceToHost, ctx->stream));
     JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return JMB_OK;

@@ -13,7 +13,7 @@
  *       -Wl,--wrap=forward4x4 -Wl,--wrap=forward8x8 -Wl,--wrap=inverse4x4 -Wl,--wrap=inverse8x8 \
  *       -Wl,--wrap=quant_4x4_normal -Wl,--wrap=quant_4x4_around \
  *       -Wl,--wrap=quant_8x8_normal -Wl,--wrap=quant_8x8_around \
- *       -Wl,--wrap=quant_8x8cavlc_normal -Wl,--wrap=quant_8x8cavlc_around
+ *       -Wl,--wrap=quant_8x8cavlc_normal -Wl,--wrap=quant_8x8cavlc_around -Wl,--wrap=luma_residual_coding
  *
  * No JM source file is edited: every symbol above is defined in one translation unit and referenced
  * from another, so the linker redirects the reference to __wrap_<sym>.
@@ -66,6 +66,7 @@ int     __real_quant_8x8_normal(Macroblock *, int **, struct quant_methods *);
 int     __real_quant_8x8_around(Macroblock *, int **, struct quant_methods *);
 int     __real_quant_8x8cavlc_normal(Macroblock *, int **, struct quant_methods *, int ***);
 int     __real_quant_8x8cavlc_around(Macroblock *, int **, struct quant_methods *, int ***);
+void    __real_luma_residual_coding(Macroblock *currMB);
 distblk __real_computeSAD(StorablePicture *, MEBlock *, distblk, MotionVector *);
 distblk __real_computeSSE(StorablePicture *, MEBlock *, distblk, MotionVector *);
 distblk __real_computeSATD(StorablePicture *, MEBlock *, distblk, MotionVector *);
@@ -85,6 +86,8 @@ static struct
   jmb_me_config    cfg;
   int              cfg_valid;
   unsigned long    calls[9];
+  int              verify;            /* JMB_SHIM_VERIFY=1: differential check of the device luma_residual_coding */
+  unsigned long    verified;
 } S;
 
 /* JM's convention for fatal conditions is error(text, code) -> message on stderr, exit(code) (lencod/src/lencod.c).
@@ -110,6 +113,8 @@ static void unsupported(const char *what)
 
 static void report(void)
 {
+  if (S.init == 1 && S.verify)
+    fprintf(stderr, "[jmb shim] luma_residual_coding verified on %lu macroblock codings (levels, cbp, cbp_blk, reconstruction)\n", S.verified);
   if (S.init == 1 && getenv("JMB_SHIM_VERBOSE"))
     fprintf(stderr, "[jmb shim] planes %lu  full %lu  fastfull %lu  subpel %lu  fwd4 %lu  fwd8 %lu  quant4 %lu  quant8 %lu  dist %lu  kernel launches %llu\n",
             S.calls[0], S.calls[1], S.calls[2], S.calls[3], S.calls[4], S.calls[5], S.calls[6], S.calls[7], S.calls[8],
@@ -133,6 +138,7 @@ static int shim_on(int family)
         fatal(700);
       }
       S.init = 1;
+      S.verify = getenv("JMB_SHIM_VERIFY") != NULL;
       if (off)
       {
         if (strstr(off, "planes")) S.off |= FAM_PLANES;
@@ -418,6 +424,145 @@ distblk __wrap_computeSATD(StorablePicture *ref1, MEBlock *mv_block, distblk min
 {
   if (!shim_on(FAM_DIST)) return __real_computeSATD(ref1, mv_block, min_mcost, cand);
   return block_dist(JMB_SATD, ref1, mv_block, min_mcost, cand);
+}
+
+/* ---- differential check of the whole-macroblock device path against JM itself (JMB_SHIM_VERIFY=1) -----------------
+ * luma_residual_coding (lencod/src/macroblock.c:1182) runs as usual (its leaves are already on the GPU); afterwards the
+ * same macroblock is coded once more by jmb_luma_residual_coding from JM's own state (partition modes in currMB->b8x8,
+ * mvs in currSlice->all_mv, references in enc_picture->mv_info) and the device's levels, cbp, cbp_blk and reconstruction
+ * must equal what JM left in cofAC / currMB / enc_picture.  Any difference stops the encoder.  H.264's zig-zag scans and
+ * JM's coefficient-cost rows are file-static in JM (block.c:72-77,170-176, transform8x8.c:44-90), so the wrapper carries them. */
+static const uint8_t V_SCAN4[16][2] = {{0,0},{1,0},{0,1},{0,2},{1,1},{2,0},{3,0},{2,1},{1,2},{0,3},{1,3},{2,2},{3,1},{3,2},{2,3},{3,3}};
+static const uint8_t V_COST4[3][16] = {{3,2,2,1,1,1,0,0,0,0,0,0,0,0,0,0},{9,9,9,9,9,9,9,9,9,9,9,9,9,9,9,9},{3,2,2,1,1,1,0,0,0,0,0,0,0,0,0,0}};
+
+static void zigzag8(uint8_t scan[64][2])
+{
+  int i = 0, j = 0, up = 1, k;
+  for (k = 0; k < 64; k++)
+  {
+    scan[k][0] = (uint8_t)i; scan[k][1] = (uint8_t)j;
+    if (up) { if (i == 7) { j++; up = 0; } else if (j == 0) { i++; up = 0; } else { i++; j--; } }
+    else    { if (j == 7) { i++; up = 1; } else if (i == 0) { j++; up = 1; } else { i--; j++; } }
+  }
+}
+
+static void verify_mismatch(Macroblock *currMB, const char *what, int a, int b)
+{
+  snprintf(errortext, ET_SIZE, "libjmb200 shim: VERIFY luma_residual_coding: macroblock %d (type %d): %s differs (JM %d, device %d)",
+           currMB->mbAddrX, currMB->mb_type, what, a, b);
+  fatal(703);
+}
+
+void __wrap_luma_residual_coding(Macroblock *currMB)
+{
+  Slice *currSlice = currMB->p_Slice;
+  VideoParameters *p_Vid = currMB->p_Vid;
+  jmb_mb_pred pred;
+  jmb_quant_desc d;
+  static int16_t levels[256];
+  static uint8_t recon[256];
+  int32_t cost8[4], sse;
+  uint32_t cbp_blk, cbp;
+  int k, bx, by, i, j, rc, n, cavlc8, qp;
+  uint8_t scan8[64][2];
+
+  __real_luma_residual_coding(currMB);
+  if (S.init != 1 || !S.verify || (S.off & FAM_TQ)) return;
+  if (currSlice->slice_type != P_SLICE || p_Vid->AdaptiveRounding || p_Vid->structure != FRAME || currSlice->mb_aff_frame_flag) return;
+  if (!(currMB->mb_type == P16x16 || currMB->mb_type == P16x8 || currMB->mb_type == P8x16 || currMB->mb_type == P8x8)) return;
+  if (currSlice->weighted_prediction || currSlice->NoResidueDirect == 1 || p_Vid->bitdepth_luma != 8) return;
+  n = currMB->luma_transform_size_8x8_flag ? 8 : 4;
+  cavlc8 = (n == 8 && currSlice->symbol_mode == CAVLC);
+  memset(&pred, 0, sizeof(pred));
+  for (k = 0; k < 4; k++)
+  {
+    PicMotionParams *m = &p_Vid->enc_picture->mv_info[currMB->block_y + 2 * (k >> 1)][currMB->block_x + 2 * (k & 1)];
+    int mode = currMB->b8x8[k].mode, ref = m->ref_idx[LIST_0], slot = -1;
+    MEBlock probe;
+    if (currMB->b8x8[k].pdir != 0 || mode < 1 || mode > 7 || ref < 0 || (n == 8 && mode > 4)) return;
+    memset(&probe, 0, sizeof(probe));
+    slot = ref_index_of(p_Vid, currSlice, &probe, currSlice->listX[LIST_0 + currMB->list_offset][ref]);
+    pred.b8mode[k] = (uint8_t)mode;
+    pred.ref[k] = (uint8_t)slot;
+    for (by = 2 * (k >> 1); by < 2 * (k >> 1) + 2; by++)
+      for (bx = 2 * (k & 1); bx < 2 * (k & 1) + 2; bx++)
+      {
+        MotionVector *mv = &currSlice->all_mv[LIST_0][ref][mode][by][bx];
+        pred.mv[by * 4 + bx][0] = mv->mv_x;
+        pred.mv[by * 4 + bx][1] = mv->mv_y;
+      }
+  }
+  qp = currMB->qp_scaled[0];
+  memset(&d, 0, sizeof(d));
+  d.n = n; d.qp = qp; d.is_cavlc = (n == 4) ? (currSlice->symbol_mode == CAVLC) : cavlc8;
+  {
+    LevelQuantParams **qpar = (n == 4) ? p_Vid->p_Quant->q_params_4x4[0][0][qp] : p_Vid->p_Quant->q_params_8x8[0][0][qp];
+    for (j = 0; j < n; j++)
+      for (i = 0; i < n; i++)
+      {
+        d.qparams[j * n + i][0] = qpar[j][i].OffsetComp;
+        d.qparams[j * n + i][1] = qpar[j][i].ScaleComp;
+        d.qparams[j * n + i][2] = qpar[j][i].InvScaleComp;
+      }
+  }
+  if (n == 4)
+  {
+    memcpy(d.scan, V_SCAN4, sizeof(V_SCAN4));
+    memcpy(d.c_cost, V_COST4[currSlice->disthres], 16);
+  }
+  else
+  {
+    zigzag8(scan8);
+    for (k = 0; k < 64; k++)       /* CAVLC: four interleaved lists, list s takes zig-zag entries 4m+s (transform8x8.c:55) */
+    {
+      int src = cavlc8 ? 4 * (k & 15) + (k >> 4) : k;
+      d.scan[k][0] = scan8[src][0]; d.scan[k][1] = scan8[src][1];
+    }
+    for (k = 0; k < 64; k++) d.c_cost[k] = (currSlice->disthres == 1) ? 9 : (k < 4 ? 3 : k < 12 ? 2 : k < 24 ? 1 : 0);
+  }
+  rc = jmb_luma_residual_coding(S.ctx, &pred, currMB->mbAddrX, 1, &d, levels, cost8, &cbp_blk, &cbp, recon, &sse, JMB_HOST);
+  if (rc) jmb_die("jmb_luma_residual_coding", rc);
+
+  if ((currMB->cbp & 15) != (int)cbp) verify_mismatch(currMB, "cbp", currMB->cbp & 15, (int)cbp);
+  if ((int)(currMB->cbp_blk & 0xffff) != (int)cbp_blk) verify_mismatch(currMB, "cbp_blk", (int)(currMB->cbp_blk & 0xffff), (int)cbp_blk);
+  for (j = 0; j < 16; j++)
+    for (i = 0; i < 16; i++)
+      if (p_Vid->enc_picture->imgY[currMB->pix_y + j][currMB->pix_x + i] != recon[j * 16 + i])
+        verify_mismatch(currMB, "reconstruction", p_Vid->enc_picture->imgY[currMB->pix_y + j][currMB->pix_x + i], recon[j * 16 + i]);
+  /* levels of every block JM says is coded: expand JM's (level, run) lists to scan order */
+  for (k = 0; k < 4; k++)
+  {
+    if (!(cbp & (1u << k))) continue;
+    if (n == 4)
+    {
+      int b4;
+      for (b4 = 0; b4 < 4; b4++)
+      {
+        int blk = (2 * (k >> 1) + (b4 >> 1)) * 4 + 2 * (k & 1) + (b4 & 1), pos = 0, e;
+        int *ACL = currSlice->cofAC[k][b4][0], *ACR = currSlice->cofAC[k][b4][1];
+        int16_t want[16];
+        memset(want, 0, sizeof(want));
+        for (e = 0; e < 16 && ACL[e] != 0; e++) { pos += ACR[e]; want[pos++] = (int16_t)ACL[e]; }
+        for (e = 0; e < 16; e++)
+          if (want[e] != levels[blk * 16 + e]) verify_mismatch(currMB, "a 4x4 level", want[e], levels[blk * 16 + e]);
+      }
+    }
+    else
+    {
+      int s, e;
+      for (s = 0; s < (cavlc8 ? 4 : 1); s++)
+      {
+        int *ACL = cavlc8 ? currSlice->cofAC[k][s][0] : currSlice->cofAC[k][0][0], *ACR = cavlc8 ? currSlice->cofAC[k][s][1] : currSlice->cofAC[k][0][1];
+        int16_t want[64];
+        int pos = 0, len = cavlc8 ? 16 : 64;
+        memset(want, 0, sizeof(want));
+        for (e = 0; e < len && ACL[e] != 0; e++) { pos += ACR[e]; want[pos++] = (int16_t)ACL[e]; }
+        for (e = 0; e < len; e++)
+          if (want[e] != levels[k * 64 + s * 16 + e]) verify_mismatch(currMB, "an 8x8 level", want[e], levels[k * 64 + s * 16 + e]);
+      }
+    }
+  }
+  S.verified++;
 }
 
 /* ---- transforms (lcommon/src/transform.c:20, :353) ---------------------------------------------------- */

@@ -266,6 +266,8 @@ def _mc_tq_reference(oracle, planes, cur, pred, w, h, n, qp, qpar, scan, cc, cav
                 b8 = (by4 >> 1) * 2 + (bx4 >> 1)
                 mode = int(pred[mb]["b8mode"][b8])
                 ux4, uy4 = (bx4 & ~1, by4 & ~1) if (mode < 5 or n == 8) else (bx4, by4)
+                if mode == 1:
+                    ux4, uy4 = 0, 0         # P16x16: one 16x16 prediction unit (macroblock.c:1225)
                 mvx, mvy = [int(v) for v in pred[mb]["mv"][uy4 * 4 + ux4]]
                 qx, qy = ((mbx + ux4 * 4) << 2) + mvx, ((mby + uy4 * 4) << 2) + mvy
                 iy = min(max(qy >> 2, -20), h + 20 - 1 - 16); ix = min(max(qx >> 2, -32), w + 32 - 1 - 16)
@@ -431,6 +433,8 @@ def test_luma_residual_coding_modes(ctx, oracle, n, cav, qp):
             for by4 in range(4):
                 for bx4 in range(4):
                     ux4, uy4 = (bx4 & ~1, by4 & ~1) if (mode < 5 or n == 8) else (bx4, by4)
+                    if mode == 1:
+                        ux4, uy4 = 0, 0         # P16x16: one 16x16 prediction unit (macroblock.c:1225)
                     mvx, mvy = [int(v) for v in pred_tab[mb]["mv"][uy4 * 4 + ux4]]
                     qx, qy = ((mbx + ux4 * 4) << 2) + mvx, ((mby + uy4 * 4) << 2) + mvy
                     iy = min(max(qy >> 2, -20), h + 20 - 1 - 16); ix = min(max(qx >> 2, -32), w + 32 - 1 - 16)
@@ -446,3 +450,22 @@ def test_luma_residual_coding_modes(ctx, oracle, n, cav, qp):
     assert seen_coded > 0 or qp > 30                        # coarse quantisers may threshold every macroblock away
     no_recon = ctx.luma_residual_coding_modes(None, qd, mask, n_mb=n_mb, want_recon=False)        # resident results, no recon
     assert np.array_equal(no_recon["sse"], got["sse"]) and np.array_equal(no_recon["levels"], got["levels"])
+
+
+def test_luma_residual_coding_explicit_prediction(ctx):
+    """The explicit-prediction form (what the shim's verify hook feeds from JM's own state) equals the all-modes form,
+    also for a sub-range of macroblocks (first_mb)."""
+    w, h, R = 64, 48, 8
+    f = _frames(w, h, 43, motion=(-2, 2))
+    ctx.configure(search_range=R)
+    ctx.ref_put(0, f[0]); ctx.pic_begin(f[1], [0])
+    reqs = _frame_reqs(w, h, np.random.default_rng(43), api.SEARCH_FULL, api.REQ_SUBPEL, lam=60)
+    res = ctx.me_search(reqs, frame=True)
+    qd = api.quant_desc(4, 27, T.q_params(27, 0, 4), T.SNGL_SCAN, T.COEFF_COST4x4[0], 1)
+    allm = ctx.luma_residual_coding_modes(res, qd)
+    for mode in (1, 2, 4, 7):
+        pred = ctx.pred_from_results(res, mode)
+        for first, cnt in ((0, len(pred)), (5, 4)):
+            o = ctx.luma_residual_coding(pred[first:first + cnt], qd, first_mb=first)
+            for k in ("levels", "cost8", "cbp_blk", "cbp", "recon", "sse"):
+                assert np.array_equal(o[k], allm[k][mode - 1][first:first + cnt]), (mode, first, k)

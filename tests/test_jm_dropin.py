@@ -119,3 +119,28 @@ def test_bitstream_identical_to_stock_jm(tmp_path, name):
     else:
         assert counts["full"] + counts["fastfull"] > 0 and counts["subpel"] > 0, line[0]
     _same_outputs(tmp_path, "ref", "gpu")
+
+
+VERIFY_CONFIGS = {
+    "baseline_4x4_cavlc": CONFIGS["full_search_baseline"],
+    "high_8x8_cavlc": CONFIGS["high_8x8_cavlc_satd8x8"],
+    "high_8x8_cabac_2refs": ["ProfileIDC=100", "SymbolMode=1", "RDOptimization=1", "Transform8x8Mode=1", "QPISlice=24", "QPPSlice=25",
+                             "SearchMode=0", "SearchRange=8", "NumberReferenceFrames=2", "AdaptiveRounding=0"],
+}
+
+
+@pytest.mark.gpu
+@needs_bins
+@pytest.mark.parametrize("name", sorted(VERIFY_CONFIGS))
+def test_device_luma_residual_coding_matches_jm_in_the_live_encoder(tmp_path, name):
+    """Differential pin of the whole-macroblock device path (jmb_luma_residual_coding: prediction .. thresholding ..
+    reconstruction) against the REAL luma_residual_coding: with JMB_SHIM_VERIFY=1 the shim recodes every inter macroblock
+    JM residual-codes (every RD candidate) on the device from JM's own state and compares levels, cbp, cbp_blk and the
+    reconstruction; the first difference aborts the encoder."""
+    w, h, frames = 96, 80, 3
+    _make_yuv(tmp_path / "input.yuv", w, h, frames, seed=17)
+    r = _encode(JMB, tmp_path, "v", w, h, frames, VERIFY_CONFIGS[name], env={"JMB_SHIM_VERIFY": "1"})
+    assert r.returncode == 0, r.stderr[-800:]
+    line = [l for l in r.stderr.splitlines() if "luma_residual_coding verified on" in l]
+    assert line, r.stderr[-400:]
+    assert int(line[0].split("verified on")[1].split()[0]) > 100, line[0]
