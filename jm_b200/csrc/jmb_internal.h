@@ -54,6 +54,7 @@ struct jmb_ctx {
   // request validation happens on the device (the requests may live there); the kernels OR a JMB_REQERR_* code and the
   // index of one offending request into d_err[0..1], which every synchronising call reads back
   int *d_err = nullptr; int *h_err = nullptr;
+  bool smem_opt_in = false;   // k_int_search's dynamic shared memory opt-in done on this context's device
 };
 int jmb_check_device_errors(jmb_ctx *ctx);   // after a stream synchronisation
 

@@ -667,10 +667,9 @@ static int me_search_impl(jmb_ctx *ctx, const jmb_me_req *reqs, int n, jmb_me_re
     d_reqs = (const jmb_me_req *)ctx->d_stage; d_res = (jmb_me_res *)ctx->d_res_keep;
   }
   jmb_time_begin(ctx, JMB_K_INT_SEARCH);
-  static bool smem_opt_in = false;
-  if (!smem_opt_in) {
+  if (!ctx->smem_opt_in) {      // per context: the attribute belongs to the device the context runs on
     JMB_CUDA(ctx, cudaFuncSetAttribute(k_int_search, cudaFuncAttributeMaxDynamicSharedMemorySize, INT_SEARCH_DYN_SMEM));
-    smem_opt_in = true;
+    ctx->smem_opt_in = true;
   }
   TMaps tm;
   memset(&tm, 0, sizeof(tm));

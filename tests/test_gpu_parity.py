@@ -469,3 +469,49 @@ def test_luma_residual_coding_explicit_prediction(ctx):
             o = ctx.luma_residual_coding(pred[first:first + cnt], qd, first_mb=first)
             for k in ("levels", "cost8", "cbp_blk", "cbp", "recon", "sse"):
                 assert np.array_equal(o[k], allm[k][mode - 1][first:first + cnt]), (mode, first, k)
+
+
+def test_full_size_1080p_properties(ctx):
+    """BASELINE size (1080p, +-32): size-independent properties of the whole-picture search instead of a CPU replay.
+    For every sampled request: the integer cost returned is exactly lambda*bits + (SAD << 5) at the returned mv (SAD
+    re-measured through jmb_dist); no candidate of a random sample of the window is cheaper (and none ties with a smaller
+    spiral index); searching again with min_mcost = the found cost finds nothing better (idempotence)."""
+    w, h, R = 1920, 1088, 32
+    f = synth.luma_frames(w, h, 2, seed=1234, motion=(5, 3))
+    ctx.configure(search_range=R)
+    ctx.ref_put(0, f[0]); ctx.pic_begin(f[1], [0])
+    rng = np.random.default_rng(77)
+    reqs = _frame_reqs(w, h, rng, api.SEARCH_FULL, 0, lam=187, jitter=8, base=(20, 12))
+    res = ctx.me_search(reqs, frame=True)
+    assert len(res) == 8160 * 41
+
+    def mvbits(v):
+        return 1 if v == 0 else 2 * (abs(int(v)).bit_length() - 1) + 3
+
+    def spiral_index(dx, dy):
+        l = max(abs(dx), abs(dy))
+        if l == 0:
+            return 0
+        base = (2 * l - 1) ** 2
+        if abs(dy) == l and abs(dx) < l:
+            return base + 2 * (dx + l - 1) + (dy > 0)
+        return base + 2 * (2 * l - 1) + 2 * (dy + l) + (dx > 0)
+
+    for i in rng.choice(len(reqs), 60, replace=False):
+        q, o = reqs[i], res[i]
+        pos = (int(q["pos_x"]), int(q["pos_y"])); bt = int(q["blocktype"]); lam = int(q["lambda"][0])
+        px, py, cx, cy = int(q["pred_x"]), int(q["pred_y"]), int(q["center_x"]), int(q["center_y"])
+        mvx, mvy = int(o["imv_x"]), int(o["imv_y"])
+        assert abs(mvx - cx) <= 4 * R and abs(mvy - cy) <= 4 * R and mvx % 4 == 0 and mvy % 4 == 0
+        cands = [(mvx, mvy)] + [(cx + 4 * int(rng.integers(-R, R + 1)), cy + 4 * int(rng.integers(-R, R + 1))) for _ in range(40)]
+        sads = ctx.dist(0, api.SAD, bt, pos, [(pos[0] * 4 + a, pos[1] * 4 + b) for a, b in cands])
+        costs = [lam * (mvbits(a - px) + mvbits(b - py)) + (int(s) << 5) for (a, b), s in zip(cands, sads)]
+        assert costs[0] == int(o["icost"]), (i, costs[0], int(o["icost"]))
+        best_idx = spiral_index((mvx - cx) // 4, (mvy - cy) // 4)
+        for (a, b), c in zip(cands[1:], costs[1:]):
+            assert c > costs[0] or (c == costs[0] and spiral_index((a - cx) // 4, (b - cy) // 4) >= best_idx), (i, (a, b), c, costs[0])
+    # idempotence on one macroblock group: min_mcost = found cost -> nothing is strictly better, the centre is kept
+    g = reqs[:41].copy(); g["min_mcost"] = res["icost"][:41]
+    again = ctx.me_search(g, frame=True)
+    assert np.array_equal(again["icost"], res["icost"][:41])
+    assert np.array_equal(again["imv_x"], g["center_x"]) and np.array_equal(again["imv_y"], g["center_y"])
