@@ -173,19 +173,40 @@ def run_ours(args):
         ctx.me_search(ds["reqs"].data_ptr(), d_res.data_ptr(), api.DEVICE, n=n_mb * api.NPART, frame=True)
         ctx.mc_tq_modes(d_res.data_ptr(), qd, 0x7F, api.DEVICE, n_mb=n_mb, out=(d_lev.data_ptr(), d_cost.data_ptr(), d_cbp.data_ptr()))
 
-    e2e_t = {"ref_put": 0.0, "pic_begin": 0.0, "me_search": 0.0, "mc_tq": 0.0}
+    # ---- end-to-end leg: K independent picture streams per GPU (K host threads, each its own context = its own CUDA
+    # stream, reference slots and staging; the calls are the synchronous JMB_HOST ones, so one stream's PCIe copies
+    # overlap the other's kernels).  Pictures are independent units (closed-GOP shards), exactly like the ranks.
+    n_streams = args.e2e_streams if args.e2e_streams > 0 else max(1, min(3, (os.cpu_count() or 1) // (2 * world)))
+    e2e_ctx = [ctx] + [api.Context(local) for _ in range(n_streams - 1)]
+    for c in e2e_ctx[1:]:
+        c.configure(search_range=SEARCH_RANGE)
+    e2e_out = [(h_res, h_lev, h_cost, h_cbp)] + [(c.pinned(n_mb * api.NPART, api.ME_RES), c.pinned((7, n_mb, 256), np.int16),
+                                                  c.pinned((7, n_mb, 4), np.int32), c.pinned((7, n_mb), np.uint32)) for c in e2e_ctx[1:]]
+    e2e_t = [{"ref_put": 0.0, "pic_begin": 0.0, "me_search": 0.0, "mc_tq": 0.0} for _ in e2e_ctx]
 
-    def step_host(s):
+    def step_host(s, k=0):
+        c, (o_res, o_lev, o_cost, o_cbp), tt = e2e_ctx[k], e2e_out[k], e2e_t[k]
         hs, _ = sets[s % N_SETS]
         t0 = time.perf_counter()
-        ctx.ref_put(s % 2, hs["ref"]); t1 = time.perf_counter()
-        ctx.pic_begin(hs["cur"], [s % 2]); t2 = time.perf_counter()
-        ctx.me_search(hs["reqs"], h_res, frame=True); t3 = time.perf_counter()
-        e2e_t["ref_put"] += t1 - t0; e2e_t["pic_begin"] += t2 - t1; e2e_t["me_search"] += t3 - t2
+        c.ref_put(s % 2, hs["ref"]); t1 = time.perf_counter()
+        c.pic_begin(hs["cur"], [s % 2]); t2 = time.perf_counter()
+        c.me_search(hs["reqs"], o_res, frame=True); t3 = time.perf_counter()
+        tt["ref_put"] += t1 - t0; tt["pic_begin"] += t2 - t1; tt["me_search"] += t3 - t2
         # residual coding of all 7 partition modes from the results still resident in HBM; levels / costs / cbp come back
-        t5 = time.perf_counter()
-        ctx._ck(ctx.L.jmb_mc_tq_modes(ctx.h, None, n_mb, 0x7F, qd.ctypes.data, h_lev.ctypes.data, h_cost.ctypes.data, h_cbp.ctypes.data, api.HOST))
-        e2e_t["mc_tq"] += time.perf_counter() - t5
+        c._ck(c.L.jmb_mc_tq_modes(c.h, None, n_mb, 0x7F, qd.ctypes.data, o_lev.ctypes.data, o_cost.ctypes.data, o_cbp.ctypes.data, api.HOST))
+        tt["mc_tq"] += time.perf_counter() - t3
+
+    def run_host_steps(first, count):
+        """`count` pictures starting at step index `first`, dealt round-robin to the streams' threads."""
+        def worker(k):
+            for s in range(first + k, first + count, n_streams):
+                step_host(s, k)
+            e2e_ctx[k].sync()
+        th = [threading.Thread(target=worker, args=(k,)) for k in range(n_streams)]
+        for t_ in th:
+            t_.start()
+        for t_ in th:
+            t_.join()
 
     def barrier():
         torch.cuda.synchronize()
@@ -220,15 +241,13 @@ def run_ours(args):
         t = torch.tensor([ms], device=f"cuda:{local}"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
 
     # ---- end-to-end timing (host buffers through the C ABI) ----------------------------------------
-    for s in range(min(args.warmup, 3)):
-        step_host(s)
+    run_host_steps(0, max(3, n_streams) * 2)
     barrier()
-    for k in e2e_t:
-        e2e_t[k] = 0.0
+    for tt in e2e_t:
+        for k in tt:
+            tt[k] = 0.0
     t0 = time.perf_counter()
-    for s in range(args.steps):
-        step_host(args.warmup + s)
-    ctx.sync()
+    run_host_steps(args.warmup, args.steps)
     e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], device=f"cuda:{local}"); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
@@ -241,7 +260,8 @@ def run_ours(args):
            "config": workload_config(world, args.anchor_bcast), "clocks": clocks, "gpu_launches": int(gpu_launches),
            "e2e": {"value": world * n_mb * args.steps / e2e_s, "unit": "macroblocks/s", "h2d_bytes_per_step": int(h2d),
                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps,
-                   "host_ms_per_step": {k: 1e3 * v / args.steps for k, v in e2e_t.items()}},
+                   "picture_streams_per_gpu": n_streams,
+                   "host_ms_per_picture": {k: 1e3 * sum(tt[k] for tt in e2e_t) / args.steps for k in e2e_t[0]}},
            "kernel_ms_per_step": kernel_break}
     peaks = {}
     try:
@@ -378,6 +398,9 @@ def main():
                     help="N>1: broadcast rank 0's reference picture over NCCL every step (pictures sharing an anchor coded on different GPUs)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-mbs-per-core", type=int, default=160)
+    ap.add_argument("--e2e-streams", type=int, default=0,
+                    help="end-to-end leg: independent picture streams per GPU (host threads x contexts); 1 = strictly serial calls; "
+                         "0 = auto: min(3, host cores / (2 x ranks)), the synchronous calls spin-wait on the host")
     ap.add_argument("--size", default="1080p", choices=["1080p", "4k"], help="picture size (default = BASELINE configs[1])")
     args = ap.parse_args()
     if args.size == "4k":
