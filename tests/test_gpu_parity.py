@@ -515,3 +515,29 @@ def test_full_size_1080p_properties(ctx):
     again = ctx.me_search(g, frame=True)
     assert np.array_equal(again["icost"], res["icost"][:41])
     assert np.array_equal(again["imv_x"], g["center_x"]) and np.array_equal(again["imv_y"], g["center_y"])
+
+
+@pytest.mark.parametrize("R", [16, 32])
+def test_full_search_group_with_scattered_centres(ctx, oracle, R):
+    """One macroblock's 41 requests with centres tens of pels apart: the union of their windows exceeds one staged chunk
+    in both directions, so the chunk loops, the repeated TMA loads and the 'a displacement belongs to some partitions only'
+    logic are all exercised -- each request must still equal its own stand-alone search."""
+    w, h = 208, 160
+    f = _frames(w, h, 51, motion=(4, -3))
+    ctx.configure(search_range=R)
+    ctx.ref_put(0, f[0]); ctx.pic_begin(f[1], [0])
+    r = oracle.ref_create(f[0])
+    rng = np.random.default_rng(51)
+    parts = api.mb_partitions()
+    for mbx, mby in [(96, 64), (0, 0), (192, 144)]:
+        reqs = np.zeros(api.NPART, api.ME_REQ)
+        for k, (t, x, y) in enumerate(parts):
+            q = reqs[k]
+            q["blocktype"], q["pos_x"], q["pos_y"] = t, mbx + x, mby + y
+            p = rng.integers(-160, 161, 2)                    # +-40 pels
+            q["pred_x"], q["pred_y"] = p
+            q["center_x"], q["center_y"] = ((int(p[0]) + 2) >> 2) * 4, ((int(p[1]) + 2) >> 2) * 4
+            q["mode"], q["flags"], q["lambda"], q["min_mcost"] = api.SEARCH_FULL, 0, int(rng.integers(1, 300)), BIG
+        res = ctx.me_search(reqs, frame=True)
+        _check_full(ctx, oracle, r, f[1], reqs, res, R)
+    oracle.ref_destroy(r)
