@@ -282,6 +282,14 @@ def run_ours(args):
                                "(VABSDIFF4/PRMT/ISETP) bound, not HBM bound -- DESIGN.md 3; traffic < algorithmic bytes because "
                                "neighbouring windows hit L2"}
 
+    # The same kernel against the bound that actually limits it: the SM ALU pipe (VABSDIFF4 / PRMT / ISETP issue at
+    # 64 lanes/clk/SM on this part, tools/ubench.cu).  Floor per displacement = 64 VABSDIFF4 + 19 PRMT + 41 ISETP.
+    alu_ops = n_mb * (2 * SEARCH_RANGE + 1) ** 2 * (64 + 19 + 41)
+    sm_hz = 1e6 * float(clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
+    alu_peak = 64.0 * 148 * sm_hz
+    out["alu_roofline"] = {"bound": "alu-pipe", "achieved": alu_ops / (k_ms / max(1, k_n) / 1e3), "peak": alu_peak, "unit": "lane-ops/s",
+                           "frac": alu_ops / (k_ms / max(1, k_n) / 1e3) / alu_peak,
+                           "note": "minimum ALU-pipe instructions of the algorithm / launch time, vs 64 lanes/clk/SM x 148 SMs x SM clock"}
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(sets[0][0], lam, ctx=ctx, api=api, budget_s=args.cpu_seconds)
     if rank == 0:
