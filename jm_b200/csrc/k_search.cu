@@ -37,7 +37,9 @@ constexpr int ADJ_PITCH = 44;      // words per column (>= NPART; 176 B keeps th
 constexpr int WQ_CAP = 192;          // per-warp queue of gate hits awaiting their exact evaluation
 constexpr int HS_PITCH = NPART + 1;   // u16 per thread: SADs of the partitions of a displacement that met the gate
 constexpr int S1_BYTES = S1_ITEMS * 4 * S1_PITCH * 2, SWEEP_BYTES = (NT / 32) * WQ_CAP * 8 + NT * HS_PITCH * 2;   // stage-1 sums and the sweep's queue / hit SADs share memory
-constexpr int INT_SEARCH_DYN_SMEM = (CW + CH / 4) * ADJ_PITCH * 4 + (S1_BYTES > SWEEP_BYTES ? S1_BYTES : SWEEP_BYTES);
+constexpr unsigned S1_NONE = 0x3fffffffu, S1_BAD = 0x40000000u;   // real costs stay far below (lambda <= 65535)
+constexpr int S1T_ROWS = S1_COLS + 4 * S1_RGS;      // exact mv-cost terms of the stage-1 columns and rows, per partition
+constexpr int INT_SEARCH_DYN_SMEM = (CW + CH / 4 + S1T_ROWS) * ADJ_PITCH * 4 + (S1_BYTES > SWEEP_BYTES ? S1_BYTES : SWEEP_BYTES);
 constexpr int IDX_BITS = 13;       // (2*64+1)^2 = 16641 > 8192: search_range <= 45 keeps idx < 8192
 
 struct PartGeom { unsigned char type, bx, by, w4, h4; };
@@ -260,7 +262,8 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
   // floor(lambda * (bits_x - 1) / 32) and floor(lambda * (bits_y - 1) / 32)
   extern __shared__ __align__(16) unsigned dyn_smem[];
   unsigned *const adjx = dyn_smem, *const adjy4 = dyn_smem + CW * ADJ_PITCH;   // adjy4: min over the 4 rows of an item
-  unsigned long long (*const wq)[WQ_CAP] = (unsigned long long (*)[WQ_CAP])(adjy4 + (CH / 4) * ADJ_PITCH);
+  unsigned *const s1x = adjy4 + (CH / 4) * ADJ_PITCH, *const s1y = s1x + S1_COLS * ADJ_PITCH;   // lambda * bits of stage 1's columns / rows
+  unsigned long long (*const wq)[WQ_CAP] = (unsigned long long (*)[WQ_CAP])(s1y + 4 * S1_RGS * ADJ_PITCH);
   unsigned short *const S1 = (unsigned short *)wq;      // stage 1 is over (barrier) before the sweep touches wq / hitsad
   unsigned short (*const hitsad)[HS_PITCH] = (unsigned short (*)[HS_PITCH])(wq + NT / 32);
 
@@ -379,6 +382,18 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
             }
             adjy4[rg * ADJ_PITCH + p] = a;
           }
+          if (s1) {      // stage 1's exact terms; S1_BAD marks a column / row that is not a plain candidate of this partition
+            for (int c = sub; c < ncol; c += lanes_per_p) {
+              const int Dx = cx0 + col0 + c, mx = 4 * Dx - q.px;
+              const bool ok = q.active && Dx >= in.x && Dx <= in.y && !(q.ffs && abs(mx) >= max_mvd_m1);
+              s1x[c * ADJ_PITCH + p] = ok ? lam * (unsigned)jmb_mvbits(mx) : S1_BAD;
+            }
+            for (int r = sub; r < 4 * nrgs; r += lanes_per_p) {
+              const int Dy = cy0 + rg0 * 4 + r, my = 4 * Dy - q.py;
+              const bool ok = q.active && Dy >= in.z && Dy <= in.w && Dy < cy0 + ch && !(q.ffs && abs(my) >= max_mvd_m1);
+              s1y[r * ADJ_PITCH + p] = ok ? lam * (unsigned)jmb_mvbits(my) : S1_BAD;
+            }
+          }
         }
       }
       if (tid == 0) sbox[11] = 0;      // next warp item of the sweep
@@ -391,25 +406,20 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
         unsigned long long k = ~0ull;
         if (p < NPART && G.rq[p].active) {
           const ReqS &q = G.rq[p];
-          const int4 in = G.inner[p];
-          const unsigned lam = (unsigned)q.lam;
-          unsigned bcost = 0xffffffffu; int bidx = 0;   // thread j looks at displacement row j of every item
+          unsigned bcost = S1_NONE; int bidx = 0;        // thread j looks at displacement row j of every item
           for (int rgi = 0; rgi < nrgs; rgi++) {
-            const int Dy = cy0 + (rg0 + rgi) * 4 + j, my = 4 * Dy - q.py;
-            if (Dy < in.z || Dy > in.w || Dy >= cy0 + ch) continue;
-            const unsigned ycost = lam * (unsigned)jmb_mvbits(my);
+            const unsigned ycost = s1y[(4 * rgi + j) * ADJ_PITCH + p];
+            if (ycost == S1_BAD) continue;
+            const int Dy = cy0 + (rg0 + rgi) * 4 + j;
             const unsigned short *sp = S1 + ((rgi * ncol) * 4 + j) * S1_PITCH + p;
             for (int c = 0; c < ncol; c++) {
-              const int Dx = cx0 + col0 + c, mx = 4 * Dx - q.px;
-              if (Dx < in.x || Dx > in.y) continue;
-              if (q.ffs && max(abs(mx), abs(my)) >= max_mvd_m1) continue;
-              const unsigned cost = ((unsigned)sp[c * 4 * S1_PITCH] << 5) + ycost + lam * (unsigned)jmb_mvbits(mx);
+              const unsigned cost = ((unsigned)sp[c * 4 * S1_PITCH] << 5) + ycost + s1x[c * ADJ_PITCH + p];
               if (cost > bcost) continue;
-              const int idx = jmb_spiral_index(Dx - q.cx, Dy - q.cy);
+              const int idx = jmb_spiral_index(cx0 + col0 + c - q.cx, Dy - q.cy);
               if (cost < bcost || idx < bidx) { bcost = cost; bidx = idx; }
             }
           }
-          if (bcost != 0xffffffffu) k = ((unsigned long long)bcost << IDX_BITS) | (unsigned)bidx;
+          if (bcost != S1_NONE) k = ((unsigned long long)bcost << IDX_BITS) | (unsigned)bidx;
 
         }
         k = min(k, __shfl_xor_sync(0xffffffffu, k, 1));
