@@ -138,7 +138,37 @@ __device__ __forceinline__ void load_ref4(const RefView &rv, int cqx, int cqy, i
 #pragma unroll
   for (int y = 0; y < 4; y++) rw[y] = ld4(ref + (size_t)y * rv.pitch);
 }
+// HadamardSAD4x4 (me_distortion.c:175-258) on two samples per register: a pair (a, b) is carried as the INTEGER
+// a + 65536 * b, on which adds and subtracts act on both halves at once (no field ever overflows: |values| <= 4080).
+// Vertical butterflies on the packed rows, one horizontal stage after swapping the halves of the right pair, and the
+// last stage folded into |u + v| + |u - v| = 2 max(|u|, |v|), so the result is the sum of the eight maxima -- exactly
+// JM's (sum |coefficient| + 1) >> 1, the sum being even.
+__device__ __forceinline__ int hadamard4_packed(const unsigned (&sw)[4], const unsigned (&rw)[4]) {
+  int lo[4], hi[4];
+#pragma unroll
+  for (int y = 0; y < 4; y++) {      // bytes 0,1 -> (b0, b1), bytes 2,3 -> (b2, b3) as 16-bit fields; difference as integers
+    lo[y] = (int)__byte_perm(sw[y], 0, 0x4140) - (int)__byte_perm(rw[y], 0, 0x4140);
+    hi[y] = (int)__byte_perm(sw[y], 0, 0x4342) - (int)__byte_perm(rw[y], 0, 0x4342);
+  }
+  int s = 0;
+  int ml[4], mh[4];
+  { const int a0 = lo[0] + lo[3], a1 = lo[1] + lo[2], a2 = lo[1] - lo[2], a3 = lo[0] - lo[3];
+    ml[0] = a0 + a1; ml[2] = a0 - a1; ml[1] = a3 + a2; ml[3] = a3 - a2; }
+  { const int a0 = hi[0] + hi[3], a1 = hi[1] + hi[2], a2 = hi[1] - hi[2], a3 = hi[0] - hi[3];
+    mh[0] = a0 + a1; mh[2] = a0 - a1; mh[1] = a3 + a2; mh[3] = a3 - a2; }
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    // row r holds (m0, m1) in ml and (m2, m3) in mh; swapping mh's halves needs the integer form re-split first
+    const int h0 = (int)(short)(mh[r] & 0xffff), h1 = (mh[r] - h0) >> 16;          // m2, m3
+    const int l0 = (int)(short)(ml[r] & 0xffff), l1 = (ml[r] - l0) >> 16;          // m0, m1
+    const int a0 = l0 + h1, a1 = l1 + h0, a2 = l1 - h0, a3 = l0 - h1;
+    s += max(abs(a0), abs(a1)) + max(abs(a2), abs(a3));
+  }
+  return s;
+}
+
 __device__ __forceinline__ int dist4(const SrcBlk &src, const unsigned (&rw)[4], int metric) {
+  if (metric == JMB_SATD) { const unsigned sw[4] = {src.w[0], src.w[1], src.w[2], src.w[3]}; return hadamard4_packed(sw, rw); }
   int d[16];
 #pragma unroll
   for (int y = 0; y < 4; y++)
