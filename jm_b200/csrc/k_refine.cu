@@ -186,6 +186,10 @@ __device__ __forceinline__ int dist4(const SrcBlk &src, const unsigned (&rw)[4],
 // the candidates of the stage, adding its share of every candidate's distortion to sums[request][candidate].
 // One thread per request then replays JM's sequential strict-'<' selection (me_fullsearch.c:221-289).
 constexpr int RT = 128, RQ = 41;
+#ifndef JMB_RF_GROUP
+#define JMB_RF_GROUP 3
+#endif
+constexpr int RF_GROUP = JMB_RF_GROUP;
 
 struct RefineS {
   short pos_x, pos_y, pred_x, pred_y;
@@ -265,13 +269,13 @@ k_subpel_refine(const jmb_me_req *__restrict__ reqs, jmb_me_res *__restrict__ re
       load_src(src, cur, cur_pitch, q.pos_x + sbx * nn, q.pos_y + sby * nn, nn);
       const int bqx = (q.pos_x << 2) + q.mvx, bqy = (q.pos_y << 2) + q.mvy;
       if (nn == 4) {
-        for (int pos = pos0; pos < pos1; pos += 3) {       // three candidates' reference rows in flight at a time
-          unsigned rw[3][4];
+        for (int pos = pos0; pos < pos1; pos += RF_GROUP) {       // RF_GROUP candidates' reference rows in flight at a time
+          unsigned rw[RF_GROUP][4];
 #pragma unroll
-          for (int k = 0; k < 3; k++)
+          for (int k = 0; k < RF_GROUP; k++)
             if (pos + k < pos1) load_ref4(rv, bqx + step * c_spiral9[pos + k][0], bqy + step * c_spiral9[pos + k][1], sbx, sby, metric, rw[k]);
 #pragma unroll
-          for (int k = 0; k < 3; k++)
+          for (int k = 0; k < RF_GROUP; k++)
             if (pos + k < pos1) atomicAdd(&sums[lo][pos + k], dist4(src, rw[k], metric));
         }
       } else {

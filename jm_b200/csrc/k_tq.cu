@@ -83,18 +83,48 @@ __device__ void inv8(int *b) {
   for (int i = 0; i < 8; i++) inv8_1d(t + i, 8, b + i, 8);
 }
 
+// H.264's frame zig-zag scans as {i (horizontal), j (vertical)} (the standard's Figure 8-8 / 8-9; JM: block.c:170,
+// transform8x8.c:44,55).  When the caller's scan is one of these the quantiser runs with compile-time indices and the
+// coefficient block stays in registers; any other scan (field scans) takes the table-driven path.
+__device__ constexpr unsigned char STD_SCAN4[16][2] = {{0,0}, {1,0}, {0,1}, {0,2}, {1,1}, {2,0}, {3,0}, {2,1}, {1,2}, {0,3}, {1,3}, {2,2}, {3,1}, {3,2}, {2,3}, {3,3}};
+__device__ constexpr unsigned char STD_SCAN8[64][2] = {{0,0}, {1,0}, {0,1}, {0,2}, {1,1}, {2,0}, {3,0}, {2,1}, {1,2}, {0,3}, {0,4}, {1,3}, {2,2}, {3,1}, {4,0}, {5,0}, {4,1}, {3,2}, {2,3}, {1,4}, {0,5}, {0,6}, {1,5}, {2,4}, {3,3}, {4,2}, {5,1}, {6,0}, {7,0}, {6,1}, {5,2}, {4,3}, {3,4}, {2,5}, {1,6}, {0,7}, {1,7}, {2,6}, {3,5}, {4,4}, {5,3}, {6,2}, {7,1}, {7,2}, {6,3}, {5,4}, {4,5}, {3,6}, {2,7}, {3,7}, {4,6}, {5,5}, {6,4}, {7,3}, {7,4}, {6,5}, {5,6}, {4,7}, {5,7}, {6,6}, {7,5}, {7,6}, {6,7}, {7,7}};
+__device__ constexpr unsigned char STD_SCAN8_CAVLC[64][2] = {{0,0}, {1,1}, {1,2}, {2,2}, {4,1}, {0,5}, {3,3}, {7,0}, {3,4}, {1,7}, {5,3}, {6,3}, {2,7}, {6,4}, {5,6}, {7,5}, {1,0}, {2,0}, {0,3}, {3,1}, {3,2}, {0,6}, {4,2}, {6,1}, {2,5}, {2,6}, {6,2}, {5,4}, {3,7}, {7,3}, {4,7}, {7,6}, {0,1}, {3,0}, {0,4}, {4,0}, {2,3}, {1,5}, {5,1}, {5,2}, {1,6}, {3,5}, {7,1}, {4,5}, {4,6}, {7,4}, {5,7}, {6,7}, {0,2}, {2,1}, {1,3}, {5,0}, {1,4}, {2,4}, {6,0}, {4,3}, {0,7}, {4,4}, {7,2}, {3,6}, {5,5}, {6,5}, {6,6}, {7,7}};
+
 struct QOut { int nonzero; int cost; };
 
 // quantise one block in scan order.  coef: in = transformed, out = dequantised (JM leaves it in tblock).
 // LISTS: write JM's (level, run) lists; otherwise write the level of every scan position to lv16.
-template <int N, bool LISTS>
-__device__ QOut quant_block(const jmb_quant_desc &q, int *coef, int *levels, int *runs, int *fadj, int16_t *lv16) {
+// STD: 0 = scan from the descriptor (any order), 1 = the standard zig-zag, 2 = the standard 8x8 CAVLC interleave
+template <int N, bool LISTS, int STD = 0>
+__device__ __forceinline__ QOut quant_block(const jmb_quant_desc &q, int *coef, int *levels, int *runs, int *fadj, int16_t *lv16) {
   constexpr int NN = N * N;
   const int qp_per = q.qp / 6, q_bits = (N == 4 ? 15 : 16) + qp_per, dq = (N == 4) ? 4 : 6;
   const bool cavlc8 = (N == 8) && q.is_cavlc;
   const bool clip = (N == 4) ? (q.is_cavlc != 0) : cavlc8;
   int nl[4] = {0, 0, 0, 0}, run[4] = {0, 0, 0, 0};
   QOut o{0, 0};
+#pragma unroll
+  for (int k = 0; k < (STD ? NN : 0); k++) {       // compile-time scan: every index below is a constant after unrolling
+    const int i = (N == 4) ? STD_SCAN4[k][0] : (STD == 2 ? STD_SCAN8_CAVLC[k][0] : STD_SCAN8[k][0]);
+    const int j = (N == 4) ? STD_SCAN4[k][1] : (STD == 2 ? STD_SCAN8_CAVLC[k][1] : STD_SCAN8[k][1]);
+    const int idx = j * N + i, s = (STD == 2) ? (k >> 4) : 0;
+    const int c = coef[idx];
+    int level = 0;
+    if (c != 0) {
+      const int scaled = abs(c) * q.qparams[idx][1];
+      level = (scaled + q.qparams[idx][0]) >> q_bits;
+      if (level != 0) {
+        if (clip) level = min(level, 2063);
+        o.cost += (level > 1) ? 999999 : q.c_cost[run[s]];
+        if (c < 0) level = -level;
+        coef[idx] = (((level * q.qparams[idx][2]) << qp_per) + (1 << (dq - 1))) >> dq;
+        o.nonzero = 1;
+      } else coef[idx] = 0;
+    }
+    lv16[k] = (int16_t)level;
+    if (level != 0) run[s] = 0; else run[s]++;
+  }
+  if (STD) return o;
   for (int k = 0; k < NN; k++) {
     const int i = q.scan[k][0], j = q.scan[k][1], idx = j * N + i;
     const int s = cavlc8 ? (k >> 4) : 0;
@@ -208,7 +238,7 @@ __global__ void k_mc_tq(const jmb_mb_pred *__restrict__ pred, int n_mb, int mb_w
 // Every inter partition mode of every macroblock in ONE launch: the prediction comes straight from the 41 search
 // results of the macroblock (the all_mv fill of mv_search.c:1005-1014 folded in), reference 0.  Thread = one transform
 // block of one (mode, macroblock); outputs are mode-major.
-template <int N>
+template <int N, int STD>
 __global__ void k_mc_tq_modes(const jmb_me_res *__restrict__ res, int n_mb, int mb_w, unsigned mode_mask, const jmb_quant_desc *__restrict__ qd,
                               const uint8_t *__restrict__ cur, int cur_pitch, const uint8_t *__restrict__ ref_plane0,
                               size_t plane_bytes, int ref_pitch, int w, int h,
@@ -242,7 +272,7 @@ __global__ void k_mc_tq_modes(const jmb_me_res *__restrict__ res, int n_mb, int 
     for (int x = 0; x < N; x++) rr[y * N + x] = (int)sp[(size_t)y * cur_pitch + x] - (int)rp[(size_t)y * ref_pitch + x];
   if (N == 4) fwd4(rr); else fwd8(rr);
   const size_t mo = (size_t)blockIdx.y * n_mb + mb;          // mode-major output index
-  QOut o = quant_block<N, false>(q, rr, nullptr, nullptr, nullptr, levels + mo * 256 + b * N * N);
+  QOut o = quant_block<N, false, STD>(q, rr, nullptr, nullptr, nullptr, levels + mo * 256 + b * N * N);
   if (o.cost) atomicAdd(&coeff_cost[mo * 4 + b8], o.cost);
   if (o.nonzero) atomicOr(&cbp_blk[mo], (N == 4) ? (1u << (by4 * 4 + bx4)) : (51u << (4 * b8 - 2 * (b8 & 1))));
 }
@@ -267,7 +297,7 @@ __global__ void k_inverse(int *blocks, int nblk) {
 // reset (reset_block, macroblock.c:806), a macroblock whose summed cost is <= _LUMA_MB_COEFF_COST_ (5) drops its luma cbp
 // and takes the prediction (:1248-1255) -> SSE of the reconstruction against the source (what RDCost_for_macroblocks
 // charges as distortion).  Thread = one transform block; the 16 (4) threads of a macroblock exchange costs by shuffle.
-template <int N>
+template <int N, int STD>
 __global__ void __launch_bounds__(128)
 k_luma_rc_modes(const jmb_me_res *__restrict__ res, const jmb_mb_pred *__restrict__ pred, int first_mb, int n_mb, int mb_w, unsigned mode_mask,
                 const jmb_quant_desc *__restrict__ qd, const uint8_t *__restrict__ cur, int cur_pitch, const uint8_t *const *__restrict__ ref_planes,
@@ -314,7 +344,7 @@ k_luma_rc_modes(const jmb_me_res *__restrict__ res, const jmb_mb_pred *__restric
   if (N == 4) fwd4(rr); else fwd8(rr);
   const size_t mo = (size_t)blockIdx.y * n_mb + mb;          // mode-major output index
   int16_t lv[N * N];
-  QOut o = quant_block<N, false>(q, rr, nullptr, nullptr, nullptr, lv);
+  QOut o = quant_block<N, false, STD>(q, rr, nullptr, nullptr, nullptr, lv);
   // coefficient thresholding across the macroblock's threads
   int c8 = o.cost;
   if (N == 4) { c8 += __shfl_xor_sync(0xffffffffu, c8, 1); c8 += __shfl_xor_sync(0xffffffffu, c8, 4); }   // the quadrant's 4 blocks
@@ -372,6 +402,17 @@ static int check_qdesc(jmb_ctx *ctx, const jmb_quant_desc *q) {
   for (int k = 0; k < q->n * q->n; k++)
     if (q->scan[k][0] >= q->n || q->scan[k][1] >= q->n) return jmb_fail(ctx, JMB_ERR_ARG, "quant desc: scan[%d] outside the block", k);
   return 0;
+}
+
+// 1 / 2 when the descriptor's scan is the standard zig-zag / the standard 8x8 CAVLC interleave (compile-time scan
+// kernels), else 0 (table-driven kernels)
+static int std_scan_kind(const jmb_quant_desc *q) {
+  static const unsigned char Z4[16][2] = {{0,0}, {1,0}, {0,1}, {0,2}, {1,1}, {2,0}, {3,0}, {2,1}, {1,2}, {0,3}, {1,3}, {2,2}, {3,1}, {3,2}, {2,3}, {3,3}};
+  static const unsigned char Z8[64][2] = {{0,0}, {1,0}, {0,1}, {0,2}, {1,1}, {2,0}, {3,0}, {2,1}, {1,2}, {0,3}, {0,4}, {1,3}, {2,2}, {3,1}, {4,0}, {5,0}, {4,1}, {3,2}, {2,3}, {1,4}, {0,5}, {0,6}, {1,5}, {2,4}, {3,3}, {4,2}, {5,1}, {6,0}, {7,0}, {6,1}, {5,2}, {4,3}, {3,4}, {2,5}, {1,6}, {0,7}, {1,7}, {2,6}, {3,5}, {4,4}, {5,3}, {6,2}, {7,1}, {7,2}, {6,3}, {5,4}, {4,5}, {3,6}, {2,7}, {3,7}, {4,6}, {5,5}, {6,4}, {7,3}, {7,4}, {6,5}, {5,6}, {4,7}, {5,7}, {6,6}, {7,5}, {7,6}, {6,7}, {7,7}};
+  static const unsigned char Z8C[64][2] = {{0,0}, {1,1}, {1,2}, {2,2}, {4,1}, {0,5}, {3,3}, {7,0}, {3,4}, {1,7}, {5,3}, {6,3}, {2,7}, {6,4}, {5,6}, {7,5}, {1,0}, {2,0}, {0,3}, {3,1}, {3,2}, {0,6}, {4,2}, {6,1}, {2,5}, {2,6}, {6,2}, {5,4}, {3,7}, {7,3}, {4,7}, {7,6}, {0,1}, {3,0}, {0,4}, {4,0}, {2,3}, {1,5}, {5,1}, {5,2}, {1,6}, {3,5}, {7,1}, {4,5}, {4,6}, {7,4}, {5,7}, {6,7}, {0,2}, {2,1}, {1,3}, {5,0}, {1,4}, {2,4}, {6,0}, {4,3}, {0,7}, {4,4}, {7,2}, {3,6}, {5,5}, {6,5}, {6,6}, {7,7}};
+  if (q->n == 4) return memcmp(q->scan, Z4, sizeof(Z4)) ? 0 : 1;
+  if (q->is_cavlc) return memcmp(q->scan, Z8C, sizeof(Z8C)) ? 0 : 2;
+  return memcmp(q->scan, Z8, sizeof(Z8)) ? 0 : 1;
 }
 
 static int upload_ref_table(jmb_ctx *ctx, const uint8_t *const **d_tab) {
@@ -583,10 +624,15 @@ int jmb_luma_residual_coding_modes(jmb_ctx *ctx, const jmb_me_res *res, int n_mb
   }
   jmb_time_begin(ctx, JMB_K_MC_TQ);
   const uint8_t *const *d_tab; rc = upload_ref_table(ctx, &d_tab); if (rc) return rc;
-  if (q->n == 4) k_luma_rc_modes<4><<<dim3((n_mb * 16 + 127) / 128, 7), 128, 0, ctx->stream>>>(d_res, nullptr, 0, n_mb, mb_w, mode_mask, d_q, ctx->cur, ctx->cur_pitch,
-        d_tab, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_c8, d_cb, d_cbp, d_rec, d_sse);
-  else k_luma_rc_modes<8><<<dim3((n_mb * 4 + 127) / 128, 7), 128, 0, ctx->stream>>>(d_res, nullptr, 0, n_mb, mb_w, mode_mask, d_q, ctx->cur, ctx->cur_pitch,
-        d_tab, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_c8, d_cb, d_cbp, d_rec, d_sse);
+#define JMB_LRC(NN, STD, GRID) k_luma_rc_modes<NN, STD><<<GRID, 128, 0, ctx->stream>>>(d_res, nullptr, 0, n_mb, mb_w, mode_mask, d_q, ctx->cur, \
+        ctx->cur_pitch, d_tab, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_c8, d_cb, d_cbp, d_rec, d_sse)
+  {
+    const int kind = std_scan_kind(q);
+    const dim3 g4((n_mb * 16 + 127) / 128, 7), g8((n_mb * 4 + 127) / 128, 7);
+    if (q->n == 4) { if (kind == 1) JMB_LRC(4, 1, g4); else JMB_LRC(4, 0, g4); }
+    else if (kind == 1) JMB_LRC(8, 1, g8); else if (kind == 2) JMB_LRC(8, 2, g8); else JMB_LRC(8, 0, g8);
+  }
+#undef JMB_LRC
   jmb_time_end(ctx, JMB_K_MC_TQ);
   JMB_LAUNCH_CHECK(ctx);
   if (loc == JMB_HOST) {
@@ -630,10 +676,15 @@ int jmb_luma_residual_coding(jmb_ctx *ctx, const jmb_mb_pred *pred, int first_mb
   const jmb_quant_desc *d_q; rc = upload_qdesc(ctx, q, &d_q); if (rc) return rc;
   const uint8_t *const *d_tab; rc = upload_ref_table(ctx, &d_tab); if (rc) return rc;
   jmb_time_begin(ctx, JMB_K_MC_TQ);
-  if (q->n == 4) k_luma_rc_modes<4><<<dim3((n_mb * 16 + 127) / 128, 1), 128, 0, ctx->stream>>>(nullptr, d_pred, first_mb, n_mb, mb_w, 1u, d_q, ctx->cur, ctx->cur_pitch,
-        d_tab, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_c8, d_cb, d_cbp, d_rec, d_sse);
-  else k_luma_rc_modes<8><<<dim3((n_mb * 4 + 127) / 128, 1), 128, 0, ctx->stream>>>(nullptr, d_pred, first_mb, n_mb, mb_w, 1u, d_q, ctx->cur, ctx->cur_pitch,
-        d_tab, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_c8, d_cb, d_cbp, d_rec, d_sse);
+#define JMB_LRC(NN, STD, GRID) k_luma_rc_modes<NN, STD><<<GRID, 128, 0, ctx->stream>>>(nullptr, d_pred, first_mb, n_mb, mb_w, 1u, d_q, ctx->cur, \
+        ctx->cur_pitch, d_tab, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_c8, d_cb, d_cbp, d_rec, d_sse)
+  {
+    const int kind = std_scan_kind(q);
+    const dim3 g4((n_mb * 16 + 127) / 128, 1), g8((n_mb * 4 + 127) / 128, 1);
+    if (q->n == 4) { if (kind == 1) JMB_LRC(4, 1, g4); else JMB_LRC(4, 0, g4); }
+    else if (kind == 1) JMB_LRC(8, 1, g8); else if (kind == 2) JMB_LRC(8, 2, g8); else JMB_LRC(8, 0, g8);
+  }
+#undef JMB_LRC
   jmb_time_end(ctx, JMB_K_MC_TQ);
   JMB_LAUNCH_CHECK(ctx);
   if (loc == JMB_HOST) {
@@ -678,10 +729,15 @@ int jmb_mc_tq_modes(jmb_ctx *ctx, const jmb_me_res *res, int n_mb, unsigned mode
   JMB_CUDA(ctx, cudaMemsetAsync(d_cc, 0, n7 * 16, ctx->stream));
   JMB_CUDA(ctx, cudaMemsetAsync(d_cbp, 0, n7 * 4, ctx->stream));
   jmb_time_begin(ctx, JMB_K_MC_TQ);
-  if (q->n == 4) k_mc_tq_modes<4><<<dim3((n_mb * 16 + 127) / 128, 7), 128, 0, ctx->stream>>>(d_res, n_mb, mb_w, mode_mask, d_q, ctx->cur, ctx->cur_pitch,
-        r0.planes, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_cc, d_cbp);
-  else k_mc_tq_modes<8><<<dim3((n_mb * 4 + 63) / 64, 7), 64, 0, ctx->stream>>>(d_res, n_mb, mb_w, mode_mask, d_q, ctx->cur, ctx->cur_pitch,
-        r0.planes, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_cc, d_cbp);
+#define JMB_MTQ(NN, STD, GRID, BLK) k_mc_tq_modes<NN, STD><<<GRID, BLK, 0, ctx->stream>>>(d_res, n_mb, mb_w, mode_mask, d_q, ctx->cur, ctx->cur_pitch, \
+        r0.planes, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_cc, d_cbp)
+  {
+    const int kind = std_scan_kind(q);
+    const dim3 g4((n_mb * 16 + 127) / 128, 7), g8((n_mb * 4 + 63) / 64, 7);
+    if (q->n == 4) { if (kind == 1) JMB_MTQ(4, 1, g4, 128); else JMB_MTQ(4, 0, g4, 128); }
+    else if (kind == 1) JMB_MTQ(8, 1, g8, 64); else if (kind == 2) JMB_MTQ(8, 2, g8, 64); else JMB_MTQ(8, 0, g8, 64);
+  }
+#undef JMB_MTQ
   jmb_time_end(ctx, JMB_K_MC_TQ);
   JMB_LAUNCH_CHECK(ctx);
   if (loc == JMB_HOST) {

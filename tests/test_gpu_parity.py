@@ -541,3 +541,32 @@ def test_full_search_group_with_scattered_centres(ctx, oracle, R):
         res = ctx.me_search(reqs, frame=True)
         _check_full(ctx, oracle, r, f[1], reqs, res, R)
     oracle.ref_destroy(r)
+
+
+def test_luma_residual_coding_with_a_non_standard_scan(ctx, oracle):
+    """A scan other than the frame zig-zag (here JM's 4x4 field scan, block.c:178) takes the table-driven quantiser instead
+    of the compile-time one: same oracle, same answers."""
+    field_scan = np.array([(0, 0), (0, 1), (1, 0), (0, 2), (0, 3), (1, 1), (1, 2), (1, 3), (2, 0), (2, 1), (2, 2), (2, 3),
+                           (3, 0), (3, 1), (3, 2), (3, 3)], np.uint8)
+    w, h, R, qp = 64, 48, 8, 26
+    f = _frames(w, h, 61, motion=(1, -2))
+    ctx.configure(search_range=R)
+    ctx.ref_put(0, f[0]); ctx.pic_begin(f[1], [0])
+    reqs = _frame_reqs(w, h, np.random.default_rng(61), api.SEARCH_FULL, api.REQ_SUBPEL, lam=T.lambda_me(qp))
+    res = ctx.me_search(reqs, frame=True)
+    qpar = T.q_params(qp, 0, 4)
+    qd = api.quant_desc(4, qp, qpar, field_scan, T.COEFF_COST4x4[0], 1)
+    got = ctx.luma_residual_coding_modes(res, qd, 0x01)
+    raw = ctx.mc_tq_modes(res, qd, 0x01)
+    r = oracle.ref_create(f[0]); planes = oracle.planes(r); oracle.ref_destroy(r)
+    pred_tab = ctx.pred_from_results(res, 1)
+    for mb in range(len(pred_tab)):
+        mbx, mby = (mb % (w // 16)) * 16, (mb // (w // 16)) * 16
+        mvx, mvy = [int(v) for v in pred_tab[mb]["mv"][0]]
+        qx, qy = (mbx << 2) + mvx, (mby << 2) + mvy
+        iy = min(max(qy >> 2, -20), h + 20 - 1 - 16); ix = min(max(qx >> 2, -32), w + 32 - 1 - 16)
+        pred = planes[qy & 3, qx & 3, iy + 20:iy + 36, ix + 32:ix + 48]
+        lv, c8, cbp, cbpb, rec, sse = oracle.luma_residual_coding(f[1][mby:mby + 16, mbx:mbx + 16], pred, 4, qp, qpar, field_scan, T.COEFF_COST4x4[0], 1)
+        assert np.array_equal(got["levels"][0, mb], lv) and got["cbp"][0, mb] == cbp and got["sse"][0, mb] == sse and np.array_equal(got["recon"][0, mb], rec)
+        if cbp == 15:                                       # nothing thresholded away: the raw transform/quant levels are the same
+            assert np.array_equal(raw[0][0, mb], lv)
