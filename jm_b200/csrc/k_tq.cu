@@ -90,6 +90,13 @@ __device__ constexpr unsigned char STD_SCAN4[16][2] = {{0,0}, {1,0}, {0,1}, {0,2
 __device__ constexpr unsigned char STD_SCAN8[64][2] = {{0,0}, {1,0}, {0,1}, {0,2}, {1,1}, {2,0}, {3,0}, {2,1}, {1,2}, {0,3}, {0,4}, {1,3}, {2,2}, {3,1}, {4,0}, {5,0}, {4,1}, {3,2}, {2,3}, {1,4}, {0,5}, {0,6}, {1,5}, {2,4}, {3,3}, {4,2}, {5,1}, {6,0}, {7,0}, {6,1}, {5,2}, {4,3}, {3,4}, {2,5}, {1,6}, {0,7}, {1,7}, {2,6}, {3,5}, {4,4}, {5,3}, {6,2}, {7,1}, {7,2}, {6,3}, {5,4}, {4,5}, {3,6}, {2,7}, {3,7}, {4,6}, {5,5}, {6,4}, {7,3}, {7,4}, {6,5}, {5,6}, {4,7}, {5,7}, {6,6}, {7,5}, {7,6}, {6,7}, {7,7}};
 __device__ constexpr unsigned char STD_SCAN8_CAVLC[64][2] = {{0,0}, {1,1}, {1,2}, {2,2}, {4,1}, {0,5}, {3,3}, {7,0}, {3,4}, {1,7}, {5,3}, {6,3}, {2,7}, {6,4}, {5,6}, {7,5}, {1,0}, {2,0}, {0,3}, {3,1}, {3,2}, {0,6}, {4,2}, {6,1}, {2,5}, {2,6}, {6,2}, {5,4}, {3,7}, {7,3}, {4,7}, {7,6}, {0,1}, {3,0}, {0,4}, {4,0}, {2,3}, {1,5}, {5,1}, {5,2}, {1,6}, {3,5}, {7,1}, {4,5}, {4,6}, {7,4}, {5,7}, {6,7}, {0,2}, {2,1}, {1,3}, {5,0}, {1,4}, {2,4}, {6,0}, {4,3}, {0,7}, {4,4}, {7,2}, {3,6}, {5,5}, {6,5}, {6,6}, {7,7}};
 
+// four consecutive samples at an arbitrary byte address: two aligned word loads + PRMT
+__device__ __forceinline__ unsigned tq_ld4(const uint8_t *p) {
+  const unsigned sh = (unsigned)(size_t)p & 3u;
+  const unsigned *a = (const unsigned *)(p - sh);
+  return __byte_perm(__ldg(a), __ldg(a + 1), 0x3210u + 0x1111u * sh);
+}
+
 struct QOut { int nonzero; int cost; };
 
 // quantise one block in scan order.  coef: in = transformed, out = dequantised (JM leaves it in tblock).
@@ -269,7 +276,11 @@ __global__ void k_mc_tq_modes(const jmb_me_res *__restrict__ res, int n_mb, int 
 #pragma unroll
   for (int y = 0; y < N; y++)
 #pragma unroll
-    for (int x = 0; x < N; x++) rr[y * N + x] = (int)sp[(size_t)y * cur_pitch + x] - (int)rp[(size_t)y * ref_pitch + x];
+    for (int x4 = 0; x4 < N; x4 += 4) {       // word loads: the source is 4-aligned, the prediction is not
+      const unsigned sv = *(const unsigned *)(sp + (size_t)y * cur_pitch + x4), pv = tq_ld4(rp + (size_t)y * ref_pitch + x4);
+#pragma unroll
+      for (int x = 0; x < 4; x++) rr[y * N + x4 + x] = (int)((sv >> (8 * x)) & 255) - (int)((pv >> (8 * x)) & 255);
+    }
   if (N == 4) fwd4(rr); else fwd8(rr);
   const size_t mo = (size_t)blockIdx.y * n_mb + mb;          // mode-major output index
   QOut o = quant_block<N, false, STD>(q, rr, nullptr, nullptr, nullptr, levels + mo * 256 + b * N * N);
