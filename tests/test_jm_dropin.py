@@ -151,3 +151,29 @@ def test_device_luma_residual_coding_matches_jm_in_the_live_encoder(tmp_path, na
     line = [l for l in r.stderr.splitlines() if "luma_residual_coding verified on" in l]
     assert line, r.stderr[-400:]
     assert int(line[0].split("verified on")[1].split()[0]) > 100, line[0]
+
+
+FIXTURES = os.path.join(ROOT, "oracle", "_ref", "fixtures")
+
+
+@pytest.mark.gpu
+@needs_bins
+@pytest.mark.skipif(not os.path.isdir(FIXTURES), reason="reference fixtures not copied (make -C oracle ref)")
+@pytest.mark.parametrize("cfg", ["encoder_baseline.cfg", "encoder.cfg", "encoder_yuv422.cfg"])
+def test_bundled_configurations(tmp_path, cfg):
+    """BASELINE configs[0] and its siblings exactly as shipped: JM's own cfg files on JM's own foreman clips (copied into
+    the git-ignored oracle/_ref/fixtures by the oracle Makefile).  encoder_baseline.cfg = Baseline, fast full search +-32,
+    5 references, adaptive rounding; encoder.cfg = High, EPZS + HME, 7 B pictures, bi-predictive ME, 8x8 transform, CABAC;
+    encoder_yuv422.cfg = High 4:2:2.  Stock encoder vs re-linked encoder: same bitstream, reconstruction and trace."""
+    import shutil
+    for f in os.listdir(FIXTURES):
+        shutil.copy(os.path.join(FIXTURES, f), tmp_path / f)
+    outs = {}
+    for tag, exe, env in (("ref", REF, {}), ("gpu", JMB, {"JMB_SHIM_VERBOSE": "1"})):
+        e = dict(os.environ); e.update(env)
+        r = subprocess.run([exe, "-d", cfg, "-p", f"OutputFile={tag}.264", "-p", f"ReconFile={tag}_rec.yuv", "-p", f"TraceFile={tag}_trace.txt"],
+                           cwd=tmp_path, env=e, capture_output=True, text=True, timeout=1500)
+        assert r.returncode == 0, (tag, r.stderr[-800:])
+        outs[tag] = r
+    assert any(l.startswith("[jmb shim]") for l in outs["gpu"].stderr.splitlines())
+    _same_outputs(tmp_path, "ref", "gpu")
