@@ -32,7 +32,11 @@ constexpr int CH = 72;             // multiple of 4 (a thread owns 4 vertically 
 constexpr int WIN_PITCH = JMB_WIN_BOX_W;   // bytes per staged window row = the TMA box width (>= CW + 15 + the fifth word)
 constexpr int WIN_ROWS = CH + 15;
 static_assert(WIN_ROWS == JMB_WIN_BOX_H && 15 + CW + 15 + 4 <= WIN_PITCH, "TMA box and window geometry disagree");
-constexpr int S1_COLS = 10, S1_RGS = 3, S1_ITEMS = S1_COLS * S1_RGS, S1_PITCH = 43;   // stage-1 neighbourhood
+#ifndef JMB_S1_COLS
+#define JMB_S1_COLS 8
+#define JMB_S1_RGS 2
+#endif
+constexpr int S1_COLS = JMB_S1_COLS, S1_RGS = JMB_S1_RGS, S1_ITEMS = S1_COLS * S1_RGS, S1_PITCH = 43;   // stage-1 neighbourhood
 constexpr int ADJ_PITCH = 44;      // words per column (>= NPART; 176 B keeps the 128-bit row reads conflict-free)
 constexpr int WQ_CAP = 192;          // per-warp queue of gate hits awaiting their exact evaluation
 constexpr int HS_PITCH = NPART + 1;   // u16 per thread: SADs of the partitions of a displacement that met the gate
