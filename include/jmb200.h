@@ -115,6 +115,28 @@ typedef struct jmb_quant_desc {
   uint8_t c_cost[64];          /* COEFF_COST4x4 / COEFF_COST8x8 row in use */
 } jmb_quant_desc;
 
+/* List quantiser description: the DC / AC members of JM's quantiser family -- quant_ac4x4_normal/_around
+ * (lencod/src/quant4x4_normal.c:117, quant4x4_around.c:132), quant_dc4x4_normal (:200), quant_dc2x2_normal/_around and
+ * quant_dc4x2_normal/_around (lencod/src/quantChroma_normal.c, quantChroma_around.c) -- are one loop over m coefficients
+ * taken in scan order.  The caller gathers the coefficients in that order and gives per-position parameters. */
+enum { JMB_DQ_LEVEL = 0,         /* coefficient := level                               (quant_dc4x4_*)            */
+       JMB_DQ_SHIFT = 1,         /* coefficient := (level * InvScale) << qp_per        (quant_dc2x2_*, _dc4x2_*)  */
+       JMB_DQ_SHIFT_RND4 = 2 };  /* coefficient := ((level * InvScale) << qp_per + 8) >> 4   (quant_ac4x4_*)      */
+typedef struct jmb_qlist_desc {
+  int32_t m;                     /* coefficients per list, 1..16 */
+  int32_t q_bits;                /* forward shift: Q_BITS + qp_per (+1 for the DC forms) */
+  int32_t qp_per;
+  int32_t dequant;               /* JMB_DQ_* */
+  int32_t clip;                  /* CAVLC: clip levels to 2063 */
+  int32_t use_cost;              /* accumulate coeff_cost (c_cost[run] / MAX_VALUE), quant_ac4x4_* only */
+  int32_t around;                /* also write fadjust (quant_ac4x4_around) */
+  int32_t adapt_rnd_weight;
+  int32_t params[16][3];         /* per list position {Offset (already doubled for the DC forms), Scale, InvScale} */
+  uint8_t c_cost[16];
+} jmb_qlist_desc;
+
+enum { JMB_HAD_4X4 = 0, JMB_IHAD_4X4 = 1, JMB_HAD_4X2 = 2, JMB_IHAD_4X2 = 3, JMB_HAD_2X2 = 4, JMB_IHAD_2X2 = 5 };
+
 /* ---- context --------------------------------------------------------------------------------- */
 int         jmb_abi_version(void);
 int         jmb_create(int device, jmb_ctx **out);
@@ -197,6 +219,16 @@ int jmb_mc_tq(jmb_ctx *ctx, const jmb_mb_pred *pred, int n_mb, const jmb_quant_d
  *   res == NULL: the results of the last jmb_me_search_frame call, still resident on the device. */
 int jmb_mc_tq_modes(jmb_ctx *ctx, const jmb_me_res *res, int n_mb, unsigned mode_mask, const jmb_quant_desc *q,
                     int16_t *levels, int32_t *coeff_cost, uint32_t *cbp_blk, int loc);
+
+/* nlist lists of q->m coefficients (scan order), in place: on return the dequantised coefficients; levels / runs [nlist][17]
+ * (terminated by level 0), fadjust [nlist][m] (around only, may be NULL), coeff_cost [nlist] (added to; may be NULL), nonzero [nlist] */
+int jmb_quant_list(jmb_ctx *ctx, const jmb_qlist_desc *q, int32_t *coef, int nlist, int32_t *levels, int32_t *runs, int32_t *fadjust,
+                   int32_t *coeff_cost, int32_t *nonzero, int loc);
+
+/* hadamard4x4 / ihadamard4x4 / hadamard4x2 / ihadamard4x2 / hadamard2x2 / ihadamard2x2 (lcommon/src/transform.c:121-330) on nblk
+ * blocks, in place.  Flat layouts: 4x4 = 16 row-major; 4x2 = 8 (forward: 2 rows x 4 in and out; inverse: 2 rows x 4 in,
+ * 4 rows x 2 out); 2x2 = 4 ({b[0][0], b[0][4], b[4][0], b[4][4]} in for the forward, as JM reads them). */
+int jmb_hadamard(jmb_ctx *ctx, int kind, int32_t *vals, int nblk, int loc);
 
 /* inverse4x4 / inverse8x8 (lcommon/src/transform.c:70, :450) on nblk blocks of n*n int32 (dequantised coefficients), in place */
 int jmb_inverse_transform(jmb_ctx *ctx, int32_t *blocks, int nblk, int n, int loc);

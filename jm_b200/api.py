@@ -26,6 +26,11 @@ ME_RES = np.dtype([("mv_x", "<i2"), ("mv_y", "<i2"), ("imv_x", "<i2"), ("imv_y",
 MB_PRED = np.dtype([("mv", "<i2", (16, 2)), ("b8mode", "u1", (4,)), ("ref", "u1", (4,))])
 QUANT_DESC = np.dtype([("n", "<i4"), ("qp", "<i4"), ("is_cavlc", "<i4"), ("around", "<i4"), ("adapt_rnd_weight", "<i4"),
                        ("qparams", "<i4", (64, 3)), ("scan", "u1", (64, 2)), ("c_cost", "u1", (64,))])
+QLIST_DESC = np.dtype([("m", "<i4"), ("q_bits", "<i4"), ("qp_per", "<i4"), ("dequant", "<i4"), ("clip", "<i4"), ("use_cost", "<i4"),
+                       ("around", "<i4"), ("adapt_rnd_weight", "<i4"), ("params", "<i4", (16, 3)), ("c_cost", "u1", (16,))])
+DQ_LEVEL, DQ_SHIFT, DQ_SHIFT_RND4 = 0, 1, 2
+HAD_4X4, IHAD_4X4, HAD_4X2, IHAD_4X2, HAD_2X2, IHAD_2X2 = range(6)
+assert QLIST_DESC.itemsize == 240
 assert ME_REQ.itemsize == 40 and ME_RES.itemsize == 24 and MB_PRED.itemsize == 72 and QUANT_DESC.itemsize == 980
 
 
@@ -68,6 +73,8 @@ def load_library():
     L.jmb_pred_from_results.argtypes = [vp, vp, i, i, vp, i]
     L.jmb_mc_tq_modes.argtypes = [vp, vp, i, C.c_uint, vp, vp, vp, vp, i]
     L.jmb_inverse_transform.argtypes = [vp, vp, i, i, i]
+    L.jmb_hadamard.argtypes = [vp, i, vp, i, i]
+    L.jmb_quant_list.argtypes = [vp, vp, vp, i, vp, vp, vp, vp, vp, i]
     L.jmb_luma_residual_coding.argtypes = [vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, i]
     L.jmb_luma_residual_coding_modes.argtypes = [vp, vp, i, C.c_uint, vp, vp, vp, vp, vp, vp, vp, i]
     L.jmb_timing_enable.argtypes = [vp, i]
@@ -98,6 +105,32 @@ def mb_partitions():
                 out.append((t, x, y))
     assert all(part_slot(t, x // 4, y // 4) == k for k, (t, x, y) in enumerate(out))
     return out
+
+
+def qlist_plan(variant, qp, qparams, scan, c_cost, is_cavlc, arw=0):
+    """How one of JM's DC / AC quantisers maps onto the list quantiser (jmb_quant_list) -- the same mapping the shim does in C.
+    variant: 6 quant_ac4x4_normal, 7 quant_ac4x4_around, 8 quant_dc4x4_normal, 9/10 quant_dc2x2_normal/_around,
+             11/12 quant_dc4x2_normal/_around.  qparams: [4][4][3] for 6,7; one triple otherwise.
+    Returns dict(order = flat index into the function's coefficient array per list position, + the descriptor fields)."""
+    per = qp // 6
+    scan = np.asarray(scan).reshape(-1, 2)
+    qparams = np.asarray(qparams, np.int64)
+    if variant in (6, 7):
+        order = [int(scan[k][1]) * 4 + int(scan[k][0]) for k in range(1, 16)]
+        params = [qparams.reshape(16, 3)[o] for o in order]
+        return dict(order=order, params=np.array(params), q_bits=15 + per, qp_per=per, dequant=DQ_SHIFT_RND4, clip=int(is_cavlc), use_cost=1,
+                    around=int(variant == 7), arw=arw, c_cost=np.asarray(c_cost, np.uint8)[:16])
+    one = qparams.reshape(-1)[:3]
+    dc = np.array([[2 * one[0], one[1], one[2]]])
+    if variant == 8:
+        order = [int(scan[k][1]) * 4 + int(scan[k][0]) for k in range(16)]
+        dq = DQ_LEVEL
+    elif variant in (9, 10):
+        order, dq = [0, 1, 2, 3], DQ_SHIFT
+    else:
+        order, dq = [int(scan[k][0]) * 4 + int(scan[k][1]) for k in range(8)], DQ_SHIFT       # j first: block.c:88-94
+    return dict(order=order, params=np.repeat(dc, len(order), 0), q_bits=16 + per, qp_per=per, dequant=dq, clip=int(is_cavlc), use_cost=0,
+                around=0, arw=arw, c_cost=np.zeros(16, np.uint8))
 
 
 def quant_desc(n, qp, qparams, scan, c_cost, is_cavlc, around=0, arw=0):
@@ -224,6 +257,26 @@ class Context:
         b = np.ascontiguousarray(blocks, np.int32).reshape(-1, n * n).copy()
         self._ck(self.L.jmb_forward_transform(self.h, _ptr(b), len(b), n, HOST))
         return b.reshape(-1, n, n)
+
+    def hadamard(self, kind, vals, per):
+        b = np.ascontiguousarray(vals, np.int32).reshape(-1, per).copy()
+        self._ck(self.L.jmb_hadamard(self.h, kind, _ptr(b), len(b), HOST))
+        return b
+
+    def quant_list(self, plan, coef_flat, cost0=0):
+        """One list through jmb_quant_list, gathered / scattered like the shim does."""
+        coef = np.ascontiguousarray(coef_flat, np.int32).reshape(-1).copy()
+        order = np.asarray(plan["order"]); m = len(order)
+        d = np.zeros(1, QLIST_DESC)
+        for k in ("m", "q_bits", "qp_per", "dequant", "clip", "use_cost", "around"):
+            d[k] = m if k == "m" else plan[k]
+        d["adapt_rnd_weight"] = plan["arw"]; d["params"][0, :m] = plan["params"]; d["c_cost"][0] = plan["c_cost"]
+        lst = coef[order].copy(); levels = np.zeros(17, np.int32); runs = np.zeros(17, np.int32); fadj = np.zeros(m, np.int32)
+        cost = np.array([cost0], np.int32); nz = np.zeros(1, np.int32)
+        self._ck(self.L.jmb_quant_list(self.h, _ptr(d), _ptr(lst), 1, _ptr(levels), _ptr(runs), _ptr(fadj), _ptr(cost), _ptr(nz), HOST))
+        coef[order] = lst
+        fa = np.zeros(len(coef), np.int32); fa[order] = fadj
+        return dict(nonzero=int(nz[0]), coef=coef, levels=levels, runs=runs, fadjust=fa, coeff_cost=int(cost[0]))
 
     def inverse_transform(self, blocks, n):
         b = np.ascontiguousarray(blocks, np.int32).reshape(-1, n * n).copy()

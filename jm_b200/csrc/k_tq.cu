@@ -288,6 +288,78 @@ __global__ void k_mc_tq_modes(const jmb_me_res *__restrict__ res, int n_mb, int 
   if (o.nonzero) atomicOr(&cbp_blk[mo], (N == 4) ? (1u << (by4 * 4 + bx4)) : (51u << (4 * b8 - 2 * (b8 & 1))));
 }
 
+// List quantiser: the DC / AC members of JM's quantiser family (quant_ac4x4_*, quant_dc4x4_normal, quant_dc2x2_*,
+// quant_dc4x2_*: lencod/src/quant4x4_normal.c:117,200, quant4x4_around.c:132, quantChroma_normal.c, quantChroma_around.c)
+// are one loop over a list of m coefficients already in scan order, with per-position {Offset, Scale, InvScale}, one
+// of three dequantisation forms and optional cost / adaptive-rounding outputs.  One thread per list.
+__global__ void k_quant_list(const jmb_qlist_desc *__restrict__ qd, int *coef, int nlist, int *levels, int *runs, int *fadjust,
+                             int *coeff_cost, int *nonzero) {
+  __shared__ jmb_qlist_desc q;
+  for (int i = threadIdx.x; i < (int)(sizeof(q) / 4); i += blockDim.x) ((int *)&q)[i] = ((const int *)qd)[i];
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nlist) return;
+  int *c = coef + (size_t)t * q.m, *lv = levels + (size_t)t * 17, *rn = runs + (size_t)t * 17;
+  int *fa = (fadjust && q.around) ? fadjust + (size_t)t * q.m : nullptr;
+  int run = 0, n = 0, nz = 0, cost = coeff_cost ? coeff_cost[t] : 0;
+  for (int k = 0; k < q.m; k++) {
+    const int v = c[k];
+    int adj = 0;
+    if (v != 0) {
+      const int scaled = abs(v) * q.params[k][1];
+      int level = (scaled + q.params[k][0]) >> q.q_bits;
+      if (level != 0) {
+        if (q.clip) level = min(level, 2063);
+        adj = (q.adapt_rnd_weight * (scaled - (level << q.q_bits)) + (1 << q.q_bits)) >> (q.q_bits + 1);
+        if (q.use_cost) cost += (level > 1) ? 999999 : q.c_cost[run];
+        if (v < 0) level = -level;
+        const int dq = (level * q.params[k][2]) << q.qp_per;
+        c[k] = q.dequant == JMB_DQ_LEVEL ? level : (q.dequant == JMB_DQ_SHIFT ? dq : ((dq + 8) >> 4));
+        lv[n] = level; rn[n] = run; n++; run = 0; nz = 1;
+      } else { c[k] = 0; run++; }
+    } else run++;
+    if (fa) fa[k] = adj;
+  }
+  lv[n] = 0;
+  if (coeff_cost) coeff_cost[t] = cost;
+  nonzero[t] = nz;
+}
+
+// hadamard4x4 / ihadamard4x4 / hadamard4x2 / ihadamard4x2 / hadamard2x2 / ihadamard2x2, lcommon/src/transform.c:121-330.
+// One thread per block; flat layouts: 4x4 row-major [16]; 4x2: forward in/out = 2 rows x 4 [8], inverse in = 2 rows x 4,
+// out = 4 rows x 2 [8]; 2x2: [4] = {b00, b04, b40, b44} in, {t0..t3} out (and the reverse).
+__global__ void k_hadamard(int kind, int *vals, int nblk) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nblk) return;
+  if (kind == JMB_HAD_4X4 || kind == JMB_IHAD_4X4) {
+    int *b = vals + (size_t)t * 16, m[16];
+    for (int i = 0; i < 4; i++) {
+      const int p0 = b[4 * i], p1 = b[4 * i + 1], p2 = b[4 * i + 2], p3 = b[4 * i + 3];
+      if (kind == JMB_HAD_4X4) { const int t0 = p0 + p3, t1 = p1 + p2, t2 = p1 - p2, t3 = p0 - p3; m[4 * i] = t0 + t1; m[4 * i + 1] = t3 + t2; m[4 * i + 2] = t0 - t1; m[4 * i + 3] = t3 - t2; }
+      else { const int q0 = p0 + p2, q1 = p0 - p2, q2 = p1 - p3, q3 = p1 + p3; m[4 * i] = q0 + q3; m[4 * i + 1] = q1 + q2; m[4 * i + 2] = q1 - q2; m[4 * i + 3] = q0 - q3; }
+    }
+    for (int i = 0; i < 4; i++) {
+      const int p0 = m[i], p1 = m[4 + i], p2 = m[8 + i], p3 = m[12 + i];
+      if (kind == JMB_HAD_4X4) { const int t0 = p0 + p3, t1 = p1 + p2, t2 = p1 - p2, t3 = p0 - p3; b[i] = (t0 + t1) >> 1; b[4 + i] = (t2 + t3) >> 1; b[8 + i] = (t0 - t1) >> 1; b[12 + i] = (t3 - t2) >> 1; }
+      else { const int q0 = p0 + p2, q1 = p0 - p2, q2 = p1 - p3, q3 = p1 + p3; b[i] = q0 + q3; b[4 + i] = q1 + q2; b[8 + i] = q1 - q2; b[12 + i] = q0 - q3; }
+    }
+  } else if (kind == JMB_HAD_4X2 || kind == JMB_IHAD_4X2) {
+    int *b = vals + (size_t)t * 8, m[8], o[8];
+    for (int i = 0; i < 4; i++) { m[i] = b[i] + b[4 + i]; m[4 + i] = b[i] - b[4 + i]; }
+    for (int i = 0; i < 2; i++) {
+      const int p0 = m[4 * i], p1 = m[4 * i + 1], p2 = m[4 * i + 2], p3 = m[4 * i + 3];
+      if (kind == JMB_HAD_4X2) { const int t0 = p0 + p3, t1 = p1 + p2, t2 = p1 - p2, t3 = p0 - p3; o[4 * i] = t0 + t1; o[4 * i + 1] = t3 + t2; o[4 * i + 2] = t0 - t1; o[4 * i + 3] = t3 - t2; }
+      else { const int t0 = p0 + p2, t1 = p0 - p2, t2 = p1 - p3, t3 = p1 + p3; o[i] = t0 + t3; o[2 + i] = t1 + t2; o[4 + i] = t1 - t2; o[6 + i] = t0 - t3; }   // block[r][i], 4 rows x 2
+    }
+    for (int i = 0; i < 8; i++) b[i] = o[i];
+  } else {
+    int *b = vals + (size_t)t * 4;
+    const int a = b[0], c = b[1], d = b[2], e = b[3];
+    if (kind == JMB_HAD_2X2) { const int p0 = a + c, p1 = a - c, p2 = d + e, p3 = d - e; b[0] = p0 + p2; b[1] = p1 + p3; b[2] = p0 - p2; b[3] = p1 - p3; }
+    else { const int t0 = a + c, t1 = a - c, t2 = d + e, t3 = d - e; b[0] = t0 + t2; b[1] = t1 + t3; b[2] = t0 - t2; b[3] = t1 - t3; }
+  }
+}
+
 template <int N>
 __global__ void k_inverse(int *blocks, int nblk) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -575,6 +647,64 @@ int jmb_mc_tq(jmb_ctx *ctx, const jmb_mb_pred *pred, int n_mb, const jmb_quant_d
     JMB_CUDA(ctx, cudaMemcpyAsync(levels, d_lv, (size_t)n_mb * 512, cudaMemcpyDeviceToHost, ctx->stream));
     JMB_CUDA(ctx, cudaMemcpyAsync(coeff_cost, d_cc, (size_t)n_mb * 16, cudaMemcpyDeviceToHost, ctx->stream));
     JMB_CUDA(ctx, cudaMemcpyAsync(cbp_blk, d_cbp, (size_t)n_mb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return JMB_OK;
+}
+
+int jmb_hadamard(jmb_ctx *ctx, int kind, int32_t *vals, int nblk, int loc) {
+  if (kind < JMB_HAD_4X4 || kind > JMB_IHAD_2X2) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_hadamard: kind %d", kind);
+  if (nblk <= 0) return JMB_OK;
+  JMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int per = (kind <= JMB_IHAD_4X4) ? 16 : (kind <= JMB_IHAD_4X2 ? 8 : 4);
+  const size_t bytes = (size_t)nblk * per * 4;
+  int *d = vals;
+  if (loc == JMB_HOST) {
+    int rc = jmb_reserve_dev(ctx, &ctx->d_stage, &ctx->d_stage_cap, bytes); if (rc) return rc;
+    JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage, vals, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    d = (int *)ctx->d_stage;
+  }
+  jmb_time_begin(ctx, JMB_K_FORWARD);
+  k_hadamard<<<(nblk + 127) / 128, 128, 0, ctx->stream>>>(kind, d, nblk);
+  jmb_time_end(ctx, JMB_K_FORWARD);
+  JMB_LAUNCH_CHECK(ctx);
+  if (loc == JMB_HOST) {
+    JMB_CUDA(ctx, cudaMemcpyAsync(vals, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return JMB_OK;
+}
+
+int jmb_quant_list(jmb_ctx *ctx, const jmb_qlist_desc *q, int32_t *coef, int nlist, int32_t *levels, int32_t *runs, int32_t *fadjust,
+                   int32_t *coeff_cost, int32_t *nonzero, int loc) {
+  if (!q || q->m < 1 || q->m > 16 || q->q_bits < 1 || q->q_bits > 30 || q->qp_per < 0 || q->qp_per > 14 || q->dequant < JMB_DQ_LEVEL || q->dequant > JMB_DQ_SHIFT_RND4)
+    return jmb_fail(ctx, JMB_ERR_ARG, "jmb_quant_list: bad descriptor");
+  if (nlist <= 0) return JMB_OK;
+  if (!coef || !levels || !runs || !nonzero) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_quant_list: NULL buffer");
+  JMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = jmb_reserve_dev(ctx, &ctx->d_qdesc, &ctx->d_qdesc_cap, sizeof(*q)); if (rc) return rc;
+  JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_qdesc, q, sizeof(*q), cudaMemcpyHostToDevice, ctx->stream));
+  int *d_c = coef, *d_lv = levels, *d_rn = runs, *d_fa = fadjust, *d_cc = coeff_cost, *d_nz = nonzero;
+  const size_t m = (size_t)q->m, n = (size_t)nlist;
+  if (loc == JMB_HOST) {      // arena: coef | levels | runs | fadjust | cost | nonzero
+    rc = jmb_reserve_dev(ctx, &ctx->d_stage, &ctx->d_stage_cap, n * (2 * m + 34 + 2) * 4); if (rc) return rc;
+    int *base = (int *)ctx->d_stage;
+    d_c = base; d_lv = base + n * m; d_rn = d_lv + n * 17; d_fa = fadjust ? d_rn + n * 17 : nullptr; d_cc = coeff_cost ? d_rn + n * 17 + n * m : nullptr; d_nz = d_rn + n * 17 + n * m + n;
+    JMB_CUDA(ctx, cudaMemcpyAsync(d_c, coef, n * m * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (coeff_cost) JMB_CUDA(ctx, cudaMemcpyAsync(d_cc, coeff_cost, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    JMB_CUDA(ctx, cudaMemsetAsync(d_lv, 0, n * 34 * 4, ctx->stream));
+  }
+  jmb_time_begin(ctx, JMB_K_QUANT);
+  k_quant_list<<<(nlist + 63) / 64, 64, 0, ctx->stream>>>((const jmb_qlist_desc *)ctx->d_qdesc, d_c, nlist, d_lv, d_rn, d_fa, d_cc, d_nz);
+  jmb_time_end(ctx, JMB_K_QUANT);
+  JMB_LAUNCH_CHECK(ctx);
+  if (loc == JMB_HOST) {
+    JMB_CUDA(ctx, cudaMemcpyAsync(coef, d_c, n * m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaMemcpyAsync(levels, d_lv, n * 17 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaMemcpyAsync(runs, d_rn, n * 17 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (fadjust && q->around) JMB_CUDA(ctx, cudaMemcpyAsync(fadjust, d_fa, n * m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (coeff_cost) JMB_CUDA(ctx, cudaMemcpyAsync(coeff_cost, d_cc, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaMemcpyAsync(nonzero, d_nz, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return JMB_OK;

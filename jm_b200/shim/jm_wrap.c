@@ -13,7 +13,11 @@
  *       -Wl,--wrap=forward4x4 -Wl,--wrap=forward8x8 -Wl,--wrap=inverse4x4 -Wl,--wrap=inverse8x8 \
  *       -Wl,--wrap=quant_4x4_normal -Wl,--wrap=quant_4x4_around \
  *       -Wl,--wrap=quant_8x8_normal -Wl,--wrap=quant_8x8_around \
- *       -Wl,--wrap=quant_8x8cavlc_normal -Wl,--wrap=quant_8x8cavlc_around -Wl,--wrap=luma_residual_coding
+ *       -Wl,--wrap=quant_8x8cavlc_normal -Wl,--wrap=quant_8x8cavlc_around -Wl,--wrap=luma_residual_coding \
+ *       -Wl,--wrap=quant_ac4x4_normal -Wl,--wrap=quant_ac4x4_around -Wl,--wrap=quant_dc4x4_normal \
+ *       -Wl,--wrap=quant_dc2x2_normal -Wl,--wrap=quant_dc2x2_around -Wl,--wrap=quant_dc4x2_normal -Wl,--wrap=quant_dc4x2_around \
+ *       -Wl,--wrap=hadamard4x4 -Wl,--wrap=ihadamard4x4 -Wl,--wrap=hadamard4x2 -Wl,--wrap=ihadamard4x2 \
+ *       -Wl,--wrap=hadamard2x2 -Wl,--wrap=ihadamard2x2
  *
  * No JM source file is edited: every symbol above is defined in one translation unit and referenced
  * from another, so the linker redirects the reference to __wrap_<sym>.
@@ -44,6 +48,7 @@
 #include "transform.h"
 #include "quant4x4.h"
 #include "quant8x8.h"
+#include "quantChroma.h"
 #include "me_distortion.h"
 #include "mv_prediction.h"
 
@@ -67,6 +72,19 @@ int     __real_quant_8x8_around(Macroblock *, int **, struct quant_methods *);
 int     __real_quant_8x8cavlc_normal(Macroblock *, int **, struct quant_methods *, int ***);
 int     __real_quant_8x8cavlc_around(Macroblock *, int **, struct quant_methods *, int ***);
 void    __real_luma_residual_coding(Macroblock *currMB);
+int     __real_quant_ac4x4_normal(Macroblock *, int **, struct quant_methods *);
+int     __real_quant_ac4x4_around(Macroblock *, int **, struct quant_methods *);
+int     __real_quant_dc4x4_normal(Macroblock *, int **, int, int *, int *, LevelQuantParams *, const byte (*)[2]);
+int     __real_quant_dc2x2_normal(Macroblock *, int **, int, int *, int *, LevelQuantParams *, int **, const byte (*)[2]);
+int     __real_quant_dc2x2_around(Macroblock *, int **, int, int *, int *, LevelQuantParams *, int **, const byte (*)[2]);
+int     __real_quant_dc4x2_normal(Macroblock *, int **, int, int *, int *, LevelQuantParams *, int **, const byte (*)[2]);
+int     __real_quant_dc4x2_around(Macroblock *, int **, int, int *, int *, LevelQuantParams *, int **, const byte (*)[2]);
+void    __real_hadamard4x4(int **, int **);
+void    __real_ihadamard4x4(int **, int **);
+void    __real_hadamard4x2(int **, int **);
+void    __real_ihadamard4x2(int **, int **);
+void    __real_hadamard2x2(int **, int *);
+void    __real_ihadamard2x2(int *, int *);
 distblk __real_computeSAD(StorablePicture *, MEBlock *, distblk, MotionVector *);
 distblk __real_computeSSE(StorablePicture *, MEBlock *, distblk, MotionVector *);
 distblk __real_computeSATD(StorablePicture *, MEBlock *, distblk, MotionVector *);
@@ -424,6 +442,162 @@ distblk __wrap_computeSATD(StorablePicture *ref1, MEBlock *mv_block, distblk min
 {
   if (!shim_on(FAM_DIST)) return __real_computeSATD(ref1, mv_block, min_mcost, cand);
   return block_dist(JMB_SATD, ref1, mv_block, min_mcost, cand);
+}
+
+/* ---- the DC / AC members of the quantiser family and the Hadamard transforms (Intra16x16 and chroma DC paths) ----
+ * quant_ac4x4_normal/_around (quant4x4_normal.c:117, quant4x4_around.c:132), quant_dc4x4_normal (:200), quant_dc2x2_* and
+ * quant_dc4x2_* (quantChroma_normal.c, quantChroma_around.c) all map onto jmb_quant_list: the wrapper gathers the
+ * coefficients in the function's scan order with the per-position parameters and scatters the results back. */
+static int quant_list(Macroblock *currMB, int m, int **cptr /* m pointers into tblock */, int32_t params[][3], int q_bits, int qp_per,
+                      int dequant, int use_cost, int around, const byte *c_cost, int *coeff_cost, int *L, int *R, int **fptr)
+{
+  jmb_qlist_desc d;
+  int32_t coef[16], levels[17], runs[17], fadj[16], cost = coeff_cost ? *coeff_cost : 0, nz = 0;
+  int k, rc;
+  memset(&d, 0, sizeof(d));
+  d.m = m; d.q_bits = q_bits; d.qp_per = qp_per; d.dequant = dequant; d.use_cost = use_cost; d.around = around;
+  d.clip = (currMB->p_Slice->symbol_mode == CAVLC);
+  d.adapt_rnd_weight = currMB->p_Vid->AdaptRndWeight;
+  for (k = 0; k < m; k++) { d.params[k][0] = params[k][0]; d.params[k][1] = params[k][1]; d.params[k][2] = params[k][2]; coef[k] = *cptr[k]; }
+  if (c_cost) for (k = 0; k < 16; k++) d.c_cost[k] = c_cost[k];
+  rc = jmb_quant_list(S.ctx, &d, coef, 1, levels, runs, around ? fadj : NULL, &cost, &nz, JMB_HOST);
+  if (rc) jmb_die("jmb_quant_list", rc);
+  for (k = 0; k < m; k++) { *cptr[k] = coef[k]; if (around && fptr) *fptr[k] = fadj[k]; }
+  for (k = 0; levels[k] != 0; k++) { L[k] = levels[k]; R[k] = runs[k]; }
+  L[k] = 0;
+  if (coeff_cost) *coeff_cost = cost;
+  S.calls[6]++;
+  return nz;
+}
+
+static int quant_ac4x4(Macroblock *currMB, int **tblock, struct quant_methods *qm, int around)
+{
+  int *cptr[15], *fptr[15];
+  int32_t params[15][3];
+  int k, qp_per = currMB->p_Vid->p_Quant->qp_per_matrix[qm->qp];
+  for (k = 1; k < 16; k++)
+  {
+    int i = qm->pos_scan[k][0], j = qm->pos_scan[k][1];
+    cptr[k - 1] = &tblock[j][qm->block_x + i];
+    fptr[k - 1] = (around && qm->fadjust) ? &qm->fadjust[j][qm->block_x + i] : NULL;
+    params[k - 1][0] = qm->q_params[j][i].OffsetComp; params[k - 1][1] = qm->q_params[j][i].ScaleComp; params[k - 1][2] = qm->q_params[j][i].InvScaleComp;
+  }
+  return quant_list(currMB, 15, cptr, params, Q_BITS + qp_per, qp_per, JMB_DQ_SHIFT_RND4, 1, around, qm->c_cost, qm->coeff_cost,
+                    qm->ACLevel, qm->ACRun, (around && qm->fadjust) ? fptr : NULL);
+}
+int __wrap_quant_ac4x4_normal(Macroblock *currMB, int **tblock, struct quant_methods *q_method)
+{
+  if (!shim_on(FAM_TQ)) return __real_quant_ac4x4_normal(currMB, tblock, q_method);
+  return quant_ac4x4(currMB, tblock, q_method, 0);
+}
+int __wrap_quant_ac4x4_around(Macroblock *currMB, int **tblock, struct quant_methods *q_method)
+{
+  if (!shim_on(FAM_TQ)) return __real_quant_ac4x4_around(currMB, tblock, q_method);
+  return quant_ac4x4(currMB, tblock, q_method, 1);
+}
+
+/* the DC forms use ONE parameter triple, a doubled offset and one more bit of shift */
+static int quant_dc(Macroblock *currMB, int m, int **cptr, int qp, LevelQuantParams *qp1, int dequant, int *L, int *R)
+{
+  int32_t params[16][3];
+  int k, qp_per = currMB->p_Vid->p_Quant->qp_per_matrix[qp];
+  for (k = 0; k < m; k++) { params[k][0] = qp1->OffsetComp << 1; params[k][1] = qp1->ScaleComp; params[k][2] = qp1->InvScaleComp; }
+  return quant_list(currMB, m, cptr, params, Q_BITS + qp_per + 1, qp_per, dequant, 0, 0, NULL, NULL, L, R, NULL);
+}
+int __wrap_quant_dc4x4_normal(Macroblock *currMB, int **tblock, int qp, int *DCLevel, int *DCRun, LevelQuantParams *q_params_4x4, const byte (*pos_scan)[2])
+{
+  int *cptr[16], k;
+  if (!shim_on(FAM_TQ)) return __real_quant_dc4x4_normal(currMB, tblock, qp, DCLevel, DCRun, q_params_4x4, pos_scan);
+  for (k = 0; k < 16; k++) cptr[k] = &tblock[pos_scan[k][1]][pos_scan[k][0]];
+  return quant_dc(currMB, 16, cptr, qp, q_params_4x4, JMB_DQ_LEVEL, DCLevel, DCRun);
+}
+static int quant_dc2x2(Macroblock *currMB, int **tblock, int qp, int *DCLevel, int *DCRun, LevelQuantParams *qp1)
+{
+  int *cptr[4], k;
+  for (k = 0; k < 4; k++) cptr[k] = &(*tblock)[k];
+  return quant_dc(currMB, 4, cptr, qp, qp1, JMB_DQ_SHIFT, DCLevel, DCRun);
+}
+int __wrap_quant_dc2x2_normal(Macroblock *currMB, int **tblock, int qp, int *DCLevel, int *DCRun, LevelQuantParams *q, int **fadjust, const byte (*pos_scan)[2])
+{
+  if (!shim_on(FAM_TQ)) return __real_quant_dc2x2_normal(currMB, tblock, qp, DCLevel, DCRun, q, fadjust, pos_scan);
+  return quant_dc2x2(currMB, tblock, qp, DCLevel, DCRun, q);
+}
+int __wrap_quant_dc2x2_around(Macroblock *currMB, int **tblock, int qp, int *DCLevel, int *DCRun, LevelQuantParams *q, int **fadjust, const byte (*pos_scan)[2])
+{
+  if (!shim_on(FAM_TQ)) return __real_quant_dc2x2_around(currMB, tblock, qp, DCLevel, DCRun, q, fadjust, pos_scan);
+  return quant_dc2x2(currMB, tblock, qp, DCLevel, DCRun, q);
+}
+static int quant_dc4x2(Macroblock *currMB, int **tblock, int qp, int *DCLevel, int *DCRun, LevelQuantParams *qp1, const byte (*pos_scan)[2])
+{
+  int *cptr[8], k;
+  for (k = 0; k < 8; k++) cptr[k] = &tblock[pos_scan[k][0]][pos_scan[k][1]];     /* j first: quantChroma_normal.c:128 */
+  return quant_dc(currMB, 8, cptr, qp, qp1, JMB_DQ_SHIFT, DCLevel, DCRun);
+}
+int __wrap_quant_dc4x2_normal(Macroblock *currMB, int **tblock, int qp, int *DCLevel, int *DCRun, LevelQuantParams *q, int **fadjust, const byte (*pos_scan)[2])
+{
+  if (!shim_on(FAM_TQ)) return __real_quant_dc4x2_normal(currMB, tblock, qp, DCLevel, DCRun, q, fadjust, pos_scan);
+  return quant_dc4x2(currMB, tblock, qp, DCLevel, DCRun, q, pos_scan);
+}
+int __wrap_quant_dc4x2_around(Macroblock *currMB, int **tblock, int qp, int *DCLevel, int *DCRun, LevelQuantParams *q, int **fadjust, const byte (*pos_scan)[2])
+{
+  if (!shim_on(FAM_TQ)) return __real_quant_dc4x2_around(currMB, tblock, qp, DCLevel, DCRun, q, fadjust, pos_scan);
+  return quant_dc4x2(currMB, tblock, qp, DCLevel, DCRun, q, pos_scan);
+}
+
+/* hadamard4x4 / ihadamard4x4 / hadamard4x2 / ihadamard4x2 / hadamard2x2 / ihadamard2x2 (lcommon/src/transform.c:121-330) */
+static void hadamard_call(int kind, int32_t *v)
+{
+  int rc = jmb_hadamard(S.ctx, kind, v, 1, JMB_HOST);
+  if (rc) jmb_die("jmb_hadamard", rc);
+  S.calls[4]++;
+}
+void __wrap_hadamard4x4(int **block, int **tblock)
+{
+  int32_t v[16]; int i, j;
+  if (!shim_on(FAM_TQ)) { __real_hadamard4x4(block, tblock); return; }
+  for (j = 0; j < 4; j++) for (i = 0; i < 4; i++) v[4 * j + i] = block[j][i];
+  hadamard_call(JMB_HAD_4X4, v);
+  for (j = 0; j < 4; j++) for (i = 0; i < 4; i++) tblock[j][i] = v[4 * j + i];
+}
+void __wrap_ihadamard4x4(int **tblock, int **block)
+{
+  int32_t v[16]; int i, j;
+  if (!shim_on(FAM_TQ)) { __real_ihadamard4x4(tblock, block); return; }
+  for (j = 0; j < 4; j++) for (i = 0; i < 4; i++) v[4 * j + i] = tblock[j][i];
+  hadamard_call(JMB_IHAD_4X4, v);
+  for (j = 0; j < 4; j++) for (i = 0; i < 4; i++) block[j][i] = v[4 * j + i];
+}
+void __wrap_hadamard4x2(int **block, int **tblock)
+{
+  int32_t v[8]; int i, j;
+  if (!shim_on(FAM_TQ)) { __real_hadamard4x2(block, tblock); return; }
+  for (j = 0; j < 2; j++) for (i = 0; i < 4; i++) v[4 * j + i] = block[j][i];
+  hadamard_call(JMB_HAD_4X2, v);
+  for (j = 0; j < 2; j++) for (i = 0; i < 4; i++) tblock[j][i] = v[4 * j + i];
+}
+void __wrap_ihadamard4x2(int **tblock, int **block)
+{
+  int32_t v[8]; int i, j;
+  if (!shim_on(FAM_TQ)) { __real_ihadamard4x2(tblock, block); return; }
+  for (j = 0; j < 2; j++) for (i = 0; i < 4; i++) v[4 * j + i] = tblock[j][i];
+  hadamard_call(JMB_IHAD_4X2, v);
+  for (j = 0; j < 4; j++) for (i = 0; i < 2; i++) block[j][i] = v[2 * j + i];
+}
+void __wrap_hadamard2x2(int **block, int tblock[4])
+{
+  int32_t v[4]; int k;
+  if (!shim_on(FAM_TQ)) { __real_hadamard2x2(block, tblock); return; }
+  v[0] = block[0][0]; v[1] = block[0][4]; v[2] = block[4][0]; v[3] = block[4][4];
+  hadamard_call(JMB_HAD_2X2, v);
+  for (k = 0; k < 4; k++) tblock[k] = v[k];
+}
+void __wrap_ihadamard2x2(int tblock[4], int block[4])
+{
+  int32_t v[4]; int k;
+  if (!shim_on(FAM_TQ)) { __real_ihadamard2x2(tblock, block); return; }
+  for (k = 0; k < 4; k++) v[k] = tblock[k];
+  hadamard_call(JMB_IHAD_2X2, v);
+  for (k = 0; k < 4; k++) block[k] = v[k];
 }
 
 /* ---- differential check of the whole-macroblock device path against JM itself (JMB_SHIM_VERIFY=1) -----------------

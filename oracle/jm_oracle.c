@@ -500,3 +500,65 @@ long long jmo_luma_residual_coding(const uint16_t *src, const uint16_t *pred, in
   for (int i = 0; i < 256; i++) { int d = (int)src[i] - (int)recon[i]; sse += d * d; }
   return sse;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * List quantiser = quant_ac4x4_normal/_around (lencod/src/quant4x4_normal.c:117-196, quant4x4_around.c:132-215),
+ * quant_dc4x4_normal (quant4x4_normal.c:200-259), quant_dc2x2_normal/_around and quant_dc4x2_normal/_around
+ * (lencod/src/quantChroma_normal.c:37-170, quantChroma_around.c): one loop over m coefficients in scan order.
+ *   params[k] = {Offset (doubled by the caller for the DC forms), Scale, InvScale};  dequant: 0 level, 1 (level*Inv)<<qp_per,
+ *   2 ((level*Inv)<<qp_per + 8)>>4.  levels/runs [17], fadjust [m] (around), *coeff_cost accumulated when use_cost.
+ * ---------------------------------------------------------------------------------------- */
+int jmo_quant_list(int m, int q_bits, int qp_per, int dequant, int clip, int use_cost, int around, int arw,
+                   const int *params, const uint8_t *c_cost, int *coef, int *levels, int *runs, int *fadjust, int *coeff_cost)
+{
+  int run = 0, n = 0, nonzero = 0;
+  for (int k = 0; k < m; k++) {
+    const int *q = params + 3 * k;
+    if (around && fadjust) fadjust[k] = 0;
+    if (coef[k] == 0) { run++; continue; }
+    int scaled = iabs_(coef[k]) * q[1];
+    int level = (scaled + q[0]) >> q_bits;
+    if (level == 0) { coef[k] = 0; run++; continue; }
+    if (clip && level > 2063) level = 2063;
+    if (around && fadjust) fadjust[k] = (arw * (scaled - (level << q_bits)) + (1 << q_bits)) >> (q_bits + 1);
+    if (use_cost) *coeff_cost += (level > 1) ? 999999 : c_cost[run];
+    if (coef[k] < 0) level = -level;
+    int dq = (level * q[2]) << qp_per;
+    coef[k] = dequant == 0 ? level : (dequant == 1 ? dq : ((dq + 8) >> 4));
+    levels[n] = level; runs[n] = run; n++; run = 0; nonzero = 1;
+  }
+  levels[n] = 0;
+  return nonzero;
+}
+
+/* hadamard4x4 / ihadamard4x4 / hadamard4x2 / ihadamard4x2 / hadamard2x2 / ihadamard2x2, lcommon/src/transform.c:121-330.
+ * kind 0..5 in that order; flat layouts as documented in include/jmb200.h (jmb_hadamard). */
+void jmo_hadamard(int kind, int *b)
+{
+  if (kind <= 1) {
+    int m[16];
+    for (int i = 0; i < 4; i++) {
+      int p0 = b[4 * i], p1 = b[4 * i + 1], p2 = b[4 * i + 2], p3 = b[4 * i + 3];
+      if (kind == 0) { int t0 = p0 + p3, t1 = p1 + p2, t2 = p1 - p2, t3 = p0 - p3; m[4 * i] = t0 + t1; m[4 * i + 1] = t3 + t2; m[4 * i + 2] = t0 - t1; m[4 * i + 3] = t3 - t2; }
+      else { int q0 = p0 + p2, q1 = p0 - p2, q2 = p1 - p3, q3 = p1 + p3; m[4 * i] = q0 + q3; m[4 * i + 1] = q1 + q2; m[4 * i + 2] = q1 - q2; m[4 * i + 3] = q0 - q3; }
+    }
+    for (int i = 0; i < 4; i++) {
+      int p0 = m[i], p1 = m[4 + i], p2 = m[8 + i], p3 = m[12 + i];
+      if (kind == 0) { int t0 = p0 + p3, t1 = p1 + p2, t2 = p1 - p2, t3 = p0 - p3; b[i] = (t0 + t1) >> 1; b[4 + i] = (t2 + t3) >> 1; b[8 + i] = (t0 - t1) >> 1; b[12 + i] = (t3 - t2) >> 1; }
+      else { int q0 = p0 + p2, q1 = p0 - p2, q2 = p1 - p3, q3 = p1 + p3; b[i] = q0 + q3; b[4 + i] = q1 + q2; b[8 + i] = q1 - q2; b[12 + i] = q0 - q3; }
+    }
+  } else if (kind <= 3) {
+    int m[8], o[8];
+    for (int i = 0; i < 4; i++) { m[i] = b[i] + b[4 + i]; m[4 + i] = b[i] - b[4 + i]; }
+    for (int i = 0; i < 2; i++) {
+      int p0 = m[4 * i], p1 = m[4 * i + 1], p2 = m[4 * i + 2], p3 = m[4 * i + 3];
+      if (kind == 2) { int t0 = p0 + p3, t1 = p1 + p2, t2 = p1 - p2, t3 = p0 - p3; o[4 * i] = t0 + t1; o[4 * i + 1] = t3 + t2; o[4 * i + 2] = t0 - t1; o[4 * i + 3] = t3 - t2; }
+      else { int t0 = p0 + p2, t1 = p0 - p2, t2 = p1 - p3, t3 = p1 + p3; o[i] = t0 + t3; o[2 + i] = t1 + t2; o[4 + i] = t1 - t2; o[6 + i] = t0 - t3; }
+    }
+    for (int i = 0; i < 8; i++) b[i] = o[i];
+  } else {
+    int a = b[0], c = b[1], d = b[2], e = b[3];
+    if (kind == 4) { int p0 = a + c, p1 = a - c, p2 = d + e, p3 = d - e; b[0] = p0 + p2; b[1] = p1 + p3; b[2] = p0 - p2; b[3] = p1 - p3; }
+    else { int t0 = a + c, t1 = a - c, t2 = d + e, t3 = d - e; b[0] = t0 + t2; b[1] = t1 + t3; b[2] = t0 - t2; b[3] = t1 - t3; }
+  }
+}

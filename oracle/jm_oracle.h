@@ -64,6 +64,9 @@ int  jmo_hadamard_sad4x4(const int16_t *diff);
 int  jmo_hadamard_sad8x8(const int16_t *diff);
 
 /* variants as in oracle/ref_harness.c::jmref_quant */
+int jmo_quant_list(int m, int q_bits, int qp_per, int dequant, int clip, int use_cost, int around, int arw,
+                   const int *params, const uint8_t *c_cost, int *coef, int *levels, int *runs, int *fadjust, int *coeff_cost);
+void jmo_hadamard(int kind, int *vals);
 void jmo_inverse4x4(int *blk /* 16, in place */);
 void jmo_inverse8x8(int *blk /* 64, in place */);
 long long jmo_luma_residual_coding(const uint16_t *src, const uint16_t *pred, int n, int qp, const int *qparams,

@@ -59,6 +59,8 @@ class Oracle:
         L.jmo_ffs_search.argtypes = [_u32p] + [C.c_int] * 8 + [C.c_int64, C.c_int, _i16p]
         L.jmo_forward4x4.argtypes = [_i32p]
         L.jmo_forward8x8.argtypes = [_i32p]
+        L.jmo_quant_list.argtypes = [C.c_int] * 8 + [_i32p, _u8p, _i32p, _i32p, _i32p, _i32p, _i32p]
+        L.jmo_hadamard.argtypes = [C.c_int, _i32p]
         L.jmo_inverse4x4.argtypes = [_i32p]
         L.jmo_inverse8x8.argtypes = [_i32p]
         L.jmo_luma_residual_coding.restype = C.c_int64
@@ -142,6 +144,15 @@ class Oracle:
         self.L.jmo_forward8x8(b.reshape(-1))
         return b
 
+    def quant_list(self, plan, coef_flat, cost0=0):
+        """plan = jm_b200.api.qlist_plan(...); coef_flat = the function's coefficient array, flattened."""
+        return _qlist_call(lambda *a: self.L.jmo_quant_list(*a), plan, coef_flat, cost0)
+
+    def hadamard(self, kind, vals):
+        b = np.ascontiguousarray(vals, np.int32).reshape(-1).copy()
+        self.L.jmo_hadamard(kind, b)
+        return b
+
     def inverse4x4(self, blk):
         b = np.ascontiguousarray(blk, np.int32).copy()
         self.L.jmo_inverse4x4(b.reshape(-1))
@@ -169,6 +180,20 @@ class Oracle:
 
     def quant(self, variant, coef, qp, qparams, scan, c_cost, is_cavlc, arw=0, cost0=0):
         return _quant_call(self.L.jmo_quant, None, variant, coef, qp, qparams, scan, c_cost, is_cavlc, arw, cost0)
+
+
+def _qlist_call(fn, plan, coef_flat, cost0):
+    """Run a list quantiser (oracle restatement) on the coefficients a JM function would see: gather in scan order,
+    quantise, scatter back.  Returns the same dict as the JM-side call."""
+    coef = np.ascontiguousarray(coef_flat, np.int32).reshape(-1).copy()
+    order = np.asarray(plan["order"])
+    lst = coef[order].copy()
+    levels = np.zeros(17, np.int32); runs = np.zeros(17, np.int32); fadj = np.zeros(len(order), np.int32); cost = np.array([cost0], np.int32)
+    nz = fn(len(order), plan["q_bits"], plan["qp_per"], plan["dequant"], plan["clip"], plan["use_cost"], plan["around"], plan["arw"],
+            np.ascontiguousarray(plan["params"], np.int32).reshape(-1), np.ascontiguousarray(plan["c_cost"], np.uint8), lst, levels, runs, fadj, cost)
+    coef[order] = lst
+    fa = np.zeros(len(coef), np.int32); fa[order] = fadj
+    return dict(nonzero=int(nz), coef=coef, levels=levels, runs=runs, fadjust=fa, coeff_cost=int(cost[0]))
 
 
 def _quant_call(fn, handle, variant, coef, qp, qparams, scan, c_cost, is_cavlc, arw, cost0):
@@ -214,6 +239,8 @@ class JMRef:
         L.jmref_mvbits.argtypes = [C.c_void_p, C.c_int]
         L.jmref_forward4x4.argtypes = [_i32p]
         L.jmref_forward8x8.argtypes = [_i32p]
+        L.jmref_quant_misc.argtypes = [C.c_void_p, C.c_int, _i32p, C.c_int, _i32p, _u8p, _u8p, C.c_int, C.c_int, _i32p, _i32p, _i32p, _i32p]
+        L.jmref_hadamard.argtypes = [C.c_int, _i32p]
         L.jmref_inverse4x4.argtypes = [_i32p]
         L.jmref_inverse8x8.argtypes = [_i32p]
         L.jmref_hadamard_sad4x4.argtypes = [_i16p]
@@ -286,6 +313,20 @@ class JMRef:
     def forward8x8(self, blk):
         b = np.ascontiguousarray(blk, np.int32).copy()
         self.L.jmref_forward8x8(b.reshape(-1))
+        return b
+
+    def quant_misc(self, variant, coef_flat, qp, qparams, scan, c_cost, is_cavlc, arw=0, cost0=0):
+        """The real quant_ac4x4_* (6,7), quant_dc4x4_normal (8), quant_dc2x2_* (9,10), quant_dc4x2_* (11,12)."""
+        coef = np.ascontiguousarray(coef_flat, np.int32).reshape(-1).copy()
+        levels = np.zeros(17, np.int32); runs = np.zeros(17, np.int32); fadj = np.zeros(16, np.int32); cost = np.array([cost0], np.int32)
+        nz = self.L.jmref_quant_misc(self.h_, variant, coef, qp, np.ascontiguousarray(qparams, np.int32).reshape(-1),
+                                     np.ascontiguousarray(scan, np.uint8).reshape(-1), np.ascontiguousarray(c_cost, np.uint8),
+                                     int(is_cavlc), int(arw), levels, runs, fadj, cost)
+        return dict(nonzero=int(nz), coef=coef, levels=levels, runs=runs, fadjust=fadj[:len(coef)], coeff_cost=int(cost[0]))
+
+    def hadamard(self, kind, vals):
+        b = np.ascontiguousarray(vals, np.int32).reshape(-1).copy()
+        self.L.jmref_hadamard(kind, b)
         return b
 
     def inverse4x4(self, blk):

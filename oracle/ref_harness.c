@@ -34,6 +34,7 @@
 #include "transform.h"
 #include "quant4x4.h"
 #include "quant8x8.h"
+#include "quantChroma.h"
 #include "refbuf.h"
 
 typedef struct jmref_ctx
@@ -365,6 +366,75 @@ int jmref_quant(void *h, int variant, int *coef, int qp, const int *qparams, con
     case 1: return quant_4x4_around(c->mb, rows, &q);
     case 2: return quant_8x8_normal(c->mb, rows, &q);
     default: return quant_8x8_around(c->mb, rows, &q);
+  }
+}
+
+/* ---- the DC / AC members of the quantiser family, and the Hadamard transforms ----
+ * variant: 6 quant_ac4x4_normal, 7 quant_ac4x4_around, 8 quant_dc4x4_normal, 9 quant_dc2x2_normal, 10 quant_dc2x2_around,
+ *          11 quant_dc4x2_normal, 12 quant_dc4x2_around
+ * coef: 6,7,8: 4x4 row-major [16]; 9,10: [4]; 11,12: 2 rows x 4 [8] (tblock[j][i], j < 2, i < 4)
+ * qparams: 6,7: 16 triples [j][i]; others: ONE triple.  scan: pairs as JM reads them for that function. */
+int jmref_quant_misc(void *h, int variant, int *coef, int qp, const int *qparams, const uint8_t *scan, const uint8_t *c_cost,
+                     int is_cavlc, int adapt_rnd_weight, int *levels, int *runs, int *fadjust, int *coeff_cost)
+{
+  jmref_ctx *c = (jmref_ctx *)h; g_ctx = c;
+  c->slice->symbol_mode = is_cavlc ? CAVLC : CABAC;
+  c->p_Vid->AdaptRndWeight = adapt_rnd_weight;
+  if (variant <= 7) {
+    int *rows[4], *frow[4], fadj_dummy[16];
+    LevelQuantParams qp_store[16], *qrows[4];
+    for (int i = 0; i < 4; i++) { rows[i] = coef + 4 * i; frow[i] = (fadjust ? fadjust : fadj_dummy) + 4 * i; qrows[i] = qp_store + 4 * i; }
+    for (int i = 0; i < 16; i++) { qp_store[i].OffsetComp = qparams[3 * i]; qp_store[i].ScaleComp = qparams[3 * i + 1]; qp_store[i].InvScaleComp = qparams[3 * i + 2]; }
+    QuantMethods q; memset(&q, 0, sizeof(q));
+    q.qp = qp; q.ACLevel = levels; q.ACRun = runs; q.fadjust = frow; q.q_params = qrows; q.coeff_cost = coeff_cost;
+    q.pos_scan = (const byte (*)[2])scan; q.c_cost = c_cost;
+    return variant == 6 ? quant_ac4x4_normal(c->mb, rows, &q) : quant_ac4x4_around(c->mb, rows, &q);
+  }
+  LevelQuantParams one = { qparams[0], qparams[1], qparams[2] };
+  if (variant == 8) {
+    int *rows[4];
+    for (int i = 0; i < 4; i++) rows[i] = coef + 4 * i;
+    return quant_dc4x4_normal(c->mb, rows, qp, levels, runs, &one, (const byte (*)[2])scan);
+  }
+  if (variant <= 10) {
+    int *rows[1] = { coef };
+    return variant == 9 ? quant_dc2x2_normal(c->mb, rows, qp, levels, runs, &one, NULL, (const byte (*)[2])scan)
+                        : quant_dc2x2_around(c->mb, rows, qp, levels, runs, &one, NULL, (const byte (*)[2])scan);
+  }
+  {
+    int *rows[2] = { coef, coef + 4 };        /* tblock[j][i], j = scan[k][0] < 2, i = scan[k][1] < 4 (block.c:88-94, :1076) */
+    return variant == 11 ? quant_dc4x2_normal(c->mb, rows, qp, levels, runs, &one, NULL, (const byte (*)[2])scan)
+                         : quant_dc4x2_around(c->mb, rows, qp, levels, runs, &one, NULL, (const byte (*)[2])scan);
+  }
+}
+
+/* kind 0..5: hadamard4x4, ihadamard4x4, hadamard4x2, ihadamard4x2, hadamard2x2, ihadamard2x2; flat layouts of jmb_hadamard */
+void jmref_hadamard(int kind, int *v)
+{
+  if (kind <= 1) {
+    int *rows[4], out[16], *orows[4];
+    for (int i = 0; i < 4; i++) { rows[i] = v + 4 * i; orows[i] = out + 4 * i; }
+    if (kind == 0) hadamard4x4(rows, orows); else ihadamard4x4(rows, orows);
+    memcpy(v, out, sizeof(out));
+  } else if (kind == 2) {
+    int *rows[2] = { v, v + 4 }, out[8], *orows[2] = { out, out + 4 };
+    hadamard4x2(rows, orows);
+    memcpy(v, out, sizeof(out));
+  } else if (kind == 3) {
+    int *rows[2] = { v, v + 4 }, out[8], *orows[4] = { out, out + 2, out + 4, out + 6 };
+    ihadamard4x2(rows, orows);
+    memcpy(v, out, sizeof(out));
+  } else if (kind == 4) {
+    int grid[5][5], *rows[5], out[4];
+    memset(grid, 0, sizeof(grid));
+    for (int i = 0; i < 5; i++) rows[i] = grid[i];
+    grid[0][0] = v[0]; grid[0][4] = v[1]; grid[4][0] = v[2]; grid[4][4] = v[3];
+    hadamard2x2(rows, out);
+    memcpy(v, out, sizeof(out));
+  } else {
+    int out[4];
+    ihadamard2x2(v, out);
+    memcpy(v, out, sizeof(out));
   }
 }
 

@@ -570,3 +570,33 @@ def test_luma_residual_coding_with_a_non_standard_scan(ctx, oracle):
         assert np.array_equal(got["levels"][0, mb], lv) and got["cbp"][0, mb] == cbp and got["sse"][0, mb] == sse and np.array_equal(got["recon"][0, mb], rec)
         if cbp == 15:                                       # nothing thresholded away: the raw transform/quant levels are the same
             assert np.array_equal(raw[0][0, mb], lv)
+
+
+@pytest.mark.parametrize("variant", [6, 7, 8, 9, 10, 11, 12])
+def test_quant_dc_ac_family(ctx, oracle, variant):
+    """jmb_quant_list standing in for quant_ac4x4_*, quant_dc4x4_normal, quant_dc2x2_*, quant_dc4x2_* (mapping: api.qlist_plan,
+    pinned against the real functions in test_oracle_vs_ref.py)."""
+    scan420 = np.array([(0, 0), (0, 1), (0, 2), (0, 3)], np.uint8)
+    scan422 = np.array([(0, 0), (0, 1), (1, 0), (0, 2), (0, 3), (1, 1), (1, 2), (1, 3)], np.uint8)
+    ncoef = {6: 16, 7: 16, 8: 16, 9: 4, 10: 4, 11: 8, 12: 8}[variant]
+    scan = {9: scan420, 10: scan420, 11: scan422, 12: scan422}.get(variant, T.SNGL_SCAN)
+    rng = np.random.default_rng(80 + variant)
+    for it in range(60):
+        qp = int(rng.integers(0, 52)); amp = int(rng.choice([6, 80, 600, 4000]))
+        coef = rng.integers(-amp, amp + 1, size=ncoef)
+        qpar = T.q_params(qp, intra=int(rng.integers(0, 2)), n=4)
+        plan = api.qlist_plan(variant, qp, qpar if variant <= 7 else qpar[0, 0], scan, T.COEFF_COST4x4[0], int(rng.integers(0, 2)), 1 + it % 8)
+        got, want = ctx.quant_list(plan, coef, cost0=3), oracle.quant_list(plan, coef, cost0=3)
+        for k in ("nonzero", "coeff_cost"):
+            assert got[k] == want[k], (variant, it, k)
+        for k in ("coef", "levels", "runs", "fadjust"):
+            assert np.array_equal(got[k], want[k]), (variant, it, k)
+
+
+def test_hadamards(ctx, oracle):
+    rng = np.random.default_rng(90)
+    for kind, per in [(api.HAD_4X4, 16), (api.IHAD_4X4, 16), (api.HAD_4X2, 8), (api.IHAD_4X2, 8), (api.HAD_2X2, 4), (api.IHAD_2X2, 4)]:
+        v = rng.integers(-30000, 30001, size=(100, per))
+        got = ctx.hadamard(kind, v, per)
+        for i in range(len(v)):
+            assert np.array_equal(got[i], oracle.hadamard(kind, v[i])), (kind, i)

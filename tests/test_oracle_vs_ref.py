@@ -162,3 +162,43 @@ def test_quant(oracle, have_ref, variant):
         assert np.array_equal(a["levels"], b["levels"]) and np.array_equal(a["runs"], b["runs"])
         if variant % 2 == 1:
             assert np.array_equal(a["fadjust"], b["fadjust"])
+
+
+SCAN_YUV420 = np.array([(0, 0), (0, 1), (0, 2), (0, 3)], np.uint8)                                  # block.c:79
+SCAN_YUV422 = np.array([(0, 0), (0, 1), (1, 0), (0, 2), (0, 3), (1, 1), (1, 2), (1, 3)], np.uint8)  # block.c:88
+
+
+@pytest.mark.parametrize("variant", [6, 7, 8, 9, 10, 11, 12])
+def test_quant_dc_ac_family(oracle, have_ref, variant):
+    """quant_ac4x4_normal/_around, quant_dc4x4_normal, quant_dc2x2_*, quant_dc4x2_* against the list quantiser fed through
+    the mapping of jm_b200.api.qlist_plan (the same mapping the shim applies)."""
+    from jm_b200 import api
+    ref = po.JMRef(32, 32, search_range=4)
+    rng = np.random.default_rng(60 + variant)
+    ncoef = {6: 16, 7: 16, 8: 16, 9: 4, 10: 4, 11: 8, 12: 8}[variant]
+    scan = {9: SCAN_YUV420, 10: SCAN_YUV420, 11: SCAN_YUV422, 12: SCAN_YUV422}.get(variant, T.SNGL_SCAN)
+    for it in range(300):
+        qp = int(rng.integers(0, 52)); amp = int(rng.choice([6, 80, 600, 4000]))
+        coef = rng.integers(-amp, amp + 1, size=ncoef)
+        if it % 5 == 0:
+            coef[rng.integers(0, ncoef)] = 0
+        qpar = T.q_params(qp, intra=int(rng.integers(0, 2)), n=4)
+        qp_arg = qpar if variant <= 7 else qpar[0, 0]
+        cav = int(rng.integers(0, 2)); arw = 1 + it % 8
+        want = ref.quant_misc(variant, coef, qp, qp_arg, scan, T.COEFF_COST4x4[0], cav, arw=arw, cost0=7)
+        got = oracle.quant_list(api.qlist_plan(variant, qp, qp_arg, scan, T.COEFF_COST4x4[0], cav, arw), coef, cost0=7)
+        assert got["nonzero"] == want["nonzero"] and np.array_equal(got["coef"], want["coef"]), (variant, it)
+        assert np.array_equal(got["levels"], want["levels"]) and np.array_equal(got["runs"], want["runs"])
+        if variant <= 7:
+            assert got["coeff_cost"] == want["coeff_cost"]
+        if variant == 7:
+            assert np.array_equal(got["fadjust"], want["fadjust"])
+
+
+def test_hadamards(oracle, have_ref):
+    ref = po.JMRef(32, 32, search_range=4)
+    rng = np.random.default_rng(70)
+    for kind, per in [(0, 16), (1, 16), (2, 8), (3, 8), (4, 4), (5, 4)]:
+        for _ in range(200):
+            v = rng.integers(-30000, 30001, size=per)
+            assert np.array_equal(oracle.hadamard(kind, v), ref.hadamard(kind, v)), kind
