@@ -91,8 +91,7 @@ __device__ __forceinline__ int jmb_clip(int lo, int hi, int v) { return min(max(
 
 // mvbits[] of lencod/src/mv_search.c:366-374: 1 for 0, else 2*floor(log2|v|)+3
 __device__ __forceinline__ int jmb_mvbits(int v) {
-  int a = abs(v);
-  return a ? (2 * (31 - __clz(a)) + 3) : 1;
+  return 65 - 2 * __clz(abs(v));      // clz(0) = 32 -> 1; |v| in [2^k, 2^(k+1)) -> 2k + 3
 }
 
 // index of displacement (dx,dy) in JM's square spiral (lencod/src/mv_search.c:406-442)

@@ -372,18 +372,19 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
           const ReqS &q = G.rq[p];
           const int4 in = G.inner[p];
           const unsigned lam = (unsigned)q.lam;
+          // (an inactive request has an empty `inner`, so its terms are all zero)
           for (int ic = sub; ic < cw; ic += lanes_per_p) {
-            unsigned a = 0;
-            if (q.active && cx0 + ic >= in.x && cx0 + ic <= in.y) a = min(65535u, (lam * (unsigned)(jmb_mvbits(4 * (cx0 + ic) - q.px) - 1)) >> 5);
+            const int Dx = cx0 + ic;
+            unsigned a = min(65535u, (lam * (unsigned)(jmb_mvbits(4 * Dx - q.px) - 1)) >> 5);
+            if (Dx < in.x || Dx > in.y) a = 0;
             adjx[ic * ADJ_PITCH + p] = a;
           }
+          // the row term is monotone in |4 Dy - py|: of the (up to) 4 rows of an item the one nearest py / 4 has the minimum
           for (int rg = sub; rg < ((ch + 3) >> 2); rg += lanes_per_p) {
-            unsigned a = 0xffffffffu;
-            for (int r = 4 * rg; r < min(4 * rg + 4, ch); r++) {
-              unsigned ar = 0;
-              if (q.active && cy0 + r >= in.z && cy0 + r <= in.w) ar = min(65535u, (lam * (unsigned)(jmb_mvbits(4 * (cy0 + r) - q.py) - 1)) >> 5);
-              a = min(a, ar);
-            }
+            const int D0 = cy0 + 4 * rg, D1 = cy0 + min(4 * rg + 3, ch - 1), Dn = q.py >> 2;
+            const int am = min(abs(4 * jmb_clip(D0, D1, Dn) - q.py), abs(4 * jmb_clip(D0, D1, Dn + 1) - q.py));
+            unsigned a = min(65535u, (lam * (unsigned)(jmb_mvbits(am) - 1)) >> 5);
+            if (D0 < in.z || D1 > in.w) a = 0;
             adjy4[rg * ADJ_PITCH + p] = a;
           }
           if (s1) {      // stage 1's exact terms; S1_BAD marks a column / row that is not a plain candidate of this partition
@@ -410,8 +411,8 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
         unsigned long long k = ~0ull;
         if (p < NPART && G.rq[p].active) {
           const ReqS &q = G.rq[p];
-          unsigned bcost = S1_NONE; int bidx = 0;        // thread j looks at displacement row j of every item
-          for (int rgi = 0; rgi < nrgs; rgi++) {
+          unsigned bcost = S1_NONE; int bc = 0, bDy = 0, bidx = -1;        // thread j looks at displacement row j of every item;
+          for (int rgi = 0; rgi < nrgs; rgi++) {                            // the spiral index is only worked out on a tie
             const unsigned ycost = s1y[(4 * rgi + j) * ADJ_PITCH + p];
             if (ycost == S1_BAD) continue;
             const int Dy = cy0 + (rg0 + rgi) * 4 + j;
@@ -419,10 +420,16 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
             for (int c = 0; c < ncol; c++) {
               const unsigned cost = ((unsigned)sp[c * 4 * S1_PITCH] << 5) + ycost + s1x[c * ADJ_PITCH + p];
               if (cost > bcost) continue;
-              const int idx = jmb_spiral_index(cx0 + col0 + c - q.cx, Dy - q.cy);
-              if (cost < bcost || idx < bidx) { bcost = cost; bidx = idx; }
+              if (cost == bcost) {
+                if (bidx < 0) bidx = jmb_spiral_index(cx0 + col0 + bc - q.cx, bDy - q.cy);
+                const int idx = jmb_spiral_index(cx0 + col0 + c - q.cx, Dy - q.cy);
+                if (idx >= bidx) continue;
+                bidx = idx;
+              } else bidx = -1;
+              bcost = cost; bc = c; bDy = Dy;
             }
           }
+          if (bcost != S1_NONE && bidx < 0) bidx = jmb_spiral_index(cx0 + col0 + bc - q.cx, bDy - q.cy);
           if (bcost != S1_NONE) k = ((unsigned long long)bcost << IDX_BITS) | (unsigned)bidx;
 
         }
@@ -436,19 +443,15 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
       // the sweep: warps draw batches of 32 items from a shared counter (a batch that meets the gate runs much
       // longer than one that does not, so a static split would leave warps waiting at the final barrier)
       const int nitems = nrg * cw, lane = tid & 31;
-      bool head = true, release = tid < 32;   // the most central batch goes first, alone (warp 0): every other batch then starts from its bounds
+      const unsigned cw_rcp = cw > 1 ? 0xffffffffu / (unsigned)cw + 1 : 0u;      // it / cw == umulhi(it, cw_rcp) for it, cw < 2^16 (cw > 1)
       for (;;) {
         int base = 0;
-        if (head) {
-          head = false;
-          if (tid >= 32) { __syncthreads(); continue; }
-          if (lane == 0) base = atomicAdd(&sbox[11], 32);
-        } else if (lane == 0) base = atomicAdd(&sbox[11], 32);
+        if (lane == 0) base = atomicAdd(&sbox[11], 32);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= nitems) break;
         const int it = base + lane, warp = tid >> 5;
         if (it < nitems) {
-        const int k = it / cw, ic = it - k * cw;
+        const int k = cw > 1 ? (int)__umulhi((unsigned)it, cw_rcp) : it, ic = it - k * cw;
         const int rg = (k & 1) ? mid - ((k + 1) >> 1) : mid + (k >> 1);   // centre rows first: tight bounds early
         const int row0 = rg * 4, xo = ic + xoff0;
         unsigned acc[4][16];
@@ -519,7 +522,6 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
         __syncwarp();
         if (lane == 0) wq_n[warp] = 0;
         __syncwarp();
-        if (release) { release = false; __syncthreads(); }
       }
     }
   }
