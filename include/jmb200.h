@@ -185,6 +185,28 @@ int jmb_ffs_surfaces(jmb_ctx *ctx, int ref, int mb_x, int mb_y, int center_x, in
 int jmb_dist(jmb_ctx *ctx, int ref, int metric, int blocktype, int pos_x, int pos_y,
              const int16_t *cand_xy, int n, int test8x8, int32_t *out, int loc);
 
+/* The other nine members of JM's distortion table (p_Vid->computeUniPred[3..5], computeBiPred1[], computeBiPred2[],
+ * lencod/src/mv_search.c:486-506): the block is compared with a PREDICTION formed from one or two references.
+ *   JMB_PRED_PLAIN            ref1                                                      computeSAD/SSE/SATD
+ *   JMB_PRED_WEIGHTED         clip(((w1*ref1 + round) >> denom) + offset)               computeSADWP :434, SATDWP :833, SSEWP :1261
+ *   JMB_PRED_AVERAGE          (ref1 + ref2 + 1) >> 1                                    computeBiPredSAD1 :525, SATD1 :943, SSE1 :1353
+ *   JMB_PRED_WEIGHTED_AVERAGE clip(((w1*ref1 + w2*ref2 + 2*round) >> (denom+1)) + offset)   computeBiPredSAD2 :624, SATD2 :1038, SSE2 :1438
+ * weight1/offset = mv_block->weight_luma/offset_luma (WEIGHTED) or weight1/weight2/offsetBi (WEIGHTED_AVERAGE,
+ * PrepareBiPredMEParams mv_search.c:205); log_weight_denom / wp_round = currSlice->luma_log_weight_denom / wp_luma_round.
+ * The second reference is read at ONE candidate (cand2, absolute quarter-pel) for the whole call, as JM's bi-predictive
+ * searches do (me_fullsearch.c:112-178, :299-390: one list moves, the other stands still); each reference gets its own
+ * UMVLine4X clamp (partition origin for SAD/SSE, every sub-block origin for SATD). */
+enum { JMB_PRED_PLAIN = 0, JMB_PRED_WEIGHTED = 1, JMB_PRED_AVERAGE = 2, JMB_PRED_WEIGHTED_AVERAGE = 3 };
+typedef struct jmb_dist_pred {
+  int32_t form;                       /* JMB_PRED_* */
+  int32_t ref2;                       /* index in the picture's reference list (AVERAGE forms) */
+  int32_t cand2_x, cand2_y;           /* absolute quarter-pel position read in ref2 */
+  int32_t weight1, weight2, offset;
+  int32_t log_weight_denom, wp_round;
+} jmb_dist_pred;
+int jmb_dist_ex(jmb_ctx *ctx, int ref, const jmb_dist_pred *pred, int metric, int blocktype, int pos_x, int pos_y,
+                const int16_t *cand_xy, int n, int test8x8, int32_t *out, int loc);
+
 /* ---- transform + quantisation ---------------------------------------------------------------- */
 /* forward4x4 / forward8x8 (lcommon/src/transform.c:20,353) on nblk blocks of n*n int32, in place */
 int jmb_forward_transform(jmb_ctx *ctx, int32_t *blocks, int nblk, int n, int loc);

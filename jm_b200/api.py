@@ -29,6 +29,8 @@ QUANT_DESC = np.dtype([("n", "<i4"), ("qp", "<i4"), ("is_cavlc", "<i4"), ("aroun
 QLIST_DESC = np.dtype([("m", "<i4"), ("q_bits", "<i4"), ("qp_per", "<i4"), ("dequant", "<i4"), ("clip", "<i4"), ("use_cost", "<i4"),
                        ("around", "<i4"), ("adapt_rnd_weight", "<i4"), ("params", "<i4", (16, 3)), ("c_cost", "u1", (16,))])
 DQ_LEVEL, DQ_SHIFT, DQ_SHIFT_RND4 = 0, 1, 2
+PRED_PLAIN, PRED_WEIGHTED, PRED_AVERAGE, PRED_WEIGHTED_AVERAGE = range(4)
+DIST_PRED = np.dtype([(k, np.int32) for k in ("form", "ref2", "cand2_x", "cand2_y", "weight1", "weight2", "offset", "log_weight_denom", "wp_round")])
 HAD_4X4, IHAD_4X4, HAD_4X2, IHAD_4X2, HAD_2X2, IHAD_2X2 = range(6)
 assert QLIST_DESC.itemsize == 240
 assert ME_REQ.itemsize == 40 and ME_RES.itemsize == 24 and MB_PRED.itemsize == 72 and QUANT_DESC.itemsize == 980
@@ -67,6 +69,7 @@ def load_library():
     L.jmb_me_search_frame.argtypes = [vp, vp, i, vp, i]
     L.jmb_ffs_surfaces.argtypes = [vp, i, i, i, i, i, vp, i]
     L.jmb_dist.argtypes = [vp, i, i, i, i, i, vp, i, i, vp, i]
+    L.jmb_dist_ex.argtypes = [vp, i, vp, i, i, i, i, vp, i, i, vp, i]
     L.jmb_forward_transform.argtypes = [vp, vp, i, i, i]
     L.jmb_quant_blocks.argtypes = [vp, vp, i, vp, i, vp, vp, vp, vp, vp, i]
     L.jmb_mc_tq.argtypes = [vp, vp, i, vp, vp, vp, vp, i]
@@ -251,6 +254,17 @@ class Context:
         cands = np.ascontiguousarray(cands, np.int16).reshape(-1, 2)
         out = np.zeros(len(cands), np.int32)
         self._ck(self.L.jmb_dist(self.h, ref, metric, blocktype, pos[0], pos[1], _ptr(cands), len(cands), test8x8, _ptr(out), HOST))
+        return out
+
+    def dist_ex(self, ref, ref2, metric, form, blocktype, pos, cands, cand2, wp=(32, 32, 0, 5, 16), test8x8=0):
+        """jmb_dist_ex: form PRED_PLAIN / PRED_WEIGHTED / PRED_AVERAGE / PRED_WEIGHTED_AVERAGE;
+        wp = (weight1, weight2, offset, luma_log_weight_denom, wp_luma_round)."""
+        cands = np.ascontiguousarray(cands, np.int16).reshape(-1, 2)
+        out = np.zeros(len(cands), np.int32)
+        d = np.zeros(1, DIST_PRED)
+        d["form"] = form; d["ref2"] = ref2; d["cand2_x"], d["cand2_y"] = cand2
+        d["weight1"], d["weight2"], d["offset"], d["log_weight_denom"], d["wp_round"] = wp
+        self._ck(self.L.jmb_dist_ex(self.h, ref, _ptr(d), metric, blocktype, pos[0], pos[1], _ptr(cands), len(cands), test8x8, _ptr(out), HOST))
         return out
 
     def forward_transform(self, blocks, n):

@@ -75,10 +75,11 @@ int jmb_check_device_errors(jmb_ctx *ctx) {
   if (ctx->h_err[0]) {
     const int code = ctx->h_err[0], idx = ctx->h_err[1];
     JMB_CUDA(ctx, cudaMemsetAsync(ctx->d_err, 0, 2 * sizeof(int), ctx->stream));
-    return jmb_fail(ctx, JMB_ERR_ARG, "motion-search request %d rejected on the device (code 0x%x:%s%s%s%s%s%s%s%s); its result was not written", idx, code,
+    return jmb_fail(ctx, JMB_ERR_ARG, "motion-search request %d rejected on the device (code 0x%x:%s%s%s%s%s%s%s%s%s); its result was not written", idx, code,
                     code & JMB_REQERR_BLOCKTYPE ? " blocktype" : "", code & JMB_REQERR_REF ? " ref" : "", code & JMB_REQERR_POS ? " position/alignment" : "",
                     code & JMB_REQERR_CENTER ? " centre-not-integer-pel" : "", code & JMB_REQERR_MODE ? " mode" : "", code & JMB_REQERR_LAMBDA ? " lambda" : "",
-                    code & JMB_REQERR_MINCOST ? " min_mcost" : "", code & JMB_REQERR_LAYOUT ? " frame-layout" : "");
+                    code & JMB_REQERR_MINCOST ? " min_mcost" : "", code & JMB_REQERR_LAYOUT ? " frame-layout" : "",
+                    code & JMB_REQERR_FPEL_METRIC ? " full-search-with-MEDistortionFPel-other-than-SAD" : "");
   }
   return JMB_OK;
 }
@@ -198,8 +199,8 @@ int jmb_me_configure(jmb_ctx *ctx, const jmb_me_config *cfg) {
   for (int i = 0; i < 3; i++)
     if (cfg->metric[i] < 0 || cfg->metric[i] > 2)
       return jmb_fail(ctx, JMB_ERR_ARG, "jmb_me_configure: metric[%d]=%d", i, cfg->metric[i]);
-  if (cfg->metric[0] != JMB_SAD)
-    return jmb_fail(ctx, JMB_ERR_UNSUPPORTED, "jmb_me_configure: integer search supports MEDistortionFPel=SAD only");
+  // metric[0] != SAD is accepted here (sub-pel-only requests and jmb_dist do not care); a FULL-search request under it
+  // is rejected on the device (JMB_REQERR_FPEL_METRIC): the search kernel is a SAD kernel
   if (cfg->search_pos2 < 1 || cfg->search_pos2 > 9 || cfg->search_pos4 < 1 || cfg->search_pos4 > 9)
     return jmb_fail(ctx, JMB_ERR_ARG, "jmb_me_configure: search_pos2/4 must be 1..9");
   ctx->me = *cfg;

@@ -105,7 +105,7 @@ __device__ __forceinline__ int jmb_spiral_index(int dx, int dy) {
 
 // request validation shared by the search and refinement kernels; 0 = fine
 enum { JMB_REQERR_BLOCKTYPE = 1, JMB_REQERR_REF = 2, JMB_REQERR_POS = 4, JMB_REQERR_CENTER = 8, JMB_REQERR_MODE = 16,
-       JMB_REQERR_LAMBDA = 32, JMB_REQERR_MINCOST = 64, JMB_REQERR_LAYOUT = 128 };
+       JMB_REQERR_LAMBDA = 32, JMB_REQERR_MINCOST = 64, JMB_REQERR_LAYOUT = 128, JMB_REQERR_FPEL_METRIC = 256 };
 __device__ __forceinline__ int jmb_req_check(const jmb_me_req &r, int w, int h, int nref) {
   if (r.blocktype < 1 || r.blocktype > 7) return JMB_REQERR_BLOCKTYPE;
   const int bsx = (r.blocktype <= 2) ? 16 : (r.blocktype <= 5 ? 8 : 4);

@@ -305,18 +305,82 @@ k_subpel_refine(const jmb_me_req *__restrict__ reqs, jmb_me_res *__restrict__ re
   }
 }
 
-__global__ void k_dist(const uint8_t *__restrict__ cur, int cur_pitch, RefView rv, int blocktype, int pos_x, int pos_y,
+// prediction sample of jmb_dist_ex: one or two references, optionally weighted (me_distortion.c:434-1520)
+struct DistPred { int form, c2x, c2y, w1, w2, off, shift, round; };
+__device__ __forceinline__ unsigned pred_word(unsigned a, unsigned b, const DistPred &P) {
+  unsigned o = 0;
+#pragma unroll
+  for (int x = 0; x < 4; x++) {
+    const int ra = (int)((a >> (8 * x)) & 255), rb = (int)((b >> (8 * x)) & 255);
+    int v;
+    if (P.form == JMB_PRED_WEIGHTED) v = jmb_clip(0, 255, ((P.w1 * ra + P.round) >> P.shift) + P.off);
+    else if (P.form == JMB_PRED_AVERAGE) v = (ra + rb + 1) >> 1;
+    else v = jmb_clip(0, 255, ((P.w1 * ra + P.w2 * rb + P.round) >> P.shift) + P.off);
+    o |= (unsigned)v << (8 * x);
+  }
+  return o;
+}
+
+// one thread per (candidate, sub-block); the sub-block's prediction is formed in registers and handed to the same
+// SAD / SSE / Hadamard code the single-reference path uses
+__global__ void k_dist(const uint8_t *__restrict__ cur, int cur_pitch, RefView rv, RefView rv2, DistPred P, int blocktype, int pos_x, int pos_y,
                        const int16_t *__restrict__ cand, int ncand, int metric, int test8x8, int *__restrict__ out) {
   const int bsx = c_bsx[blocktype], bsy = c_bsy[blocktype];
   const int n = (metric == JMB_SATD && test8x8) ? 8 : 4;
   const int nsx = bsx / n, nsub = nsx * (bsy / n);
   const int it = blockIdx.x * blockDim.x + threadIdx.x;
   if (it >= ncand * nsub) return;
-  const int c = it / nsub, sb = it - c * nsub;
+  const int c = it / nsub, sb = it - c * nsub, sbx = sb % nsx, sby = sb / nsx;
   SrcBlk src;
-  load_src(src, cur, cur_pitch, pos_x + (sb % nsx) * n, pos_y + (sb / nsx) * n, n);
-  const int d = (n == 4) ? subblock_dist(rv, src, cand[2 * c], cand[2 * c + 1], sb % nsx, sb / nsx, 4, metric)
-                         : subblock_dist(rv, src, cand[2 * c], cand[2 * c + 1], sb % nsx, sb / nsx, 8, metric);
+  load_src(src, cur, cur_pitch, pos_x + sbx * n, pos_y + sby * n, n);
+  const int c1x = cand[2 * c], c1y = cand[2 * c + 1];
+  const bool two = P.form >= JMB_PRED_AVERAGE;
+  const uint8_t *r1, *r2 = nullptr;
+  if (metric == JMB_SATD) {      // every sub-block origin is clamped, in each reference
+    r1 = umv(rv, c1y + ((sby * n) << 2), c1x + ((sbx * n) << 2));
+    if (two) r2 = umv(rv2, P.c2y + ((sby * n) << 2), P.c2x + ((sbx * n) << 2));
+  } else {                       // the partition origin is clamped
+    r1 = umv(rv, c1y, c1x) + (size_t)(sby * n) * rv.pitch + sbx * n;
+    if (two) r2 = umv(rv2, P.c2y, P.c2x) + (size_t)(sby * n) * rv2.pitch + sbx * n;
+  }
+  int d;
+  if (n == 4) {
+    unsigned rw[4];
+#pragma unroll
+    for (int y = 0; y < 4; y++) {
+      rw[y] = ld4(r1 + (size_t)y * rv.pitch);
+      if (P.form != JMB_PRED_PLAIN) rw[y] = pred_word(rw[y], two ? ld4(r2 + (size_t)y * rv2.pitch) : 0u, P);
+    }
+    d = dist4(src, rw, metric);
+  } else {
+    int a[64];
+#pragma unroll
+    for (int y = 0; y < 8; y++) {
+      unsigned lo, hi, lo2 = 0, hi2 = 0;
+      ld8(r1 + (size_t)y * rv.pitch, lo, hi);
+      if (two) ld8(r2 + (size_t)y * rv2.pitch, lo2, hi2);
+      if (P.form != JMB_PRED_PLAIN) { lo = pred_word(lo, lo2, P); hi = pred_word(hi, hi2, P); }
+      unsigned s0 = src.w[2 * y], s1 = src.w[2 * y + 1];
+      if (P.form == JMB_PRED_WEIGHTED_AVERAGE && y) {
+        // computeBiPredSATD2's 8x8 branch never advances the source pointer past the eighth sample of a row
+        // (me_distortion.c:1166), so row y reads JM's block-compact source copy y samples early -- reproduced
+        s0 = s1 = 0;
+        const int L0 = (sby * 8 + y) * bsx + sbx * 8 - y;
+#pragma unroll
+        for (int x = 0; x < 8; x++) {
+          const int L = L0 + x, row = L / bsx, col = L - row * bsx;
+          const unsigned v = cur[(size_t)(pos_y + row) * cur_pitch + pos_x + col];
+          if (x < 4) s0 |= v << (8 * x); else s1 |= v << (8 * (x - 4));
+        }
+      }
+#pragma unroll
+      for (int x = 0; x < 4; x++) {
+        a[y * 8 + x] = (int)((s0 >> (8 * x)) & 255) - (int)((lo >> (8 * x)) & 255);
+        a[y * 8 + 4 + x] = (int)((s1 >> (8 * x)) & 255) - (int)((hi >> (8 * x)) & 255);
+      }
+    }
+    d = hadamard8(a);
+  }
   atomicAdd(&out[c], d);
 }
 }  // namespace
@@ -331,8 +395,8 @@ int jmb_launch_refine(jmb_ctx *ctx, const jmb_me_req *d_reqs, jmb_me_res *d_res,
   return JMB_OK;
 }
 
-extern "C" int jmb_dist(jmb_ctx *ctx, int ref, int metric, int blocktype, int pos_x, int pos_y,
-                        const int16_t *cand_xy, int n, int test8x8, int32_t *out, int loc) {
+extern "C" int jmb_dist_ex(jmb_ctx *ctx, int ref, const jmb_dist_pred *pred, int metric, int blocktype, int pos_x, int pos_y,
+                           const int16_t *cand_xy, int n, int test8x8, int32_t *out, int loc) {
   static const int bsx[8] = {0, 16, 16, 8, 8, 8, 4, 4}, bsy[8] = {0, 16, 8, 16, 8, 4, 8, 4};
   if (n <= 0) return JMB_OK;
   if (!ctx->cur || ref < 0 || ref >= ctx->nref) return jmb_fail(ctx, JMB_ERR_STATE, "jmb_dist: no picture / bad ref %d", ref);
@@ -340,8 +404,24 @@ extern "C" int jmb_dist(jmb_ctx *ctx, int ref, int metric, int blocktype, int po
   if (pos_x < 0 || pos_y < 0 || (pos_x & 3) || (pos_y & 3) || pos_x + bsx[blocktype] > ctx->cur_w || pos_y + bsy[blocktype] > ctx->cur_h)
     return jmb_fail(ctx, JMB_ERR_ARG, "jmb_dist: block (%d,%d) type %d", pos_x, pos_y, blocktype);
   if (test8x8 && metric == JMB_SATD && blocktype > 4) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_dist: test8x8 needs blocktype <= 4");
+  DistPred P{JMB_PRED_PLAIN, 0, 0, 0, 0, 0, 0, 0};
+  int ref2 = ref;
+  if (pred) {
+    if (pred->form < JMB_PRED_PLAIN || pred->form > JMB_PRED_WEIGHTED_AVERAGE) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_dist_ex: prediction form %d", pred->form);
+    const bool two = pred->form >= JMB_PRED_AVERAGE, wp = pred->form == JMB_PRED_WEIGHTED || pred->form == JMB_PRED_WEIGHTED_AVERAGE;
+    if (two && (pred->ref2 < 0 || pred->ref2 >= ctx->nref)) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_dist_ex: bad ref2 %d", pred->ref2);
+    if (two && (pred->cand2_x < -32768 || pred->cand2_x > 32767 || pred->cand2_y < -32768 || pred->cand2_y > 32767))
+      return jmb_fail(ctx, JMB_ERR_ARG, "jmb_dist_ex: cand2 (%d,%d)", pred->cand2_x, pred->cand2_y);
+    if (wp && (pred->log_weight_denom < 0 || pred->log_weight_denom > 7 || pred->weight1 < -32768 || pred->weight1 > 32767 ||
+               pred->weight2 < -32768 || pred->weight2 > 32767 || pred->offset < -32768 || pred->offset > 32767 || pred->wp_round < 0 || pred->wp_round > 64))
+      return jmb_fail(ctx, JMB_ERR_ARG, "jmb_dist_ex: weights (%d,%d) offset %d denom %d round %d", pred->weight1, pred->weight2, pred->offset,
+                      pred->log_weight_denom, pred->wp_round);
+    P.form = pred->form; P.c2x = pred->cand2_x; P.c2y = pred->cand2_y; P.w1 = pred->weight1; P.w2 = pred->weight2; P.off = pred->offset;
+    P.shift = pred->log_weight_denom + (two ? 1 : 0); P.round = pred->wp_round * (two ? 2 : 1);
+    if (two) ref2 = pred->ref2;
+  }
   JMB_CUDA(ctx, cudaSetDevice(ctx->device));
-  const jmb_ref &r = ctx->refs[ctx->ref_list[ref]];
+  const jmb_ref &r = ctx->refs[ctx->ref_list[ref]], &rb = ctx->refs[ctx->ref_list[ref2]];
   const int16_t *d_c = cand_xy; int *d_o = out;
   if (loc == JMB_HOST) {
     int rc = jmb_reserve_dev(ctx, &ctx->d_stage, &ctx->d_stage_cap, (size_t)n * 4); if (rc) return rc;
@@ -352,9 +432,9 @@ extern "C" int jmb_dist(jmb_ctx *ctx, int ref, int metric, int blocktype, int po
   JMB_CUDA(ctx, cudaMemsetAsync(d_o, 0, (size_t)n * 4, ctx->stream));
   const int nn = (metric == JMB_SATD && test8x8) ? 8 : 4;
   const int items = n * (bsx[blocktype] / nn) * (bsy[blocktype] / nn);
-  RefView rv{r.planes, r.plane_bytes, r.pitch, r.w, r.h};
+  RefView rv{r.planes, r.plane_bytes, r.pitch, r.w, r.h}, rv2{rb.planes, rb.plane_bytes, rb.pitch, rb.w, rb.h};
   jmb_time_begin(ctx, JMB_K_DIST);
-  k_dist<<<(items + 127) / 128, 128, 0, ctx->stream>>>(ctx->cur, ctx->cur_pitch, rv, blocktype, pos_x, pos_y, d_c, n, metric, test8x8, d_o);
+  k_dist<<<(items + 127) / 128, 128, 0, ctx->stream>>>(ctx->cur, ctx->cur_pitch, rv, rv2, P, blocktype, pos_x, pos_y, d_c, n, metric, test8x8, d_o);
   jmb_time_end(ctx, JMB_K_DIST);
   JMB_LAUNCH_CHECK(ctx);
   if (loc == JMB_HOST) {
@@ -362,4 +442,9 @@ extern "C" int jmb_dist(jmb_ctx *ctx, int ref, int metric, int blocktype, int po
     JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return JMB_OK;
+}
+
+extern "C" int jmb_dist(jmb_ctx *ctx, int ref, int metric, int blocktype, int pos_x, int pos_y,
+                        const int16_t *cand_xy, int n, int test8x8, int32_t *out, int loc) {
+  return jmb_dist_ex(ctx, ref, nullptr, metric, blocktype, pos_x, pos_y, cand_xy, n, test8x8, out, loc);
 }

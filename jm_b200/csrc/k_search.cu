@@ -255,7 +255,7 @@ __device__ __forceinline__ void sad_item(const uint8_t *win, const unsigned *ssr
 #endif
 __global__ void __launch_bounds__(NT, JMB_IS_MINB)
 k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups, jmb_me_res *__restrict__ res,
-             const __grid_constant__ TMaps tm, int w, int h, int R, int max_mvd_m1, int nref, int *__restrict__ err) {
+             const __grid_constant__ TMaps tm, int w, int h, int R, int max_mvd_m1, int nref, int fpel_metric, int *__restrict__ err) {
   __shared__ Grp G;
   __shared__ __align__(128) uint8_t win[WIN_ROWS * WIN_PITCH];   // TMA destination: the search window tile
   __shared__ __align__(128) unsigned ssrc[16 * 4];               // TMA destination: the 16x16 source macroblock
@@ -291,6 +291,7 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
         if (r.blocktype != pg.type || (r.pos_x & 15) != pg.bx * 4 || (r.pos_y & 15) != pg.by * 4 || ((r.pos_x ^ r0.pos_x) & ~15) ||
             ((r.pos_y ^ r0.pos_y) & ~15) || r.ref != r0.ref) bad = JMB_REQERR_LAYOUT;
       }
+      if (!bad && !(r.flags & JMB_REQ_SKIP_INT) && r.mode == JMB_SEARCH_FULL && fpel_metric != JMB_SAD) bad = JMB_REQERR_FPEL_METRIC;   // (the fast full search is a SAD search whatever the metric, me_fullfast.c:492-556)
       jmb_req_report(err, bad, ri);
       if (!bad && !(r.flags & JMB_REQ_SKIP_INT)) {
         q.active = 1;
@@ -692,7 +693,7 @@ static int me_search_impl(jmb_ctx *ctx, const jmb_me_req *reqs, int n, jmb_me_re
   tm.cur = ctx->tmap_cur;
   for (int i = 0; i < ctx->nref; i++) tm.ref[i] = ctx->refs[ctx->ref_list[i]].tmap_int;
   k_int_search<<<n_groups, NT, INT_SEARCH_DYN_SMEM, ctx->stream>>>(d_reqs, d_groups, d_res, tm, ctx->cur_w, ctx->cur_h, ctx->me.search_range,
-                                                                  ctx->me.max_mvd - 1, ctx->nref, ctx->d_err);
+                                                                  ctx->me.max_mvd - 1, ctx->nref, ctx->me.metric[0], ctx->d_err);
   jmb_time_end(ctx, JMB_K_INT_SEARCH);
   JMB_LAUNCH_CHECK(ctx);
   if (any_subpel) { rc = jmb_launch_refine(ctx, d_reqs, d_res, n, d_tab); if (rc) return rc; }

@@ -17,7 +17,10 @@
  *       -Wl,--wrap=quant_ac4x4_normal -Wl,--wrap=quant_ac4x4_around -Wl,--wrap=quant_dc4x4_normal \
  *       -Wl,--wrap=quant_dc2x2_normal -Wl,--wrap=quant_dc2x2_around -Wl,--wrap=quant_dc4x2_normal -Wl,--wrap=quant_dc4x2_around \
  *       -Wl,--wrap=hadamard4x4 -Wl,--wrap=ihadamard4x4 -Wl,--wrap=hadamard4x2 -Wl,--wrap=ihadamard4x2 \
- *       -Wl,--wrap=hadamard2x2 -Wl,--wrap=ihadamard2x2
+ *       -Wl,--wrap=hadamard2x2 -Wl,--wrap=ihadamard2x2 \
+ *       -Wl,--wrap=computeSADWP -Wl,--wrap=computeSSEWP -Wl,--wrap=computeSATDWP -Wl,--wrap=computeBiPredSAD1 -Wl,--wrap=computeBiPredSAD2 \
+ *       -Wl,--wrap=computeBiPredSSE1 -Wl,--wrap=computeBiPredSSE2 -Wl,--wrap=computeBiPredSATD1 -Wl,--wrap=computeBiPredSATD2 \
+ *       -Wl,--wrap=full_search_bipred_motion_estimation -Wl,--wrap=sub_pel_bipred_motion_estimation
  *
  * No JM source file is edited: every symbol above is defined in one translation unit and referenced
  * from another, so the linker redirects the reference to __wrap_<sym>.
@@ -72,6 +75,17 @@ int     __real_quant_8x8_around(Macroblock *, int **, struct quant_methods *);
 int     __real_quant_8x8cavlc_normal(Macroblock *, int **, struct quant_methods *, int ***);
 int     __real_quant_8x8cavlc_around(Macroblock *, int **, struct quant_methods *, int ***);
 void    __real_luma_residual_coding(Macroblock *currMB);
+distblk __real_computeSADWP(StorablePicture *, MEBlock *, distblk, MotionVector *);
+distblk __real_computeSSEWP(StorablePicture *, MEBlock *, distblk, MotionVector *);
+distblk __real_computeSATDWP(StorablePicture *, MEBlock *, distblk, MotionVector *);
+distblk __real_computeBiPredSAD1(StorablePicture *, StorablePicture *, MEBlock *, distblk, MotionVector *, MotionVector *);
+distblk __real_computeBiPredSAD2(StorablePicture *, StorablePicture *, MEBlock *, distblk, MotionVector *, MotionVector *);
+distblk __real_computeBiPredSSE1(StorablePicture *, StorablePicture *, MEBlock *, distblk, MotionVector *, MotionVector *);
+distblk __real_computeBiPredSSE2(StorablePicture *, StorablePicture *, MEBlock *, distblk, MotionVector *, MotionVector *);
+distblk __real_computeBiPredSATD1(StorablePicture *, StorablePicture *, MEBlock *, distblk, MotionVector *, MotionVector *);
+distblk __real_computeBiPredSATD2(StorablePicture *, StorablePicture *, MEBlock *, distblk, MotionVector *, MotionVector *);
+distblk __real_full_search_bipred_motion_estimation(Macroblock *, int, MotionVector *, MotionVector *, MotionVector *, MotionVector *, MEBlock *, int, distblk, int);
+distblk __real_sub_pel_bipred_motion_estimation(Macroblock *, MEBlock *, int, MotionVector *, MotionVector *, MotionVector *, MotionVector *, distblk, int *);
 int     __real_quant_ac4x4_normal(Macroblock *, int **, struct quant_methods *);
 int     __real_quant_ac4x4_around(Macroblock *, int **, struct quant_methods *);
 int     __real_quant_dc4x4_normal(Macroblock *, int **, int, int *, int *, LevelQuantParams *, const byte (*)[2]);
@@ -103,7 +117,7 @@ static struct
   int              list[JMB_MAX_REFS], nlist;
   jmb_me_config    cfg;
   int              cfg_valid;
-  unsigned long    calls[9];
+  unsigned long    calls[10];
   int              verify;            /* JMB_SHIM_VERIFY=1: differential check of the device luma_residual_coding */
   unsigned long    verified;
 } S;
@@ -134,9 +148,9 @@ static void report(void)
   if (S.init == 1 && S.verify)
     fprintf(stderr, "[jmb shim] luma_residual_coding verified on %lu macroblock codings (levels, cbp, cbp_blk, reconstruction)\n", S.verified);
   if (S.init == 1 && getenv("JMB_SHIM_VERBOSE"))
-    fprintf(stderr, "[jmb shim] planes %lu  full %lu  fastfull %lu  subpel %lu  fwd4 %lu  fwd8 %lu  quant4 %lu  quant8 %lu  dist %lu  kernel launches %llu\n",
+    fprintf(stderr, "[jmb shim] planes %lu  full %lu  fastfull %lu  subpel %lu  fwd4 %lu  fwd8 %lu  quant4 %lu  quant8 %lu  dist %lu  kernel launches %llu  bipred/weighted distortions %lu\n",
             S.calls[0], S.calls[1], S.calls[2], S.calls[3], S.calls[4], S.calls[5], S.calls[6], S.calls[7], S.calls[8],
-            (unsigned long long)jmb_launch_count(S.ctx));
+            (unsigned long long)jmb_launch_count(S.ctx), S.calls[9]);
 }
 
 static int shim_on(int family)
@@ -236,7 +250,6 @@ static int ref_index_of(VideoParameters *p_Vid, Slice *currSlice, MEBlock *mv_bl
 
   if (p_Vid->structure != FRAME || currSlice->mb_aff_frame_flag) unsupported("field / MBAFF picture");
   if (mv_block->ChromaMEEnable) unsupported("ChromaMEEnable");
-  if (mv_block->apply_weights) unsupported("weighted-prediction motion estimation");
   if (!ref_picture) unsupported("a search without a reference picture");
 
   for (i = 0; i < JMB_MAX_REFS; i++)
@@ -312,6 +325,10 @@ distblk __wrap_full_search_motion_estimation(Macroblock *currMB, MotionVector *p
   MotionVector *mv = &mv_block->mv[(short)mv_block->list];
   int rc;
   if (!shim_on(FAM_ME)) return __real_full_search_motion_estimation(currMB, pred_mv, mv_block, min_mcost, lambda_factor);
+  /* weighted-reference ME (UseWeightedReferenceME): JM's own loop runs and takes every distortion from the device
+   * through mv_block->computePredFPel = computeSADWP (wrapped below) */
+  if (mv_block->apply_weights || currMB->p_Inp->MEErrorMetric[F_PEL] != ERROR_SAD)      /* likewise a full-pel metric other than SAD */
+    return __real_full_search_motion_estimation(currMB, pred_mv, mv_block, min_mcost, lambda_factor);
   if (!currMB->p_Inp->rdopt) unsupported("RDOptimization=0 (the (0,0) bias of full_search_motion_estimation)");
   S.calls[1]++;
   configure(currMB, mv_block, imin(mv_block->searchRange.max_x, mv_block->searchRange.max_y) >> 2);
@@ -340,6 +357,7 @@ void __wrap_setup_fast_full_search(Macroblock *currMB, MEBlock *mv_block, int li
   PixelPos block[4];
   if (!shim_on(FAM_ME)) { __real_setup_fast_full_search(currMB, mv_block, list); return; }
   if (!p_Inp->rdopt) unsupported("RDOptimization=0 with fast full search");
+  if (mv_block->apply_weights) unsupported("fast full search with UseWeightedReferenceME (its weighted SAD surfaces are inline host code; use SearchMode -1 or 3)");
   get_neighbors(currMB, block, 0, 0, 16);
   currMB->GetMVPredictor(currMB, block, &pmv, ref, p_Vid->enc_picture->mv_info, list, 0, 0, 16, 16);
 #if (JM_INT_DIVIDE)
@@ -389,6 +407,7 @@ distblk __wrap_sub_pel_motion_estimation(Macroblock *currMB, MotionVector *pred,
   MotionVector *mv = &mv_block->mv[mv_block->list];
   int rc;
   if (!shim_on(FAM_SUBPEL)) return __real_sub_pel_motion_estimation(currMB, pred, mv_block, min_mcost, lambda);
+  if (mv_block->apply_weights) return __real_sub_pel_motion_estimation(currMB, pred, mv_block, min_mcost, lambda);   /* -> compute*WP on the device */
   if (!currMB->p_Inp->rdopt) unsupported("RDOptimization=0 (the (0,0) bias of sub_pel_motion_estimation)");
   S.calls[3]++;
   configure(currMB, mv_block, 0);
@@ -442,6 +461,197 @@ distblk __wrap_computeSATD(StorablePicture *ref1, MEBlock *mv_block, distblk min
 {
   if (!shim_on(FAM_DIST)) return __real_computeSATD(ref1, mv_block, min_mcost, cand);
   return block_dist(JMB_SATD, ref1, mv_block, min_mcost, cand);
+}
+
+/* ---- the other nine members of the distortion table (mv_search.c:486-506): weighted and bi-predictive forms -------
+ * computeSADWP/SSEWP/SATDWP (me_distortion.c:434,1261,833), computeBiPredSAD1/SSE1/SATD1 (:525,:1353,:943),
+ * computeBiPredSAD2/SSE2/SATD2 (:624,:1438,:1038) -> jmb_dist_ex.  Weights as PrepareMEParams / PrepareBiPredMEParams
+ * (mv_search.c:183,206) left them in the MEBlock. */
+static void dist_refs(MEBlock *mv_block, StorablePicture *ref1, StorablePicture *ref2, int *i1, int *i2)
+{
+  VideoParameters *p_Vid = mv_block->p_Vid;
+  *i1 = ref_index_of(p_Vid, mv_block->p_Slice, mv_block, ref1);
+  *i2 = ref2 ? ref_index_of(p_Vid, mv_block->p_Slice, mv_block, ref2) : *i1;
+  if (ref2) *i1 = ref_index_of(p_Vid, mv_block->p_Slice, mv_block, ref1);      /* registering ref2 may have re-ordered the list */
+}
+
+static void dist_pred_of(jmb_dist_pred *P, int form, MEBlock *mv_block, int ref2, const MotionVector *cand2)
+{
+  Slice *currSlice = mv_block->p_Slice;
+  memset(P, 0, sizeof(*P));
+  P->form = form;
+  P->ref2 = ref2;
+  if (cand2) { P->cand2_x = cand2->mv_x; P->cand2_y = cand2->mv_y; }
+  if (mv_block->p_Vid->max_imgpel_value != 255) unsupported("weighted / bi-predictive distortion at a bit depth other than 8");
+  if (form == JMB_PRED_WEIGHTED) { P->weight1 = mv_block->weight_luma; P->offset = mv_block->offset_luma; }
+  if (form == JMB_PRED_WEIGHTED_AVERAGE) { P->weight1 = mv_block->weight1; P->weight2 = mv_block->weight2; P->offset = mv_block->offsetBi; }
+  P->log_weight_denom = currSlice->luma_log_weight_denom;
+  P->wp_round = currSlice->wp_luma_round;
+}
+
+static distblk block_dist_ex(int metric, int form, StorablePicture *ref1, StorablePicture *ref2, MEBlock *mv_block, distblk min_mcost,
+                             MotionVector *cand1, MotionVector *cand2)
+{
+  jmb_dist_pred P;
+  int16_t xy[2];
+  int32_t d = 0;
+  int rc, i1, i2;
+  S.calls[8]++;
+  S.calls[9]++;
+  dist_refs(mv_block, ref1, ref2, &i1, &i2);
+  dist_pred_of(&P, form, mv_block, i2, cand2);
+  xy[0] = cand1->mv_x;
+  xy[1] = cand1->mv_y;
+  rc = jmb_dist_ex(S.ctx, i1, &P, metric, mv_block->blocktype, mv_block->pos_x, mv_block->pos_y, xy, 1,
+                   metric == JMB_SATD && mv_block->test8x8, &d, JMB_HOST);
+  if (rc) jmb_die("jmb_dist_ex", rc);
+  return d > dist_down(min_mcost) ? min_mcost : dist_scale((distblk)d);
+}
+
+#define WRAP_UNI_WP(NAME, METRIC) \
+distblk __wrap_##NAME(StorablePicture *ref1, MEBlock *mv_block, distblk min_mcost, MotionVector *cand) \
+{ \
+  if (!shim_on(FAM_DIST)) return __real_##NAME(ref1, mv_block, min_mcost, cand); \
+  return block_dist_ex(METRIC, JMB_PRED_WEIGHTED, ref1, NULL, mv_block, min_mcost, cand, NULL); \
+}
+#define WRAP_BIPRED(NAME, METRIC, FORM) \
+distblk __wrap_##NAME(StorablePicture *ref1, StorablePicture *ref2, MEBlock *mv_block, distblk min_mcost, MotionVector *cand1, MotionVector *cand2) \
+{ \
+  if (!shim_on(FAM_DIST)) return __real_##NAME(ref1, ref2, mv_block, min_mcost, cand1, cand2); \
+  return block_dist_ex(METRIC, FORM, ref1, ref2, mv_block, min_mcost, cand1, cand2); \
+}
+WRAP_UNI_WP(computeSADWP, JMB_SAD)
+WRAP_UNI_WP(computeSSEWP, JMB_SSE)
+WRAP_UNI_WP(computeSATDWP, JMB_SATD)
+WRAP_BIPRED(computeBiPredSAD1, JMB_SAD, JMB_PRED_AVERAGE)
+WRAP_BIPRED(computeBiPredSSE1, JMB_SSE, JMB_PRED_AVERAGE)
+WRAP_BIPRED(computeBiPredSATD1, JMB_SATD, JMB_PRED_AVERAGE)
+WRAP_BIPRED(computeBiPredSAD2, JMB_SAD, JMB_PRED_WEIGHTED_AVERAGE)
+WRAP_BIPRED(computeBiPredSSE2, JMB_SSE, JMB_PRED_WEIGHTED_AVERAGE)
+WRAP_BIPRED(computeBiPredSATD2, JMB_SATD, JMB_PRED_WEIGHTED_AVERAGE)
+
+/* ---- bi-predictive searches (currMB->BiPredME / SubPelBiPredME for SearchMode -1 and 0, mv_search.c:162-170) ----------
+ * One list moves, the other stands still.  Every candidate's distortion comes from ONE jmb_dist_ex call; the host then
+ * replays JM's sequential selection (strict '<', candidates whose mv cost alone reaches min_mcost skipped, the early exit
+ * of the distortion = "return the threshold") on the complete distortions. */
+static int bipred_metric(MEBlock *mv_block, int level)
+{
+  int m = mv_block->p_Vid->p_Inp->MEErrorMetric[level];
+  if (m != ERROR_SAD && m != ERROR_SSE && m != ERROR_SATD) unsupported("a motion-estimation error metric other than SAD / SSE / SATD");
+  return m == ERROR_SAD ? JMB_SAD : m == ERROR_SSE ? JMB_SSE : JMB_SATD;
+}
+
+static void bipred_dists(Macroblock *currMB, MEBlock *mv_block, int list, int level, const int16_t *cands, int n,
+                         const MotionVector *cand2, int32_t *d)
+{
+  Slice *currSlice = currMB->p_Slice;
+  int list_offset = currMB->p_Vid->mb_data[currMB->mbAddrX].list_offset;
+  StorablePicture *ref1 = currSlice->listX[list + list_offset][(int)mv_block->ref_idx];
+  StorablePicture *ref2 = currSlice->listX[(list ^ 1) + list_offset][0];
+  int metric = bipred_metric(mv_block, level), i1, i2, rc;
+  jmb_dist_pred P;
+  dist_refs(mv_block, ref1, ref2, &i1, &i2);
+  dist_pred_of(&P, mv_block->apply_weights ? JMB_PRED_WEIGHTED_AVERAGE : JMB_PRED_AVERAGE, mv_block, i2, cand2);
+  rc = jmb_dist_ex(S.ctx, i1, &P, metric, mv_block->blocktype, mv_block->pos_x, mv_block->pos_y, cands, n,
+                   metric == JMB_SATD && mv_block->test8x8, d, JMB_HOST);
+  if (rc) jmb_die("jmb_dist_ex(bipred)", rc);
+  S.calls[8] += (unsigned long)n;
+  S.calls[9] += (unsigned long)n;
+}
+
+distblk __wrap_full_search_bipred_motion_estimation(Macroblock *currMB, int list, MotionVector *pred_mv1, MotionVector *pred_mv2,
+                                                    MotionVector *mv1, MotionVector *mv2, MEBlock *mv_block, int search_range,
+                                                    distblk min_mcost, int lambda_factor)
+{
+  VideoParameters *p_Vid = currMB->p_Vid;
+  int pos, best_pos = 0, max_pos = (2 * (search_range >> 2) + 1) * (2 * (search_range >> 2) + 1);
+  MotionVector center1, center2, cand, pred1, pred2;
+  int16_t *xy;
+  int32_t *d;
+  distblk mcost, mc2;
+  if (!shim_on(FAM_ME)) return __real_full_search_bipred_motion_estimation(currMB, list, pred_mv1, pred_mv2, mv1, mv2, mv_block, search_range, min_mcost, lambda_factor);
+  pred1.mv_x = mv_block->pos_x_padded + pred_mv1->mv_x;  pred1.mv_y = mv_block->pos_y_padded + pred_mv1->mv_y;
+  pred2.mv_x = mv_block->pos_x_padded + pred_mv2->mv_x;  pred2.mv_y = mv_block->pos_y_padded + pred_mv2->mv_y;
+  center1.mv_x = mv_block->pos_x_padded + mv1->mv_x;     center1.mv_y = mv_block->pos_y_padded + mv1->mv_y;
+  center2.mv_x = mv_block->pos_x_padded + mv2->mv_x;     center2.mv_y = mv_block->pos_y_padded + mv2->mv_y;
+  xy = (int16_t *)malloc((size_t)max_pos * (2 * sizeof(int16_t) + sizeof(int32_t)));
+  if (!xy) no_mem_exit("jmb shim: bipred candidates");
+  d = (int32_t *)(xy + 2 * (size_t)max_pos);
+  for (pos = 0; pos < max_pos; pos++)
+  {
+    xy[2 * pos]     = (int16_t)(center1.mv_x + p_Vid->spiral_qpel_search[pos].mv_x);
+    xy[2 * pos + 1] = (int16_t)(center1.mv_y + p_Vid->spiral_qpel_search[pos].mv_y);
+  }
+  bipred_dists(currMB, mv_block, list, F_PEL, xy, max_pos, &center2, d);
+  mc2 = mv_cost(p_Vid, lambda_factor, &center2, &pred2);
+  for (pos = 0; pos < max_pos; pos++)
+  {
+    distblk thr;
+    cand.mv_x = xy[2 * pos];  cand.mv_y = xy[2 * pos + 1];
+    mcost = mv_cost(p_Vid, lambda_factor, &cand, &pred1) + mc2;
+    if (mcost >= min_mcost) continue;
+    thr = min_mcost - mcost;
+    mcost += d[pos] > dist_down(thr) ? thr : dist_scale((distblk)d[pos]);
+    if (mcost < min_mcost) { best_pos = pos; min_mcost = mcost; }
+  }
+  free(xy);
+  if (best_pos) add_mvs(mv1, &p_Vid->spiral_qpel_search[best_pos]);
+  S.calls[1]++;
+  return min_mcost;
+}
+
+distblk __wrap_sub_pel_bipred_motion_estimation(Macroblock *currMB, MEBlock *mv_block, int list, MotionVector *pred_mv1, MotionVector *pred_mv2,
+                                                MotionVector *mv1, MotionVector *mv2, distblk min_mcost, int *lambda)
+{
+  VideoParameters *p_Vid = currMB->p_Vid;
+  int stage;
+  MotionVector smv;
+  if (!shim_on(FAM_SUBPEL)) return __real_sub_pel_bipred_motion_estimation(currMB, mv_block, list, pred_mv1, pred_mv2, mv1, mv2, min_mcost, lambda);
+  smv = pad_MVs(*mv2, mv_block);
+  for (stage = 0; stage < 2; stage++)      /* half-pel (me_fullsearch.c:330-358), then quarter-pel (:365-392) */
+  {
+    const MotionVector *spiral = stage ? p_Vid->spiral_search : p_Vid->spiral_hpel_search;
+    int lambda_factor = lambda[stage ? Q_PEL : H_PEL];
+    int pos0, pos1, pos, best_pos = 0, n;
+    int16_t xy[2 * 9];
+    int32_t d[9];
+    distblk mc2, mcost;
+    MotionVector cand;
+    if (!stage)
+    {
+      pos0 = (min_mcost == DISTBLK_MAX) ? 0 : p_Vid->start_me_refinement_hp;
+      pos1 = !p_Vid->start_me_refinement_hp ? imax(1, mv_block->search_pos2) : mv_block->search_pos2;
+    }
+    else
+    {
+      if (!p_Vid->start_me_refinement_qp) min_mcost = DISTBLK_MAX;
+      pos0 = p_Vid->start_me_refinement_qp;
+      pos1 = mv_block->search_pos4;
+    }
+    if (pos1 > 9) unsupported("more than nine sub-pel refinement positions");
+    n = pos1 - pos0;
+    if (n <= 0) continue;
+    for (pos = pos0; pos < pos1; pos++)
+    {
+      xy[2 * (pos - pos0)]     = (int16_t)(mv1->mv_x + spiral[pos].mv_x + mv_block->pos_x_padded);      /* pad_MVs */
+      xy[2 * (pos - pos0) + 1] = (int16_t)(mv1->mv_y + spiral[pos].mv_y + mv_block->pos_y_padded);
+    }
+    bipred_dists(currMB, mv_block, list, stage ? Q_PEL : H_PEL, xy, n, &smv, d);
+    mc2 = mv_cost(p_Vid, lambda_factor, mv2, pred_mv2);
+    for (pos = pos0; pos < pos1; pos++)
+    {
+      distblk thr;
+      cand.mv_x = mv1->mv_x + spiral[pos].mv_x;  cand.mv_y = mv1->mv_y + spiral[pos].mv_y;
+      mcost = mv_cost(p_Vid, lambda_factor, &cand, pred_mv1) + mc2;
+      if (mcost >= min_mcost) continue;
+      thr = min_mcost - mcost;
+      mcost += d[pos - pos0] > dist_down(thr) ? thr : dist_scale((distblk)d[pos - pos0]);
+      if (mcost < min_mcost) { min_mcost = mcost; best_pos = pos; }
+    }
+    if (best_pos) add_mvs(mv1, &spiral[best_pos]);
+  }
+  S.calls[3]++;
+  return min_mcost;
 }
 
 /* ---- the DC / AC members of the quantiser family and the Hadamard transforms (Intra16x16 and chroma DC paths) ----

@@ -192,6 +192,52 @@ int jmo_dist(const jmo_ref *r, const uint16_t *src, int bsx, int bsy, int cx, in
   return acc;
 }
 
+/* Prediction sample of the weighted / bi-predictive distortions:
+ * computeSADWP me_distortion.c:434 (also SATDWP :833, SSEWP :1261):   clip(((w * ref + round) >> denom) + offset)
+ * computeBiPredSAD1 :525 (SATD1 :943, SSE1 :1353):                    (ref1 + ref2 + 1) >> 1
+ * computeBiPredSAD2 :624 (SATD2 :1038, SSE2 :1438):                   clip(((w1*ref1 + w2*ref2 + 2*round) >> (denom+1)) + offsetBi)
+ * Clamps as in the plain functions, applied to each reference on its own. */
+static inline int pred_sample(int form, int a, int b, const int *wp, int maxv)
+{
+  switch (form) {
+  case 1:  return iclip(0, maxv, ((wp[0] * a + wp[4]) >> wp[3]) + wp[2]);
+  case 2:  return (a + b + 1) >> 1;
+  case 3:  return iclip(0, maxv, ((wp[0] * a + wp[1] * b + 2 * wp[4]) >> (wp[3] + 1)) + wp[2]);
+  default: return a;
+  }
+}
+
+int jmo_dist_ex(const jmo_ref *r1, const jmo_ref *r2, const uint16_t *src, int bsx, int bsy, int c1x, int c1y, int c2x, int c2y,
+                int metric, int test8x8, int form, const int *wp, int maxv)
+{
+  int acc = 0, two = form >= 2;
+  if (metric != JMO_SATD) {
+    const uint16_t *a = umv_line(r1, c1y, c1x), *b = two ? umv_line(r2, c2y, c2x) : a;
+    for (int y = 0; y < bsy; y++)
+      for (int x = 0; x < bsx; x++) {
+        int d = src[y * bsx + x] - pred_sample(form, a[(size_t)y * r1->W + x], b[(size_t)y * r1->W + x], wp, maxv);
+        acc += (metric == JMO_SAD) ? iabs_(d) : d * d;
+      }
+    return acc;
+  }
+  int n = test8x8 ? 8 : 4;
+  int16_t diff[64];
+  for (int by = 0; by < bsy; by += n)
+    for (int bx = 0; bx < bsx; bx += n) {
+      const uint16_t *a = umv_line(r1, c1y + (by << 2), c1x + (bx << 2));
+      const uint16_t *b = two ? umv_line(r2, c2y + (by << 2), c2x + (bx << 2)) : a;
+      /* computeBiPredSATD2's 8x8 branch does not advance the source pointer after the eighth sample of a row
+       * (me_distortion.c:1166 "*d++ = (short) ((*src_line) - weighted_pel);"), so row y of a sub-block reads the
+       * block-compact source y samples early.  Reproduced: the encoder's decisions depend on it. */
+      int slip = (form == 3 && test8x8) ? 1 : 0;
+      for (int y = 0; y < n; y++)
+        for (int x = 0; x < n; x++)
+          diff[y * n + x] = (int16_t)(src[(by + y) * bsx + bx + x - slip * y] - pred_sample(form, a[(size_t)y * r1->W + x], b[(size_t)y * r1->W + x], wp, maxv));
+      acc += test8x8 ? jmo_hadamard_sad8x8(diff) : jmo_hadamard_sad4x4(diff);
+    }
+  return acc;
+}
+
 static const int k_bs[8][2] = {{16,16},{16,16},{16,8},{8,16},{8,8},{8,4},{4,8},{4,4}}; /* macroblock.h:58-68 */
 
 static void get_block(const uint16_t *cur, int stride, int px, int py, int bsx, int bsy, uint16_t *out)

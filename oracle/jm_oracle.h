@@ -39,6 +39,12 @@ int  jmo_mvbits(int v);
 int jmo_dist(const jmo_ref *r, const uint16_t *src, int bsx, int bsy, int cand_x, int cand_y,
              int metric, int test8x8);
 
+/* the weighted / bi-predictive members of the distortion table (me_distortion.c:434-1520):
+ * form 0 plain, 1 weighted, 2 average of two references, 3 weighted average; wp = {weight1, weight2, offset,
+ * luma_log_weight_denom, wp_luma_round}; max_value = max_imgpel_value */
+int jmo_dist_ex(const jmo_ref *r1, const jmo_ref *r2, const uint16_t *src, int bsx, int bsy, int c1x, int c1y, int c2x, int c2y,
+                int metric, int test8x8, int form, const int *wp, int max_value);
+
 int64_t jmo_full_search(const jmo_ref *r, const uint16_t *cur, int cur_stride, int blocktype,
                         int pos_x, int pos_y, int pred_x, int pred_y, int center_x, int center_y,
                         int lambda, int64_t min_mcost, int search_range, int16_t *mv_out);

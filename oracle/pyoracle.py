@@ -49,6 +49,7 @@ class Oracle:
         L.jmo_ref_get_plane.argtypes = [C.c_void_p, C.c_int, C.c_int, _u16p]
         L.jmo_spiral.argtypes = [C.c_int, _i16p]
         L.jmo_dist.argtypes = [C.c_void_p, _u16p] + [C.c_int] * 6
+        L.jmo_dist_ex.argtypes = [C.c_void_p, C.c_void_p, _u16p] + [C.c_int] * 9 + [_i32p, C.c_int]
         L.jmo_full_search.restype = C.c_int64
         L.jmo_full_search.argtypes = [C.c_void_p, _u16p] + [C.c_int] * 9 + [C.c_int64, C.c_int, _i16p]
         L.jmo_sub_pel.restype = C.c_int64
@@ -99,6 +100,13 @@ class Oracle:
         bsx, bsy = BLOCK_SIZE[blocktype]
         src = np.ascontiguousarray(cur[pos[1]:pos[1] + bsy, pos[0]:pos[0] + bsx], np.uint16)
         return self.L.jmo_dist(r[0], src, bsx, bsy, cand[0], cand[1], metric, test8x8)
+
+    def dist_ex(self, r1, r2, cur, blocktype, pos, cand1, cand2, metric, form, wp=(32, 32, 0, 5, 16), test8x8=0, max_value=255):
+        """wp = (weight1, weight2, offset, luma_log_weight_denom, wp_luma_round); form 0 plain, 1 weighted, 2 average, 3 weighted average"""
+        bsx, bsy = BLOCK_SIZE[blocktype]
+        src = np.ascontiguousarray(cur[pos[1]:pos[1] + bsy, pos[0]:pos[0] + bsx], np.uint16)
+        return self.L.jmo_dist_ex(r1[0], (r2 or r1)[0], src, bsx, bsy, cand1[0], cand1[1], cand2[0], cand2[1], metric, test8x8, form,
+                                  np.asarray(wp, np.int32), max_value)
 
     def full_search(self, r, cur, blocktype, pos, pred, center, lam, min_mcost, R):
         cur = np.ascontiguousarray(cur, np.uint16)
@@ -229,6 +237,9 @@ class JMRef:
         L.jmref_full_search.argtypes = [C.c_void_p] + [C.c_int] * 8 + [C.c_int64, _i16p]
         L.jmref_sub_pel.restype = C.c_int64
         L.jmref_sub_pel.argtypes = [C.c_void_p] + [C.c_int] * 7 + [_i32p, C.c_int64, C.c_int, _i16p]
+        L.jmref_set_ref2.argtypes = [C.c_void_p, _u16p, C.c_int]
+        L.jmref_dist_ex.restype = C.c_int64
+        L.jmref_dist_ex.argtypes = [C.c_void_p] + [C.c_int] * 10 + [C.c_int64, _i32p]
         L.jmref_dist.restype = C.c_int64
         L.jmref_dist.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_int64]
         L.jmref_ffs_setup.argtypes = [C.c_void_p] + [C.c_int] * 4 + [_i16p]
@@ -253,6 +264,10 @@ class JMRef:
     def set_ref(self, luma):
         luma = np.ascontiguousarray(luma, np.uint16)
         self.L.jmref_set_ref(self.h_, luma, luma.shape[1])
+
+    def set_ref2(self, luma):
+        luma = np.ascontiguousarray(luma, np.uint16)
+        self.L.jmref_set_ref2(self.h_, luma, luma.shape[1])
 
     def set_cur(self, luma):
         luma = np.ascontiguousarray(luma, np.uint16)
@@ -288,6 +303,10 @@ class JMRef:
 
     def dist(self, metric, blocktype, pos, cand, test8x8=0, min_mcost=DISTBLK_MAX):
         return self.L.jmref_dist(self.h_, metric, blocktype, pos[0], pos[1], cand[0], cand[1], test8x8, min_mcost)
+
+    def dist_ex(self, metric, form, blocktype, pos, cand1, cand2, wp=(32, 32, 0, 5, 16), test8x8=0, min_mcost=DISTBLK_MAX):
+        return self.L.jmref_dist_ex(self.h_, metric, form, blocktype, pos[0], pos[1], cand1[0], cand1[1], cand2[0], cand2[1],
+                                    test8x8, min_mcost, np.asarray(wp, np.int32))
 
     def ffs_setup(self, mb, pmv):
         c = np.zeros(2, np.int16)

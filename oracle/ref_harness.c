@@ -45,6 +45,7 @@ typedef struct jmref_ctx
   Macroblock      *mb;
   StorablePicture *ref;
   StorablePicture *ref_list[2];
+  StorablePicture *ref2;       /* second reference of the bi-predictive distortions (jmref_set_ref2) */
   imgpel         **cur;        /* current (source) luma, row pointers */
   int              w, h;
   MotionVector     stub_pmv;   /* what the stubbed GetMVPredictor returns */
@@ -154,6 +155,31 @@ void *jmref_open(int width, int height, int search_range, int metric_f, int metr
   return c;
 }
 
+static StorablePicture *new_ref_picture(int width, int height)
+{
+  StorablePicture *s = (StorablePicture *)calloc(1, sizeof(StorablePicture));
+  s->size_x = width; s->size_y = height;
+  s->size_x_padded = width + 2 * IMG_PAD_SIZE_X;
+  s->size_y_padded = height + 2 * IMG_PAD_SIZE_Y;
+  s->size_x_pad = width + 2 * IMG_PAD_SIZE_X - 1 - MB_BLOCK_SIZE - IMG_PAD_SIZE_X;
+  s->size_y_pad = height + 2 * IMG_PAD_SIZE_Y - 1 - MB_BLOCK_SIZE - IMG_PAD_SIZE_Y;
+  get_mem2Dpel(&s->imgY, height, width);
+  get_mem4Dpel_pad(&s->imgY_sub, 4, 4, height, width, IMG_PAD_SIZE_Y, IMG_PAD_SIZE_X);
+  s->p_img_sub[0] = s->imgY_sub;
+  s->p_curr_img = s->imgY;
+  s->p_curr_img_sub = s->imgY_sub;
+  return s;
+}
+
+void jmref_set_ref2(void *h, const uint16_t *luma, int stride)
+{
+  jmref_ctx *c = (jmref_ctx *)h;
+  if (!c->ref2) c->ref2 = new_ref_picture(c->w, c->h);
+  for (int y = 0; y < c->h; y++)
+    memcpy(c->ref2->imgY[y], luma + (size_t)y * stride, c->w * sizeof(imgpel));
+  getSubImagesLuma(c->p_Vid, c->ref2);
+}
+
 void jmref_set_ref(void *h, const uint16_t *luma, int stride)
 {
   jmref_ctx *c = (jmref_ctx *)h;
@@ -245,6 +271,37 @@ int64_t jmref_dist(void *h, int metric, int blocktype, int pos_x, int pos_y, int
   if (metric == 0)      r = computeSAD (c->ref, &b, (distblk)min_mcost, &cand);
   else if (metric == 1) r = computeSSE (c->ref, &b, (distblk)min_mcost, &cand);
   else                  r = computeSATD(c->ref, &b, (distblk)min_mcost, &cand);
+  free_mem2Dpel(b.orig_pic);
+  return (int64_t)r;
+}
+
+/* the twelve members of the distortion table (mv_search.c:486-506): form 0 computeSAD/SSE/SATD, 1 compute*WP,
+ * 2 computeBiPred*1, 3 computeBiPred*2; wp = {weight1, weight2, offset, luma_log_weight_denom, wp_luma_round} */
+int64_t jmref_dist_ex(void *h, int metric, int form, int blocktype, int pos_x, int pos_y, int c1x, int c1y, int c2x, int c2y,
+                      int test8x8, int64_t min_mcost, const int *wp)
+{
+  jmref_ctx *c = (jmref_ctx *)h; g_ctx = c;
+  MEBlock b; MotionVector cand1, cand2;
+  fill_mv_block(c, &b, blocktype, pos_x, pos_y, test8x8);
+  cand1.mv_x = (short)c1x; cand1.mv_y = (short)c1y; cand2.mv_x = (short)c2x; cand2.mv_y = (short)c2y;
+  b.weight_luma = (short)wp[0]; b.offset_luma = (short)wp[2];
+  b.weight1 = (short)wp[0]; b.weight2 = (short)wp[1]; b.offsetBi = (short)wp[2];
+  c->slice->luma_log_weight_denom = (short)wp[3]; c->slice->wp_luma_round = wp[4];
+  distblk r = 0, m = (distblk)min_mcost;
+  switch (form * 3 + metric) {
+  case 0:  r = computeSAD (c->ref, &b, m, &cand1); break;
+  case 1:  r = computeSSE (c->ref, &b, m, &cand1); break;
+  case 2:  r = computeSATD(c->ref, &b, m, &cand1); break;
+  case 3:  r = computeSADWP (c->ref, &b, m, &cand1); break;
+  case 4:  r = computeSSEWP (c->ref, &b, m, &cand1); break;
+  case 5:  r = computeSATDWP(c->ref, &b, m, &cand1); break;
+  case 6:  r = computeBiPredSAD1 (c->ref, c->ref2, &b, m, &cand1, &cand2); break;
+  case 7:  r = computeBiPredSSE1 (c->ref, c->ref2, &b, m, &cand1, &cand2); break;
+  case 8:  r = computeBiPredSATD1(c->ref, c->ref2, &b, m, &cand1, &cand2); break;
+  case 9:  r = computeBiPredSAD2 (c->ref, c->ref2, &b, m, &cand1, &cand2); break;
+  case 10: r = computeBiPredSSE2 (c->ref, c->ref2, &b, m, &cand1, &cand2); break;
+  case 11: r = computeBiPredSATD2(c->ref, c->ref2, &b, m, &cand1, &cand2); break;
+  }
   free_mem2Dpel(b.orig_pic);
   return (int64_t)r;
 }

@@ -214,6 +214,34 @@ def test_dist(ctx, oracle, metric):
     oracle.ref_destroy(r)
 
 
+@pytest.mark.parametrize("form", [api.PRED_WEIGHTED, api.PRED_AVERAGE, api.PRED_WEIGHTED_AVERAGE])
+@pytest.mark.parametrize("metric", [api.SAD, api.SSE, api.SATD])
+def test_dist_weighted_and_bipred(ctx, oracle, metric, form):
+    """jmb_dist_ex standing in for compute*WP, computeBiPred*1, computeBiPred*2 (restatement pinned in test_oracle_vs_ref.py)."""
+    w, h = 96, 64
+    f = _frames(w, h, 15, n=3)
+    ctx.ref_put(0, f[0]); ctx.ref_put(1, f[2]); ctx.pic_begin(f[1], [0, 1])
+    r1, r2 = oracle.ref_create(f[0]), oracle.ref_create(f[2])
+    rng = np.random.default_rng(10 * form + metric)
+    for it in range(16):
+        bt = int(rng.integers(1, 8)); bsx, bsy = api.BLOCK_SIZE[bt]
+        pos = (int(rng.integers(0, (w - bsx) // 4 + 1)) * 4, int(rng.integers(0, (h - bsy) // 4 + 1)) * 4)
+        t8 = int(metric == api.SATD and bt <= 4 and rng.integers(0, 2))
+        cands = np.stack([pos[0] * 4 + rng.integers(-220, 220, 30), pos[1] * 4 + rng.integers(-170, 170, 30)], 1).astype(np.int16)
+        c2 = (pos[0] * 4 + int(rng.integers(-220, 220)), pos[1] * 4 + int(rng.integers(-170, 170)))
+        denom = int(rng.integers(0, 8))
+        wt = [int(rng.integers(-128, 128)) if it % 4 == 0 else int((1 << denom) * rng.uniform(0.5, 1.5)) for _ in range(2)]
+        wp = (wt[0], wt[1], int(rng.integers(-40, 41)), denom, (1 << (denom - 1)) if denom else 0)
+        got = ctx.dist_ex(0, 1, metric, form, bt, pos, cands, c2, wp, t8)
+        want = [oracle.dist_ex(r1, r2, f[1], bt, pos, (int(c[0]), int(c[1])), c2, metric, form, wp, t8) for c in cands]
+        assert got.tolist() == want, (it, bt, t8, wp)
+    oracle.ref_destroy(r1); oracle.ref_destroy(r2)
+    with pytest.raises(api.JMBError):
+        ctx.dist_ex(0, 5, metric, api.PRED_AVERAGE, 1, (0, 0), [[0, 0]], (0, 0))          # ref2 not in the list
+    with pytest.raises(api.JMBError):
+        ctx.dist_ex(0, 1, metric, api.PRED_WEIGHTED, 1, (0, 0), [[0, 0]], (0, 0), wp=(32, 32, 0, 9, 16))   # denom out of range
+
+
 def test_forward_transforms(ctx, oracle):
     rng = np.random.default_rng(20)
     b4 = rng.integers(-255, 256, size=(500, 4, 4)); b8 = rng.integers(-255, 256, size=(300, 8, 8))
@@ -336,6 +364,13 @@ def test_errors_are_loud(ctx):
     with pytest.raises(api.JMBError, match="lambda"):
         ctx.me_search(badlam, frame=True)
     ctx.me_search(good, frame=True)        # the error word is cleared once reported
+    # the integer full search is a SAD search: under MEDistortionFPel = SSE it refuses, sub-pel-only requests still run
+    ctx.configure(search_range=4, metric=(api.SSE, api.SSE, api.SSE))
+    with pytest.raises(api.JMBError, match="MEDistortionFPel"):
+        ctx.me_search(good, frame=True)
+    sub = good.copy(); sub["flags"] = api.REQ_SUBPEL | api.REQ_SKIP_INT
+    ctx.me_search(sub, frame=True)
+    ctx.configure(search_range=4)
 
 
 def test_pred_from_results_and_resident_chain(ctx, oracle):

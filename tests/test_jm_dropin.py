@@ -26,9 +26,11 @@ def _md5(path):
     return hashlib.md5(open(path, "rb").read()).hexdigest()
 
 
-def _make_yuv(path, w, h, n, seed, fmt420=True):
+def _make_yuv(path, w, h, n, seed, fmt420=True, fade=0.0):
     from jm_b200 import synth
     frames = synth.luma_frames(w, h, n, seed=seed, motion=(3, -2))
+    if fade:      # a fade to black: gives explicit weighted prediction something to find
+        frames = [np.clip(np.rint(f * (1.0 - fade * i)) + 2 * i, 0, 255).astype(np.uint16) for i, f in enumerate(frames)]
     if fmt420:
         synth.write_yuv420(path, frames, textured_chroma=True)
     else:
@@ -74,6 +76,23 @@ CONFIGS = {
     "yuv422_satd_subpel": ["ProfileIDC=122", "YUVFormat=2", "SymbolMode=1", "RDOptimization=1", "Transform8x8Mode=1", "QPISlice=28",
                            "QPPSlice=28", "SearchMode=-1", "SearchRange=8", "NumberReferenceFrames=1", "AdaptiveRounding=1",
                            "MEDistortionHPel=2", "MEDistortionQPel=2"],
+    # bi-predictive motion estimation (currMB->BiPredME / SubPelBiPredME): full_search_bipred_motion_estimation and
+    # sub_pel_bipred_motion_estimation run as ONE batched device call per stage (computeBiPredSAD1 / computeBiPredSATD1)
+    "b_frames_bipred_me": ["ProfileIDC=100", "SymbolMode=1", "RDOptimization=1", "Transform8x8Mode=1", "QPISlice=28", "QPPSlice=28", "QPBSlice=30",
+                           "SearchMode=-1", "SearchRange=8", "NumberReferenceFrames=2", "AdaptiveRounding=1", "BiPredMotionEstimation=1",
+                           "BiPredMERefinements=1", "BiPredMESearchRange=8", "BiPredMESubPel=2", "BiPredSearch16x8=1", "BiPredSearch8x16=1",
+                           "BiPredSearch8x8=1", "MEDistortionHPel=2", "MEDistortionQPel=2"],
+    # the same with SSE as the error metric at every level (computeSSE, computeBiPredSSE1)
+    "b_frames_bipred_me_sse": ["ProfileIDC=100", "SymbolMode=0", "RDOptimization=1", "Transform8x8Mode=0", "QPISlice=28", "QPPSlice=28", "QPBSlice=30",
+                               "SearchMode=-1", "SearchRange=8", "NumberReferenceFrames=2", "AdaptiveRounding=0", "BiPredMotionEstimation=1",
+                               "BiPredMERefinements=0", "BiPredMESearchRange=4", "BiPredMESubPel=1", "MEDistortionFPel=1", "MEDistortionHPel=1",
+                               "MEDistortionQPel=1"],
+    # explicit weighted prediction on a fade, weighted-reference ME: JM's own search loops run on the host and every
+    # distortion (computeSADWP / computeSATDWP / computeBiPredSAD2 / computeBiPredSATD2, incl. its 8x8 branch) is the device's
+    "b_frames_weighted_fade": ["ProfileIDC=100", "SymbolMode=1", "RDOptimization=1", "Transform8x8Mode=1", "QPISlice=28", "QPPSlice=28", "QPBSlice=30",
+                               "SearchMode=-1", "SearchRange=8", "NumberReferenceFrames=2", "AdaptiveRounding=1", "BiPredMotionEstimation=1",
+                               "BiPredMERefinements=1", "BiPredMESearchRange=4", "BiPredMESubPel=2", "BiPredSearch8x8=1", "MEDistortionHPel=2",
+                               "MEDistortionQPel=2", "WeightedPrediction=1", "WeightedBiprediction=1", "UseWeightedReferenceME=1"],
 }
 
 
@@ -112,7 +131,7 @@ def test_bitstream_identical_to_stock_jm(tmp_path, name):
     bframes = 2 if name.startswith("b_frames") else 0
     if bframes:
         frames = 7
-    _make_yuv(tmp_path / "input.yuv", w, h, frames, seed=11, fmt420="YUVFormat=2" not in CONFIGS[name])
+    _make_yuv(tmp_path / "input.yuv", w, h, frames, seed=11, fmt420="YUVFormat=2" not in CONFIGS[name], fade=0.06 if "fade" in name else 0.0)
     r1 = _encode(REF, tmp_path, "ref", w, h, frames, CONFIGS[name], bframes=bframes)
     r2 = _encode(JMB, tmp_path, "gpu", w, h, frames, CONFIGS[name], env={"JMB_SHIM_VERBOSE": "1"}, bframes=bframes)
     assert r1.returncode == 0, r1.stderr[-800:]
@@ -121,10 +140,13 @@ def test_bitstream_identical_to_stock_jm(tmp_path, name):
     assert line, "the shim did not report: was the GPU path used?"
     counts = dict(zip(line[0].split()[2::2][:9], [int(x) for x in line[0].split()[3::2][:9]]))
     assert counts["planes"] >= (frames - 1) // (bframes + 1) and counts["quant4"] + counts["quant8"] > 0, line[0]
-    if "SearchMode=3" in CONFIGS[name]:
-        assert counts["dist"] > 0, line[0]                       # EPZS: distortion oracle
+    if "SearchMode=3" in CONFIGS[name] or "UseWeightedReferenceME=1" in CONFIGS[name]:
+        assert counts["dist"] > 0, line[0]                       # EPZS / weighted-reference ME: distortion oracle
     else:
         assert counts["full"] + counts["fastfull"] > 0 and counts["subpel"] > 0, line[0]
+    if "BiPredMotionEstimation=1" in CONFIGS[name]:
+        assert counts["dist"] > 0, line[0]                       # the bi-predictive candidates went through jmb_dist_ex
+        assert int(line[0].split("bipred/weighted distortions")[1].split()[0]) > 0, line[0]
     _same_outputs(tmp_path, "ref", "gpu")
 
 

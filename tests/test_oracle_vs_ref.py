@@ -62,6 +62,41 @@ def test_distortion(pair, metric):
         assert o.dist(r, f[1], bt, pos, cand, metric, t8) << 5 == ref.dist(metric, bt, pos, cand, t8)
 
 
+@pytest.mark.parametrize("form", [1, 2, 3])
+@pytest.mark.parametrize("metric", [po.SAD, po.SSE, po.SATD])
+def test_weighted_and_bipred_distortion(pair, metric, form):
+    """computeSADWP/SSEWP/SATDWP, computeBiPredSAD1/SSE1/SATD1, computeBiPredSAD2/SSE2/SATD2 (me_distortion.c:434-1520)."""
+    o, ref, r, f = pair
+    f2 = synth.luma_frames(W, H, 3, seed=7, motion=(3, -2))[2]
+    ref.set_ref2(f2)
+    r2 = o.ref_create(f2)
+    rng = np.random.default_rng(10 * form + metric)
+    for it in range(300):
+        bt = int(rng.integers(1, 8))
+        bsx, bsy = po.BLOCK_SIZE[bt]
+        pos = (int(rng.integers(0, (W - bsx) // 4 + 1)) * 4, int(rng.integers(0, (H - bsy) // 4 + 1)) * 4)
+        c1 = (pos[0] * 4 + int(rng.integers(-200, 200)), pos[1] * 4 + int(rng.integers(-160, 160)))
+        c2 = (pos[0] * 4 + int(rng.integers(-200, 200)), pos[1] * 4 + int(rng.integers(-160, 160)))
+        t8 = int(metric == po.SATD and bt <= 4 and rng.integers(0, 2))
+        denom = int(rng.integers(0, 8))
+        # weights around 1.0 and wild ones (negative, large: the iClip1 of the weighted sample is hit), offsets of both signs
+        w = [int(rng.integers(-128, 128)) if it % 4 == 0 else int((1 << denom) * rng.uniform(0.5, 1.5)) for _ in range(2)]
+        wp = (w[0], w[1], int(rng.integers(-40, 41)), denom, (1 << (denom - 1)) if denom else 0)
+        assert o.dist_ex(r, r2, f[1], bt, pos, c1, c2, metric, form, wp, t8) << 5 == ref.dist_ex(metric, form, bt, pos, c1, c2, wp, t8), (it, bt, wp)
+    o.ref_destroy(r2)
+
+
+def test_distortion_early_exit_is_min_mcost(pair):
+    """JM's row / sub-block early exit returns the threshold itself (dist_scale_f, mv_search.h:19-23): a losing candidate."""
+    o, ref, r, f = pair
+    ref.set_ref2(f[0])
+    for form in range(4):
+        for metric in (po.SAD, po.SSE, po.SATD):
+            full = ref.dist_ex(metric, form, 1, (16, 16), (70, 60), (50, 70))
+            assert ref.dist_ex(metric, form, 1, (16, 16), (70, 60), (50, 70), min_mcost=full - 32) == full - 32
+            assert ref.dist_ex(metric, form, 1, (16, 16), (70, 60), (50, 70), min_mcost=full) == full
+
+
 def test_full_search(pair):
     o, ref, r, f = pair
     rng = np.random.default_rng(11)
