@@ -108,6 +108,52 @@ def main():
         for key in ("qp", "intra", "cav", "arw", "coef_in", "nonzero", "coef", "levels", "runs", "fadjust", "coeff_cost"):
             g[f"quant{variant}_{key}"] = np.array([r[key] for r in rows])
 
+    # ---- appended after the first release of the file: everything above regenerates bit-identically ----
+    # the weighted / bi-predictive distortion forms: compute*WP (form 1), computeBiPred*1 (2), computeBiPred*2 (3)
+    f3 = synth.luma_frames(W, H, 3, seed=2024, motion=(2, -3))[2]
+    g["ref2_luma"] = f3
+    ref.set_ref2(f3)
+    n = 180
+    dx = np.zeros((n, 15), np.int64)   # metric, form, bt, pos_x, pos_y, c1x, c1y, c2x, c2y, t8, w1, w2, off, denom, dist(<<5)
+    for i in range(n):
+        metric, form = i % 3, 1 + (i // 3) % 3
+        bt = int(rng.integers(1, 8)); bsx, bsy = po.BLOCK_SIZE[bt]
+        pos = (int(rng.integers(0, (W - bsx) // 4 + 1)) * 4, int(rng.integers(0, (H - bsy) // 4 + 1)) * 4)
+        c1 = (pos[0] * 4 + int(rng.integers(-200, 200)), pos[1] * 4 + int(rng.integers(-160, 160)))
+        c2 = (pos[0] * 4 + int(rng.integers(-200, 200)), pos[1] * 4 + int(rng.integers(-160, 160)))
+        t8 = int(metric == po.SATD and bt <= 4 and rng.integers(0, 2))
+        denom = int(rng.integers(0, 8))
+        w = [int(rng.integers(-128, 128)) if i % 5 == 0 else int((1 << denom) * rng.uniform(0.5, 1.5)) for _ in range(2)]
+        off = int(rng.integers(-40, 41))
+        wp = (w[0], w[1], off, denom, (1 << (denom - 1)) if denom else 0)
+        dx[i] = [metric, form, bt, pos[0], pos[1], c1[0], c1[1], c2[0], c2[1], t8, w[0], w[1], off, denom, ref.dist_ex(metric, form, bt, pos, c1, c2, wp, t8)]
+    g["dist_ex"] = dx
+
+    # inverse4x4 / inverse8x8 and the six Hadamard transforms (kind 0..5: hadamard4x4, ihadamard4x4, hadamard4x2, ihadamard4x2, hadamard2x2, ihadamard2x2)
+    c4 = rng.integers(-4000, 4001, size=(48, 4, 4)).astype(np.int32); c8 = rng.integers(-4000, 4001, size=(24, 8, 8)).astype(np.int32)
+    g["coef4"], g["coef8"] = c4, c8
+    g["inv4"] = np.stack([ref.inverse4x4(b) for b in c4]); g["inv8"] = np.stack([ref.inverse8x8(b) for b in c8])
+    for kind, per in enumerate((16, 16, 8, 8, 4, 4)):
+        v = rng.integers(-30000, 30001, size=(32, per)).astype(np.int32)
+        g[f"hadk{kind}_in"] = v; g[f"hadk{kind}_out"] = np.stack([ref.hadamard(kind, x) for x in v])
+
+    # quant_ac4x4_normal/_around (6,7), quant_dc4x4_normal (8), quant_dc2x2_normal/_around (9,10), quant_dc4x2_normal/_around (11,12)
+    scan420 = np.array([(0, 0), (0, 1), (0, 2), (0, 3)], np.uint8)
+    scan422 = np.array([(0, 0), (0, 1), (1, 0), (0, 2), (0, 3), (1, 1), (1, 2), (1, 3)], np.uint8)
+    for variant in range(6, 13):
+        ncoef = {6: 16, 7: 16, 8: 16, 9: 4, 10: 4, 11: 8, 12: 8}[variant]
+        scan = {9: scan420, 10: scan420, 11: scan422, 12: scan422}.get(variant, T.SNGL_SCAN)
+        rows = []
+        for it in range(30):
+            qp = int(rng.integers(0, 52)); amp = int(rng.choice([6, 80, 600, 4000]))
+            coef = rng.integers(-amp, amp + 1, size=ncoef).astype(np.int32)
+            intra = int(rng.integers(0, 2)); cav = int(rng.integers(0, 2)); arw = 1 + it % 8
+            qpar = T.q_params(qp, intra, 4)
+            o = ref.quant_misc(variant, coef, qp, qpar if variant <= 7 else qpar[0, 0], scan, T.COEFF_COST4x4[0], cav, arw=arw, cost0=3)
+            rows.append(dict(qp=qp, intra=intra, cav=cav, arw=arw, coef_in=coef, **o))
+        for key in ("qp", "intra", "cav", "arw", "coef_in", "nonzero", "coef", "levels", "runs", "fadjust", "coeff_cost"):
+            g[f"quant{variant}_{key}"] = np.array([r[key] for r in rows])
+
     # whole-encoder pins: md5 of the stock encoder's bitstream on seeded synthetic input (tests/test_jm_dropin.py configs)
     out = os.path.join(HERE, "jm_golden.npz")
     np.savez_compressed(out, **g)

@@ -151,3 +151,60 @@ def test_oracle_luma_residual_coding_consistency(oracle):
     q = oracle.quant(0, oracle.forward4x4(x), 20, T.q_params(20, 0, 4), T.SNGL_SCAN, T.COEFF_COST4x4[0], 1)
     back = (oracle.inverse4x4(q["coef"]) + 32) >> 6
     assert np.abs(back - x).max() <= 12          # QP 20: quantiser step 6.5
+
+
+# ---- the widened path: weighted / bi-predictive distortions, inverse transforms, Hadamards, DC / AC list quantisers ----
+SCAN420 = np.array([(0, 0), (0, 1), (0, 2), (0, 3)], np.uint8)
+SCAN422 = np.array([(0, 0), (0, 1), (1, 0), (0, 2), (0, 3), (1, 1), (1, 2), (1, 3)], np.uint8)
+
+
+def _wp(w1, w2, off, denom):
+    return (int(w1), int(w2), int(off), int(denom), (1 << (int(denom) - 1)) if denom else 0)
+
+
+def _misc_cases(variant):
+    from jm_b200 import api
+    scan = {9: SCAN420, 10: SCAN420, 11: SCAN422, 12: SCAN422}.get(variant, T.SNGL_SCAN)
+    for i in range(len(G[f"quant{variant}_qp"])):
+        g = {k: G[f"quant{variant}_{k}"][i] for k in ("qp", "intra", "cav", "arw", "coef_in", "nonzero", "coef", "levels", "runs", "fadjust", "coeff_cost")}
+        qpar = T.q_params(int(g["qp"]), int(g["intra"]), 4)
+        plan = api.qlist_plan(variant, int(g["qp"]), qpar if variant <= 7 else qpar[0, 0], scan, T.COEFF_COST4x4[0], int(g["cav"]), int(g["arw"]))
+        yield plan, g
+
+
+def _check_misc(o, g, variant):
+    assert o["nonzero"] == g["nonzero"] and o["coeff_cost"] == g["coeff_cost"], variant
+    for k in ("coef", "levels", "runs", "fadjust"):
+        assert np.array_equal(o[k], g[k]), (variant, k)
+
+
+def test_oracle_widened_path(oracle):
+    r1, r2 = oracle.ref_create(G["ref_luma"]), oracle.ref_create(G["ref2_luma"])
+    for metric, form, bt, px, py, c1x, c1y, c2x, c2y, t8, w1, w2, off, denom, d in G["dist_ex"].tolist():
+        assert oracle.dist_ex(r1, r2, G["cur_luma"], bt, (px, py), (c1x, c1y), (c2x, c2y), metric, form, _wp(w1, w2, off, denom), t8) << 5 == d
+    oracle.ref_destroy(r1); oracle.ref_destroy(r2)
+    for i, b in enumerate(G["coef4"]):
+        assert np.array_equal(oracle.inverse4x4(b), G["inv4"][i])
+    for i, b in enumerate(G["coef8"]):
+        assert np.array_equal(oracle.inverse8x8(b), G["inv8"][i])
+    for kind in range(6):
+        for v, want in zip(G[f"hadk{kind}_in"], G[f"hadk{kind}_out"]):
+            assert np.array_equal(oracle.hadamard(kind, v), want), kind
+    for variant in range(6, 13):
+        for plan, g in _misc_cases(variant):
+            _check_misc(oracle.quant_list(plan, g["coef_in"], cost0=3), g, variant)
+
+
+@pytest.mark.gpu
+def test_gpu_widened_path(ctx):
+    ctx.ref_put(0, G["ref_luma"]); ctx.ref_put(1, G["ref2_luma"]); ctx.pic_begin(G["cur_luma"], [0, 1])
+    for metric, form, bt, px, py, c1x, c1y, c2x, c2y, t8, w1, w2, off, denom, d in G["dist_ex"].tolist():
+        got = ctx.dist_ex(0, 1, metric, form, bt, (px, py), [(c1x, c1y)], (c2x, c2y), _wp(w1, w2, off, denom), t8)
+        assert int(got[0]) << 5 == d, (metric, form, bt)
+    assert np.array_equal(ctx.inverse_transform(G["coef4"], 4), G["inv4"])
+    assert np.array_equal(ctx.inverse_transform(G["coef8"], 8), G["inv8"])
+    for kind, per in enumerate((16, 16, 8, 8, 4, 4)):
+        assert np.array_equal(ctx.hadamard(kind, G[f"hadk{kind}_in"], per), G[f"hadk{kind}_out"]), kind
+    for variant in range(6, 13):
+        for plan, g in _misc_cases(variant):
+            _check_misc(ctx.quant_list(plan, g["coef_in"], cost0=3), g, variant)
