@@ -176,7 +176,11 @@ def run_ours(args):
     # ---- end-to-end leg: K independent picture streams per GPU (K host threads, each its own context = its own CUDA
     # stream, reference slots and staging; the calls are the synchronous JMB_HOST ones, so one stream's PCIe copies
     # overlap the other's kernels).  Pictures are independent units (closed-GOP shards), exactly like the ranks.
-    n_streams = args.e2e_streams if args.e2e_streams > 0 else max(1, min(3, (os.cpu_count() or 1) // (2 * world)))
+    # Measured on the 16-core B200 box (tools/gpu_e2e.sh): 3 streams 6.6 M, 5 streams 7.2 M, 6 streams 7.3-7.4 M, 8 streams 7.5 M
+    # macroblocks/s; 4 streams is bimodal (7.1 M / 4.0 M: the streams' copies convoy), so it is skipped.
+    n_streams = args.e2e_streams if args.e2e_streams > 0 else max(1, min(6, (os.cpu_count() or 1) // world - 2))
+    if args.e2e_streams <= 0 and n_streams == 4:
+        n_streams = 5
     e2e_ctx = [ctx] + [api.Context(local) for _ in range(n_streams - 1)]
     for c in e2e_ctx[1:]:
         c.configure(search_range=SEARCH_RANGE)
@@ -341,6 +345,7 @@ def cpu_baseline(hs, lam, ctx=None, api=None, budget_s=12.0):
                      f"sub_pel_motion_estimation x41 + forward4x4/quant_4x4_normal x112 per MB",
            "me_seconds": float(secs[0]), "tq_seconds": float(secs[1])}
     if ctx is not None:
+        ctx.ref_put(0, hs["ref"]); ctx.pic_begin(hs["cur"], [0])      # whatever picture the timed legs left resident, this is set 0
         g = ctx.me_search(hs["reqs"], frame=True).reshape(n_mb, 41)
         ok = bool(np.array_equal(g["mv_x"][idx], mv[:, :, 0]) and np.array_equal(g["mv_y"][idx], mv[:, :, 1]) and
                   np.array_equal(g["cost"][idx], cost))

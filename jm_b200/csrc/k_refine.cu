@@ -187,7 +187,8 @@ __device__ __forceinline__ int dist4(const SrcBlk &src, const unsigned (&rw)[4],
 // One thread per request then replays JM's sequential strict-'<' selection (me_fullsearch.c:221-289).
 constexpr int RT = 128, RQ = 41;
 #ifndef JMB_RF_GROUP
-#define JMB_RF_GROUP 3
+#define JMB_RF_GROUP 1      // candidates whose reference rows are in flight together; the kernel waits on L2 loads, and occupancy
+                            // hides them better than in-thread batching: (group, CTAs/SM) (3,4) 0.243 ms, (2,6) 0.194, (2,8) 0.176, (1,8) 0.1745
 #endif
 constexpr int RF_GROUP = JMB_RF_GROUP;
 
@@ -201,7 +202,7 @@ struct RefineS {
 };
 
 #ifndef JMB_RF_MINB
-#define JMB_RF_MINB 4
+#define JMB_RF_MINB 8
 #endif
 __global__ void __launch_bounds__(RT, JMB_RF_MINB)
 k_subpel_refine(const jmb_me_req *__restrict__ reqs, jmb_me_res *__restrict__ res, int n, const uint8_t *__restrict__ cur, int cur_pitch,

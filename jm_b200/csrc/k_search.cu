@@ -44,6 +44,9 @@ constexpr int S1_BYTES = S1_ITEMS * 4 * S1_PITCH * 2, SWEEP_BYTES = (NT / 32) * 
 constexpr unsigned S1_NONE = 0x3fffffffu, S1_BAD = 0x40000000u;   // real costs stay far below (lambda <= 65535)
 constexpr int S1T_ROWS = S1_COLS + 4 * S1_RGS;      // exact mv-cost terms of the stage-1 columns and rows, per partition
 constexpr int INT_SEARCH_DYN_SMEM = (CW + CH / 4 + S1T_ROWS) * ADJ_PITCH * 4 + (S1_BYTES > SWEEP_BYTES ? S1_BYTES : SWEEP_BYTES);
+#ifndef JMB_IS_SMEM_PAD
+#define JMB_IS_SMEM_PAD 0      // tuning builds only: extra dynamic shared memory lowers the CTAs per SM (occupancy probe at 128 registers: 4 CTAs 0.72 ms, 3 CTAs 0.77, 2 CTAs 0.92)
+#endif
 constexpr int IDX_BITS = 13;       // (2*64+1)^2 = 16641 > 8192: search_range <= 45 keeps idx < 8192
 
 struct PartGeom { unsigned char type, bx, by, w4, h4; };
@@ -251,7 +254,7 @@ __device__ __forceinline__ void sad_item(const uint8_t *win, const unsigned *ssr
 // arithmetic loop when one of its SADs beats the current bound (sad < thr), which after the seeding step
 // below is rare.  ALU-pipe work per displacement: 64 VABSDIFF4 + 19 PRMT + 41 ISETP.
 #ifndef JMB_IS_MINB
-#define JMB_IS_MINB 4
+#define JMB_IS_MINB 3      // 3 CTAs of 128 threads: 167 registers, nothing spilled (4 CTAs cap the kernel at 128 registers: 0.72 -> 0.70 ms)
 #endif
 __global__ void __launch_bounds__(NT, JMB_IS_MINB)
 k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups, jmb_me_res *__restrict__ res,
@@ -685,14 +688,14 @@ static int me_search_impl(jmb_ctx *ctx, const jmb_me_req *reqs, int n, jmb_me_re
   }
   jmb_time_begin(ctx, JMB_K_INT_SEARCH);
   if (!ctx->smem_opt_in) {      // per context: the attribute belongs to the device the context runs on
-    JMB_CUDA(ctx, cudaFuncSetAttribute(k_int_search, cudaFuncAttributeMaxDynamicSharedMemorySize, INT_SEARCH_DYN_SMEM));
+    JMB_CUDA(ctx, cudaFuncSetAttribute(k_int_search, cudaFuncAttributeMaxDynamicSharedMemorySize, INT_SEARCH_DYN_SMEM + JMB_IS_SMEM_PAD));
     ctx->smem_opt_in = true;
   }
   TMaps tm;
   memset(&tm, 0, sizeof(tm));
   tm.cur = ctx->tmap_cur;
   for (int i = 0; i < ctx->nref; i++) tm.ref[i] = ctx->refs[ctx->ref_list[i]].tmap_int;
-  k_int_search<<<n_groups, NT, INT_SEARCH_DYN_SMEM, ctx->stream>>>(d_reqs, d_groups, d_res, tm, ctx->cur_w, ctx->cur_h, ctx->me.search_range,
+  k_int_search<<<n_groups, NT, INT_SEARCH_DYN_SMEM + JMB_IS_SMEM_PAD, ctx->stream>>>(d_reqs, d_groups, d_res, tm, ctx->cur_w, ctx->cur_h, ctx->me.search_range,
                                                                   ctx->me.max_mvd - 1, ctx->nref, ctx->me.metric[0], ctx->d_err);
   jmb_time_end(ctx, JMB_K_INT_SEARCH);
   JMB_LAUNCH_CHECK(ctx);

@@ -4,5 +4,5 @@ for rep in 1 2; do
 for so in tools/_bin/libjmb200_nt*.so; do
   for mode in "" "--scene-cut"; do
   JMB200_LIB=$PWD/$so python bench.py --steps 30 --warmup 3 --no-cpu --e2e-streams 1 $mode 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$so $mode', 'int_search ms', round(d['kernel_ms_per_step']['int_search'],4), 'step', round(d['ms_per_step'],4))"
+import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$so $mode', 'int_search ms', round(d['kernel_ms_per_step']['int_search'],4), 'refine ms', round(d['kernel_ms_per_step']['subpel_refine'],4), 'step', round(d['ms_per_step'],4))"
 done; done; done
