@@ -6,7 +6,7 @@ O=gpurun_out
 mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $O/${TAG}_smi.txt 2>&1
 nproc > $O/${TAG}_nproc.txt; lscpu | head -20 >> $O/${TAG}_nproc.txt
-timeout 900 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $O/${TAG}_pytest_gpu.log
+timeout 900 python -m pytest tests -m gpu -x -q --durations=12 > $O/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $O/${TAG}_pytest_gpu.log
 tail -5 $O/${TAG}_pytest_gpu.log
 timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' > $O/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" | tee -a $O/${TAG}_smoke.log
 tail -3 $O/${TAG}_smoke.log
