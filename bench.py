@@ -176,9 +176,9 @@ def run_ours(args):
     # ---- end-to-end leg: K independent picture streams per GPU (K host threads, each its own context = its own CUDA
     # stream, reference slots and staging; the calls are the synchronous JMB_HOST ones, so one stream's PCIe copies
     # overlap the other's kernels).  Pictures are independent units (closed-GOP shards), exactly like the ranks.
-    # Measured on the 16-core B200 box (tools/gpu_e2e.sh): 3 streams 6.6 M, 5 streams 7.2 M, 6 streams 7.3-7.4 M, 8 streams 7.5 M
-    # macroblocks/s; 4 streams is bimodal (7.1 M / 4.0 M: the streams' copies convoy), so it is skipped.
-    n_streams = args.e2e_streams if args.e2e_streams > 0 else max(1, min(6, (os.cpu_count() or 1) // world - 2))
+    # Measured on the 16-core B200 box (tools/gpu_e2e.sh, macroblocks/s over repeated runs): 3 streams 6.6 M; 6 streams 6.4-8.1 M;
+    # 8 streams 7.7-7.9 M (the tightest); 10 streams 5.3-6.4 M; 4 streams is bimodal (7.1 M / 4.0 M: the streams' copies convoy).
+    n_streams = args.e2e_streams if args.e2e_streams > 0 else max(1, min(8, (os.cpu_count() or 1) // world - 2))
     if args.e2e_streams <= 0 and n_streams == 4:
         n_streams = 5
     e2e_ctx = [ctx] + [api.Context(local) for _ in range(n_streams - 1)]

@@ -245,6 +245,10 @@ __global__ void k_mc_tq(const jmb_mb_pred *__restrict__ pred, int n_mb, int mb_w
 // Every inter partition mode of every macroblock in ONE launch: the prediction comes straight from the 41 search
 // results of the macroblock (the all_mv fill of mv_search.c:1005-1014 folded in), reference 0.  Thread = one transform
 // block of one (mode, macroblock); outputs are mode-major.
+// first request of partition mode m in a macroblock's 41 results, and the mode's partition size in 4x4 units
+// (constant memory: as local arrays indexed by the mode they lived on the stack, 24 stores + 3 loads per thread)
+__constant__ int c_mode_base[8] = {0, 0, 1, 3, 5, 9, 17, 25}, c_mode_w4[8] = {4, 4, 4, 2, 2, 2, 1, 1}, c_mode_h4[8] = {4, 4, 2, 4, 2, 1, 2, 1};
+
 template <int N, int STD>
 __global__ void k_mc_tq_modes(const jmb_me_res *__restrict__ res, int n_mb, int mb_w, unsigned mode_mask, const jmb_quant_desc *__restrict__ qd,
                               const uint8_t *__restrict__ cur, int cur_pitch, const uint8_t *__restrict__ ref_plane0,
@@ -265,8 +269,7 @@ __global__ void k_mc_tq_modes(const jmb_me_res *__restrict__ res, int n_mb, int 
   int ux4 = bx4, uy4 = by4;                                  // prediction unit (macroblock.c:946-971)
   if (mode < 5 || N == 8) { ux4 &= ~1; uy4 &= ~1; }
   if (mode == 1) { ux4 = 0; uy4 = 0; }                       // P16x16: one 16x16 prediction, one origin clamp (macroblock.c:1225)
-  const int base[8] = {0, 0, 1, 3, 5, 9, 17, 25}, w4[8] = {4, 4, 4, 2, 2, 2, 1, 1}, h4[8] = {4, 4, 2, 4, 2, 1, 2, 1};
-  const jmb_me_res r = res[mb * 41 + base[mode] + (uy4 / h4[mode]) * (4 / w4[mode]) + ux4 / w4[mode]];
+  const jmb_me_res r = res[mb * 41 + c_mode_base[mode] + (uy4 / c_mode_h4[mode]) * (4 / c_mode_w4[mode]) + ux4 / c_mode_w4[mode]];
   const int qx = ((mbx + ux4 * 4) << 2) + r.mv_x, qy = ((mby + uy4 * 4) << 2) + r.mv_y;
   const int iy = jmb_clip(-JMB_PAD_Y, h + JMB_PAD_Y - 1 - 16, qy >> 2), ix = jmb_clip(-JMB_PAD_X, w + JMB_PAD_X - 1 - 16, qx >> 2);
   const uint8_t *rp = ref_plane0 + (size_t)((qy & 3) * 4 + (qx & 3)) * plane_bytes +
@@ -406,8 +409,7 @@ k_luma_rc_modes(const jmb_me_res *__restrict__ res, const jmb_mb_pred *__restric
   int mvx, mvy, rf = 0;
   if (pred) { mvx = pred[mb].mv[uy4 * 4 + ux4][0]; mvy = pred[mb].mv[uy4 * 4 + ux4][1]; rf = pred[mb].ref[b8]; }
   else {
-    const int base[8] = {0, 0, 1, 3, 5, 9, 17, 25}, w4[8] = {4, 4, 4, 2, 2, 2, 1, 1}, h4[8] = {4, 4, 2, 4, 2, 1, 2, 1};
-    const jmb_me_res r = res[(first_mb + mb) * 41 + base[mode] + (uy4 / h4[mode]) * (4 / w4[mode]) + ux4 / w4[mode]];
+    const jmb_me_res r = res[(first_mb + mb) * 41 + c_mode_base[mode] + (uy4 / c_mode_h4[mode]) * (4 / c_mode_w4[mode]) + ux4 / c_mode_w4[mode]];
     mvx = r.mv_x; mvy = r.mv_y;
   }
   const int qx = ((mbx + ux4 * 4) << 2) + mvx, qy = ((mby + uy4 * 4) << 2) + mvy;

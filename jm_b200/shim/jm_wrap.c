@@ -103,6 +103,8 @@ distblk __real_computeSAD(StorablePicture *, MEBlock *, distblk, MotionVector *)
 distblk __real_computeSSE(StorablePicture *, MEBlock *, distblk, MotionVector *);
 distblk __real_computeSATD(StorablePicture *, MEBlock *, distblk, MotionVector *);
 
+typedef char jmb_distpel_is_32_bits[sizeof(distpel) == sizeof(uint32_t) ? 1 : -1];      /* jmb_ffs_surfaces writes JM's BlockSAD element type */
+
 enum { FAM_PLANES = 1, FAM_ME = 2, FAM_SUBPEL = 4, FAM_TQ = 8, FAM_DIST = 16 };
 
 static struct
@@ -120,6 +122,9 @@ static struct
   unsigned long    calls[10];
   int              verify;            /* JMB_SHIM_VERIFY=1: differential check of the device luma_residual_coding */
   unsigned long    verified;
+  int              ffs_search;        /* JMB_SHIM_FFS=search: every partition's fast full search is a device call of its own */
+  uint32_t        *ffs_buf;           /* pinned: one macroblock's BlockSAD surfaces as jmb_ffs_surfaces lays them out */
+  size_t           ffs_cap;
 } S;
 
 /* JM's convention for fatal conditions is error(text, code) -> message on stderr, exit(code) (lencod/src/lencod.c).
@@ -171,6 +176,7 @@ static int shim_on(int family)
       }
       S.init = 1;
       S.verify = getenv("JMB_SHIM_VERIFY") != NULL;
+      S.ffs_search = getenv("JMB_SHIM_FFS") && !strcmp(getenv("JMB_SHIM_FFS"), "search");
       if (off)
       {
         if (strstr(off, "planes")) S.off |= FAM_PLANES;
@@ -344,8 +350,9 @@ distblk __wrap_full_search_motion_estimation(Macroblock *currMB, MotionVector *p
   return (distblk)r.icost;
 }
 
-/* setup_fast_full_search (lencod/src/me_fullfast.c:269): only its search-centre rule (:305-329) survives --
- * the BlockSAD surfaces it used to fill are evaluated inside the search kernel. */
+/* setup_fast_full_search (lencod/src/me_fullfast.c:269): the search-centre rule (:305-329) on the host, the BlockSAD
+ * surfaces from the device (jmb_ffs_surfaces).  With JMB_SHIM_FFS=search no surfaces are built: each partition's search is
+ * then a device call of its own (jmb_me_search, FAST_FULL mode), which evaluates the SADs in registers. */
 void __wrap_setup_fast_full_search(Macroblock *currMB, MEBlock *mv_block, int list)
 {
   VideoParameters *p_Vid = currMB->p_Vid;
@@ -370,6 +377,35 @@ void __wrap_setup_fast_full_search(Macroblock *currMB, MEBlock *mv_block, int li
   c->mv_x = (short)iClip3(p_Vid->MaxHmvR[4] + search_range, p_Vid->MaxHmvR[5] - search_range, c->mv_x);
   c->mv_y = (short)iClip3(p_Vid->MaxVmvR[4] + search_range, p_Vid->MaxVmvR[5] - search_range, c->mv_y);
   ff->search_center_padded[list][ref] = pad_MVs(*c, mv_block);
+  if (!S.ffs_search)
+  {
+    /* Default: the device builds the macroblock's BlockSAD surfaces (:492-556 + update_full_search_large_blocks) in ONE
+     * call and hands them to JM in JM's own arrays; the 41 per-partition arg-mins then run in JM's own
+     * fast_full_search_motion_estimation on the host, exactly as JM splits the work (67 % / 7 % of its run time). */
+    static const unsigned short used[8] = {0, 0x0001, 0x0101, 0x0005, 0x0505, 0x5555, 0x0f0f, 0xffff};   /* slots per block type */
+    Slice *currSlice = currMB->p_Slice;
+    int list_offset = p_Vid->mb_data[currMB->mbAddrX].list_offset;
+    int sr = ff->max_search_range[list][ref], max_pos = (2 * sr + 1) * (2 * sr + 1), bt, k, rc, ri;
+    size_t bytes = (size_t)8 * 16 * max_pos * sizeof(uint32_t);
+    if (mv_block->pos_x != currMB->pix_x || mv_block->pos_y != currMB->opix_y)
+      unsupported("setup_fast_full_search entered with a block that is not at the macroblock origin");
+    if (bytes > S.ffs_cap)
+    {
+      if (S.ffs_buf) jmb_host_free(S.ctx, S.ffs_buf);
+      rc = jmb_host_alloc(S.ctx, bytes, (void **)&S.ffs_buf);
+      if (rc) jmb_die("jmb_host_alloc", rc);
+      S.ffs_cap = bytes;
+    }
+    configure(currMB, mv_block, sr);
+    ri = ref_index_of(p_Vid, currSlice, mv_block, currSlice->listX[list + list_offset][ref]);
+    rc = jmb_ffs_surfaces(S.ctx, ri, currMB->pix_x, currMB->opix_y, c->mv_x, c->mv_y, S.ffs_buf, JMB_HOST);
+    if (rc) jmb_die("jmb_ffs_surfaces", rc);
+    for (bt = 1; bt < 8; bt++)
+      for (k = 0; k < 16; k++)
+        if ((used[bt] >> k) & 1)
+          memcpy(ff->BlockSAD[list][ref][bt][k], S.ffs_buf + ((size_t)bt * 16 + k) * max_pos, (size_t)max_pos * sizeof(distpel));
+    S.calls[2]++;
+  }
   ff->search_setup_done[list][ref] = 1;
 }
 
@@ -384,6 +420,8 @@ distblk __wrap_fast_full_search_motion_estimation(Macroblock *currMB, MotionVect
   jmb_me_res r;
   if (!shim_on(FAM_ME)) return __real_fast_full_search_motion_estimation(currMB, pred_mv, mv_block, min_mcost, lambda_factor);
   if (!currMB->p_Inp->rdopt) unsupported("RDOptimization=0 with fast full search");
+  if (!S.ffs_search)      /* surfaces came from the device (setup above); the arg-min over them is JM's own loop */
+    return __real_fast_full_search_motion_estimation(currMB, pred_mv, mv_block, min_mcost, lambda_factor);
   S.calls[2]++;
   if (!ff->search_setup_done[list][ref]) currMB->p_SetupFastFullPelSearch(currMB, mv_block, list);
   configure(currMB, mv_block, imax(mv_block->searchRange.max_x, mv_block->searchRange.max_y) >> 2);

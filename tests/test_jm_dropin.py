@@ -84,13 +84,13 @@ CONFIGS = {
                            "BiPredSearch8x8=1", "MEDistortionHPel=2", "MEDistortionQPel=2"],
     # the same with SSE as the error metric at every level (computeSSE, computeBiPredSSE1)
     "b_frames_bipred_me_sse": ["ProfileIDC=100", "SymbolMode=0", "RDOptimization=1", "Transform8x8Mode=0", "QPISlice=28", "QPPSlice=28", "QPBSlice=30",
-                               "SearchMode=-1", "SearchRange=8", "NumberReferenceFrames=2", "AdaptiveRounding=0", "BiPredMotionEstimation=1",
+                               "SearchMode=-1", "SearchRange=4", "NumberReferenceFrames=2", "AdaptiveRounding=0", "BiPredMotionEstimation=1",
                                "BiPredMERefinements=0", "BiPredMESearchRange=4", "BiPredMESubPel=1", "MEDistortionFPel=1", "MEDistortionHPel=1",
                                "MEDistortionQPel=1"],
     # explicit weighted prediction on a fade, weighted-reference ME: JM's own search loops run on the host and every
     # distortion (computeSADWP / computeSATDWP / computeBiPredSAD2 / computeBiPredSATD2, incl. its 8x8 branch) is the device's
     "b_frames_weighted_fade": ["ProfileIDC=100", "SymbolMode=1", "RDOptimization=1", "Transform8x8Mode=1", "QPISlice=28", "QPPSlice=28", "QPBSlice=30",
-                               "SearchMode=-1", "SearchRange=8", "NumberReferenceFrames=2", "AdaptiveRounding=1", "BiPredMotionEstimation=1",
+                               "SearchMode=-1", "SearchRange=4", "NumberReferenceFrames=2", "AdaptiveRounding=1", "BiPredMotionEstimation=1",
                                "BiPredMERefinements=1", "BiPredMESearchRange=4", "BiPredMESubPel=2", "BiPredSearch8x8=1", "MEDistortionHPel=2",
                                "MEDistortionQPel=2", "WeightedPrediction=1", "WeightedBiprediction=1", "UseWeightedReferenceME=1"],
 }
@@ -130,7 +130,7 @@ def test_bitstream_identical_to_stock_jm(tmp_path, name):
     w, h, frames = 96, 80, 4
     bframes = 2 if name.startswith("b_frames") else 0
     if bframes:
-        frames = 7
+        frames = 4 if name in ("b_frames_bipred_me_sse", "b_frames_weighted_fade") else 7      # (these two run JM's own search loops, one device call per candidate)
     _make_yuv(tmp_path / "input.yuv", w, h, frames, seed=11, fmt420="YUVFormat=2" not in CONFIGS[name], fade=0.06 if "fade" in name else 0.0)
     r1 = _encode(REF, tmp_path, "ref", w, h, frames, CONFIGS[name], bframes=bframes)
     r2 = _encode(JMB, tmp_path, "gpu", w, h, frames, CONFIGS[name], env={"JMB_SHIM_VERBOSE": "1"}, bframes=bframes)
@@ -139,7 +139,7 @@ def test_bitstream_identical_to_stock_jm(tmp_path, name):
     line = [l for l in r2.stderr.splitlines() if l.startswith("[jmb shim]")]
     assert line, "the shim did not report: was the GPU path used?"
     counts = dict(zip(line[0].split()[2::2][:9], [int(x) for x in line[0].split()[3::2][:9]]))
-    assert counts["planes"] >= (frames - 1) // (bframes + 1) and counts["quant4"] + counts["quant8"] > 0, line[0]
+    assert counts["planes"] >= max(1, (frames - 1) // (bframes + 1)) and counts["quant4"] + counts["quant8"] > 0, line[0]
     if "SearchMode=3" in CONFIGS[name] or "UseWeightedReferenceME=1" in CONFIGS[name]:
         assert counts["dist"] > 0, line[0]                       # EPZS / weighted-reference ME: distortion oracle
     else:
@@ -190,12 +190,34 @@ def test_bundled_configurations(tmp_path, cfg):
     import shutil
     for f in os.listdir(FIXTURES):
         shutil.copy(os.path.join(FIXTURES, f), tmp_path / f)
-    outs = {}
+    import time
+    outs, secs = {}, {}
     for tag, exe, env in (("ref", REF, {}), ("gpu", JMB, {"JMB_SHIM_VERBOSE": "1"})):
         e = dict(os.environ); e.update(env)
+        t0 = time.perf_counter()
         r = subprocess.run([exe, "-d", cfg, "-p", f"OutputFile={tag}.264", "-p", f"ReconFile={tag}_rec.yuv", "-p", f"TraceFile={tag}_trace.txt"],
                            cwd=tmp_path, env=e, capture_output=True, text=True, timeout=1500)
+        secs[tag] = time.perf_counter() - t0
         assert r.returncode == 0, (tag, r.stderr[-800:])
         outs[tag] = r
     assert any(l.startswith("[jmb shim]") for l in outs["gpu"].stderr.splitlines())
+    _same_outputs(tmp_path, "ref", "gpu")
+    # wall time of the two encoders (process start and CUDA context creation included), kept with the run's artefacts
+    log = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(log):
+        me = {t: [l.strip() for l in outs[t].stdout.splitlines() if "Total ME time" in l or "Total encoding time" in l] for t in outs}
+        with open(os.path.join(log, "dropin_times.txt"), "a") as f:
+            f.write(f"{cfg}: lencod_ref {secs['ref']:.2f} s, lencod_jmb {secs['gpu']:.2f} s | ref {me['ref']} | jmb {me['gpu']}\n")
+
+
+@pytest.mark.gpu
+@needs_bins
+def test_fast_full_search_as_per_partition_device_searches(tmp_path):
+    """JMB_SHIM_FFS=search: no BlockSAD surfaces are handed to JM; each partition's fast full search is a jmb_me_search call
+    (FAST_FULL mode) of its own -- the path the picture-level API uses.  Same bitstream."""
+    w, h, frames = 96, 80, 3
+    _make_yuv(tmp_path / "input.yuv", w, h, frames, seed=12)
+    r1 = _encode(REF, tmp_path, "ref", w, h, frames, CONFIGS["fast_full_search_around"])
+    r2 = _encode(JMB, tmp_path, "gpu", w, h, frames, CONFIGS["fast_full_search_around"], env={"JMB_SHIM_FFS": "search", "JMB_SHIM_VERBOSE": "1"})
+    assert r1.returncode == 0 and r2.returncode == 0, (r1.stderr[-500:], r2.stderr[-500:])
     _same_outputs(tmp_path, "ref", "gpu")
