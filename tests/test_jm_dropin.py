@@ -97,14 +97,16 @@ CONFIGS = {
 
 
 @needs_bins
-def test_relink_is_neutral(tmp_path):
+@pytest.mark.parametrize("name", ["fast_full_search_around", "b_frames_bipred_me", "b_frames_weighted_fade", "yuv422_satd_subpel"])
+def test_relink_is_neutral(tmp_path, name):
     """BASELINE config 0 (plumbing): with every wrapper passing through to JM's own code the re-linked encoder is
-    bit-identical to the stock one -- the --wrap link itself changes nothing.  Runs on CPU."""
+    bit-identical to the stock one -- the --wrap link of all 44 symbols itself changes nothing.  Runs on CPU."""
     w, h = 96, 80
-    _make_yuv(tmp_path / "input.yuv", w, h, 3, seed=3)
-    extra = CONFIGS["fast_full_search_around"]
-    r1 = _encode(REF, tmp_path, "ref", w, h, 3, extra)
-    r2 = _encode(JMB, tmp_path, "pt", w, h, 3, extra, env={"JMB_SHIM": "passthrough"})
+    bframes = 2 if name.startswith("b_frames") else 0
+    frames = 4 if bframes else 3
+    _make_yuv(tmp_path / "input.yuv", w, h, frames, seed=3, fmt420="YUVFormat=2" not in CONFIGS[name], fade=0.06 if "fade" in name else 0.0)
+    r1 = _encode(REF, tmp_path, "ref", w, h, frames, CONFIGS[name], bframes=bframes)
+    r2 = _encode(JMB, tmp_path, "pt", w, h, frames, CONFIGS[name], env={"JMB_SHIM": "passthrough"}, bframes=bframes)
     assert r1.returncode == 0 and r2.returncode == 0, (r1.stderr[-500:], r2.stderr[-500:])
     _same_outputs(tmp_path, "ref", "pt")
 
