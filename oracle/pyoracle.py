@@ -240,6 +240,8 @@ class JMRef:
         L.jmref_set_ref2.argtypes = [C.c_void_p, _u16p, C.c_int]
         L.jmref_dist_ex.restype = C.c_int64
         L.jmref_dist_ex.argtypes = [C.c_void_p] + [C.c_int] * 10 + [C.c_int64, _i32p]
+        L.jmref_bipred_search.restype = C.c_int64
+        L.jmref_bipred_search.argtypes = [C.c_void_p] + [C.c_int] * 5 + [_i32p] * 4 + [C.c_int, _i32p, C.c_int64, C.c_int, _i32p, _i16p]
         L.jmref_dist.restype = C.c_int64
         L.jmref_dist.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_int64]
         L.jmref_ffs_setup.argtypes = [C.c_void_p] + [C.c_int] * 4 + [_i16p]
@@ -307,6 +309,15 @@ class JMRef:
     def dist_ex(self, metric, form, blocktype, pos, cand1, cand2, wp=(32, 32, 0, 5, 16), test8x8=0, min_mcost=DISTBLK_MAX):
         return self.L.jmref_dist_ex(self.h_, metric, form, blocktype, pos[0], pos[1], cand1[0], cand1[1], cand2[0], cand2[1],
                                     test8x8, min_mcost, np.asarray(wp, np.int32))
+
+    def bipred_search(self, which, form, blocktype, pos, pred1, pred2, mv1, mv2, search_range_qpel, lam3, min_mcost=DISTBLK_MAX,
+                      test8x8=0, wp=(32, 32, 0, 5, 16)):
+        """The real full_search_bipred_motion_estimation (which=0) / sub_pel_bipred_motion_estimation (which=1)."""
+        a = lambda v: np.asarray(v, np.int32)
+        mv = np.zeros(2, np.int16)
+        c = self.L.jmref_bipred_search(self.h_, which, form, blocktype, pos[0], pos[1], a(pred1), a(pred2), a(mv1), a(mv2),
+                                       search_range_qpel, a(lam3), min_mcost, test8x8, a(wp), mv)
+        return (int(mv[0]), int(mv[1])), c
 
     def ffs_setup(self, mb, pmv):
         c = np.zeros(2, np.int16)

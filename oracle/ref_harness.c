@@ -306,6 +306,34 @@ int64_t jmref_dist_ex(void *h, int metric, int form, int blocktype, int pos_x, i
   return (int64_t)r;
 }
 
+/* The real bi-predictive searches (me_fullsearch.c:112, :299): list 0 moves (reference = c->ref), list 1 stands still at mv2
+ * (reference = c->ref2).  form 2: computeBiPred*1, form 3: computeBiPred*2 with wp = {weight1, weight2, offsetBi, denom, round}.
+ * which = 0: full_search_bipred_motion_estimation (search_range in quarter-pels), 1: sub_pel_bipred_motion_estimation. */
+int64_t jmref_bipred_search(void *h, int which, int form, int blocktype, int pos_x, int pos_y, const int *pred1, const int *pred2,
+                            const int *mv1_in, const int *mv2_in, int search_range_qpel, const int *lambda3, int64_t min_mcost,
+                            int test8x8, const int *wp, int16_t *mv_out)
+{
+  jmref_ctx *c = (jmref_ctx *)h; g_ctx = c;
+  VideoParameters *p_Vid = c->p_Vid;
+  MEBlock b; MotionVector p1, p2, m1, m2; int lam[3] = { lambda3[0], lambda3[1], lambda3[2] };
+  StorablePicture *l1[1] = { c->ref2 };
+  fill_mv_block(c, &b, blocktype, pos_x, pos_y, test8x8);
+  c->slice->listX[1] = l1; c->slice->listXsize[1] = 1;
+  b.weight1 = (short)wp[0]; b.weight2 = (short)wp[1]; b.offsetBi = (short)wp[2];
+  c->slice->luma_log_weight_denom = (short)wp[3]; c->slice->wp_luma_round = wp[4];
+  b.computeBiPredFPel = form == 3 ? p_Vid->computeBiPred2[F_PEL] : p_Vid->computeBiPred1[F_PEL];
+  b.computeBiPredHPel = form == 3 ? p_Vid->computeBiPred2[H_PEL] : p_Vid->computeBiPred1[H_PEL];
+  b.computeBiPredQPel = form == 3 ? p_Vid->computeBiPred2[Q_PEL] : p_Vid->computeBiPred1[Q_PEL];
+  p1.mv_x = (short)pred1[0]; p1.mv_y = (short)pred1[1]; p2.mv_x = (short)pred2[0]; p2.mv_y = (short)pred2[1];
+  m1.mv_x = (short)mv1_in[0]; m1.mv_y = (short)mv1_in[1]; m2.mv_x = (short)mv2_in[0]; m2.mv_y = (short)mv2_in[1];
+  distblk r;
+  if (which == 0) r = full_search_bipred_motion_estimation(c->mb, 0, &p1, &p2, &m1, &m2, &b, search_range_qpel, (distblk)min_mcost, lam[0]);
+  else            r = sub_pel_bipred_motion_estimation(c->mb, &b, 0, &p1, &p2, &m1, &m2, (distblk)min_mcost, lam);
+  mv_out[0] = m1.mv_x; mv_out[1] = m1.mv_y;
+  free_mem2Dpel(b.orig_pic);
+  return (int64_t)r;
+}
+
 /* Fast full search: one setup per macroblock (pmv = 16x16 predictor), then per-partition arg-min. */
 void jmref_ffs_setup(void *h, int mb_pix_x, int mb_pix_y, int pmv_x, int pmv_y, int16_t *center_out)
 {

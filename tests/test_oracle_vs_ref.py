@@ -97,6 +97,63 @@ def test_distortion_early_exit_is_min_mcost(pair):
             assert ref.dist_ex(metric, form, 1, (16, 16), (70, 60), (50, 70), min_mcost=full) == full
 
 
+def _bipred_replay(o, r1, r2, cur, bt, pos, pred1, pred2, mv1, mv2, lam, min_mcost, metric, form, wp, t8, offsets, start=0):
+    """What jm_b200/shim/jm_wrap.c does for the bi-predictive searches: the COMPLETE distortion of every candidate (one
+    jmb_dist_ex call on the device; here the restatement), then JM's sequential selection -- candidates whose mv cost alone
+    reaches min_mcost skipped, a distortion above the remaining budget returned as the budget itself (dist_scale_f,
+    mv_search.h:19), strict '<'.  offsets = the candidates' quarter-pel offsets from mv1 in JM's order."""
+    px, py = pos[0] * 4, pos[1] * 4
+    c2 = (px + mv2[0], py + mv2[1])
+    mc2 = lam * (o.mvbits(mv2[0] - pred2[0]) + o.mvbits(mv2[1] - pred2[1]))
+    best = 0
+    for k, (ox, oy) in enumerate(offsets):
+        if k < start:
+            continue
+        cx, cy = mv1[0] + ox, mv1[1] + oy
+        mcost = lam * (o.mvbits(cx - pred1[0]) + o.mvbits(cy - pred1[1])) + mc2
+        if mcost >= min_mcost:
+            continue
+        d = o.dist_ex(r1, r2, cur, bt, pos, (px + cx, py + cy), c2, metric, form, wp, t8)
+        thr = min_mcost - mcost
+        mcost += thr if d > (thr >> 5) else (d << 5)
+        if mcost < min_mcost:
+            best, min_mcost = k, mcost
+    return (mv1[0] + offsets[best][0], mv1[1] + offsets[best][1]), min_mcost
+
+
+@pytest.mark.parametrize("form", [2, 3])
+def test_bipred_searches_decide_like_batched_distortions_plus_replay(pair, form):
+    """full_search_bipred_motion_estimation (me_fullsearch.c:112) and sub_pel_bipred_motion_estimation (:299), the REAL
+    functions with their early exits, against complete distortions + the replay the shim performs."""
+    o, ref, r, f = pair
+    f2 = synth.luma_frames(W, H, 3, seed=7, motion=(3, -2))[2]
+    ref.set_ref2(f2)
+    r2 = o.ref_create(f2)
+    sp = o.spiral(R)
+    rng = np.random.default_rng(40 + form)
+    for it in range(24):
+        bt = int(rng.integers(1, 5)); bsx, bsy = po.BLOCK_SIZE[bt]
+        pos = (int(rng.integers(0, (W - bsx) // bsx + 1)) * bsx, int(rng.integers(0, (H - bsy) // bsy + 1)) * bsy)
+        pred1 = (int(rng.integers(-24, 25)), int(rng.integers(-24, 25))); pred2 = (int(rng.integers(-24, 25)), int(rng.integers(-24, 25)))
+        mv1 = (int(rng.integers(-6, 7)) * 4, int(rng.integers(-6, 7)) * 4); mv2 = (int(rng.integers(-30, 31)), int(rng.integers(-30, 31)))
+        lam = int(rng.integers(1, 300)); t8 = int(bt <= 4 and rng.integers(0, 2))
+        wp = (int(rng.integers(20, 45)), int(rng.integers(20, 45)), int(rng.integers(-5, 6)), 5, 16)
+        big = po.DISTBLK_MAX if it % 3 else int(rng.integers(2000, 60000))          # an incoming bound as well
+        # integer stage: (2*2+1)^2 candidates in spiral order, SAD
+        sr = 2
+        offs = [(4 * int(x), 4 * int(y)) for x, y in sp[:(2 * sr + 1) ** 2]]
+        got = _bipred_replay(o, r, r2, f[1], bt, pos, pred1, pred2, mv1, mv2, lam, big, po.SAD, form, wp, 0, offs)
+        assert got == ref.bipred_search(0, form, bt, pos, pred1, pred2, mv1, mv2, sr << 2, [lam] * 3, big, 0, wp), (it, "full")
+        # sub-pel stages (me_fullsearch.c:330-392): nine half-pel candidates from position 0 (the full-pel metric differs from the
+        # half-pel one: start_me_refinement_hp = 0), then quarter-pel positions 1..8 around the winner (start_me_refinement_qp = 1)
+        m1, c = _bipred_replay(o, r, r2, f[1], bt, pos, pred1, pred2, mv1, mv2, lam, big, po.SATD, form, wp, t8,
+                               [(2 * int(x), 2 * int(y)) for x, y in sp[:9]])
+        m1, c = _bipred_replay(o, r, r2, f[1], bt, pos, pred1, pred2, m1, mv2, lam, c, po.SATD, form, wp, t8,
+                               [(int(x), int(y)) for x, y in sp[:9]], start=1)
+        assert (m1, c) == ref.bipred_search(1, form, bt, pos, pred1, pred2, mv1, mv2, 0, [lam] * 3, big, t8, wp), (it, "sub-pel")
+    o.ref_destroy(r2)
+
+
 def test_full_search(pair):
     o, ref, r, f = pair
     rng = np.random.default_rng(11)
