@@ -31,6 +31,7 @@ constexpr int CW = 92;             // chunk of displacements handled per staging
 constexpr int CH = 72;             // multiple of 4 (a thread owns 4 vertically adjacent displacements)
 constexpr int WIN_PITCH = JMB_WIN_BOX_W;   // bytes per staged window row = the TMA box width (>= CW + 15 + the fifth word)
 constexpr int WIN_ROWS = CH + 15;
+static_assert(3 * NPART <= NT, "the stage-1 scan wants three threads per partition");
 static_assert(WIN_ROWS == JMB_WIN_BOX_H && 15 + CW + 15 + 4 <= WIN_PITCH, "TMA box and window geometry disagree");
 #ifndef JMB_S1_COLS
 #define JMB_S1_COLS 8
@@ -348,7 +349,7 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
       // Stage 1 (first chunk only): exact, gate-free evaluation of a small neighbourhood of the search centre
       // (S1_COLS columns x 4*S1_RGS rows) so that the bounds are tight before the sweep starts.  Phase a: warp 0,
       // one thread per item, computes the SADs and leaves the 41 partition sums of its 4 displacements in shared
-      // memory -- while the other warps build the column table of the gate.  Phase b: four threads per partition
+      // memory -- while the other warps build the column table of the gate.  Phase b: three threads per partition
       // scan the sums with the exact cost and publish the winner.
       const int ncol = min(S1_COLS, cw), nrgs = min(S1_RGS, nrg);
       const int col0 = jmb_clip(0, cw - ncol, G.rq[sbox[10]].cx - cx0 - ncol / 2);
@@ -410,17 +411,17 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
       phase ^= 1;
       __syncthreads();
       if (s1) {
-        for (int pp = 0; pp < NPART; pp += NT / 4) {      // uniform trip count: the shuffles below need whole warps
-        const int p = pp + (tid >> 2), j = tid & 3;
-        unsigned long long k = ~0ull;
+        // three threads per partition (41 x 3 <= NT): thread j scans displacement rows j, j+3, j+6 of the neighbourhood;
+        // the spiral index is only worked out on a tie; each thread publishes its own winner (shared-memory atomics)
+        const int p = tid / 3, j = tid - 3 * p;
         if (p < NPART && G.rq[p].active) {
           const ReqS &q = G.rq[p];
-          unsigned bcost = S1_NONE; int bc = 0, bDy = 0, bidx = -1;        // thread j looks at displacement row j of every item;
-          for (int rgi = 0; rgi < nrgs; rgi++) {                            // the spiral index is only worked out on a tie
-            const unsigned ycost = s1y[(4 * rgi + j) * ADJ_PITCH + p];
+          unsigned bcost = S1_NONE; int bc = 0, bDy = 0, bidx = -1;
+          for (int r = j; r < 4 * nrgs; r += 3) {
+            const unsigned ycost = s1y[r * ADJ_PITCH + p];
             if (ycost == S1_BAD) continue;
-            const int Dy = cy0 + (rg0 + rgi) * 4 + j;
-            const unsigned short *sp = S1 + ((rgi * ncol) * 4 + j) * S1_PITCH + p;
+            const int Dy = cy0 + rg0 * 4 + r;
+            const unsigned short *sp = S1 + (((r >> 2) * ncol) * 4 + (r & 3)) * S1_PITCH + p;
             for (int c = 0; c < ncol; c++) {
               const unsigned cost = ((unsigned)sp[c * 4 * S1_PITCH] << 5) + ycost + s1x[c * ADJ_PITCH + p];
               if (cost > bcost) continue;
@@ -433,13 +434,11 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
               bcost = cost; bc = c; bDy = Dy;
             }
           }
-          if (bcost != S1_NONE && bidx < 0) bidx = jmb_spiral_index(cx0 + col0 + bc - q.cx, bDy - q.cy);
-          if (bcost != S1_NONE) k = ((unsigned long long)bcost << IDX_BITS) | (unsigned)bidx;
-
-        }
-        k = min(k, __shfl_xor_sync(0xffffffffu, k, 1));
-        k = min(k, __shfl_xor_sync(0xffffffffu, k, 2));
-        if (p < NPART && j == 0 && k != ~0ull && k < G.best[p]) publish(&G, p, k);
+          if (bcost != S1_NONE) {
+            if (bidx < 0) bidx = jmb_spiral_index(cx0 + col0 + bc - q.cx, bDy - q.cy);
+            const unsigned long long k = ((unsigned long long)bcost << IDX_BITS) | (unsigned)bidx;
+            if (k < *(volatile unsigned long long *)&G.best[p]) publish(&G, p, k);
+          }
         }
         __syncthreads();
       }
