@@ -61,3 +61,25 @@ def test_product_never_imports_oracle():
 def test_canonical_partition_order():
     parts = api.mb_partitions()
     assert len(parts) == 41 and parts[0] == (1, 0, 0) and parts[-1] == (7, 12, 12)
+
+
+def test_c_example_builds_against_the_header_and_library(tmp_path):
+    """examples/picture_form.c is the picture form of the ABI from plain C (no Python, no torch): it must compile with a C
+    compiler against include/jmb200.h alone and link against libjmb200.so; without a GPU it stops at jmb_create."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "picture_form")
+    libdir = os.path.dirname(api.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "picture_form.c"),
+                        "-L", libdir, "-ljmb200", f"-Wl,-rpath,{libdir}", "-lm", "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-1500:]
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return
+    except ImportError:
+        pass
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "no CPU path" in r.stderr, (r.returncode, r.stderr[-300:])
