@@ -1,23 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- macroblocks/sec of the JM lencod ME + transform/quant hot path on B200.
 
-One "step" = the hot path over ONE 1080p P-picture (coded 1920x1088 = 8160 macroblocks, 1 reference):
-  K6  jmb_ref_put            16 quarter-pel planes of the reference           (getSubImagesLuma)
-  --  jmb_pic_begin          current picture to the device
-  K1-K3 jmb_me_search_frame  full search +-32, all 41 partitions of every MB  (full_search_motion_estimation)
-  K5  (same call)            half-/quarter-pel SATD refinement of every one   (sub_pel_motion_estimation)
-  K7/K8 jmb_mc_tq_modes      prediction -> residual -> forward4x4 -> quant for each of the 7 partition
-                             modes (what JM's RDO loop residual-codes per inter candidate), one launch
+One "step" = the hot path over ONE P-picture (config 2, the default: 1080p coded 1920x1088 = 8160 macroblocks, 1 reference):
+  K6    jmb_ref_put_u8              16 quarter-pel planes of the reference             (getSubImagesLuma)
+  --    jmb_pic_begin_u8            current picture to the device
+  K1-K3 jmb_me_search_frame_pred    requests generated on the device from the 41 predictors of every macroblock,
+                                    full search +-32 of all 41 partitions             (full_search_motion_estimation)
+  K5    (same call)                 half-/quarter-pel SATD refinement of every one    (sub_pel_motion_estimation)
+  K7/K8 jmb_mc_tq_modes_compact     prediction -> residual -> forward4x4 -> quant for each of the 7 partition modes (what
+                                    JM's RDO loop residual-codes per inter candidate), (level, run) tokens out, one launch
 Predictors are synthetic (true motion + per-MB / per-partition jitter), lambda from QP 28.
 
   value : device-timed (CUDA events on the library's stream), inputs resident in HBM, rotating over
           4 distinct input sets (> L2 in total) so no step re-reads a warm L2.
   e2e   : the same step through the C ABI with pinned HOST buffers (H2D/D2H inside the timed region).
   --impl reference : JM's own functions (oracle/_ref/libjmref.so) on the host cores, bounded sample.
+  --config {2,3,4,5} : BASELINE.json configs[1..4]; see CONFIGS below.  Default 2.
 
 Launch: python bench.py [--gpus N --steps K --warmup W]; for N > 1 under torchrun (one rank per GPU,
 weak scaling: every rank encodes its own pictures, i.e. independent closed-GOP segments; no collective
-on the data path).
+on the data path).  No measured leg ever sets JMB_SHIM / JMB_SHIM_OFF (debug switches of the drop-in shim).
 """
 import argparse
 import json
@@ -32,47 +34,44 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H = 1920, 1088                  # coded size of 1080p (1920x1080 -> 68 MB rows); --size 4k: 3840x2176
-SIZE_NAME = "1080p"
 SEARCH_RANGE = 32
 QP = 28
 N_SETS = 4
 BYTES_PER_MB_REF = 13804           # 512 src + 12800 window + 492 results
 
+# BASELINE.json configs[1..4] (configs[0] is the reference's own CPU-only plumbing case, tests/test_jm_dropin.py)
+CONFIGS = {
+    2: dict(name="1080p 4:2:0 synthetic, FullSearch +-32 (SearchMode=-1) 41 partitions/MB + SATD sub-pel + 4x4 transform/quant of 7 "
+                 "partition modes, Baseline, 1 ref, QP28", w=1920, h=1088, size="1080p", search="full", n=4, chroma=None),
+    3: dict(name="4K 4:2:0 synthetic (3840x2160 = 32400 macroblocks), EPZS integer + sub-pel search of 41 partitions/MB (encoder.cfg "
+                 "pattern settings) + 8x8 transform/quant of the 4 partition modes that allow it, High, 1 ref, QP28",
+            w=3840, h=2160, size="4K", search="epzs", n=8, chroma=None),
+    4: dict(name="1080p 4:2:2 synthetic (encoder_yuv422.cfg metrics: SAD full-pel, SATD half-/quarter-pel), fast full search +-32 + "
+                 "SATD sub-pel refinement + 4x4 transform/quant of 7 modes + 4:2:2 chroma prediction/residual/DC path, QP28",
+            w=1920, h=1088, size="1080p", search="fastfull", n=4, chroma="422"),
+    5: dict(name="4K 4:2:0 synthetic (3840x2160), FullSearch +-32 + SATD sub-pel + 4x4 transform/quant of 7 modes; every rank codes "
+                 "a picture against rank 0's reconstructed anchor read over NVLink (peer-mapped, no host copy)",
+            w=3840, h=2160, size="4K", search="full", n=4, chroma=None, anchor=True),
+}
 
-def workload_config(n_gpus, anchor_bcast=False):
-    return {"workload": f"{SIZE_NAME} 4:2:0 synthetic, FullSearch +-32 (SearchMode=-1) 41 partitions/MB + SATD sub-pel + "
-                        "4x4 transform/quant of 7 partition modes, Baseline, 1 ref, QP28",
-            "width": W, "height": H, "macroblocks_per_step": (W // 16) * (H // 16), "search_range": SEARCH_RANGE,
-            "l2": f"rotating over {N_SETS} distinct input sets (> 126 MB in total)",
-            "parallelism": (f"{n_gpus} x pictures sharing one anchor: ncclBroadcast of the reconstructed reference (4.2 MB u16 luma) per step"
-                            if anchor_bcast and n_gpus > 1 else
-                            f"{n_gpus} x independent picture streams (closed-GOP shards), no data-path collective")}
+
+def workload_config(cfg_id, n_gpus):
+    c = CONFIGS[cfg_id]
+    par = (f"{n_gpus} x pictures sharing one anchor: each rank's sub-pel kernel reads rank 0's reconstructed luma over NVLink "
+           f"({c['w'] * c['h'] / 1e6:.1f} MB u8 per picture per rank)" if c.get("anchor") and n_gpus > 1 else
+           f"{n_gpus} x independent picture streams (closed-GOP shards), no data-path collective")
+    return {"workload": c["name"], "baseline_config": cfg_id, "width": c["w"], "height": c["h"],
+            "macroblocks_per_step": (c["w"] // 16) * (c["h"] // 16), "search_range": SEARCH_RANGE,
+            "l2": f"rotating over {N_SETS} distinct input sets (> 126 MB in total)", "parallelism": par}
 
 
-def make_requests(api, seed, motion_q=(20, 12)):
-    """41 requests per MB in canonical order; predictors = true motion + jitter."""
+def make_pred_table(api, seed, n_mb, motion_q=(20, 12)):
+    """41 predictors per macroblock (canonical partition order) = true motion + per-MB and per-partition jitter."""
     rng = np.random.default_rng(seed)
-    parts = api.mb_partitions()
-    mbw, mbh = W // 16, H // 16
-    n_mb = mbw * mbh
-    reqs = np.zeros((n_mb, api.NPART), api.ME_REQ)
-    mbx = (np.arange(n_mb) % mbw) * 16
-    mby = (np.arange(n_mb) // mbw) * 16
-    mbpred = np.array(motion_q)[None, :] + rng.integers(-8, 9, size=(n_mb, 2))
-    for k, (t, x, y) in enumerate(parts):
-        p = mbpred + rng.integers(-3, 4, size=(n_mb, 2))
-        reqs["blocktype"][:, k] = t
-        reqs["pos_x"][:, k] = mbx + x
-        reqs["pos_y"][:, k] = mby + y
-        reqs["pred_x"][:, k] = p[:, 0]
-        reqs["pred_y"][:, k] = p[:, 1]
-        reqs["center_x"][:, k] = ((p[:, 0] + 2) >> 2) * 4
-        reqs["center_y"][:, k] = ((p[:, 1] + 2) >> 2) * 4
-    reqs["mode"] = api.SEARCH_FULL
-    reqs["flags"] = api.REQ_SUBPEL
-    reqs["min_mcost"] = api.DISTBLK_MAX
-    return reqs.reshape(-1)
+    pred = np.zeros(n_mb, api.MB_MVPRED)
+    mbpred = np.array(motion_q)[None, None, :] + rng.integers(-8, 9, size=(n_mb, 1, 2))
+    pred["pred"] = mbpred + rng.integers(-3, 4, size=(n_mb, 41, 2))
+    return pred
 
 
 class ClockSampler:
@@ -120,11 +119,112 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class Workload:
+    """Everything one configuration needs: inputs (host pinned + device), outputs, and the per-picture call sequence."""
+
+    def __init__(self, args, api, synth, T, ctx, local, rank, world, torch):
+        self.cfg = CONFIGS[args.config]
+        self.api, self.ctx, self.torch, self.local = api, ctx, torch, local
+        self.W, self.H = self.cfg["w"], self.cfg["h"]
+        W, H = self.W, self.H
+        self.n_mb = (W // 16) * (H // 16)
+        self.lam = T.lambda_me(QP)
+        n = self.cfg["n"]
+        if n == 4:
+            self.qd = api.quant_desc(4, QP, T.q_params(QP, 0, 4), T.SNGL_SCAN, T.COEFF_COST4x4[0], 1)
+            self.mode_mask = 0x7F
+        else:      # High profile, CABAC, 8x8 transform: partition modes 1..4
+            self.qd = api.quant_desc(8, QP, T.q_params(QP, 0, 8), T.SNGL_SCAN8x8, T.COEFF_COST8x8[0], 0)
+            self.mode_mask = 0x0F
+        mode = api.SEARCH_FAST_FULL if self.cfg["search"] == "fastfull" else api.SEARCH_FULL
+        self.fp = api.frame_params([self.lam] * 3, mode=mode, flags=api.REQ_SUBPEL | (api.REQ_TEST8X8 if n == 8 else 0))
+        self.token_cap = 7 * self.n_mb * 24
+        dev = f"cuda:{local}"
+        anchor = bool(self.cfg.get("anchor"))
+        self.sets = []
+        for s in range(N_SETS):
+            # anchor mode: every rank codes a picture of the SAME sequence against rank 0's anchor
+            f = synth.luma_frames(W, H, 2, seed=1234 + (0 if anchor else 97 * rank) + s, motion=(5, 3))
+            if args.scene_cut:      # robustness probe: the reference is an unrelated picture (nothing matches)
+                f[0] = synth.luma_frames(W, H, 1, seed=999 + s)[0]
+            pred = make_pred_table(api, 50 + 13 * rank + s, self.n_mb)
+            hs = {"ref": ctx.pinned((H, W), np.uint8), "cur": ctx.pinned((H, W), np.uint8), "pred": ctx.pinned(self.n_mb, api.MB_MVPRED)}
+            hs["ref"][:] = f[0]; hs["cur"][:] = f[1]; hs["pred"][:] = pred
+            ds = {k: torch.from_numpy(v.view(np.uint8).reshape(-1).copy()).to(dev) for k, v in hs.items()}
+            self.sets.append((hs, ds))
+        self.d_res8 = torch.empty(self.n_mb * api.NPART * 8, dtype=torch.uint8, device=dev)
+        self.d_heads = torch.empty(7 * self.n_mb * 16, dtype=torch.uint8, device=dev)
+        self.d_tokens = torch.empty(self.token_cap * 4, dtype=torch.uint8, device=dev)
+        self.d_ntok = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.peer_refs = None
+        self.tokens_seen = 0
+
+    def host_outputs(self, c):
+        return (c.pinned(self.n_mb * self.api.NPART, self.api.ME_RES8), c.pinned((7, self.n_mb), self.api.TQ_HEAD),
+                c.pinned(self.token_cap, self.api.TQ_TOKEN), np.zeros(1, np.uint32))
+
+    def setup_anchor(self, dist, rank, world):
+        """config 5: rank 0 owns the reconstructed anchors in exportable device memory; every other rank maps them (IPC ->
+        NVLink peer access) once.  torch.distributed only carries the 64-byte handles."""
+        api, ctx = self.api, self.ctx
+        handles = [None] * N_SETS
+        if rank == 0:
+            self.anchor_bufs = []
+            for s in range(N_SETS):
+                p = ctx.dev_alloc(self.W * self.H)
+                ctx.dev_copy(p, self.sets[s][0]["ref"], self.W * self.H, api.DEVICE, api.HOST)
+                self.anchor_bufs.append(p)
+                handles[s] = ctx.peer_export(p).tobytes()
+        if world > 1:
+            dist.broadcast_object_list(handles, src=0)
+        if rank == 0:
+            self.peer_refs = self.anchor_bufs
+        else:
+            self.peer_refs = [ctx.peer_open(np.frombuffer(hd, np.uint8)) for hd in handles]
+
+    def step_device(self, s):
+        api, ctx = self.api, self.ctx
+        hs, ds = self.sets[s % N_SETS]
+        shape = (self.H, self.W)
+        ref_ptr = self.peer_refs[s % N_SETS] if self.peer_refs else ds["ref"].data_ptr()
+        ctx.ref_put_u8(s % 2, ref_ptr, api.DEVICE, shape=shape)
+        ctx.pic_begin_u8(ds["cur"].data_ptr(), [s % 2], api.DEVICE, shape=shape)
+        ctx.me_search_frame_pred(ds["pred"].data_ptr(), self.fp, self.d_res8.data_ptr(), api.DEVICE, n_mb=self.n_mb)
+        ctx.mc_tq_modes_compact(None, self.qd, self.mode_mask, api.DEVICE, n_mb=self.n_mb,
+                                out=(self.d_heads.data_ptr(), self.d_tokens.data_ptr(), self.d_ntok.data_ptr()), token_cap=self.token_cap)
+
+    def step_host(self, s, c, outs, tt):
+        """The same picture through the C ABI with pinned HOST buffers: the uploads and the search are only enqueued
+        (JMB_HOST_ASYNC); the residual-coding call returns with heads and tokens in the caller's buffers."""
+        api = self.api
+        hs, _ = self.sets[s % N_SETS]
+        o_res, o_heads, o_tok, o_n = outs
+        t0 = time.perf_counter()
+        c.ref_put_u8(s % 2, hs["ref"], api.HOST_ASYNC)
+        c.pic_begin_u8(hs["cur"], [s % 2], api.HOST_ASYNC)
+        c.me_search_frame_pred(hs["pred"], self.fp, o_res, api.HOST_ASYNC)
+        t1 = time.perf_counter()
+        c._ck(c.L.jmb_mc_tq_modes_compact(c.h, None, self.n_mb, self.mode_mask, self.qd.ctypes.data, o_heads.ctypes.data, o_tok.ctypes.data,
+                                          self.token_cap, o_n.ctypes.data, api.HOST))
+        tt["enqueue"] += t1 - t0; tt["residual_coding_and_wait"] += time.perf_counter() - t1
+        self.tokens_seen = int(o_n[0])
+
+    def bytes_per_step(self):
+        api = self.api
+        h2d = 2 * self.W * self.H + self.n_mb * api.MB_MVPRED.itemsize + api.FRAME_PARAMS.itemsize + api.QUANT_DESC.itemsize
+        d2h = self.n_mb * api.NPART * api.ME_RES8.itemsize + 7 * self.n_mb * api.TQ_HEAD.itemsize + 4 + 4 * self.tokens_seen
+        return int(h2d), int(d2h)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from jm_b200 import api, synth
     from jm_b200 import h264_tables as T
+
+    if CONFIGS[args.config]["search"] == "epzs" or CONFIGS[args.config]["chroma"]:
+        import bench_more      # configs 3 and 4 carry extra stages (EPZS search, chroma path)
+        return bench_more.run(args, globals())
 
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -134,79 +234,32 @@ def run_ours(args):
     ctx = api.Context(local)
     ctx.configure(search_range=SEARCH_RANGE)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local)
-    n_mb = (W // 16) * (H // 16)
-    lam = T.lambda_me(QP)
-    qd = api.quant_desc(4, QP, T.q_params(QP, 0, 4), T.SNGL_SCAN, T.COEFF_COST4x4[0], 1)
-
-    # ---- inputs: N_SETS distinct (reference, current) pairs + request lists, on host (pinned) and in HBM
-    sets = []
-    for s in range(N_SETS):
-        # anchor-broadcast mode: every rank codes a picture of the SAME sequence against rank 0's anchor
-        f = synth.luma_frames(W, H, 2, seed=1234 + (0 if args.anchor_bcast else 97 * rank) + s, motion=(5, 3))
-        reqs = make_requests(api, seed=50 + 13 * rank + s)
-        reqs["lambda"] = lam
-        hs = {"ref": ctx.pinned((H, W), np.uint16), "cur": ctx.pinned((H, W), np.uint16), "reqs": ctx.pinned(len(reqs), api.ME_REQ)}
-        if args.scene_cut:      # robustness probe: the reference is an unrelated picture (nothing matches)
-            f[0] = synth.luma_frames(W, H, 1, seed=999 + s)[0]
-        hs["ref"][:] = f[0]; hs["cur"][:] = f[1]; hs["reqs"][:] = reqs
-        ds = {k: torch.from_numpy(v.view(np.uint8).reshape(-1).copy()).cuda(local) for k, v in hs.items()}
-        sets.append((hs, ds))
-    d_res = torch.empty(n_mb * api.NPART * api.ME_RES.itemsize, dtype=torch.uint8, device=f"cuda:{local}")
-    d_lev = torch.empty(7 * n_mb * 256, dtype=torch.int16, device=f"cuda:{local}")
-    d_cost = torch.empty(7 * n_mb * 4, dtype=torch.int32, device=f"cuda:{local}")
-    d_cbp = torch.empty(7 * n_mb, dtype=torch.int32, device=f"cuda:{local}")
-    h_res = ctx.pinned(n_mb * api.NPART, api.ME_RES)
-    h_lev = ctx.pinned((7, n_mb, 256), np.int16); h_cost = ctx.pinned((7, n_mb, 4), np.int32); h_cbp = ctx.pinned((7, n_mb), np.uint32)
+    wl = Workload(args, api, synth, T, ctx, local, rank, world, torch)
+    n_mb = wl.n_mb
+    if wl.cfg.get("anchor"):
+        wl.setup_anchor(dist, rank, world)
     torch.cuda.synchronize()
 
-    from jm_b200 import shard
-
-    def step_device(s):
-        hs, ds = sets[s % N_SETS]
-        if args.anchor_bcast and world > 1:
-            # B-picture fan-out: rank 0 holds the reconstructed anchor; one NCCL broadcast of its u16 luma
-            # plane, then every rank builds its own quarter-pel planes and codes its own picture against it
-            with torch.cuda.stream(stream):
-                shard.broadcast_anchor(ds["ref"], src=0)
-        ctx.ref_put(s % 2, ds["ref"].data_ptr(), api.DEVICE, shape=(H, W))
-        ctx.pic_begin(ds["cur"].data_ptr(), [s % 2], api.DEVICE, shape=(H, W))
-        ctx.me_search(ds["reqs"].data_ptr(), d_res.data_ptr(), api.DEVICE, n=n_mb * api.NPART, frame=True)
-        ctx.mc_tq_modes(d_res.data_ptr(), qd, 0x7F, api.DEVICE, n_mb=n_mb, out=(d_lev.data_ptr(), d_cost.data_ptr(), d_cbp.data_ptr()))
-
-    # ---- end-to-end leg: K independent picture streams per GPU (K host threads, each its own context = its own CUDA
-    # stream, reference slots and staging; the calls are the synchronous JMB_HOST ones, so one stream's PCIe copies
-    # overlap the other's kernels).  Pictures are independent units (closed-GOP shards), exactly like the ranks.
-    # Measured on the 16-core B200 box (tools/gpu_e2e.sh, macroblocks/s over repeated runs): 3 streams 6.6 M; 6 streams 6.4-8.1 M;
-    # 8 streams 7.7-7.9 M (the tightest); 10 streams 5.3-6.4 M; 4 streams is bimodal (7.1 M / 4.0 M: the streams' copies convoy).
-    n_streams = args.e2e_streams if args.e2e_streams > 0 else max(1, min(8, (os.cpu_count() or 1) // world - 2))
-    if args.e2e_streams <= 0 and n_streams == 4:
-        n_streams = 5
+    # ---- end-to-end leg: K independent picture streams per GPU (K host threads, each its own context = its own CUDA stream,
+    # reference slots and staging), pictures being independent units (closed-GOP shards) exactly like the ranks; the
+    # single-stream figure (one thread, one context, strictly serial pictures) is reported beside it.
+    n_streams = args.e2e_streams if args.e2e_streams > 0 else max(1, min(3, (os.cpu_count() or 1) // world - 1))
     e2e_ctx = [ctx] + [api.Context(local) for _ in range(n_streams - 1)]
     for c in e2e_ctx[1:]:
         c.configure(search_range=SEARCH_RANGE)
-    e2e_out = [(h_res, h_lev, h_cost, h_cbp)] + [(c.pinned(n_mb * api.NPART, api.ME_RES), c.pinned((7, n_mb, 256), np.int16),
-                                                  c.pinned((7, n_mb, 4), np.int32), c.pinned((7, n_mb), np.uint32)) for c in e2e_ctx[1:]]
-    e2e_t = [{"ref_put": 0.0, "pic_begin": 0.0, "me_search": 0.0, "mc_tq": 0.0} for _ in e2e_ctx]
+    e2e_out = [wl.host_outputs(c) for c in e2e_ctx]
+    e2e_t = [{"enqueue": 0.0, "residual_coding_and_wait": 0.0} for _ in e2e_ctx]
 
-    def step_host(s, k=0):
-        c, (o_res, o_lev, o_cost, o_cbp), tt = e2e_ctx[k], e2e_out[k], e2e_t[k]
-        hs, _ = sets[s % N_SETS]
-        t0 = time.perf_counter()
-        c.ref_put(s % 2, hs["ref"]); t1 = time.perf_counter()
-        c.pic_begin(hs["cur"], [s % 2]); t2 = time.perf_counter()
-        c.me_search(hs["reqs"], o_res, frame=True); t3 = time.perf_counter()
-        tt["ref_put"] += t1 - t0; tt["pic_begin"] += t2 - t1; tt["me_search"] += t3 - t2
-        # residual coding of all 7 partition modes from the results still resident in HBM; levels / costs / cbp come back
-        c._ck(c.L.jmb_mc_tq_modes(c.h, None, n_mb, 0x7F, qd.ctypes.data, o_lev.ctypes.data, o_cost.ctypes.data, o_cbp.ctypes.data, api.HOST))
-        tt["mc_tq"] += time.perf_counter() - t3
-
-    def run_host_steps(first, count):
+    def run_host_steps(first, count, streams):
         """`count` pictures starting at step index `first`, dealt round-robin to the streams' threads."""
         def worker(k):
-            for s in range(first + k, first + count, n_streams):
-                step_host(s, k)
+            for s in range(first + k, first + count, streams):
+                wl.step_host(s, e2e_ctx[k], e2e_out[k], e2e_t[k])
             e2e_ctx[k].sync()
-        th = [threading.Thread(target=worker, args=(k,)) for k in range(n_streams)]
+        if streams == 1:
+            worker(0)
+            return
+        th = [threading.Thread(target=worker, args=(k,)) for k in range(streams)]
         for t_ in th:
             t_.start()
         for t_ in th:
@@ -221,7 +274,7 @@ def run_ours(args):
     # ---- device-resident timing -------------------------------------------------------------------
     sampler = ClockSampler(local); sampler.start()       # started early: nvidia-smi needs ~100 ms to deliver its first sample
     for s in range(args.warmup):
-        step_device(s)
+        wl.step_device(s)
     ctx.sync()
     barrier()
     ctx.timing(True)
@@ -230,7 +283,7 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for s in range(args.steps):
-        step_device(args.warmup + s)
+        wl.step_device(args.warmup + s)
     e1.record(stream)
     e1.synchronize()
     sampler.mark_end()
@@ -239,34 +292,42 @@ def run_ours(args):
     gpu_launches = ctx.launches - launches0
     ms = e0.elapsed_time(e1)
     k_ms, k_n = ctx.timing_get("int_search")
-    kernel_break = {k: ctx.timing_get(k)[0] / max(1, args.steps) for k in ("subpel_planes", "pack_cur", "int_search", "subpel_refine", "mc_tq")}
+    kernel_break = {k: ctx.timing_get(k)[0] / max(1, args.steps) for k in ("subpel_planes", "pack_cur", "gen_requests", "int_search", "subpel_refine", "mc_tq")}
     ctx.timing(False)
+    ctx.sync()
+    tokens_dev = int(wl.d_ntok.item())
     if world > 1:
         t = torch.tensor([ms], device=f"cuda:{local}"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
 
     # ---- end-to-end timing (host buffers through the C ABI) ----------------------------------------
-    run_host_steps(0, max(3, n_streams) * 2)
-    barrier()
-    for tt in e2e_t:
-        for k in tt:
-            tt[k] = 0.0
-    t0 = time.perf_counter()
-    run_host_steps(args.warmup, args.steps)
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=f"cuda:{local}"); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
-    h2d = 2 * W * H * 2 + n_mb * api.NPART * api.ME_REQ.itemsize + api.QUANT_DESC.itemsize
-    d2h = n_mb * api.NPART * api.ME_RES.itemsize + 7 * n_mb * (512 + 16 + 4)
+    def timed_host(streams, steps):
+        run_host_steps(0, max(3, streams) * 2, streams)      # warm-up (buffers grown, pages touched)
+        barrier()
+        for tt in e2e_t:
+            for k in tt:
+                tt[k] = 0.0
+        t0 = time.perf_counter()
+        run_host_steps(args.warmup, steps, streams)
+        el = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([el], device=f"cuda:{local}"); dist.all_reduce(t, op=dist.ReduceOp.MAX); el = float(t.item())
+        return el
+    e2e_s = timed_host(n_streams, args.steps)
+    host_ms = {k: 1e3 * sum(tt[k] for tt in e2e_t) / args.steps for k in e2e_t[0]}
+    e2e_1 = timed_host(1, args.steps) if n_streams > 1 else e2e_s
+    h2d, d2h = wl.bytes_per_step()
 
     out = {"metric": "macroblocks/sec 1080p full-search ME+DCT/quant", "value": world * n_mb * args.steps / (ms / 1e3),
            "unit": "macroblocks/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-           "config": workload_config(world, args.anchor_bcast), "clocks": clocks, "gpu_launches": int(gpu_launches),
-           "e2e": {"value": world * n_mb * args.steps / e2e_s, "unit": "macroblocks/s", "h2d_bytes_per_step": int(h2d),
-                   "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps,
-                   "picture_streams_per_gpu": n_streams,
-                   "host_ms_per_picture": {k: 1e3 * sum(tt[k] for tt in e2e_t) / args.steps for k in e2e_t[0]}},
-           "kernel_ms_per_step": kernel_break}
+           "config": workload_config(args.config, world), "clocks": clocks, "gpu_launches": int(gpu_launches),
+           "e2e": {"value": world * n_mb * args.steps / e2e_s, "unit": "macroblocks/s", "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
+                   "picture_streams_per_gpu": n_streams, "host_ms_per_picture": host_ms,
+                   "single_stream_value": world * n_mb * args.steps / e2e_1, "single_stream_ms_per_step": 1e3 * e2e_1 / args.steps},
+           "kernel_ms_per_step": kernel_break, "tokens_per_step": tokens_dev}
+    if wl.cfg.get("anchor") and world > 1:
+        out["nvlink_bytes_per_step_per_rank"] = wl.W * wl.H
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -276,7 +337,7 @@ def run_ours(args):
     achieved = BYTES_PER_MB_REF * n_mb / (k_ms / max(1, k_n) / 1e3) / 1e9
     traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (tools/ncu_summary.py)
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "int_search_traffic.json")))[args.size]["dram_bytes_per_launch"]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "int_search_traffic.json")))[wl.cfg["size"].lower()]["dram_bytes_per_launch"]
     except Exception:
         pass
     out["roofline"] = {"bound": "hbm", "kernel": "k_int_search", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -285,6 +346,16 @@ def run_ours(args):
                        "note": "search-window model of SURVEY 8(d): 13804 B per macroblock*reference; the kernel is ALU-pipe "
                                "(VABSDIFF4/PRMT/ISETP) bound, not HBM bound -- DESIGN.md 3; traffic < algorithmic bytes because "
                                "neighbouring windows hit L2"}
+    # the streaming kernels against the same HBM peak (algorithmic bytes per launch stated in DESIGN.md 3)
+    sp_ms = kernel_break["subpel_planes"]; tq_ms = kernel_break["mc_tq"]
+    sp_bytes = wl.W * wl.H + 16 * ((wl.W + 64 + 127) // 128 * 128) * (wl.H + 40)
+    nmodes = bin(wl.mode_mask).count("1")
+    tq_bytes = nmodes * n_mb * (256 + 256 + 16) + n_mb * 41 * 24 + 4 * tokens_dev
+    out["roofline_other"] = {
+        "k_subpel_planes": {"algorithmic_bytes_per_launch": sp_bytes, "launch_ms": sp_ms, "achieved": sp_bytes / (sp_ms / 1e3) / 1e9 if sp_ms else None,
+                            "frac": sp_bytes / (sp_ms / 1e3) / 1e9 / peak if sp_ms else None},
+        "k_mc_tq_modes_c": {"algorithmic_bytes_per_launch": tq_bytes, "launch_ms": tq_ms, "achieved": tq_bytes / (tq_ms / 1e3) / 1e9 if tq_ms else None,
+                            "frac": tq_bytes / (tq_ms / 1e3) / 1e9 / peak if tq_ms else None}}
 
     # The same kernel against the bound that actually limits it: the SM ALU pipe (VABSDIFF4 / PRMT / ISETP issue at
     # 64 lanes/clk/SM on this part, tools/ubench.cu).  Floor per displacement = 64 VABSDIFF4 + 19 PRMT + 41 ISETP.
@@ -295,7 +366,7 @@ def run_ours(args):
                            "frac": alu_ops / (k_ms / max(1, k_n) / 1e3) / alu_peak,
                            "note": "minimum ALU-pipe instructions of the algorithm / launch time, vs 64 lanes/clk/SM x 148 SMs x SM clock"}
     if rank == 0 and world == 1 and not args.no_cpu:
-        out["cpu_baseline"] = cpu_baseline(sets[0][0], lam, ctx=ctx, api=api, budget_s=args.cpu_seconds)
+        out["cpu_baseline"] = cpu_baseline(wl, ctx=ctx, api=api, budget_s=args.cpu_seconds)
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
@@ -305,10 +376,10 @@ def run_ours(args):
 _JM = {}
 
 
-def _cpu_init(ref_luma, cur_luma):
+def _cpu_init(ref_luma, cur_luma, w, h):
     """One process = one JM instance (JM is single-threaded); its quarter-pel planes are built once, untimed."""
     from oracle import pyoracle as po
-    ref = po.JMRef(W, H, SEARCH_RANGE)
+    ref = po.JMRef(w, h, SEARCH_RANGE)
     ref.set_ref(ref_luma); ref.set_cur(cur_luma)
     _JM["ref"] = ref
 
@@ -322,19 +393,34 @@ def _cpu_worker(a):
     return mv, cost, lev, secs
 
 
-def cpu_baseline(hs, lam, ctx=None, api=None, budget_s=12.0):
+def expand_tokens(heads, tokens, mbs, per=16):
+    """(level, run) tokens of the macroblocks `mbs` -> dense [len(mbs)][7][256] levels (layout of JM's per-block scan order)."""
+    out = np.zeros((len(mbs), 7, 256), np.int16)
+    for i, mb in enumerate(mbs):
+        for m in range(heads.shape[0]):
+            hd = heads[m, mb]
+            pos = {}
+            for tk in tokens[int(hd["token_off"]): int(hd["token_off"]) + int(hd["n_tokens"])]:
+                blk = int(tk["blk"]); p = pos.get(blk, 0) + int(tk["run"])
+                out[i, m, blk * per + p] = tk["level"]
+                pos[blk] = p + 1
+    return out
+
+
+def cpu_baseline(wl, ctx=None, api=None, budget_s=12.0):
     """JM's own leaf functions (kind 'reference') on 1 host core over a bounded sample of set 0's macroblocks;
-    also re-checks the GPU results of that sample bit-for-bit."""
+    also re-checks the GPU results of that sample -- motion vectors, costs AND quantised levels -- bit-for-bit."""
     from oracle import pyoracle as po
     if not po.ref_available():
         return {"value": None, "unit": "macroblocks/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref/libjmref.so missing"}
-    n_mb = (W // 16) * (H // 16)
-    reqs = np.array(hs["reqs"]).reshape(n_mb, 41)
+    hs = wl.sets[0][0]
+    n_mb, W, H = wl.n_mb, wl.W, wl.H
+    mbw = W // 16
+    pred = np.array(hs["pred"])["pred"]
     # calibrate on 32 MBs, then size the sample for ~budget_s
     idx = np.linspace(0, n_mb - 1, 32).astype(int)
-    _cpu_init(np.array(hs["ref"]), np.array(hs["cur"]))
-    args = lambda ii: (np.stack([reqs["pos_x"][ii, 0], reqs["pos_y"][ii, 0]], 1),
-                       np.stack([reqs["pred_x"][ii], reqs["pred_y"][ii]], 2), lam)
+    _cpu_init(np.array(hs["ref"]).astype(np.uint16), np.array(hs["cur"]).astype(np.uint16), W, H)
+    args = lambda ii: (np.stack([(ii % mbw) * 16, (ii // mbw) * 16], 1), pred[ii], wl.lam)
     _, _, _, secs = _cpu_worker(args(idx))
     per_mb = max(1e-5, float(secs.sum()) / len(idx))
     n = int(min(n_mb, max(64, budget_s / per_mb)))
@@ -345,11 +431,14 @@ def cpu_baseline(hs, lam, ctx=None, api=None, budget_s=12.0):
                      f"sub_pel_motion_estimation x41 + forward4x4/quant_4x4_normal x112 per MB",
            "me_seconds": float(secs[0]), "tq_seconds": float(secs[1])}
     if ctx is not None:
-        ctx.ref_put(0, hs["ref"]); ctx.pic_begin(hs["cur"], [0])      # whatever picture the timed legs left resident, this is set 0
-        g = ctx.me_search(hs["reqs"], frame=True).reshape(n_mb, 41)
-        ok = bool(np.array_equal(g["mv_x"][idx], mv[:, :, 0]) and np.array_equal(g["mv_y"][idx], mv[:, :, 1]) and
-                  np.array_equal(g["cost"][idx], cost))
-        res["gpu_matches_reference_on_sample"] = ok
+        ctx.ref_put_u8(0, np.array(hs["ref"])); ctx.pic_begin_u8(np.array(hs["cur"]), [0])
+        g = ctx.me_search_frame_pred(np.array(hs["pred"]), wl.fp).reshape(n_mb, 41)
+        heads, tokens = ctx.mc_tq_modes_compact(None, wl.qd, wl.mode_mask, n_mb=n_mb, token_cap=wl.token_cap)
+        ok_mv = bool(np.array_equal(g["mv_x"][idx], mv[:, :, 0]) and np.array_equal(g["mv_y"][idx], mv[:, :, 1]) and
+                     np.array_equal(g["cost"][idx], cost))
+        ok_lev = bool(np.array_equal(expand_tokens(heads, tokens, idx), lev))
+        res["gpu_matches_reference_on_sample"] = ok_mv and ok_lev
+        res["checked"] = {"mv_and_cost": ok_mv, "levels": ok_lev, "nonzero_levels_in_sample": int((lev != 0).sum())}
     return res
 
 
@@ -358,28 +447,33 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
+    if CONFIGS[args.config]["search"] == "epzs" or CONFIGS[args.config]["chroma"]:
+        import bench_more
+        return bench_more.run_reference(args, globals())
     import multiprocessing as mp
     from jm_b200 import api, synth
-    from jm_b200 import h264_tables as T
     from oracle import pyoracle as po
+    from jm_b200 import h264_tables as T
     world = int(os.environ.get("WORLD_SIZE", 1))
     if not po.ref_available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libjmref.so not built"}))
         return
+    c = CONFIGS[args.config]
+    W, H = c["w"], c["h"]
     cores = os.cpu_count() or 1
     lam = T.lambda_me(QP)
     f = synth.luma_frames(W, H, 2, seed=1234, motion=(5, 3))
-    reqs = make_requests(api, seed=50).reshape(-1, 41)
-    n_mb = len(reqs)
+    n_mb = (W // 16) * (H // 16)
+    mbw = W // 16
+    pred = make_pred_table(api, 50, n_mb)["pred"]
     per_core = args.ref_mbs_per_core
     rng = np.random.default_rng(0)
 
     def job(step):
         idx = rng.permutation(n_mb)[: per_core * cores].reshape(cores, per_core)
-        return [(np.stack([reqs["pos_x"][ii, 0], reqs["pos_y"][ii, 0]], 1),
-                 np.stack([reqs["pred_x"][ii], reqs["pred_y"][ii]], 2), lam) for ii in idx]
+        return [(np.stack([(ii % mbw) * 16, (ii // mbw) * 16], 1), pred[ii], lam) for ii in idx]
 
-    with mp.get_context("fork").Pool(cores, initializer=_cpu_init, initargs=(f[0], f[1])) as pool:
+    with mp.get_context("fork").Pool(cores, initializer=_cpu_init, initargs=(f[0], f[1], W, H)) as pool:
         for s in range(args.warmup):
             pool.map(_cpu_worker, job(s))
         t0 = time.perf_counter()
@@ -390,11 +484,11 @@ def run_reference(args):
     out = {"impl": "reference", "metric": "macroblocks/sec 1080p full-search ME+DCT/quant", "value": v, "unit": "macroblocks/s",
            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-           "config": workload_config(world),
+           "config": workload_config(args.config, world), "sample_macroblocks_per_step": per_core * cores,
            "cpu_baseline": {"value": v, "unit": "macroblocks/s", "cores": cores, "kind": "reference",
-                            "sample": f"each step = {per_core * cores} random macroblocks of the 1080p picture ({per_core} per core, one JM "
+                            "sample": f"each step = {per_core * cores} random macroblocks of the {c['size']} picture ({per_core} per core, one JM "
                                       f"instance per core, quarter-pel planes built once before the timed region), "
-                                      f"JM's own full_search/sub_pel/forward4x4/quant_4x4_normal"},
+                                      f"JM's own full_search/sub_pel/forward4x4/quant_4x4_normal; value = sampled macroblocks / time"},
            "e2e": {"value": v, "unit": "macroblocks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -405,21 +499,19 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configs[1..4] (default 2 = configs[1])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--scene-cut", action="store_true", help="probe: unrelated reference picture (worst case for the search gate)")
-    ap.add_argument("--anchor-bcast", action="store_true",
-                    help="N>1: broadcast rank 0's reference picture over NCCL every step (pictures sharing an anchor coded on different GPUs)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-mbs-per-core", type=int, default=160)
     ap.add_argument("--e2e-streams", type=int, default=0,
-                    help="end-to-end leg: independent picture streams per GPU (host threads x contexts); 1 = strictly serial calls; "
-                         "0 = auto: min(3, host cores / (2 x ranks)), the synchronous calls spin-wait on the host")
-    ap.add_argument("--size", default="1080p", choices=["1080p", "4k"], help="picture size (default = BASELINE configs[1])")
+                    help="end-to-end leg: independent picture streams per GPU (host threads x contexts); 1 = strictly serial pictures; "
+                         "0 = auto: min(3, host cores / ranks - 1)")
     args = ap.parse_args()
-    if args.size == "4k":
-        global W, H, SIZE_NAME
-        W, H, SIZE_NAME = 3840, 2176, "4K (3840x2160 coded 3840x2176)"
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    for k in ("JMB_SHIM", "JMB_SHIM_OFF"):      # debug switches of the drop-in shim: never part of a measured leg
+        if os.environ.get(k):
+            sys.exit(f"bench.py: {k} is set; the measured legs run the device path only")
     if args.impl == "reference":
         run_reference(args)
     else:

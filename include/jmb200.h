@@ -16,9 +16,9 @@
  *     and addressed with JM's UMVLine4X origin clamp (lencod/inc/refbuf.h:22-26).
  *
  * Memory location of every data pointer is given by a `loc` argument: JMB_HOST (pageable or pinned
- * host memory; the call copies in/out and returns when the results are in the caller's buffers) or
- * JMB_DEVICE (device memory of the context's GPU; the call only enqueues work on the context's
- * stream -- use jmb_sync()).  There is NO CPU implementation behind this ABI: without a CUDA device
+ * host memory; the call copies in/out and returns when the results are in the caller's buffers),
+ * JMB_HOST_ASYNC (pinned host memory, nothing waited for) or JMB_DEVICE (device memory of the
+ * context's GPU; the call only enqueues work on the context's stream -- use jmb_sync()).  There is NO CPU implementation behind this ABI: without a CUDA device
  * jmb_create() fails with JMB_ERR_NO_DEVICE and nothing else can be called.
  *
  * Return value: 0 on success, a negative JMB_ERR_* otherwise; jmb_last_error() gives the text.
@@ -35,9 +35,12 @@
 extern "C" {
 #endif
 
-#define JMB_ABI_VERSION 1
+#define JMB_ABI_VERSION 2
 
-enum { JMB_HOST = 0, JMB_DEVICE = 1 };
+enum { JMB_HOST = 0, JMB_DEVICE = 1,
+       JMB_HOST_ASYNC = 2 };   /* PINNED host memory; copies are only enqueued on the context's stream: the buffers must stay
+                                  valid, and hold no results, until jmb_sync() -- accepted by the picture-form entry points
+                                  (jmb_ref_put*, jmb_pic_begin*, jmb_me_search_frame*, jmb_mc_tq_modes) */
 enum { JMB_SAD = 0, JMB_SSE = 1, JMB_SATD = 2 };            /* ERROR_SAD/SSE/SATD, lencod/inc/defines.h */
 enum { JMB_SEARCH_FULL = 0,                                 /* full_search_motion_estimation  */
        JMB_SEARCH_FAST_FULL = 1 };                          /* fast_full_search_motion_estimation */
@@ -156,10 +159,31 @@ int jmb_ref_drop(jmb_ctx *ctx, int slot);           /* free_storable_picture, le
 /* copy one quarter-pel plane [fy][fx] back as JM lays it out: (height+40) x (width+64) uint16_t */
 int jmb_ref_get_plane(jmb_ctx *ctx, int slot, int fy, int fx, uint16_t *out, int loc);
 
+/* The same picture as 8-bit samples (one byte each): JM's imgpel is uint16_t but every BASELINE configuration codes 8-bit
+ * video, so a caller that holds bytes (the YUV file JM reads, lcommon/src/input.c) sends half the bytes over the host link. */
+int jmb_ref_put_u8(jmb_ctx *ctx, int slot, const uint8_t *luma, int width, int height, int stride, int loc);
+
+/* Reconstructed-reference exchange between GPUs of one box WITHOUT a host round trip or a collective library: the owner
+ * exports an IPC handle of a device buffer holding its reconstructed luma (uint16_t or uint8_t samples); a peer process
+ * opens it once (jmb_peer_open, cached per handle) and then builds ITS OWN quarter-pel planes reading the owner's samples
+ * straight over NVLink (the sub-pel kernel's loads are the transfer: jmb_ref_put* with loc = JMB_DEVICE on the mapped
+ * pointer).  Stands where config 5 of BASELINE.json asks for the reconstructed-reference broadcast.
+ *   handle: 64 bytes (cudaIpcMemHandle_t), to be carried to the peers by any means (a file, a socket, torch.distributed). */
+#define JMB_IPC_HANDLE_BYTES 64
+int jmb_dev_alloc(jmb_ctx *ctx, size_t bytes, void **out);          /* device memory of the context's GPU (exportable) */
+int jmb_dev_free(jmb_ctx *ctx, void *p);
+int jmb_dev_copy(jmb_ctx *ctx, void *dst, const void *src, size_t bytes, int dst_loc, int src_loc);   /* on the context's stream */
+int jmb_peer_export(jmb_ctx *ctx, const void *dev_ptr, unsigned char handle[JMB_IPC_HANDLE_BYTES]);
+int jmb_peer_open(jmb_ctx *ctx, const unsigned char handle[JMB_IPC_HANDLE_BYTES], void **mapped);
+int jmb_peer_close(jmb_ctx *ctx, void *mapped);
+
 /* ---- current picture: p_Vid->pCurImg, read by get_original_block (lencod/src/mv_search.c:786) and
  * setup_fast_full_search (lencod/src/me_fullfast.c:333-337) ------------------------------------- */
 int jmb_pic_begin(jmb_ctx *ctx, const uint16_t *cur, int width, int height, int stride, int loc,
                   const int *ref_slots, int nref);
+
+int jmb_pic_begin_u8(jmb_ctx *ctx, const uint8_t *cur, int width, int height, int stride, int loc,
+                     const int *ref_slots, int nref);
 
 /* ---- motion search --------------------------------------------------------------------------- */
 int jmb_me_configure(jmb_ctx *ctx, const jmb_me_config *cfg);
@@ -172,6 +196,31 @@ int jmb_me_search(jmb_ctx *ctx, const jmb_me_req *reqs, int n, jmb_me_res *res, 
  * macroblock: slot = base[type] + (by4/h4)*(4/w4) + bx4/w4 with base = {0,1,3,5,9,17,25}).
  * No grouping pass is needed, so with JMB_DEVICE nothing touches the host. */
 int jmb_me_search_frame(jmb_ctx *ctx, const jmb_me_req *reqs, int n_mb, jmb_me_res *res, int loc);
+
+/* Whole-picture form with the requests GENERATED ON THE DEVICE: the caller sends only what BlockMotionSearch cannot know
+ * without it -- the 41 motion-vector predictors of every macroblock (GetMVPredictor, lencod/src/mv_prediction.c:192), 4 bytes
+ * each -- and the slice-level constants; block geometry, search centre, flags and bounds follow from JM's own rules:
+ *   centre, FULL:      ((pred + 2) >> 2) * 4 per partition (mv_search.c:931-932), clipped to the mv range (:957, clip_mv_range
+ *                      lencod/src/conformance.c:640);
+ *   centre, FAST_FULL: the rounded 16x16 predictor for all 41 partitions, clipped to [min + 4R, max - 4R] (me_fullfast.c:309-327);
+ *   min_mcost = DISTBLK_MAX (mv_search.c:871);  JMB_REQ_TEST8X8 only for block types <= 4 (mv_search.c:1630);
+ *   final mv clipped to the mv range again (mv_search.c:981).
+ * Macroblocks 0 .. n_mb-1 of the current picture in raster order.  Results: 8 bytes per search. */
+typedef struct jmb_mb_mvpred { int16_t pred[41][2]; } jmb_mb_mvpred;            /* canonical partition order, quarter-pel; 164 bytes */
+typedef struct jmb_frame_params {
+  int32_t lambda[3];               /* lambda_factor[F_PEL, H_PEL, Q_PEL] of the slice (mode_decision.c:192) */
+  int32_t mode;                    /* JMB_SEARCH_FULL / JMB_SEARCH_FAST_FULL */
+  int32_t flags;                   /* JMB_REQ_SUBPEL, JMB_REQ_TEST8X8 */
+  int32_t ref;                     /* index in the picture's reference list */
+  int32_t mv_min_x, mv_max_x;      /* p_Vid->MaxHmvR[4], [5]: quarter-pel mv range of the level (conformance.c:604) */
+  int32_t mv_min_y, mv_max_y;      /* p_Vid->MaxVmvR[4], [5] */
+} jmb_frame_params;
+typedef struct jmb_me_res8 {
+  int16_t mv_x, mv_y;              /* final mv, quarter-pel */
+  int32_t cost;                    /* the cost SubPelME (or IntPelME) returned; INT32_MAX when it does not fit (nothing beat DISTBLK_MAX) */
+} jmb_me_res8;
+/* res may be NULL (results stay on the device for jmb_mc_tq_modes* / jmb_luma_residual_coding_modes with res = NULL) */
+int jmb_me_search_frame_pred(jmb_ctx *ctx, const jmb_mb_mvpred *pred, int n_mb, const jmb_frame_params *fp, jmb_me_res8 *res, int loc);
 
 /* BlockSAD surfaces of one macroblock exactly as setup_fast_full_search leaves them:
  * out[(blocktype*16 + slot) * max_pos + pos], blocktype 1..7, uint32 (distpel), spiral order.
@@ -241,6 +290,19 @@ int jmb_mc_tq(jmb_ctx *ctx, const jmb_mb_pred *pred, int n_mb, const jmb_quant_d
  *   res == NULL: the results of the last jmb_me_search_frame call, still resident on the device. */
 int jmb_mc_tq_modes(jmb_ctx *ctx, const jmb_me_res *res, int n_mb, unsigned mode_mask, const jmb_quant_desc *q,
                     int16_t *levels, int32_t *coeff_cost, uint32_t *cbp_blk, int loc);
+
+/* jmb_mc_tq_modes with the output in JM's own shape -- (level, run) lists, quant4x4_normal.c:94-112 -- instead of dense
+ * levels: per (mode, macroblock) one 16-byte head and, only for nonzero levels, 4-byte tokens.  Tokens of one (mode,
+ * macroblock) are contiguous at tokens[head.token_off .. +head.n_tokens), ordered by transform block then scan position
+ * = ACLevel/ACRun order; blk = 4x4 block index by*4+bx (n = 4), quadrant b8 (n = 8), b8*4 + list (n = 8 CAVLC: the four
+ * interleaved lists of quant_8x8cavlc_normal).  cost8 = coeff_cost per 8x8 quadrant saturated at 255 (JM only compares it
+ * with _LUMA_COEFF_COST_ = 4 and _LUMA_MB_COEFF_COST_ = 5, macroblock.c:1238-1255; one level > 1 alone adds 999999).
+ * heads [7][n_mb] mode-major; *n_tokens = tokens produced; JMB_ERR_STATE if they exceed token_cap (nothing lost on the device:
+ * call again with a larger buffer).  JMB_HOST copies the heads, then exactly the tokens produced. */
+typedef struct jmb_tq_head { uint32_t cbp_blk; uint32_t token_off; uint16_t n_tokens; uint8_t cost8[4]; uint16_t reserved_; } jmb_tq_head;
+typedef struct jmb_tq_token { int16_t level; uint8_t run; uint8_t blk; } jmb_tq_token;
+int jmb_mc_tq_modes_compact(jmb_ctx *ctx, const jmb_me_res *res, int n_mb, unsigned mode_mask, const jmb_quant_desc *q,
+                            jmb_tq_head *heads, jmb_tq_token *tokens, uint32_t token_cap, uint32_t *n_tokens, int loc);
 
 /* nlist lists of q->m coefficients (scan order), in place: on return the dequantised coefficients; levels / runs [nlist][17]
  * (terminated by level 0), fadjust [nlist][m] (around only, may be NULL), coeff_cost [nlist] (added to; may be NULL), nonzero [nlist] */

@@ -11,7 +11,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("JMB200_LIB") or os.path.join(HERE, "lib", "libjmb200.so")     # JMB200_LIB: tuning builds (tools/)
-HOST, DEVICE = 0, 1
+HOST, DEVICE, HOST_ASYNC = 0, 1, 2
 SAD, SSE, SATD = 0, 1, 2
 SEARCH_FULL, SEARCH_FAST_FULL = 0, 1
 REQ_SUBPEL, REQ_TEST8X8, REQ_SKIP_INT = 1, 2, 4
@@ -32,6 +32,16 @@ DQ_LEVEL, DQ_SHIFT, DQ_SHIFT_RND4 = 0, 1, 2
 PRED_PLAIN, PRED_WEIGHTED, PRED_AVERAGE, PRED_WEIGHTED_AVERAGE = range(4)
 DIST_PRED = np.dtype([(k, np.int32) for k in ("form", "ref2", "cand2_x", "cand2_y", "weight1", "weight2", "offset", "log_weight_denom", "wp_round")])
 HAD_4X4, IHAD_4X4, HAD_4X2, IHAD_4X2, HAD_2X2, IHAD_2X2 = range(6)
+MB_MVPRED = np.dtype([("pred", "<i2", (41, 2))])
+FRAME_PARAMS = np.dtype([("lambda", "<i4", (3,)), ("mode", "<i4"), ("flags", "<i4"), ("ref", "<i4"),
+                         ("mv_min_x", "<i4"), ("mv_max_x", "<i4"), ("mv_min_y", "<i4"), ("mv_max_y", "<i4")])
+ME_RES8 = np.dtype([("mv_x", "<i2"), ("mv_y", "<i2"), ("cost", "<i4")])
+TQ_HEAD = np.dtype([("cbp_blk", "<u4"), ("token_off", "<u4"), ("n_tokens", "<u2"), ("cost8", "u1", (4,)), ("reserved_", "<u2")])
+TQ_TOKEN = np.dtype([("level", "<i2"), ("run", "u1"), ("blk", "u1")])
+assert MB_MVPRED.itemsize == 164 and FRAME_PARAMS.itemsize == 40 and ME_RES8.itemsize == 8 and TQ_HEAD.itemsize == 16 and TQ_TOKEN.itemsize == 4
+IPC_HANDLE_BYTES = 64
+# level 4 .. 5.1 mv range in quarter-pel (LEVELHMVLIMIT / LEVELVMVLIMIT, lencod/src/conformance.c): +-2048 x +-512 pels
+MV_RANGE_L51 = (-8192, 8191, -2048, 2047)
 assert QLIST_DESC.itemsize == 240
 assert ME_REQ.itemsize == 40 and ME_RES.itemsize == 24 and MB_PRED.itemsize == 72 and QUANT_DESC.itemsize == 980
 
@@ -80,6 +90,16 @@ def load_library():
     L.jmb_quant_list.argtypes = [vp, vp, vp, i, vp, vp, vp, vp, vp, i]
     L.jmb_luma_residual_coding.argtypes = [vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, i]
     L.jmb_luma_residual_coding_modes.argtypes = [vp, vp, i, C.c_uint, vp, vp, vp, vp, vp, vp, vp, i]
+    L.jmb_ref_put_u8.argtypes = [vp, i, vp, i, i, i, i]
+    L.jmb_pic_begin_u8.argtypes = [vp, vp, i, i, i, i, C.POINTER(i), i]
+    L.jmb_me_search_frame_pred.argtypes = [vp, vp, i, vp, vp, i]
+    L.jmb_mc_tq_modes_compact.argtypes = [vp, vp, i, C.c_uint, vp, vp, vp, C.c_uint32, vp, i]
+    L.jmb_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    L.jmb_dev_free.argtypes = [vp, vp]
+    L.jmb_dev_copy.argtypes = [vp, vp, vp, C.c_size_t, i, i]
+    L.jmb_peer_export.argtypes = [vp, vp, vp]
+    L.jmb_peer_open.argtypes = [vp, vp, C.POINTER(vp)]
+    L.jmb_peer_close.argtypes = [vp, vp]
     L.jmb_timing_enable.argtypes = [vp, i]
     L.jmb_timing_get.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(i)]
     return L
@@ -134,6 +154,40 @@ def qlist_plan(variant, qp, qparams, scan, c_cost, is_cavlc, arw=0):
         order, dq = [int(scan[k][0]) * 4 + int(scan[k][1]) for k in range(8)], DQ_SHIFT       # j first: block.c:88-94
     return dict(order=order, params=np.repeat(dc, len(order), 0), q_bits=16 + per, qp_per=per, dequant=dq, clip=int(is_cavlc), use_cost=0,
                 around=0, arw=arw, c_cost=np.zeros(16, np.uint8))
+
+
+def frame_params(lam, mode=SEARCH_FULL, flags=REQ_SUBPEL, ref=0, mv_range=MV_RANGE_L51):
+    fp = np.zeros(1, FRAME_PARAMS)
+    fp["lambda"] = lam; fp["mode"] = mode; fp["flags"] = flags; fp["ref"] = ref
+    fp["mv_min_x"], fp["mv_max_x"], fp["mv_min_y"], fp["mv_max_y"] = mv_range
+    return fp
+
+
+def requests_from_pred(pred, fp, mb_w, search_range):
+    """The jmb_me_req list jmb_me_search_frame_pred generates on the device (same rules; used by tests and the CPU legs)."""
+    n_mb = len(pred)
+    parts = mb_partitions()
+    fp = fp[0]
+    reqs = np.zeros((n_mb, NPART), ME_REQ)
+    mbx = (np.arange(n_mb) % mb_w) * 16; mby = (np.arange(n_mb) // mb_w) * 16
+    R4 = 4 * search_range
+    for k, (t, x, y) in enumerate(parts):
+        reqs["blocktype"][:, k] = t
+        reqs["pos_x"][:, k] = mbx + x; reqs["pos_y"][:, k] = mby + y
+        p = pred["pred"][:, k].astype(np.int32)
+        reqs["pred_x"][:, k] = p[:, 0]; reqs["pred_y"][:, k] = p[:, 1]
+        if int(fp["mode"]) == SEARCH_FAST_FULL:
+            b = pred["pred"][:, 0].astype(np.int32)
+            reqs["center_x"][:, k] = np.clip(((b[:, 0] + 2) >> 2) * 4, fp["mv_min_x"] + R4, fp["mv_max_x"] - R4)
+            reqs["center_y"][:, k] = np.clip(((b[:, 1] + 2) >> 2) * 4, fp["mv_min_y"] + R4, fp["mv_max_y"] - R4)
+        else:
+            reqs["center_x"][:, k] = np.clip(((p[:, 0] + 2) >> 2) * 4, fp["mv_min_x"], fp["mv_max_x"])
+            reqs["center_y"][:, k] = np.clip(((p[:, 1] + 2) >> 2) * 4, fp["mv_min_y"], fp["mv_max_y"])
+        reqs["flags"][:, k] = int(fp["flags"]) & (REQ_SUBPEL | (REQ_TEST8X8 if t <= 4 else 0))
+    reqs["mode"] = int(fp["mode"]); reqs["ref"] = int(fp["ref"])
+    reqs["lambda"] = fp["lambda"]
+    reqs["min_mcost"] = DISTBLK_MAX
+    return reqs.reshape(-1)
 
 
 def quant_desc(n, qp, qparams, scan, c_cost, is_cavlc, around=0, arw=0):
@@ -210,6 +264,77 @@ class Context:
             h, w = shape
             stride = stride or w
         self._ck(self.L.jmb_ref_put(self.h, slot, _ptr(luma), w, h, stride, bitdepth, loc))
+
+    def ref_put_u8(self, slot, luma, loc=HOST, shape=None, stride=None):
+        if loc != DEVICE:
+            assert luma.dtype == np.uint8 and luma.flags["C_CONTIGUOUS"]
+            h, w = luma.shape
+            stride = w
+        else:
+            h, w = shape
+            stride = stride or w
+        self._ck(self.L.jmb_ref_put_u8(self.h, slot, _ptr(luma), w, h, stride, loc))
+
+    def pic_begin_u8(self, cur, ref_slots, loc=HOST, shape=None, stride=None):
+        if loc != DEVICE:
+            assert cur.dtype == np.uint8 and cur.flags["C_CONTIGUOUS"]
+            h, w = cur.shape
+            stride = w
+        else:
+            h, w = shape
+            stride = stride or w
+        arr = (C.c_int * len(ref_slots))(*ref_slots)
+        self._ck(self.L.jmb_pic_begin_u8(self.h, _ptr(cur), w, h, stride, loc, arr, len(ref_slots)))
+
+    def me_search_frame_pred(self, pred, fp, res=None, loc=HOST, n_mb=None, want_res=True):
+        """pred: MB_MVPRED[n_mb] (or device pointer); fp: FRAME_PARAMS[1]; returns ME_RES8[n_mb * 41] (HOST)."""
+        if loc != DEVICE:
+            n_mb = len(pred)
+            if res is None and want_res:
+                res = np.zeros(n_mb * NPART, ME_RES8)
+        self._ck(self.L.jmb_me_search_frame_pred(self.h, _ptr(pred), n_mb, _ptr(fp), None if res is None else _ptr(res), loc))
+        return res
+
+    def mc_tq_modes_compact(self, res, qdesc, mode_mask=0x7F, loc=HOST, n_mb=None, out=None, token_cap=None):
+        """res=None: resident search results.  HOST: returns (heads[7][n_mb], tokens[n_tokens])."""
+        if loc == HOST:
+            if res is not None:
+                res = np.ascontiguousarray(res, ME_RES)
+                n_mb = len(res) // NPART
+            token_cap = token_cap or 7 * n_mb * 256
+            heads = np.zeros((7, n_mb), TQ_HEAD); tokens = np.zeros(token_cap, TQ_TOKEN); n_tok = np.zeros(1, np.uint32)
+        else:
+            heads, tokens, n_tok = out
+        self._ck(self.L.jmb_mc_tq_modes_compact(self.h, None if res is None else _ptr(res), n_mb, mode_mask, _ptr(qdesc), _ptr(heads),
+                                                _ptr(tokens), token_cap, _ptr(n_tok), loc))
+        if loc == HOST:
+            return heads, tokens[:int(n_tok[0])]
+        return heads, tokens, n_tok
+
+    def dev_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._ck(self.L.jmb_dev_alloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def dev_free(self, p):
+        self._ck(self.L.jmb_dev_free(self.h, p))
+
+    def dev_copy(self, dst, src, nbytes, dst_loc, src_loc):
+        self._ck(self.L.jmb_dev_copy(self.h, _ptr(dst), _ptr(src), nbytes, dst_loc, src_loc))
+
+    def peer_export(self, dev_ptr):
+        h = np.zeros(IPC_HANDLE_BYTES, np.uint8)
+        self._ck(self.L.jmb_peer_export(self.h, dev_ptr, _ptr(h)))
+        return h
+
+    def peer_open(self, handle):
+        handle = np.ascontiguousarray(handle, np.uint8)
+        p = C.c_void_p()
+        self._ck(self.L.jmb_peer_open(self.h, _ptr(handle), C.byref(p)))
+        return p.value
+
+    def peer_close(self, mapped):
+        self._ck(self.L.jmb_peer_close(self.h, mapped))
 
     def ref_drop(self, slot):
         self._ck(self.L.jmb_ref_drop(self.h, slot))

@@ -87,7 +87,8 @@ int jmb_check_device_errors(jmb_ctx *ctx) {
 extern "C" {
 
 static const char *k_names[JMB_K_COUNT] = {"subpel_planes", "pack_cur", "int_search", "subpel_refine", "dist", "ffs_surfaces",
-                                           "forward", "quant_blocks", "mc_tq", "pred_from_results"};
+                                           "forward", "quant_blocks", "mc_tq", "pred_from_results", "gen_requests", "epzs",
+                                           "chroma", "deblock", "argmin"};
 
 int jmb_timing_enable(jmb_ctx *ctx, int on) {
   JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -170,8 +171,19 @@ void jmb_destroy(jmb_ctx *ctx) {
   if (ctx->d_stage5) cudaFree(ctx->d_stage5);
   if (ctx->d_res_keep) cudaFree(ctx->d_res_keep);
   if (ctx->d_pred_keep) cudaFree(ctx->d_pred_keep);
+  for (int i = 0; i < ctx->n_peers; i++) cudaIpcCloseMemHandle(ctx->peers[i].mapped);
+  if (ctx->d_mvpred) cudaFree(ctx->d_mvpred);
+  if (ctx->d_res8) cudaFree(ctx->d_res8);
+  if (ctx->d_heads) cudaFree(ctx->d_heads);
+  if (ctx->d_tokens) cudaFree(ctx->d_tokens);
+  if (ctx->d_tok_count) cudaFree(ctx->d_tok_count);
+  if (ctx->h_tok_count) cudaFreeHost(ctx->h_tok_count);
   if (ctx->d_err) cudaFree(ctx->d_err);
   if (ctx->h_err) cudaFreeHost(ctx->h_err);
+  for (int k = 0; k < 16; k++) {
+    for (int i = 0; i < ctx->ev_cap[k]; i++) { cudaEventDestroy(ctx->ev[k][i].a); cudaEventDestroy(ctx->ev[k][i].b); }
+    free(ctx->ev[k]);
+  }
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -194,8 +206,12 @@ int jmb_host_free(jmb_ctx *ctx, void *p) {
 
 int jmb_me_configure(jmb_ctx *ctx, const jmb_me_config *cfg) {
   if (!cfg) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_me_configure: cfg is NULL");
-  if (cfg->search_range < 1 || cfg->search_range > 64)
-    return jmb_fail(ctx, JMB_ERR_UNSUPPORTED, "jmb_me_configure: search_range %d not in 1..64", cfg->search_range);
+  if (cfg->search_range < 1 || cfg->search_range > JMB_MAX_SEARCH_RANGE)
+    return jmb_fail(ctx, JMB_ERR_UNSUPPORTED, "jmb_me_configure: search_range %d not in 1..%d", cfg->search_range, JMB_MAX_SEARCH_RANGE);
+  if (cfg->max_mvd < 2) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_me_configure: max_mvd %d (must be > 1)", cfg->max_mvd);
+  // start_me_refinement_hp/qp are 0 or 1 (mv_search.c:445-446); the refinement kernel indexes its nine candidates with them
+  if ((cfg->start_hp & ~1) || (cfg->start_qp & ~1))
+    return jmb_fail(ctx, JMB_ERR_ARG, "jmb_me_configure: start_hp %d / start_qp %d must be 0 or 1", cfg->start_hp, cfg->start_qp);
   for (int i = 0; i < 3; i++)
     if (cfg->metric[i] < 0 || cfg->metric[i] > 2)
       return jmb_fail(ctx, JMB_ERR_ARG, "jmb_me_configure: metric[%d]=%d", i, cfg->metric[i]);
@@ -211,6 +227,7 @@ int jmb_me_configure(jmb_ctx *ctx, const jmb_me_config *cfg) {
 // Bring `bytes` of caller data (host or device) to the device; returns the device pointer to read.
 static int to_device(jmb_ctx *ctx, const void *src, size_t bytes, int loc, void **dptr, void **scratch, size_t *cap) {
   if (loc == JMB_DEVICE) { *dptr = (void *)src; return 0; }
+  if (!jmb_is_host(loc)) return jmb_fail(ctx, JMB_ERR_ARG, "loc %d is not JMB_HOST / JMB_DEVICE / JMB_HOST_ASYNC", loc);
   int rc = jmb_reserve_dev(ctx, scratch, cap, bytes);
   if (rc) return rc;
   JMB_CUDA(ctx, cudaMemcpyAsync(*scratch, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -218,13 +235,11 @@ static int to_device(jmb_ctx *ctx, const void *src, size_t bytes, int loc, void 
   return 0;
 }
 
-int jmb_ref_put(jmb_ctx *ctx, int slot, const uint16_t *luma, int width, int height, int stride,
-                int bitdepth, int loc) {
+static int ref_put_impl(jmb_ctx *ctx, int slot, const void *luma, int sample_bytes, int width, int height, int stride, int loc) {
   if (slot < 0 || slot >= JMB_MAX_REFS) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_ref_put: slot %d", slot);
-  if (bitdepth != 8)
-    return jmb_fail(ctx, JMB_ERR_UNSUPPORTED, "jmb_ref_put: bit depth %d (this build packs samples to 8 bits)", bitdepth);
   if (width < 16 || height < 16 || (width & 15) || (height & 15) || stride < width)
     return jmb_fail(ctx, JMB_ERR_ARG, "jmb_ref_put: %dx%d stride %d (need multiples of 16)", width, height, stride);
+  if (!luma) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_ref_put: NULL picture");
   JMB_CUDA(ctx, cudaSetDevice(ctx->device));
   jmb_ref *r = &ctx->refs[slot];
   int W = width + 2 * JMB_PAD_X, H = height + 2 * JMB_PAD_Y;
@@ -238,18 +253,30 @@ int jmb_ref_put(jmb_ctx *ctx, int slot, const uint16_t *luma, int width, int hei
     if (rc) return rc;
   }
   void *d_src = nullptr;
-  int rc = to_device(ctx, luma, (size_t)stride * height * sizeof(uint16_t), loc, &d_src, &ctx->d_stage, &ctx->d_stage_cap);
+  int rc = to_device(ctx, luma, (size_t)stride * height * sample_bytes, loc, &d_src, &ctx->d_stage, &ctx->d_stage_cap);
   if (rc) return rc;
-  rc = jmb_launch_subpel(ctx, (const uint16_t *)d_src, stride, r);
+  rc = jmb_launch_subpel(ctx, d_src, sample_bytes, stride, r);
   if (rc) return rc;
   r->valid = true;
   if (loc == JMB_HOST) JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return JMB_OK;
 }
 
+int jmb_ref_put(jmb_ctx *ctx, int slot, const uint16_t *luma, int width, int height, int stride,
+                int bitdepth, int loc) {
+  if (bitdepth != 8)
+    return jmb_fail(ctx, JMB_ERR_UNSUPPORTED, "jmb_ref_put: bit depth %d (this build packs samples to 8 bits)", bitdepth);
+  return ref_put_impl(ctx, slot, luma, 2, width, height, stride, loc);
+}
+
+int jmb_ref_put_u8(jmb_ctx *ctx, int slot, const uint8_t *luma, int width, int height, int stride, int loc) {
+  return ref_put_impl(ctx, slot, luma, 1, width, height, stride, loc);
+}
+
 int jmb_ref_drop(jmb_ctx *ctx, int slot) {
   if (slot < 0 || slot >= JMB_MAX_REFS) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_ref_drop: slot %d", slot);
   jmb_ref *r = &ctx->refs[slot];
+  JMB_CUDA(ctx, cudaSetDevice(ctx->device));
   if (r->planes) { JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); JMB_CUDA(ctx, cudaFree(r->planes)); }
   *r = jmb_ref();
   return JMB_OK;
@@ -291,11 +318,12 @@ __global__ void k_pack_cur(const uint16_t *__restrict__ src, int stride, int w, 
   *(uint32_t *)(dst + (size_t)y * pitch + x4) = v;
 }
 
-int jmb_pic_begin(jmb_ctx *ctx, const uint16_t *cur, int width, int height, int stride, int loc,
-                  const int *ref_slots, int nref) {
+static int pic_begin_impl(jmb_ctx *ctx, const void *cur, int sample_bytes, int width, int height, int stride, int loc,
+                          const int *ref_slots, int nref) {
   if (width < 16 || height < 16 || (width & 15) || (height & 15) || stride < width)
     return jmb_fail(ctx, JMB_ERR_ARG, "jmb_pic_begin: %dx%d stride %d", width, height, stride);
   if (nref < 0 || nref > JMB_MAX_REFS) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_pic_begin: nref %d", nref);
+  if (!cur) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_pic_begin: NULL picture");
   for (int i = 0; i < nref; i++) {
     int s = ref_slots[i];
     if (s < 0 || s >= JMB_MAX_REFS || !ctx->refs[s].valid)
@@ -320,16 +348,88 @@ int jmb_pic_begin(jmb_ctx *ctx, const uint16_t *cur, int width, int height, int 
     if (rc) return rc;
   }
   ctx->cur_w = width; ctx->cur_h = height; ctx->cur_pitch = pitch;
-  void *d_src = nullptr;
-  int rc = to_device(ctx, cur, (size_t)stride * height * sizeof(uint16_t), loc, &d_src, &ctx->d_stage, &ctx->d_stage_cap);
-  if (rc) return rc;
-  dim3 grid((width / 4 + 127) / 128, height);
-  jmb_time_begin(ctx, JMB_K_PACK);
-  k_pack_cur<<<grid, 128, 0, ctx->stream>>>((const uint16_t *)d_src, stride, width, height, ctx->cur, pitch);
-  jmb_time_end(ctx, JMB_K_PACK);
-  JMB_LAUNCH_CHECK(ctx);
+  if (sample_bytes == 1) {      // bytes already: one strided copy straight into the search layout, no kernel
+    JMB_CUDA(ctx, cudaMemcpy2DAsync(ctx->cur, pitch, cur, stride, width, height,
+                                    loc == JMB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    void *d_src = nullptr;
+    int rc = to_device(ctx, cur, (size_t)stride * height * sizeof(uint16_t), loc, &d_src, &ctx->d_stage, &ctx->d_stage_cap);
+    if (rc) return rc;
+    dim3 grid((width / 4 + 127) / 128, height);
+    jmb_time_begin(ctx, JMB_K_PACK);
+    k_pack_cur<<<grid, 128, 0, ctx->stream>>>((const uint16_t *)d_src, stride, width, height, ctx->cur, pitch);
+    jmb_time_end(ctx, JMB_K_PACK);
+    JMB_LAUNCH_CHECK(ctx);
+  }
   if (loc == JMB_HOST) JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return JMB_OK;
+}
+
+int jmb_pic_begin(jmb_ctx *ctx, const uint16_t *cur, int width, int height, int stride, int loc,
+                  const int *ref_slots, int nref) {
+  return pic_begin_impl(ctx, cur, 2, width, height, stride, loc, ref_slots, nref);
+}
+
+int jmb_pic_begin_u8(jmb_ctx *ctx, const uint8_t *cur, int width, int height, int stride, int loc,
+                     const int *ref_slots, int nref) {
+  if (!jmb_is_host(loc) && loc != JMB_DEVICE) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_pic_begin_u8: loc %d", loc);
+  return pic_begin_impl(ctx, cur, 1, width, height, stride, loc, ref_slots, nref);
+}
+
+// ---- plain device memory + peer (NVLink) mapping -------------------------------------------------------------------
+int jmb_dev_alloc(jmb_ctx *ctx, size_t bytes, void **out) {
+  if (!out || !bytes) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_dev_alloc: bad argument");
+  JMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  JMB_CUDA(ctx, cudaMalloc(out, bytes));
+  return JMB_OK;
+}
+int jmb_dev_free(jmb_ctx *ctx, void *p) {
+  JMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  JMB_CUDA(ctx, cudaFree(p));
+  return JMB_OK;
+}
+int jmb_dev_copy(jmb_ctx *ctx, void *dst, const void *src, size_t bytes, int dst_loc, int src_loc) {
+  if (!dst || !src) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_dev_copy: NULL pointer");
+  JMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  JMB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
+  if (dst_loc == JMB_HOST || src_loc == JMB_HOST) JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return JMB_OK;
+}
+int jmb_peer_export(jmb_ctx *ctx, const void *dev_ptr, unsigned char handle[JMB_IPC_HANDLE_BYTES]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == JMB_IPC_HANDLE_BYTES, "IPC handle size");
+  if (!dev_ptr || !handle) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_peer_export: NULL pointer");
+  JMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  JMB_CUDA(ctx, cudaIpcGetMemHandle(&h, (void *)dev_ptr));
+  memcpy(handle, &h, sizeof(h));
+  return JMB_OK;
+}
+int jmb_peer_open(jmb_ctx *ctx, const unsigned char handle[JMB_IPC_HANDLE_BYTES], void **mapped) {
+  if (!handle || !mapped) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_peer_open: NULL pointer");
+  for (int i = 0; i < ctx->n_peers; i++)
+    if (!memcmp(ctx->peers[i].handle, handle, JMB_IPC_HANDLE_BYTES)) { *mapped = ctx->peers[i].mapped; return JMB_OK; }
+  if (ctx->n_peers == 32) return jmb_fail(ctx, JMB_ERR_STATE, "jmb_peer_open: 32 peer buffers are open already");
+  JMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void *p = nullptr;
+  JMB_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  memcpy(ctx->peers[ctx->n_peers].handle, handle, JMB_IPC_HANDLE_BYTES);
+  ctx->peers[ctx->n_peers++].mapped = p;
+  *mapped = p;
+  return JMB_OK;
+}
+int jmb_peer_close(jmb_ctx *ctx, void *mapped) {
+  for (int i = 0; i < ctx->n_peers; i++)
+    if (ctx->peers[i].mapped == mapped) {
+      JMB_CUDA(ctx, cudaSetDevice(ctx->device));
+      JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      JMB_CUDA(ctx, cudaIpcCloseMemHandle(mapped));
+      ctx->peers[i] = ctx->peers[--ctx->n_peers];
+      return JMB_OK;
+    }
+  return jmb_fail(ctx, JMB_ERR_ARG, "jmb_peer_close: not a pointer jmb_peer_open returned");
 }
 
 }  // extern "C"

@@ -9,6 +9,7 @@
 
 #define JMB_PAD_X 32   // IMG_PAD_SIZE_X, lencod/inc/defines.h:121
 #define JMB_PAD_Y 20   // IMG_PAD_SIZE_Y, lencod/inc/defines.h:122
+#define JMB_MAX_SEARCH_RANGE 64   // largest SearchRange the search kernels index (k_search.cu IDX_BITS)
 
 // One reference picture in HBM: 16 quarter-pel planes of u8 samples (bit depth 8), plane-major,
 // each (h+40) rows of `pitch` bytes (pitch = (w+64) rounded up to 128 B so every row starts on a
@@ -55,6 +56,15 @@ struct jmb_ctx {
   // index of one offending request into d_err[0..1], which every synchronising call reads back
   int *d_err = nullptr; int *h_err = nullptr;
   bool smem_opt_in = false;   // k_int_search's dynamic shared memory opt-in done on this context's device
+  // picture form with device-generated requests / compact outputs
+  void *d_mvpred = nullptr; size_t d_mvpred_cap = 0;
+  void *d_res8 = nullptr; size_t d_res8_cap = 0;
+  void *d_heads = nullptr; size_t d_heads_cap = 0;
+  void *d_tokens = nullptr; size_t d_tokens_cap = 0;
+  unsigned *d_tok_count = nullptr; unsigned *h_tok_count = nullptr;
+  // peer buffers opened with jmb_peer_open (cudaIpcOpenMemHandle is expensive: one mapping per handle)
+  struct Peer { unsigned char handle[JMB_IPC_HANDLE_BYTES]; void *mapped; };
+  Peer peers[32]; int n_peers = 0;
 };
 int jmb_check_device_errors(jmb_ctx *ctx);   // after a stream synchronisation
 
@@ -82,7 +92,8 @@ int jmb_reserve_dev(jmb_ctx *ctx, void **p, size_t *cap, size_t bytes);
 
 // kernel classes for the optional per-kernel CUDA-event timing (jmb_timing_enable / jmb_timing_get)
 enum { JMB_K_SUBPEL = 0, JMB_K_PACK, JMB_K_INT_SEARCH, JMB_K_REFINE, JMB_K_DIST, JMB_K_FFS_SURF, JMB_K_FORWARD,
-       JMB_K_QUANT, JMB_K_MC_TQ, JMB_K_PRED, JMB_K_COUNT };
+       JMB_K_QUANT, JMB_K_MC_TQ, JMB_K_PRED, JMB_K_GEN, JMB_K_EPZS, JMB_K_CHROMA, JMB_K_DEBLOCK, JMB_K_ARGMIN, JMB_K_COUNT };
+static_assert(JMB_K_COUNT <= 16, "jmb_ctx::ev holds 16 kernel classes");
 void jmb_time_begin(jmb_ctx *ctx, int kid);
 void jmb_time_end(jmb_ctx *ctx, int kid);
 
@@ -124,4 +135,5 @@ __device__ __forceinline__ void jmb_req_report(int *err, int code, int index) {
 }
 
 // kernels (defined in k_*.cu), launched through these host wrappers
-int jmb_launch_subpel(jmb_ctx *ctx, const uint16_t *d_src, int src_stride, jmb_ref *r);
+int jmb_launch_subpel(jmb_ctx *ctx, const void *d_src, int sample_bytes, int src_stride, jmb_ref *r);
+static inline bool jmb_is_host(int loc) { return loc == JMB_HOST || loc == JMB_HOST_ASYNC; }

@@ -48,7 +48,11 @@ constexpr int INT_SEARCH_DYN_SMEM = (CW + CH / 4 + S1T_ROWS) * ADJ_PITCH * 4 + (
 #ifndef JMB_IS_SMEM_PAD
 #define JMB_IS_SMEM_PAD 0      // tuning builds only: extra dynamic shared memory lowers the CTAs per SM (occupancy probe at 128 registers: 4 CTAs 0.72 ms, 3 CTAs 0.77, 2 CTAs 0.92)
 #endif
-constexpr int IDX_BITS = 13;       // (2*64+1)^2 = 16641 > 8192: search_range <= 45 keeps idx < 8192
+constexpr int IDX_BITS = 15;       // spiral index field of the packed (cost << IDX_BITS) | index keys
+constexpr int MAX_SEARCH_RANGE = 64;   // JM's largest SearchRange: (2*64+1)^2 = 16641 positions
+static_assert((2 * MAX_SEARCH_RANGE + 1) * (2 * MAX_SEARCH_RANGE + 1) <= (1 << IDX_BITS), "spiral indices must fit IDX_BITS");
+static_assert(48 + IDX_BITS <= 63, "min_mcost <= 2^48 (jmb_req_check) shifted by IDX_BITS must stay below 2^63");
+static_assert(MAX_SEARCH_RANGE == JMB_MAX_SEARCH_RANGE, "jmb_me_configure and the search kernel must agree on the limit");
 
 struct PartGeom { unsigned char type, bx, by, w4, h4; };
 // canonical partition order: by type, then raster order of the partitions inside the macroblock
@@ -295,7 +299,9 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
         if (r.blocktype != pg.type || (r.pos_x & 15) != pg.bx * 4 || (r.pos_y & 15) != pg.by * 4 || ((r.pos_x ^ r0.pos_x) & ~15) ||
             ((r.pos_y ^ r0.pos_y) & ~15) || r.ref != r0.ref) bad = JMB_REQERR_LAYOUT;
       }
-      if (!bad && !(r.flags & JMB_REQ_SKIP_INT) && r.mode == JMB_SEARCH_FULL && fpel_metric != JMB_SAD) bad = JMB_REQERR_FPEL_METRIC;   // (the fast full search is a SAD search whatever the metric, me_fullfast.c:492-556)
+      // this kernel is a SAD kernel: full_search_motion_estimation takes computePredFPel = the MEDistortionFPel metric, and
+      // setup_fast_full_search builds squared-error surfaces for any metric other than SAD (dist_method, me_fullfast.c:274)
+      if (!bad && !(r.flags & JMB_REQ_SKIP_INT) && fpel_metric != JMB_SAD) bad = JMB_REQERR_FPEL_METRIC;
       jmb_req_report(err, bad, ri);
       if (!bad && !(r.flags & JMB_REQ_SKIP_INT)) {
         q.active = 1;
@@ -629,12 +635,34 @@ static int upload_ref_table(jmb_ctx *ctx, const uint8_t *const **d_tab, int plan
   return 0;
 }
 
+// the launches of one search call: integer search of n_groups (macroblock, reference) groups, then the refinement
+static int me_search_launch(jmb_ctx *ctx, const jmb_me_req *d_reqs, const int *d_groups, int n_groups, int n, jmb_me_res *d_res,
+                            bool any_subpel, const uint8_t *const *d_tab) {
+  jmb_time_begin(ctx, JMB_K_INT_SEARCH);
+  if (!ctx->smem_opt_in) {      // per context: the attribute belongs to the device the context runs on
+    JMB_CUDA(ctx, cudaFuncSetAttribute(k_int_search, cudaFuncAttributeMaxDynamicSharedMemorySize, INT_SEARCH_DYN_SMEM + JMB_IS_SMEM_PAD));
+    ctx->smem_opt_in = true;
+  }
+  TMaps tm;
+  memset(&tm, 0, sizeof(tm));
+  tm.cur = ctx->tmap_cur;
+  for (int i = 0; i < ctx->nref; i++) tm.ref[i] = ctx->refs[ctx->ref_list[i]].tmap_int;
+  k_int_search<<<n_groups, NT, INT_SEARCH_DYN_SMEM + JMB_IS_SMEM_PAD, ctx->stream>>>(d_reqs, d_groups, d_res, tm, ctx->cur_w, ctx->cur_h, ctx->me.search_range,
+                                                                  ctx->me.max_mvd - 1, ctx->nref, ctx->me.metric[0], ctx->d_err);
+  jmb_time_end(ctx, JMB_K_INT_SEARCH);
+  JMB_LAUNCH_CHECK(ctx);
+  if (any_subpel) { int rc = jmb_launch_refine(ctx, d_reqs, d_res, n, d_tab); if (rc) return rc; }
+  ctx->last_res = d_res; ctx->last_res_n = n;
+  return JMB_OK;
+}
+
 static int me_search_impl(jmb_ctx *ctx, const jmb_me_req *reqs, int n, jmb_me_res *res, int loc, bool frame_layout) {
   if (n <= 0) return JMB_OK;
   if (!ctx->cur || ctx->nref == 0) return jmb_fail(ctx, JMB_ERR_STATE, "jmb_me_search: call jmb_pic_begin with >= 1 reference first");
-  if (ctx->me.search_range > 45) return jmb_fail(ctx, JMB_ERR_UNSUPPORTED, "search_range %d > 45", ctx->me.search_range);
+  if (ctx->me.search_range > MAX_SEARCH_RANGE) return jmb_fail(ctx, JMB_ERR_UNSUPPORTED, "search_range %d > %d", ctx->me.search_range, MAX_SEARCH_RANGE);
+  if (loc == JMB_HOST_ASYNC && !frame_layout) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_me_search: JMB_HOST_ASYNC needs the frame layout (the grouping pass reads the requests on the host)");
+  if (!reqs || !res) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_me_search: NULL buffer");
   JMB_CUDA(ctx, cudaSetDevice(ctx->device));
-  const jmb_ref &r0 = ctx->refs[ctx->ref_list[0]];
   const uint8_t *const *d_tab = nullptr;
   int rc = upload_ref_table(ctx, &d_tab, 0);
   if (rc) return rc;
@@ -643,8 +671,9 @@ static int me_search_impl(jmb_ctx *ctx, const jmb_me_req *reqs, int n, jmb_me_re
   const int *d_groups = nullptr; int n_groups = 0;
   bool any_subpel = false;
   const jmb_me_req *h_reqs = nullptr;
+  const bool host = jmb_is_host(loc);
 
-  if (loc == JMB_HOST) h_reqs = reqs;
+  if (host) h_reqs = reqs;
   else if (!frame_layout) {
     // grouping needs the request headers on the host
     rc = jmb_reserve_host(ctx, &ctx->h_stage, &ctx->h_stage_cap, (size_t)n * sizeof(jmb_me_req)); if (rc) return rc;
@@ -679,33 +708,64 @@ static int me_search_impl(jmb_ctx *ctx, const jmb_me_req *reqs, int n, jmb_me_re
     JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_groups, hg, (size_t)n_groups * NPART * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     d_groups = (const int *)ctx->d_groups;
   }
-  if (loc == JMB_HOST) {
+  if (host) {
     rc = jmb_reserve_dev(ctx, &ctx->d_stage, &ctx->d_stage_cap, (size_t)n * sizeof(jmb_me_req)); if (rc) return rc;
     rc = jmb_reserve_dev(ctx, &ctx->d_res_keep, &ctx->d_res_keep_cap, (size_t)n * sizeof(jmb_me_res)); if (rc) return rc;
     JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage, reqs, (size_t)n * sizeof(jmb_me_req), cudaMemcpyHostToDevice, ctx->stream));
     d_reqs = (const jmb_me_req *)ctx->d_stage; d_res = (jmb_me_res *)ctx->d_res_keep;
   }
-  jmb_time_begin(ctx, JMB_K_INT_SEARCH);
-  if (!ctx->smem_opt_in) {      // per context: the attribute belongs to the device the context runs on
-    JMB_CUDA(ctx, cudaFuncSetAttribute(k_int_search, cudaFuncAttributeMaxDynamicSharedMemorySize, INT_SEARCH_DYN_SMEM + JMB_IS_SMEM_PAD));
-    ctx->smem_opt_in = true;
-  }
-  TMaps tm;
-  memset(&tm, 0, sizeof(tm));
-  tm.cur = ctx->tmap_cur;
-  for (int i = 0; i < ctx->nref; i++) tm.ref[i] = ctx->refs[ctx->ref_list[i]].tmap_int;
-  k_int_search<<<n_groups, NT, INT_SEARCH_DYN_SMEM + JMB_IS_SMEM_PAD, ctx->stream>>>(d_reqs, d_groups, d_res, tm, ctx->cur_w, ctx->cur_h, ctx->me.search_range,
-                                                                  ctx->me.max_mvd - 1, ctx->nref, ctx->me.metric[0], ctx->d_err);
-  jmb_time_end(ctx, JMB_K_INT_SEARCH);
-  JMB_LAUNCH_CHECK(ctx);
-  if (any_subpel) { rc = jmb_launch_refine(ctx, d_reqs, d_res, n, d_tab); if (rc) return rc; }
-  ctx->last_res = d_res; ctx->last_res_n = n;
-  if (loc == JMB_HOST) {
+  rc = me_search_launch(ctx, d_reqs, d_groups, n_groups, n, d_res, any_subpel, d_tab);
+  if (rc) return rc;
+  if (host) {
     JMB_CUDA(ctx, cudaMemcpyAsync(res, d_res, (size_t)n * sizeof(jmb_me_res), cudaMemcpyDeviceToHost, ctx->stream));
-    return jmb_check_device_errors(ctx);
+    if (loc == JMB_HOST) return jmb_check_device_errors(ctx);
   }
   return JMB_OK;
 }
+
+namespace {
+// Requests of a whole picture from the 41 predictors of every macroblock (jmb_me_search_frame_pred): block geometry from the
+// partition index, search centre and flags by the rules of BlockMotionSearch / setup_fast_full_search.
+__global__ void k_gen_requests(const jmb_mb_mvpred *__restrict__ pred, int n_mb, int mb_w, jmb_frame_params fp, int R, jmb_me_req *__restrict__ reqs) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_mb * NPART) return;
+  const int mb = t / NPART, p = t - mb * NPART;
+  const PartGeom pg = c_part[p];
+  const int px = pred[mb].pred[p][0], py = pred[mb].pred[p][1];
+  jmb_me_req q;
+  q.pos_x = (int16_t)((mb % mb_w) * 16 + pg.bx * 4); q.pos_y = (int16_t)((mb / mb_w) * 16 + pg.by * 4);
+  q.pred_x = (int16_t)px; q.pred_y = (int16_t)py;
+  if (fp.mode == JMB_SEARCH_FAST_FULL) {      // one centre per macroblock: the rounded 16x16 predictor (me_fullfast.c:309-327)
+    const int bx = pred[mb].pred[0][0], by = pred[mb].pred[0][1];
+    q.center_x = (int16_t)jmb_clip(fp.mv_min_x + 4 * R, fp.mv_max_x - 4 * R, ((bx + 2) >> 2) * 4);
+    q.center_y = (int16_t)jmb_clip(fp.mv_min_y + 4 * R, fp.mv_max_y - 4 * R, ((by + 2) >> 2) * 4);
+  } else {                                    // mv_search.c:931-932, clip_mv_range :957
+    q.center_x = (int16_t)jmb_clip(fp.mv_min_x, fp.mv_max_x, ((px + 2) >> 2) * 4);
+    q.center_y = (int16_t)jmb_clip(fp.mv_min_y, fp.mv_max_y, ((py + 2) >> 2) * 4);
+  }
+  q.blocktype = pg.type; q.ref = (uint8_t)fp.ref; q.mode = (uint8_t)fp.mode;
+  q.flags = (uint8_t)(fp.flags & (JMB_REQ_SUBPEL | (pg.type <= 4 ? JMB_REQ_TEST8X8 : 0)));
+  q.lambda[0] = fp.lambda[0]; q.lambda[1] = fp.lambda[1]; q.lambda[2] = fp.lambda[2];
+  q.reserved_ = 0;
+  q.min_mcost = (int64_t)0x7fffffff << 5;      // DISTBLK_MAX, lencod/inc/defines.h:136
+  reqs[t] = q;
+}
+
+// final clip of the mv (mv_search.c:981) applied to the resident results, and their 8-byte form
+__global__ void k_pack_results(jmb_me_res *__restrict__ res, int n, jmb_frame_params fp, jmb_me_res8 *__restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  jmb_me_res r = res[t];
+  const int mx = jmb_clip(fp.mv_min_x, fp.mv_max_x, r.mv_x), my = jmb_clip(fp.mv_min_y, fp.mv_max_y, r.mv_y);
+  if (mx != r.mv_x || my != r.mv_y) { res[t].mv_x = (int16_t)mx; res[t].mv_y = (int16_t)my; }
+  if (out) {
+    jmb_me_res8 o;
+    o.mv_x = (int16_t)mx; o.mv_y = (int16_t)my;
+    o.cost = r.cost > 0x7fffffffLL ? 0x7fffffff : (int32_t)r.cost;
+    out[t] = o;
+  }
+}
+}  // namespace
 
 extern "C" {
 
@@ -715,6 +775,57 @@ int jmb_me_search(jmb_ctx *ctx, const jmb_me_req *reqs, int n, jmb_me_res *res, 
 
 int jmb_me_search_frame(jmb_ctx *ctx, const jmb_me_req *reqs, int n_mb, jmb_me_res *res, int loc) {
   return me_search_impl(ctx, reqs, n_mb * NPART, res, loc, true);
+}
+
+int jmb_me_search_frame_pred(jmb_ctx *ctx, const jmb_mb_mvpred *pred, int n_mb, const jmb_frame_params *fp, jmb_me_res8 *res, int loc) {
+  if (n_mb <= 0) return JMB_OK;
+  if (!pred || !fp) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_me_search_frame_pred: NULL argument");
+  if (!ctx->cur || ctx->nref == 0) return jmb_fail(ctx, JMB_ERR_STATE, "jmb_me_search_frame_pred: call jmb_pic_begin with >= 1 reference first");
+  const int mb_w = ctx->cur_w / 16, mb_total = mb_w * (ctx->cur_h / 16), R = ctx->me.search_range;
+  if (n_mb > mb_total) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_me_search_frame_pred: n_mb %d (picture has %d)", n_mb, mb_total);
+  if (fp->mode < JMB_SEARCH_FULL || fp->mode > JMB_SEARCH_FAST_FULL || fp->ref < 0 || fp->ref >= ctx->nref)
+    return jmb_fail(ctx, JMB_ERR_ARG, "jmb_me_search_frame_pred: mode %d ref %d", fp->mode, fp->ref);
+  if (fp->mv_min_x > fp->mv_max_x || fp->mv_min_y > fp->mv_max_y || fp->mv_min_x < -32768 || fp->mv_max_x > 32767 || fp->mv_min_y < -32768 ||
+      fp->mv_max_y > 32767 || ((fp->mv_min_x | fp->mv_min_y) & 3) ||
+      (fp->mode == JMB_SEARCH_FAST_FULL && (fp->mv_min_x + 4 * R > fp->mv_max_x - 4 * R || fp->mv_min_y + 4 * R > fp->mv_max_y - 4 * R)))
+    return jmb_fail(ctx, JMB_ERR_ARG, "jmb_me_search_frame_pred: mv range x %d..%d y %d..%d", fp->mv_min_x, fp->mv_max_x, fp->mv_min_y, fp->mv_max_y);
+  for (int k = 0; k < 3; k++)
+    if (fp->lambda[k] < 0 || fp->lambda[k] > 65535) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_me_search_frame_pred: lambda[%d]=%d not in 0..65535", k, fp->lambda[k]);
+  if (R > MAX_SEARCH_RANGE) return jmb_fail(ctx, JMB_ERR_UNSUPPORTED, "search_range %d > %d", R, MAX_SEARCH_RANGE);
+  JMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const bool host = jmb_is_host(loc);
+  const int n = n_mb * NPART;
+  const jmb_mb_mvpred *d_pred = pred;
+  int rc;
+  if (host) {
+    rc = jmb_reserve_dev(ctx, &ctx->d_mvpred, &ctx->d_mvpred_cap, (size_t)n_mb * sizeof(jmb_mb_mvpred)); if (rc) return rc;
+    JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_mvpred, pred, (size_t)n_mb * sizeof(jmb_mb_mvpred), cudaMemcpyHostToDevice, ctx->stream));
+    d_pred = (const jmb_mb_mvpred *)ctx->d_mvpred;
+  }
+  rc = jmb_reserve_dev(ctx, &ctx->d_stage, &ctx->d_stage_cap, (size_t)n * sizeof(jmb_me_req)); if (rc) return rc;
+  rc = jmb_reserve_dev(ctx, &ctx->d_res_keep, &ctx->d_res_keep_cap, (size_t)n * sizeof(jmb_me_res)); if (rc) return rc;
+  const uint8_t *const *d_tab = nullptr;
+  rc = upload_ref_table(ctx, &d_tab, 0); if (rc) return rc;
+  jmb_me_req *d_reqs = (jmb_me_req *)ctx->d_stage; jmb_me_res *d_res = (jmb_me_res *)ctx->d_res_keep;
+  jmb_time_begin(ctx, JMB_K_GEN);
+  k_gen_requests<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_pred, n_mb, mb_w, *fp, R, d_reqs);
+  jmb_time_end(ctx, JMB_K_GEN);
+  JMB_LAUNCH_CHECK(ctx);
+  rc = me_search_launch(ctx, d_reqs, nullptr, n_mb, n, d_res, (fp->flags & JMB_REQ_SUBPEL) != 0, d_tab); if (rc) return rc;
+  jmb_me_res8 *d_out = res;
+  if (host && res) {
+    rc = jmb_reserve_dev(ctx, &ctx->d_res8, &ctx->d_res8_cap, (size_t)n * sizeof(jmb_me_res8)); if (rc) return rc;
+    d_out = (jmb_me_res8 *)ctx->d_res8;
+  }
+  jmb_time_begin(ctx, JMB_K_GEN);
+  k_pack_results<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_res, n, *fp, d_out);
+  jmb_time_end(ctx, JMB_K_GEN);
+  JMB_LAUNCH_CHECK(ctx);
+  if (host) {
+    if (res) JMB_CUDA(ctx, cudaMemcpyAsync(res, d_out, (size_t)n * sizeof(jmb_me_res8), cudaMemcpyDeviceToHost, ctx->stream));
+    if (loc == JMB_HOST) return jmb_check_device_errors(ctx);
+  }
+  return JMB_OK;
 }
 
 int jmb_ffs_surfaces(jmb_ctx *ctx, int ref, int mb_x, int mb_y, int center_x, int center_y, uint32_t *out, int loc) {

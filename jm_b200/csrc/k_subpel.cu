@@ -26,8 +26,9 @@ __device__ __forceinline__ int tap6(int a, int b, int c, int d, int e, int f) {
 __device__ __forceinline__ int clip255(int v) { return min(max(v, 0), 255); }
 __device__ __forceinline__ uint32_t avg4(uint32_t a, uint32_t b) { return __vavgu4(a, b); }  // (a+b+1)>>1 per byte
 
+template <typename SRC>      // uint16_t (JM's imgpel) or uint8_t samples; the source may be a peer GPU's memory mapped over NVLink
 __global__ void __launch_bounds__(256)
-k_subpel_planes(const uint16_t *__restrict__ src, int src_stride, int w, int h, int W, int H,
+k_subpel_planes(const SRC *__restrict__ src, int src_stride, int w, int h, int W, int H,
                 uint8_t *__restrict__ planes, int pitch, size_t plane_bytes) {
   __shared__ uint8_t sG[GH][GW];
   __shared__ int16_t sT[GH][TW];   // un-rounded horizontal six-tap, range [-2550, 10710]
@@ -85,10 +86,11 @@ k_subpel_planes(const uint16_t *__restrict__ src, int src_stride, int w, int h, 
 
 }  // namespace
 
-int jmb_launch_subpel(jmb_ctx *ctx, const uint16_t *d_src, int src_stride, jmb_ref *r) {
+int jmb_launch_subpel(jmb_ctx *ctx, const void *d_src, int sample_bytes, int src_stride, jmb_ref *r) {
   dim3 grid((r->W + TW - 1) / TW, (r->H + TH - 1) / TH);
   jmb_time_begin(ctx, JMB_K_SUBPEL);
-  k_subpel_planes<<<grid, 256, 0, ctx->stream>>>(d_src, src_stride, r->w, r->h, r->W, r->H, r->planes, r->pitch, r->plane_bytes);
+  if (sample_bytes == 2) k_subpel_planes<uint16_t><<<grid, 256, 0, ctx->stream>>>((const uint16_t *)d_src, src_stride, r->w, r->h, r->W, r->H, r->planes, r->pitch, r->plane_bytes);
+  else k_subpel_planes<uint8_t><<<grid, 256, 0, ctx->stream>>>((const uint8_t *)d_src, src_stride, r->w, r->h, r->W, r->H, r->planes, r->pitch, r->plane_bytes);
   jmb_time_end(ctx, JMB_K_SUBPEL);
   JMB_LAUNCH_CHECK(ctx);
   return JMB_OK;

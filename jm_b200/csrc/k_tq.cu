@@ -99,6 +99,14 @@ __device__ __forceinline__ unsigned tq_ld4(const uint8_t *p) {
 
 struct QOut { int nonzero; int cost; };
 
+// partition mode / reference of one quadrant of a jmb_mb_pred; 0 = fine (JMB_REQERR_* otherwise)
+__device__ __forceinline__ int pred_check(int mode, int ref, int n, int nref) {
+  int e = 0;
+  if (mode < 1 || mode > 7 || (n == 8 && mode > 4)) e |= JMB_REQERR_BLOCKTYPE;
+  if (ref >= nref) e |= JMB_REQERR_REF;
+  return e;
+}
+
 // quantise one block in scan order.  coef: in = transformed, out = dequantised (JM leaves it in tblock).
 // LISTS: write JM's (level, run) lists; otherwise write the level of every scan position to lv16.
 // STD: 0 = scan from the descriptor (any order), 1 = the standard zig-zag, 2 = the standard 8x8 CAVLC interleave
@@ -204,7 +212,7 @@ __global__ void k_quant_blocks(const jmb_quant_desc *__restrict__ qd, int do_tra
 template <int N>
 __global__ void k_mc_tq(const jmb_mb_pred *__restrict__ pred, int n_mb, int mb_w, const jmb_quant_desc *__restrict__ qd,
                         const uint8_t *__restrict__ cur, int cur_pitch, const uint8_t *const *__restrict__ ref_planes,
-                        size_t plane_bytes, int ref_pitch, int w, int h,
+                        size_t plane_bytes, int ref_pitch, int w, int h, int nref, int *__restrict__ err,
                         int16_t *__restrict__ levels, int *__restrict__ coeff_cost, unsigned *__restrict__ cbp_blk) {
   __shared__ jmb_quant_desc q;
   for (int i = threadIdx.x; i < (int)(sizeof(q) / 4); i += blockDim.x) ((int *)&q)[i] = ((const int *)qd)[i];
@@ -218,6 +226,10 @@ __global__ void k_mc_tq(const jmb_mb_pred *__restrict__ pred, int n_mb, int mb_w
   const int b8 = (by4 >> 1) * 2 + (bx4 >> 1);
   const jmb_mb_pred *mp = pred + mb;
   const int mode = mp->b8mode[b8];
+  {   // the table may live on the device: validated here, like the search requests (jmb_req_check)
+    const int bad = pred_check(mode, mp->ref[b8], N, nref);
+    if (bad) { jmb_req_report(err, bad, mb); return; }
+  }
   // prediction unit: the 8x8 quadrant for modes 1..4, the 4x4 block for modes 5..7 (macroblock.c:946-971)
   int ux4 = bx4, uy4 = by4;
   if (mode < 5 || N == 8) { ux4 &= ~1; uy4 &= ~1; }
@@ -289,6 +301,124 @@ __global__ void k_mc_tq_modes(const jmb_me_res *__restrict__ res, int n_mb, int 
   QOut o = quant_block<N, false, STD>(q, rr, nullptr, nullptr, nullptr, levels + mo * 256 + b * N * N);
   if (o.cost) atomicAdd(&coeff_cost[mo * 4 + b8], o.cost);
   if (o.nonzero) atomicOr(&cbp_blk[mo], (N == 4) ? (1u << (by4 * 4 + bx4)) : (51u << (4 * b8 - 2 * (b8 & 1))));
+}
+
+
+// jmb_mc_tq_modes_compact: the kernel above with JM's own output shape -- (level, run) tokens for the nonzero levels only and
+// one 16-byte head per (mode, macroblock) -- and the quantiser description in the CONSTANT bank (a __grid_constant__
+// parameter: with the compile-time scan every Scale / Offset is an immediate constant operand of the multiply-add, no load at
+// all; the dense kernel spends most of its issue slots waiting for ~50 broadcast LDS of these per thread).
+// Token space is handed out per macroblock: the threads of a macroblock (16 or 4 adjacent lanes) count their nonzero
+// levels, scan the counts with shuffles, the first lane takes the macroblock's range with ONE atomicAdd.
+template <int N, int STD>
+__global__ void __launch_bounds__(128)
+k_mc_tq_modes_c(const jmb_me_res *__restrict__ res, int n_mb, int mb_w, unsigned mode_mask, const __grid_constant__ jmb_quant_desc q,
+                const uint8_t *__restrict__ cur, int cur_pitch, const uint8_t *__restrict__ ref_plane0, size_t plane_bytes, int ref_pitch,
+                int w, int h, jmb_tq_head *__restrict__ heads, jmb_tq_token *__restrict__ tokens, unsigned token_cap, unsigned *__restrict__ tok_count) {
+  constexpr int PER_MB = (N == 4) ? 16 : 4, NN = N * N;
+  const int mode = blockIdx.y + 1;
+  if (!((mode_mask >> blockIdx.y) & 1)) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = t < n_mb * PER_MB;                       // whole macroblocks are live or dead together
+  const int mb = live ? t / PER_MB : 0, b = t % PER_MB;
+  const int mbx = (mb % mb_w) * 16, mby = (mb / mb_w) * 16;
+  const int bx4 = (N == 4) ? (b & 3) : (b & 1) * 2, by4 = (N == 4) ? (b >> 2) : (b >> 1) * 2;
+  const int b8 = (by4 >> 1) * 2 + (bx4 >> 1);
+  int ux4 = bx4, uy4 = by4;                                  // prediction unit (macroblock.c:946-971)
+  if (mode < 5 || N == 8) { ux4 &= ~1; uy4 &= ~1; }
+  if (mode == 1) { ux4 = 0; uy4 = 0; }
+  const jmb_me_res r = res[mb * 41 + c_mode_base[mode] + (uy4 / c_mode_h4[mode]) * (4 / c_mode_w4[mode]) + ux4 / c_mode_w4[mode]];
+  const int qx = ((mbx + ux4 * 4) << 2) + r.mv_x, qy = ((mby + uy4 * 4) << 2) + r.mv_y;
+  const int iy = jmb_clip(-JMB_PAD_Y, h + JMB_PAD_Y - 1 - 16, qy >> 2), ix = jmb_clip(-JMB_PAD_X, w + JMB_PAD_X - 1 - 16, qx >> 2);
+  const uint8_t *rp = ref_plane0 + (size_t)((qy & 3) * 4 + (qx & 3)) * plane_bytes +
+                      (size_t)(iy + JMB_PAD_Y + (by4 - uy4) * 4) * ref_pitch + (ix + JMB_PAD_X + (bx4 - ux4) * 4);
+  const uint8_t *sp = cur + (size_t)(mby + by4 * 4) * cur_pitch + mbx + bx4 * 4;
+  int rr[NN];
+#pragma unroll
+  for (int y = 0; y < N; y++)
+#pragma unroll
+    for (int x4 = 0; x4 < N; x4 += 4) {
+      const unsigned sv = *(const unsigned *)(sp + (size_t)y * cur_pitch + x4), pv = tq_ld4(rp + (size_t)y * ref_pitch + x4);
+#pragma unroll
+      for (int x = 0; x < 4; x++) rr[y * N + x4 + x] = (int)((sv >> (8 * x)) & 255) - (int)((pv >> (8 * x)) & 255);
+    }
+  if (N == 4) fwd4(rr); else fwd8(rr);
+
+  // quantisation in scan order (quant_4x4_normal, quant_8x8_normal, quant_8x8cavlc_normal): levels stay in rr[scan position]
+  const int qp_per = q.qp / 6, q_bits = (N == 4 ? 15 : 16) + qp_per;
+  const bool cavlc8 = (N == 8) && q.is_cavlc;
+  const bool clip = (N == 4) ? (q.is_cavlc != 0) : cavlc8;
+  unsigned long long nzm = 0;                                // bit k: scan position k holds a nonzero level
+  int lv[NN];
+  int cost = 0;
+  {
+    int run[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < NN; k++) {
+      int i, j;
+      if (STD) { i = (N == 4) ? STD_SCAN4[k][0] : (STD == 2 ? STD_SCAN8_CAVLC[k][0] : STD_SCAN8[k][0]);
+                 j = (N == 4) ? STD_SCAN4[k][1] : (STD == 2 ? STD_SCAN8_CAVLC[k][1] : STD_SCAN8[k][1]); }
+      else { i = q.scan[k][0]; j = q.scan[k][1]; }
+      const int idx = j * N + i, s = cavlc8 ? (k >> 4) : 0;
+      const int c = STD ? rr[idx] : rr[idx];
+      int level = 0;
+      if (c != 0) {
+        level = (abs(c) * q.qparams[idx][1] + q.qparams[idx][0]) >> q_bits;
+        if (level != 0) {
+          if (clip) level = min(level, 2063);
+          cost += (level > 1) ? 999999 : q.c_cost[run[s]];
+          if (c < 0) level = -level;
+          nzm |= 1ull << k;
+        }
+      }
+      lv[k] = level;
+      if (level != 0) run[s] = 0; else run[s]++;
+    }
+  }
+  const int cnt = __popcll(nzm);
+  // macroblock-wide exchange: cost per quadrant, coded-block bits, token range
+  int c8 = cost;
+  if (N == 4) { c8 += __shfl_xor_sync(0xffffffffu, c8, 1); c8 += __shfl_xor_sync(0xffffffffu, c8, 4); }
+  unsigned bits = cnt ? ((N == 4) ? (1u << (by4 * 4 + bx4)) : (51u << (4 * b8 - 2 * (b8 & 1)))) : 0u;
+  int incl = cnt;
+#pragma unroll
+  for (int sh = 1; sh < PER_MB; sh <<= 1) {
+    bits |= __shfl_xor_sync(0xffffffffu, bits, sh);
+    const int up = __shfl_up_sync(0xffffffffu, incl, sh, PER_MB);
+    if ((int)(threadIdx.x & (PER_MB - 1)) >= sh) incl += up;
+  }
+  const int lane = threadIdx.x & 31, leader = lane & ~(PER_MB - 1);
+  const int total = __shfl_sync(0xffffffffu, incl, leader + PER_MB - 1);
+  unsigned base = 0;
+  if (lane == leader && live && total) base = atomicAdd(tok_count, (unsigned)total);
+  base = __shfl_sync(0xffffffffu, base, leader);
+  // cost8 of the four quadrants to the leader
+  unsigned c8sat = (unsigned)min(c8, 255);
+  unsigned cq[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) cq[k] = __shfl_sync(0xffffffffu, c8sat, leader + ((N == 4) ? ((k >> 1) * 8 + (k & 1) * 2) : k));
+  if (!live) return;
+  const size_t mo = (size_t)blockIdx.y * n_mb + mb;
+  if (lane == leader) {
+    uint4 hv;
+    hv.x = bits; hv.y = base; hv.z = (unsigned)total | (cq[0] << 16) | (cq[1] << 24); hv.w = cq[2] | (cq[3] << 8);
+    *(uint4 *)&heads[mo] = hv;
+  }
+  if (cnt && base + (unsigned)total <= token_cap) {
+    jmb_tq_token *o = tokens + base + (incl - cnt);
+#pragma unroll
+    for (int k = 0; k < NN; k++) {
+      if ((nzm >> k) & 1) {
+        const int s = cavlc8 ? (k >> 4) : 0, k0 = cavlc8 ? (k & ~15) : 0;
+        const unsigned long long before = nzm & ((1ull << k) - 1) & ~((1ull << k0) - 1);     // earlier nonzero levels of the same list
+        const int run = before ? (k - 1 - (63 - __clzll(before))) : (k - k0);
+        jmb_tq_token tk;
+        tk.level = (int16_t)lv[k]; tk.run = (uint8_t)run;
+        tk.blk = (uint8_t)((N == 4) ? b : (cavlc8 ? b8 * 4 + s : b8));
+        o[__popcll(nzm & ((1ull << k) - 1))] = tk;
+      }
+    }
+  }
 }
 
 // List quantiser: the DC / AC members of JM's quantiser family (quant_ac4x4_*, quant_dc4x4_normal, quant_dc2x2_*,
@@ -387,7 +517,7 @@ template <int N, int STD>
 __global__ void __launch_bounds__(128)
 k_luma_rc_modes(const jmb_me_res *__restrict__ res, const jmb_mb_pred *__restrict__ pred, int first_mb, int n_mb, int mb_w, unsigned mode_mask,
                 const jmb_quant_desc *__restrict__ qd, const uint8_t *__restrict__ cur, int cur_pitch, const uint8_t *const *__restrict__ ref_planes,
-                size_t plane_bytes, int ref_pitch, int w, int h,
+                size_t plane_bytes, int ref_pitch, int w, int h, int nref, int *__restrict__ err,
                 int16_t *__restrict__ levels, int *__restrict__ cost8, unsigned *__restrict__ cbp_blk, unsigned *__restrict__ cbp,
                 uint8_t *__restrict__ recon, int *__restrict__ sse) {
   __shared__ jmb_quant_desc q;
@@ -396,18 +526,25 @@ k_luma_rc_modes(const jmb_me_res *__restrict__ res, const jmb_mb_pred *__restric
   constexpr int PER_MB = (N == 4) ? 16 : 4;
   if (!((mode_mask >> blockIdx.y) & 1)) return;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = t < n_mb * PER_MB;                         // dead threads still take part in the shuffles
+  bool live = t < n_mb * PER_MB;                               // dead threads still take part in the shuffles
   const int mb = live ? t / PER_MB : 0, b = t % PER_MB;        // mb: index into the outputs / pred; picture address = first_mb + mb
   const int mbx = ((first_mb + mb) % mb_w) * 16, mby = ((first_mb + mb) / mb_w) * 16;
   const int bx4 = (N == 4) ? (b & 3) : (b & 1) * 2, by4 = (N == 4) ? (b >> 2) : (b >> 1) * 2;
   const int b8 = (by4 >> 1) * 2 + (bx4 >> 1);
   // prediction source: an explicit table (mode / mvs / reference per quadrant) or mode blockIdx.y+1 of the search results
-  const int mode = pred ? pred[mb].b8mode[b8] : blockIdx.y + 1;
+  int mode = pred ? pred[mb].b8mode[b8] : blockIdx.y + 1;
+  if (pred) {   // a device-resident table is validated here; a rejected macroblock writes nothing (the whole macroblock: its
+                // threads exchange costs by shuffle, so every one of them must see the same verdict)
+    int bad = pred_check(mode, pred[mb].ref[b8], N, nref);
+#pragma unroll
+    for (int sh = 1; sh < PER_MB; sh <<= 1) bad |= __shfl_xor_sync(0xffffffffu, bad, sh);
+    if (bad) { if (live && b == 0) jmb_req_report(err, bad, first_mb + mb); live = false; mode = 1; }
+  }
   int ux4 = bx4, uy4 = by4;
   if (mode < 5 || N == 8) { ux4 &= ~1; uy4 &= ~1; }
   if (mode == 1) { ux4 = 0; uy4 = 0; }                       // P16x16: one 16x16 prediction, one origin clamp (macroblock.c:1225)
   int mvx, mvy, rf = 0;
-  if (pred) { mvx = pred[mb].mv[uy4 * 4 + ux4][0]; mvy = pred[mb].mv[uy4 * 4 + ux4][1]; rf = pred[mb].ref[b8]; }
+  if (pred) { mvx = pred[mb].mv[uy4 * 4 + ux4][0]; mvy = pred[mb].mv[uy4 * 4 + ux4][1]; rf = min((int)pred[mb].ref[b8], nref - 1); }
   else {
     const jmb_me_res r = res[(first_mb + mb) * 41 + c_mode_base[mode] + (uy4 / c_mode_h4[mode]) * (4 / c_mode_w4[mode]) + ux4 / c_mode_w4[mode]];
     mvx = r.mv_x; mvy = r.mv_y;
@@ -640,9 +777,9 @@ int jmb_mc_tq(jmb_ctx *ctx, const jmb_mb_pred *pred, int n_mb, const jmb_quant_d
   JMB_CUDA(ctx, cudaMemsetAsync(d_cbp, 0, (size_t)n_mb * 4, ctx->stream));
   jmb_time_begin(ctx, JMB_K_MC_TQ);
   if (q->n == 4) k_mc_tq<4><<<(n_mb * 16 + 127) / 128, 128, 0, ctx->stream>>>(d_pred, n_mb, mb_w, d_q, ctx->cur, ctx->cur_pitch,
-        (const uint8_t *const *)ctx->d_reftab, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_cc, d_cbp);
+        (const uint8_t *const *)ctx->d_reftab, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, ctx->nref, ctx->d_err, d_lv, d_cc, d_cbp);
   else k_mc_tq<8><<<(n_mb * 4 + 63) / 64, 64, 0, ctx->stream>>>(d_pred, n_mb, mb_w, d_q, ctx->cur, ctx->cur_pitch,
-        (const uint8_t *const *)ctx->d_reftab, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_cc, d_cbp);
+        (const uint8_t *const *)ctx->d_reftab, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, ctx->nref, ctx->d_err, d_lv, d_cc, d_cbp);
   jmb_time_end(ctx, JMB_K_MC_TQ);
   JMB_LAUNCH_CHECK(ctx);
   if (loc == JMB_HOST) {
@@ -765,10 +902,20 @@ int jmb_luma_residual_coding_modes(jmb_ctx *ctx, const jmb_me_res *res, int n_mb
     d_lv = (int16_t *)a; d_c8 = (int *)(a + n7 * 512); d_cb = (unsigned *)(a + n7 * 528); d_cbp = (unsigned *)(a + n7 * 532);
     d_sse = (int *)(a + n7 * 536); d_rec = recon ? (uint8_t *)(a + n7 * 540) : nullptr;
   }
-  jmb_time_begin(ctx, JMB_K_MC_TQ);
+  for (int m = 0; m < 7; m++)      // modes outside the mask are not computed: every output of theirs reads as zero
+    if (!((mode_mask >> m) & 1)) {
+      const size_t o = (size_t)m * n_mb;
+      JMB_CUDA(ctx, cudaMemsetAsync(d_lv + o * 256, 0, (size_t)n_mb * 512, ctx->stream));
+      JMB_CUDA(ctx, cudaMemsetAsync(d_c8 + o * 4, 0, (size_t)n_mb * 16, ctx->stream));
+      JMB_CUDA(ctx, cudaMemsetAsync(d_cb + o, 0, (size_t)n_mb * 4, ctx->stream));
+      JMB_CUDA(ctx, cudaMemsetAsync(d_cbp + o, 0, (size_t)n_mb * 4, ctx->stream));
+      JMB_CUDA(ctx, cudaMemsetAsync(d_sse + o, 0, (size_t)n_mb * 4, ctx->stream));
+      if (d_rec) JMB_CUDA(ctx, cudaMemsetAsync(d_rec + o * 256, 0, (size_t)n_mb * 256, ctx->stream));
+    }
   const uint8_t *const *d_tab; rc = upload_ref_table(ctx, &d_tab); if (rc) return rc;
+  jmb_time_begin(ctx, JMB_K_MC_TQ);
 #define JMB_LRC(NN, STD, GRID) k_luma_rc_modes<NN, STD><<<GRID, 128, 0, ctx->stream>>>(d_res, nullptr, 0, n_mb, mb_w, mode_mask, d_q, ctx->cur, \
-        ctx->cur_pitch, d_tab, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_c8, d_cb, d_cbp, d_rec, d_sse)
+        ctx->cur_pitch, d_tab, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, ctx->nref, ctx->d_err, d_lv, d_c8, d_cb, d_cbp, d_rec, d_sse)
   {
     const int kind = std_scan_kind(q);
     const dim3 g4((n_mb * 16 + 127) / 128, 7), g8((n_mb * 4 + 127) / 128, 7);
@@ -820,7 +967,7 @@ int jmb_luma_residual_coding(jmb_ctx *ctx, const jmb_mb_pred *pred, int first_mb
   const uint8_t *const *d_tab; rc = upload_ref_table(ctx, &d_tab); if (rc) return rc;
   jmb_time_begin(ctx, JMB_K_MC_TQ);
 #define JMB_LRC(NN, STD, GRID) k_luma_rc_modes<NN, STD><<<GRID, 128, 0, ctx->stream>>>(nullptr, d_pred, first_mb, n_mb, mb_w, 1u, d_q, ctx->cur, \
-        ctx->cur_pitch, d_tab, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_c8, d_cb, d_cbp, d_rec, d_sse)
+        ctx->cur_pitch, d_tab, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, ctx->nref, ctx->d_err, d_lv, d_c8, d_cb, d_cbp, d_rec, d_sse)
   {
     const int kind = std_scan_kind(q);
     const dim3 g4((n_mb * 16 + 127) / 128, 1), g8((n_mb * 4 + 127) / 128, 1);
@@ -871,6 +1018,8 @@ int jmb_mc_tq_modes(jmb_ctx *ctx, const jmb_me_res *res, int n_mb, unsigned mode
   }
   JMB_CUDA(ctx, cudaMemsetAsync(d_cc, 0, n7 * 16, ctx->stream));
   JMB_CUDA(ctx, cudaMemsetAsync(d_cbp, 0, n7 * 4, ctx->stream));
+  for (int m = 0; m < 7; m++)      // modes outside the mask are not computed: their levels read as zero, never as stale memory
+    if (!((mode_mask >> m) & 1)) JMB_CUDA(ctx, cudaMemsetAsync(d_lv + (size_t)m * n_mb * 256, 0, (size_t)n_mb * 512, ctx->stream));
   jmb_time_begin(ctx, JMB_K_MC_TQ);
 #define JMB_MTQ(NN, STD, GRID, BLK) k_mc_tq_modes<NN, STD><<<GRID, BLK, 0, ctx->stream>>>(d_res, n_mb, mb_w, mode_mask, d_q, ctx->cur, ctx->cur_pitch, \
         r0.planes, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_lv, d_cc, d_cbp)
@@ -888,6 +1037,70 @@ int jmb_mc_tq_modes(jmb_ctx *ctx, const jmb_me_res *res, int n_mb, unsigned mode
     JMB_CUDA(ctx, cudaMemcpyAsync(coeff_cost, d_cc, n7 * 16, cudaMemcpyDeviceToHost, ctx->stream));
     JMB_CUDA(ctx, cudaMemcpyAsync(cbp_blk, d_cbp, n7 * 4, cudaMemcpyDeviceToHost, ctx->stream));
     JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return JMB_OK;
+}
+
+int jmb_mc_tq_modes_compact(jmb_ctx *ctx, const jmb_me_res *res, int n_mb, unsigned mode_mask, const jmb_quant_desc *q,
+                            jmb_tq_head *heads, jmb_tq_token *tokens, uint32_t token_cap, uint32_t *n_tokens, int loc) {
+  int rc = check_qdesc(ctx, q); if (rc) return rc;
+  if (!ctx->cur || ctx->nref == 0) return jmb_fail(ctx, JMB_ERR_STATE, "jmb_mc_tq_modes_compact: call jmb_pic_begin first");
+  const int mb_w = ctx->cur_w / 16, mb_total = mb_w * (ctx->cur_h / 16);
+  if (n_mb <= 0 || n_mb > mb_total) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_mc_tq_modes_compact: n_mb %d (picture has %d)", n_mb, mb_total);
+  if (!mode_mask || (mode_mask >> 7)) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_mc_tq_modes_compact: mode_mask 0x%x (bits 0..6 = modes 1..7)", mode_mask);
+  if (q->n == 8 && (mode_mask >> 4)) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_mc_tq_modes_compact: the 8x8 transform applies to modes 1..4 only");
+  if (q->around) return jmb_fail(ctx, JMB_ERR_UNSUPPORTED, "jmb_mc_tq_modes_compact: adaptive rounding is a leaf-form feature (jmb_quant_blocks)");
+  if (!heads || !tokens || !n_tokens || !token_cap) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_mc_tq_modes_compact: NULL output");
+  if (loc == JMB_HOST_ASYNC) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_mc_tq_modes_compact: the token count decides the second copy; use JMB_HOST or JMB_DEVICE");
+  JMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const jmb_ref &r0 = ctx->refs[ctx->ref_list[0]];
+  const jmb_me_res *d_res = res;
+  if (!res) {
+    if (!ctx->last_res || ctx->last_res_n < n_mb * 41) return jmb_fail(ctx, JMB_ERR_STATE, "jmb_mc_tq_modes_compact: no resident search results for %d macroblocks", n_mb);
+    d_res = ctx->last_res;
+  } else if (loc == JMB_HOST) {
+    rc = jmb_reserve_dev(ctx, &ctx->d_stage4, &ctx->d_stage4_cap, (size_t)n_mb * 41 * sizeof(jmb_me_res)); if (rc) return rc;
+    JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage4, res, (size_t)n_mb * 41 * sizeof(jmb_me_res), cudaMemcpyHostToDevice, ctx->stream));
+    d_res = (const jmb_me_res *)ctx->d_stage4;
+  }
+  const size_t n7 = (size_t)7 * n_mb;
+  if (!ctx->d_tok_count) {
+    JMB_CUDA(ctx, cudaMalloc(&ctx->d_tok_count, sizeof(unsigned)));
+    JMB_CUDA(ctx, cudaHostAlloc(&ctx->h_tok_count, sizeof(unsigned), cudaHostAllocDefault));
+  }
+  jmb_tq_head *d_heads = heads; jmb_tq_token *d_tok = tokens; unsigned *d_cnt = ctx->d_tok_count;
+  if (loc == JMB_HOST) {
+    rc = jmb_reserve_dev(ctx, &ctx->d_heads, &ctx->d_heads_cap, n7 * sizeof(jmb_tq_head)); if (rc) return rc;
+    rc = jmb_reserve_dev(ctx, &ctx->d_tokens, &ctx->d_tokens_cap, (size_t)token_cap * sizeof(jmb_tq_token)); if (rc) return rc;
+    d_heads = (jmb_tq_head *)ctx->d_heads; d_tok = (jmb_tq_token *)ctx->d_tokens;
+  }
+  JMB_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned), ctx->stream));
+  for (int m = 0; m < 7; m++)      // modes outside the mask: empty heads
+    if (!((mode_mask >> m) & 1)) JMB_CUDA(ctx, cudaMemsetAsync(d_heads + (size_t)m * n_mb, 0, (size_t)n_mb * sizeof(jmb_tq_head), ctx->stream));
+  jmb_time_begin(ctx, JMB_K_MC_TQ);
+#define JMB_MTQC(NN, STD, GRID) k_mc_tq_modes_c<NN, STD><<<GRID, 128, 0, ctx->stream>>>(d_res, n_mb, mb_w, mode_mask, *q, ctx->cur, ctx->cur_pitch, \
+        r0.planes, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_heads, d_tok, token_cap, d_cnt)
+  {
+    const int kind = std_scan_kind(q);
+    const dim3 g4((n_mb * 16 + 127) / 128, 7), g8((n_mb * 4 + 127) / 128, 7);
+    if (q->n == 4) { if (kind == 1) JMB_MTQC(4, 1, g4); else JMB_MTQC(4, 0, g4); }
+    else if (kind == 1) JMB_MTQC(8, 1, g8); else if (kind == 2) JMB_MTQC(8, 2, g8); else JMB_MTQC(8, 0, g8);
+  }
+#undef JMB_MTQC
+  jmb_time_end(ctx, JMB_K_MC_TQ);
+  JMB_LAUNCH_CHECK(ctx);
+  if (loc == JMB_HOST) {
+    JMB_CUDA(ctx, cudaMemcpyAsync(heads, d_heads, n7 * sizeof(jmb_tq_head), cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaMemcpyAsync(ctx->h_tok_count, d_cnt, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_tokens = *ctx->h_tok_count;
+    if (*n_tokens > token_cap) return jmb_fail(ctx, JMB_ERR_STATE, "jmb_mc_tq_modes_compact: %u tokens produced, room for %u", *n_tokens, token_cap);
+    if (*n_tokens) {
+      JMB_CUDA(ctx, cudaMemcpyAsync(tokens, d_tok, (size_t)*n_tokens * sizeof(jmb_tq_token), cudaMemcpyDeviceToHost, ctx->stream));
+      JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+  } else {
+    JMB_CUDA(ctx, cudaMemcpyAsync(n_tokens, d_cnt, sizeof(unsigned), cudaMemcpyDeviceToDevice, ctx->stream));
   }
   return JMB_OK;
 }

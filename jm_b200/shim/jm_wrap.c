@@ -364,6 +364,8 @@ void __wrap_setup_fast_full_search(Macroblock *currMB, MEBlock *mv_block, int li
   PixelPos block[4];
   if (!shim_on(FAM_ME)) { __real_setup_fast_full_search(currMB, mv_block, list); return; }
   if (!p_Inp->rdopt) unsupported("RDOptimization=0 with fast full search");
+  /* setup_fast_full_search builds SQUARED-error surfaces for any full-pel metric but SAD (dist_method, me_fullfast.c:274) */
+  if (p_Inp->MEErrorMetric[F_PEL] != ERROR_SAD) unsupported("fast full search with MEDistortionFPel other than SAD (squared-error BlockSAD surfaces)");
   if (mv_block->apply_weights) unsupported("fast full search with UseWeightedReferenceME (its weighted SAD surfaces are inline host code; use SearchMode -1 or 3)");
   get_neighbors(currMB, block, 0, 0, 16);
   currMB->GetMVPredictor(currMB, block, &pmv, ref, p_Vid->enc_picture->mv_info, list, 0, 0, 16, 16);

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 18
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/jmb200.h but not exported"
-    assert lib.jmb_abi_version() == 1
+    assert lib.jmb_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
