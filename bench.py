@@ -138,7 +138,7 @@ class Workload:
             self.mode_mask = 0x0F
         mode = api.SEARCH_FAST_FULL if self.cfg["search"] == "fastfull" else api.SEARCH_FULL
         self.fp = api.frame_params([self.lam] * 3, mode=mode, flags=api.REQ_SUBPEL | (api.REQ_TEST8X8 if n == 8 else 0))
-        self.token_cap = 7 * self.n_mb * 24
+        self.token_cap = 7 * self.n_mb * (256 if args.scene_cut else 96)      # 256 per (mode, macroblock) is the hard maximum
         dev = f"cuda:{local}"
         anchor = bool(self.cfg.get("anchor"))
         self.sets = []
@@ -296,6 +296,21 @@ def run_ours(args):
     ctx.timing(False)
     ctx.sync()
     tokens_dev = int(wl.d_ntok.item())
+    worst_ms = None
+    if not args.scene_cut and not args.no_worst:
+        # worst case of the search gate: the reference is an unrelated picture (nothing matches, every bound stays loose)
+        f = synth.luma_frames(wl.W, wl.H, 1, seed=999)[0].astype(np.uint8)
+        d_cut = torch.from_numpy(f.reshape(-1).copy()).to(f"cuda:{local}")
+        hs, ds = wl.sets[0]
+        for it in range(4):
+            if it == 1:
+                ctx.timing(True)
+            ctx.ref_put_u8(0, d_cut.data_ptr(), api.DEVICE, shape=(wl.H, wl.W))
+            ctx.pic_begin_u8(ds["cur"].data_ptr(), [0], api.DEVICE, shape=(wl.H, wl.W))
+            ctx.me_search_frame_pred(ds["pred"].data_ptr(), wl.fp, wl.d_res8.data_ptr(), api.DEVICE, n_mb=n_mb)
+        w_ms, w_n = ctx.timing_get("int_search")
+        worst_ms = w_ms / max(1, w_n)
+        ctx.timing(False)
     if world > 1:
         t = torch.tensor([ms], device=f"cuda:{local}"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
 
@@ -343,6 +358,7 @@ def run_ours(args):
     out["roofline"] = {"bound": "hbm", "kernel": "k_int_search", "achieved": achieved, "peak": peak, "unit": "GB/s",
                        "frac": achieved / peak, "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
                        "algorithmic_bytes_per_launch": BYTES_PER_MB_REF * n_mb, "launch_ms": k_ms / max(1, k_n),
+                       "worst_case_launch_ms": worst_ms,
                        "note": "search-window model of SURVEY 8(d): 13804 B per macroblock*reference; the kernel is ALU-pipe "
                                "(VABSDIFF4/PRMT/ISETP) bound, not HBM bound -- DESIGN.md 3; traffic < algorithmic bytes because "
                                "neighbouring windows hit L2"}
@@ -501,6 +517,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configs[1..4] (default 2 = configs[1])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-worst", action="store_true", help="skip the worst-case (unrelated reference) probe of the search kernel")
     ap.add_argument("--scene-cut", action="store_true", help="probe: unrelated reference picture (worst case for the search gate)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-mbs-per-core", type=int, default=160)

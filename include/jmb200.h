@@ -222,6 +222,75 @@ typedef struct jmb_me_res8 {
 /* res may be NULL (results stay on the device for jmb_mc_tq_modes* / jmb_luma_residual_coding_modes with res = NULL) */
 int jmb_me_search_frame_pred(jmb_ctx *ctx, const jmb_mb_mvpred *pred, int n_mb, const jmb_frame_params *fp, jmb_me_res8 *res, int loc);
 
+/* ---- EPZS (SearchMode 3) --------------------------------------------------------------------------------------------
+ * One request = one EPZS_integer_motion_estimation call (lencod/src/me_epzs_int.c:42-426) followed, with JMB_EPZS_SUBPEL, by
+ * what BlockMotionSearch does next (mv_search.c:964-976): EPZS_sub_pel_motion_estimation (lencod/src/me_epzs_sub.c:30-213).
+ * The whole state machine runs on the device, one warp per request: centre check, early terminations against the previous
+ * distortions, the ordered predictor list, the refinement pattern walk (pattern_data, me_epzs_common.c:48-76) incl. the
+ * second-best ("dual") pass, and the sub-pel stage.  The caller supplies what JM's HOST state holds:
+ *   - the predictor list in up to four segments, in JM's generator order, each behind the cost gate its generator sits
+ *     behind in JM: segment s is checked when gate[s] == 0 or centre cost > gate[s] * stop
+ *     (spatial / spatial-memory / hierarchical / co-located: always; the co-located block's neighbours
+ *     me_epzs_common.c:1556: gate 1; window predictors me_epzs_int.c:193-203: gate 0 or 3; block-type predictors :211: 0 or 2);
+ *   - stop = EPZSDetermineStopCriterion(...) (me_epzs_common.c:1874), medthres / subthres of the block type (:454-457),
+ *     prev_sad = *prevSad (p_EPZS->distortion[list][blocktype-1][pos_x>>2]);
+ *   - range_x/y = mv_block->searchRange.max_x/max_y in quarter-pel (candidates further from the start mv are skipped).
+ * Candidate lists: cands[2 * (cand_off + i)] = mv_x, [+1] = mv_y (motion vectors, quarter-pel).
+ * Sub-pel stage metrics / start positions come from jmb_me_configure (metric[1], metric[2], start_hp, start_qp,
+ * search_pos2); start_qp must be 1 (JM indexes next_start_pos[][-1] otherwise, me_epzs_sub.c:141,182). */
+enum { JMB_EPZS_PAT_SDIAMOND = 0, JMB_EPZS_PAT_SQUARE = 1, JMB_EPZS_PAT_EDIAMOND = 2, JMB_EPZS_PAT_LDIAMOND = 3,
+       JMB_EPZS_PAT_SBDIAMOND = 4, JMB_EPZS_PAT_PMVFAST = 5 };
+#define JMB_EPZS_REF_GT0_FRAME 1   /* ref > 0 in a frame picture: the prevSad early exits apply (:103, :254, :362) */
+#define JMB_EPZS_ADAPT_PATTERN 2   /* EPZSPattern != 0 (:286) */
+#define JMB_EPZS_SQUARE_HINT   4   /* ref > 0 && blocktype != 1 (:296) */
+#define JMB_EPZS_DUAL          8   /* EPZSDualRefinement > 0 (:384) */
+#define JMB_EPZS_SUBPEL       16   /* continue with the sub-pel stage */
+#define JMB_EPZS_TEST8X8      32   /* MEBlock.test8x8: SATD on 8x8 sub-blocks */
+#define JMB_EPZS_SKIP_INT     64   /* sub-pel stage only: start_x/y = the integer-stage mv, min_mcost = the cost handed to SubPelME */
+#define JMB_EPZS_WINDOW_GEN  128   /* segment 2 is JM's window_predictor set (EPZSWindowPredictorInit mode 0, me_epzs_common.c:352-371) and
+                                      is generated on the device, not read from the list: n_cand[2] = 8 * rings - 1 points around the start
+                                      mv at distances range_x >> (rings - 1), ..., range_x >> 0, eight per ring in JM's order */
+typedef struct jmb_epzs_req {      /* 88 bytes */
+  int16_t pos_x, pos_y;            /* block origin, pels */
+  int16_t pred_x, pred_y;          /* pred_mv, quarter-pel */
+  int16_t start_x, start_y;        /* *mv on entry, quarter-pel */
+  uint8_t blocktype, ref, flags, pattern;   /* pattern = p_EPZS->searchPattern (JMB_EPZS_PAT_*) */
+  uint8_t pattern_dual, jm_ref, reserved_[2];   /* p_EPZS->searchPatternD; jm_ref = mv_block->ref_idx: JM's rules that tell reference 0
+                                                   from the others read this, `ref` only selects the picture in the device list */
+  uint8_t n_cand[4], gate[4];
+  int32_t cand_off;
+  int32_t lambda[3];               /* lambda_factor[F_PEL, H_PEL, Q_PEL] */
+  int16_t range_x, range_y;
+  int64_t stop, medthres, prev_sad, subthres, min_mcost;
+} jmb_epzs_req;
+typedef struct jmb_epzs_res {      /* 40 bytes */
+  int16_t mv_x, mv_y;              /* final mv */
+  int16_t imv_x, imv_y;            /* mv the integer stage leaves in *mv (= what goes to p_motion) */
+  int64_t cost, icost;             /* returned by SubPelME / by EPZS_integer_motion_estimation */
+  int64_t prev_sad;                /* *prevSad as the integer stage leaves it */
+  int32_t exit_code;               /* which return of the integer stage: 1 :103, 2 :135, 3 :254, 4 :362, 5 the end */
+  int32_t n_evals;                 /* distortions evaluated (diagnostic; parallel evaluation may count a few more than JM) */
+} jmb_epzs_res;
+int jmb_epzs_search(jmb_ctx *ctx, const jmb_epzs_req *reqs, int n, const int16_t *cands, int n_cands, jmb_epzs_res *res, int loc);
+
+/* Whole-picture form with the requests generated on the device: per macroblock the 41 predictors (= start mvs, EPZSSubPelGrid)
+ * and n_shared candidate mvs checked by every partition of the macroblock (what the spatial / co-located generators yield for
+ * a macroblock whose neighbours' motion the caller knows), plus the window predictors around the start mv when `window` is set
+ * (gate 3); thresholds per block type.  Results as jmb_me_search_frame_pred. */
+typedef struct jmb_epzs_frame_params {
+  int32_t lambda[3];
+  int32_t flags;                   /* JMB_EPZS_ADAPT_PATTERN | JMB_EPZS_DUAL | JMB_EPZS_SUBPEL | JMB_EPZS_TEST8X8 (block types <= 4) */
+  int32_t ref;
+  int32_t pattern, pattern_dual;
+  int32_t n_shared;                /* candidates per macroblock in `shared` (<= 32) */
+  int32_t window;                  /* 0: none; else window predictors +-(4 << k), k = 0..window-1, 8 per ring (EPZSWindowPredictorInit) */
+  int32_t range;                   /* searchRange.max_x = max_y, quarter-pel */
+  int32_t medthres[8], minthres[8], maxthres[8], subthres[8];
+  int32_t mv_min_x, mv_max_x, mv_min_y, mv_max_y;
+} jmb_epzs_frame_params;
+int jmb_epzs_search_frame(jmb_ctx *ctx, const jmb_mb_mvpred *pred, const int16_t *shared, int n_mb, const jmb_epzs_frame_params *fp,
+                          jmb_me_res8 *res, int loc);
+
 /* BlockSAD surfaces of one macroblock exactly as setup_fast_full_search leaves them:
  * out[(blocktype*16 + slot) * max_pos + pos], blocktype 1..7, uint32 (distpel), spiral order.
  * (lencod/src/me_fullfast.c:59-81 allocation, :492-556, :196-260) */

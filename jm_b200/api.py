@@ -39,6 +39,23 @@ ME_RES8 = np.dtype([("mv_x", "<i2"), ("mv_y", "<i2"), ("cost", "<i4")])
 TQ_HEAD = np.dtype([("cbp_blk", "<u4"), ("token_off", "<u4"), ("n_tokens", "<u2"), ("cost8", "u1", (4,)), ("reserved_", "<u2")])
 TQ_TOKEN = np.dtype([("level", "<i2"), ("run", "u1"), ("blk", "u1")])
 assert MB_MVPRED.itemsize == 164 and FRAME_PARAMS.itemsize == 40 and ME_RES8.itemsize == 8 and TQ_HEAD.itemsize == 16 and TQ_TOKEN.itemsize == 4
+EPZS_REQ = np.dtype([("pos_x", "<i2"), ("pos_y", "<i2"), ("pred_x", "<i2"), ("pred_y", "<i2"), ("start_x", "<i2"), ("start_y", "<i2"),
+                     ("blocktype", "u1"), ("ref", "u1"), ("flags", "u1"), ("pattern", "u1"), ("pattern_dual", "u1"), ("jm_ref", "u1"), ("reserved_", "u1", (2,)),
+                     ("n_cand", "u1", (4,)), ("gate", "u1", (4,)), ("cand_off", "<i4"), ("lambda", "<i4", (3,)),
+                     ("range_x", "<i2"), ("range_y", "<i2"), ("stop", "<i8"), ("medthres", "<i8"), ("prev_sad", "<i8"),
+                     ("subthres", "<i8"), ("min_mcost", "<i8")])
+EPZS_RES = np.dtype([("mv_x", "<i2"), ("mv_y", "<i2"), ("imv_x", "<i2"), ("imv_y", "<i2"), ("cost", "<i8"), ("icost", "<i8"),
+                     ("prev_sad", "<i8"), ("exit_code", "<i4"), ("n_evals", "<i4")])
+EPZS_FRAME_PARAMS = np.dtype([("lambda", "<i4", (3,)), ("flags", "<i4"), ("ref", "<i4"), ("pattern", "<i4"), ("pattern_dual", "<i4"),
+                              ("n_shared", "<i4"), ("window", "<i4"), ("range", "<i4"), ("medthres", "<i4", (8,)), ("minthres", "<i4", (8,)),
+                              ("maxthres", "<i4", (8,)), ("subthres", "<i4", (8,)), ("mv_min_x", "<i4"), ("mv_max_x", "<i4"),
+                              ("mv_min_y", "<i4"), ("mv_max_y", "<i4")])
+assert EPZS_REQ.itemsize == 88 and EPZS_RES.itemsize == 40 and EPZS_FRAME_PARAMS.itemsize == 184
+EPZS_REF_GT0_FRAME, EPZS_ADAPT_PATTERN, EPZS_SQUARE_HINT, EPZS_DUAL, EPZS_SUBPEL, EPZS_TEST8X8, EPZS_SKIP_INT, EPZS_WINDOW_GEN = 1, 2, 4, 8, 16, 32, 64, 128
+# MED / MIN / MAX_THRES_BASE of lencod/src/me_epzs_common.c:34-37 scaled as EPZSStructInit does (:454-457): costs carry 5 fractional bits
+EPZS_MIN_BASE = [0, 64, 32, 32, 16, 8, 8, 4]
+EPZS_MED_BASE = [0, 192, 96, 96, 48, 24, 24, 12]
+EPZS_MAX_BASE = [0, 768, 384, 384, 192, 96, 96, 48]
 IPC_HANDLE_BYTES = 64
 # level 4 .. 5.1 mv range in quarter-pel (LEVELHMVLIMIT / LEVELVMVLIMIT, lencod/src/conformance.c): +-2048 x +-512 pels
 MV_RANGE_L51 = (-8192, 8191, -2048, 2047)
@@ -94,6 +111,8 @@ def load_library():
     L.jmb_pic_begin_u8.argtypes = [vp, vp, i, i, i, i, C.POINTER(i), i]
     L.jmb_me_search_frame_pred.argtypes = [vp, vp, i, vp, vp, i]
     L.jmb_mc_tq_modes_compact.argtypes = [vp, vp, i, C.c_uint, vp, vp, vp, C.c_uint32, vp, i]
+    L.jmb_epzs_search.argtypes = [vp, vp, i, vp, i, vp, i]
+    L.jmb_epzs_search_frame.argtypes = [vp, vp, vp, i, vp, vp, i]
     L.jmb_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     L.jmb_dev_free.argtypes = [vp, vp]
     L.jmb_dev_copy.argtypes = [vp, vp, vp, C.c_size_t, i, i]
@@ -187,6 +206,48 @@ def requests_from_pred(pred, fp, mb_w, search_range):
     reqs["mode"] = int(fp["mode"]); reqs["ref"] = int(fp["ref"])
     reqs["lambda"] = fp["lambda"]
     reqs["min_mcost"] = DISTBLK_MAX
+    return reqs.reshape(-1)
+
+
+def epzs_frame_params(lam, flags=EPZS_ADAPT_PATTERN | EPZS_DUAL | EPZS_SUBPEL, ref=0, pattern=2, pattern_dual=2, n_shared=0, window=0,
+                      search_range=32, scales=(0, 1, 2, 1), mv_range=MV_RANGE_L51):
+    """Defaults = bin/encoder.cfg: EPZSPattern 2 (extended diamond), EPZSDualRefinement 3 (extended diamond), threshold scalers
+    EPZSMinThresScale 0, Med 1, Max 2, SubPel 1.  Thresholds are costs: base * scale << 5 (up_scale, me_epzs_common.c:459)."""
+    fp = np.zeros(1, EPZS_FRAME_PARAMS)
+    fp["lambda"] = lam; fp["flags"] = flags; fp["ref"] = ref; fp["pattern"] = pattern; fp["pattern_dual"] = pattern_dual
+    fp["n_shared"] = n_shared; fp["window"] = window; fp["range"] = 4 * search_range
+    fp["minthres"][0] = [scales[0] * b << 5 for b in EPZS_MIN_BASE]; fp["medthres"][0] = [scales[1] * b << 5 for b in EPZS_MED_BASE]
+    fp["maxthres"][0] = [scales[2] * b << 5 for b in EPZS_MAX_BASE]; fp["subthres"][0] = [scales[3] * b << 5 for b in EPZS_MED_BASE]
+    fp["mv_min_x"], fp["mv_max_x"], fp["mv_min_y"], fp["mv_max_y"] = mv_range
+    return fp
+
+
+def epzs_requests_from_frame(pred, fp, mb_w):
+    """The jmb_epzs_req list jmb_epzs_search_frame generates on the device (same rules; tests and the CPU legs)."""
+    fp = fp[0]
+    n_mb = len(pred)
+    reqs = np.zeros((n_mb, NPART), EPZS_REQ)
+    mbx = (np.arange(n_mb) % mb_w) * 16; mby = (np.arange(n_mb) // mb_w) * 16
+    big = DISTBLK_MAX
+    ld = 2 * int(fp["lambda"][0])
+    for k, (t, x, y) in enumerate(mb_partitions()):
+        p = pred["pred"][:, k].astype(np.int32)
+        reqs["pos_x"][:, k] = mbx + x; reqs["pos_y"][:, k] = mby + y
+        reqs["pred_x"][:, k] = p[:, 0]; reqs["pred_y"][:, k] = p[:, 1]
+        reqs["start_x"][:, k] = np.clip(p[:, 0], fp["mv_min_x"], fp["mv_max_x"]); reqs["start_y"][:, k] = np.clip(p[:, 1], fp["mv_min_y"], fp["mv_max_y"])
+        reqs["blocktype"][:, k] = t
+        reqs["flags"][:, k] = (int(fp["flags"]) & (EPZS_ADAPT_PATTERN | EPZS_DUAL | EPZS_SUBPEL | (EPZS_TEST8X8 if t <= 4 else 0))) | (EPZS_WINDOW_GEN if fp["window"] else 0)
+        med = int(fp["medthres"][t])
+        stop = min(max(big, int(fp["minthres"][t])), int(fp["maxthres"][t]) + ld)
+        stop = ((8 * max(med + ld, stop) + med) >> 3) + ld
+        reqs["stop"][:, k] = stop; reqs["medthres"][:, k] = med; reqs["subthres"][:, k] = int(fp["subthres"][t])
+    reqs["ref"] = int(fp["ref"]); reqs["jm_ref"] = int(fp["ref"]); reqs["pattern"] = int(fp["pattern"]); reqs["pattern_dual"] = int(fp["pattern_dual"])
+    reqs["n_cand"][:, :, 0] = int(fp["n_shared"]); reqs["n_cand"][:, :, 2] = 8 * int(fp["window"]) - 1 if fp["window"] else 0
+    reqs["gate"][:, :, 2] = 3
+    reqs["cand_off"] = (np.arange(n_mb) * int(fp["n_shared"]))[:, None]
+    reqs["lambda"] = fp["lambda"]
+    reqs["range_x"] = reqs["range_y"] = int(fp["range"])
+    reqs["prev_sad"] = big; reqs["min_mcost"] = big
     return reqs.reshape(-1)
 
 
@@ -310,6 +371,24 @@ class Context:
         if loc == HOST:
             return heads, tokens[:int(n_tok[0])]
         return heads, tokens, n_tok
+
+    def epzs_search(self, reqs, cands, loc=HOST, res=None, n=None, n_cands=None):
+        if loc != DEVICE:
+            reqs = np.ascontiguousarray(reqs, EPZS_REQ); n = len(reqs)
+            cands = np.ascontiguousarray(cands, np.int16).reshape(-1, 2); n_cands = len(cands)
+            if res is None:
+                res = np.zeros(n, EPZS_RES)
+        self._ck(self.L.jmb_epzs_search(self.h, _ptr(reqs), n, _ptr(cands) if n_cands else None, n_cands, _ptr(res), loc))
+        return res
+
+    def epzs_search_frame(self, pred, shared, fp, res=None, loc=HOST, n_mb=None, want_res=True):
+        if loc != DEVICE:
+            n_mb = len(pred)
+            if res is None and want_res:
+                res = np.zeros(n_mb * NPART, ME_RES8)
+        self._ck(self.L.jmb_epzs_search_frame(self.h, _ptr(pred), None if shared is None else _ptr(shared), n_mb, _ptr(fp),
+                                              None if res is None else _ptr(res), loc))
+        return res
 
     def dev_alloc(self, nbytes):
         p = C.c_void_p()

@@ -56,6 +56,7 @@ struct jmb_ctx {
   // index of one offending request into d_err[0..1], which every synchronising call reads back
   int *d_err = nullptr; int *h_err = nullptr;
   bool smem_opt_in = false;   // k_int_search's dynamic shared memory opt-in done on this context's device
+  size_t epzs_smem = 0;       // dynamic shared memory k_epzs has been opted in for
   // picture form with device-generated requests / compact outputs
   void *d_mvpred = nullptr; size_t d_mvpred_cap = 0;
   void *d_res8 = nullptr; size_t d_res8_cap = 0;

@@ -54,6 +54,9 @@
 #include "quantChroma.h"
 #include "me_distortion.h"
 #include "mv_prediction.h"
+#include "me_epzs.h"
+#include "me_epzs_int.h"
+#include "me_epzs_common.h"
 
 #include "jmb200.h"
 
@@ -99,6 +102,8 @@ void    __real_hadamard4x2(int **, int **);
 void    __real_ihadamard4x2(int **, int **);
 void    __real_hadamard2x2(int **, int *);
 void    __real_ihadamard2x2(int *, int *);
+distblk __real_EPZS_integer_motion_estimation(Macroblock *, MotionVector *, MEBlock *, distblk, int);
+distblk __real_EPZS_sub_pel_motion_estimation(Macroblock *, MotionVector *, MEBlock *, distblk, int *);
 distblk __real_computeSAD(StorablePicture *, MEBlock *, distblk, MotionVector *);
 distblk __real_computeSSE(StorablePicture *, MEBlock *, distblk, MotionVector *);
 distblk __real_computeSATD(StorablePicture *, MEBlock *, distblk, MotionVector *);
@@ -461,6 +466,263 @@ distblk __wrap_sub_pel_motion_estimation(Macroblock *currMB, MotionVector *pred,
   q.lambda[2] = lambda[Q_PEL];
   rc = jmb_me_search(S.ctx, &q, 1, &r, JMB_HOST);
   if (rc) jmb_die("jmb_me_search(sub-pel)", rc);
+  mv->mv_x = r.mv_x;
+  mv->mv_y = r.mv_y;
+  return (distblk)r.cost;
+}
+
+
+/* ---- EPZS (SearchMode 3 with EPZSSubPelGrid: currMB->IntPelME = EPZS_integer_motion_estimation, me_epzs_common.c:155;
+ *      currMB->SubPelME = EPZS_sub_pel_motion_estimation with EPZSSubPelME = 1) --------------------------------------------
+ * The state machine of a search runs on the device in ONE call (jmb_epzs_search).  What stays here is JM's host state:
+ * the predictor generators (JM's own functions, called in JM's order, me_epzs_int.c:152-212) fill p_EPZS->predictor->point;
+ * the wrapper only notes where each generator's output starts and which cost gate JM puts in front of it, so that the
+ * device can apply the gate once it knows the cost of the start mv.  The two generators that take the start cost as an
+ * argument are called with both outcomes (EPZS_temporal_predictors with a cost below and above the stop criterion: the
+ * co-located predictor comes first either way, its neighbours only in the second case).
+ * JMB_EPZS_CAPTURE=<file> (with JMB_SHIM=passthrough, CPU only): every call is recorded -- request, predictor list, the
+ * pictures, and what JM's REAL function returned -- for tests/golden/make_epzs_golden.py, which pins the oracle. */
+static FILE *epzs_cap;
+static int   epzs_cap_init;
+static struct { StorablePicture *pic; int poc; } epzs_cap_ref[64];
+static int   epzs_cap_nref, epzs_cap_cur_id = -1, epzs_cap_cur_poc = -0x7fffffff;
+static unsigned long epzs_cap_calls;
+
+static int epzs_capture_on(void)
+{
+  if (!epzs_cap_init)
+  {
+    const char *f = getenv("JMB_EPZS_CAPTURE");
+    epzs_cap_init = 1;
+    if (f) { epzs_cap = fopen(f, "wb"); if (!epzs_cap) { snprintf(errortext, ET_SIZE, "cannot open %s", f); fatal(704); } }
+  }
+  return epzs_cap != NULL;
+}
+
+static void epzs_cap_picture(int id, imgpel **img, int w, int h)
+{
+  int32_t hdr[4] = {1, id, w, h};
+  int x, y;
+  fwrite(hdr, 4, 4, epzs_cap);
+  for (y = 0; y < h; y++) for (x = 0; x < w; x++) fputc((int)img[y][x], epzs_cap);
+}
+
+static void epzs_cap_ids(VideoParameters *p_Vid, StorablePicture *ref, int *ref_id, int *cur_id)
+{
+  int i;
+  for (i = 0; i < epzs_cap_nref; i++) if (epzs_cap_ref[i].pic == ref && epzs_cap_ref[i].poc == ref->poc) break;
+  if (i == epzs_cap_nref)
+  {
+    if (epzs_cap_nref == 64) epzs_cap_nref = 0, i = 0;
+    epzs_cap_ref[i].pic = ref; epzs_cap_ref[i].poc = ref->poc; epzs_cap_nref++;
+    epzs_cap_picture(1000 + ref->poc * 64 + i, ref->imgY, ref->size_x, ref->size_y);
+  }
+  *ref_id = 1000 + ref->poc * 64 + i;
+  if (epzs_cap_cur_poc != p_Vid->enc_picture->poc)
+  {
+    epzs_cap_cur_poc = p_Vid->enc_picture->poc;
+    epzs_cap_cur_id = 500000 + epzs_cap_cur_poc;
+    epzs_cap_picture(epzs_cap_cur_id, p_Vid->pCurImg, p_Vid->width, p_Vid->height);
+  }
+  *cur_id = epzs_cap_cur_id;
+}
+
+static int epzs_pattern_id(VideoParameters *p_Vid, EPZSStructure *p)
+{
+  if (p == p_Vid->sdiamond)  return JMB_EPZS_PAT_SDIAMOND;
+  if (p == p_Vid->square)    return JMB_EPZS_PAT_SQUARE;
+  if (p == p_Vid->ediamond)  return JMB_EPZS_PAT_EDIAMOND;
+  if (p == p_Vid->ldiamond)  return JMB_EPZS_PAT_LDIAMOND;
+  if (p == p_Vid->sbdiamond) return JMB_EPZS_PAT_SBDIAMOND;
+  if (p == p_Vid->pmvfast)   return JMB_EPZS_PAT_PMVFAST;
+  unsupported("an EPZS refinement pattern that is not one of JM's six");
+  return 0;
+}
+
+#define EPZS_MAX_CANDS 512
+/* the request of one EPZS_integer_motion_estimation call; returns the number of candidates written to cands (x,y pairs) */
+static int epzs_build_request(Macroblock *currMB, MotionVector *pred_mv, MEBlock *mv_block, int lambda_factor, jmb_epzs_req *q, int16_t *cands)
+{
+  Slice *currSlice = currMB->p_Slice;
+  VideoParameters *p_Vid = currMB->p_Vid;
+  InputParameters *p_Inp = currMB->p_Inp;
+  EPZSParameters *p_EPZS = currSlice->p_EPZS;
+  int blocktype = mv_block->blocktype, list = mv_block->list, cur_list = list + currMB->list_offset, ref = mv_block->ref_idx;
+  MotionVector *mv = &mv_block->mv[list];
+  StorablePicture *ref_picture = currSlice->listX[cur_list][ref];
+  distblk lambda_dist = weighted_cost(lambda_factor, 2);
+  distblk *prevSad = &p_EPZS->distortion[cur_list][blocktype - 1][mv_block->pos_x2];
+  SPoint *point = p_EPZS->predictor->point;
+  int prednum = 5, seg_end[4], s, i, k = 0, n0, frame_gt0 = (ref > 0 && currSlice->structure == FRAME), fixed3_border, static_ok;
+  short invalid_refs;
+
+  memset(q, 0, sizeof(*q));
+  q->pos_x = mv_block->pos_x;  q->pos_y = mv_block->pos_y;
+  q->pred_x = pred_mv->mv_x;   q->pred_y = pred_mv->mv_y;
+  q->start_x = mv->mv_x;       q->start_y = mv->mv_y;
+  q->blocktype = (uint8_t)blocktype;
+  q->jm_ref = (uint8_t)ref;
+  q->lambda[0] = lambda_factor;
+  q->range_x = (int16_t)mv_block->searchRange.max_x;  q->range_y = (int16_t)mv_block->searchRange.max_y;
+  q->pattern = (uint8_t)epzs_pattern_id(p_Vid, p_EPZS->searchPattern);
+  q->pattern_dual = (uint8_t)epzs_pattern_id(p_Vid, p_EPZS->searchPatternD);
+  q->flags = (uint8_t)((frame_gt0 ? JMB_EPZS_REF_GT0_FRAME : 0) | (p_Inp->EPZSPattern != 0 ? JMB_EPZS_ADAPT_PATTERN : 0) |
+                       ((ref > 0 && blocktype != 1) ? JMB_EPZS_SQUARE_HINT : 0) | (p_Inp->EPZSDual > 0 ? JMB_EPZS_DUAL : 0));
+  q->medthres = p_EPZS->medthres[blocktype];
+  q->subthres = p_EPZS->subthres[blocktype];
+  q->prev_sad = *prevSad;
+  q->stop = EPZSDetermineStopCriterion(p_EPZS, prevSad, mv_block, lambda_dist);
+  q->min_mcost = DISTBLK_MAX;
+
+  /* segment 0: generators JM always runs (me_epzs_int.c:152-170) + the co-located predictor */
+  invalid_refs = EPZS_spatial_predictors(p_EPZS, mv_block, list, currMB->list_offset, ref, p_Vid->enc_picture->mv_info);
+  if (p_Inp->EPZSSpatialMem) EPZS_spatial_memory_predictors(p_EPZS, mv_block, cur_list, &prednum, ref_picture->size_x >> 2);
+  if (p_Inp->HMEEnable == 1 && p_Inp->EPZSUseHMEPredictors == 1) EPZS_hierarchical_predictors(p_EPZS, mv_block, &prednum, ref_picture, currSlice);
+  n0 = prednum;
+#if (MVC_EXTENSION_ENABLE)
+  if (p_Inp->EPZSTemporal[currSlice->view_id])
+#else
+  if (p_Inp->EPZSTemporal)
+#endif
+  {
+    EPZS_temporal_predictors(currMB, ref_picture, p_EPZS, mv_block, &prednum, q->stop, 0);                 /* start cost <= stop */
+    seg_end[0] = prednum;
+    prednum = n0;
+    EPZS_temporal_predictors(currMB, ref_picture, p_EPZS, mv_block, &prednum, q->stop, DISTBLK_MAX);       /* start cost > stop */
+    seg_end[1] = prednum;                                                                                   /* segment 1: gate 1 */
+    q->gate[1] = 1;
+  }
+  else seg_end[0] = seg_end[1] = prednum;
+  /* segment 2: window predictors (:193-203) */
+  fixed3_border = (p_Inp->EPZSFixed == 3 && (currMB->mb_x == 0 || currMB->mb_y == 0));
+  static_ok = ((ref < 2 && blocktype < 4) || (ref < 1 && blocktype == 4) || ((currSlice->structure != FRAME || currMB->list_offset) && ref < 3))
+              && (p_Inp->EPZSFixed > 1 || (p_Inp->EPZSFixed && currSlice->slice_type == P_SLICE));
+  if (fixed3_border || static_ok)
+  {
+    EPZSWindowPredictors(mv, p_EPZS->predictor, &prednum,
+                         (p_Inp->EPZSAggressiveWindow != 0) || ((invalid_refs > 2) && (ref < 1 + (currSlice->structure != FRAME || currMB->list_offset)))
+                         ? p_EPZS->window_predictor_ext : p_EPZS->window_predictor);
+    q->gate[2] = fixed3_border ? 0 : 3;
+  }
+  seg_end[2] = prednum;
+  /* segment 3: block-type / reference predictors (:211-214) */
+  if (currMB->mbAddrX != 0 && p_Inp->EPZSBlockType)
+  {
+    EPZSBlockTypePredictorsMB(currSlice, mv_block, point, &prednum);
+    q->gate[3] = (ref == 0) ? 0 : 2;
+  }
+  seg_end[3] = prednum;
+  if (prednum > EPZS_MAX_CANDS) unsupported("more than 512 EPZS predictors for one block");
+  for (s = 0, i = 0; s < 4; s++)
+  {
+    int cnt = seg_end[s] - i;
+    if (cnt > 255) unsupported("more than 255 EPZS predictors in one generator group");
+    q->n_cand[s] = (uint8_t)cnt;
+    for (; i < seg_end[s]; i++) { cands[2 * k] = point[i].motion.mv_x; cands[2 * k + 1] = point[i].motion.mv_y; k++; }
+  }
+  return k;
+}
+
+static int epzs_device_ok(Macroblock *currMB, MEBlock *mv_block)
+{
+  VideoParameters *p_Vid = currMB->p_Vid;
+  return !mv_block->apply_weights && !mv_block->ChromaMEEnable && p_Vid->structure == FRAME && !currMB->p_Slice->mb_aff_frame_flag &&
+         currMB->p_Inp->MEErrorMetric[F_PEL] == ERROR_SAD && p_Vid->start_me_refinement_qp == 1 && p_Vid->bitdepth_luma == 8;
+}
+
+/* stands behind EPZS_integer_motion_estimation (lencod/src/me_epzs_int.c:42) */
+distblk __wrap_EPZS_integer_motion_estimation(Macroblock *currMB, MotionVector *pred_mv, MEBlock *mv_block, distblk min_mcost, int lambda_factor)
+{
+  Slice *currSlice = currMB->p_Slice;
+  InputParameters *p_Inp = currMB->p_Inp;
+  EPZSParameters *p_EPZS = currSlice->p_EPZS;
+  int list = mv_block->list, cur_list = list + currMB->list_offset, ref = mv_block->ref_idx, blocktype = mv_block->blocktype, ncand, rc;
+  MotionVector *mv = &mv_block->mv[list];
+  distblk *prevSad = &p_EPZS->distortion[cur_list][blocktype - 1][mv_block->pos_x2];
+  jmb_epzs_req q;
+  jmb_epzs_res r;
+  int16_t cands[2 * EPZS_MAX_CANDS];
+
+  if (epzs_capture_on())
+  {
+    int32_t hdr[8];
+    distblk ret;
+    ncand = epzs_build_request(currMB, pred_mv, mv_block, lambda_factor, &q, cands);
+    epzs_cap_ids(currMB->p_Vid, currSlice->listX[cur_list][ref], &hdr[1], &hdr[2]);
+    ret = __real_EPZS_integer_motion_estimation(currMB, pred_mv, mv_block, min_mcost, lambda_factor);
+    hdr[0] = 2; hdr[3] = ncand; hdr[4] = mv->mv_x; hdr[5] = mv->mv_y; hdr[6] = 0; hdr[7] = 0;
+    fwrite(hdr, 4, 8, epzs_cap); fwrite(&q, sizeof(q), 1, epzs_cap); fwrite(cands, 4, (size_t)ncand, epzs_cap);
+    { int64_t o[2] = {(int64_t)ret, (int64_t)*prevSad}; fwrite(o, 8, 2, epzs_cap); }
+    epzs_cap_calls++;
+    return ret;
+  }
+  if (!shim_on(FAM_ME) || !epzs_device_ok(currMB, mv_block))      /* JM's own walk; its distortions still come from the device (computeSAD*) */
+    return __real_EPZS_integer_motion_estimation(currMB, pred_mv, mv_block, min_mcost, lambda_factor);
+  S.calls[1]++;
+  configure(currMB, mv_block, 0);
+  ncand = epzs_build_request(currMB, pred_mv, mv_block, lambda_factor, &q, cands);
+  q.ref = (uint8_t)ref_index(currMB, mv_block);
+  ++p_EPZS->BlkCount;      /* JM's visit stamp advances once per search (me_epzs_int.c:77-79); its map itself is not used */
+  if (p_EPZS->BlkCount == 0) ++p_EPZS->BlkCount;
+  rc = jmb_epzs_search(S.ctx, &q, 1, cands, ncand, &r, JMB_HOST);
+  if (rc) jmb_die("jmb_epzs_search", rc);
+  *prevSad = (distblk)r.prev_sad;
+#if EPZSREF
+  if (p_Inp->EPZSSpatialMem)
+    p_EPZS->p_motion[cur_list][ref][blocktype - 1][mv_block->block_y][mv_block->pos_x2].mv_x = r.imv_x,
+    p_EPZS->p_motion[cur_list][ref][blocktype - 1][mv_block->block_y][mv_block->pos_x2].mv_y = r.imv_y;
+#else
+  if (p_Inp->EPZSSpatialMem && ref == 0)
+    p_EPZS->p_motion[cur_list][blocktype - 1][mv_block->block_y][mv_block->pos_x2].mv_x = r.imv_x,
+    p_EPZS->p_motion[cur_list][blocktype - 1][mv_block->block_y][mv_block->pos_x2].mv_y = r.imv_y;
+#endif
+  mv->mv_x = r.imv_x;
+  mv->mv_y = r.imv_y;
+  return (distblk)r.icost;
+}
+
+/* stands behind EPZS_sub_pel_motion_estimation (lencod/src/me_epzs_sub.c:30) */
+distblk __wrap_EPZS_sub_pel_motion_estimation(Macroblock *currMB, MotionVector *pred, MEBlock *mv_block, distblk min_mcost, int *lambda)
+{
+  Slice *currSlice = currMB->p_Slice;
+  EPZSParameters *p_EPZS = currSlice->p_EPZS;
+  MotionVector *mv = &mv_block->mv[(int)mv_block->list];
+  jmb_epzs_req q;
+  jmb_epzs_res r;
+  int16_t none[2] = {0, 0};
+  int rc, capture = epzs_capture_on();
+
+  if (!capture && (!shim_on(FAM_SUBPEL) || !epzs_device_ok(currMB, mv_block)))
+    return __real_EPZS_sub_pel_motion_estimation(currMB, pred, mv_block, min_mcost, lambda);
+  memset(&q, 0, sizeof(q));
+  q.pos_x = mv_block->pos_x;  q.pos_y = mv_block->pos_y;
+  q.pred_x = pred->mv_x;      q.pred_y = pred->mv_y;
+  q.start_x = mv->mv_x;       q.start_y = mv->mv_y;
+  q.blocktype = (uint8_t)mv_block->blocktype;
+  q.flags = (uint8_t)(JMB_EPZS_SUBPEL | JMB_EPZS_SKIP_INT | (mv_block->test8x8 ? JMB_EPZS_TEST8X8 : 0));
+  q.lambda[0] = lambda[F_PEL]; q.lambda[1] = lambda[H_PEL]; q.lambda[2] = lambda[Q_PEL];
+  q.range_x = q.range_y = 1;
+  q.subthres = p_EPZS->subthres[mv_block->blocktype];
+  q.prev_sad = DISTBLK_MAX;
+  q.min_mcost = min_mcost;
+  if (capture)
+  {
+    int32_t hdr[8];
+    distblk ret;
+    epzs_cap_ids(currMB->p_Vid, currSlice->listX[mv_block->list + currMB->list_offset][(int)mv_block->ref_idx], &hdr[1], &hdr[2]);
+    ret = __real_EPZS_sub_pel_motion_estimation(currMB, pred, mv_block, min_mcost, lambda);
+    hdr[0] = 3; hdr[3] = 0; hdr[4] = mv->mv_x; hdr[5] = mv->mv_y;
+    hdr[6] = currMB->p_Vid->start_me_refinement_hp | (currMB->p_Vid->start_me_refinement_qp << 1) | (mv_block->search_pos2 << 2);
+    hdr[7] = currMB->p_Inp->MEErrorMetric[H_PEL] | (currMB->p_Inp->MEErrorMetric[Q_PEL] << 4);
+    fwrite(hdr, 4, 8, epzs_cap); fwrite(&q, sizeof(q), 1, epzs_cap);
+    { int64_t o[2] = {(int64_t)ret, 0}; fwrite(o, 8, 2, epzs_cap); }
+    return ret;
+  }
+  S.calls[3]++;
+  configure(currMB, mv_block, 0);
+  q.ref = (uint8_t)ref_index(currMB, mv_block);
+  rc = jmb_epzs_search(S.ctx, &q, 1, none, 0, &r, JMB_HOST);
+  if (rc) jmb_die("jmb_epzs_search(sub-pel)", rc);
   mv->mv_x = r.mv_x;
   mv->mv_y = r.mv_y;
   return (distblk)r.cost;

@@ -608,3 +608,210 @@ void jmo_hadamard(int kind, int *b)
     else { int t0 = a + c, t1 = a - c, t2 = d + e, t3 = d - e; b[0] = t0 + t2; b[1] = t1 + t3; b[2] = t0 - t2; b[3] = t1 - t3; }
   }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * EPZS.  EPZS_integer_motion_estimation (lencod/src/me_epzs_int.c:42-426) and
+ * EPZS_sub_pel_motion_estimation (lencod/src/me_epzs_sub.c:30-213), restated for a caller that
+ * supplies what JM's host state would: the ordered predictor list in up to four segments, each
+ * behind the cost gate its generator sits behind in JM (always / min_mcost > k * stopCriterion:
+ * me_epzs_common.c:1556 temporal neighbours k=1, me_epzs_int.c:193-198 window predictors k=3,
+ * :211 block-type predictors k=2), the stop criterion (EPZSDetermineStopCriterion,
+ * me_epzs_common.c:1874), medthres / subthres (:454-457) and *prevSad.  Refinement patterns:
+ * pattern_data, me_epzs_common.c:48-76 (offsets in quarter-pel, next start, next count) with the
+ * chaining of EPZSInit (:178-230): sbdiamond and pmvfast hand over to the small diamond.
+ * Distortions go through jmo_dist with JM's threshold form (d > thr>>5 ? thr : d<<5,
+ * mv_search.h:19-23, me_distortion.c:349-426).
+ * ---------------------------------------------------------------------------------------- */
+static const short epzs_pat[6][12][4] = {
+  {{0, 4, 3, 3}, {4, 0, 0, 3}, {0, -4, 1, 3}, {-4, 0, 2, 3}},
+  {{0, 4, 7, 3}, {4, 4, 7, 5}, {4, 0, 1, 3}, {4, -4, 1, 5}, {0, -4, 3, 3}, {-4, -4, 3, 5}, {-4, 0, 5, 3}, {-4, 4, 5, 5}},
+  {{-4, 4, 10, 5}, {0, 8, 10, 8}, {0, 4, 10, 7}, {4, 4, 1, 5}, {8, 0, 1, 8}, {4, 0, 1, 7}, {4, -4, 4, 5}, {0, -8, 4, 8},
+   {0, -4, 4, 7}, {-4, -4, 7, 5}, {-8, 0, 7, 8}, {-4, 0, 7, 7}},
+  {{0, 8, 6, 5}, {4, 4, 0, 3}, {8, 0, 0, 5}, {4, -4, 2, 3}, {0, -8, 2, 5}, {-4, -4, 4, 3}, {-8, 0, 4, 5}, {-4, 4, 6, 3}},
+  {{0, 8, 6, 12}, {4, 4, 0, 12}, {8, 0, 0, 12}, {4, -4, 2, 12}, {0, -8, 2, 12}, {-4, -4, 4, 12}, {-8, 0, 4, 12}, {-4, 4, 6, 12},
+   {0, 2, 6, 12}, {2, 0, 0, 12}, {0, -2, 2, 12}, {-2, 0, 4, 12}},
+  {{0, 8, 6, 5}, {4, 4, 0, 3}, {8, 0, 0, 5}, {4, -4, 2, 3}, {0, -8, 2, 5}, {-4, -4, 4, 3}, {-8, 0, 4, 5}, {-4, 4, 6, 3}}};
+static const int epzs_pat_n[6] = {4, 8, 12, 8, 12, 8}, epzs_pat_stop[6] = {1, 1, 1, 1, 0, 0}, epzs_pat_next[6] = {0, 1, 2, 3, 0, 0};
+/* nextLast is TRUE for every pattern EPZSInit builds */
+
+static const int bt_sx[8] = {16, 16, 16, 8, 8, 8, 4, 4}, bt_sy[8] = {16, 16, 8, 16, 8, 4, 8, 4};
+
+typedef struct { const jmo_ref *r; const uint16_t *src; int bsx, bsy, px, py; int evals; } epzs_blk;
+static int64_t epzs_dist(epzs_blk *b, int metric, int t8, int mvx, int mvy, int64_t thr)
+{
+  int d = jmo_dist(b->r, b->src, b->bsx, b->bsy, b->px * 4 + mvx, b->py * 4 + mvy, metric, t8);
+  b->evals++;
+  return (int64_t)d > (thr >> 5) ? thr : ((int64_t)d << 5);
+}
+
+void jmo_epzs(const jmo_ref *r, const uint16_t *cur, int cur_stride, const jmo_epzs_req *q, const int16_t *cands,
+              const int *me /* metric_h, metric_q, start_hp, start_qp, search_pos2 */, jmo_epzs_res *o)
+{
+  const int64_t BIG = (int64_t)0x7fffffff << 5;
+  uint16_t src[256];
+  epzs_blk B = {r, src, bt_sx[q->blocktype], bt_sy[q->blocktype], q->pos_x, q->pos_y, 0};
+  get_block(cur, cur_stride, q->pos_x, q->pos_y, B.bsx, B.bsy, src);
+  const int sx = q->start_x, sy = q->start_y, px = q->pred_x, py = q->pred_y, rx = q->range_x, ry = q->range_y;
+  int tx = sx, ty = sy;                       /* tmp */
+  int64_t min_mcost = q->min_mcost, prev = q->prev_sad;
+  int exit_code = 0;
+  const int gt0 = (q->flags & JMO_EPZS_REF_GT0_FRAME) != 0;
+
+  if (!(q->flags & JMO_EPZS_SKIP_INT)) {
+    const int lam = q->lambda[0];
+    const int64_t ld = 2 * (int64_t)lam, med = q->medthres, stop = q->stop;
+    const int mw = 2 * rx + 1;
+    uint8_t *map = (uint8_t *)calloc((size_t)mw * (2 * ry + 1), 1);
+#define VIS(x, y) map[((y) - sy + ry) * mw + ((x) - sx + rx)]
+#define INR(x, y) (iabs_((x) - sx) - rx <= 0 && iabs_((y) - sy) - ry <= 0)
+    VIS(sx, sy) = 1;
+    min_mcost = mvcost(lam, sx, sy, px, py);
+    min_mcost += epzs_dist(&B, JMO_SAD, 0, sx, sy, BIG - min_mcost);
+    if (gt0 && (prev < (med + ld < min_mcost ? med + ld : min_mcost) || prev * 8 < min_mcost)) exit_code = 1;   /* :103-117 */
+    else if (min_mcost > med + ld) {                                                                    /* :121 */
+      if (min_mcost < (stop >> 1)) {                                                                    /* :135-150 */
+        if (q->jm_ref == 0 || prev > min_mcost) prev = min_mcost;
+        exit_code = 2;
+      } else {
+        int64_t second = BIG, mcost;
+        const int64_t centre_cost = min_mcost;      /* JM runs the generators (and their gates) before it checks any predictor */
+        int check_median = 0, t2x = 0, t2y = 0;
+        const int16_t *c = cands + 2 * (size_t)q->cand_off;
+        for (int s = 0; s < 4; s++) {                                                                   /* predictor generators, :152-212 */
+          const int on = q->gate[s] == 0 || centre_cost > (int64_t)q->gate[s] * stop;
+          const int gen = s == 2 && (q->flags & JMO_EPZS_WINDOW_GEN);       /* EPZSWindowPredictorInit mode 0, me_epzs_common.c:352-371 */
+          static const signed char ring[8][2] = {{1, 0}, {1, 1}, {0, 1}, {-1, 1}, {-1, 0}, {-1, -1}, {0, -1}, {1, -1}};
+          for (int i = 0; i < q->n_cand[s]; i++) {
+            int vx, vy;
+            if (gen) { const int rings = (q->n_cand[s] + 8) >> 3, sp = rx >> (rings - 1 - (i >> 3)); vx = sx + ring[i & 7][0] * sp; vy = sy + ring[i & 7][1] * sp; }
+            else { vx = c[0]; vy = c[1]; c += 2; }                                                      /* :215-252 */
+            if (!on) continue;
+            if (!INR(vx, vy) || VIS(vx, vy)) continue;
+            VIS(vx, vy) = 1;
+            mcost = mvcost(lam, vx, vy, px, py);
+            if (mcost < second) {
+              mcost += epzs_dist(&B, JMO_SAD, 0, vx, vy, second - mcost);
+              if (mcost < min_mcost) { t2x = tx; t2y = ty; tx = vx; ty = vy; second = min_mcost; min_mcost = mcost; check_median = 1; }
+              else if (mcost < second) { t2x = vx; t2y = vy; second = mcost; check_median = 1; }
+            }
+          }
+        }
+        if (gt0 && prev * 3 < min_mcost) exit_code = 3;                                                 /* :254-273 */
+        else if (min_mcost > stop) {                                                                    /* :279 */
+          int pat = q->pattern, cx, cy;
+          if (q->flags & JMO_EPZS_ADAPT_PATTERN) {                                                      /* :286-300 */
+            if (min_mcost < stop + ((3 * med) >> 1))
+              pat = ((tx == 0 && ty == 0) || (iabs_(tx - sx) < 10 && iabs_(ty - sy) < 10)) ? 0 : 1;
+            else if (q->flags & JMO_EPZS_SQUARE_HINT) pat = 1;
+          }
+          cx = tx; cy = ty;
+          for (;;) {
+            int pattern_stop = 0, point = 0, next_last = 0, total = epzs_pat_n[pat], dir = 0;
+            do {                                                                                        /* :307-360 */
+              int check = total;
+              do {
+                const int vx = cx + epzs_pat[pat][point][0], vy = cy + epzs_pat[pat][point][1];
+                if (INR(vx, vy) && !VIS(vx, vy)) {
+                  VIS(vx, vy) = 1;
+                  mcost = mvcost(lam, vx, vy, px, py);
+                  if (mcost < min_mcost) {
+                    mcost += epzs_dist(&B, JMO_SAD, 0, vx, vy, min_mcost - mcost);
+                    if (mcost < min_mcost) { tx = vx; ty = vy; min_mcost = mcost; dir = point; }
+                  }
+                }
+                if (++point >= epzs_pat_n[pat]) point -= epzs_pat_n[pat];
+              } while (--check > 0);
+              if (next_last || (tx == cx && ty == cy)) {
+                pattern_stop = epzs_pat_stop[pat];
+                pat = epzs_pat_next[pat];
+                total = epzs_pat_n[pat];
+                next_last = 1;
+                dir = 0; point = 0;
+              } else {
+                total = epzs_pat[pat][dir][3];
+                point = epzs_pat[pat][dir][2];
+                cx = tx; cy = ty;
+              }
+            } while (pattern_stop != 1);
+            if (gt0 && (4 * prev < min_mcost || (3 * prev < min_mcost && prev <= stop))) { exit_code = 4; break; }   /* :362-376 */
+            if (!(check_median && (q->jm_ref == 0 || min_mcost < 2 * prev) && min_mcost > ((3 * stop) >> 1) && (q->flags & JMO_EPZS_DUAL))) break;   /* :379-384 */
+            if ((tx == 0 && ty == 0) || (tx == sx && ty == sy)) pat = (iabs_(tx - sx) < 10 && iabs_(ty - sy) < 10) ? 0 : 1;   /* :391-399 */
+            else pat = q->pattern_dual;
+            cx = t2x; cy = t2y;
+            check_median = 0;
+          }
+        }
+      }
+    }
+    if (!exit_code) { if (q->jm_ref == 0 || prev > min_mcost) prev = min_mcost; exit_code = 5; }           /* :409-410 */
+    free(map);
+#undef VIS
+#undef INR
+  }
+  o->imv_x = (int16_t)tx; o->imv_y = (int16_t)ty; o->icost = min_mcost; o->prev_sad = prev; o->exit_code = exit_code;
+  int mvx = tx, mvy = ty;
+
+  /* BlockMotionSearch between the two stages (mv_search.c:964-976): sub-pel only for ref 0, or when the integer cost is below
+   * 3.5 x the (updated) previous distortion; DISTBLK_MAX on entry unless start_me_refinement_hp */
+  if ((q->flags & JMO_EPZS_SUBPEL) && ((q->flags & JMO_EPZS_SKIP_INT) || !gt0 || 2 * min_mcost < 7 * prev)) {
+    static const signed char hp[10][2] = {{0, 0}, {-2, 0}, {0, 2}, {2, 0}, {0, -2}, {-2, 2}, {2, 2}, {2, -2}, {-2, -2}, {-2, 2}};
+    static const int ns[5][5] = {{0, 8, 5, 6, 7}, {8, 0, 5, 8, 8}, {5, 5, 0, 6, 5}, {6, 6, 6, 0, 7}, {7, 8, 7, 7, 0}};
+    static const int ne[5][5] = {{0, 10, 7, 8, 9}, {10, 0, 6, 10, 9}, {7, 6, 0, 7, 7}, {8, 8, 7, 0, 8}, {9, 9, 9, 8, 0}};
+    const int metric_h = me[0], metric_q = me[1], start_hp = me[2], start_qp = me[3], search_pos2 = me[4];
+    const int t8 = (q->flags & JMO_EPZS_TEST8X8) != 0;
+    const int max_pos2 = (!start_hp || !start_qp) ? (search_pos2 > 1 ? search_pos2 : 1) : search_pos2;
+    int lam = q->lambda[1], pos, best = 0, second_pos = 0, done = 0;
+    int64_t second = BIG, mcost, sub_thr = q->subthres + 2 * (int64_t)lam;
+    if (!(q->flags & JMO_EPZS_SKIP_INT) && !start_hp) min_mcost = BIG;
+    for (pos = start_hp; pos < (5 < max_pos2 ? 5 : max_pos2); pos++) {                                   /* me_epzs_sub.c:66-90 */
+      const int vx = mvx + hp[pos][0], vy = mvy + hp[pos][1];
+      mcost = mvcost(lam, vx, vy, px, py);
+      if (mcost < second) {
+        mcost += epzs_dist(&B, metric_h, t8, vx, vy, second - mcost);
+        if (mcost < min_mcost) { second = min_mcost; second_pos = best; min_mcost = mcost; best = pos; }
+        else if (mcost < second) { second = mcost; second_pos = pos; }
+      }
+    }
+    if (best == 0 && px == mvx && py == mvy && min_mcost < sub_thr) done = 1;                            /* :92-95 */
+    if (!done) {
+      if (search_pos2 >= 9 && (best != 0 || (iabs_(px - mvx) + iabs_(py - mvy)))) {                      /* :97-122 */
+        const int p0 = ns[best][second_pos], p1 = ne[best][second_pos];
+        for (pos = p0; pos < p1; pos++) {
+          const int vx = mvx + hp[pos][0], vy = mvy + hp[pos][1];
+          mcost = mvcost(lam, vx, vy, px, py);
+          if (mcost < min_mcost) {
+            mcost += epzs_dist(&B, metric_h, t8, vx, vy, min_mcost - mcost);
+            if (mcost < min_mcost) { min_mcost = mcost; best = pos; }
+          }
+        }
+      }
+      if (best) { mvx += hp[best][0]; mvy += hp[best][1]; }
+      const int end_pos = (min_mcost < sub_thr) ? 1 : 5;                                                 /* :135-170 */
+      second = BIG;
+      if (!start_qp) { best = -1; min_mcost = BIG; } else best = 0;
+      lam = q->lambda[2];
+      for (pos = start_qp; pos < end_pos; pos++) {
+        const int vx = mvx + hp[pos][0] / 2, vy = mvy + hp[pos][1] / 2;
+        mcost = mvcost(lam, vx, vy, px, py);
+        if (mcost < second) {
+          mcost += epzs_dist(&B, metric_q, t8, vx, vy, second - mcost);
+          if (mcost < min_mcost) { second = min_mcost; second_pos = best; min_mcost = mcost; best = pos; }
+          else if (mcost < second) { second = mcost; second_pos = pos; }
+        }
+      }
+      if (min_mcost > sub_thr && (best != 0 || (iabs_(px - mvx) + iabs_(py - mvy)))) {                   /* :173-200 */
+        const int p0 = ns[best][second_pos], p1 = ne[best][second_pos];
+        for (pos = p0; pos < p1; pos++) {
+          const int vx = mvx + hp[pos][0] / 2, vy = mvy + hp[pos][1] / 2;
+          mcost = mvcost(lam, vx, vy, px, py);
+          if (mcost < min_mcost) {
+            mcost += epzs_dist(&B, metric_q, t8, vx, vy, min_mcost - mcost);
+            if (mcost < min_mcost) { min_mcost = mcost; best = pos; }
+          }
+        }
+      }
+      if (best > 0) { mvx += hp[best][0] / 2; mvy += hp[best][1] / 2; }
+    }
+  }
+  o->mv_x = (int16_t)mvx; o->mv_y = (int16_t)mvy; o->cost = min_mcost; o->n_evals = B.evals;
+}

@@ -82,6 +82,34 @@ int jmo_quant(int variant, int *coef, int qp, const int *qparams, const uint8_t 
               const uint8_t *c_cost, int is_cavlc, int adapt_rnd_weight,
               int *levels, int *runs, int *fadjust, int *coeff_cost);
 
+/* EPZS (me_epzs_int.c:42-426, me_epzs_sub.c:30-213) for a caller-supplied predictor list; the structs have the layout of
+ * jmb_epzs_req / jmb_epzs_res of the product ABI so the tests feed both with the same bytes */
+#define JMO_EPZS_REF_GT0_FRAME 1
+#define JMO_EPZS_ADAPT_PATTERN 2
+#define JMO_EPZS_SQUARE_HINT   4
+#define JMO_EPZS_DUAL          8
+#define JMO_EPZS_SUBPEL       16
+#define JMO_EPZS_TEST8X8      32
+#define JMO_EPZS_SKIP_INT     64
+#define JMO_EPZS_WINDOW_GEN  128   /* segment 2 = JM's window_predictor set around the start mv (EPZSWindowPredictorInit mode 0) */
+typedef struct jmo_epzs_req {
+  int16_t pos_x, pos_y, pred_x, pred_y, start_x, start_y;
+  uint8_t blocktype, ref, flags, pattern;
+  uint8_t pattern_dual, jm_ref, reserved_[2];
+  uint8_t n_cand[4], gate[4];
+  int32_t cand_off;
+  int32_t lambda[3];
+  int16_t range_x, range_y;
+  int64_t stop, medthres, prev_sad, subthres, min_mcost;
+} jmo_epzs_req;
+typedef struct jmo_epzs_res {
+  int16_t mv_x, mv_y, imv_x, imv_y;
+  int64_t cost, icost, prev_sad;
+  int32_t exit_code, n_evals;
+} jmo_epzs_res;
+void jmo_epzs(const jmo_ref *r, const uint16_t *cur, int cur_stride, const jmo_epzs_req *q, const int16_t *cands,
+              const int *me /* metric_h, metric_q, start_hp, start_qp, search_pos2 */, jmo_epzs_res *o);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,9 @@ SAD, SSE, SATD = 0, 1, 2
 DISTBLK_MAX = 0x7FFFFFFF << 5   # lencod/inc/defines.h:136
 BLOCK_SIZE = [(16, 16), (16, 16), (16, 8), (8, 16), (8, 8), (8, 4), (4, 8), (4, 4)]
 
+EPZS_RES = np.dtype([("mv_x", "<i2"), ("mv_y", "<i2"), ("imv_x", "<i2"), ("imv_y", "<i2"), ("cost", "<i8"), ("icost", "<i8"),
+                     ("prev_sad", "<i8"), ("exit_code", "<i4"), ("n_evals", "<i4")])
+
 _u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
 _i16p = np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS")
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
@@ -70,6 +73,22 @@ class Oracle:
         L.jmo_hadamard_sad8x8.argtypes = [_i16p]
         L.jmo_quant.argtypes = [C.c_int, _i32p, C.c_int, _i32p, _u8p, _u8p, C.c_int, C.c_int,
                                 _i32p, _i32p, _i32p, _i32p]
+
+        L.jmo_epzs.argtypes = [C.c_void_p, _u16p, C.c_int, C.c_void_p, _i16p, _i32p, C.c_void_p]
+
+    def epzs(self, r, cur, reqs, cands, me):
+        """reqs: structured array with the layout of jmb_epzs_req; cands int16 [n][2]; me = (metric_h, metric_q, start_hp,
+        start_qp, search_pos2).  Returns a structured array with the layout of jmb_epzs_res."""
+        cur = np.ascontiguousarray(cur, np.uint16)
+        reqs = np.ascontiguousarray(reqs)
+        cands = np.ascontiguousarray(cands, np.int16).reshape(-1)
+        if len(cands) == 0:
+            cands = np.zeros(2, np.int16)
+        res = np.zeros(len(reqs), EPZS_RES)
+        me = np.asarray(me, np.int32)
+        for i in range(len(reqs)):
+            self.L.jmo_epzs(r[0], cur, cur.shape[1], reqs[i:i + 1].ctypes.data, cands, me, res[i:i + 1].ctypes.data)
+        return res
 
     # -- reference planes ---------------------------------------------------------------
     def ref_create(self, luma, max_value=255):

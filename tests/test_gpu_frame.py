@@ -31,14 +31,14 @@ def _pred_table(rng, n_mb, base=(0, 0), jitter=6):
 
 
 @pytest.mark.parametrize("mode", [api.SEARCH_FULL, api.SEARCH_FAST_FULL])
-@pytest.mark.parametrize("mv_range", [api.MV_RANGE_L51, (-24, 23, -16, 15)])
+@pytest.mark.parametrize("mv_range", [api.MV_RANGE_L51, (-24, 24, -16, 16)])
 def test_frame_pred_equals_explicit_requests_and_oracle(ctx, oracle, mode, mv_range):
     """The device builds the 41 requests of every macroblock from the predictor table by JM's rules (centre rounding
     mv_search.c:931, clip_mv_range :957/:981, me_fullfast.c:309-327); results must equal the explicit-request form and
     the oracle's search + refinement."""
     w, h, R = 80, 64, 4 if mv_range[1] < 100 else 8
     if mode == api.SEARCH_FAST_FULL and mv_range[1] < 100:
-        mv_range = (-64, 63, -48, 47)           # the fast-full centre clip needs min + 4R <= max - 4R
+        mv_range = (-64, 64, -48, 48)           # the fast-full centre clip needs min + 4R <= max - 4R
     f = synth.luma_frames(w, h, 2, seed=31, motion=(-2, 3))
     ctx.configure(search_range=R)
     ctx.ref_put(0, f[0]); ctx.pic_begin(f[1], [0])
