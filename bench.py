@@ -38,6 +38,9 @@ SEARCH_RANGE = 32
 QP = 28
 N_SETS = 4
 BYTES_PER_MB_REF = 13804           # 512 src + 12800 window + 492 results
+METRIC = {2: "macroblocks/sec 1080p full-search ME+DCT/quant", 3: "macroblocks/sec 4K EPZS ME + 8x8 DCT/quant",
+          4: "macroblocks/sec 1080p 4:2:2 fast-full-search ME + SATD sub-pel + DCT/quant incl. chroma",
+          5: "macroblocks/sec 4K full-search ME+DCT/quant, reconstructed anchor read over NVLink"}
 
 # BASELINE.json configs[1..4] (configs[0] is the reference's own CPU-only plumbing case, tests/test_jm_dropin.py)
 CONFIGS = {
@@ -63,6 +66,14 @@ def workload_config(cfg_id, n_gpus):
     return {"workload": c["name"], "baseline_config": cfg_id, "width": c["w"], "height": c["h"],
             "macroblocks_per_step": (c["w"] // 16) * (c["h"] // 16), "search_range": SEARCH_RANGE,
             "l2": f"rotating over {N_SETS} distinct input sets (> 126 MB in total)", "parallelism": par}
+
+
+def make_shared_candidates(seed, n_mb, n_shared, motion_q=(20, 12)):
+    """EPZS: candidate mvs every partition of a macroblock checks = zero mv + neighbour-like motion (true motion + jitter)."""
+    rng = np.random.default_rng(seed + 7)
+    c = (np.array(motion_q)[None, None, :] + rng.integers(-10, 11, size=(n_mb, n_shared, 2))).astype(np.int16)
+    c[:, 0] = 0
+    return c
 
 
 def make_pred_table(api, seed, n_mb, motion_q=(20, 12)):
@@ -124,6 +135,7 @@ class Workload:
 
     def __init__(self, args, api, synth, T, ctx, local, rank, world, torch):
         self.cfg = CONFIGS[args.config]
+        self.args = args
         self.api, self.ctx, self.torch, self.local = api, ctx, torch, local
         self.W, self.H = self.cfg["w"], self.cfg["h"]
         W, H = self.W, self.H
@@ -139,6 +151,12 @@ class Workload:
         mode = api.SEARCH_FAST_FULL if self.cfg["search"] == "fastfull" else api.SEARCH_FULL
         self.fp = api.frame_params([self.lam] * 3, mode=mode, flags=api.REQ_SUBPEL | (api.REQ_TEST8X8 if n == 8 else 0))
         self.token_cap = 7 * self.n_mb * (256 if args.scene_cut else 96)      # 256 per (mode, macroblock) is the hard maximum
+        self.epzs = self.cfg["search"] == "epzs"
+        self.n_shared = 8
+        if self.epzs:      # bin/encoder.cfg: EPZSPattern 2, EPZSDualRefinement 3, window predictors (EPZSFixedPredictors), thresholds 0/1/2/1
+            self.efp = api.epzs_frame_params([self.lam] * 3, flags=api.EPZS_ADAPT_PATTERN | api.EPZS_DUAL | api.EPZS_SUBPEL | (api.EPZS_TEST8X8 if n == 8 else 0),
+                                             pattern=api.EPZS_PAT_EDIAMOND, pattern_dual=api.EPZS_PAT_EDIAMOND, n_shared=self.n_shared, window=4,
+                                             search_range=SEARCH_RANGE)
         dev = f"cuda:{local}"
         anchor = bool(self.cfg.get("anchor"))
         self.sets = []
@@ -150,6 +168,9 @@ class Workload:
             pred = make_pred_table(api, 50 + 13 * rank + s, self.n_mb)
             hs = {"ref": ctx.pinned((H, W), np.uint8), "cur": ctx.pinned((H, W), np.uint8), "pred": ctx.pinned(self.n_mb, api.MB_MVPRED)}
             hs["ref"][:] = f[0]; hs["cur"][:] = f[1]; hs["pred"][:] = pred
+            if self.epzs:      # per macroblock: the zero mv + what the spatial / co-located generators would yield (neighbours' motion)
+                hs["shared"] = ctx.pinned((self.n_mb, self.n_shared, 2), np.int16)
+                hs["shared"][:] = make_shared_candidates(50 + 13 * rank + s, self.n_mb, self.n_shared)
             ds = {k: torch.from_numpy(v.view(np.uint8).reshape(-1).copy()).to(dev) for k, v in hs.items()}
             self.sets.append((hs, ds))
         self.d_res8 = torch.empty(self.n_mb * api.NPART * 8, dtype=torch.uint8, device=dev)
@@ -189,7 +210,10 @@ class Workload:
         ref_ptr = self.peer_refs[s % N_SETS] if self.peer_refs else ds["ref"].data_ptr()
         ctx.ref_put_u8(s % 2, ref_ptr, api.DEVICE, shape=shape)
         ctx.pic_begin_u8(ds["cur"].data_ptr(), [s % 2], api.DEVICE, shape=shape)
-        ctx.me_search_frame_pred(ds["pred"].data_ptr(), self.fp, self.d_res8.data_ptr(), api.DEVICE, n_mb=self.n_mb)
+        if self.epzs:
+            ctx.epzs_search_frame(ds["pred"].data_ptr(), ds["shared"].data_ptr(), self.efp, self.d_res8.data_ptr(), api.DEVICE, n_mb=self.n_mb)
+        else:
+            ctx.me_search_frame_pred(ds["pred"].data_ptr(), self.fp, self.d_res8.data_ptr(), api.DEVICE, n_mb=self.n_mb)
         ctx.mc_tq_modes_compact(None, self.qd, self.mode_mask, api.DEVICE, n_mb=self.n_mb,
                                 out=(self.d_heads.data_ptr(), self.d_tokens.data_ptr(), self.d_ntok.data_ptr()), token_cap=self.token_cap)
 
@@ -202,16 +226,32 @@ class Workload:
         t0 = time.perf_counter()
         c.ref_put_u8(s % 2, hs["ref"], api.HOST_ASYNC)
         c.pic_begin_u8(hs["cur"], [s % 2], api.HOST_ASYNC)
-        c.me_search_frame_pred(hs["pred"], self.fp, o_res, api.HOST_ASYNC)
+        if self.epzs:
+            c.epzs_search_frame(hs["pred"], hs["shared"], self.efp, o_res, api.HOST_ASYNC)
+        else:
+            c.me_search_frame_pred(hs["pred"], self.fp, o_res, api.HOST_ASYNC)
         t1 = time.perf_counter()
         c._ck(c.L.jmb_mc_tq_modes_compact(c.h, None, self.n_mb, self.mode_mask, self.qd.ctypes.data, o_heads.ctypes.data, o_tok.ctypes.data,
                                           self.token_cap, o_n.ctypes.data, api.HOST))
         tt["enqueue"] += t1 - t0; tt["residual_coding_and_wait"] += time.perf_counter() - t1
         self.tokens_seen = int(o_n[0])
 
+    def epzs_algorithmic_bytes(self):
+        api, ctx = self.api, self.ctx
+        hs = self.sets[0][0]
+        idx = np.linspace(0, self.n_mb - 1, 128).astype(int)
+        ctx.ref_put_u8(0, np.array(hs["ref"])); ctx.pic_begin_u8(np.array(hs["cur"]), [0])
+        reqs = api.epzs_requests_from_frame(np.array(hs["pred"])[idx], self.efp, self.W // 16, mb_index=idx)
+        res = ctx.epzs_search(reqs, np.array(hs["shared"])[idx].reshape(-1, 2))
+        bs = np.array([api.BLOCK_SIZE[t][0] * api.BLOCK_SIZE[t][1] for t in range(8)])[reqs["blocktype"]]
+        per_mb = float((bs * (1 + res["n_evals"])).sum()) / len(idx) + api.MB_MVPRED.itemsize + self.n_shared * 4 + 41 * 8
+        return per_mb * self.n_mb, float(res["n_evals"].mean())
+
     def bytes_per_step(self):
         api = self.api
         h2d = 2 * self.W * self.H + self.n_mb * api.MB_MVPRED.itemsize + api.FRAME_PARAMS.itemsize + api.QUANT_DESC.itemsize
+        if self.epzs:
+            h2d += self.n_mb * self.n_shared * 4 + api.EPZS_FRAME_PARAMS.itemsize - api.FRAME_PARAMS.itemsize
         d2h = self.n_mb * api.NPART * api.ME_RES8.itemsize + 7 * self.n_mb * api.TQ_HEAD.itemsize + 4 + 4 * self.tokens_seen
         return int(h2d), int(d2h)
 
@@ -221,10 +261,6 @@ def run_ours(args):
     import torch.distributed as dist
     from jm_b200 import api, synth
     from jm_b200 import h264_tables as T
-
-    if CONFIGS[args.config]["search"] == "epzs" or CONFIGS[args.config]["chroma"]:
-        import bench_more      # configs 3 and 4 carry extra stages (EPZS search, chroma path)
-        return bench_more.run(args, globals())
 
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -291,13 +327,14 @@ def run_ours(args):
     clocks = sampler.stop()
     gpu_launches = ctx.launches - launches0
     ms = e0.elapsed_time(e1)
-    k_ms, k_n = ctx.timing_get("int_search")
-    kernel_break = {k: ctx.timing_get(k)[0] / max(1, args.steps) for k in ("subpel_planes", "pack_cur", "gen_requests", "int_search", "subpel_refine", "mc_tq")}
+    top = "epzs" if wl.epzs else "int_search"
+    k_ms, k_n = ctx.timing_get(top)
+    kernel_break = {k: ctx.timing_get(k)[0] / max(1, args.steps) for k in ("subpel_planes", "pack_cur", "gen_requests", "int_search", "subpel_refine", "epzs", "mc_tq")}
     ctx.timing(False)
     ctx.sync()
     tokens_dev = int(wl.d_ntok.item())
     worst_ms = None
-    if not args.scene_cut and not args.no_worst:
+    if not args.scene_cut and not args.no_worst and not wl.epzs:
         # worst case of the search gate: the reference is an unrelated picture (nothing matches, every bound stays loose)
         f = synth.luma_frames(wl.W, wl.H, 1, seed=999)[0].astype(np.uint8)
         d_cut = torch.from_numpy(f.reshape(-1).copy()).to(f"cuda:{local}")
@@ -332,7 +369,7 @@ def run_ours(args):
     e2e_1 = timed_host(1, args.steps) if n_streams > 1 else e2e_s
     h2d, d2h = wl.bytes_per_step()
 
-    out = {"metric": "macroblocks/sec 1080p full-search ME+DCT/quant", "value": world * n_mb * args.steps / (ms / 1e3),
+    out = {"metric": METRIC[args.config], "value": world * n_mb * args.steps / (ms / 1e3),
            "unit": "macroblocks/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
            "config": workload_config(args.config, world), "clocks": clocks, "gpu_launches": int(gpu_launches),
@@ -349,19 +386,31 @@ def run_ours(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = BYTES_PER_MB_REF * n_mb / (k_ms / max(1, k_n) / 1e3) / 1e9
-    traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (tools/ncu_summary.py)
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "int_search_traffic.json")))[wl.cfg["size"].lower()]["dram_bytes_per_launch"]
-    except Exception:
-        pass
-    out["roofline"] = {"bound": "hbm", "kernel": "k_int_search", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                       "frac": achieved / peak, "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
-                       "algorithmic_bytes_per_launch": BYTES_PER_MB_REF * n_mb, "launch_ms": k_ms / max(1, k_n),
-                       "worst_case_launch_ms": worst_ms,
-                       "note": "search-window model of SURVEY 8(d): 13804 B per macroblock*reference; the kernel is ALU-pipe "
-                               "(VABSDIFF4/PRMT/ISETP) bound, not HBM bound -- DESIGN.md 3; traffic < algorithmic bytes because "
-                               "neighbouring windows hit L2"}
+    launch_ms = k_ms / max(1, k_n)
+    if wl.epzs:
+        # k_epzs: algorithmic bytes = per search the source block once + one reference block per distortion evaluated (u8 samples)
+        # + request tables in / results out; the evaluation counts come from the kernel's own n_evals on a sample of set 0
+        alg_bytes, evals_per_search = wl.epzs_algorithmic_bytes()
+        achieved = alg_bytes / (launch_ms / 1e3) / 1e9
+        out["roofline"] = {"bound": "hbm", "kernel": "k_epzs", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                           "traffic": None, "peak_source": "measured" if peaks else "fallback", "algorithmic_bytes_per_launch": alg_bytes,
+                           "launch_ms": launch_ms, "distortions_per_search": evals_per_search,
+                           "note": "EPZS evaluates ~10-60 scattered block distortions per search, each decided by the one before: the kernel is "
+                                   "bound by L2 latency and the serial walk, not by HBM bandwidth -- DESIGN.md 3"}
+    else:
+        achieved = BYTES_PER_MB_REF * n_mb / (launch_ms / 1e3) / 1e9
+        traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (tools/ncu_summary.py)
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "int_search_traffic.json")))[wl.cfg["size"].lower()]["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        out["roofline"] = {"bound": "hbm", "kernel": "k_int_search", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                           "frac": achieved / peak, "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
+                           "algorithmic_bytes_per_launch": BYTES_PER_MB_REF * n_mb, "launch_ms": launch_ms,
+                           "worst_case_launch_ms": worst_ms,
+                           "note": "search-window model of SURVEY 8(d): 13804 B per macroblock*reference; the kernel is ALU-pipe "
+                                   "(VABSDIFF4/PRMT/ISETP) bound, not HBM bound -- DESIGN.md 3; traffic < algorithmic bytes because "
+                                   "neighbouring windows hit L2"}
     # the streaming kernels against the same HBM peak (algorithmic bytes per launch stated in DESIGN.md 3)
     sp_ms = kernel_break["subpel_planes"]; tq_ms = kernel_break["mc_tq"]
     sp_bytes = wl.W * wl.H + 16 * ((wl.W + 64 + 127) // 128 * 128) * (wl.H + 40)
@@ -373,14 +422,15 @@ def run_ours(args):
         "k_mc_tq_modes_c": {"algorithmic_bytes_per_launch": tq_bytes, "launch_ms": tq_ms, "achieved": tq_bytes / (tq_ms / 1e3) / 1e9 if tq_ms else None,
                             "frac": tq_bytes / (tq_ms / 1e3) / 1e9 / peak if tq_ms else None}}
 
-    # The same kernel against the bound that actually limits it: the SM ALU pipe (VABSDIFF4 / PRMT / ISETP issue at
-    # 64 lanes/clk/SM on this part, tools/ubench.cu).  Floor per displacement = 64 VABSDIFF4 + 19 PRMT + 41 ISETP.
-    alu_ops = n_mb * (2 * SEARCH_RANGE + 1) ** 2 * (64 + 19 + 41)
-    sm_hz = 1e6 * float(clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
-    alu_peak = 64.0 * 148 * sm_hz
-    out["alu_roofline"] = {"bound": "alu-pipe", "achieved": alu_ops / (k_ms / max(1, k_n) / 1e3), "peak": alu_peak, "unit": "lane-ops/s",
-                           "frac": alu_ops / (k_ms / max(1, k_n) / 1e3) / alu_peak,
-                           "note": "minimum ALU-pipe instructions of the algorithm / launch time, vs 64 lanes/clk/SM x 148 SMs x SM clock"}
+    if not wl.epzs:
+        # The same kernel against the bound that actually limits it: the SM ALU pipe (VABSDIFF4 / PRMT / ISETP issue at
+        # 64 lanes/clk/SM on this part, tools/ubench.cu).  Floor per displacement = 64 VABSDIFF4 + 19 PRMT + 41 ISETP.
+        alu_ops = n_mb * (2 * SEARCH_RANGE + 1) ** 2 * (64 + 19 + 41)
+        sm_hz = 1e6 * float(clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
+        alu_peak = 64.0 * 148 * sm_hz
+        out["alu_roofline"] = {"bound": "alu-pipe", "achieved": alu_ops / (launch_ms / 1e3), "peak": alu_peak, "unit": "lane-ops/s",
+                               "frac": alu_ops / (launch_ms / 1e3) / alu_peak,
+                               "note": "minimum ALU-pipe instructions of the algorithm / launch time, vs 64 lanes/clk/SM x 148 SMs x SM clock"}
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(wl, ctx=ctx, api=api, budget_s=args.cpu_seconds)
     if rank == 0:
@@ -392,21 +442,54 @@ def run_ours(args):
 _JM = {}
 
 
-def _cpu_init(ref_luma, cur_luma, w, h):
-    """One process = one JM instance (JM is single-threaded); its quarter-pel planes are built once, untimed."""
+def _cpu_init(cfg_id, ref_luma, cur_luma, w, h):
+    """One process = one instance of the CPU implementation; its quarter-pel planes are built once, untimed.
+    Full search / fast full search: JM's own functions (oracle/_ref/libjmref.so, JM is single-threaded).  EPZS: the CPU
+    restatement pinned to JM's recorded calls (oracle/jm_oracle.c::jmo_epzs; the real function needs the whole encoder state)."""
     from oracle import pyoracle as po
-    ref = po.JMRef(w, h, SEARCH_RANGE)
-    ref.set_ref(ref_luma); ref.set_cur(cur_luma)
-    _JM["ref"] = ref
+    _JM["cfg"] = cfg_id
+    if CONFIGS[cfg_id]["search"] == "epzs":
+        o = po.Oracle()
+        _JM["oracle"] = o
+        _JM["ref"] = o.ref_create(ref_luma)
+        _JM["cur"] = np.ascontiguousarray(cur_luma, np.uint16)
+    else:
+        ref = po.JMRef(w, h, SEARCH_RANGE)
+        ref.set_ref(ref_luma); ref.set_cur(cur_luma)
+        _JM["ref"] = ref
+    _JM["w"] = w
 
 
 def _cpu_worker(a):
-    mb_xy, preds, lam = a
+    """(macroblock addresses, their predictor rows, their shared-candidate rows or None, lambda) -> mv, cost, levels, (ME s, TQ s)"""
+    idx, preds, shared, lam = a
+    from jm_b200 import api
     from jm_b200 import h264_tables as T
     from oracle import pyoracle as po
-    ref = _JM["ref"]
-    mv, cost, lev, secs = po.jmref_run_mbs(ref, mb_xy, preds, [lam] * 3, QP, T.q_params(QP, 0, 4), T.SNGL_SCAN, T.COEFF_COST4x4[0])
-    return mv, cost, lev, secs
+    cfg = CONFIGS[_JM["cfg"]]
+    mbw = _JM["w"] // 16
+    mb_xy = np.stack([(idx % mbw) * 16, (idx // mbw) * 16], 1)
+    if cfg["search"] != "epzs":
+        return po.jmref_run_mbs(_JM["ref"], mb_xy, preds, [lam] * 3, QP, T.q_params(QP, 0, 4), T.SNGL_SCAN, T.COEFF_COST4x4[0])
+    o, r, cur = _JM["oracle"], _JM["ref"], _JM["cur"]
+    n = cfg["n"]
+    efp = api.epzs_frame_params([lam] * 3, flags=api.EPZS_ADAPT_PATTERN | api.EPZS_DUAL | api.EPZS_SUBPEL | (api.EPZS_TEST8X8 if n == 8 else 0),
+                                pattern=api.EPZS_PAT_EDIAMOND, pattern_dual=api.EPZS_PAT_EDIAMOND, n_shared=shared.shape[1], window=4,
+                                search_range=SEARCH_RANGE)
+    pr = np.zeros(len(idx), api.MB_MVPRED); pr["pred"] = preds
+    reqs = api.epzs_requests_from_frame(pr, efp, mbw, mb_index=idx)
+    t0 = time.perf_counter()
+    res = o.epzs_batch(r, cur, reqs, shared.reshape(-1, 2), (po.SATD, po.SATD, 0, 1, 9))
+    t1 = time.perf_counter()
+    mv = np.stack([res["mv_x"], res["mv_y"]], 1).reshape(len(idx), 41, 2)
+    scan, cc = (T.SNGL_SCAN, T.COEFF_COST4x4[0]) if n == 4 else (T.SNGL_SCAN8x8, T.COEFF_COST8x8[0])
+    qp_ = T.q_params(QP, 0, n)
+    lev = np.zeros((len(idx), 7, 256), np.int16)
+    mask = 0x7F if n == 4 else 0x0F
+    for i in range(len(idx)):
+        lev[i] = o.mc_tq_modes_mb(r, cur, (int(mb_xy[i, 0]), int(mb_xy[i, 1])), mv[i], n, QP, qp_, scan, cc, n == 4, mask)
+    t2 = time.perf_counter()
+    return mv, res["cost"].reshape(len(idx), 41), lev, np.array([t1 - t0, t2 - t1])
 
 
 def expand_tokens(heads, tokens, mbs, per=16):
@@ -424,35 +507,41 @@ def expand_tokens(heads, tokens, mbs, per=16):
 
 
 def cpu_baseline(wl, ctx=None, api=None, budget_s=12.0):
-    """JM's own leaf functions (kind 'reference') on 1 host core over a bounded sample of set 0's macroblocks;
-    also re-checks the GPU results of that sample -- motion vectors, costs AND quantised levels -- bit-for-bit."""
+    """The CPU implementation of the step on 1 host core over a bounded sample of set 0's macroblocks (kind 'reference' = JM's
+    own functions; 'port' = the pinned restatement, EPZS only); also re-checks the GPU results of that sample -- motion
+    vectors, costs AND quantised levels -- bit-for-bit."""
     from oracle import pyoracle as po
-    if not po.ref_available():
+    if not wl.epzs and not po.ref_available():
         return {"value": None, "unit": "macroblocks/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref/libjmref.so missing"}
     hs = wl.sets[0][0]
     n_mb, W, H = wl.n_mb, wl.W, wl.H
-    mbw = W // 16
     pred = np.array(hs["pred"])["pred"]
+    shared = np.array(hs["shared"]) if wl.epzs else None
     # calibrate on 32 MBs, then size the sample for ~budget_s
     idx = np.linspace(0, n_mb - 1, 32).astype(int)
-    _cpu_init(np.array(hs["ref"]).astype(np.uint16), np.array(hs["cur"]).astype(np.uint16), W, H)
-    args = lambda ii: (np.stack([(ii % mbw) * 16, (ii // mbw) * 16], 1), pred[ii], wl.lam)
+    _cpu_init(wl.args.config, np.array(hs["ref"]).astype(np.uint16), np.array(hs["cur"]).astype(np.uint16), W, H)
+    args = lambda ii: (ii, pred[ii], shared[ii] if shared is not None else None, wl.lam)
     _, _, _, secs = _cpu_worker(args(idx))
     per_mb = max(1e-5, float(secs.sum()) / len(idx))
     n = int(min(n_mb, max(64, budget_s / per_mb)))
     idx = np.linspace(0, n_mb - 1, n).astype(int)
     mv, cost, lev, secs = _cpu_worker(args(idx))
-    res = {"value": n / float(secs.sum()), "unit": "macroblocks/s", "cores": 1, "kind": "reference",
-           "sample": f"{n} of {n_mb} macroblocks of input set 0 (evenly spaced), JM full_search_motion_estimation + "
-                     f"sub_pel_motion_estimation x41 + forward4x4/quant_4x4_normal x112 per MB",
+    what = ("the CPU restatement of EPZS_integer_motion_estimation + EPZS_sub_pel_motion_estimation x41 (pinned to recorded calls of the real "
+            "functions, tests/test_epzs_golden.py) + forward8x8/quant_8x8_normal x16 per MB" if wl.epzs else
+            "JM full_search_motion_estimation + sub_pel_motion_estimation x41 + forward4x4/quant_4x4_normal x112 per MB")
+    res = {"value": n / float(secs.sum()), "unit": "macroblocks/s", "cores": 1, "kind": "port" if wl.epzs else "reference",
+           "sample": f"{n} of {n_mb} macroblocks of input set 0 (evenly spaced), {what}",
            "me_seconds": float(secs[0]), "tq_seconds": float(secs[1])}
     if ctx is not None:
         ctx.ref_put_u8(0, np.array(hs["ref"])); ctx.pic_begin_u8(np.array(hs["cur"]), [0])
-        g = ctx.me_search_frame_pred(np.array(hs["pred"]), wl.fp).reshape(n_mb, 41)
+        if wl.epzs:
+            g = ctx.epzs_search_frame(np.array(hs["pred"]), np.array(hs["shared"]), wl.efp).reshape(n_mb, 41)
+        else:
+            g = ctx.me_search_frame_pred(np.array(hs["pred"]), wl.fp).reshape(n_mb, 41)
         heads, tokens = ctx.mc_tq_modes_compact(None, wl.qd, wl.mode_mask, n_mb=n_mb, token_cap=wl.token_cap)
         ok_mv = bool(np.array_equal(g["mv_x"][idx], mv[:, :, 0]) and np.array_equal(g["mv_y"][idx], mv[:, :, 1]) and
                      np.array_equal(g["cost"][idx], cost))
-        ok_lev = bool(np.array_equal(expand_tokens(heads, tokens, idx), lev))
+        ok_lev = bool(np.array_equal(expand_tokens(heads, tokens, idx, per=16 if wl.cfg["n"] == 4 else 64), lev))
         res["gpu_matches_reference_on_sample"] = ok_mv and ok_lev
         res["checked"] = {"mv_and_cost": ok_mv, "levels": ok_lev, "nonzero_levels_in_sample": int((lev != 0).sum())}
     return res
@@ -463,18 +552,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    if CONFIGS[args.config]["search"] == "epzs" or CONFIGS[args.config]["chroma"]:
-        import bench_more
-        return bench_more.run_reference(args, globals())
     import multiprocessing as mp
     from jm_b200 import api, synth
     from oracle import pyoracle as po
     from jm_b200 import h264_tables as T
     world = int(os.environ.get("WORLD_SIZE", 1))
-    if not po.ref_available():
+    c = CONFIGS[args.config]
+    epzs = c["search"] == "epzs"
+    if not epzs and not po.ref_available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libjmref.so not built"}))
         return
-    c = CONFIGS[args.config]
     W, H = c["w"], c["h"]
     cores = os.cpu_count() or 1
     lam = T.lambda_me(QP)
@@ -482,14 +569,15 @@ def run_reference(args):
     n_mb = (W // 16) * (H // 16)
     mbw = W // 16
     pred = make_pred_table(api, 50, n_mb)["pred"]
-    per_core = args.ref_mbs_per_core
+    shared = make_shared_candidates(50, n_mb, 8) if epzs else None
+    per_core = args.ref_mbs_per_core * (8 if epzs else 1)      # an EPZS macroblock is ~50x cheaper than a full-search one
     rng = np.random.default_rng(0)
 
     def job(step):
         idx = rng.permutation(n_mb)[: per_core * cores].reshape(cores, per_core)
-        return [(np.stack([(ii % mbw) * 16, (ii // mbw) * 16], 1), pred[ii], lam) for ii in idx]
+        return [(ii, pred[ii], shared[ii] if epzs else None, lam) for ii in idx]
 
-    with mp.get_context("fork").Pool(cores, initializer=_cpu_init, initargs=(f[0], f[1], W, H)) as pool:
+    with mp.get_context("fork").Pool(cores, initializer=_cpu_init, initargs=(args.config, f[0], f[1], W, H)) as pool:
         for s in range(args.warmup):
             pool.map(_cpu_worker, job(s))
         t0 = time.perf_counter()
@@ -497,14 +585,16 @@ def run_reference(args):
             pool.map(_cpu_worker, job(args.warmup + s))
         el = time.perf_counter() - t0
     v = per_core * cores * args.steps / el
-    out = {"impl": "reference", "metric": "macroblocks/sec 1080p full-search ME+DCT/quant", "value": v, "unit": "macroblocks/s",
+    out = {"impl": "reference", "metric": METRIC[args.config], "value": v, "unit": "macroblocks/s",
            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
            "config": workload_config(args.config, world), "sample_macroblocks_per_step": per_core * cores,
-           "cpu_baseline": {"value": v, "unit": "macroblocks/s", "cores": cores, "kind": "reference",
-                            "sample": f"each step = {per_core * cores} random macroblocks of the {c['size']} picture ({per_core} per core, one JM "
-                                      f"instance per core, quarter-pel planes built once before the timed region), "
-                                      f"JM's own full_search/sub_pel/forward4x4/quant_4x4_normal; value = sampled macroblocks / time"},
+           "cpu_baseline": {"value": v, "unit": "macroblocks/s", "cores": cores, "kind": "port" if epzs else "reference",
+                            "sample": f"each step = {per_core * cores} random macroblocks of the {c['size']} picture ({per_core} per core, one "
+                                      f"instance per core, quarter-pel planes built once before the timed region), " +
+                                      ("the pinned CPU restatement of JM's EPZS integer + sub-pel searches + forward8x8/quant_8x8_normal"
+                                       if epzs else "JM's own full_search/sub_pel/forward4x4/quant_4x4_normal") +
+                                      "; value = sampled macroblocks / time"},
            "e2e": {"value": v, "unit": "macroblocks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 

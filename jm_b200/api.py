@@ -51,6 +51,7 @@ EPZS_FRAME_PARAMS = np.dtype([("lambda", "<i4", (3,)), ("flags", "<i4"), ("ref",
                               ("maxthres", "<i4", (8,)), ("subthres", "<i4", (8,)), ("mv_min_x", "<i4"), ("mv_max_x", "<i4"),
                               ("mv_min_y", "<i4"), ("mv_max_y", "<i4")])
 assert EPZS_REQ.itemsize == 88 and EPZS_RES.itemsize == 40 and EPZS_FRAME_PARAMS.itemsize == 184
+EPZS_PAT_SDIAMOND, EPZS_PAT_SQUARE, EPZS_PAT_EDIAMOND, EPZS_PAT_LDIAMOND, EPZS_PAT_SBDIAMOND, EPZS_PAT_PMVFAST = range(6)
 EPZS_REF_GT0_FRAME, EPZS_ADAPT_PATTERN, EPZS_SQUARE_HINT, EPZS_DUAL, EPZS_SUBPEL, EPZS_TEST8X8, EPZS_SKIP_INT, EPZS_WINDOW_GEN = 1, 2, 4, 8, 16, 32, 64, 128
 # MED / MIN / MAX_THRES_BASE of lencod/src/me_epzs_common.c:34-37 scaled as EPZSStructInit does (:454-457): costs carry 5 fractional bits
 EPZS_MIN_BASE = [0, 64, 32, 32, 16, 8, 8, 4]
@@ -222,12 +223,14 @@ def epzs_frame_params(lam, flags=EPZS_ADAPT_PATTERN | EPZS_DUAL | EPZS_SUBPEL, r
     return fp
 
 
-def epzs_requests_from_frame(pred, fp, mb_w):
-    """The jmb_epzs_req list jmb_epzs_search_frame generates on the device (same rules; tests and the CPU legs)."""
+def epzs_requests_from_frame(pred, fp, mb_w, mb_index=None):
+    """The jmb_epzs_req list jmb_epzs_search_frame generates on the device (same rules; tests and the CPU legs).
+    mb_index: picture addresses of the macroblocks in `pred` (default 0..n-1); cand_off always counts from `pred`'s first row."""
     fp = fp[0]
     n_mb = len(pred)
     reqs = np.zeros((n_mb, NPART), EPZS_REQ)
-    mbx = (np.arange(n_mb) % mb_w) * 16; mby = (np.arange(n_mb) // mb_w) * 16
+    addr = np.arange(n_mb) if mb_index is None else np.asarray(mb_index)
+    mbx = (addr % mb_w) * 16; mby = (addr // mb_w) * 16
     big = DISTBLK_MAX
     ld = 2 * int(fp["lambda"][0])
     for k, (t, x, y) in enumerate(mb_partitions()):

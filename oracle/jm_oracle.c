@@ -815,3 +815,48 @@ void jmo_epzs(const jmo_ref *r, const uint16_t *cur, int cur_stride, const jmo_e
   }
   o->mv_x = (int16_t)mvx; o->mv_y = (int16_t)mvy; o->cost = min_mcost; o->n_evals = B.evals;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Batch forms used by bench.py's CPU legs (kind "port") and by the picture-sized parity checks.
+ * ---------------------------------------------------------------------------------------- */
+void jmo_epzs_batch(const jmo_ref *r, const uint16_t *cur, int cur_stride, const jmo_epzs_req *reqs, int n, const int16_t *cands,
+                    const int *me, jmo_epzs_res *res)
+{
+  for (int i = 0; i < n; i++) jmo_epzs(r, cur, cur_stride, &reqs[i], cands, me, &res[i]);
+}
+
+/* prediction -> residual -> forward transform -> quantisation of the partition modes in mode_mask for one macroblock, from the
+ * 41 motion vectors of its searches: luma_prediction (mc_prediction.c:117-236, one origin clamp per prediction unit:
+ * macroblock.c:946-971, :1225) -> forward4x4 / forward8x8 -> quant_4x4_normal / quant_8x8_normal / quant_8x8cavlc_normal
+ * (variants 0 / 2 / 4 of jmo_quant).  levels: [7][256] dense in scan order, layout of jmb_mc_tq_modes. */
+void jmo_mc_tq_modes_mb(const jmo_ref *r, const uint16_t *cur, int cur_stride, int mb_x, int mb_y, const int16_t *mv41, int n, int qp,
+                        const int *qparams, const uint8_t *scan, const uint8_t *c_cost, int is_cavlc, unsigned mode_mask, int16_t *levels)
+{
+  static const int base[8] = {0, 0, 1, 3, 5, 9, 17, 25}, w4[8] = {4, 4, 4, 2, 2, 2, 1, 1}, h4[8] = {4, 4, 2, 4, 2, 1, 2, 1};
+  const int per_mb = (n == 4) ? 16 : 4, nn = n * n, cavlc8 = (n == 8 && is_cavlc);
+  memset(levels, 0, 7 * 256 * sizeof(int16_t));
+  for (int mode = 1; mode <= 7; mode++) {
+    if (!((mode_mask >> (mode - 1)) & 1)) continue;
+    for (int b = 0; b < per_mb; b++) {
+      const int bx4 = (n == 4) ? (b & 3) : (b & 1) * 2, by4 = (n == 4) ? (b >> 2) : (b >> 1) * 2;
+      int ux4 = bx4, uy4 = by4;
+      if (mode < 5 || n == 8) { ux4 &= ~1; uy4 &= ~1; }
+      if (mode == 1) { ux4 = 0; uy4 = 0; }
+      const int slot = base[mode] + (uy4 / h4[mode]) * (4 / w4[mode]) + ux4 / w4[mode];
+      const int qx = ((mb_x + ux4 * 4) << 2) + mv41[2 * slot], qy = ((mb_y + uy4 * 4) << 2) + mv41[2 * slot + 1];
+      const uint16_t *rl = umv_line(r, qy, qx) + (by4 - uy4) * 4 * r->W + (bx4 - ux4) * 4;
+      int blk[64], lv[68], rn[68], fa[64], cost = 0;
+      for (int y = 0; y < n; y++)
+        for (int x = 0; x < n; x++)
+          blk[y * n + x] = (int)cur[(size_t)(mb_y + by4 * 4 + y) * cur_stride + mb_x + bx4 * 4 + x] - (int)rl[y * r->W + x];
+      if (n == 4) jmo_forward4x4(blk); else jmo_forward8x8(blk);
+      jmo_quant(n == 4 ? 0 : (cavlc8 ? 4 : 2), blk, qp, qparams, scan, c_cost, is_cavlc, 0, lv, rn, fa, &cost);
+      int16_t *o = levels + (mode - 1) * 256 + b * nn;
+      if (cavlc8) {
+        for (int s = 0; s < 4; s++)
+          for (int i = 0, k = 0; lv[17 * s + i]; i++) { k += rn[17 * s + i]; o[16 * s + k++] = (int16_t)lv[17 * s + i]; }
+      } else
+        for (int i = 0, k = 0; lv[i]; i++) { k += rn[i]; o[k++] = (int16_t)lv[i]; }
+    }
+  }
+}

@@ -110,6 +110,11 @@ typedef struct jmo_epzs_res {
 void jmo_epzs(const jmo_ref *r, const uint16_t *cur, int cur_stride, const jmo_epzs_req *q, const int16_t *cands,
               const int *me /* metric_h, metric_q, start_hp, start_qp, search_pos2 */, jmo_epzs_res *o);
 
+void jmo_epzs_batch(const jmo_ref *r, const uint16_t *cur, int cur_stride, const jmo_epzs_req *reqs, int n, const int16_t *cands,
+                    const int *me, jmo_epzs_res *res);
+void jmo_mc_tq_modes_mb(const jmo_ref *r, const uint16_t *cur, int cur_stride, int mb_x, int mb_y, const int16_t *mv41, int n, int qp,
+                        const int *qparams, const uint8_t *scan, const uint8_t *c_cost, int is_cavlc, unsigned mode_mask, int16_t *levels);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,6 +75,28 @@ class Oracle:
                                 _i32p, _i32p, _i32p, _i32p]
 
         L.jmo_epzs.argtypes = [C.c_void_p, _u16p, C.c_int, C.c_void_p, _i16p, _i32p, C.c_void_p]
+        L.jmo_epzs_batch.argtypes = [C.c_void_p, _u16p, C.c_int, C.c_void_p, C.c_int, _i16p, _i32p, C.c_void_p]
+        L.jmo_mc_tq_modes_mb.argtypes = [C.c_void_p, _u16p, C.c_int, C.c_int, C.c_int, _i16p, C.c_int, C.c_int, _i32p, _u8p, _u8p, C.c_int,
+                                         C.c_uint, _i16p]
+
+    def epzs_batch(self, r, cur, reqs, cands, me):
+        """jmo_epzs over a whole request array in one C call (timed by bench.py's CPU legs)."""
+        cur = np.ascontiguousarray(cur, np.uint16)
+        reqs = np.ascontiguousarray(reqs)
+        cands = np.ascontiguousarray(cands, np.int16).reshape(-1)
+        if len(cands) == 0:
+            cands = np.zeros(2, np.int16)
+        res = np.zeros(len(reqs), EPZS_RES)
+        self.L.jmo_epzs_batch(r[0], cur, cur.shape[1], reqs.ctypes.data, len(reqs), cands, np.asarray(me, np.int32), res.ctypes.data)
+        return res
+
+    def mc_tq_modes_mb(self, r, cur, mb, mv41, n, qp, qparams, scan, c_cost, is_cavlc, mode_mask):
+        cur = np.ascontiguousarray(cur, np.uint16)
+        lev = np.zeros((7, 256), np.int16)
+        self.L.jmo_mc_tq_modes_mb(r[0], cur, cur.shape[1], mb[0], mb[1], np.ascontiguousarray(mv41, np.int16).reshape(-1), n, qp,
+                                  np.ascontiguousarray(qparams, np.int32).reshape(-1), np.ascontiguousarray(scan, np.uint8).reshape(-1),
+                                  np.ascontiguousarray(c_cost, np.uint8), int(is_cavlc), mode_mask, lev)
+        return lev
 
     def epzs(self, r, cur, reqs, cands, me):
         """reqs: structured array with the layout of jmb_epzs_req; cands int16 [n][2]; me = (metric_h, metric_q, start_hp,
