@@ -291,6 +291,18 @@ typedef struct jmb_epzs_frame_params {
 int jmb_epzs_search_frame(jmb_ctx *ctx, const jmb_mb_mvpred *pred, const int16_t *shared, int n_mb, const jmb_epzs_frame_params *fp,
                           jmb_me_res8 *res, int loc);
 
+/* ---- macroblock-resident surfaces + per-partition arg-min: the form JM's sequential call sites can use -----------------------
+ * jmb_mb_surfaces: the sixteen 4x4 SAD surfaces of macroblock (mb_x, mb_y) against reference `ref` for every displacement within
+ * `radius` integer pels of the centre (quarter-pel, multiple of 4) -- setup_fast_full_search's BlockSAD (me_fullfast.c:492-556),
+ * kept as uint16 in HBM, one set per reference, valid until the next jmb_pic_begin / jmb_ref_put.  Only enqueues work.
+ * jmb_mb_search: one partition's search over the resident surfaces -- fast_full_search_motion_estimation (me_fullfast.c:618-689,
+ * JMB_SEARCH_FAST_FULL: macroblock-origin clamp, max_mvd guard) or full_search_motion_estimation (me_fullsearch.c:39-103,
+ * JMB_SEARCH_FULL: the request's own centre, partition-origin clamp) -- followed by the sub-pel refinement with JMB_REQ_SUBPEL
+ * (or that alone with JMB_REQ_SKIP_INT).  Synchronous; the answer comes back through a host-mapped mailbox (no copy calls).
+ * JMB_ERR_STATE when the request's window is not covered by the resident surfaces (the caller then uses jmb_me_search). */
+int jmb_mb_surfaces(jmb_ctx *ctx, int ref, int mb_x, int mb_y, int center_x, int center_y, int radius);
+int jmb_mb_search(jmb_ctx *ctx, const jmb_me_req *req, jmb_me_res *res);
+
 /* BlockSAD surfaces of one macroblock exactly as setup_fast_full_search leaves them:
  * out[(blocktype*16 + slot) * max_pos + pos], blocktype 1..7, uint32 (distpel), spiral order.
  * (lencod/src/me_fullfast.c:59-81 allocation, :492-556, :196-260) */
@@ -324,6 +336,14 @@ typedef struct jmb_dist_pred {
 } jmb_dist_pred;
 int jmb_dist_ex(jmb_ctx *ctx, int ref, const jmb_dist_pred *pred, int metric, int blocktype, int pos_x, int pos_y,
                 const int16_t *cand_xy, int n, int test8x8, int32_t *out, int loc);
+
+/* The mode-decision distortion back-ends p_Vid->distortion4x4 / distortion8x8 (select_distortion, lencod/src/me_distortion.c:
+ * 38-170): SAD / SSE / Hadamard SAD of nblk difference blocks of n x n int16 (n = 4 or 8) the caller formed -- the skip, direct
+ * and bi-predictive candidates of GetSkipCostMB / BPredPartitionCost / BIDPartitionCost (mv_search.c:589-675, :1159-1325), the
+ * 8x8 transform-size decision (macroblock.c:1413) and the intra chroma mode cost (intra_chroma.c:443).  out[i] is NOT scaled by
+ * 32.  thres (may be NULL; 8x8 SAD only) = dist_down(min_cost) per block: distortion8x8SADthres stops summing rows once the
+ * running sum exceeds it and returns that partial sum. */
+int jmb_block_distortion(jmb_ctx *ctx, int metric, int n, const int16_t *diff, int nblk, const int32_t *thres, int32_t *out, int loc);
 
 /* ---- transform + quantisation ---------------------------------------------------------------- */
 /* forward4x4 / forward8x8 (lcommon/src/transform.c:20,353) on nblk blocks of n*n int32, in place */
@@ -414,7 +434,7 @@ int jmb_pred_from_results(jmb_ctx *ctx, const jmb_me_res *res, int n_mb, int mod
 
 /* ---- measurement: CUDA events recorded on the context's stream around every kernel launch ----- */
 /* kernel names: subpel_planes, pack_cur, int_search, subpel_refine, dist, ffs_surfaces, forward,
- * quant_blocks, mc_tq, pred_from_results */
+ * quant_blocks, mc_tq, pred_from_results, gen_requests, epzs, chroma, deblock, argmin */
 int jmb_timing_enable(jmb_ctx *ctx, int on);      /* also clears the accumulated samples */
 int jmb_timing_get(jmb_ctx *ctx, const char *kernel, double *total_ms, int *launches);
 

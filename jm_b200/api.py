@@ -112,6 +112,9 @@ def load_library():
     L.jmb_pic_begin_u8.argtypes = [vp, vp, i, i, i, i, C.POINTER(i), i]
     L.jmb_me_search_frame_pred.argtypes = [vp, vp, i, vp, vp, i]
     L.jmb_mc_tq_modes_compact.argtypes = [vp, vp, i, C.c_uint, vp, vp, vp, C.c_uint32, vp, i]
+    L.jmb_block_distortion.argtypes = [vp, i, i, vp, i, vp, vp, i]
+    L.jmb_mb_surfaces.argtypes = [vp, i, i, i, i, i, i]
+    L.jmb_mb_search.argtypes = [vp, vp, vp]
     L.jmb_epzs_search.argtypes = [vp, vp, i, vp, i, vp, i]
     L.jmb_epzs_search_frame.argtypes = [vp, vp, vp, i, vp, vp, i]
     L.jmb_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
@@ -374,6 +377,23 @@ class Context:
         if loc == HOST:
             return heads, tokens[:int(n_tok[0])]
         return heads, tokens, n_tok
+
+    def mb_surfaces(self, ref, mb, center, radius):
+        self._ck(self.L.jmb_mb_surfaces(self.h, ref, mb[0], mb[1], center[0], center[1], radius))
+
+    def mb_search(self, req):
+        req = np.ascontiguousarray(req, ME_REQ).reshape(1)
+        res = np.zeros(1, ME_RES)
+        self._ck(self.L.jmb_mb_search(self.h, _ptr(req), _ptr(res)))
+        return res[0]
+
+    def block_distortion(self, metric, n, diff, thres=None):
+        diff = np.ascontiguousarray(diff, np.int16).reshape(-1, n * n)
+        out = np.zeros(len(diff), np.int32)
+        if thres is not None:
+            thres = np.ascontiguousarray(thres, np.int32)
+        self._ck(self.L.jmb_block_distortion(self.h, metric, n, _ptr(diff), len(diff), None if thres is None else _ptr(thres), _ptr(out), HOST))
+        return out
 
     def epzs_search(self, reqs, cands, loc=HOST, res=None, n=None, n_cands=None):
         if loc != DEVICE:

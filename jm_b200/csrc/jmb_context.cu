@@ -172,6 +172,9 @@ void jmb_destroy(jmb_ctx *ctx) {
   if (ctx->d_res_keep) cudaFree(ctx->d_res_keep);
   if (ctx->d_pred_keep) cudaFree(ctx->d_pred_keep);
   for (int i = 0; i < ctx->n_peers; i++) cudaIpcCloseMemHandle(ctx->peers[i].mapped);
+  for (int i = 0; i < JMB_MAX_REFS; i++) if (ctx->surf[i].buf) cudaFree(ctx->surf[i].buf);
+  if (ctx->mbox) cudaFreeHost(ctx->mbox);
+  if (ctx->d_one) cudaFree(ctx->d_one);
   if (ctx->d_mvpred) cudaFree(ctx->d_mvpred);
   if (ctx->d_res8) cudaFree(ctx->d_res8);
   if (ctx->d_heads) cudaFree(ctx->d_heads);
@@ -258,6 +261,7 @@ static int ref_put_impl(jmb_ctx *ctx, int slot, const void *luma, int sample_byt
   rc = jmb_launch_subpel(ctx, d_src, sample_bytes, stride, r);
   if (rc) return rc;
   r->valid = true;
+  ctx->pic_serial++;
   if (loc == JMB_HOST) JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return JMB_OK;
 }
@@ -348,6 +352,7 @@ static int pic_begin_impl(jmb_ctx *ctx, const void *cur, int sample_bytes, int w
     if (rc) return rc;
   }
   ctx->cur_w = width; ctx->cur_h = height; ctx->cur_pitch = pitch;
+  ctx->pic_serial++;
   if (sample_bytes == 1) {      // bytes already: one strided copy straight into the search layout, no kernel
     JMB_CUDA(ctx, cudaMemcpy2DAsync(ctx->cur, pitch, cur, stride, width, height,
                                     loc == JMB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));

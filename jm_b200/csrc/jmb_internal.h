@@ -56,7 +56,13 @@ struct jmb_ctx {
   // index of one offending request into d_err[0..1], which every synchronising call reads back
   int *d_err = nullptr; int *h_err = nullptr;
   bool smem_opt_in = false;   // k_int_search's dynamic shared memory opt-in done on this context's device
-  size_t epzs_smem = 0;       // dynamic shared memory k_epzs has been opted in for
+  // macroblock-resident SAD surfaces (jmb_mb_surfaces) per reference of the picture's list, and the host-mapped mailbox the
+  // per-partition searches answer through (jmb_mb_search)
+  struct Surf { void *buf = nullptr; size_t cap = 0; bool valid = false; int mb_x = 0, mb_y = 0, x0 = 0, y0 = 0, n = 0; unsigned long pic_serial = 0; };
+  Surf surf[JMB_MAX_REFS];
+  unsigned long pic_serial = 0, reftab_serial = 0, mb_calls = 0;      // pic_serial: bumped by every jmb_pic_begin / jmb_ref_put
+  void *mbox = nullptr, *d_mbox = nullptr, *d_one = nullptr; int mbox_seq = 0;
+  int epzs_grid[2] = {0, 0};  // persistent grid sizes of k_epzs_int / k_epzs_sub on this context's device
   // picture form with device-generated requests / compact outputs
   void *d_mvpred = nullptr; size_t d_mvpred_cap = 0;
   void *d_res8 = nullptr; size_t d_res8_cap = 0;

@@ -8,8 +8,8 @@
 // rows are split over 32 / n lanes and reduced by shuffle), then lane 0 replays JM's sequential selection on the complete
 // distortions -- JM's early-terminated distortion returns the threshold it was given (mv_search.h:19-23), which can never win
 // a strict '<', so complete sums decide alike.  JM's visited map (EPZSMap, stamped with BlkCount) is a per-warp bitmap in
-// shared memory over the (2 range + 1)^2 quarter-pel positions around the start mv; only the words a search touched are
-// cleared before the next one.  Warps are persistent: each walks requests warp, warp + #warps, ...
+// shared memory (a small hash set of the positions around the start mv; only the slots a search filled are cleared before the
+// next one).  Warps are persistent: each walks requests warp, warp + #warps, ...  The sub-pel stage is a second launch.
 #include "jmb_dist_dev.cuh"
 
 namespace {
@@ -108,17 +108,47 @@ __device__ __forceinline__ int epzs_check(const jmb_epzs_req &q, int w, int h, i
   return e;
 }
 
-__global__ void __launch_bounds__(EW * 32)
-k_epzs(const jmb_epzs_req *__restrict__ reqs, int n, const short2 *__restrict__ cands, int n_cands, jmb_epzs_res *__restrict__ res,
-       const uint8_t *__restrict__ cur, int cur_pitch, const uint8_t *const *__restrict__ ref_planes, size_t plane_bytes, int ref_pitch,
-       int w, int h, jmb_me_config me, int nref, int map_words, int max_range, int *__restrict__ err) {
-  extern __shared__ unsigned dyn_map[];
+// JM's visited map (EPZSMap) as a small open-addressing hash set per warp: a search visits at most a few hundred of the
+// (2 range + 1)^2 positions, and a 4 KB table instead of a 8-33 KB bitmap lets four times as many searches be in flight.
+constexpr int HS = 1024;       // slots (power of two)
+struct Visited {
+  unsigned *tab;               // HS keys, 0 = empty
+  unsigned short *touched;     // slots filled by the current search (lane 0's bookkeeping)
+  int n;
+  __device__ __forceinline__ static unsigned key_of(int dx, int dy) { return (((unsigned)(dy + 2048) << 16) | (unsigned)(dx + 2048)) + 1u; }
+  __device__ __forceinline__ static unsigned slot_of(unsigned k) { return (k * 2654435761u) >> 22; }
+  __device__ __forceinline__ bool seen(int dx, int dy) const {
+    const unsigned k = key_of(dx, dy);
+    for (unsigned s = slot_of(k);; s = (s + 1) & (HS - 1)) { const unsigned v = tab[s]; if (v == k) return true; if (!v) return false; }
+  }
+  __device__ __forceinline__ int visit(int dx, int dy) {      // lane 0: 1 = visited before, 0 = new, -1 = table full
+    const unsigned k = key_of(dx, dy);
+    for (unsigned s = slot_of(k);; s = (s + 1) & (HS - 1)) {
+      const unsigned v = tab[s];
+      if (v == k) return 1;
+      if (!v) {
+        if (n >= HS - HS / 4) return -1;
+        tab[s] = k;
+        if (n < TCAP) touched[n] = (unsigned short)s;
+        n++;
+        return 0;
+      }
+    }
+  }
+};
+
+// ---- integer stage: EPZS_integer_motion_estimation (me_epzs_int.c:42-426) ---------------------------------------------
+__global__ void __launch_bounds__(EW * 32, 6)
+k_epzs_int(const jmb_epzs_req *__restrict__ reqs, int n, const short2 *__restrict__ cands, int n_cands, jmb_epzs_res *__restrict__ res,
+           const uint8_t *__restrict__ cur, int cur_pitch, const uint8_t *const *__restrict__ ref_planes, size_t plane_bytes, int ref_pitch,
+           int w, int h, int nref, int max_range, int *__restrict__ err) {
   __shared__ WarpS wss[EW];
+  __shared__ unsigned htab[EW][HS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned *const map = dyn_map + (size_t)warp * map_words;
   WarpS &ws = wss[warp];
+  Visited vis{htab[warp], ws.touched, 0};
   const long long BIG = (long long)0x7fffffff << 5;      // DISTBLK_MAX
-  for (int i = lane; i < map_words; i += 32) map[i] = 0;
+  for (int i = lane; i < HS; i += 32) vis.tab[i] = 0;
   __syncwarp();
 
   for (int ri = blockIdx.x * EW + warp; ri < n; ri += gridDim.x * EW) {
@@ -127,217 +157,230 @@ k_epzs(const jmb_epzs_req *__restrict__ reqs, int n, const short2 *__restrict__ 
       const int bad = epzs_check(q, w, h, nref, n_cands, max_range);
       if (bad) { if (lane == 0) jmb_req_report(err, bad, ri); continue; }
     }
+    if (q.flags & JMB_EPZS_SKIP_INT) {      // sub-pel only: the integer-stage fields of the result echo the request
+      if (lane == 0) {
+        jmb_epzs_res o;
+        o.mv_x = o.imv_x = q.start_x; o.mv_y = o.imv_y = q.start_y; o.cost = o.icost = q.min_mcost; o.prev_sad = q.prev_sad; o.exit_code = 0; o.n_evals = 0;
+        res[ri] = o;
+      }
+      continue;
+    }
     Blk b{RefView{ref_planes[q.ref], plane_bytes, ref_pitch, w, h}, cur, cur_pitch, q.pos_x, q.pos_y, c_bsx[q.blocktype], c_bsy[q.blocktype]};
-    const int sx = q.start_x, sy = q.start_y, px = q.pred_x, py = q.pred_y, rx = q.range_x, ry = q.range_y, mw = 2 * rx + 1;
+    const int sx = q.start_x, sy = q.start_y, px = q.pred_x, py = q.pred_y, rx = q.range_x, ry = q.range_y;
     const bool gt0 = (q.flags & JMB_EPZS_REF_GT0_FRAME) != 0;
-    int tx = sx, ty = sy, exit_code = 0, evals = 0, n_touched = 0;
-    long long minc = q.min_mcost, prev = q.prev_sad;
-
-    // visited map: test-and-set by lane 0 only
+    int tx = sx, ty = sy, exit_code = 0, evals = 0, full = 0;
+    long long minc, prev = q.prev_sad;
+    vis.n = 0;
     auto in_range = [&](int vx, int vy) { return abs(vx - sx) <= rx && abs(vy - sy) <= ry; };
-    auto bit_of = [&](int vx, int vy) { return (vy - sy + ry) * mw + (vx - sx + rx); };
-    auto seen = [&](int vx, int vy) { const int bi = bit_of(vx, vy); return (map[bi >> 5] >> (bi & 31)) & 1u; };
-    auto visit = [&](int vx, int vy) {      // lane 0: returns true when the position was visited before
-      const int bi = bit_of(vx, vy);
-      const unsigned m = 1u << (bi & 31), old = map[bi >> 5];
-      if (old & m) return true;
-      if (!old) { if (n_touched < TCAP) ws.touched[n_touched] = (unsigned short)(bi >> 5); n_touched++; }
-      map[bi >> 5] = old | m;
-      return false;
-    };
-
-    if (!(q.flags & JMB_EPZS_SKIP_INT)) {
-      const int lam = q.lambda[0];
-      const long long ld = 2ll * lam, med = q.medthres, stop = q.stop;
-      // ---- the start mv (me_epzs_int.c:93-100) ----
-      if (lane == 0) { ws.mv[0] = make_short2((short)sx, (short)sy); visit(sx, sy); }
-      __syncwarp();
-      eval_sad(b, ws, 1, 1u, lane);
-      evals++;
-      minc = mv_cost(lam, sx, sy, px, py) + ((long long)ws.dist[0] << 5);
-      if (gt0 && (prev < min(med + ld, minc) || prev * 8 < minc)) exit_code = 1;                        // :103-117
-      else if (minc > med + ld) {                                                                        // :121
-        if (minc < (stop >> 1)) {                                                                        // :135-150
-          if (q.jm_ref == 0 || prev > minc) prev = minc;
-          exit_code = 2;
-        } else {
-          long long second = BIG;
-          const long long centre_cost = minc;      // JM runs the predictor generators (and their gates) before it checks any predictor
-          int check_median = 0, t2x = 0, t2y = 0;
-          int off = q.cand_off;
-          // ---- predictor list (:215-252) ----
-          for (int s = 0; s < 4; s++) {
-            const int ns = q.n_cand[s];
-            const bool gen = s == 2 && (q.flags & JMB_EPZS_WINDOW_GEN);
-            const bool on = q.gate[s] == 0 || centre_cost > (long long)q.gate[s] * stop;
-            if (on)
-              for (int i0 = 0; i0 < ns; i0 += 32) {
-                const int nb = min(32, ns - i0);
-                bool ok = false;
-                if (lane < nb) {
-                  short2 v;
-                  if (gen) {      // window predictors around the start mv: rings of size range >> k, k descending (EPZSWindowPredictorInit)
-                    const int i = i0 + lane, rings = (ns + 8) >> 3, sp = rx >> (rings - 1 - (i >> 3));
-                    v = make_short2((short)(sx + c_ring[i & 7][0] * sp), (short)(sy + c_ring[i & 7][1] * sp));
-                  } else v = cands[off + i0 + lane];
-                  ws.mv[lane] = v;
-                  ok = in_range(v.x, v.y) && !seen(v.x, v.y);
-                }
-                const unsigned valid = __ballot_sync(0xffffffffu, ok);
-                __syncwarp();
-                if (valid) eval_sad(b, ws, nb, valid, lane);
-                evals += __popc(valid);
-                if (lane == 0) {
-                  for (int c = 0; c < nb; c++) {
-                    if (!((valid >> c) & 1)) continue;
-                    const int vx = ws.mv[c].x, vy = ws.mv[c].y;
-                    if (visit(vx, vy)) continue;
-                    long long mcost = mv_cost(lam, vx, vy, px, py);
-                    if (mcost < second) {
-                      mcost += (long long)ws.dist[c] << 5;
-                      if (mcost < minc) { t2x = tx; t2y = ty; tx = vx; ty = vy; second = minc; minc = mcost; check_median = 1; }
-                      else if (mcost < second) { t2x = vx; t2y = vy; second = mcost; check_median = 1; }
-                    }
-                  }
-                }
-                __syncwarp();
+    const int lam = q.lambda[0];
+    const long long ld = 2ll * lam, med = q.medthres, stop = q.stop;
+    // ---- the start mv (:93-100) ----
+    if (lane == 0) { ws.mv[0] = make_short2((short)sx, (short)sy); vis.visit(0, 0); }
+    __syncwarp();
+    eval_sad(b, ws, 1, 1u, lane);
+    evals++;
+    minc = mv_cost(lam, sx, sy, px, py) + ((long long)ws.dist[0] << 5);
+    if (gt0 && (prev < min(med + ld, minc) || prev * 8 < minc)) exit_code = 1;                        // :103-117
+    else if (minc > med + ld) {                                                                        // :121
+      if (minc < (stop >> 1)) {                                                                        // :135-150
+        if (q.jm_ref == 0 || prev > minc) prev = minc;
+        exit_code = 2;
+      } else {
+        long long second = BIG;
+        const long long centre_cost = minc;      // JM runs the predictor generators (and their gates) before it checks any predictor
+        int check_median = 0, t2x = 0, t2y = 0;
+        int off = q.cand_off;
+        // ---- predictor list (:215-252) ----
+        for (int s = 0; s < 4; s++) {
+          const int ns = q.n_cand[s];
+          const bool gen = s == 2 && (q.flags & JMB_EPZS_WINDOW_GEN);
+          const bool on = q.gate[s] == 0 || centre_cost > (long long)q.gate[s] * stop;
+          if (on)
+            for (int i0 = 0; i0 < ns; i0 += 32) {
+              const int nb = min(32, ns - i0);
+              bool ok = false;
+              if (lane < nb) {
+                short2 v;
+                if (gen) {      // window predictors around the start mv: rings of size range >> k, k descending (EPZSWindowPredictorInit)
+                  const int i = i0 + lane, rings = (ns + 8) >> 3, sp = rx >> (rings - 1 - (i >> 3));
+                  v = make_short2((short)(sx + c_ring[i & 7][0] * sp), (short)(sy + c_ring[i & 7][1] * sp));
+                } else v = cands[off + i0 + lane];
+                ws.mv[lane] = v;
+                ok = in_range(v.x, v.y) && !vis.seen(v.x - sx, v.y - sy);
               }
-            if (!gen) off += ns;
-          }
-          tx = __shfl_sync(0xffffffffu, tx, 0); ty = __shfl_sync(0xffffffffu, ty, 0);
-          t2x = __shfl_sync(0xffffffffu, t2x, 0); t2y = __shfl_sync(0xffffffffu, t2y, 0);
-          check_median = __shfl_sync(0xffffffffu, check_median, 0);
-          minc = shfl_ll(minc);
-          if (gt0 && prev * 3 < minc) exit_code = 3;                                                     // :254-273
-          else if (minc > stop) {                                                                        // :279
-            int pat = q.pattern, cx, cy;
-            if (q.flags & JMB_EPZS_ADAPT_PATTERN) {                                                      // :286-300
-              if (minc < stop + ((3 * med) >> 1))
-                pat = ((tx == 0 && ty == 0) || (abs(tx - sx) < 10 && abs(ty - sy) < 10)) ? JMB_EPZS_PAT_SDIAMOND : JMB_EPZS_PAT_SQUARE;
-              else if (q.flags & JMB_EPZS_SQUARE_HINT) pat = JMB_EPZS_PAT_SQUARE;
-            }
-            cx = tx; cy = ty;
-            for (;;) {
-              int pattern_stop = 0, point = 0, next_last = 0, total = c_pat_n[pat], dir = 0;
-              do {                                                                                       // :307-360
-                const int np = c_pat_n[pat];
-                bool ok = false;
-                int pi = 0;
-                if (lane < total) {
-                  pi = point + lane; if (pi >= np) pi -= np;
-                  const short2 v = make_short2((short)(cx + c_pat[pat][pi][0]), (short)(cy + c_pat[pat][pi][1]));
-                  ws.mv[lane] = v;
-                  ok = in_range(v.x, v.y) && !seen(v.x, v.y);
-                }
-                const unsigned valid = __ballot_sync(0xffffffffu, ok);
-                __syncwarp();
-                if (valid) eval_sad(b, ws, total, valid, lane);
-                evals += __popc(valid);
-                if (lane == 0) {
-                  for (int c = 0; c < total; c++) {
-                    if (!((valid >> c) & 1)) continue;
-                    const int vx = ws.mv[c].x, vy = ws.mv[c].y;
-                    if (visit(vx, vy)) continue;
-                    long long mcost = mv_cost(lam, vx, vy, px, py);
-                    if (mcost < minc) {
-                      mcost += (long long)ws.dist[c] << 5;
-                      if (mcost < minc) { tx = vx; ty = vy; minc = mcost; dir = point + c; if (dir >= np) dir -= np; }
-                    }
+              const unsigned valid = __ballot_sync(0xffffffffu, ok);
+              __syncwarp();
+              if (valid) eval_sad(b, ws, nb, valid, lane);
+              evals += __popc(valid);
+              if (lane == 0) {
+                for (int c = 0; c < nb; c++) {
+                  if (!((valid >> c) & 1)) continue;
+                  const int vx = ws.mv[c].x, vy = ws.mv[c].y;
+                  const int vs = vis.visit(vx - sx, vy - sy);
+                  if (vs) { full |= vs < 0; continue; }
+                  long long mcost = mv_cost(lam, vx, vy, px, py);
+                  if (mcost < second) {
+                    mcost += (long long)ws.dist[c] << 5;
+                    if (mcost < minc) { t2x = tx; t2y = ty; tx = vx; ty = vy; second = minc; minc = mcost; check_median = 1; }
+                    else if (mcost < second) { t2x = vx; t2y = vy; second = mcost; check_median = 1; }
                   }
                 }
-                __syncwarp();
-                tx = __shfl_sync(0xffffffffu, tx, 0); ty = __shfl_sync(0xffffffffu, ty, 0); dir = __shfl_sync(0xffffffffu, dir, 0);
-                minc = shfl_ll(minc);
-                if (next_last || (tx == cx && ty == cy)) {
-                  pattern_stop = c_pat_stop[pat];
-                  pat = c_pat_next[pat];
-                  total = c_pat_n[pat];
-                  next_last = 1; dir = 0; point = 0;
-                } else {
-                  total = c_pat[pat][dir][3];
-                  point = c_pat[pat][dir][2];
-                  cx = tx; cy = ty;
-                }
-              } while (pattern_stop != 1);
-              if (gt0 && (4 * prev < minc || (3 * prev < minc && prev <= stop))) { exit_code = 4; break; }      // :362-376
-              if (!(check_median && (q.jm_ref == 0 || minc < 2 * prev) && minc > ((3 * stop) >> 1) && (q.flags & JMB_EPZS_DUAL))) break;   // :379-384
-              if ((tx == 0 && ty == 0) || (tx == sx && ty == sy))                                         // :391-399
-                pat = (abs(tx - sx) < 10 && abs(ty - sy) < 10) ? JMB_EPZS_PAT_SDIAMOND : JMB_EPZS_PAT_SQUARE;
-              else pat = q.pattern_dual;
-              cx = t2x; cy = t2y;
-              check_median = 0;
+              }
+              __syncwarp();
             }
+          if (!gen) off += ns;
+        }
+        tx = __shfl_sync(0xffffffffu, tx, 0); ty = __shfl_sync(0xffffffffu, ty, 0);
+        t2x = __shfl_sync(0xffffffffu, t2x, 0); t2y = __shfl_sync(0xffffffffu, t2y, 0);
+        check_median = __shfl_sync(0xffffffffu, check_median, 0);
+        minc = shfl_ll(minc);
+        if (gt0 && prev * 3 < minc) exit_code = 3;                                                     // :254-273
+        else if (minc > stop) {                                                                        // :279
+          int pat = q.pattern, cx, cy;
+          if (q.flags & JMB_EPZS_ADAPT_PATTERN) {                                                      // :286-300
+            if (minc < stop + ((3 * med) >> 1))
+              pat = ((tx == 0 && ty == 0) || (abs(tx - sx) < 10 && abs(ty - sy) < 10)) ? JMB_EPZS_PAT_SDIAMOND : JMB_EPZS_PAT_SQUARE;
+            else if (q.flags & JMB_EPZS_SQUARE_HINT) pat = JMB_EPZS_PAT_SQUARE;
+          }
+          cx = tx; cy = ty;
+          for (;;) {
+            int pattern_stop = 0, point = 0, next_last = 0, total = c_pat_n[pat], dir = 0;
+            do {                                                                                       // :307-360
+              const int np = c_pat_n[pat];
+              bool ok = false;
+              if (lane < total) {
+                int pi = point + lane; if (pi >= np) pi -= np;
+                const short2 v = make_short2((short)(cx + c_pat[pat][pi][0]), (short)(cy + c_pat[pat][pi][1]));
+                ws.mv[lane] = v;
+                ok = in_range(v.x, v.y) && !vis.seen(v.x - sx, v.y - sy);
+              }
+              const unsigned valid = __ballot_sync(0xffffffffu, ok);
+              __syncwarp();
+              if (valid) eval_sad(b, ws, total, valid, lane);
+              evals += __popc(valid);
+              if (lane == 0) {
+                for (int c = 0; c < total; c++) {
+                  if (!((valid >> c) & 1)) continue;
+                  const int vx = ws.mv[c].x, vy = ws.mv[c].y;
+                  const int vs = vis.visit(vx - sx, vy - sy);
+                  if (vs) { full |= vs < 0; continue; }
+                  long long mcost = mv_cost(lam, vx, vy, px, py);
+                  if (mcost < minc) {
+                    mcost += (long long)ws.dist[c] << 5;
+                    if (mcost < minc) { tx = vx; ty = vy; minc = mcost; dir = point + c; if (dir >= np) dir -= np; }
+                  }
+                }
+              }
+              __syncwarp();
+              tx = __shfl_sync(0xffffffffu, tx, 0); ty = __shfl_sync(0xffffffffu, ty, 0); dir = __shfl_sync(0xffffffffu, dir, 0);
+              minc = shfl_ll(minc);
+              if (next_last || (tx == cx && ty == cy)) {
+                pattern_stop = c_pat_stop[pat];
+                pat = c_pat_next[pat];
+                total = c_pat_n[pat];
+                next_last = 1; dir = 0; point = 0;
+              } else {
+                total = c_pat[pat][dir][3];
+                point = c_pat[pat][dir][2];
+                cx = tx; cy = ty;
+              }
+            } while (pattern_stop != 1);
+            if (gt0 && (4 * prev < minc || (3 * prev < minc && prev <= stop))) { exit_code = 4; break; }      // :362-376
+            if (!(check_median && (q.jm_ref == 0 || minc < 2 * prev) && minc > ((3 * stop) >> 1) && (q.flags & JMB_EPZS_DUAL))) break;   // :379-384
+            if ((tx == 0 && ty == 0) || (tx == sx && ty == sy))                                         // :391-399
+              pat = (abs(tx - sx) < 10 && abs(ty - sy) < 10) ? JMB_EPZS_PAT_SDIAMOND : JMB_EPZS_PAT_SQUARE;
+            else pat = q.pattern_dual;
+            cx = t2x; cy = t2y;
+            check_median = 0;
           }
         }
       }
-      if (!exit_code) { if (q.jm_ref == 0 || prev > minc) prev = minc; exit_code = 5; }                    // :409-410
-      // clean the visited map for the next search of this warp
-      n_touched = __shfl_sync(0xffffffffu, n_touched, 0);
-      if (n_touched > TCAP) { for (int i = lane; i < map_words; i += 32) map[i] = 0; }
-      else for (int i = lane; i < n_touched; i += 32) map[ws.touched[i]] = 0;
-      __syncwarp();
     }
-    const int imx = tx, imy = ty;
-    const long long icost = minc;
-    int mvx = tx, mvy = ty;
-
-    // ---- sub-pel stage: BlockMotionSearch's gate (mv_search.c:964-976), then EPZS_sub_pel_motion_estimation ----
-    if ((q.flags & JMB_EPZS_SUBPEL) && ((q.flags & JMB_EPZS_SKIP_INT) || !gt0 || 2 * minc < 7 * prev)) {
-      const int t8 = (q.flags & JMB_EPZS_TEST8X8) != 0;
-      const int max_pos2 = (!me.start_hp || !me.start_qp) ? max(1, me.search_pos2) : me.search_pos2;
-      int lam = q.lambda[1], best = 0, second_pos = 0;
-      long long second = BIG;
-      const long long sub_thr = q.subthres + 2ll * lam;
-      bool done = false;
-      if (!(q.flags & JMB_EPZS_SKIP_INT) && !me.start_hp) minc = BIG;
-      // one batch + replay; `wide`: the first loop of a stage (second-best tracking), else the refinement loop
-      auto stage = [&](int p0, int p1, int div, int metric, bool wide) {
-        const int nb = p1 - p0;
-        if (nb <= 0) return;
-        if (lane < nb) ws.mv[lane] = make_short2((short)(mvx + c_hp[p0 + lane][0] / div), (short)(mvy + c_hp[p0 + lane][1] / div));
-        __syncwarp();
-        eval_sub(b, ws, nb, metric, t8, lane);
-        evals += nb;
-        if (lane == 0)
-          for (int c = 0; c < nb; c++) {
-            const int pos = p0 + c;
-            long long mcost = mv_cost(lam, ws.mv[c].x, ws.mv[c].y, px, py);
-            if (wide) {
-              if (mcost < second) {
-                mcost += (long long)ws.dist[c] << 5;
-                if (mcost < minc) { second = minc; second_pos = best; minc = mcost; best = pos; }
-                else if (mcost < second) { second = mcost; second_pos = pos; }
-              }
-            } else if (mcost < minc) {
-              mcost += (long long)ws.dist[c] << 5;
-              if (mcost < minc) { minc = mcost; best = pos; }
-            }
-          }
-        __syncwarp();
-        best = __shfl_sync(0xffffffffu, best, 0); second_pos = __shfl_sync(0xffffffffu, second_pos, 0);
-        minc = shfl_ll(minc); second = shfl_ll(second);
-      };
-      stage(me.start_hp, min(5, max_pos2), 1, me.metric[1], true);                                       // me_epzs_sub.c:66-90
-      if (best == 0 && px == mvx && py == mvy && minc < sub_thr) done = true;                           // :92-95
-      if (!done) {
-        if (me.search_pos2 >= 9 && (best != 0 || (abs(px - mvx) + abs(py - mvy))))                       // :97-122
-          stage(c_ns[best][second_pos], c_ne[best][second_pos], 1, me.metric[1], false);
-        if (best) { mvx += c_hp[best][0]; mvy += c_hp[best][1]; }
-        const int end_pos = (minc < sub_thr) ? 1 : 5;                                                    // :135-170
-        second = BIG; best = 0;      // start_me_refinement_qp == 1 (checked by the host side); second_pos carries over as in JM
-        lam = q.lambda[2];
-        stage(me.start_qp, end_pos, 2, me.metric[2], true);
-        if (minc > sub_thr && (best != 0 || (abs(px - mvx) + abs(py - mvy))))                            // :173-200
-          stage(c_ns[best][second_pos], c_ne[best][second_pos], 2, me.metric[2], false);
-        if (best > 0) { mvx += c_hp[best][0] / 2; mvy += c_hp[best][1] / 2; }
-      }
-    }
+    if (!exit_code) { if (q.jm_ref == 0 || prev > minc) prev = minc; exit_code = 5; }                    // :409-410
+    // empty the visited set for the next search of this warp
+    const int nt = __shfl_sync(0xffffffffu, vis.n, 0);
+    if (__shfl_sync(0xffffffffu, full, 0) && lane == 0) jmb_req_report(err, EPZS_ERR_FIELD, ri);      // (more positions than the set holds: never silently wrong)
+    if (nt > TCAP) { for (int i = lane; i < HS; i += 32) vis.tab[i] = 0; }
+    else for (int i = lane; i < nt; i += 32) vis.tab[ws.touched[i]] = 0;
+    __syncwarp();
     if (lane == 0) {
       jmb_epzs_res o;
-      o.mv_x = (int16_t)mvx; o.mv_y = (int16_t)mvy; o.imv_x = (int16_t)imx; o.imv_y = (int16_t)imy;
-      o.cost = minc; o.icost = icost; o.prev_sad = prev; o.exit_code = exit_code; o.n_evals = evals;
+      o.mv_x = o.imv_x = (int16_t)tx; o.mv_y = o.imv_y = (int16_t)ty;
+      o.cost = o.icost = minc; o.prev_sad = prev; o.exit_code = exit_code; o.n_evals = evals;
       res[ri] = o;
     }
+  }
+}
+
+// ---- sub-pel stage: BlockMotionSearch's gate (mv_search.c:964-976), then EPZS_sub_pel_motion_estimation (me_epzs_sub.c:30-213);
+// a second launch so that the Hadamard code's registers do not limit how many integer searches are in flight ----------------
+__global__ void __launch_bounds__(EW * 32, 3)
+k_epzs_sub(const jmb_epzs_req *__restrict__ reqs, int n, jmb_epzs_res *__restrict__ res, const uint8_t *__restrict__ cur, int cur_pitch,
+           const uint8_t *const *__restrict__ ref_planes, size_t plane_bytes, int ref_pitch, int w, int h, jmb_me_config me, int nref) {
+  __shared__ WarpS wss[EW];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpS &ws = wss[warp];
+  const long long BIG = (long long)0x7fffffff << 5;
+  for (int ri = blockIdx.x * EW + warp; ri < n; ri += gridDim.x * EW) {
+    const jmb_epzs_req q = reqs[ri];
+    if (!(q.flags & JMB_EPZS_SUBPEL) || q.blocktype < 1 || q.blocktype > 7 || q.ref >= nref) continue;      // (rejected requests were reported by the integer stage)
+    const jmb_epzs_res r0 = res[ri];
+    if (r0.exit_code == 0 && !(q.flags & JMB_EPZS_SKIP_INT)) continue;                                        // integer stage did not run: rejected
+    const bool gt0 = (q.flags & JMB_EPZS_REF_GT0_FRAME) != 0;
+    long long minc = r0.icost;
+    if (!((q.flags & JMB_EPZS_SKIP_INT) || !gt0 || 2 * minc < 7 * r0.prev_sad)) continue;
+    Blk b{RefView{ref_planes[q.ref], plane_bytes, ref_pitch, w, h}, cur, cur_pitch, q.pos_x, q.pos_y, c_bsx[q.blocktype], c_bsy[q.blocktype]};
+    const int px = q.pred_x, py = q.pred_y;
+    int mvx = r0.imv_x, mvy = r0.imv_y, evals = r0.n_evals;
+    const int t8 = (q.flags & JMB_EPZS_TEST8X8) != 0;
+    const int max_pos2 = (!me.start_hp || !me.start_qp) ? max(1, me.search_pos2) : me.search_pos2;
+    int lam = q.lambda[1], best = 0, second_pos = 0;
+    long long second = BIG;
+    const long long sub_thr = q.subthres + 2ll * lam;
+    bool done = false;
+    if (!(q.flags & JMB_EPZS_SKIP_INT) && !me.start_hp) minc = BIG;
+    // one batch + replay; `wide`: the first loop of a stage (second-best tracking), else the refinement loop
+    auto stage = [&](int p0, int p1, int div, int metric, bool wide) {
+      const int nb = p1 - p0;
+      if (nb <= 0) return;
+      if (lane < nb) ws.mv[lane] = make_short2((short)(mvx + c_hp[p0 + lane][0] / div), (short)(mvy + c_hp[p0 + lane][1] / div));
+      __syncwarp();
+      eval_sub(b, ws, nb, metric, t8, lane);
+      evals += nb;
+      if (lane == 0)
+        for (int c = 0; c < nb; c++) {
+          const int pos = p0 + c;
+          long long mcost = mv_cost(lam, ws.mv[c].x, ws.mv[c].y, px, py);
+          if (wide) {
+            if (mcost < second) {
+              mcost += (long long)ws.dist[c] << 5;
+              if (mcost < minc) { second = minc; second_pos = best; minc = mcost; best = pos; }
+              else if (mcost < second) { second = mcost; second_pos = pos; }
+            }
+          } else if (mcost < minc) {
+            mcost += (long long)ws.dist[c] << 5;
+            if (mcost < minc) { minc = mcost; best = pos; }
+          }
+        }
+      __syncwarp();
+      best = __shfl_sync(0xffffffffu, best, 0); second_pos = __shfl_sync(0xffffffffu, second_pos, 0);
+      minc = shfl_ll(minc); second = shfl_ll(second);
+    };
+    stage(me.start_hp, min(5, max_pos2), 1, me.metric[1], true);                                       // me_epzs_sub.c:66-90
+    if (best == 0 && px == mvx && py == mvy && minc < sub_thr) done = true;                           // :92-95
+    if (!done) {
+      if (me.search_pos2 >= 9 && (best != 0 || (abs(px - mvx) + abs(py - mvy))))                       // :97-122
+        stage(c_ns[best][second_pos], c_ne[best][second_pos], 1, me.metric[1], false);
+      if (best) { mvx += c_hp[best][0]; mvy += c_hp[best][1]; }
+      const int end_pos = (minc < sub_thr) ? 1 : 5;                                                    // :135-170
+      second = BIG; best = 0;      // start_me_refinement_qp == 1 (checked by the host side); second_pos carries over as in JM
+      lam = q.lambda[2];
+      stage(me.start_qp, end_pos, 2, me.metric[2], true);
+      if (minc > sub_thr && (best != 0 || (abs(px - mvx) + abs(py - mvy))))                            // :173-200
+        stage(c_ns[best][second_pos], c_ne[best][second_pos], 2, me.metric[2], false);
+      if (best > 0) { mvx += c_hp[best][0] / 2; mvy += c_hp[best][1] / 2; }
+    }
+    if (lane == 0) { res[ri].mv_x = (int16_t)mvx; res[ri].mv_y = (int16_t)mvy; res[ri].cost = minc; res[ri].n_evals = evals; }
   }
 }
 
@@ -395,30 +438,33 @@ __global__ void k_epzs_pack(const jmb_epzs_res *__restrict__ res, int n, jmb_epz
 
 }  // namespace
 
-static int epzs_launch(jmb_ctx *ctx, const jmb_epzs_req *d_reqs, int n, const int16_t *d_cands, int n_cands, jmb_epzs_res *d_res, int max_range) {
+static int epzs_launch(jmb_ctx *ctx, const jmb_epzs_req *d_reqs, int n, const int16_t *d_cands, int n_cands, jmb_epzs_res *d_res, int max_range,
+                       bool any_subpel) {
   const jmb_ref &r0 = ctx->refs[ctx->ref_list[0]];
   const uint8_t *tab[JMB_MAX_REFS];
   for (int i = 0; i < JMB_MAX_REFS; i++) tab[i] = i < ctx->nref ? ctx->refs[ctx->ref_list[i]].planes : nullptr;
   int rc = jmb_reserve_dev(ctx, &ctx->d_reftab, &ctx->d_reftab_cap, sizeof(tab)); if (rc) return rc;
   JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_reftab, tab, sizeof(tab), cudaMemcpyHostToDevice, ctx->stream));
-  const int map_words = ((2 * max_range + 1) * (2 * max_range + 1) + 31) / 32;
-  const size_t smem = (size_t)EW * map_words * sizeof(unsigned);
-  if (smem > 200 * 1024) return jmb_fail(ctx, JMB_ERR_UNSUPPORTED, "jmb_epzs_search: search range %d quarter-pel needs %zu bytes of visited map", max_range, smem);
-  if (smem > ctx->epzs_smem) {
-    JMB_CUDA(ctx, cudaFuncSetAttribute(k_epzs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ctx->epzs_smem = smem;
+  if (!ctx->epzs_grid[0]) {      // persistent warps: as many CTAs as fit the device at once
+    int sms = 148, per_sm = 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    JMB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_epzs_int, EW * 32, 0));
+    ctx->epzs_grid[0] = sms * max(1, per_sm);
+    JMB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_epzs_sub, EW * 32, 0));
+    ctx->epzs_grid[1] = sms * max(1, per_sm);
   }
-  int per_sm = 1;
-  JMB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_epzs, EW * 32, smem));
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-  const int grid = (int)min((long long)(n + EW - 1) / EW, (long long)sms * max(1, per_sm));
+  const int blocks = (n + EW - 1) / EW;
   jmb_time_begin(ctx, JMB_K_EPZS);
-  k_epzs<<<grid, EW * 32, smem, ctx->stream>>>(d_reqs, n, (const short2 *)d_cands, n_cands, d_res, ctx->cur, ctx->cur_pitch,
-                                                  (const uint8_t *const *)ctx->d_reftab, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h,
-                                                  ctx->me, ctx->nref, map_words, max_range, ctx->d_err);
-  jmb_time_end(ctx, JMB_K_EPZS);
+  k_epzs_int<<<min(blocks, ctx->epzs_grid[0]), EW * 32, 0, ctx->stream>>>(d_reqs, n, (const short2 *)d_cands, n_cands, d_res, ctx->cur, ctx->cur_pitch,
+                                                                           (const uint8_t *const *)ctx->d_reftab, r0.plane_bytes, r0.pitch, ctx->cur_w,
+                                                                           ctx->cur_h, ctx->nref, max_range, ctx->d_err);
   JMB_LAUNCH_CHECK(ctx);
+  if (any_subpel) {
+    k_epzs_sub<<<min(blocks, ctx->epzs_grid[1]), EW * 32, 0, ctx->stream>>>(d_reqs, n, d_res, ctx->cur, ctx->cur_pitch, (const uint8_t *const *)ctx->d_reftab,
+                                                                             r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, ctx->me, ctx->nref);
+    JMB_LAUNCH_CHECK(ctx);
+  }
+  jmb_time_end(ctx, JMB_K_EPZS);
   return JMB_OK;
 }
 
@@ -452,7 +498,7 @@ int jmb_epzs_search(jmb_ctx *ctx, const jmb_epzs_req *reqs, int n, const int16_t
     if (n_cands) JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage2, cands, (size_t)n_cands * 4, cudaMemcpyHostToDevice, ctx->stream));
     d_reqs = (const jmb_epzs_req *)ctx->d_stage; d_cands = (const int16_t *)ctx->d_stage2; d_res = (jmb_epzs_res *)ctx->d_stage5;
   } else max_range = 4 * ctx->me.search_range;      // device-resident requests: ranges are checked on the device against the configured one
-  rc = epzs_launch(ctx, d_reqs, n, d_cands, n_cands, d_res, max_range); if (rc) return rc;
+  rc = epzs_launch(ctx, d_reqs, n, d_cands, n_cands, d_res, max_range, true); if (rc) return rc;
   if (host) {
     JMB_CUDA(ctx, cudaMemcpyAsync(res, d_res, (size_t)n * sizeof(jmb_epzs_res), cudaMemcpyDeviceToHost, ctx->stream));
     if (loc == JMB_HOST) return jmb_check_device_errors(ctx);
@@ -502,7 +548,7 @@ int jmb_epzs_search_frame(jmb_ctx *ctx, const jmb_mb_mvpred *pred, const int16_t
   k_gen_epzs<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_pred, n_mb, mb_w, *fp, d_reqs);
   jmb_time_end(ctx, JMB_K_GEN);
   JMB_LAUNCH_CHECK(ctx);
-  rc = epzs_launch(ctx, d_reqs, n, d_shared, n_cands, d_eres, fp->range); if (rc) return rc;
+  rc = epzs_launch(ctx, d_reqs, n, d_shared, n_cands, d_eres, fp->range, (fp->flags & JMB_EPZS_SUBPEL) != 0); if (rc) return rc;
   jmb_me_res8 *d_out = res;
   if (host && res) {
     rc = jmb_reserve_dev(ctx, &ctx->d_res8, &ctx->d_res8_cap, (size_t)n * sizeof(jmb_me_res8)); if (rc) return rc;

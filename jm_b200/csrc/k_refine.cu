@@ -221,6 +221,30 @@ __global__ void k_dist(const uint8_t *__restrict__ cur, int cur_pitch, RefView r
   }
   atomicAdd(&out[c], d);
 }
+
+// Mode-decision distortion back-ends (lencod/src/me_distortion.c:38-146): distortion4x4SAD / SSE / SATD and distortion8x8SAD /
+// SADthres / SSE / SATD of DIFFERENCE blocks the caller formed (skip / direct / bi-predictive candidates: mv_search.c:589-675,
+// :1159-1325, macroblock.c:1413, intra_chroma.c:443).  One thread per block.  thres > 0 reproduces distortion8x8SADthres:
+// the row loop stops once the running sum exceeds thres and the partial sum is what JM returns.
+__global__ void k_block_dist(const int16_t *__restrict__ diff, int nblk, int n, int metric, const int *__restrict__ thres, int *__restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nblk) return;
+  const int16_t *d = diff + (size_t)t * n * n;
+  int s = 0;
+  if (metric == JMB_SATD) {
+    if (n == 4) { int v[16]; for (int k = 0; k < 16; k++) v[k] = d[k]; s = hadamard4(v); }
+    else { int v[64]; for (int k = 0; k < 64; k++) v[k] = d[k]; s = hadamard8(v); }
+  } else if (metric == JMB_SSE) {
+    for (int k = 0; k < n * n; k++) s += (int)d[k] * (int)d[k];
+  } else {
+    const int lim = thres ? thres[t] : 0x7fffffff;
+    for (int j = 0; j < n; j++) {
+      for (int i = 0; i < n; i++) s += abs((int)d[j * n + i]);
+      if (n == 8 && thres && s > lim) break;
+    }
+  }
+  out[t] = s;
+}
 }  // namespace
 
 int jmb_launch_refine(jmb_ctx *ctx, const jmb_me_req *d_reqs, jmb_me_res *d_res, int n, const uint8_t *const *d_ref_planes) {
@@ -285,4 +309,29 @@ extern "C" int jmb_dist_ex(jmb_ctx *ctx, int ref, const jmb_dist_pred *pred, int
 extern "C" int jmb_dist(jmb_ctx *ctx, int ref, int metric, int blocktype, int pos_x, int pos_y,
                         const int16_t *cand_xy, int n, int test8x8, int32_t *out, int loc) {
   return jmb_dist_ex(ctx, ref, nullptr, metric, blocktype, pos_x, pos_y, cand_xy, n, test8x8, out, loc);
+}
+
+extern "C" int jmb_block_distortion(jmb_ctx *ctx, int metric, int n, const int16_t *diff, int nblk, const int32_t *thres, int32_t *out, int loc) {
+  if (nblk <= 0) return JMB_OK;
+  if ((n != 4 && n != 8) || metric < JMB_SAD || metric > JMB_SATD || !diff || !out) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_block_distortion: n %d metric %d", n, metric);
+  if (thres && (n != 8 || metric != JMB_SAD)) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_block_distortion: thresholds belong to the 8x8 SAD (distortion8x8SADthres)");
+  JMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t db = (size_t)nblk * n * n * sizeof(int16_t), ob = (size_t)nblk * sizeof(int32_t);
+  const int16_t *d_d = diff; const int *d_t = thres; int *d_o = out;
+  if (jmb_is_host(loc)) {
+    int rc = jmb_reserve_dev(ctx, &ctx->d_stage, &ctx->d_stage_cap, db + 2 * ob + 16); if (rc) return rc;
+    char *a = (char *)ctx->d_stage;
+    JMB_CUDA(ctx, cudaMemcpyAsync(a, diff, db, cudaMemcpyHostToDevice, ctx->stream));
+    d_d = (const int16_t *)a; d_o = (int *)(a + ((db + 15) & ~(size_t)15));
+    if (thres) { d_t = d_o + nblk; JMB_CUDA(ctx, cudaMemcpyAsync((void *)d_t, thres, ob, cudaMemcpyHostToDevice, ctx->stream)); }
+  }
+  jmb_time_begin(ctx, JMB_K_DIST);
+  k_block_dist<<<(nblk + 127) / 128, 128, 0, ctx->stream>>>(d_d, nblk, n, metric, d_t, d_o);
+  jmb_time_end(ctx, JMB_K_DIST);
+  JMB_LAUNCH_CHECK(ctx);
+  if (jmb_is_host(loc)) {
+    JMB_CUDA(ctx, cudaMemcpyAsync(out, d_o, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    if (loc == JMB_HOST) JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return JMB_OK;
 }

@@ -593,6 +593,111 @@ __global__ void k_ffs_surfaces(const uint8_t *__restrict__ cur, int cur_pitch, c
 #undef O
 }
 
+
+// ---- macroblock-resident SAD surfaces + per-partition arg-min: the drop-in path of JM's strictly sequential call sites --------
+// JM decides one partition at a time (each search's predictor needs the previous decisions), but the expensive half
+// of a search -- the sixteen 4x4 SADs of every displacement -- does not depend on the predictor.  jmb_mb_surfaces computes them
+// ONCE per macroblock and reference over a window a little larger than the search window (setup_fast_full_search's BlockSAD,
+// me_fullfast.c:492-556, kept as u16 and never leaving HBM); jmb_mb_search then is what fast_full_search_motion_estimation
+// (:618-689) / full_search_motion_estimation (me_fullsearch.c:39-103) do per partition: partition sums
+// (update_full_search_large_blocks :196-260, here on the fly), mv cost with the call's own predictor, arg-min with JM's
+// tie-break -- one small launch, answer through a host-mapped mailbox.
+constexpr int SF_NT = 192, SF_BH = 8, SF_PITCH = 96;      // surface kernel: threads, displacement rows per CTA, u16 per surface row
+static_assert(SF_PITCH >= CW, "a surface row holds one staging chunk of displacements");
+
+__global__ void __launch_bounds__(SF_NT)
+k_mb_surfaces(const __grid_constant__ TMaps tm, int ref, int mbx, int mby, int x0, int y0, int ncol, int nrow, unsigned short *__restrict__ out) {
+  __shared__ __align__(128) uint8_t win[WIN_ROWS * WIN_PITCH];
+  __shared__ __align__(128) unsigned ssrc[16 * 4];
+  __shared__ __align__(8) unsigned long long mbar;
+  const int tid = threadIdx.x, band = blockIdx.x;
+  const int by0 = y0 + band * SF_BH, bh = min(SF_BH, nrow - band * SF_BH);      // displacement rows of this CTA
+  const int ax = mbx + x0 + JMB_PAD_X, xoff0 = ax & 15;
+  if (tid == 0) {
+    mbar_init(&mbar, 1);
+    mbar_expect_tx(&mbar, WIN_ROWS * WIN_PITCH + 256);
+    tma_load_2d(win, &tm.ref[ref], ax - xoff0, mby + by0 + JMB_PAD_Y, &mbar);
+    tma_load_2d(ssrc, &tm.cur, mbx, mby, &mbar);
+  }
+  __syncthreads();
+  mbar_wait(&mbar, 0);
+  const int nrg = (bh + 3) >> 2;
+  for (int it = tid; it < nrg * ncol; it += SF_NT) {
+    const int rg = it / ncol, ic = it - rg * ncol;
+    unsigned acc[4][16];
+    sad_item(win, ssrc, rg * 4, ic + xoff0, acc);
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      const int r = band * SF_BH + rg * 4 + s;
+      if (rg * 4 + s < bh)
+#pragma unroll
+        for (int b = 0; b < 16; b++) out[((size_t)b * nrow + r) * SF_PITCH + ic] = (unsigned short)acc[s][b];
+    }
+  }
+}
+
+struct SurfView { const unsigned short *p; int x0, y0, ncol, nrow; };      // surfaces of displacements [x0, x0+ncol) x [y0, y0+nrow)
+
+constexpr int AM_NT = 256;
+__global__ void __launch_bounds__(AM_NT)
+k_mb_argmin(jmb_me_req r, SurfView sv, int w, int h, int R, int max_mvd_m1, jmb_me_req *__restrict__ req_out, jmb_me_res *__restrict__ res,
+            volatile int *flag, int seq) {
+  __shared__ unsigned long long wbest[AM_NT / 32];
+  const int tid = threadIdx.x;
+  const PartGeom *pg = nullptr;
+  // partition geometry from the request (validated on the host)
+  const int bx4 = (r.pos_x & 15) >> 2, by4 = (r.pos_y & 15) >> 2;
+  const int w4 = (r.blocktype <= 2) ? 4 : (r.blocktype <= 5 ? 2 : 1);
+  const int h4 = (r.blocktype == 1 || r.blocktype == 3) ? 4 : ((r.blocktype == 2 || r.blocktype == 4 || r.blocktype == 6) ? 2 : 1);
+  (void)pg;
+  const bool ffs = r.mode == JMB_SEARCH_FAST_FULL;
+  const int ox = ffs ? (r.pos_x & ~15) : r.pos_x, oy = ffs ? (r.pos_y & ~15) : r.pos_y;      // origin the clamp applies to
+  const int dlo_x = -JMB_PAD_X - ox, dhi_x = (w + JMB_PAD_X - 1 - 16) - ox, dlo_y = -JMB_PAD_Y - oy, dhi_y = (h + JMB_PAD_Y - 1 - 16) - oy;
+  const int cx = r.center_x >> 2, cy = r.center_y >> 2, px = r.pred_x, py = r.pred_y, lam = r.lambda[0];
+  const int side = 2 * R + 1;
+  unsigned long long best = (unsigned long long)r.min_mcost << IDX_BITS;
+  for (int i = tid; i < side * side; i += AM_NT) {
+    const int dyi = i / side, dxi = i - dyi * side;
+    const int dx = cx - R + dxi, dy = cy - R + dyi;                  // the candidate (integer pels)
+    const int mx = 4 * dx - px, my = 4 * dy - py;
+    if (ffs && max(abs(mx), abs(my)) >= max_mvd_m1) continue;       // me_fullfast.c:671
+    const int Dx = jmb_clip(dlo_x, dhi_x, dx) - sv.x0, Dy = jmb_clip(dlo_y, dhi_y, dy) - sv.y0;   // where the block(s) are read (UMVLine4X)
+    unsigned sad = 0;
+    for (int y = 0; y < h4; y++)
+      for (int x = 0; x < w4; x++)
+        sad += sv.p[((size_t)((by4 + y) * 4 + bx4 + x) * sv.nrow + Dy) * SF_PITCH + Dx];
+    const unsigned long long cost = ((unsigned long long)sad << 5) + (unsigned long long)((long long)lam * (jmb_mvbits(mx) + jmb_mvbits(my)));
+    const unsigned long long k = (cost << IDX_BITS) | (unsigned)jmb_spiral_index(dx - cx, dy - cy);
+    best = min(best, k);
+  }
+#pragma unroll
+  for (int sh = 16; sh; sh >>= 1) {
+    const unsigned long long o = ((unsigned long long)__shfl_xor_sync(0xffffffffu, (unsigned)(best >> 32), sh) << 32) | __shfl_xor_sync(0xffffffffu, (unsigned)best, sh);
+    best = min(best, o);
+  }
+  if ((tid & 31) == 0) wbest[tid >> 5] = best;
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 1; i < AM_NT / 32; i++) best = min(best, wbest[i]);
+    int dx = 0, dy = 0;
+    if (best != ((unsigned long long)r.min_mcost << IDX_BITS)) spiral_xy((int)(best & ((1u << IDX_BITS) - 1)), &dx, &dy);
+    jmb_me_res o;
+    o.imv_x = o.mv_x = (int16_t)(4 * (cx + dx)); o.imv_y = o.mv_y = (int16_t)(4 * (cy + dy));
+    o.icost = o.cost = (long long)(best >> IDX_BITS);
+    *res = o;
+    *req_out = r;                     // the refinement kernel that may follow reads the request from device memory
+    if (flag) { __threadfence_system(); *flag = seq; }
+  }
+}
+
+// one request handed over by value (sub-pel-only calls of the drop-in path) + the completion flag of the mailbox
+__global__ void k_stage_req(jmb_me_req r, jmb_me_req *__restrict__ out) { *out = r; }
+__global__ void k_post_flag(const jmb_me_res *__restrict__ src, jmb_me_res *__restrict__ mailbox, volatile int *flag, int seq) {
+  *mailbox = *src;
+  __threadfence_system();
+  *flag = seq;
+}
+
 }  // namespace
 
 int jmb_launch_refine(jmb_ctx *ctx, const jmb_me_req *d_reqs, jmb_me_res *d_res, int n, const uint8_t *const *d_ref_planes);
@@ -825,6 +930,100 @@ int jmb_me_search_frame_pred(jmb_ctx *ctx, const jmb_mb_mvpred *pred, int n_mb, 
     if (res) JMB_CUDA(ctx, cudaMemcpyAsync(res, d_out, (size_t)n * sizeof(jmb_me_res8), cudaMemcpyDeviceToHost, ctx->stream));
     if (loc == JMB_HOST) return jmb_check_device_errors(ctx);
   }
+  return JMB_OK;
+}
+
+int jmb_mb_surfaces(jmb_ctx *ctx, int ref, int mb_x, int mb_y, int center_x, int center_y, int radius) {
+  if (!ctx->cur || ref < 0 || ref >= ctx->nref) return jmb_fail(ctx, JMB_ERR_STATE, "jmb_mb_surfaces: no picture / bad ref %d", ref);
+  if ((mb_x & 15) || (mb_y & 15) || mb_x < 0 || mb_y < 0 || mb_x + 16 > ctx->cur_w || mb_y + 16 > ctx->cur_h || ((center_x | center_y) & 3))
+    return jmb_fail(ctx, JMB_ERR_ARG, "jmb_mb_surfaces: macroblock (%d,%d) centre (%d,%d)", mb_x, mb_y, center_x, center_y);
+  if (radius < 1 || 2 * radius + 1 > CW) return jmb_fail(ctx, JMB_ERR_UNSUPPORTED, "jmb_mb_surfaces: radius %d (window wider than %d displacements)", radius, CW);
+  JMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  jmb_ctx::Surf &sf = ctx->surf[ref];
+  const int n = 2 * radius + 1;
+  const size_t bytes = (size_t)16 * n * SF_PITCH * sizeof(unsigned short);
+  int rc = jmb_reserve_dev(ctx, &sf.buf, &sf.cap, bytes); if (rc) return rc;
+  sf.valid = true; sf.mb_x = mb_x; sf.mb_y = mb_y; sf.x0 = (center_x >> 2) - radius; sf.y0 = (center_y >> 2) - radius; sf.n = n;
+  sf.pic_serial = ctx->pic_serial;
+  TMaps tm;
+  memset(&tm, 0, sizeof(tm));
+  tm.cur = ctx->tmap_cur;
+  for (int i = 0; i < ctx->nref; i++) tm.ref[i] = ctx->refs[ctx->ref_list[i]].tmap_int;
+  jmb_time_begin(ctx, JMB_K_FFS_SURF);
+  k_mb_surfaces<<<(n + SF_BH - 1) / SF_BH, SF_NT, 0, ctx->stream>>>(tm, ref, mb_x, mb_y, sf.x0, sf.y0, n, n, (unsigned short *)sf.buf);
+  jmb_time_end(ctx, JMB_K_FFS_SURF);
+  JMB_LAUNCH_CHECK(ctx);
+  return JMB_OK;
+}
+
+static int mailbox_init(jmb_ctx *ctx) {
+  if (ctx->mbox) return 0;
+  JMB_CUDA(ctx, cudaHostAlloc(&ctx->mbox, 256, cudaHostAllocMapped));
+  memset(ctx->mbox, 0, 256);
+  JMB_CUDA(ctx, cudaHostGetDevicePointer(&ctx->d_mbox, ctx->mbox, 0));
+  JMB_CUDA(ctx, cudaMalloc(&ctx->d_one, sizeof(jmb_me_req) + sizeof(jmb_me_res) + 64));
+  return 0;
+}
+
+// wait for the mailbox flag (the kernels write the result into host-mapped memory, then the flag); falls back to a stream
+// synchronisation when the flag does not show up in time (e.g. a launch failure, reported by the synchronisation)
+static int mailbox_wait(jmb_ctx *ctx, int seq) {
+  volatile int *flag = (volatile int *)((char *)ctx->mbox + 128);
+  for (long spin = 0; *flag != seq; spin++) {
+    if (spin > 2000000L) { JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); if (*flag != seq) return jmb_fail(ctx, JMB_ERR_CUDA, "mailbox: no answer from the device"); }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+  return 0;
+}
+
+int jmb_mb_search(jmb_ctx *ctx, const jmb_me_req *req, jmb_me_res *res) {
+  if (!req || !res) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_mb_search: NULL argument");
+  if (!ctx->cur || ctx->nref == 0) return jmb_fail(ctx, JMB_ERR_STATE, "jmb_mb_search: call jmb_pic_begin first");
+  int rc = validate_req(ctx, *req, 0); if (rc) return rc;
+  const bool skip_int = (req->flags & JMB_REQ_SKIP_INT) != 0, subpel = (req->flags & JMB_REQ_SUBPEL) != 0;
+  if (!skip_int && ctx->me.metric[0] != JMB_SAD) return jmb_fail(ctx, JMB_ERR_UNSUPPORTED, "jmb_mb_search: the surfaces are SAD surfaces (MEDistortionFPel = SAD)");
+  JMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  rc = mailbox_init(ctx); if (rc) return rc;
+  jmb_me_req *d_req = (jmb_me_req *)ctx->d_one;
+  jmb_me_res *d_res = (jmb_me_res *)((char *)ctx->d_one + 64), *mb_res = (jmb_me_res *)ctx->d_mbox;
+  volatile int *d_flag = (volatile int *)((char *)ctx->d_mbox + 128);
+  const int seq = ++ctx->mbox_seq;
+  if (!skip_int) {
+    const jmb_ctx::Surf &sf = ctx->surf[req->ref];
+    const int R = ctx->me.search_range, w = ctx->cur_w, h = ctx->cur_h;
+    const bool ffs = req->mode == JMB_SEARCH_FAST_FULL;
+    if (!sf.valid || sf.pic_serial != ctx->pic_serial || sf.mb_x != (req->pos_x & ~15) || sf.mb_y != (req->pos_y & ~15))
+      return jmb_fail(ctx, JMB_ERR_STATE, "jmb_mb_search: no surfaces resident for macroblock (%d,%d) reference %d", req->pos_x & ~15, req->pos_y & ~15, req->ref);
+    // every position the search reads (after UMVLine4X's clamp) must lie inside the resident surfaces
+    const int ox = ffs ? (req->pos_x & ~15) : req->pos_x, oy = ffs ? (req->pos_y & ~15) : req->pos_y;
+    const int dlo_x = -JMB_PAD_X - ox, dhi_x = (w + JMB_PAD_X - 1 - 16) - ox, dlo_y = -JMB_PAD_Y - oy, dhi_y = (h + JMB_PAD_Y - 1 - 16) - oy;
+    const int cx = req->center_x >> 2, cy = req->center_y >> 2;
+    auto clip = [](int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); };
+    const int lx = clip(dlo_x, dhi_x, cx - R), hx = clip(dlo_x, dhi_x, cx + R), ly = clip(dlo_y, dhi_y, cy - R), hy = clip(dlo_y, dhi_y, cy + R);
+    if (lx < sf.x0 || hx >= sf.x0 + sf.n || ly < sf.y0 || hy >= sf.y0 + sf.n)
+      return jmb_fail(ctx, JMB_ERR_STATE, "jmb_mb_search: window of the request (centre %d,%d) is not covered by the resident surfaces", req->center_x, req->center_y);
+    SurfView sv{(const unsigned short *)sf.buf, sf.x0, sf.y0, sf.n, sf.n};
+    jmb_time_begin(ctx, JMB_K_ARGMIN);
+    k_mb_argmin<<<1, AM_NT, 0, ctx->stream>>>(*req, sv, w, h, R, ctx->me.max_mvd - 1, d_req, subpel ? d_res : mb_res, subpel ? nullptr : d_flag, seq);
+    jmb_time_end(ctx, JMB_K_ARGMIN);
+    JMB_LAUNCH_CHECK(ctx);
+  } else {
+    k_stage_req<<<1, 1, 0, ctx->stream>>>(*req, d_req);
+    JMB_LAUNCH_CHECK(ctx);
+  }
+  if (subpel) {
+    const uint8_t *const *d_tab = nullptr;
+    if (!ctx->reftab_serial || ctx->reftab_serial != ctx->pic_serial) { rc = upload_ref_table(ctx, &d_tab, 0); if (rc) return rc; ctx->reftab_serial = ctx->pic_serial; }
+    d_tab = (const uint8_t *const *)ctx->d_reftab;
+    rc = jmb_launch_refine(ctx, d_req, d_res, 1, d_tab); if (rc) return rc;
+    k_post_flag<<<1, 1, 0, ctx->stream>>>(d_res, mb_res, d_flag, seq);
+    JMB_LAUNCH_CHECK(ctx);
+  }
+  rc = mailbox_wait(ctx, seq); if (rc) return rc;
+  *res = *(const jmb_me_res *)ctx->mbox;
+  if (ctx->h_err && (++ctx->mb_calls & 1023) == 0) return jmb_check_device_errors(ctx);      // device-side validation words, now and then
   return JMB_OK;
 }
 

@@ -104,6 +104,7 @@ void    __real_hadamard2x2(int **, int *);
 void    __real_ihadamard2x2(int *, int *);
 distblk __real_EPZS_integer_motion_estimation(Macroblock *, MotionVector *, MEBlock *, distblk, int);
 distblk __real_EPZS_sub_pel_motion_estimation(Macroblock *, MotionVector *, MEBlock *, distblk, int *);
+void    __real_select_distortion(VideoParameters *p_Vid, InputParameters *p_Inp);
 distblk __real_computeSAD(StorablePicture *, MEBlock *, distblk, MotionVector *);
 distblk __real_computeSSE(StorablePicture *, MEBlock *, distblk, MotionVector *);
 distblk __real_computeSATD(StorablePicture *, MEBlock *, distblk, MotionVector *);
@@ -763,6 +764,38 @@ distblk __wrap_computeSATD(StorablePicture *ref1, MEBlock *mv_block, distblk min
 {
   if (!shim_on(FAM_DIST)) return __real_computeSATD(ref1, mv_block, min_mcost, cand);
   return block_dist(JMB_SATD, ref1, mv_block, min_mcost, cand);
+}
+
+
+/* ---- mode-decision distortion back-ends: p_Vid->distortion4x4 / distortion8x8 (lencod/src/me_distortion.c:38-170) ------------
+ * select_distortion installs them from inside their own translation unit, so the wrapper lets it run and then points the two
+ * function pointers at device-backed versions (jmb_block_distortion).  Callers: GetSkipCostMB, BPredPartitionCost,
+ * BIDPartitionCost (mv_search.c:589-675, :1159-1325), the transform-size decision (macroblock.c:1413), intra chroma mode cost. */
+static int md_metric;
+static distblk md_block(short *diff, int n)
+{
+  int32_t d = 0;
+  int rc;
+  if (!shim_on(FAM_DIST))
+  { /* bisecting: JM's own arithmetic */
+    if (n == 4) return md_metric == ERROR_SAD ? distortion4x4SAD(diff, DISTBLK_MAX) : md_metric == ERROR_SSE ? distortion4x4SSE(diff, DISTBLK_MAX) : distortion4x4SATD(diff, DISTBLK_MAX);
+    return md_metric == ERROR_SAD ? distortion8x8SAD(diff, DISTBLK_MAX) : md_metric == ERROR_SSE ? distortion8x8SSE(diff, DISTBLK_MAX) : distortion8x8SATD(diff, DISTBLK_MAX);
+  }
+  rc = jmb_block_distortion(S.ctx, md_metric == ERROR_SAD ? JMB_SAD : md_metric == ERROR_SSE ? JMB_SSE : JMB_SATD, n, diff, 1, NULL, &d, JMB_HOST);
+  if (rc) jmb_die("jmb_block_distortion", rc);
+  S.calls[8]++;
+  return dist_scale((distblk)d);
+}
+static distblk md_distortion4x4(short *diff, distblk min_dist) { (void)min_dist; return md_block(diff, 4); }
+static distblk md_distortion8x8(short *diff, distblk min_dist) { (void)min_dist; return md_block(diff, 8); }
+
+void __wrap_select_distortion(VideoParameters *p_Vid, InputParameters *p_Inp)
+{
+  __real_select_distortion(p_Vid, p_Inp);
+  md_metric = (p_Inp->ModeDecisionMetric == ERROR_SAD || p_Inp->ModeDecisionMetric == ERROR_SSE) ? p_Inp->ModeDecisionMetric : ERROR_SATD;
+  if (getenv("JMB_SHIM") && !strcmp(getenv("JMB_SHIM"), "passthrough")) return;
+  p_Vid->distortion4x4 = md_distortion4x4;
+  p_Vid->distortion8x8 = md_distortion8x8;
 }
 
 /* ---- the other nine members of the distortion table (mv_search.c:486-506): weighted and bi-predictive forms -------

@@ -171,3 +171,27 @@ def test_epzs_rejects_bad_requests(ctx):
     with pytest.raises(api.JMBError, match="start_me_refinement_qp"):
         ctx.epzs_search(q, np.zeros((0, 2), np.int16))
     ctx.configure(search_range=8)
+
+
+@pytest.mark.parametrize("n", [4, 8])
+@pytest.mark.parametrize("metric", [api.SAD, api.SSE, api.SATD])
+def test_mode_decision_distortion_backends(ctx, oracle, n, metric):
+    """jmb_block_distortion = distortion4x4/8x8 SAD, SSE, SATD (me_distortion.c:38-146) on difference blocks; the 8x8 SAD also with
+    JM's row-wise threshold (distortion8x8SADthres)."""
+    rng = np.random.default_rng(70 + n + metric)
+    diff = rng.integers(-255, 256, size=(500, n * n)).astype(np.int16)
+    diff[::7] = rng.integers(-3, 4, size=(len(diff[::7]), n * n))
+    got = ctx.block_distortion(metric, n, diff)
+    if metric == api.SATD:
+        want = [oracle.hadamard4x4(d) if n == 4 else oracle.hadamard8x8(d) for d in diff]
+    elif metric == api.SSE:
+        want = (diff.astype(np.int64) ** 2).sum(1)
+    else:
+        want = np.abs(diff.astype(np.int64)).sum(1)
+    assert got.tolist() == [int(v) for v in want]
+    if n == 8 and metric == api.SAD:
+        thres = rng.integers(0, 6000, len(diff)).astype(np.int32)
+        got = ctx.block_distortion(metric, n, diff, thres)
+        rows = np.abs(diff.astype(np.int64)).reshape(-1, 8, 8).sum(2).cumsum(1)
+        want = [int(r[np.argmax(r > t)]) if (r > t).any() else int(r[-1]) for r, t in zip(rows, thres)]
+        assert got.tolist() == want

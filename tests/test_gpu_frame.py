@@ -246,3 +246,47 @@ def test_reference_read_from_a_peer_mapping():
     finally:
         a.send(b"done")
         proc.join(60)
+
+
+@pytest.mark.parametrize("mode", [api.SEARCH_FULL, api.SEARCH_FAST_FULL])
+def test_mb_surfaces_and_per_partition_argmin(ctx, mode):
+    """jmb_mb_surfaces + jmb_mb_search (the drop-in form: SAD surfaces once per macroblock, one small arg-min launch per
+    partition, answer through the mapped mailbox) must give exactly what the one-launch-per-request search gives -- which
+    tests/test_gpu_parity.py checks against the oracle -- incl. border macroblocks (UMVLine4X clamps), incoming bounds and the
+    sub-pel refinement; a window the resident surfaces do not cover is refused."""
+    w, h, R, E = 96, 80, 12, 6
+    f = synth.luma_frames(w, h, 2, seed=43, motion=(3, -2))
+    ctx.configure(search_range=R)
+    ctx.ref_put(0, f[0]); ctx.pic_begin(f[1], [0])
+    rng = np.random.default_rng(44)
+    parts = api.mb_partitions()
+    for mb in [(0, 0), (80, 64), (32, 32), (80, 0), (0, 64), (48, 16)]:
+        base = rng.integers(-40, 41, 2)
+        c0 = (((int(base[0]) + 2) >> 2) * 4, ((int(base[1]) + 2) >> 2) * 4)
+        ctx.mb_surfaces(0, mb, c0, R + E)
+        for k in rng.permutation(41)[:14]:
+            t, x, y = parts[k]
+            q = np.zeros(1, api.ME_REQ)
+            q["blocktype"] = t; q["pos_x"] = mb[0] + x; q["pos_y"] = mb[1] + y
+            p = base + rng.integers(-3 * E // 2, 3 * E // 2 + 1, 2)
+            q["pred_x"], q["pred_y"] = p
+            if mode == api.SEARCH_FULL:
+                q["center_x"] = ((int(p[0]) + 2) >> 2) * 4; q["center_y"] = ((int(p[1]) + 2) >> 2) * 4
+            else:
+                q["center_x"], q["center_y"] = c0
+            q["mode"] = mode; q["flags"] = api.REQ_SUBPEL if k % 2 else 0
+            q["lambda"] = int(rng.integers(1, 200))
+            q["min_mcost"] = BIG if k % 3 else int(rng.integers(200, 30000))
+            want = ctx.me_search(q)[0]
+            got = ctx.mb_search(q)
+            assert got == want, (mb, q, got, want)
+        # sub-pel only (the SubPelME call site)
+        q["flags"] = api.REQ_SUBPEL | api.REQ_SKIP_INT
+        assert ctx.mb_search(q) == ctx.me_search(q)[0]
+    q["flags"] = 0; q["center_x"] = int(q["center_x"]) + 4 * (E + 8)
+    with pytest.raises(api.JMBError, match="not covered"):
+        ctx.mb_search(q)
+    ctx.pic_begin(f[1], [0])            # a new picture invalidates the resident surfaces
+    q["center_x"] = c0[0]
+    with pytest.raises(api.JMBError, match="no surfaces resident"):
+        ctx.mb_search(q)
