@@ -109,7 +109,6 @@ distblk __real_computeSAD(StorablePicture *, MEBlock *, distblk, MotionVector *)
 distblk __real_computeSSE(StorablePicture *, MEBlock *, distblk, MotionVector *);
 distblk __real_computeSATD(StorablePicture *, MEBlock *, distblk, MotionVector *);
 
-typedef char jmb_distpel_is_32_bits[sizeof(distpel) == sizeof(uint32_t) ? 1 : -1];      /* jmb_ffs_surfaces writes JM's BlockSAD element type */
 
 enum { FAM_PLANES = 1, FAM_ME = 2, FAM_SUBPEL = 4, FAM_TQ = 8, FAM_DIST = 16 };
 
@@ -128,9 +127,12 @@ static struct
   unsigned long    calls[10];
   int              verify;            /* JMB_SHIM_VERIFY=1: differential check of the device luma_residual_coding */
   unsigned long    verified;
-  int              ffs_search;        /* JMB_SHIM_FFS=search: every partition's fast full search is a device call of its own */
-  uint32_t        *ffs_buf;           /* pinned: one macroblock's BlockSAD surfaces as jmb_ffs_surfaces lays them out */
-  size_t           ffs_cap;
+  /* surfaces resident on the device for the full search (jmb_mb_surfaces): macroblock and centre per device reference */
+  struct { int valid, mb_x, mb_y, cx, cy, radius; unsigned long pic; } surf[JMB_MAX_REFS];
+  unsigned long    pic_count;         /* bumped whenever the current picture / reference set is (re)sent */
+  /* the sub-pel refinement computed speculatively with the integer search of the same block (one device call instead of two) */
+  struct { int valid, pos_x, pos_y, blocktype, list, ref_idx, test8x8, lambda_h, lambda_q; MotionVector pred, imv, mv; distblk min_in, cost; } spec;
+  unsigned long    spec_hits, surf_builds;
 } S;
 
 /* JM's convention for fatal conditions is error(text, code) -> message on stderr, exit(code) (lencod/src/lencod.c).
@@ -159,9 +161,9 @@ static void report(void)
   if (S.init == 1 && S.verify)
     fprintf(stderr, "[jmb shim] luma_residual_coding verified on %lu macroblock codings (levels, cbp, cbp_blk, reconstruction)\n", S.verified);
   if (S.init == 1 && getenv("JMB_SHIM_VERBOSE"))
-    fprintf(stderr, "[jmb shim] planes %lu  full %lu  fastfull %lu  subpel %lu  fwd4 %lu  fwd8 %lu  quant4 %lu  quant8 %lu  dist %lu  kernel launches %llu  bipred/weighted distortions %lu\n",
+    fprintf(stderr, "[jmb shim] planes %lu  full %lu  fastfull %lu  subpel %lu  fwd4 %lu  fwd8 %lu  quant4 %lu  quant8 %lu  dist %lu  kernel launches %llu  bipred/weighted distortions %lu  subpel served by the integer search's call %lu  surface builds %lu\n",
             S.calls[0], S.calls[1], S.calls[2], S.calls[3], S.calls[4], S.calls[5], S.calls[6], S.calls[7], S.calls[8],
-            (unsigned long long)jmb_launch_count(S.ctx), S.calls[9]);
+            (unsigned long long)jmb_launch_count(S.ctx), S.calls[9], S.spec_hits, S.surf_builds);
 }
 
 static int shim_on(int family)
@@ -182,7 +184,6 @@ static int shim_on(int family)
       }
       S.init = 1;
       S.verify = getenv("JMB_SHIM_VERIFY") != NULL;
-      S.ffs_search = getenv("JMB_SHIM_FFS") && !strcmp(getenv("JMB_SHIM_FFS"), "search");
       if (off)
       {
         if (strstr(off, "planes")) S.off |= FAM_PLANES;
@@ -279,6 +280,8 @@ static int ref_index_of(VideoParameters *p_Vid, Slice *currSlice, MEBlock *mv_bl
     rc = jmb_pic_begin(S.ctx, (const uint16_t *)&cur[0][0], p_Vid->width, p_Vid->height, (int)(cur[1] - cur[0]), JMB_HOST, S.list, S.nlist);
     if (rc) jmb_die("jmb_pic_begin", rc);
     S.pic_valid = 1;
+    S.pic_count++;
+    S.spec.valid = 0;
   }
   for (i = 0; i < S.nlist; i++)
     if (S.list[i] == slot) return i;
@@ -329,13 +332,46 @@ static void fill_request(jmb_me_req *q, MEBlock *mv_block, MotionVector *pred_mv
   q->min_mcost = min_mcost;
 }
 
-/* stands behind full_search_motion_estimation (lencod/src/me_fullsearch.c:39) = currMB->IntPelME for SearchMode -1 */
+/* One partition's search + (speculatively) its sub-pel refinement in ONE device call over the macroblock's resident surfaces.
+ * BlockMotionSearch calls SubPelME right after IntPelME with the same block, predictor and -- in every configuration JM
+ * ships -- the same lambda at all three levels (mv_search.c:960-976); the refinement is therefore computed along with the
+ * integer search and handed out when SubPelME asks for exactly that (anything else: a device call of its own). */
+static int mb_search(Macroblock *currMB, MotionVector *pred_mv, MEBlock *mv_block, distblk min_mcost, int lambda_factor, int mode,
+                     int ri, int center_x, int center_y, jmb_me_res *r)
+{
+  VideoParameters *p_Vid = currMB->p_Vid;
+  jmb_me_req q;
+  int rc, spec = !currMB->p_Inp->DisableSubpelME[p_Vid->view_id];
+  fill_request(&q, mv_block, pred_mv, ri, min_mcost);
+  q.center_x = (int16_t)center_x;
+  q.center_y = (int16_t)center_y;
+  q.mode = (uint8_t)mode;
+  q.flags = (uint8_t)(spec ? (JMB_REQ_SUBPEL | (mv_block->test8x8 ? JMB_REQ_TEST8X8 : 0)) : 0);
+  q.lambda[0] = q.lambda[1] = q.lambda[2] = lambda_factor;
+  rc = jmb_mb_search(S.ctx, &q, r);
+  if (rc) return rc;
+  S.spec.valid = spec;
+  S.spec.pos_x = mv_block->pos_x; S.spec.pos_y = mv_block->pos_y; S.spec.blocktype = mv_block->blocktype;
+  S.spec.list = mv_block->list; S.spec.ref_idx = mv_block->ref_idx; S.spec.test8x8 = mv_block->test8x8;
+  S.spec.lambda_h = S.spec.lambda_q = lambda_factor;
+  S.spec.pred = *pred_mv;
+  S.spec.imv.mv_x = r->imv_x; S.spec.imv.mv_y = r->imv_y;
+  S.spec.mv.mv_x = r->mv_x;   S.spec.mv.mv_y = r->mv_y;
+  S.spec.min_in = p_Vid->start_me_refinement_hp ? (distblk)r->icost : DISTBLK_MAX;      /* what BlockMotionSearch hands to SubPelME */
+  S.spec.cost = (distblk)r->cost;
+  return 0;
+}
+
+/* stands behind full_search_motion_estimation (lencod/src/me_fullsearch.c:39) = currMB->IntPelME for SearchMode -1.
+ * The 4x4 SADs of the macroblock are computed once (jmb_mb_surfaces, a window E pels wider than the search window around the
+ * first partition's centre) and every partition's arg-min runs over them; a partition whose own window leaves that area gets
+ * fresh surfaces around its centre. */
 distblk __wrap_full_search_motion_estimation(Macroblock *currMB, MotionVector *pred_mv, MEBlock *mv_block, distblk min_mcost, int lambda_factor)
 {
   jmb_me_req q;
   jmb_me_res r;
   MotionVector *mv = &mv_block->mv[(short)mv_block->list];
-  int rc;
+  int rc, ri, R, E, mbx, mby, pass;
   if (!shim_on(FAM_ME)) return __real_full_search_motion_estimation(currMB, pred_mv, mv_block, min_mcost, lambda_factor);
   /* weighted-reference ME (UseWeightedReferenceME): JM's own loop runs and takes every distortion from the device
    * through mv_block->computePredFPel = computeSADWP (wrapped below) */
@@ -343,12 +379,32 @@ distblk __wrap_full_search_motion_estimation(Macroblock *currMB, MotionVector *p
     return __real_full_search_motion_estimation(currMB, pred_mv, mv_block, min_mcost, lambda_factor);
   if (!currMB->p_Inp->rdopt) unsupported("RDOptimization=0 (the (0,0) bias of full_search_motion_estimation)");
   S.calls[1]++;
-  configure(currMB, mv_block, imin(mv_block->searchRange.max_x, mv_block->searchRange.max_y) >> 2);
-  fill_request(&q, mv_block, pred_mv, ref_index(currMB, mv_block), min_mcost);
+  R = imin(mv_block->searchRange.max_x, mv_block->searchRange.max_y) >> 2;
+  configure(currMB, mv_block, R);
+  ri = ref_index(currMB, mv_block);
+  mbx = mv_block->pos_x & ~15; mby = mv_block->pos_y & ~15;
+  E = imin(8, (91 - (2 * R + 1)) / 2);
+  if (E >= 0)
+    for (pass = 0; pass < 2; pass++)
+    {
+      if (pass || !S.surf[ri].valid || S.surf[ri].pic != S.pic_count || S.surf[ri].mb_x != mbx || S.surf[ri].mb_y != mby)
+      { /* (re)build the surfaces around this partition's centre (mv_search.c:931-957 left it in mv) */
+        rc = jmb_mb_surfaces(S.ctx, ri, mbx, mby, mv->mv_x, mv->mv_y, R + E);
+        if (rc) jmb_die("jmb_mb_surfaces", rc);
+        S.surf[ri].valid = 1; S.surf[ri].pic = S.pic_count; S.surf[ri].mb_x = mbx; S.surf[ri].mb_y = mby;
+        S.surf_builds++;
+      }
+      rc = mb_search(currMB, pred_mv, mv_block, min_mcost, lambda_factor, JMB_SEARCH_FULL, ri, mv->mv_x, mv->mv_y, &r);
+      if (!rc) { mv->mv_x = r.imv_x; mv->mv_y = r.imv_y; return (distblk)r.icost; }
+      if (rc != JMB_ERR_STATE) jmb_die("jmb_mb_search(full)", rc);      /* JMB_ERR_STATE: window not covered -> fresh surfaces */
+    }
+  /* search ranges the surface kernel does not take (2R+1 > 91 displacements): one launch per request */
+  fill_request(&q, mv_block, pred_mv, ri, min_mcost);
   q.center_x = mv->mv_x;           /* the search centre BlockMotionSearch left in mv (mv_search.c:931-957) */
   q.center_y = mv->mv_y;
   q.mode = JMB_SEARCH_FULL;
   q.lambda[0] = lambda_factor;
+  S.spec.valid = 0;
   rc = jmb_me_search(S.ctx, &q, 1, &r, JMB_HOST);
   if (rc) jmb_die("jmb_me_search(full)", rc);
   mv->mv_x = r.imv_x;
@@ -356,16 +412,17 @@ distblk __wrap_full_search_motion_estimation(Macroblock *currMB, MotionVector *p
   return (distblk)r.icost;
 }
 
-/* setup_fast_full_search (lencod/src/me_fullfast.c:269): the search-centre rule (:305-329) on the host, the BlockSAD
- * surfaces from the device (jmb_ffs_surfaces).  With JMB_SHIM_FFS=search no surfaces are built: each partition's search is
- * then a device call of its own (jmb_me_search, FAST_FULL mode), which evaluates the SADs in registers. */
+/* setup_fast_full_search (lencod/src/me_fullfast.c:269): the search-centre rule (:305-329) on the host; the BlockSAD surfaces
+ * (:492-556) are built on the device and STAY there (jmb_mb_surfaces) -- JM's own BlockSAD arrays are never filled. */
 void __wrap_setup_fast_full_search(Macroblock *currMB, MEBlock *mv_block, int list)
 {
   VideoParameters *p_Vid = currMB->p_Vid;
   InputParameters *p_Inp = currMB->p_Inp;
   MEFullFast *ff = p_Vid->p_ffast_me;
+  Slice *currSlice = currMB->p_Slice;
   short ref = mv_block->ref_idx;
-  int search_range = ff->max_search_range[list][ref] << 2;
+  int search_range = ff->max_search_range[list][ref] << 2, sr = ff->max_search_range[list][ref], ri, rc;
+  int list_offset = p_Vid->mb_data[currMB->mbAddrX].list_offset;
   MotionVector pmv, *c = &ff->search_center[list][ref];
   PixelPos block[4];
   if (!shim_on(FAM_ME)) { __real_setup_fast_full_search(currMB, mv_block, list); return; }
@@ -373,6 +430,7 @@ void __wrap_setup_fast_full_search(Macroblock *currMB, MEBlock *mv_block, int li
   /* setup_fast_full_search builds SQUARED-error surfaces for any full-pel metric but SAD (dist_method, me_fullfast.c:274) */
   if (p_Inp->MEErrorMetric[F_PEL] != ERROR_SAD) unsupported("fast full search with MEDistortionFPel other than SAD (squared-error BlockSAD surfaces)");
   if (mv_block->apply_weights) unsupported("fast full search with UseWeightedReferenceME (its weighted SAD surfaces are inline host code; use SearchMode -1 or 3)");
+  if (2 * sr + 1 > 91) unsupported("fast full search with a SearchRange above 45");
   get_neighbors(currMB, block, 0, 0, 16);
   currMB->GetMVPredictor(currMB, block, &pmv, ref, p_Vid->enc_picture->mv_info, list, 0, 0, 16, 16);
 #if (JM_INT_DIVIDE)
@@ -385,61 +443,42 @@ void __wrap_setup_fast_full_search(Macroblock *currMB, MEBlock *mv_block, int li
   c->mv_x = (short)iClip3(p_Vid->MaxHmvR[4] + search_range, p_Vid->MaxHmvR[5] - search_range, c->mv_x);
   c->mv_y = (short)iClip3(p_Vid->MaxVmvR[4] + search_range, p_Vid->MaxVmvR[5] - search_range, c->mv_y);
   ff->search_center_padded[list][ref] = pad_MVs(*c, mv_block);
-  if (!S.ffs_search)
-  {
-    /* Default: the device builds the macroblock's BlockSAD surfaces (:492-556 + update_full_search_large_blocks) in ONE
-     * call and hands them to JM in JM's own arrays; the 41 per-partition arg-mins then run in JM's own
-     * fast_full_search_motion_estimation on the host, exactly as JM splits the work (67 % / 7 % of its run time). */
-    static const unsigned short used[8] = {0, 0x0001, 0x0101, 0x0005, 0x0505, 0x5555, 0x0f0f, 0xffff};   /* slots per block type */
-    Slice *currSlice = currMB->p_Slice;
-    int list_offset = p_Vid->mb_data[currMB->mbAddrX].list_offset;
-    int sr = ff->max_search_range[list][ref], max_pos = (2 * sr + 1) * (2 * sr + 1), bt, k, rc, ri;
-    size_t bytes = (size_t)8 * 16 * max_pos * sizeof(uint32_t);
-    if (mv_block->pos_x != currMB->pix_x || mv_block->pos_y != currMB->opix_y)
-      unsupported("setup_fast_full_search entered with a block that is not at the macroblock origin");
-    if (bytes > S.ffs_cap)
-    {
-      if (S.ffs_buf) jmb_host_free(S.ctx, S.ffs_buf);
-      rc = jmb_host_alloc(S.ctx, bytes, (void **)&S.ffs_buf);
-      if (rc) jmb_die("jmb_host_alloc", rc);
-      S.ffs_cap = bytes;
-    }
-    configure(currMB, mv_block, sr);
-    ri = ref_index_of(p_Vid, currSlice, mv_block, currSlice->listX[list + list_offset][ref]);
-    rc = jmb_ffs_surfaces(S.ctx, ri, currMB->pix_x, currMB->opix_y, c->mv_x, c->mv_y, S.ffs_buf, JMB_HOST);
-    if (rc) jmb_die("jmb_ffs_surfaces", rc);
-    for (bt = 1; bt < 8; bt++)
-      for (k = 0; k < 16; k++)
-        if ((used[bt] >> k) & 1)
-          memcpy(ff->BlockSAD[list][ref][bt][k], S.ffs_buf + ((size_t)bt * 16 + k) * max_pos, (size_t)max_pos * sizeof(distpel));
-    S.calls[2]++;
-  }
+  if (mv_block->pos_x != currMB->pix_x || mv_block->pos_y != currMB->opix_y)
+    unsupported("setup_fast_full_search entered with a block that is not at the macroblock origin");
+  configure(currMB, mv_block, sr);
+  ri = ref_index_of(p_Vid, currSlice, mv_block, currSlice->listX[list + list_offset][ref]);
+  rc = jmb_mb_surfaces(S.ctx, ri, currMB->pix_x, currMB->opix_y, c->mv_x, c->mv_y, sr);
+  if (rc) jmb_die("jmb_mb_surfaces", rc);
+  S.surf_builds++;
+  S.calls[2]++;
   ff->search_setup_done[list][ref] = 1;
 }
 
-/* stands behind fast_full_search_motion_estimation (lencod/src/me_fullfast.c:618) = currMB->IntPelME for SearchMode 0 */
+/* stands behind fast_full_search_motion_estimation (lencod/src/me_fullfast.c:618) = currMB->IntPelME for SearchMode 0:
+ * the arg-min of one partition over the resident surfaces, on the device */
 distblk __wrap_fast_full_search_motion_estimation(Macroblock *currMB, MotionVector *pred_mv, MEBlock *mv_block, distblk min_mcost, int lambda_factor)
 {
   VideoParameters *p_Vid = currMB->p_Vid;
   MEFullFast *ff = p_Vid->p_ffast_me;
   int list = mv_block->list, rc;
   short ref = mv_block->ref_idx;
-  jmb_me_req q;
   jmb_me_res r;
   if (!shim_on(FAM_ME)) return __real_fast_full_search_motion_estimation(currMB, pred_mv, mv_block, min_mcost, lambda_factor);
   if (!currMB->p_Inp->rdopt) unsupported("RDOptimization=0 with fast full search");
-  if (!S.ffs_search)      /* surfaces came from the device (setup above); the arg-min over them is JM's own loop */
-    return __real_fast_full_search_motion_estimation(currMB, pred_mv, mv_block, min_mcost, lambda_factor);
   S.calls[2]++;
   if (!ff->search_setup_done[list][ref]) currMB->p_SetupFastFullPelSearch(currMB, mv_block, list);
   configure(currMB, mv_block, imax(mv_block->searchRange.max_x, mv_block->searchRange.max_y) >> 2);
-  fill_request(&q, mv_block, pred_mv, ref_index(currMB, mv_block), min_mcost);
-  q.center_x = ff->search_center[list][ref].mv_x;
-  q.center_y = ff->search_center[list][ref].mv_y;
-  q.mode = JMB_SEARCH_FAST_FULL;
-  q.lambda[0] = lambda_factor;
-  rc = jmb_me_search(S.ctx, &q, 1, &r, JMB_HOST);
-  if (rc) jmb_die("jmb_me_search(fast full)", rc);
+  rc = mb_search(currMB, pred_mv, mv_block, min_mcost, lambda_factor, JMB_SEARCH_FAST_FULL, ref_index(currMB, mv_block),
+                 ff->search_center[list][ref].mv_x, ff->search_center[list][ref].mv_y, &r);
+  if (rc == JMB_ERR_STATE)
+  { /* the device's reference set changed since the setup (a recycled slot was uploaded again): build the surfaces again */
+    MEBlock at_mb = *mv_block;
+    at_mb.pos_x = currMB->pix_x; at_mb.pos_y = currMB->opix_y;
+    currMB->p_SetupFastFullPelSearch(currMB, &at_mb, list);
+    rc = mb_search(currMB, pred_mv, mv_block, min_mcost, lambda_factor, JMB_SEARCH_FAST_FULL, ref_index(currMB, mv_block),
+                   ff->search_center[list][ref].mv_x, ff->search_center[list][ref].mv_y, &r);
+  }
+  if (rc) jmb_die("jmb_mb_search(fast full)", rc);
   mv_block->mv[list].mv_x = r.imv_x;
   mv_block->mv[list].mv_y = r.imv_y;
   return (distblk)r.icost;
@@ -450,12 +489,23 @@ distblk __wrap_sub_pel_motion_estimation(Macroblock *currMB, MotionVector *pred,
 {
   jmb_me_req q;
   jmb_me_res r;
-  MotionVector *mv = &mv_block->mv[mv_block->list];
+  MotionVector *mv = &mv_block->mv[(int)mv_block->list];
   int rc;
   if (!shim_on(FAM_SUBPEL)) return __real_sub_pel_motion_estimation(currMB, pred, mv_block, min_mcost, lambda);
   if (mv_block->apply_weights) return __real_sub_pel_motion_estimation(currMB, pred, mv_block, min_mcost, lambda);   /* -> compute*WP on the device */
   if (!currMB->p_Inp->rdopt) unsupported("RDOptimization=0 (the (0,0) bias of sub_pel_motion_estimation)");
   S.calls[3]++;
+  if (S.spec.valid && S.spec.pos_x == mv_block->pos_x && S.spec.pos_y == mv_block->pos_y && S.spec.blocktype == mv_block->blocktype &&
+      S.spec.list == mv_block->list && S.spec.ref_idx == mv_block->ref_idx && S.spec.test8x8 == mv_block->test8x8 &&
+      S.spec.lambda_h == lambda[H_PEL] && S.spec.lambda_q == lambda[Q_PEL] && S.spec.pred.mv_x == pred->mv_x && S.spec.pred.mv_y == pred->mv_y &&
+      S.spec.imv.mv_x == mv->mv_x && S.spec.imv.mv_y == mv->mv_y && S.spec.min_in == min_mcost)
+  { /* exactly the refinement the integer search's device call already did */
+    S.spec.valid = 0;
+    S.spec_hits++;
+    *mv = S.spec.mv;
+    return S.spec.cost;
+  }
+  S.spec.valid = 0;
   configure(currMB, mv_block, 0);
   fill_request(&q, mv_block, pred, ref_index(currMB, mv_block), min_mcost);
   q.center_x = mv->mv_x;
@@ -465,13 +515,12 @@ distblk __wrap_sub_pel_motion_estimation(Macroblock *currMB, MotionVector *pred,
   q.lambda[0] = lambda[F_PEL];
   q.lambda[1] = lambda[H_PEL];
   q.lambda[2] = lambda[Q_PEL];
-  rc = jmb_me_search(S.ctx, &q, 1, &r, JMB_HOST);
-  if (rc) jmb_die("jmb_me_search(sub-pel)", rc);
+  rc = jmb_mb_search(S.ctx, &q, &r);
+  if (rc) jmb_die("jmb_mb_search(sub-pel)", rc);
   mv->mv_x = r.mv_x;
   mv->mv_y = r.mv_y;
   return (distblk)r.cost;
 }
-
 
 /* ---- EPZS (SearchMode 3 with EPZSSubPelGrid: currMB->IntPelME = EPZS_integer_motion_estimation, me_epzs_common.c:155;
  *      currMB->SubPelME = EPZS_sub_pel_motion_estimation with EPZSSubPelME = 1) --------------------------------------------

@@ -68,6 +68,12 @@ CONFIGS = {
     # stays JM's host code, every distortion it evaluates (computeSAD / computeSATD) comes from the device
     "epzs_high_8x8": ["ProfileIDC=100", "SymbolMode=1", "RDOptimization=1", "Transform8x8Mode=1", "QPISlice=28", "QPPSlice=28",
                       "SearchMode=3", "SearchRange=16", "NumberReferenceFrames=2", "AdaptiveRounding=1"],
+    # the same with bin/encoder.cfg's EPZSSubPelGrid=1 (+ its pattern settings): currMB->IntPelME = EPZS_integer_motion_estimation and
+    # SubPelME = EPZS_sub_pel_motion_estimation, whose WHOLE state machines run on the device -- one jmb_epzs_search call per search
+    "epzs_subpelgrid_high_8x8": ["ProfileIDC=100", "SymbolMode=1", "RDOptimization=1", "Transform8x8Mode=1", "QPISlice=28", "QPPSlice=28",
+                                 "SearchMode=3", "SearchRange=32", "NumberReferenceFrames=3", "AdaptiveRounding=1", "EPZSSubPelGrid=1",
+                                 "EPZSPattern=2", "EPZSDualRefinement=3", "EPZSFixedPredictors=3", "EPZSTemporal=1", "EPZSSpatialMem=1",
+                                 "EPZSBlockType=1", "MEDistortionHPel=2", "MEDistortionQPel=2"],
     # B pictures (two between anchors, Main-style tools in High): list-1 searches and more DPB traffic go through the shim,
     # the bi-predictive refinement and direct modes stay JM's C code
     "b_frames_high": ["ProfileIDC=100", "SymbolMode=1", "RDOptimization=1", "Transform8x8Mode=1", "QPISlice=28", "QPPSlice=28", "QPBSlice=30",
@@ -142,7 +148,9 @@ def test_bitstream_identical_to_stock_jm(tmp_path, name):
     assert line, "the shim did not report: was the GPU path used?"
     counts = dict(zip(line[0].split()[2::2][:9], [int(x) for x in line[0].split()[3::2][:9]]))
     assert counts["planes"] >= max(1, (frames - 1) // (bframes + 1)) and counts["quant4"] + counts["quant8"] > 0, line[0]
-    if "SearchMode=3" in CONFIGS[name] or "UseWeightedReferenceME=1" in CONFIGS[name]:
+    if "EPZSSubPelGrid=1" in CONFIGS[name]:
+        assert counts["full"] > 0 and counts["subpel"] > 0 and counts["dist"] < counts["full"], line[0]      # searches as whole device calls
+    elif "SearchMode=3" in CONFIGS[name] or "UseWeightedReferenceME=1" in CONFIGS[name]:
         assert counts["dist"] > 0, line[0]                       # EPZS / weighted-reference ME: distortion oracle
     else:
         assert counts["full"] + counts["fastfull"] > 0 and counts["subpel"] > 0, line[0]
@@ -214,12 +222,18 @@ def test_bundled_configurations(tmp_path, cfg):
 
 @pytest.mark.gpu
 @needs_bins
-def test_fast_full_search_as_per_partition_device_searches(tmp_path):
-    """JMB_SHIM_FFS=search: no BlockSAD surfaces are handed to JM; each partition's fast full search is a jmb_me_search call
-    (FAST_FULL mode) of its own -- the path the picture-level API uses.  Same bitstream."""
+@pytest.mark.parametrize("name", ["fast_full_search_around", "full_search_baseline"])
+def test_searches_run_on_resident_surfaces_with_device_argmin(tmp_path, name):
+    """No arg-min on the host: the macroblock's SAD surfaces stay on the device (jmb_mb_surfaces) and every partition's search is
+    a device arg-min over them (jmb_mb_search); the sub-pel refinement BlockMotionSearch asks for next comes out of the same
+    device call.  Same bitstream as stock JM."""
     w, h, frames = 96, 80, 3
     _make_yuv(tmp_path / "input.yuv", w, h, frames, seed=12)
-    r1 = _encode(REF, tmp_path, "ref", w, h, frames, CONFIGS["fast_full_search_around"])
-    r2 = _encode(JMB, tmp_path, "gpu", w, h, frames, CONFIGS["fast_full_search_around"], env={"JMB_SHIM_FFS": "search", "JMB_SHIM_VERBOSE": "1"})
+    r1 = _encode(REF, tmp_path, "ref", w, h, frames, CONFIGS[name])
+    r2 = _encode(JMB, tmp_path, "gpu", w, h, frames, CONFIGS[name], env={"JMB_SHIM_VERBOSE": "1"})
     assert r1.returncode == 0 and r2.returncode == 0, (r1.stderr[-500:], r2.stderr[-500:])
     _same_outputs(tmp_path, "ref", "gpu")
+    line = [l for l in r2.stderr.splitlines() if l.startswith("[jmb shim]")][0]
+    served = int(line.split("served by the integer search's call")[1].split()[0]); builds = int(line.split("surface builds")[1].split()[0])
+    searches = int(line.split("full")[1].split()[0]) + int(line.split("fastfull")[1].split()[0])
+    assert builds > 0 and served > 0.9 * searches, line
