@@ -393,6 +393,32 @@ typedef struct jmb_tq_token { int16_t level; uint8_t run; uint8_t blk; } jmb_tq_
 int jmb_mc_tq_modes_compact(jmb_ctx *ctx, const jmb_me_res *res, int n_mb, unsigned mode_mask, const jmb_quant_desc *q,
                             jmb_tq_head *heads, jmb_tq_token *tokens, uint32_t token_cap, uint32_t *n_tokens, int loc);
 
+/* ---- chroma of inter macroblocks: motion-compensated prediction + residual coding ------------------------
+ * jmb_ref_put_chroma / jmb_pic_chroma: the U and V planes of a reference slot / of the current picture (8-bit samples when
+ * sample_bytes = 1, uint16_t when 2), width_c x height_c each (4:2:0: w/2 x h/2; 4:2:2: w/2 x h).
+ * jmb_chroma_residual_coding: for macroblocks first_mb .. first_mb + n_mb - 1 of a P slice, both components:
+ *   prediction      OneComponentChromaPrediction4x4 (lencod/src/mc_prediction.c:292-352): every chroma sample takes the motion
+ *                   vector of the luma 4x4 block above it, bilinear at 1/8 sample (1/4 vertically for 4:2:2), picture clamp;
+ *   residual coding residual_transform_quant_chroma_4x4 (lencod/src/block.c:954-1202): forward4x4 of the 4 / 8 blocks, DC through
+ *                   hadamard2x2 + quant_dc2x2_normal (4:2:0) or hadamard4x2 + quant_dc4x2_normal at qp + 3 (4:2:2), quant_ac4x4_normal
+ *                   with one running coeff_cost per component, the _CHROMA_COEFF_COST_ threshold, inverse4x4 + sample_reconstruct.
+ * Motion: pred[i] (as jmb_mc_tq) or, with pred == NULL, partition mode `mode` of the resident search results, reference 0.
+ * Outputs per macroblock: dc_levels [2][8] and ac_levels [2][8][15] int16, dense in scan order (SCAN_YUV420 / SCAN_YUV422, zig-zag
+ * positions 1..15; block b = by * 2 + bx); cbp_blk_chroma = bits 16.. of currMB->cbp_blk shifted down by 16 (cbp_blk_chroma,
+ * block.c:158); cr_cbp = what chroma_residual_coding adds to currMB->cbp >> 4 (0, 1, 2); recon [2][16][8] uint8 (may be NULL). */
+typedef struct jmb_chroma_desc {
+  int32_t yuv_format;              /* 1 = 4:2:0, 2 = 4:2:2 */
+  int32_t is_cavlc;
+  int32_t qp_ac[2], qp_dc[2];      /* currMB->qpc[uv] + bitdepth_chroma_qp_scale; the DC qp is that + 3 for 4:2:2 */
+  int32_t params_ac[2][16][3];     /* q_params_4x4[uv + 1][0][qp_ac][j][i] = {OffsetComp, ScaleComp, InvScaleComp} at [j * 4 + i] */
+  int32_t params_dc[2][3];         /* q_params_4x4[uv + 1][0][qp_dc][0][0] */
+  uint8_t c_cost[16];              /* COEFF_COST4x4[disthres] */
+} jmb_chroma_desc;
+int jmb_ref_put_chroma(jmb_ctx *ctx, int slot, const void *u, const void *v, int sample_bytes, int width_c, int height_c, int stride, int loc);
+int jmb_pic_chroma(jmb_ctx *ctx, const void *u, const void *v, int sample_bytes, int width_c, int height_c, int stride, int loc);
+int jmb_chroma_residual_coding(jmb_ctx *ctx, const jmb_mb_pred *pred, int mode, int first_mb, int n_mb, const jmb_chroma_desc *d,
+                               int16_t *dc_levels, int16_t *ac_levels, uint32_t *cbp_blk_chroma, uint32_t *cr_cbp, uint8_t *recon, int loc);
+
 /* nlist lists of q->m coefficients (scan order), in place: on return the dequantised coefficients; levels / runs [nlist][17]
  * (terminated by level 0), fadjust [nlist][m] (around only, may be NULL), coeff_cost [nlist] (added to; may be NULL), nonzero [nlist] */
 int jmb_quant_list(jmb_ctx *ctx, const jmb_qlist_desc *q, int32_t *coef, int nlist, int32_t *levels, int32_t *runs, int32_t *fadjust,

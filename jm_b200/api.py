@@ -57,6 +57,9 @@ EPZS_REF_GT0_FRAME, EPZS_ADAPT_PATTERN, EPZS_SQUARE_HINT, EPZS_DUAL, EPZS_SUBPEL
 EPZS_MIN_BASE = [0, 64, 32, 32, 16, 8, 8, 4]
 EPZS_MED_BASE = [0, 192, 96, 96, 48, 24, 24, 12]
 EPZS_MAX_BASE = [0, 768, 384, 384, 192, 96, 96, 48]
+CHROMA_DESC = np.dtype([("yuv_format", "<i4"), ("is_cavlc", "<i4"), ("qp_ac", "<i4", (2,)), ("qp_dc", "<i4", (2,)),
+                        ("params_ac", "<i4", (2, 16, 3)), ("params_dc", "<i4", (2, 3)), ("c_cost", "u1", (16,))])
+assert CHROMA_DESC.itemsize == 448
 IPC_HANDLE_BYTES = 64
 # level 4 .. 5.1 mv range in quarter-pel (LEVELHMVLIMIT / LEVELVMVLIMIT, lencod/src/conformance.c): +-2048 x +-512 pels
 MV_RANGE_L51 = (-8192, 8191, -2048, 2047)
@@ -113,6 +116,9 @@ def load_library():
     L.jmb_me_search_frame_pred.argtypes = [vp, vp, i, vp, vp, i]
     L.jmb_mc_tq_modes_compact.argtypes = [vp, vp, i, C.c_uint, vp, vp, vp, C.c_uint32, vp, i]
     L.jmb_block_distortion.argtypes = [vp, i, i, vp, i, vp, vp, i]
+    L.jmb_ref_put_chroma.argtypes = [vp, i, vp, vp, i, i, i, i, i]
+    L.jmb_pic_chroma.argtypes = [vp, vp, vp, i, i, i, i, i]
+    L.jmb_chroma_residual_coding.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp, vp, vp, i]
     L.jmb_mb_surfaces.argtypes = [vp, i, i, i, i, i, i]
     L.jmb_mb_search.argtypes = [vp, vp, vp]
     L.jmb_epzs_search.argtypes = [vp, vp, i, vp, i, vp, i]
@@ -257,6 +263,25 @@ def epzs_requests_from_frame(pred, fp, mb_w, mb_index=None):
     return reqs.reshape(-1)
 
 
+# QP_SCALE_CR of lcommon (chroma qp from luma qp, H.264 table 8-15) and the chroma descriptor JM's tables give for an inter macroblock
+QP_SCALE_CR = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 29, 30, 31, 32, 32, 33,
+               34, 34, 35, 35, 36, 36, 37, 37, 37, 38, 38, 38, 39, 39, 39, 39]
+
+
+def chroma_desc(yuv_format, qp_luma, q_params_fn, c_cost, is_cavlc, chroma_qp_offset=(0, 0)):
+    """q_params_fn(qp) -> [4][4][3] inter luma/chroma parameters (flat matrices: the same table serves Y, U and V)."""
+    d = np.zeros(1, CHROMA_DESC)
+    d["yuv_format"] = yuv_format; d["is_cavlc"] = int(is_cavlc)
+    for uv in range(2):
+        qpc = QP_SCALE_CR[min(51, max(0, qp_luma + chroma_qp_offset[uv]))]
+        qp_dc = qpc + (3 if yuv_format == 2 else 0)
+        d["qp_ac"][0, uv] = qpc; d["qp_dc"][0, uv] = qp_dc
+        d["params_ac"][0, uv] = np.asarray(q_params_fn(qpc), np.int32).reshape(16, 3)
+        d["params_dc"][0, uv] = np.asarray(q_params_fn(qp_dc), np.int32).reshape(16, 3)[0]
+    d["c_cost"][0] = np.asarray(c_cost, np.uint8)[:16]
+    return d
+
+
 def quant_desc(n, qp, qparams, scan, c_cost, is_cavlc, around=0, arw=0):
     q = np.zeros(1, QUANT_DESC)
     q["n"], q["qp"], q["is_cavlc"], q["around"], q["adapt_rnd_weight"] = n, qp, int(is_cavlc), int(around), int(arw)
@@ -377,6 +402,32 @@ class Context:
         if loc == HOST:
             return heads, tokens[:int(n_tok[0])]
         return heads, tokens, n_tok
+
+    def ref_put_chroma(self, slot, u, v, loc=HOST, shape=None, sample_bytes=1):
+        if loc != DEVICE:
+            assert u.dtype == v.dtype and u.flags["C_CONTIGUOUS"] and v.flags["C_CONTIGUOUS"] and u.shape == v.shape
+            shape = u.shape; sample_bytes = u.dtype.itemsize
+        self._ck(self.L.jmb_ref_put_chroma(self.h, slot, _ptr(u), _ptr(v), sample_bytes, shape[1], shape[0], shape[1], loc))
+
+    def pic_chroma(self, u, v, loc=HOST, shape=None, sample_bytes=1):
+        if loc != DEVICE:
+            assert u.dtype == v.dtype and u.flags["C_CONTIGUOUS"] and v.flags["C_CONTIGUOUS"] and u.shape == v.shape
+            shape = u.shape; sample_bytes = u.dtype.itemsize
+        self._ck(self.L.jmb_pic_chroma(self.h, _ptr(u), _ptr(v), sample_bytes, shape[1], shape[0], shape[1], loc))
+
+    def chroma_residual_coding(self, desc, pred=None, mode=1, first_mb=0, n_mb=None, loc=HOST, out=None, want_recon=True):
+        """pred: MB_PRED[n_mb] or None (partition mode `mode` of the resident search results).  HOST: returns dict(dc, ac, cbp_blk,
+        cr_cbp, recon) with dc [n_mb][2][8], ac [n_mb][2][8][15], cbp_blk / cr_cbp [n_mb][2], recon [n_mb][2][16][8]."""
+        if loc != DEVICE:
+            if pred is not None:
+                pred = np.ascontiguousarray(pred, MB_PRED); n_mb = len(pred)
+            o = dict(dc=np.zeros((n_mb, 2, 8), np.int16), ac=np.zeros((n_mb, 2, 8, 15), np.int16), cbp_blk=np.zeros((n_mb, 2), np.uint32),
+                     cr_cbp=np.zeros((n_mb, 2), np.uint32), recon=np.zeros((n_mb, 2, 16, 8), np.uint8) if want_recon else None)
+            self._ck(self.L.jmb_chroma_residual_coding(self.h, None if pred is None else _ptr(pred), mode, first_mb, n_mb, _ptr(desc), _ptr(o["dc"]),
+                                                       _ptr(o["ac"]), _ptr(o["cbp_blk"]), _ptr(o["cr_cbp"]), None if o["recon"] is None else _ptr(o["recon"]), loc))
+            return o
+        dc, ac, cb, cc, rec = out
+        self._ck(self.L.jmb_chroma_residual_coding(self.h, None if pred is None else _ptr(pred), mode, first_mb, n_mb, _ptr(desc), dc, ac, cb, cc, rec, loc))
 
     def mb_surfaces(self, ref, mb, center, radius):
         self._ck(self.L.jmb_mb_surfaces(self.h, ref, mb[0], mb[1], center[0], center[1], radius))

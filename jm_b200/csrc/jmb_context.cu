@@ -157,7 +157,8 @@ void jmb_destroy(jmb_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (int i = 0; i < JMB_MAX_REFS; i++) if (ctx->refs[i].planes) cudaFree(ctx->refs[i].planes);
+  for (int i = 0; i < JMB_MAX_REFS; i++) { if (ctx->refs[i].planes) cudaFree(ctx->refs[i].planes); if (ctx->refs[i].chroma) cudaFree(ctx->refs[i].chroma); }
+  if (ctx->cur_c) cudaFree(ctx->cur_c);
   if (ctx->cur) cudaFree(ctx->cur);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->h_groups) cudaFreeHost(ctx->h_groups);
@@ -282,6 +283,7 @@ int jmb_ref_drop(jmb_ctx *ctx, int slot) {
   jmb_ref *r = &ctx->refs[slot];
   JMB_CUDA(ctx, cudaSetDevice(ctx->device));
   if (r->planes) { JMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); JMB_CUDA(ctx, cudaFree(r->planes)); }
+  if (r->chroma) JMB_CUDA(ctx, cudaFree(r->chroma));
   *r = jmb_ref();
   return JMB_OK;
 }

@@ -19,6 +19,7 @@ struct jmb_ref {
   int w = 0, h = 0, W = 0, H = 0, pitch = 0;
   size_t plane_bytes = 0;
   bool valid = false;
+  uint8_t *chroma = nullptr; int wc = 0, hc = 0, pitch_c = 0;      // U plane then V plane, u8, hc rows of pitch_c bytes each
   CUtensorMap tmap_int;      // TMA descriptor of the integer plane [0][0]: u8, W x H, box = search-window tile
 };
 
@@ -30,6 +31,7 @@ struct jmb_ctx {
   jmb_ref refs[JMB_MAX_REFS];
   // current picture (u8) and the reference list of this picture
   uint8_t *cur = nullptr; int cur_w = 0, cur_h = 0, cur_pitch = 0; size_t cur_cap = 0;
+  uint8_t *cur_c = nullptr; int cur_wc = 0, cur_hc = 0, cur_pitch_c = 0; size_t cur_c_cap = 0;      // current picture's U, V planes
   CUtensorMap tmap_cur;      // TMA descriptor of the current picture: box = one 16x16 macroblock
   int ref_list[JMB_MAX_REFS]; int nref = 0;
   jmb_me_config me;

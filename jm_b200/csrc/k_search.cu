@@ -18,7 +18,7 @@
 //  Both clamps are "displacement clamps": the block(s) are read at D = clamp(d, Dlo, Dhi) per axis,
 //  so a thread that owns displacement D serves every candidate d that clamps onto it.
 //  JM's early terminations only replace a losing cost by min_mcost, so complete sums decide alike.
-#include "jmb_internal.h"
+#include "jmb_dist_dev.cuh"
 
 namespace {
 
@@ -629,9 +629,8 @@ k_mb_surfaces(const __grid_constant__ TMaps tm, int ref, int mbx, int mby, int x
 #pragma unroll
     for (int s = 0; s < 4; s++) {
       const int r = band * SF_BH + rg * 4 + s;
-      if (rg * 4 + s < bh)
-#pragma unroll
-        for (int b = 0; b < 16; b++) out[((size_t)b * nrow + r) * SF_PITCH + ic] = (unsigned short)acc[s][b];
+      if (rg * 4 + s < bh)      // the 41 partition SADs of this displacement (update_full_search_large_blocks), one surface per partition
+        for_each_partition(acc[s], [&](int p, unsigned v) { out[((size_t)p * nrow + r) * SF_PITCH + ic] = (unsigned short)v; });
     }
   }
 }
@@ -639,64 +638,102 @@ k_mb_surfaces(const __grid_constant__ TMaps tm, int ref, int mbx, int mby, int x
 struct SurfView { const unsigned short *p; int x0, y0, ncol, nrow; };      // surfaces of displacements [x0, x0+ncol) x [y0, y0+nrow)
 
 constexpr int AM_NT = 256;
+__constant__ signed char c_sp9[9][2] = {{0,0},{0,-1},{0,1},{-1,-1},{1,-1},{-1,0},{1,0},{-1,1},{1,1}};      // spiral_search[0..8], mv_search.c:410-442
+
+// One partition's search in ONE launch: arg-min over its resident SAD surface, then -- JMB_REQ_SUBPEL -- the half- /
+// quarter-pel refinement of sub_pel_motion_estimation (me_fullsearch.c:186-289, as k_subpel_refine does for whole pictures),
+// answer and completion flag written straight into host-mapped memory.
 __global__ void __launch_bounds__(AM_NT)
-k_mb_argmin(jmb_me_req r, SurfView sv, int w, int h, int R, int max_mvd_m1, jmb_me_req *__restrict__ req_out, jmb_me_res *__restrict__ res,
-            volatile int *flag, int seq) {
+k_mb_search(jmb_me_req r, int slot, SurfView sv, const uint8_t *__restrict__ cur, int cur_pitch, RefView rv, int w, int h, int R, int max_mvd_m1,
+            jmb_me_config me, jmb_me_res *__restrict__ mailbox, volatile int *flag, int seq) {
   __shared__ unsigned long long wbest[AM_NT / 32];
+  __shared__ int sums[9];
+  __shared__ int s_mvx, s_mvy;
+  __shared__ long long s_min, s_icost;
   const int tid = threadIdx.x;
-  const PartGeom *pg = nullptr;
-  // partition geometry from the request (validated on the host)
-  const int bx4 = (r.pos_x & 15) >> 2, by4 = (r.pos_y & 15) >> 2;
-  const int w4 = (r.blocktype <= 2) ? 4 : (r.blocktype <= 5 ? 2 : 1);
-  const int h4 = (r.blocktype == 1 || r.blocktype == 3) ? 4 : ((r.blocktype == 2 || r.blocktype == 4 || r.blocktype == 6) ? 2 : 1);
-  (void)pg;
-  const bool ffs = r.mode == JMB_SEARCH_FAST_FULL;
-  const int ox = ffs ? (r.pos_x & ~15) : r.pos_x, oy = ffs ? (r.pos_y & ~15) : r.pos_y;      // origin the clamp applies to
-  const int dlo_x = -JMB_PAD_X - ox, dhi_x = (w + JMB_PAD_X - 1 - 16) - ox, dlo_y = -JMB_PAD_Y - oy, dhi_y = (h + JMB_PAD_Y - 1 - 16) - oy;
-  const int cx = r.center_x >> 2, cy = r.center_y >> 2, px = r.pred_x, py = r.pred_y, lam = r.lambda[0];
-  const int side = 2 * R + 1;
-  unsigned long long best = (unsigned long long)r.min_mcost << IDX_BITS;
-  for (int i = tid; i < side * side; i += AM_NT) {
-    const int dyi = i / side, dxi = i - dyi * side;
-    const int dx = cx - R + dxi, dy = cy - R + dyi;                  // the candidate (integer pels)
-    const int mx = 4 * dx - px, my = 4 * dy - py;
-    if (ffs && max(abs(mx), abs(my)) >= max_mvd_m1) continue;       // me_fullfast.c:671
-    const int Dx = jmb_clip(dlo_x, dhi_x, dx) - sv.x0, Dy = jmb_clip(dlo_y, dhi_y, dy) - sv.y0;   // where the block(s) are read (UMVLine4X)
-    unsigned sad = 0;
-    for (int y = 0; y < h4; y++)
-      for (int x = 0; x < w4; x++)
-        sad += sv.p[((size_t)((by4 + y) * 4 + bx4 + x) * sv.nrow + Dy) * SF_PITCH + Dx];
-    const unsigned long long cost = ((unsigned long long)sad << 5) + (unsigned long long)((long long)lam * (jmb_mvbits(mx) + jmb_mvbits(my)));
-    const unsigned long long k = (cost << IDX_BITS) | (unsigned)jmb_spiral_index(dx - cx, dy - cy);
-    best = min(best, k);
-  }
+  const long long DISTBLK_MAX = (long long)0x7fffffff << 5;
+  if (!(r.flags & JMB_REQ_SKIP_INT)) {
+    const bool ffs = r.mode == JMB_SEARCH_FAST_FULL;
+    const int ox = ffs ? (r.pos_x & ~15) : r.pos_x, oy = ffs ? (r.pos_y & ~15) : r.pos_y;      // origin the clamp applies to
+    const int dlo_x = -JMB_PAD_X - ox, dhi_x = (w + JMB_PAD_X - 1 - 16) - ox, dlo_y = -JMB_PAD_Y - oy, dhi_y = (h + JMB_PAD_Y - 1 - 16) - oy;
+    const int cx = r.center_x >> 2, cy = r.center_y >> 2, px = r.pred_x, py = r.pred_y, lam = r.lambda[0];
+    const int side = 2 * R + 1;
+    const unsigned short *surf = sv.p + (size_t)slot * sv.nrow * SF_PITCH;
+    unsigned long long best = (unsigned long long)r.min_mcost << IDX_BITS;
+    for (int i = tid; i < side * side; i += AM_NT) {
+      const int dyi = i / side, dxi = i - dyi * side;
+      const int dx = cx - R + dxi, dy = cy - R + dyi;                  // the candidate (integer pels)
+      const int mx = 4 * dx - px, my = 4 * dy - py;
+      if (ffs && max(abs(mx), abs(my)) >= max_mvd_m1) continue;       // me_fullfast.c:671
+      const int Dx = jmb_clip(dlo_x, dhi_x, dx) - sv.x0, Dy = jmb_clip(dlo_y, dhi_y, dy) - sv.y0;   // where the block is read (UMVLine4X)
+      const unsigned sad = surf[(size_t)Dy * SF_PITCH + Dx];
+      const unsigned long long cost = ((unsigned long long)sad << 5) + (unsigned long long)((long long)lam * (jmb_mvbits(mx) + jmb_mvbits(my)));
+      best = min(best, (cost << IDX_BITS) | (unsigned)jmb_spiral_index(dx - cx, dy - cy));
+    }
 #pragma unroll
-  for (int sh = 16; sh; sh >>= 1) {
-    const unsigned long long o = ((unsigned long long)__shfl_xor_sync(0xffffffffu, (unsigned)(best >> 32), sh) << 32) | __shfl_xor_sync(0xffffffffu, (unsigned)best, sh);
-    best = min(best, o);
-  }
-  if ((tid & 31) == 0) wbest[tid >> 5] = best;
+    for (int sh = 16; sh; sh >>= 1) {
+      const unsigned long long o = ((unsigned long long)__shfl_xor_sync(0xffffffffu, (unsigned)(best >> 32), sh) << 32) | __shfl_xor_sync(0xffffffffu, (unsigned)best, sh);
+      best = min(best, o);
+    }
+    if ((tid & 31) == 0) wbest[tid >> 5] = best;
+    __syncthreads();
+    if (tid == 0) {
+      for (int i = 1; i < AM_NT / 32; i++) best = min(best, wbest[i]);
+      int dx = 0, dy = 0;
+      if (best != ((unsigned long long)r.min_mcost << IDX_BITS)) spiral_xy((int)(best & ((1u << IDX_BITS) - 1)), &dx, &dy);
+      s_mvx = 4 * (cx + dx); s_mvy = 4 * (cy + dy);
+      s_icost = (long long)(best >> IDX_BITS);
+      s_min = me.start_hp ? s_icost : DISTBLK_MAX;                    // BlockMotionSearch, mv_search.c:971-974
+    }
+  } else if (tid == 0) { s_mvx = r.center_x; s_mvy = r.center_y; s_icost = s_min = r.min_mcost; }
   __syncthreads();
+  const int imx = s_mvx, imy = s_mvy;
+  if (r.flags & JMB_REQ_SUBPEL) {
+#pragma unroll 1
+    for (int stage = 0; stage < 2; stage++) {
+      const int metric = me.metric[1 + stage], step = stage ? 1 : 2;
+      const int pos0 = stage ? me.start_qp : me.start_hp;
+      const int pos1 = stage ? me.search_pos4 : (!me.start_hp ? max(1, me.search_pos2) : me.search_pos2);
+      const int nn = (metric == JMB_SATD && (r.flags & JMB_REQ_TEST8X8)) ? 8 : 4;
+      const int nsx = c_bsx[r.blocktype] / nn, nsub = nsx * (c_bsy[r.blocktype] / nn);
+      if (tid < 9) sums[tid] = 0;
+      __syncthreads();
+      const int mvx = s_mvx, mvy = s_mvy, ncand = pos1 - pos0;
+      for (int it = tid; it < ncand * nsub; it += AM_NT) {
+        const int c = it / nsub, sb = it - c * nsub, sbx = sb % nsx, sby = sb / nsx, pos = pos0 + c;
+        SrcBlk src;
+        load_src(src, cur, cur_pitch, r.pos_x + sbx * nn, r.pos_y + sby * nn, nn);
+        atomicAdd(&sums[pos], subblock_dist(rv, src, (r.pos_x << 2) + mvx + step * c_sp9[pos][0], (r.pos_y << 2) + mvy + step * c_sp9[pos][1], sbx, sby, nn, metric));
+      }
+      __syncthreads();
+      if (tid == 0) {      // JM's sequential strict-'<' selection (me_fullsearch.c:221-289)
+        long long mn = s_min;
+        if (stage == 1 && !me.start_qp) mn = DISTBLK_MAX;
+        const int lam = r.lambda[1 + stage];
+        int best = 0;
+        for (int pos = pos0; pos < pos1; pos++) {
+          const int cxq = mvx + step * c_sp9[pos][0], cyq = mvy + step * c_sp9[pos][1];
+          long long mc = (long long)lam * (jmb_mvbits(cxq - r.pred_x) + jmb_mvbits(cyq - r.pred_y));
+          if (mc >= mn) continue;
+          mc += (long long)sums[pos] << 5;
+          if (mc < mn) { mn = mc; best = pos; }
+        }
+        s_min = mn; s_mvx = mvx + step * c_sp9[best][0]; s_mvy = mvy + step * c_sp9[best][1];
+      }
+      __syncthreads();
+    }
+  }
   if (tid == 0) {
-    for (int i = 1; i < AM_NT / 32; i++) best = min(best, wbest[i]);
-    int dx = 0, dy = 0;
-    if (best != ((unsigned long long)r.min_mcost << IDX_BITS)) spiral_xy((int)(best & ((1u << IDX_BITS) - 1)), &dx, &dy);
     jmb_me_res o;
-    o.imv_x = o.mv_x = (int16_t)(4 * (cx + dx)); o.imv_y = o.mv_y = (int16_t)(4 * (cy + dy));
-    o.icost = o.cost = (long long)(best >> IDX_BITS);
-    *res = o;
-    *req_out = r;                     // the refinement kernel that may follow reads the request from device memory
-    if (flag) { __threadfence_system(); *flag = seq; }
+    o.imv_x = (int16_t)imx; o.imv_y = (int16_t)imy; o.icost = s_icost;
+    if (r.flags & JMB_REQ_SUBPEL) { o.mv_x = (int16_t)s_mvx; o.mv_y = (int16_t)s_mvy; o.cost = s_min; }
+    else { o.mv_x = o.imv_x; o.mv_y = o.imv_y; o.cost = s_icost; }
+    *mailbox = o;
+    __threadfence_system();
+    *flag = seq;
   }
 }
 
-// one request handed over by value (sub-pel-only calls of the drop-in path) + the completion flag of the mailbox
-__global__ void k_stage_req(jmb_me_req r, jmb_me_req *__restrict__ out) { *out = r; }
-__global__ void k_post_flag(const jmb_me_res *__restrict__ src, jmb_me_res *__restrict__ mailbox, volatile int *flag, int seq) {
-  *mailbox = *src;
-  __threadfence_system();
-  *flag = seq;
-}
 
 }  // namespace
 
@@ -941,7 +978,7 @@ int jmb_mb_surfaces(jmb_ctx *ctx, int ref, int mb_x, int mb_y, int center_x, int
   JMB_CUDA(ctx, cudaSetDevice(ctx->device));
   jmb_ctx::Surf &sf = ctx->surf[ref];
   const int n = 2 * radius + 1;
-  const size_t bytes = (size_t)16 * n * SF_PITCH * sizeof(unsigned short);
+  const size_t bytes = (size_t)NPART * n * SF_PITCH * sizeof(unsigned short);
   int rc = jmb_reserve_dev(ctx, &sf.buf, &sf.cap, bytes); if (rc) return rc;
   sf.valid = true; sf.mb_x = mb_x; sf.mb_y = mb_y; sf.x0 = (center_x >> 2) - radius; sf.y0 = (center_y >> 2) - radius; sf.n = n;
   sf.pic_serial = ctx->pic_serial;
@@ -961,7 +998,6 @@ static int mailbox_init(jmb_ctx *ctx) {
   JMB_CUDA(ctx, cudaHostAlloc(&ctx->mbox, 256, cudaHostAllocMapped));
   memset(ctx->mbox, 0, 256);
   JMB_CUDA(ctx, cudaHostGetDevicePointer(&ctx->d_mbox, ctx->mbox, 0));
-  JMB_CUDA(ctx, cudaMalloc(&ctx->d_one, sizeof(jmb_me_req) + sizeof(jmb_me_res) + 64));
   return 0;
 }
 
@@ -982,17 +1018,18 @@ int jmb_mb_search(jmb_ctx *ctx, const jmb_me_req *req, jmb_me_res *res) {
   if (!req || !res) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_mb_search: NULL argument");
   if (!ctx->cur || ctx->nref == 0) return jmb_fail(ctx, JMB_ERR_STATE, "jmb_mb_search: call jmb_pic_begin first");
   int rc = validate_req(ctx, *req, 0); if (rc) return rc;
-  const bool skip_int = (req->flags & JMB_REQ_SKIP_INT) != 0, subpel = (req->flags & JMB_REQ_SUBPEL) != 0;
+  const bool skip_int = (req->flags & JMB_REQ_SKIP_INT) != 0;
   if (!skip_int && ctx->me.metric[0] != JMB_SAD) return jmb_fail(ctx, JMB_ERR_UNSUPPORTED, "jmb_mb_search: the surfaces are SAD surfaces (MEDistortionFPel = SAD)");
+  if ((req->flags & JMB_REQ_TEST8X8) && req->blocktype > 4) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_mb_search: JMB_REQ_TEST8X8 needs blocktype <= 4");
   JMB_CUDA(ctx, cudaSetDevice(ctx->device));
   rc = mailbox_init(ctx); if (rc) return rc;
-  jmb_me_req *d_req = (jmb_me_req *)ctx->d_one;
-  jmb_me_res *d_res = (jmb_me_res *)((char *)ctx->d_one + 64), *mb_res = (jmb_me_res *)ctx->d_mbox;
+  jmb_me_res *mb_res = (jmb_me_res *)ctx->d_mbox;
   volatile int *d_flag = (volatile int *)((char *)ctx->d_mbox + 128);
   const int seq = ++ctx->mbox_seq;
+  const int R = ctx->me.search_range, w = ctx->cur_w, h = ctx->cur_h;
+  SurfView sv{nullptr, 0, 0, 0, 0};
   if (!skip_int) {
     const jmb_ctx::Surf &sf = ctx->surf[req->ref];
-    const int R = ctx->me.search_range, w = ctx->cur_w, h = ctx->cur_h;
     const bool ffs = req->mode == JMB_SEARCH_FAST_FULL;
     if (!sf.valid || sf.pic_serial != ctx->pic_serial || sf.mb_x != (req->pos_x & ~15) || sf.mb_y != (req->pos_y & ~15))
       return jmb_fail(ctx, JMB_ERR_STATE, "jmb_mb_search: no surfaces resident for macroblock (%d,%d) reference %d", req->pos_x & ~15, req->pos_y & ~15, req->ref);
@@ -1004,26 +1041,16 @@ int jmb_mb_search(jmb_ctx *ctx, const jmb_me_req *req, jmb_me_res *res) {
     const int lx = clip(dlo_x, dhi_x, cx - R), hx = clip(dlo_x, dhi_x, cx + R), ly = clip(dlo_y, dhi_y, cy - R), hy = clip(dlo_y, dhi_y, cy + R);
     if (lx < sf.x0 || hx >= sf.x0 + sf.n || ly < sf.y0 || hy >= sf.y0 + sf.n)
       return jmb_fail(ctx, JMB_ERR_STATE, "jmb_mb_search: window of the request (centre %d,%d) is not covered by the resident surfaces", req->center_x, req->center_y);
-    SurfView sv{(const unsigned short *)sf.buf, sf.x0, sf.y0, sf.n, sf.n};
-    jmb_time_begin(ctx, JMB_K_ARGMIN);
-    k_mb_argmin<<<1, AM_NT, 0, ctx->stream>>>(*req, sv, w, h, R, ctx->me.max_mvd - 1, d_req, subpel ? d_res : mb_res, subpel ? nullptr : d_flag, seq);
-    jmb_time_end(ctx, JMB_K_ARGMIN);
-    JMB_LAUNCH_CHECK(ctx);
-  } else {
-    k_stage_req<<<1, 1, 0, ctx->stream>>>(*req, d_req);
-    JMB_LAUNCH_CHECK(ctx);
+    sv = SurfView{(const unsigned short *)sf.buf, sf.x0, sf.y0, sf.n, sf.n};
   }
-  if (subpel) {
-    const uint8_t *const *d_tab = nullptr;
-    if (!ctx->reftab_serial || ctx->reftab_serial != ctx->pic_serial) { rc = upload_ref_table(ctx, &d_tab, 0); if (rc) return rc; ctx->reftab_serial = ctx->pic_serial; }
-    d_tab = (const uint8_t *const *)ctx->d_reftab;
-    rc = jmb_launch_refine(ctx, d_req, d_res, 1, d_tab); if (rc) return rc;
-    k_post_flag<<<1, 1, 0, ctx->stream>>>(d_res, mb_res, d_flag, seq);
-    JMB_LAUNCH_CHECK(ctx);
-  }
+  const jmb_ref &rr = ctx->refs[ctx->ref_list[req->ref]];
+  RefView rv{rr.planes, rr.plane_bytes, rr.pitch, rr.w, rr.h};
+  jmb_time_begin(ctx, JMB_K_ARGMIN);
+  k_mb_search<<<1, AM_NT, 0, ctx->stream>>>(*req, part_slot(*req), sv, ctx->cur, ctx->cur_pitch, rv, w, h, R, ctx->me.max_mvd - 1, ctx->me, mb_res, d_flag, seq);
+  jmb_time_end(ctx, JMB_K_ARGMIN);
+  JMB_LAUNCH_CHECK(ctx);
   rc = mailbox_wait(ctx, seq); if (rc) return rc;
   *res = *(const jmb_me_res *)ctx->mbox;
-  if (ctx->h_err && (++ctx->mb_calls & 1023) == 0) return jmb_check_device_errors(ctx);      // device-side validation words, now and then
   return JMB_OK;
 }
 

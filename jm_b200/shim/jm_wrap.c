@@ -78,6 +78,7 @@ int     __real_quant_8x8_around(Macroblock *, int **, struct quant_methods *);
 int     __real_quant_8x8cavlc_normal(Macroblock *, int **, struct quant_methods *, int ***);
 int     __real_quant_8x8cavlc_around(Macroblock *, int **, struct quant_methods *, int ***);
 void    __real_luma_residual_coding(Macroblock *currMB);
+void    __real_chroma_residual_coding(Macroblock *currMB);
 distblk __real_computeSADWP(StorablePicture *, MEBlock *, distblk, MotionVector *);
 distblk __real_computeSSEWP(StorablePicture *, MEBlock *, distblk, MotionVector *);
 distblk __real_computeSATDWP(StorablePicture *, MEBlock *, distblk, MotionVector *);
@@ -156,10 +157,11 @@ static void unsupported(const char *what)
   fatal(701);
 }
 
+static unsigned long chroma_verified;
 static void report(void)
 {
   if (S.init == 1 && S.verify)
-    fprintf(stderr, "[jmb shim] luma_residual_coding verified on %lu macroblock codings (levels, cbp, cbp_blk, reconstruction)\n", S.verified);
+    fprintf(stderr, "[jmb shim] luma_residual_coding verified on %lu macroblock codings (levels, cbp, cbp_blk, reconstruction); chroma_residual_coding verified on %lu\n", S.verified, chroma_verified);
   if (S.init == 1 && getenv("JMB_SHIM_VERBOSE"))
     fprintf(stderr, "[jmb shim] planes %lu  full %lu  fastfull %lu  subpel %lu  fwd4 %lu  fwd8 %lu  quant4 %lu  quant8 %lu  dist %lu  kernel launches %llu  bipred/weighted distortions %lu  subpel served by the integer search's call %lu  surface builds %lu\n",
             S.calls[0], S.calls[1], S.calls[2], S.calls[3], S.calls[4], S.calls[5], S.calls[6], S.calls[7], S.calls[8],
@@ -220,6 +222,12 @@ static int put_ref(VideoParameters *p_Vid, StorablePicture *s)
     int stride = (int)(img[1] - img[0]);
     int rc = jmb_ref_put(S.ctx, slot, (const uint16_t *)&img[0][0], s->size_x, s->size_y, stride, p_Vid->bitdepth_luma, JMB_HOST);
     if (rc) jmb_die("jmb_ref_put", rc);
+    if (S.verify && (p_Vid->yuv_format == YUV420 || p_Vid->yuv_format == YUV422) && s->imgUV && p_Vid->bitdepth_chroma == 8)
+    { /* the chroma path is checked differentially (JMB_SHIM_VERIFY): it needs the reference's chroma planes too */
+      rc = jmb_ref_put_chroma(S.ctx, slot, &s->imgUV[0][0][0], &s->imgUV[1][0][0], (int)sizeof(imgpel), s->size_x_cr, s->size_y_cr,
+                              (int)(s->imgUV[0][1] - s->imgUV[0][0]), JMB_HOST);
+      if (rc) jmb_die("jmb_ref_put_chroma", rc);
+    }
   }
   S.slot_pic[slot] = s;
   S.slot_stamp[slot] = ++S.stamp;
@@ -282,6 +290,12 @@ static int ref_index_of(VideoParameters *p_Vid, Slice *currSlice, MEBlock *mv_bl
     S.pic_valid = 1;
     S.pic_count++;
     S.spec.valid = 0;
+    if (S.verify && (p_Vid->yuv_format == YUV420 || p_Vid->yuv_format == YUV422) && p_Vid->bitdepth_chroma == 8)
+    {
+      imgpel **cu = p_Vid->pImgOrg[1], **cv = p_Vid->pImgOrg[2];
+      rc = jmb_pic_chroma(S.ctx, &cu[0][0], &cv[0][0], (int)sizeof(imgpel), p_Vid->width_cr, p_Vid->height_cr, (int)(cu[1] - cu[0]), JMB_HOST);
+      if (rc) jmb_die("jmb_pic_chroma", rc);
+    }
   }
   for (i = 0; i < S.nlist; i++)
     if (S.list[i] == slot) return i;
@@ -1331,6 +1345,99 @@ void __wrap_luma_residual_coding(Macroblock *currMB)
     }
   }
   S.verified++;
+}
+
+
+/* ---- differential check of the device chroma path against JM itself (JMB_SHIM_VERIFY=1) ------------------------------------
+ * chroma_residual_coding (lencod/src/macroblock.c:1439) runs as usual; afterwards the same inter macroblock's two chroma
+ * components are predicted and residual-coded by jmb_chroma_residual_coding from JM's own state and the DC / AC levels, the
+ * chroma bits of cbp_blk, the chroma cbp and the reconstruction must equal what JM left.  Any difference stops the encoder. */
+static void chroma_mismatch(Macroblock *currMB, const char *what, int uv, int a, int b)
+{
+  snprintf(errortext, ET_SIZE, "libjmb200 shim: VERIFY chroma_residual_coding: macroblock %d (type %d) component %d: %s differs (JM %d, device %d)",
+           currMB->mbAddrX, currMB->mb_type, uv, what, a, b);
+  fatal(705);
+}
+
+void __wrap_chroma_residual_coding(Macroblock *currMB)
+{
+  Slice *currSlice = currMB->p_Slice;
+  VideoParameters *p_Vid = currMB->p_Vid;
+  QuantParameters *p_Quant = p_Vid->p_Quant;
+  jmb_mb_pred pred;
+  jmb_chroma_desc d;
+  static int16_t dc[2][8], ac[2][8][15];
+  static uint8_t recon[2][16][8];
+  uint32_t cb[2], cc[2];
+  int k, bx, by, uv, i, j, rc, yuv = p_Vid->yuv_format, nb, hmb, cbp_before = currMB->cbp;
+
+  __real_chroma_residual_coding(currMB);
+  if (S.init != 1 || !S.verify || (S.off & FAM_TQ)) return;
+  if (currSlice->slice_type != P_SLICE || p_Vid->AdaptiveRounding || p_Vid->structure != FRAME || currSlice->mb_aff_frame_flag) return;
+  if (!(currMB->mb_type == P16x16 || currMB->mb_type == P16x8 || currMB->mb_type == P8x16 || currMB->mb_type == P8x8)) return;
+  if (currSlice->weighted_prediction || currSlice->NoResidueDirect || p_Vid->bitdepth_chroma != 8 || (yuv != YUV420 && yuv != YUV422)) return;
+  if (currMB->is_field_mode) return;
+  nb = (yuv == YUV420) ? 4 : 8; hmb = 2 * nb;
+  memset(&pred, 0, sizeof(pred));
+  for (k = 0; k < 4; k++)
+  {
+    PicMotionParams *m = &p_Vid->enc_picture->mv_info[currMB->block_y + 2 * (k >> 1)][currMB->block_x + 2 * (k & 1)];
+    int mode = currMB->b8x8[k].mode, ref = m->ref_idx[LIST_0];
+    MEBlock probe;
+    if (currMB->b8x8[k].pdir != 0 || mode < 1 || mode > 7 || ref < 0) return;
+    memset(&probe, 0, sizeof(probe));
+    pred.b8mode[k] = (uint8_t)mode;
+    pred.ref[k] = (uint8_t)ref_index_of(p_Vid, currSlice, &probe, currSlice->listX[LIST_0 + currMB->list_offset][ref]);
+    for (by = 2 * (k >> 1); by < 2 * (k >> 1) + 2; by++)
+      for (bx = 2 * (k & 1); bx < 2 * (k & 1) + 2; bx++)
+      {
+        MotionVector *mv = &currSlice->all_mv[LIST_0][ref][mode][by][bx];
+        pred.mv[by * 4 + bx][0] = mv->mv_x;
+        pred.mv[by * 4 + bx][1] = mv->mv_y;
+      }
+  }
+  memset(&d, 0, sizeof(d));
+  d.yuv_format = yuv;
+  d.is_cavlc = (currSlice->symbol_mode == CAVLC);
+  for (uv = 0; uv < 2; uv++)
+  {
+    int qp = currMB->qpc[uv] + currSlice->bitdepth_chroma_qp_scale, qp_dc = qp + (yuv == YUV422 ? 3 : 0);
+    LevelQuantParams **qa = p_Quant->q_params_4x4[uv + 1][0][qp], **qd = p_Quant->q_params_4x4[uv + 1][0][qp_dc];
+    d.qp_ac[uv] = qp; d.qp_dc[uv] = qp_dc;
+    for (j = 0; j < 4; j++)
+      for (i = 0; i < 4; i++)
+      {
+        d.params_ac[uv][j * 4 + i][0] = qa[j][i].OffsetComp; d.params_ac[uv][j * 4 + i][1] = qa[j][i].ScaleComp; d.params_ac[uv][j * 4 + i][2] = qa[j][i].InvScaleComp;
+      }
+    d.params_dc[uv][0] = qd[0][0].OffsetComp; d.params_dc[uv][1] = qd[0][0].ScaleComp; d.params_dc[uv][2] = qd[0][0].InvScaleComp;
+  }
+  memcpy(d.c_cost, V_COST4[currSlice->disthres], 16);
+  rc = jmb_chroma_residual_coding(S.ctx, &pred, 0, currMB->mbAddrX, 1, &d, &dc[0][0], &ac[0][0][0], cb, cc, &recon[0][0][0], JMB_HOST);
+  if (rc) jmb_die("jmb_chroma_residual_coding", rc);
+
+  if ((int)(cc[0] > cc[1] ? cc[0] : cc[1]) != ((currMB->cbp - cbp_before) >> 4)) chroma_mismatch(currMB, "chroma cbp", 0, (currMB->cbp - cbp_before) >> 4, (int)(cc[0] > cc[1] ? cc[0] : cc[1]));
+  for (uv = 0; uv < 2; uv++)
+  {
+    int uv_scale = uv * (p_Vid->num_blk8x8_uv >> 1), e, pos, b;
+    int16_t want[16];
+    int jm_bits = (int)((currMB->cbp_blk >> (16 + uv * nb)) & ((1 << nb) - 1));
+    if (jm_bits != (int)cb[uv]) chroma_mismatch(currMB, "cbp_blk chroma bits", uv, jm_bits, (int)cb[uv]);
+    for (j = 0; j < hmb; j++)
+      for (i = 0; i < 8; i++)
+        if (p_Vid->enc_picture->imgUV[uv][currMB->pix_c_y + j][currMB->pix_c_x + i] != recon[uv][j][i])
+          chroma_mismatch(currMB, "reconstruction", uv, p_Vid->enc_picture->imgUV[uv][currMB->pix_c_y + j][currMB->pix_c_x + i], recon[uv][j][i]);
+    memset(want, 0, sizeof(want));
+    for (e = 0, pos = 0; e < nb && currSlice->cofDC[uv + 1][0][e] != 0; e++) { pos += currSlice->cofDC[uv + 1][1][e]; want[pos++] = (int16_t)currSlice->cofDC[uv + 1][0][e]; }
+    for (e = 0; e < nb; e++) if (want[e] != dc[uv][e]) chroma_mismatch(currMB, "a DC level", uv, want[e], dc[uv][e]);
+    for (b = 0; b < nb; b++)
+    {
+      int *ACL = currSlice->cofAC[4 + (b >> 2) + uv_scale][b & 3][0], *ACR = currSlice->cofAC[4 + (b >> 2) + uv_scale][b & 3][1];
+      memset(want, 0, sizeof(want));
+      for (e = 0, pos = 0; e < 15 && ACL[e] != 0; e++) { pos += ACR[e]; want[pos++] = (int16_t)ACL[e]; }
+      for (e = 0; e < 15; e++) if (want[e] != ac[uv][b][e]) chroma_mismatch(currMB, "an AC level", uv, want[e], ac[uv][b][e]);
+    }
+  }
+  chroma_verified++;
 }
 
 /* ---- transforms (lcommon/src/transform.c:20, :353) ---------------------------------------------------- */

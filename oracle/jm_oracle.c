@@ -860,3 +860,114 @@ void jmo_mc_tq_modes_mb(const jmo_ref *r, const uint16_t *cur, int cur_stride, i
     }
   }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Chroma of an inter macroblock: motion-compensated prediction and residual coding.
+ *  - prediction: OneComponentChromaPrediction4x4_regenerate (lencod/src/mc_prediction.c:292-352): every chroma sample takes the
+ *    motion vector of the luma 4x4 block it lies under; bilinear interpolation at 1/8 (1/4 vertically for 4:2:2) sample
+ *    precision, source coordinates clamped to the picture; C integer division (toward zero) as in JM.
+ *  - residual coding: residual_transform_quant_chroma_4x4 (lencod/src/block.c:954-1202) for intra = 0, frame scan, no adaptive
+ *    rounding: forward4x4 of the 4 (4:2:0) or 8 (4:2:2) blocks, DC through hadamard2x2 + quant_dc2x2_normal or hadamard4x2 +
+ *    quant_dc4x2_normal at qp + 3 (SCAN_YUV420 / SCAN_YUV422, block.c:78-94), quant_ac4x4_normal per block with one running
+ *    coeff_cost per component, the _CHROMA_COEFF_COST_ (4) threshold, cbp_blk bits (cbp_blk_chroma, block.c:158), inverse4x4 and
+ *    sample_reconstruct.  The DC / AC quantisers and Hadamards are the pinned list quantiser / jmo_hadamard of this file.
+ * ---------------------------------------------------------------------------------------- */
+void jmo_chroma_pred(const uint8_t *ref_c, int wc, int hc, int stride, int yuv, int mb_cx, int mb_cy, const int16_t *mv16 /* [16][2] luma 4x4 mvs */,
+                     uint8_t *pred /* [hc_mb][8] */)
+{
+  const int hmb = (yuv == 1) ? 8 : 16, f1x = 8, f1y = 64 / hmb, f2x = f1x - 1, f2y = f1y - 1, f3 = f1x * f1y, f4 = f3 >> 1;
+  const int ydiv = hmb >> 2;
+  for (int j = 0; j < hmb; j++)
+    for (int i = 0; i < 8; i++) {
+      const int16_t *mv = mv16 + 2 * ((j / ydiv) * 4 + i / 2);
+      const int ii = (i + mb_cx) * f1x + mv[0], jj = (j + mb_cy) * f1y + mv[1];
+      const int ii0 = iclip(0, wc - 1, ii / f1x), jj0 = iclip(0, hc - 1, jj / f1y);
+      const int ii1 = iclip(0, wc - 1, (ii + f2x) / f1x), jj1 = iclip(0, hc - 1, (jj + f2y) / f1y);
+      const int if1 = ii & f2x, if0 = f1x - if1, jf1 = jj & f2y, jf0 = f1y - jf1;
+      pred[j * 8 + i] = (uint8_t)((if0 * jf0 * ref_c[jj0 * stride + ii0] + if1 * jf0 * ref_c[jj0 * stride + ii1] +
+                                   if0 * jf1 * ref_c[jj1 * stride + ii0] + if1 * jf1 * ref_c[jj1 * stride + ii1] + f4) / f3);
+    }
+}
+
+/* one component of one macroblock.  src / pred [hmb][8]; qp_ac / qp_dc scaled chroma qps; params_ac [16][3] (row-major j*4+i),
+ * params_dc [3]; out: dc_levels[8] and ac_levels[nb][15] dense in scan order, *cbp_bits = the component's bits of cbp_blk
+ * shifted down by 16 + uv * nb (bit b = block b raster, 2 blocks per row), recon [hmb][8]; returns cr_cbp (0, 1, 2). */
+int jmo_chroma_rc(const uint8_t *src, const uint8_t *pred, int yuv, int qp_ac, int qp_dc, const int *params_ac, const int *params_dc,
+                  const uint8_t *c_cost, int is_cavlc, int16_t *dc_levels, int16_t *ac_levels, unsigned *cbp_bits, uint8_t *recon)
+{
+  static const uint8_t scan4[16][2] = {{0,0},{1,0},{0,1},{0,2},{1,1},{2,0},{3,0},{2,1},{1,2},{0,3},{1,3},{2,2},{3,1},{3,2},{2,3},{3,3}};
+  static const uint8_t scan422[8][2] = {{0,0},{0,1},{1,0},{0,2},{0,3},{1,1},{1,2},{1,3}};
+  const int hmb = (yuv == 1) ? 8 : 16, nb = hmb / 2;
+  int rres[16][8], blk[16], lv[17], rn[17], fa[16], cost = 0, dczero, nonzero[8] = {0}, any_ac = 0, cr_cbp = 0, cr_tmp = 0;
+  memset(dc_levels, 0, 8 * sizeof(int16_t)); memset(ac_levels, 0, (size_t)nb * 15 * sizeof(int16_t));
+  *cbp_bits = 0;
+  for (int b = 0; b < nb; b++) {      /* integer transform (block.c:1011-1027) */
+    const int n1 = (b & 1) * 4, n2 = (b >> 1) * 4;
+    for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) blk[y * 4 + x] = (int)src[(n2 + y) * 8 + n1 + x] - (int)pred[(n2 + y) * 8 + n1 + x];
+    jmo_forward4x4(blk);
+    for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) rres[n2 + y][n1 + x] = blk[y * 4 + x];
+  }
+  if (yuv == 1) {                     /* CHROMA DC YUV420 (:1029-1054) */
+    int m1[4] = {rres[0][0], rres[0][4], rres[4][0], rres[4][4]}, pdc[4 * 3];
+    jmo_hadamard(4, m1);
+    for (int k = 0; k < 4; k++) { pdc[3 * k] = params_dc[0] << 1; pdc[3 * k + 1] = params_dc[1]; pdc[3 * k + 2] = params_dc[2]; }
+    dczero = jmo_quant_list(4, 15 + qp_dc / 6 + 1, qp_dc / 6, 1, is_cavlc, 0, 0, 0, pdc, c_cost, m1, lv, rn, fa, NULL);
+    for (int i = 0, k = 0; lv[i]; i++) { k += rn[i]; dc_levels[k++] = (int16_t)lv[i]; }
+    jmo_hadamard(5, m1);
+    rres[0][0] = m1[0] >> 5; rres[0][4] = m1[1] >> 5; rres[4][0] = m1[2] >> 5; rres[4][4] = m1[3] >> 5;
+  } else {                            /* CHROMA DC YUV422 (:1055-1092): tblk[x][y] = DC of block (x, y), transposed */
+    int t[8], list[8], pdc[8 * 3], o[8];
+    for (int x = 0; x < 2; x++) for (int y = 0; y < 4; y++) t[x * 4 + y] = rres[y * 4][x * 4];
+    jmo_hadamard(2, t);
+    for (int k = 0; k < 8; k++) { list[k] = t[scan422[k][0] * 4 + scan422[k][1]]; pdc[3 * k] = params_dc[0] << 1; pdc[3 * k + 1] = params_dc[1]; pdc[3 * k + 2] = params_dc[2]; }
+    dczero = jmo_quant_list(8, 15 + qp_dc / 6 + 1, qp_dc / 6, 1, is_cavlc, 0, 0, 0, pdc, c_cost, list, lv, rn, fa, NULL);
+    for (int i = 0, k = 0; lv[i]; i++) { k += rn[i]; dc_levels[k++] = (int16_t)lv[i]; }
+    for (int k = 0; k < 8; k++) t[scan422[k][0] * 4 + scan422[k][1]] = list[k];
+    jmo_hadamard(3, t);               /* out: 4 rows x 2 */
+    for (int k = 0; k < 8; k++) o[k] = t[k];
+    for (int j = 0; j < 4; j++) {
+      rres[j << 2][0] = (o[2 * j] + 32) >> 6;
+      rres[j << 2][4] = (o[2 * j + 1] + 32) >> 6;
+    }
+  }
+  if (dczero) { *cbp_bits = (1u << nb) - 1; cr_cbp = 1; }
+  for (int b = 0; b < nb; b++) {      /* chroma AC (:1094-1132) */
+    const int n1 = (b & 1) * 4, n2 = (b >> 1) * 4;
+    int list[15], pac[15 * 3];
+    for (int k = 1; k < 16; k++) {
+      const int i = scan4[k][0], j = scan4[k][1];
+      list[k - 1] = rres[n2 + j][n1 + i];
+      pac[3 * (k - 1)] = params_ac[3 * (j * 4 + i)]; pac[3 * (k - 1) + 1] = params_ac[3 * (j * 4 + i) + 1]; pac[3 * (k - 1) + 2] = params_ac[3 * (j * 4 + i) + 2];
+    }
+    nonzero[b] = jmo_quant_list(15, 15 + qp_ac / 6, qp_ac / 6, 2, is_cavlc, 1, 0, 0, pac, c_cost, list, lv, rn, fa, &cost);
+    for (int k = 1; k < 16; k++) rres[n2 + scan4[k][1]][n1 + scan4[k][0]] = list[k - 1];
+    for (int i = 0, k = 0; lv[i]; i++) { k += rn[i]; ac_levels[b * 15 + k++] = (int16_t)lv[i]; }
+    if (nonzero[b]) { *cbp_bits |= 1u << b; cr_tmp = 2; any_ac = 1; }
+  }
+  if (any_ac && cost < 4) {           /* _CHROMA_COEFF_COST_ (:1134-1170) */
+    cr_tmp = 0;
+    for (int b = 0; b < nb; b++)
+      if (nonzero[b]) {
+        const int n1 = (b & 1) * 4, n2 = (b >> 1) * 4;
+        nonzero[b] = 0;
+        if (!dczero) *cbp_bits = 0;
+        for (int k = 1; k < 16; k++) rres[n2 + scan4[k][1]][n1 + scan4[k][0]] = 0;
+        memset(ac_levels + b * 15, 0, 15 * sizeof(int16_t));
+      }
+  }
+  if (cr_tmp == 2) cr_cbp = 2;
+  int any = 0;
+  for (int b = 0; b < nb; b++) {      /* inverse transform + reconstruction (:1176-1199) */
+    const int n1 = (b & 1) * 4, n2 = (b >> 1) * 4;
+    if (rres[n2][n1] != 0 || nonzero[b]) {
+      for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) blk[y * 4 + x] = rres[n2 + y][n1 + x];
+      jmo_inverse4x4(blk);
+      for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) rres[n2 + y][n1 + x] = blk[y * 4 + x];
+      any = 1;
+    }
+  }
+  for (int y = 0; y < hmb; y++)
+    for (int x = 0; x < 8; x++)
+      recon[y * 8 + x] = any ? (uint8_t)iclip(0, 255, ((rres[y][x] + 32) >> 6) + pred[y * 8 + x]) : pred[y * 8 + x];
+  return cr_cbp;
+}

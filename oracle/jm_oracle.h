@@ -110,6 +110,9 @@ typedef struct jmo_epzs_res {
 void jmo_epzs(const jmo_ref *r, const uint16_t *cur, int cur_stride, const jmo_epzs_req *q, const int16_t *cands,
               const int *me /* metric_h, metric_q, start_hp, start_qp, search_pos2 */, jmo_epzs_res *o);
 
+void jmo_chroma_pred(const uint8_t *ref_c, int wc, int hc, int stride, int yuv, int mb_cx, int mb_cy, const int16_t *mv16, uint8_t *pred);
+int jmo_chroma_rc(const uint8_t *src, const uint8_t *pred, int yuv, int qp_ac, int qp_dc, const int *params_ac, const int *params_dc,
+                  const uint8_t *c_cost, int is_cavlc, int16_t *dc_levels, int16_t *ac_levels, unsigned *cbp_bits, uint8_t *recon);
 void jmo_epzs_batch(const jmo_ref *r, const uint16_t *cur, int cur_stride, const jmo_epzs_req *reqs, int n, const int16_t *cands,
                     const int *me, jmo_epzs_res *res);
 void jmo_mc_tq_modes_mb(const jmo_ref *r, const uint16_t *cur, int cur_stride, int mb_x, int mb_y, const int16_t *mv41, int n, int qp,

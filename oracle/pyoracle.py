@@ -75,9 +75,27 @@ class Oracle:
                                 _i32p, _i32p, _i32p, _i32p]
 
         L.jmo_epzs.argtypes = [C.c_void_p, _u16p, C.c_int, C.c_void_p, _i16p, _i32p, C.c_void_p]
+        L.jmo_chroma_pred.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i16p, _u8p]
+        L.jmo_chroma_rc.argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_int, _i32p, _i32p, _u8p, C.c_int, _i16p, _i16p, _u32p, _u8p]
         L.jmo_epzs_batch.argtypes = [C.c_void_p, _u16p, C.c_int, C.c_void_p, C.c_int, _i16p, _i32p, C.c_void_p]
         L.jmo_mc_tq_modes_mb.argtypes = [C.c_void_p, _u16p, C.c_int, C.c_int, C.c_int, _i16p, C.c_int, C.c_int, _i32p, _u8p, _u8p, C.c_int,
                                          C.c_uint, _i16p]
+
+    def chroma_pred(self, ref_c, yuv, mb_c, mv16):
+        """ref_c: one chroma plane (uint8); mb_c = (x, y) of the macroblock in chroma samples; mv16: [16][2] luma 4x4 mvs."""
+        ref_c = np.ascontiguousarray(ref_c, np.uint8)
+        hmb = 8 if yuv == 1 else 16
+        pred = np.zeros((hmb, 8), np.uint8)
+        self.L.jmo_chroma_pred(ref_c, ref_c.shape[1], ref_c.shape[0], ref_c.shape[1], yuv, mb_c[0], mb_c[1], np.ascontiguousarray(mv16, np.int16).reshape(-1), pred)
+        return pred
+
+    def chroma_rc(self, src, pred, yuv, qp_ac, qp_dc, params_ac, params_dc, c_cost, is_cavlc):
+        hmb = 8 if yuv == 1 else 16
+        dc = np.zeros(8, np.int16); ac = np.zeros((8, 15), np.int16); bits = np.zeros(1, np.uint32); rec = np.zeros((hmb, 8), np.uint8)
+        cr = self.L.jmo_chroma_rc(np.ascontiguousarray(src, np.uint8), np.ascontiguousarray(pred, np.uint8), yuv, qp_ac, qp_dc,
+                                  np.ascontiguousarray(params_ac, np.int32).reshape(-1), np.ascontiguousarray(params_dc, np.int32).reshape(-1),
+                                  np.ascontiguousarray(c_cost, np.uint8), int(is_cavlc), dc, ac.reshape(-1), bits, rec)
+        return dict(dc=dc, ac=ac, cbp_blk=int(bits[0]), cr_cbp=int(cr), recon=rec)
 
     def epzs_batch(self, r, cur, reqs, cands, me):
         """jmo_epzs over a whole request array in one C call (timed by bench.py's CPU legs)."""

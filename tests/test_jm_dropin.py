@@ -149,7 +149,9 @@ def test_bitstream_identical_to_stock_jm(tmp_path, name):
     counts = dict(zip(line[0].split()[2::2][:9], [int(x) for x in line[0].split()[3::2][:9]]))
     assert counts["planes"] >= max(1, (frames - 1) // (bframes + 1)) and counts["quant4"] + counts["quant8"] > 0, line[0]
     if "EPZSSubPelGrid=1" in CONFIGS[name]:
-        assert counts["full"] > 0 and counts["subpel"] > 0 and counts["dist"] < counts["full"], line[0]      # searches as whole device calls
+        # whole searches as single device calls (EPZS_integer_motion_estimation / EPZS_sub_pel_motion_estimation); JM's
+        # sub-macroblock and bi-predictive EPZS variants still ask for one distortion at a time
+        assert counts["full"] > 0 and counts["subpel"] > 0, line[0]
     elif "SearchMode=3" in CONFIGS[name] or "UseWeightedReferenceME=1" in CONFIGS[name]:
         assert counts["dist"] > 0, line[0]                       # EPZS / weighted-reference ME: distortion oracle
     else:
@@ -183,6 +185,22 @@ def test_device_luma_residual_coding_matches_jm_in_the_live_encoder(tmp_path, na
     line = [l for l in r.stderr.splitlines() if "luma_residual_coding verified on" in l]
     assert line, r.stderr[-400:]
     assert int(line[0].split("verified on")[1].split()[0]) > 100, line[0]
+    assert int(line[0].split("chroma_residual_coding verified on")[1].split()[0]) > 100, line[0]      # 4:2:0 chroma: prediction, 2x2 DC path, AC, thresholds
+
+
+@pytest.mark.gpu
+@needs_bins
+def test_device_chroma_residual_coding_422_matches_jm_in_the_live_encoder(tmp_path):
+    """The same differential pin for 4:2:2 (BASELINE config 4's chroma): hadamard4x2 + quant_dc4x2 at qp + 3, eight AC blocks per
+    component, 1/4-sample vertical chroma motion."""
+    w, h, frames = 96, 80, 3
+    _make_yuv(tmp_path / "input.yuv", w, h, frames, seed=18, fmt420=False)
+    cfg = ["ProfileIDC=122", "YUVFormat=2", "SymbolMode=1", "RDOptimization=1", "Transform8x8Mode=0", "QPISlice=26", "QPPSlice=27",
+           "SearchMode=0", "SearchRange=8", "NumberReferenceFrames=2", "AdaptiveRounding=0", "MEDistortionHPel=2", "MEDistortionQPel=2"]
+    r = _encode(JMB, tmp_path, "v", w, h, frames, cfg, env={"JMB_SHIM_VERIFY": "1"})
+    assert r.returncode == 0, r.stderr[-800:]
+    line = [l for l in r.stderr.splitlines() if "chroma_residual_coding verified on" in l]
+    assert line and int(line[0].split("chroma_residual_coding verified on")[1].split()[0]) > 100, r.stderr[-400:]
 
 
 FIXTURES = os.path.join(ROOT, "oracle", "_ref", "fixtures")

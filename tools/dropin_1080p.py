@@ -37,7 +37,7 @@ def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
     frames = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     out = {}
-    for name, (w, h, modes) in {"1080p": (1920, 1088, ["me"]), "cif": (352, 288, ["me", "full"])}.items():
+    for name, (w, h, modes) in {"1080p": (1920, 1088, ["me"]), "cif": (352, 288, ["me"] + (["full"] if os.environ.get("DROPIN_FULL") else []))}.items():
         with tempfile.TemporaryDirectory() as d:
             T._make_yuv(os.path.join(d, "input.yuv"), w, h, frames, seed=21)
             res = {"frames": frames, "macroblocks_per_frame": (w // 16) * (h // 16), "stock": run(T.REF, d, "ref", w, h, frames, {})}
