@@ -68,6 +68,15 @@ def workload_config(cfg_id, n_gpus):
             "l2": f"rotating over {N_SETS} distinct input sets (> 126 MB in total)", "parallelism": par}
 
 
+def make_chroma_planes(luma, yuv, seed):
+    """Chroma planes with texture that moves with the luma: decimated luma + noise (4:2:0: w/2 x h/2; 4:2:2: w/2 x h)."""
+    rng = np.random.default_rng(seed)
+    ys = 2 if yuv == 1 else 1
+    u = luma[::ys, 0::2].astype(np.int32) // 2 + 60 + rng.integers(-2, 3, (luma.shape[0] // ys, luma.shape[1] // 2))
+    v = luma[::ys, 1::2].astype(np.int32) // 2 + 50 + rng.integers(-2, 3, (luma.shape[0] // ys, luma.shape[1] // 2))
+    return np.clip(u, 0, 255).astype(np.uint8), np.clip(v, 0, 255).astype(np.uint8)
+
+
 def make_shared_candidates(seed, n_mb, n_shared, motion_q=(20, 12)):
     """EPZS: candidate mvs every partition of a macroblock checks = zero mv + neighbour-like motion (true motion + jitter)."""
     rng = np.random.default_rng(seed + 7)
@@ -159,6 +168,11 @@ class Workload:
                                              search_range=SEARCH_RANGE)
         dev = f"cuda:{local}"
         anchor = bool(self.cfg.get("anchor"))
+        self.chroma = self.cfg["chroma"]                       # "422": the 4:2:2 chroma prediction / residual / 4x2 DC path rides along
+        self.yuv = 2 if self.chroma == "422" else 1
+        if self.chroma:
+            self.cdesc = api.chroma_desc(self.yuv, QP, lambda q: T.q_params(q, 0, 4), T.COEFF_COST4x4[0], 0)
+            self.hc = H if self.yuv == 2 else H // 2
         self.sets = []
         for s in range(N_SETS):
             # anchor mode: every rank codes a picture of the SAME sequence against rank 0's anchor
@@ -168,6 +182,11 @@ class Workload:
             pred = make_pred_table(api, 50 + 13 * rank + s, self.n_mb)
             hs = {"ref": ctx.pinned((H, W), np.uint8), "cur": ctx.pinned((H, W), np.uint8), "pred": ctx.pinned(self.n_mb, api.MB_MVPRED)}
             hs["ref"][:] = f[0]; hs["cur"][:] = f[1]; hs["pred"][:] = pred
+            if self.chroma:
+                for nm, luma, sd in (("ref", f[0], 11), ("cur", f[1], 12)):
+                    u, v = make_chroma_planes(luma, self.yuv, sd + s)
+                    hs[nm + "_u"] = ctx.pinned(u.shape, np.uint8); hs[nm + "_v"] = ctx.pinned(v.shape, np.uint8)
+                    hs[nm + "_u"][:] = u; hs[nm + "_v"][:] = v
             if self.epzs:      # per macroblock: the zero mv + what the spatial / co-located generators would yield (neighbours' motion)
                 hs["shared"] = ctx.pinned((self.n_mb, self.n_shared, 2), np.int16)
                 hs["shared"][:] = make_shared_candidates(50 + 13 * rank + s, self.n_mb, self.n_shared)
@@ -177,12 +196,20 @@ class Workload:
         self.d_heads = torch.empty(7 * self.n_mb * 16, dtype=torch.uint8, device=dev)
         self.d_tokens = torch.empty(self.token_cap * 4, dtype=torch.uint8, device=dev)
         self.d_ntok = torch.zeros(1, dtype=torch.int32, device=dev)
+        if self.chroma:
+            n2 = 7 * self.n_mb * 2
+            self.d_cdc = torch.empty(n2 * 8, dtype=torch.int16, device=dev); self.d_cac = torch.empty(n2 * 120, dtype=torch.int16, device=dev)
+            self.d_ccb = torch.empty(n2, dtype=torch.int32, device=dev); self.d_ccc = torch.empty(n2, dtype=torch.int32, device=dev)
         self.peer_refs = None
         self.tokens_seen = 0
 
     def host_outputs(self, c):
-        return (c.pinned(self.n_mb * self.api.NPART, self.api.ME_RES8), c.pinned((7, self.n_mb), self.api.TQ_HEAD),
-                c.pinned(self.token_cap, self.api.TQ_TOKEN), np.zeros(1, np.uint32))
+        o = [c.pinned(self.n_mb * self.api.NPART, self.api.ME_RES8), c.pinned((7, self.n_mb), self.api.TQ_HEAD),
+             c.pinned(self.token_cap, self.api.TQ_TOKEN), np.zeros(1, np.uint32)]
+        if self.chroma:
+            o.append(dict(dc=c.pinned((7, self.n_mb, 2, 8), np.int16), ac=c.pinned((7, self.n_mb, 2, 8, 15), np.int16),
+                          cb=c.pinned((7, self.n_mb, 2), np.uint32), cc=c.pinned((7, self.n_mb, 2), np.uint32)))
+        return tuple(o)
 
     def setup_anchor(self, dist, rank, world):
         """config 5: rank 0 owns the reconstructed anchors in exportable device memory; every other rank maps them (IPC ->
@@ -210,26 +237,44 @@ class Workload:
         ref_ptr = self.peer_refs[s % N_SETS] if self.peer_refs else ds["ref"].data_ptr()
         ctx.ref_put_u8(s % 2, ref_ptr, api.DEVICE, shape=shape)
         ctx.pic_begin_u8(ds["cur"].data_ptr(), [s % 2], api.DEVICE, shape=shape)
+        if self.chroma:
+            cshape = (self.hc, self.W // 2)
+            ctx.ref_put_chroma(s % 2, ds["ref_u"].data_ptr(), ds["ref_v"].data_ptr(), api.DEVICE, shape=cshape)
+            ctx.pic_chroma(ds["cur_u"].data_ptr(), ds["cur_v"].data_ptr(), api.DEVICE, shape=cshape)
         if self.epzs:
             ctx.epzs_search_frame(ds["pred"].data_ptr(), ds["shared"].data_ptr(), self.efp, self.d_res8.data_ptr(), api.DEVICE, n_mb=self.n_mb)
         else:
             ctx.me_search_frame_pred(ds["pred"].data_ptr(), self.fp, self.d_res8.data_ptr(), api.DEVICE, n_mb=self.n_mb)
         ctx.mc_tq_modes_compact(None, self.qd, self.mode_mask, api.DEVICE, n_mb=self.n_mb,
                                 out=(self.d_heads.data_ptr(), self.d_tokens.data_ptr(), self.d_ntok.data_ptr()), token_cap=self.token_cap)
+        if self.chroma:      # chroma prediction + residual coding of every partition mode's motion (what the RD loop codes per candidate)
+            n2 = self.n_mb * 2
+            for m in range(7):
+                ctx.chroma_residual_coding(self.cdesc, None, m + 1, 0, self.n_mb, api.DEVICE,
+                                           out=(self.d_cdc.data_ptr() + m * n2 * 16, self.d_cac.data_ptr() + m * n2 * 240,
+                                                self.d_ccb.data_ptr() + m * n2 * 4, self.d_ccc.data_ptr() + m * n2 * 4, None))
 
     def step_host(self, s, c, outs, tt):
         """The same picture through the C ABI with pinned HOST buffers: the uploads and the search are only enqueued
         (JMB_HOST_ASYNC); the residual-coding call returns with heads and tokens in the caller's buffers."""
         api = self.api
         hs, _ = self.sets[s % N_SETS]
-        o_res, o_heads, o_tok, o_n = outs
+        o_res, o_heads, o_tok, o_n = outs[:4]
         t0 = time.perf_counter()
         c.ref_put_u8(s % 2, hs["ref"], api.HOST_ASYNC)
         c.pic_begin_u8(hs["cur"], [s % 2], api.HOST_ASYNC)
+        if self.chroma:
+            c.ref_put_chroma(s % 2, hs["ref_u"], hs["ref_v"], api.HOST_ASYNC)
+            c.pic_chroma(hs["cur_u"], hs["cur_v"], api.HOST_ASYNC)
         if self.epzs:
             c.epzs_search_frame(hs["pred"], hs["shared"], self.efp, o_res, api.HOST_ASYNC)
         else:
             c.me_search_frame_pred(hs["pred"], self.fp, o_res, api.HOST_ASYNC)
+        if self.chroma:      # results of all 7 modes come back with the copies queued behind the kernels; the call below waits for everything
+            oc = outs[4]
+            for m in range(7):
+                c._ck(c.L.jmb_chroma_residual_coding(c.h, None, m + 1, 0, self.n_mb, self.cdesc.ctypes.data, oc["dc"][m].ctypes.data, oc["ac"][m].ctypes.data,
+                                                     oc["cb"][m].ctypes.data, oc["cc"][m].ctypes.data, None, api.HOST_ASYNC))
         t1 = time.perf_counter()
         c._ck(c.L.jmb_mc_tq_modes_compact(c.h, None, self.n_mb, self.mode_mask, self.qd.ctypes.data, o_heads.ctypes.data, o_tok.ctypes.data,
                                           self.token_cap, o_n.ctypes.data, api.HOST))
@@ -252,6 +297,9 @@ class Workload:
         h2d = 2 * self.W * self.H + self.n_mb * api.MB_MVPRED.itemsize + api.FRAME_PARAMS.itemsize + api.QUANT_DESC.itemsize
         if self.epzs:
             h2d += self.n_mb * self.n_shared * 4 + api.EPZS_FRAME_PARAMS.itemsize - api.FRAME_PARAMS.itemsize
+        if self.chroma:
+            h2d += 4 * (self.W // 2) * self.hc + api.CHROMA_DESC.itemsize
+            d2h += 7 * self.n_mb * 2 * (16 + 240 + 4 + 4)
         d2h = self.n_mb * api.NPART * api.ME_RES8.itemsize + 7 * self.n_mb * api.TQ_HEAD.itemsize + 4 + 4 * self.tokens_seen
         return int(h2d), int(d2h)
 
@@ -329,7 +377,7 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     top = "epzs" if wl.epzs else "int_search"
     k_ms, k_n = ctx.timing_get(top)
-    kernel_break = {k: ctx.timing_get(k)[0] / max(1, args.steps) for k in ("subpel_planes", "pack_cur", "gen_requests", "int_search", "subpel_refine", "epzs", "mc_tq")}
+    kernel_break = {k: ctx.timing_get(k)[0] / max(1, args.steps) for k in ("subpel_planes", "pack_cur", "gen_requests", "int_search", "subpel_refine", "epzs", "mc_tq", "chroma")}
     ctx.timing(False)
     ctx.sync()
     tokens_dev = int(wl.d_ntok.item())
@@ -421,6 +469,11 @@ def run_ours(args):
                             "frac": sp_bytes / (sp_ms / 1e3) / 1e9 / peak if sp_ms else None},
         "k_mc_tq_modes_c": {"algorithmic_bytes_per_launch": tq_bytes, "launch_ms": tq_ms, "achieved": tq_bytes / (tq_ms / 1e3) / 1e9 if tq_ms else None,
                             "frac": tq_bytes / (tq_ms / 1e3) / 1e9 / peak if tq_ms else None}}
+    if wl.chroma:      # k_chroma_rc, 7 launches per step: per macroblock and mode 2 x (source + reference samples) in, dc / ac / flags out
+        c_ms = kernel_break["chroma"]
+        c_bytes = 7 * n_mb * 2 * (2 * 8 * (16 if wl.yuv == 2 else 8) + 16 + 240 + 8)
+        out["roofline_other"]["k_chroma_rc"] = {"algorithmic_bytes_per_step": c_bytes, "ms_per_step": c_ms, "launches_per_step": 7,
+                                                "achieved": c_bytes / (c_ms / 1e3) / 1e9 if c_ms else None, "frac": c_bytes / (c_ms / 1e3) / 1e9 / peak if c_ms else None}
 
     if not wl.epzs:
         # The same kernel against the bound that actually limits it: the SM ALU pipe (VABSDIFF4 / PRMT / ISETP issue at
@@ -442,26 +495,30 @@ def run_ours(args):
 _JM = {}
 
 
-def _cpu_init(cfg_id, ref_luma, cur_luma, w, h):
+def _cpu_init(cfg_id, ref_luma, cur_luma, w, h, chroma=None):
     """One process = one instance of the CPU implementation; its quarter-pel planes are built once, untimed.
     Full search / fast full search: JM's own functions (oracle/_ref/libjmref.so, JM is single-threaded).  EPZS: the CPU
-    restatement pinned to JM's recorded calls (oracle/jm_oracle.c::jmo_epzs; the real function needs the whole encoder state)."""
+    restatement pinned to JM's recorded calls (oracle/jm_oracle.c::jmo_epzs; the real function needs the whole encoder state).
+    chroma = (ref_u, ref_v, cur_u, cur_v) for config 4."""
     from oracle import pyoracle as po
     _JM["cfg"] = cfg_id
-    if CONFIGS[cfg_id]["search"] == "epzs":
+    cfg = CONFIGS[cfg_id]
+    if cfg["search"] == "epzs" or cfg["chroma"]:
         o = po.Oracle()
         _JM["oracle"] = o
-        _JM["ref"] = o.ref_create(ref_luma)
+        _JM["oref"] = o.ref_create(ref_luma)
         _JM["cur"] = np.ascontiguousarray(cur_luma, np.uint16)
-    else:
-        ref = po.JMRef(w, h, SEARCH_RANGE)
+    if cfg["search"] != "epzs":
+        ref = po.JMRef(w, h, SEARCH_RANGE, fast_full=int(cfg["search"] == "fastfull"))
         ref.set_ref(ref_luma); ref.set_cur(cur_luma)
         _JM["ref"] = ref
+    _JM["chroma"] = chroma
     _JM["w"] = w
 
 
 def _cpu_worker(a):
-    """(macroblock addresses, their predictor rows, their shared-candidate rows or None, lambda) -> mv, cost, levels, (ME s, TQ s)"""
+    """(macroblock addresses, their predictor rows, their shared-candidate rows or None, lambda) -> mv, cost, levels, (ME s, TQ s)
+    [+ chroma results for config 4]"""
     idx, preds, shared, lam = a
     from jm_b200 import api
     from jm_b200 import h264_tables as T
@@ -469,27 +526,61 @@ def _cpu_worker(a):
     cfg = CONFIGS[_JM["cfg"]]
     mbw = _JM["w"] // 16
     mb_xy = np.stack([(idx % mbw) * 16, (idx // mbw) * 16], 1)
-    if cfg["search"] != "epzs":
-        return po.jmref_run_mbs(_JM["ref"], mb_xy, preds, [lam] * 3, QP, T.q_params(QP, 0, 4), T.SNGL_SCAN, T.COEFF_COST4x4[0])
-    o, r, cur = _JM["oracle"], _JM["ref"], _JM["cur"]
     n = cfg["n"]
-    efp = api.epzs_frame_params([lam] * 3, flags=api.EPZS_ADAPT_PATTERN | api.EPZS_DUAL | api.EPZS_SUBPEL | (api.EPZS_TEST8X8 if n == 8 else 0),
-                                pattern=api.EPZS_PAT_EDIAMOND, pattern_dual=api.EPZS_PAT_EDIAMOND, n_shared=shared.shape[1], window=4,
-                                search_range=SEARCH_RANGE)
-    pr = np.zeros(len(idx), api.MB_MVPRED); pr["pred"] = preds
-    reqs = api.epzs_requests_from_frame(pr, efp, mbw, mb_index=idx)
-    t0 = time.perf_counter()
-    res = o.epzs_batch(r, cur, reqs, shared.reshape(-1, 2), (po.SATD, po.SATD, 0, 1, 9))
-    t1 = time.perf_counter()
-    mv = np.stack([res["mv_x"], res["mv_y"]], 1).reshape(len(idx), 41, 2)
+    if cfg["search"] == "full":
+        return po.jmref_run_mbs(_JM["ref"], mb_xy, preds, [lam] * 3, QP, T.q_params(QP, 0, 4), T.SNGL_SCAN, T.COEFF_COST4x4[0])
+    o, r, cur = _JM["oracle"], _JM["oref"], _JM["cur"]
+    if cfg["search"] == "epzs":
+        efp = api.epzs_frame_params([lam] * 3, flags=api.EPZS_ADAPT_PATTERN | api.EPZS_DUAL | api.EPZS_SUBPEL | (api.EPZS_TEST8X8 if n == 8 else 0),
+                                    pattern=api.EPZS_PAT_EDIAMOND, pattern_dual=api.EPZS_PAT_EDIAMOND, n_shared=shared.shape[1], window=4,
+                                    search_range=SEARCH_RANGE)
+        pr = np.zeros(len(idx), api.MB_MVPRED); pr["pred"] = preds
+        reqs = api.epzs_requests_from_frame(pr, efp, mbw, mb_index=idx)
+        t0 = time.perf_counter()
+        res = o.epzs_batch(r, cur, reqs, shared.reshape(-1, 2), (po.SATD, po.SATD, 0, 1, 9))
+        t1 = time.perf_counter()
+        mv = np.stack([res["mv_x"], res["mv_y"]], 1).reshape(len(idx), 41, 2)
+        cost = res["cost"].reshape(len(idx), 41)
+    else:      # fast full search: JM's own setup_fast_full_search + fast_full_search_motion_estimation + sub_pel_motion_estimation
+        jm = _JM["ref"]
+        parts = api.mb_partitions()
+        mv = np.zeros((len(idx), 41, 2), np.int16); cost = np.zeros((len(idx), 41), np.int64)
+        t0 = time.perf_counter()
+        for i in range(len(idx)):
+            mb = (int(mb_xy[i, 0]), int(mb_xy[i, 1]))
+            jm.ffs_setup(mb, (int(preds[i, 0, 0]), int(preds[i, 0, 1])))
+            for k, (t, x, y) in enumerate(parts):
+                p = (int(preds[i, k, 0]), int(preds[i, k, 1])); pos = (mb[0] + x, mb[1] + y)
+                imv, _ = jm.ffs_search(t, pos, p, lam, po.DISTBLK_MAX)
+                m2, c2 = jm.sub_pel(t, pos, p, imv, [lam] * 3, po.DISTBLK_MAX)
+                mv[i, k] = m2; cost[i, k] = c2
+        t1 = time.perf_counter()
     scan, cc = (T.SNGL_SCAN, T.COEFF_COST4x4[0]) if n == 4 else (T.SNGL_SCAN8x8, T.COEFF_COST8x8[0])
     qp_ = T.q_params(QP, 0, n)
     lev = np.zeros((len(idx), 7, 256), np.int16)
     mask = 0x7F if n == 4 else 0x0F
     for i in range(len(idx)):
         lev[i] = o.mc_tq_modes_mb(r, cur, (int(mb_xy[i, 0]), int(mb_xy[i, 1])), mv[i], n, QP, qp_, scan, cc, n == 4, mask)
+    chroma_out = None
+    if cfg["chroma"]:      # 4:2:2 chroma prediction + residual coding of each mode's motion (the pinned restatement)
+        yuv = 2
+        ru, rv, cu, cv = _JM["chroma"]
+        d = api.chroma_desc(yuv, QP, lambda q: T.q_params(q, 0, 4), T.COEFF_COST4x4[0], 0)
+        base = [0, 0, 1, 3, 5, 9, 17, 25]; w4 = [4, 4, 4, 2, 2, 2, 1, 1]; h4 = [4, 4, 2, 4, 2, 1, 2, 1]
+        chroma_out = dict(dc=np.zeros((len(idx), 7, 2, 8), np.int16), cb=np.zeros((len(idx), 7, 2), np.uint32), cc=np.zeros((len(idx), 7, 2), np.uint32))
+        for i in range(len(idx)):
+            cx, cy = int(mb_xy[i, 0]) // 2, int(mb_xy[i, 1])
+            for m in range(1, 8):
+                mv16 = np.array([mv[i, base[m] + (by // h4[m]) * (4 // w4[m]) + bx // w4[m]] for by in range(4) for bx in range(4)], np.int16)
+                for uv, (rp, cp) in enumerate(((ru, cu), (rv, cv))):
+                    p = o.chroma_pred(rp, yuv, (cx, cy), mv16)
+                    c = o.chroma_rc(cp[cy:cy + 16, cx:cx + 8], p, yuv, int(d["qp_ac"][0, uv]), int(d["qp_dc"][0, uv]), d["params_ac"][0, uv],
+                                    d["params_dc"][0, uv], T.COEFF_COST4x4[0], 0)
+                    chroma_out["dc"][i, m - 1, uv] = c["dc"]; chroma_out["cb"][i, m - 1, uv] = c["cbp_blk"]; chroma_out["cc"][i, m - 1, uv] = c["cr_cbp"]
     t2 = time.perf_counter()
-    return mv, res["cost"].reshape(len(idx), 41), lev, np.array([t1 - t0, t2 - t1])
+    if chroma_out is not None:
+        return mv, cost, lev, np.array([t1 - t0, t2 - t1]), chroma_out
+    return mv, cost, lev, np.array([t1 - t0, t2 - t1])
 
 
 def expand_tokens(heads, tokens, mbs, per=16):
@@ -519,21 +610,27 @@ def cpu_baseline(wl, ctx=None, api=None, budget_s=12.0):
     shared = np.array(hs["shared"]) if wl.epzs else None
     # calibrate on 32 MBs, then size the sample for ~budget_s
     idx = np.linspace(0, n_mb - 1, 32).astype(int)
-    _cpu_init(wl.args.config, np.array(hs["ref"]).astype(np.uint16), np.array(hs["cur"]).astype(np.uint16), W, H)
+    chroma = tuple(np.array(hs[k]) for k in ("ref_u", "ref_v", "cur_u", "cur_v")) if wl.chroma else None
+    _cpu_init(wl.args.config, np.array(hs["ref"]).astype(np.uint16), np.array(hs["cur"]).astype(np.uint16), W, H, chroma)
     args = lambda ii: (ii, pred[ii], shared[ii] if shared is not None else None, wl.lam)
-    _, _, _, secs = _cpu_worker(args(idx))
+    secs = _cpu_worker(args(idx))[3]
     per_mb = max(1e-5, float(secs.sum()) / len(idx))
     n = int(min(n_mb, max(64, budget_s / per_mb)))
     idx = np.linspace(0, n_mb - 1, n).astype(int)
-    mv, cost, lev, secs = _cpu_worker(args(idx))
+    out_cpu = _cpu_worker(args(idx))
+    mv, cost, lev, secs = out_cpu[:4]
     what = ("the CPU restatement of EPZS_integer_motion_estimation + EPZS_sub_pel_motion_estimation x41 (pinned to recorded calls of the real "
             "functions, tests/test_epzs_golden.py) + forward8x8/quant_8x8_normal x16 per MB" if wl.epzs else
+            "JM setup_fast_full_search + fast_full_search_motion_estimation x41 + sub_pel_motion_estimation x41 (the real functions), "
+            "4x4 transform/quant x112 and the 4:2:2 chroma prediction/residual coding x7 per MB through the pinned restatement" if wl.chroma else
             "JM full_search_motion_estimation + sub_pel_motion_estimation x41 + forward4x4/quant_4x4_normal x112 per MB")
     res = {"value": n / float(secs.sum()), "unit": "macroblocks/s", "cores": 1, "kind": "port" if wl.epzs else "reference",
            "sample": f"{n} of {n_mb} macroblocks of input set 0 (evenly spaced), {what}",
            "me_seconds": float(secs[0]), "tq_seconds": float(secs[1])}
     if ctx is not None:
         ctx.ref_put_u8(0, np.array(hs["ref"])); ctx.pic_begin_u8(np.array(hs["cur"]), [0])
+        if wl.chroma:
+            ctx.ref_put_chroma(0, np.array(hs["ref_u"]), np.array(hs["ref_v"])); ctx.pic_chroma(np.array(hs["cur_u"]), np.array(hs["cur_v"]))
         if wl.epzs:
             g = ctx.epzs_search_frame(np.array(hs["pred"]), np.array(hs["shared"]), wl.efp).reshape(n_mb, 41)
         else:
@@ -544,6 +641,15 @@ def cpu_baseline(wl, ctx=None, api=None, budget_s=12.0):
         ok_lev = bool(np.array_equal(expand_tokens(heads, tokens, idx, per=16 if wl.cfg["n"] == 4 else 64), lev))
         res["gpu_matches_reference_on_sample"] = ok_mv and ok_lev
         res["checked"] = {"mv_and_cost": ok_mv, "levels": ok_lev, "nonzero_levels_in_sample": int((lev != 0).sum())}
+        if wl.chroma:
+            co = out_cpu[4]
+            ok_c = True
+            for m in range(7):
+                gc = ctx.chroma_residual_coding(wl.cdesc, None, m + 1, 0, n_mb, want_recon=False)
+                ok_c = ok_c and bool(np.array_equal(gc["dc"][idx], co["dc"][:, m]) and np.array_equal(gc["cbp_blk"][idx], co["cb"][:, m]) and
+                                     np.array_equal(gc["cr_cbp"][idx], co["cc"][:, m]))
+            res["checked"]["chroma_dc_levels_and_cbp"] = ok_c
+            res["gpu_matches_reference_on_sample"] = res["gpu_matches_reference_on_sample"] and ok_c
     return res
 
 
@@ -570,6 +676,9 @@ def run_reference(args):
     mbw = W // 16
     pred = make_pred_table(api, 50, n_mb)["pred"]
     shared = make_shared_candidates(50, n_mb, 8) if epzs else None
+    chroma = None
+    if c["chroma"]:
+        chroma = make_chroma_planes(f[0], 2, 11) + make_chroma_planes(f[1], 2, 12)
     per_core = args.ref_mbs_per_core * (8 if epzs else 1)      # an EPZS macroblock is ~50x cheaper than a full-search one
     rng = np.random.default_rng(0)
 
@@ -577,7 +686,7 @@ def run_reference(args):
         idx = rng.permutation(n_mb)[: per_core * cores].reshape(cores, per_core)
         return [(ii, pred[ii], shared[ii] if epzs else None, lam) for ii in idx]
 
-    with mp.get_context("fork").Pool(cores, initializer=_cpu_init, initargs=(args.config, f[0], f[1], W, H)) as pool:
+    with mp.get_context("fork").Pool(cores, initializer=_cpu_init, initargs=(args.config, f[0], f[1], W, H, chroma)) as pool:
         for s in range(args.warmup):
             pool.map(_cpu_worker, job(s))
         t0 = time.perf_counter()
@@ -593,7 +702,9 @@ def run_reference(args):
                             "sample": f"each step = {per_core * cores} random macroblocks of the {c['size']} picture ({per_core} per core, one "
                                       f"instance per core, quarter-pel planes built once before the timed region), " +
                                       ("the pinned CPU restatement of JM's EPZS integer + sub-pel searches + forward8x8/quant_8x8_normal"
-                                       if epzs else "JM's own full_search/sub_pel/forward4x4/quant_4x4_normal") +
+                                       if epzs else "JM's own setup_fast_full_search / fast_full_search / sub_pel functions + the pinned restatement for "
+                                       "4x4 transform/quant and the 4:2:2 chroma path" if c["chroma"] else
+                                       "JM's own full_search/sub_pel/forward4x4/quant_4x4_normal") +
                                       "; value = sampled macroblocks / time"},
            "e2e": {"value": v, "unit": "macroblocks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
