@@ -297,10 +297,10 @@ class Workload:
         h2d = 2 * self.W * self.H + self.n_mb * api.MB_MVPRED.itemsize + api.FRAME_PARAMS.itemsize + api.QUANT_DESC.itemsize
         if self.epzs:
             h2d += self.n_mb * self.n_shared * 4 + api.EPZS_FRAME_PARAMS.itemsize - api.FRAME_PARAMS.itemsize
+        d2h = self.n_mb * api.NPART * api.ME_RES8.itemsize + 7 * self.n_mb * api.TQ_HEAD.itemsize + 4 + 4 * self.tokens_seen
         if self.chroma:
             h2d += 4 * (self.W // 2) * self.hc + api.CHROMA_DESC.itemsize
             d2h += 7 * self.n_mb * 2 * (16 + 240 + 4 + 4)
-        d2h = self.n_mb * api.NPART * api.ME_RES8.itemsize + 7 * self.n_mb * api.TQ_HEAD.itemsize + 4 + 4 * self.tokens_seen
         return int(h2d), int(d2h)
 
 
