@@ -458,13 +458,15 @@ static int epzs_launch(jmb_ctx *ctx, const jmb_epzs_req *d_reqs, int n, const in
   k_epzs_int<<<min(blocks, ctx->epzs_grid[0]), EW * 32, 0, ctx->stream>>>(d_reqs, n, (const short2 *)d_cands, n_cands, d_res, ctx->cur, ctx->cur_pitch,
                                                                            (const uint8_t *const *)ctx->d_reftab, r0.plane_bytes, r0.pitch, ctx->cur_w,
                                                                            ctx->cur_h, ctx->nref, max_range, ctx->d_err);
+  jmb_time_end(ctx, JMB_K_EPZS);
   JMB_LAUNCH_CHECK(ctx);
   if (any_subpel) {
+    jmb_time_begin(ctx, JMB_K_REFINE);      // reported as "subpel_refine", like the refinement that follows the full search
     k_epzs_sub<<<min(blocks, ctx->epzs_grid[1]), EW * 32, 0, ctx->stream>>>(d_reqs, n, d_res, ctx->cur, ctx->cur_pitch, (const uint8_t *const *)ctx->d_reftab,
                                                                              r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, ctx->me, ctx->nref);
+    jmb_time_end(ctx, JMB_K_REFINE);
     JMB_LAUNCH_CHECK(ctx);
   }
-  jmb_time_end(ctx, JMB_K_EPZS);
   return JMB_OK;
 }
 
