@@ -85,6 +85,34 @@ __device__ __forceinline__ void load_src(SrcBlk &s, const uint8_t *cur, int cur_
   }
 }
 
+// HadamardSAD8x8 (me_distortion.c:266-347) of an 8x8 sub-block in registers, two samples per register: a row's eight
+// differences are four integers a + 65536 b (no field leaves +-16320 / 2: the last butterfly stage is never formed).  Two
+// horizontal stages act on whole registers, three vertical ones on the rows, and the third horizontal stage is folded into
+// |u + v| + |u - v| = 2 max(|u|, |v|): the maxima add up to half the coefficient sum S, and JM's (S + 2) >> 2 is (M + 1) >> 1.
+__device__ __forceinline__ int hadamard8_packed(const SrcBlk &src, const uint8_t *ref, int pitch) {
+  int p[8][4];
+#pragma unroll
+  for (int y = 0; y < 8; y++) {
+    unsigned lo, hi;
+    ld8(ref + (size_t)y * pitch, lo, hi);
+    const int d0 = (int)__byte_perm(src.w[2 * y], 0, 0x4140) - (int)__byte_perm(lo, 0, 0x4140), d1 = (int)__byte_perm(src.w[2 * y], 0, 0x4342) - (int)__byte_perm(lo, 0, 0x4342);
+    const int d2 = (int)__byte_perm(src.w[2 * y + 1], 0, 0x4140) - (int)__byte_perm(hi, 0, 0x4140), d3 = (int)__byte_perm(src.w[2 * y + 1], 0, 0x4342) - (int)__byte_perm(hi, 0, 0x4342);
+    const int a0 = d0 + d2, a1 = d1 + d3, a2 = d0 - d2, a3 = d1 - d3;
+    p[y][0] = a0 + a1; p[y][1] = a0 - a1; p[y][2] = a2 + a3; p[y][3] = a2 - a3;
+  }
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int b0 = p[0][k] + p[4][k], b1 = p[1][k] + p[5][k], b2 = p[2][k] + p[6][k], b3 = p[3][k] + p[7][k];
+    const int b4 = p[0][k] - p[4][k], b5 = p[1][k] - p[5][k], b6 = p[2][k] - p[6][k], b7 = p[3][k] - p[7][k];
+    const int c0 = b0 + b2, c1 = b1 + b3, c2 = b0 - b2, c3 = b1 - b3, c4 = b4 + b6, c5 = b5 + b7, c6 = b4 - b6, c7 = b5 - b7;
+    const int e[8] = {c0 + c1, c0 - c1, c2 + c3, c2 - c3, c4 + c5, c4 - c5, c6 + c7, c6 - c7};
+#pragma unroll
+    for (int i = 0; i < 8; i++) { const int l = (int)(short)(e[i] & 0xffff), h = (e[i] - l) >> 16; s += max(abs(l), abs(h)); }
+  }
+  return (s + 1) >> 1;
+}
+
 // distortion contribution of sub-block (sbx, sby) [units of n pels] of a block at (pos_x,pos_y)
 // against the candidate at absolute quarter-pel (cqx, cqy)
 __device__ __forceinline__ int subblock_dist(const RefView &rv, const SrcBlk &src, int cqx, int cqy, int sbx, int sby, int n, int metric) {
@@ -105,18 +133,7 @@ __device__ __forceinline__ int subblock_dist(const RefView &rv, const SrcBlk &sr
     for (int i = 0; i < 16; i++) s += (metric == JMB_SAD) ? abs(d[i]) : d[i] * d[i];
     return s;
   }
-  int a[64];
-#pragma unroll
-  for (int y = 0; y < 8; y++) {
-    unsigned lo, hi;
-    ld8(ref + (size_t)y * rv.pitch, lo, hi);
-#pragma unroll
-    for (int x = 0; x < 4; x++) {
-      a[y * 8 + x] = (int)((src.w[2 * y] >> (8 * x)) & 255) - (int)((lo >> (8 * x)) & 255);
-      a[y * 8 + 4 + x] = (int)((src.w[2 * y + 1] >> (8 * x)) & 255) - (int)((hi >> (8 * x)) & 255);
-    }
-  }
-  return hadamard8(a);
+  return hadamard8_packed(src, ref, rv.pitch);
 }
 
 // 4x4 sub-block, split in two so that the loads of several candidates can be in flight before the first Hadamard

@@ -14,8 +14,15 @@
 
 namespace {
 
-constexpr int EW = 4;          // warps per CTA
-constexpr int TCAP = 384;      // touched bitmap words remembered per search (more: the whole map is cleared)
+constexpr int EG = 41;         // searches per CTA: consecutive requests (one macroblock's 41 partitions in the picture form)
+constexpr int ET = 128;        // threads per CTA
+constexpr int CB = 32;         // candidates a search puts up per round
+#ifndef JMB_EPZS_SUB_MINB
+#define JMB_EPZS_SUB_MINB 4
+#endif
+#ifndef JMB_EPZS_INT_MINB
+#define JMB_EPZS_INT_MINB 6
+#endif
 
 // pattern_data (me_epzs_common.c:48-76): {mv_x, mv_y, start_nmbr, next_points}, quarter-pel; chaining as EPZSInit (:178-230):
 // every pattern stops on itself except sbdiamond / pmvfast, which hand over to the small diamond; nextLast is TRUE for all
@@ -36,62 +43,14 @@ __constant__ unsigned char c_ne[5][5] = {{0, 10, 7, 8, 9}, {10, 0, 6, 10, 9}, {7
 // window predictor ring, EPZSWindowPredictorInit mode 0 (me_epzs_common.c:352-371): i = +1 then -1
 __constant__ signed char c_ring[8][2] = {{1, 0}, {1, 1}, {0, 1}, {-1, 1}, {-1, 0}, {-1, -1}, {0, -1}, {1, -1}};
 
-struct WarpS {
-  short2 mv[32];
-  int dist[32];
-  unsigned short touched[TCAP];
-};
 
-struct Blk { RefView rv; const uint8_t *cur; int cur_pitch, pos_x, pos_y, bsx, bsy; };
-
-__device__ __forceinline__ long long mv_cost(int lam, int vx, int vy, int px, int py) {
-  return (long long)lam * (jmb_mvbits(vx - px) + jmb_mvbits(vy - py));
-}
-
-// SAD (computeSAD, me_distortion.c:349: partition-origin clamp) of the candidates ws.mv[0..n) whose bit is set in `valid`;
-// a candidate's rows are split over 32 / pow2(n) lanes
-__device__ __forceinline__ void eval_sad(const Blk &b, WarpS &ws, int n, unsigned valid, int lane) {
-  const int p2 = n <= 1 ? 1 : 1 << (32 - __clz(n - 1));
-  const int lpc = min(32 / p2, b.bsy);
-  const int c = lane / lpc, sub = lane - c * lpc;
-  int s = 0;
-  if (c < n && ((valid >> c) & 1)) {
-    const short2 v = ws.mv[c];
-    const uint8_t *ref = umv(b.rv, (b.pos_y << 2) + v.y, (b.pos_x << 2) + v.x);
-    const uint8_t *src = b.cur + (size_t)b.pos_y * b.cur_pitch + b.pos_x;
-    for (int y = sub; y < b.bsy; y += lpc)
-      for (int x = 0; x < b.bsx; x += 4)
-        s += __vsadu4(*(const unsigned *)(src + (size_t)y * b.cur_pitch + x), ld4(ref + (size_t)y * b.rv.pitch + x));
-  }
-  for (int sh = 1; sh < lpc; sh <<= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);
-  if (c < n && sub == 0) ws.dist[c] = s;
-  __syncwarp();
-}
-
-// distortion of the sub-pel candidates ws.mv[0..n) with the stage's metric (computeSAD / SSE / SATD incl. the 8x8 Hadamard):
-// work item = (candidate, sub-block), summed with shared-memory atomics
-__device__ __forceinline__ void eval_sub(const Blk &b, WarpS &ws, int n, int metric, int t8, int lane) {
-  if (lane < n) ws.dist[lane] = 0;
-  __syncwarp();
-  const int nn = (metric == JMB_SATD && t8) ? 8 : 4, nsx = b.bsx / nn, nsub = nsx * (b.bsy / nn);
-  for (int it = lane; it < n * nsub; it += 32) {
-    const int c = it / nsub, sb = it - c * nsub, sbx = sb % nsx, sby = sb / nsx;
-    SrcBlk src;
-    load_src(src, b.cur, b.cur_pitch, b.pos_x + sbx * nn, b.pos_y + sby * nn, nn);
-    const short2 v = ws.mv[c];
-    atomicAdd(&ws.dist[c], subblock_dist(b.rv, src, (b.pos_x << 2) + v.x, (b.pos_y << 2) + v.y, sbx, sby, nn, metric));
-  }
-  __syncwarp();
-}
-
-__device__ __forceinline__ long long shfl_ll(long long v) {
-  return (long long)(((unsigned long long)(unsigned)__shfl_sync(0xffffffffu, (int)((unsigned long long)v >> 32), 0) << 32) |
-                     (unsigned)__shfl_sync(0xffffffffu, (int)(unsigned long long)v, 0));
+__device__ __forceinline__ unsigned mv_cost32(int lam, int vx, int vy, int px, int py) {      // lambda <= 65535, mvbits <= 33 each: < 2^23
+  return (unsigned)lam * (unsigned)(jmb_mvbits(vx - px) + jmb_mvbits(vy - py));
 }
 
 enum { EPZS_ERR_FIELD = 512 };      // a request field out of range (reported through d_err like the JMB_REQERR_* codes)
 
-__device__ __forceinline__ int epzs_check(const jmb_epzs_req &q, int w, int h, int nref, int n_cands, int max_range) {
+__device__ __forceinline__ int epzs_check(const jmb_epzs_req &q, int w, int h, int nref, int n_cands, int max_range, int hcap) {
   if (q.blocktype < 1 || q.blocktype > 7) return JMB_REQERR_BLOCKTYPE;
   const int bsx = c_bsx[q.blocktype], bsy = c_bsy[q.blocktype];
   int e = 0;
@@ -102,286 +61,347 @@ __device__ __forceinline__ int epzs_check(const jmb_epzs_req &q, int w, int h, i
   if (q.stop < 0 || q.stop > lim || q.medthres < 0 || q.medthres > lim || q.prev_sad < 0 || q.prev_sad > lim || q.subthres < 0 ||
       q.subthres > lim || q.min_mcost < 0 || q.min_mcost > lim) e |= JMB_REQERR_MINCOST;
   const int tot = q.n_cand[0] + q.n_cand[1] + ((q.flags & JMB_EPZS_WINDOW_GEN) ? 0 : q.n_cand[2]) + q.n_cand[3];
+  const int listed = q.n_cand[0] + q.n_cand[1] + q.n_cand[2] + q.n_cand[3];
   if (q.pattern > 5 || q.pattern_dual > 5 || q.range_x < 1 || q.range_y < 1 || q.range_x > max_range || q.range_y > max_range ||
       q.cand_off < 0 || q.cand_off + tot > n_cands || ((q.flags & JMB_EPZS_TEST8X8) && q.blocktype > 4) ||
-      ((q.flags & JMB_EPZS_WINDOW_GEN) && q.n_cand[2] > 63)) e |= EPZS_ERR_FIELD;
+      ((q.flags & JMB_EPZS_WINDOW_GEN) && q.n_cand[2] > 63) || (!(q.flags & JMB_EPZS_SKIP_INT) && listed + 1 > hcap)) e |= EPZS_ERR_FIELD;
   return e;
 }
 
-// JM's visited map (EPZSMap) as a small open-addressing hash set per warp: a search visits at most a few hundred of the
-// (2 range + 1)^2 positions, and a 4 KB table instead of a 8-33 KB bitmap lets four times as many searches be in flight.
-constexpr int HS = 1024;       // slots (power of two)
-struct Visited {
-  unsigned *tab;               // HS keys, 0 = empty
-  unsigned short *touched;     // slots filled by the current search (lane 0's bookkeeping)
-  int n;
-  __device__ __forceinline__ static unsigned key_of(int dx, int dy) { return (((unsigned)(dy + 2048) << 16) | (unsigned)(dx + 2048)) + 1u; }
-  __device__ __forceinline__ static unsigned slot_of(unsigned k) { return (k * 2654435761u) >> 22; }
-  __device__ __forceinline__ bool seen(int dx, int dy) const {
-    const unsigned k = key_of(dx, dy);
-    for (unsigned s = slot_of(k);; s = (s + 1) & (HS - 1)) { const unsigned v = tab[s]; if (v == k) return true; if (!v) return false; }
-  }
-  __device__ __forceinline__ int visit(int dx, int dy) {      // lane 0: 1 = visited before, 0 = new, -1 = table full
-    const unsigned k = key_of(dx, dy);
-    for (unsigned s = slot_of(k);; s = (s + 1) & (HS - 1)) {
-      const unsigned v = tab[s];
-      if (v == k) return 1;
-      if (!v) {
-        if (n >= HS - HS / 4) return -1;
-        tab[s] = k;
-        if (n < TCAP) touched[n] = (unsigned short)s;
-        n++;
-        return 0;
-      }
-    }
-  }
+// ---- integer stage: EPZS_integer_motion_estimation (me_epzs_int.c:42-426) ---------------------------------------------
+// One CTA walks EG searches TOGETHER, round by round.  Thread s < EG directs search s: it replays JM's control flow (early
+// exits, predictor list, pattern walk, dual refinement) on COMPLETE costs and puts up the candidates of its next step; then
+// all 128 threads evaluate everything that was put up -- one 4x4 block of one search per thread (the blocks of a macroblock's
+// 41 partitions are 112 of them), walking that search's candidates and adding mv cost + (SAD << 5) into tot[search][candidate]
+// -- and the directors read the totals.  JM's early-terminated distortion returns the bound it was given (mv_search.h:19-23),
+// which can never win a strict '<', so complete sums decide alike.
+// JM's visited map (EPZSMap) is needed for one thing only: a predictor list that repeats a position (or the start mv) must not
+// count it twice in the best / second-best pair -- a small hash set per search, filled while the list is read.  The pattern
+// walk needs none: a position met again costs at least the current minimum (which only falls), and only a strict '<' moves.
+struct IntS {
+  short pos_x, pos_y, px, py;
+  int lam, first;                 // first: index of the search's first 4x4 block among the CTA's
+  unsigned char blocktype, ref, nc, lbx;   // nc: candidates put up this round; lbx: log2(4x4 blocks per row)
+  short2 cand[CB];
+  unsigned char cidx[CB];         // pattern rounds: which point of the round
 };
 
-// ---- integer stage: EPZS_integer_motion_estimation (me_epzs_int.c:42-426) ---------------------------------------------
-__global__ void __launch_bounds__(EW * 32, 6)
+__global__ void __launch_bounds__(ET, JMB_EPZS_INT_MINB)
 k_epzs_int(const jmb_epzs_req *__restrict__ reqs, int n, const short2 *__restrict__ cands, int n_cands, jmb_epzs_res *__restrict__ res,
            const uint8_t *__restrict__ cur, int cur_pitch, const uint8_t *const *__restrict__ ref_planes, size_t plane_bytes, int ref_pitch,
-           int w, int h, int nref, int max_range, int *__restrict__ err) {
-  __shared__ WarpS wss[EW];
-  __shared__ unsigned htab[EW][HS];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WarpS &ws = wss[warp];
-  Visited vis{htab[warp], ws.touched, 0};
+           int w, int h, int nref, int max_range, int hslots, int *__restrict__ err) {
+  __shared__ IntS S[EG];
+  __shared__ int tot[EG][CB];
+  __shared__ int s_first[EG + 1];
+  extern __shared__ unsigned hset[];      // [EG][hslots]: positions (relative to the start mv) the predictor list has named, 0 = empty
+  const int tid = threadIdx.x, base = blockIdx.x * EG, cnt = min(EG, n - base);
   const long long BIG = (long long)0x7fffffff << 5;      // DISTBLK_MAX
-  for (int i = lane; i < HS; i += 32) vis.tab[i] = 0;
-  __syncwarp();
+  enum { PH_START, PH_PRED, PH_PAT, PH_DONE };
+  int phase = PH_DONE;
+  // director state
+  int sx = 0, sy = 0, rx = 0, ry = 0, tx = 0, ty = 0, t2x = 0, t2y = 0, check_median = 0, exit_code = 0, evals = 0, seg = 0, i0 = 0, off = 0, nset = 0, full = 0;
+  int pat = 0, cx = 0, cy = 0, point = 0, total = 0, next_last = 0, pattern_stop = 0, dir = 0, pending = 0;
+  unsigned flags = 0, ncw = 0, gtw = 0, jm_ref = 0, pats = 0;
+  long long minc = 0, second = 0, prev = 0, med = 0, stop = 0, ld = 0, centre_cost = 0;
+  unsigned *const hs = hset + (size_t)tid * hslots;
 
-  for (int ri = blockIdx.x * EW + warp; ri < n; ri += gridDim.x * EW) {
-    const jmb_epzs_req q = reqs[ri];
-    {
-      const int bad = epzs_check(q, w, h, nref, n_cands, max_range);
-      if (bad) { if (lane == 0) jmb_req_report(err, bad, ri); continue; }
+  for (int i = tid; i < cnt * hslots; i += ET) hset[i] = 0;
+  if (tid < cnt) {
+    const jmb_epzs_req q = reqs[base + tid];
+    IntS &me_ = S[tid];
+    me_.nc = 0; me_.first = 0; me_.lbx = 0; me_.blocktype = 7;
+    const int bad = epzs_check(q, w, h, nref, n_cands, max_range, hslots - hslots / 4);
+    jmb_epzs_res o;
+    o.mv_x = o.imv_x = q.start_x; o.mv_y = o.imv_y = q.start_y; o.cost = o.icost = q.min_mcost; o.prev_sad = q.prev_sad; o.exit_code = 0; o.n_evals = 0;
+    if (bad) { jmb_req_report(err, bad, base + tid); res[base + tid] = o; }
+    else if (q.flags & JMB_EPZS_SKIP_INT) res[base + tid] = o;      // sub-pel only: the integer-stage fields of the result echo the request
+    else {
+      me_.pos_x = q.pos_x; me_.pos_y = q.pos_y; me_.px = q.pred_x; me_.py = q.pred_y; me_.lam = q.lambda[0];
+      me_.blocktype = q.blocktype; me_.ref = q.ref; me_.lbx = (unsigned char)(c_bsx[q.blocktype] >> 3);      // 4 -> 0, 8 -> 1, 16 -> 2
+      sx = q.start_x; sy = q.start_y; rx = q.range_x; ry = q.range_y; tx = sx; ty = sy;
+      flags = q.flags; jm_ref = q.jm_ref; pats = q.pattern | (q.pattern_dual << 8);
+      ncw = q.n_cand[0] | (q.n_cand[1] << 8) | (q.n_cand[2] << 16) | ((unsigned)q.n_cand[3] << 24);
+      gtw = q.gate[0] | (q.gate[1] << 8) | (q.gate[2] << 16) | ((unsigned)q.gate[3] << 24);
+      off = q.cand_off; prev = q.prev_sad; med = q.medthres; stop = q.stop; ld = 2ll * q.lambda[0];
+      phase = PH_START;
+      me_.cand[0] = make_short2((short)sx, (short)sy); me_.nc = 1; tot[tid][0] = 0;      // the start mv (:93-100)
     }
-    if (q.flags & JMB_EPZS_SKIP_INT) {      // sub-pel only: the integer-stage fields of the result echo the request
-      if (lane == 0) {
-        jmb_epzs_res o;
-        o.mv_x = o.imv_x = q.start_x; o.mv_y = o.imv_y = q.start_y; o.cost = o.icost = q.min_mcost; o.prev_sad = q.prev_sad; o.exit_code = 0; o.n_evals = 0;
-        res[ri] = o;
+  }
+  __syncthreads();
+  if (tid == 0) {      // the CTA's 4x4 blocks, search after search (searches that take no part own none)
+    int f = 0;
+    for (int i = 0; i < cnt; i++) { s_first[i] = f; if (S[i].nc) f += (c_bsx[S[i].blocktype] >> 2) * (c_bsy[S[i].blocktype] >> 2); }
+    s_first[cnt] = f;
+  }
+  __syncthreads();
+  const int nblk = s_first[cnt];
+  auto in_range = [&](int vx, int vy) { return abs(vx - sx) <= rx && abs(vy - sy) <= ry; };
+  // claims (dx, dy) in the search's set: true if it was not there
+  auto claim = [&](int dx, int dy) -> bool {
+    const unsigned k = (((unsigned)(dy + 2048) << 16) | (unsigned)(dx + 2048)) + 1u;
+    for (unsigned sl = (k * 2654435761u) >> 8;; sl++) {
+      sl &= (unsigned)hslots - 1u;
+      const unsigned v = hs[sl];
+      if (v == k) return false;
+      if (!v) { if (nset >= hslots - hslots / 4) { full = 1; return false; } hs[sl] = k; nset++; return true; }
+    }
+  };
+
+  for (;;) {
+    if (!__syncthreads_or(phase != PH_DONE)) break;
+    // ---- everybody: the distortions of what was put up ----
+    for (int item = tid; item < nblk; item += ET) {
+      int lo = 0, hi = cnt - 1;                        // last search whose first block is <= item (searches without blocks share a first index: skip them)
+      while (lo < hi) { const int m = (lo + hi + 1) >> 1; if (s_first[m] <= item) lo = m; else hi = m - 1; }
+      while (s_first[lo + 1] == s_first[lo]) lo--;
+      const IntS &q = S[lo];
+      const int nc = q.nc;
+      if (!nc) continue;
+      const int blk = item - s_first[lo], bx = blk & ((1 << q.lbx) - 1), by = blk >> q.lbx;
+      const uint8_t *sp = cur + (size_t)(q.pos_y + by * 4) * cur_pitch + q.pos_x + bx * 4;
+      const unsigned s0 = *(const unsigned *)sp, s1 = *(const unsigned *)(sp + cur_pitch), s2 = *(const unsigned *)(sp + 2 * (size_t)cur_pitch),
+                     s3 = *(const unsigned *)(sp + 3 * (size_t)cur_pitch);
+      const RefView rv{ref_planes[q.ref], plane_bytes, ref_pitch, w, h};
+      const int bqx = q.pos_x << 2, bqy = q.pos_y << 2;
+      const size_t boff = (size_t)(by * 4) * ref_pitch + bx * 4;
+      for (int c = 0; c < nc; c++) {
+        const short2 v = q.cand[c];
+        const uint8_t *rp = umv(rv, bqy + v.y, bqx + v.x) + boff;      // computeSAD (me_distortion.c:349): the PARTITION origin is clamped
+        unsigned d = __vsadu4(s0, ld4(rp)) + __vsadu4(s1, ld4(rp + ref_pitch)) + __vsadu4(s2, ld4(rp + 2 * (size_t)ref_pitch)) + __vsadu4(s3, ld4(rp + 3 * (size_t)ref_pitch));
+        d <<= 5;
+        if (blk == 0) d += mv_cost32(q.lam, v.x, v.y, q.px, q.py);
+        atomicAdd(&tot[lo][c], (int)d);
       }
-      continue;
     }
-    Blk b{RefView{ref_planes[q.ref], plane_bytes, ref_pitch, w, h}, cur, cur_pitch, q.pos_x, q.pos_y, c_bsx[q.blocktype], c_bsy[q.blocktype]};
-    const int sx = q.start_x, sy = q.start_y, px = q.pred_x, py = q.pred_y, rx = q.range_x, ry = q.range_y;
-    const bool gt0 = (q.flags & JMB_EPZS_REF_GT0_FRAME) != 0;
-    int tx = sx, ty = sy, exit_code = 0, evals = 0, full = 0;
-    long long minc, prev = q.prev_sad;
-    vis.n = 0;
-    auto in_range = [&](int vx, int vy) { return abs(vx - sx) <= rx && abs(vy - sy) <= ry; };
-    const int lam = q.lambda[0];
-    const long long ld = 2ll * lam, med = q.medthres, stop = q.stop;
-    // ---- the start mv (:93-100) ----
-    if (lane == 0) { ws.mv[0] = make_short2((short)sx, (short)sy); vis.visit(0, 0); }
-    __syncwarp();
-    eval_sad(b, ws, 1, 1u, lane);
-    evals++;
-    minc = mv_cost(lam, sx, sy, px, py) + ((long long)ws.dist[0] << 5);
-    if (gt0 && (prev < min(med + ld, minc) || prev * 8 < minc)) exit_code = 1;                        // :103-117
-    else if (minc > med + ld) {                                                                        // :121
-      if (minc < (stop >> 1)) {                                                                        // :135-150
-        if (q.jm_ref == 0 || prev > minc) prev = minc;
-        exit_code = 2;
-      } else {
-        long long second = BIG;
-        const long long centre_cost = minc;      // JM runs the predictor generators (and their gates) before it checks any predictor
-        int check_median = 0, t2x = 0, t2y = 0;
-        int off = q.cand_off;
-        // ---- predictor list (:215-252) ----
-        for (int s = 0; s < 4; s++) {
-          const int ns = q.n_cand[s];
-          const bool gen = s == 2 && (q.flags & JMB_EPZS_WINDOW_GEN);
-          const bool on = q.gate[s] == 0 || centre_cost > (long long)q.gate[s] * stop;
-          if (on)
-            for (int i0 = 0; i0 < ns; i0 += 32) {
-              const int nb = min(32, ns - i0);
-              bool ok = false;
-              if (lane < nb) {
-                short2 v;
-                if (gen) {      // window predictors around the start mv: rings of size range >> k, k descending (EPZSWindowPredictorInit)
-                  const int i = i0 + lane, rings = (ns + 8) >> 3, sp = rx >> (rings - 1 - (i >> 3));
-                  v = make_short2((short)(sx + c_ring[i & 7][0] * sp), (short)(sy + c_ring[i & 7][1] * sp));
-                } else v = cands[off + i0 + lane];
-                ws.mv[lane] = v;
-                ok = in_range(v.x, v.y) && !vis.seen(v.x - sx, v.y - sy);
-              }
-              const unsigned valid = __ballot_sync(0xffffffffu, ok);
-              __syncwarp();
-              if (valid) eval_sad(b, ws, nb, valid, lane);
-              evals += __popc(valid);
-              if (lane == 0) {
-                for (int c = 0; c < nb; c++) {
-                  if (!((valid >> c) & 1)) continue;
-                  const int vx = ws.mv[c].x, vy = ws.mv[c].y;
-                  const int vs = vis.visit(vx - sx, vy - sy);
-                  if (vs) { full |= vs < 0; continue; }
-                  long long mcost = mv_cost(lam, vx, vy, px, py);
-                  if (mcost < second) {
-                    mcost += (long long)ws.dist[c] << 5;
-                    if (mcost < minc) { t2x = tx; t2y = ty; tx = vx; ty = vy; second = minc; minc = mcost; check_median = 1; }
-                    else if (mcost < second) { t2x = vx; t2y = vy; second = mcost; check_median = 1; }
-                  }
-                }
-              }
-              __syncwarp();
+    __syncthreads();
+    // ---- directors: read the totals, decide, put up the next candidates ----
+    if (phase != PH_DONE) {
+      IntS &me_ = S[tid];
+      int have = me_.nc;      // totals of `have` candidates are in tot[tid][]
+      me_.nc = 0;
+      bool posted = false;
+      while (!posted && phase != PH_DONE) {
+        if (phase == PH_START) {
+          evals++;
+          minc = (unsigned)tot[tid][0];
+          const bool gt0 = (flags & JMB_EPZS_REF_GT0_FRAME) != 0;
+          if (gt0 && (prev < min(med + ld, minc) || prev * 8 < minc)) { exit_code = 1; phase = PH_DONE; }               // :103-117
+          else if (!(minc > med + ld)) phase = PH_DONE;                                                                 // :121
+          else if (minc < (stop >> 1)) { if (jm_ref == 0 || prev > minc) prev = minc; exit_code = 2; phase = PH_DONE; } // :135-150
+          else {
+            second = BIG; centre_cost = minc;      // JM runs the predictor generators (and their gates) before it checks any predictor
+            claim(0, 0);
+            seg = 0; i0 = 0; have = 0; phase = PH_PRED;
+          }
+        } else if (phase == PH_PRED) {
+          // JM's rule (:226-251) keeps the two cheapest candidates so far, the earlier one first on a tie
+          for (int c = 0; c < have; c++) {
+            const long long v = (unsigned)tot[tid][c];
+            const short2 m = me_.cand[c];
+            if (v < minc) { second = minc; t2x = tx; t2y = ty; minc = v; tx = m.x; ty = m.y; check_median = 1; }
+            else if (v < second) { second = v; t2x = m.x; t2y = m.y; check_median = 1; }
+          }
+          have = 0;
+          int k = 0;
+          while (k == 0 && seg < 4) {      // the next stretch of the list (:215-252): what is in range and new
+            const int ns = (ncw >> (8 * seg)) & 255, gate = (gtw >> (8 * seg)) & 255;
+            const bool gen = seg == 2 && (flags & JMB_EPZS_WINDOW_GEN);
+            if (i0 >= ns || !(gate == 0 || centre_cost > (long long)gate * stop)) { if (!gen) off += ns; seg++; i0 = 0; continue; }
+            const int nb = min(CB, ns - i0);
+            for (int i = i0; i < i0 + nb; i++) {
+              short2 v;
+              if (gen) {      // window predictors around the start mv: rings of size range >> k, k descending (EPZSWindowPredictorInit)
+                const int rings = (ns + 8) >> 3, spc = rx >> (rings - 1 - (i >> 3));
+                v = make_short2((short)(sx + c_ring[i & 7][0] * spc), (short)(sy + c_ring[i & 7][1] * spc));
+              } else v = cands[off + i];
+              if (in_range(v.x, v.y) && claim(v.x - sx, v.y - sy)) me_.cand[k++] = v;
             }
-          if (!gen) off += ns;
-        }
-        tx = __shfl_sync(0xffffffffu, tx, 0); ty = __shfl_sync(0xffffffffu, ty, 0);
-        t2x = __shfl_sync(0xffffffffu, t2x, 0); t2y = __shfl_sync(0xffffffffu, t2y, 0);
-        check_median = __shfl_sync(0xffffffffu, check_median, 0);
-        minc = shfl_ll(minc);
-        if (gt0 && prev * 3 < minc) exit_code = 3;                                                     // :254-273
-        else if (minc > stop) {                                                                        // :279
-          int pat = q.pattern, cx, cy;
-          if (q.flags & JMB_EPZS_ADAPT_PATTERN) {                                                      // :286-300
-            if (minc < stop + ((3 * med) >> 1))
-              pat = ((tx == 0 && ty == 0) || (abs(tx - sx) < 10 && abs(ty - sy) < 10)) ? JMB_EPZS_PAT_SDIAMOND : JMB_EPZS_PAT_SQUARE;
-            else if (q.flags & JMB_EPZS_SQUARE_HINT) pat = JMB_EPZS_PAT_SQUARE;
+            i0 += nb;
           }
-          cx = tx; cy = ty;
-          for (;;) {
-            int pattern_stop = 0, point = 0, next_last = 0, total = c_pat_n[pat], dir = 0;
-            do {                                                                                       // :307-360
-              const int np = c_pat_n[pat];
-              bool ok = false;
-              if (lane < total) {
-                int pi = point + lane; if (pi >= np) pi -= np;
-                const short2 v = make_short2((short)(cx + c_pat[pat][pi][0]), (short)(cy + c_pat[pat][pi][1]));
-                ws.mv[lane] = v;
-                ok = in_range(v.x, v.y) && !vis.seen(v.x - sx, v.y - sy);
+          if (k) { for (int c = 0; c < k; c++) tot[tid][c] = 0; me_.nc = (unsigned char)k; evals += k; posted = true; }
+          else {      // the list is through
+            const bool gt0 = (flags & JMB_EPZS_REF_GT0_FRAME) != 0;
+            if (gt0 && prev * 3 < minc) { exit_code = 3; phase = PH_DONE; }                                             // :254-273
+            else if (!(minc > stop)) phase = PH_DONE;                                                                   // :279
+            else {
+              pat = pats & 255;
+              if (flags & JMB_EPZS_ADAPT_PATTERN) {                                                                     // :286-300
+                if (minc < stop + ((3 * med) >> 1))
+                  pat = ((tx == 0 && ty == 0) || (abs(tx - sx) < 10 && abs(ty - sy) < 10)) ? JMB_EPZS_PAT_SDIAMOND : JMB_EPZS_PAT_SQUARE;
+                else if (flags & JMB_EPZS_SQUARE_HINT) pat = JMB_EPZS_PAT_SQUARE;
               }
-              const unsigned valid = __ballot_sync(0xffffffffu, ok);
-              __syncwarp();
-              if (valid) eval_sad(b, ws, total, valid, lane);
-              evals += __popc(valid);
-              if (lane == 0) {
-                for (int c = 0; c < total; c++) {
-                  if (!((valid >> c) & 1)) continue;
-                  const int vx = ws.mv[c].x, vy = ws.mv[c].y;
-                  const int vs = vis.visit(vx - sx, vy - sy);
-                  if (vs) { full |= vs < 0; continue; }
-                  long long mcost = mv_cost(lam, vx, vy, px, py);
-                  if (mcost < minc) {
-                    mcost += (long long)ws.dist[c] << 5;
-                    if (mcost < minc) { tx = vx; ty = vy; minc = mcost; dir = point + c; if (dir >= np) dir -= np; }
-                  }
-                }
-              }
-              __syncwarp();
-              tx = __shfl_sync(0xffffffffu, tx, 0); ty = __shfl_sync(0xffffffffu, ty, 0); dir = __shfl_sync(0xffffffffu, dir, 0);
-              minc = shfl_ll(minc);
-              if (next_last || (tx == cx && ty == cy)) {
-                pattern_stop = c_pat_stop[pat];
-                pat = c_pat_next[pat];
-                total = c_pat_n[pat];
-                next_last = 1; dir = 0; point = 0;
-              } else {
-                total = c_pat[pat][dir][3];
-                point = c_pat[pat][dir][2];
-                cx = tx; cy = ty;
-              }
-            } while (pattern_stop != 1);
-            if (gt0 && (4 * prev < minc || (3 * prev < minc && prev <= stop))) { exit_code = 4; break; }      // :362-376
-            if (!(check_median && (q.jm_ref == 0 || minc < 2 * prev) && minc > ((3 * stop) >> 1) && (q.flags & JMB_EPZS_DUAL))) break;   // :379-384
-            if ((tx == 0 && ty == 0) || (tx == sx && ty == sy))                                         // :391-399
-              pat = (abs(tx - sx) < 10 && abs(ty - sy) < 10) ? JMB_EPZS_PAT_SDIAMOND : JMB_EPZS_PAT_SQUARE;
-            else pat = q.pattern_dual;
-            cx = t2x; cy = t2y;
-            check_median = 0;
+              cx = tx; cy = ty;
+              pattern_stop = 0; point = 0; next_last = 0; total = c_pat_n[pat]; dir = 0; pending = 0;
+              phase = PH_PAT;
+            }
           }
+        } else {      // PH_PAT: the pattern walk (:307-360)
+          if (pending) {
+            const int np = c_pat_n[pat];
+            long long bestv = minc; int bc = -1;
+            for (int c = 0; c < have; c++) { const long long v = (unsigned)tot[tid][c]; if (v < bestv) { bestv = v; bc = c; } }      // the first of the cheapest
+            if (bc >= 0) { tx = me_.cand[bc].x; ty = me_.cand[bc].y; minc = bestv; dir = point + me_.cidx[bc]; if (dir >= np) dir -= np; }
+            have = 0; pending = 0;
+            if (next_last || (tx == cx && ty == cy)) {
+              pattern_stop = c_pat_stop[pat];
+              pat = c_pat_next[pat];
+              total = c_pat_n[pat];
+              next_last = 1; dir = 0; point = 0;
+            } else {
+              total = c_pat[pat][dir][3];
+              point = c_pat[pat][dir][2];
+              cx = tx; cy = ty;
+            }
+            if (pattern_stop == 1) {
+              const bool gt0 = (flags & JMB_EPZS_REF_GT0_FRAME) != 0;
+              if (gt0 && (4 * prev < minc || (3 * prev < minc && prev <= stop))) { exit_code = 4; phase = PH_DONE; continue; }      // :362-376
+              if (!(check_median && (jm_ref == 0 || minc < 2 * prev) && minc > ((3 * stop) >> 1) && (flags & JMB_EPZS_DUAL))) { phase = PH_DONE; continue; }   // :379-384
+              if ((tx == 0 && ty == 0) || (tx == sx && ty == sy))                                                        // :391-399
+                pat = (abs(tx - sx) < 10 && abs(ty - sy) < 10) ? JMB_EPZS_PAT_SDIAMOND : JMB_EPZS_PAT_SQUARE;
+              else pat = (pats >> 8) & 255;
+              cx = t2x; cy = t2y;
+              check_median = 0;
+              pattern_stop = 0; point = 0; next_last = 0; total = c_pat_n[pat]; dir = 0;
+            }
+          }
+          const int np = c_pat_n[pat];
+          int k = 0;
+          for (int l = 0; l < total; l++) {
+            int pi = point + l; if (pi >= np) pi -= np;
+            const int vx = cx + c_pat[pat][pi][0], vy = cy + c_pat[pat][pi][1];
+            if (in_range(vx, vy)) { me_.cand[k] = make_short2((short)vx, (short)vy); me_.cidx[k] = (unsigned char)l; k++; }
+          }
+          pending = 1;
+          if (k) { for (int c = 0; c < k; c++) tot[tid][c] = 0; me_.nc = (unsigned char)k; evals += k; posted = true; }
         }
       }
-    }
-    if (!exit_code) { if (q.jm_ref == 0 || prev > minc) prev = minc; exit_code = 5; }                    // :409-410
-    // empty the visited set for the next search of this warp
-    const int nt = __shfl_sync(0xffffffffu, vis.n, 0);
-    if (__shfl_sync(0xffffffffu, full, 0) && lane == 0) jmb_req_report(err, EPZS_ERR_FIELD, ri);      // (more positions than the set holds: never silently wrong)
-    if (nt > TCAP) { for (int i = lane; i < HS; i += 32) vis.tab[i] = 0; }
-    else for (int i = lane; i < nt; i += 32) vis.tab[ws.touched[i]] = 0;
-    __syncwarp();
-    if (lane == 0) {
-      jmb_epzs_res o;
-      o.mv_x = o.imv_x = (int16_t)tx; o.mv_y = o.imv_y = (int16_t)ty;
-      o.cost = o.icost = minc; o.prev_sad = prev; o.exit_code = exit_code; o.n_evals = evals;
-      res[ri] = o;
+      if (phase == PH_DONE) {
+        if (!exit_code) { if (jm_ref == 0 || prev > minc) prev = minc; exit_code = 5; }                                  // :409-410
+        if (full) jmb_req_report(err, EPZS_ERR_FIELD, base + tid);      // (more positions than the set holds: never silently wrong)
+        jmb_epzs_res o;
+        o.mv_x = o.imv_x = (int16_t)tx; o.mv_y = o.imv_y = (int16_t)ty;
+        o.cost = o.icost = minc; o.prev_sad = prev; o.exit_code = exit_code; o.n_evals = evals;
+        res[base + tid] = o;
+      }
     }
   }
 }
 
-// ---- sub-pel stage: BlockMotionSearch's gate (mv_search.c:964-976), then EPZS_sub_pel_motion_estimation (me_epzs_sub.c:30-213);
-// a second launch so that the Hadamard code's registers do not limit how many integer searches are in flight ----------------
-__global__ void __launch_bounds__(EW * 32, 3)
+// ---- sub-pel stage: BlockMotionSearch's gate (mv_search.c:964-976), then EPZS_sub_pel_motion_estimation (me_epzs_sub.c:30-213).
+// Same shape: EG searches per CTA, thread s directs search s through the four steps (half-pel diamond, its refinement towards
+// the second best, the same two at quarter-pel), all threads evaluate -- one 4x4 (or, with the 8x8 Hadamard, 8x8) sub-block of
+// one search per work item, walking that search's candidates of the step.
+struct SubS {
+  short pos_x, pos_y;
+  int first;
+  unsigned char blocktype, ref, t8, nc, nsub, nn, nsx, pad_;
+  short2 cand[5];
+};
+
+__global__ void __launch_bounds__(ET, JMB_EPZS_SUB_MINB)
 k_epzs_sub(const jmb_epzs_req *__restrict__ reqs, int n, jmb_epzs_res *__restrict__ res, const uint8_t *__restrict__ cur, int cur_pitch,
            const uint8_t *const *__restrict__ ref_planes, size_t plane_bytes, int ref_pitch, int w, int h, jmb_me_config me, int nref) {
-  __shared__ WarpS wss[EW];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WarpS &ws = wss[warp];
+  __shared__ SubS S[EG];
+  __shared__ int sums[EG][5];
+  __shared__ int s_first[EG + 1];
+  const int tid = threadIdx.x, base = blockIdx.x * EG, cnt = min(EG, n - base);
   const long long BIG = (long long)0x7fffffff << 5;
-  for (int ri = blockIdx.x * EW + warp; ri < n; ri += gridDim.x * EW) {
-    const jmb_epzs_req q = reqs[ri];
-    if (!(q.flags & JMB_EPZS_SUBPEL) || q.blocktype < 1 || q.blocktype > 7 || q.ref >= nref) continue;      // (rejected requests were reported by the integer stage)
-    const jmb_epzs_res r0 = res[ri];
-    if (r0.exit_code == 0 && !(q.flags & JMB_EPZS_SKIP_INT)) continue;                                        // integer stage did not run: rejected
-    const bool gt0 = (q.flags & JMB_EPZS_REF_GT0_FRAME) != 0;
-    long long minc = r0.icost;
-    if (!((q.flags & JMB_EPZS_SKIP_INT) || !gt0 || 2 * minc < 7 * r0.prev_sad)) continue;
-    Blk b{RefView{ref_planes[q.ref], plane_bytes, ref_pitch, w, h}, cur, cur_pitch, q.pos_x, q.pos_y, c_bsx[q.blocktype], c_bsy[q.blocktype]};
-    const int px = q.pred_x, py = q.pred_y;
-    int mvx = r0.imv_x, mvy = r0.imv_y, evals = r0.n_evals;
-    const int t8 = (q.flags & JMB_EPZS_TEST8X8) != 0;
-    const int max_pos2 = (!me.start_hp || !me.start_qp) ? max(1, me.search_pos2) : me.search_pos2;
-    int lam = q.lambda[1], best = 0, second_pos = 0;
-    long long second = BIG;
-    const long long sub_thr = q.subthres + 2ll * lam;
-    bool done = false;
-    if (!(q.flags & JMB_EPZS_SKIP_INT) && !me.start_hp) minc = BIG;
-    // one batch + replay; `wide`: the first loop of a stage (second-best tracking), else the refinement loop
-    auto stage = [&](int p0, int p1, int div, int metric, bool wide) {
-      const int nb = p1 - p0;
-      if (nb <= 0) return;
-      if (lane < nb) ws.mv[lane] = make_short2((short)(mvx + c_hp[p0 + lane][0] / div), (short)(mvy + c_hp[p0 + lane][1] / div));
-      __syncwarp();
-      eval_sub(b, ws, nb, metric, t8, lane);
-      evals += nb;
-      if (lane == 0)
-        for (int c = 0; c < nb; c++) {
-          const int pos = p0 + c;
-          long long mcost = mv_cost(lam, ws.mv[c].x, ws.mv[c].y, px, py);
-          if (wide) {
-            if (mcost < second) {
-              mcost += (long long)ws.dist[c] << 5;
-              if (mcost < minc) { second = minc; second_pos = best; minc = mcost; best = pos; }
-              else if (mcost < second) { second = mcost; second_pos = pos; }
-            }
-          } else if (mcost < minc) {
-            mcost += (long long)ws.dist[c] << 5;
-            if (mcost < minc) { minc = mcost; best = pos; }
-          }
-        }
-      __syncwarp();
-      best = __shfl_sync(0xffffffffu, best, 0); second_pos = __shfl_sync(0xffffffffu, second_pos, 0);
-      minc = shfl_ll(minc); second = shfl_ll(second);
-    };
-    stage(me.start_hp, min(5, max_pos2), 1, me.metric[1], true);                                       // me_epzs_sub.c:66-90
-    if (best == 0 && px == mvx && py == mvy && minc < sub_thr) done = true;                           // :92-95
-    if (!done) {
-      if (me.search_pos2 >= 9 && (best != 0 || (abs(px - mvx) + abs(py - mvy))))                       // :97-122
-        stage(c_ns[best][second_pos], c_ne[best][second_pos], 1, me.metric[1], false);
-      if (best) { mvx += c_hp[best][0]; mvy += c_hp[best][1]; }
-      const int end_pos = (minc < sub_thr) ? 1 : 5;                                                    // :135-170
-      second = BIG; best = 0;      // start_me_refinement_qp == 1 (checked by the host side); second_pos carries over as in JM
-      lam = q.lambda[2];
-      stage(me.start_qp, end_pos, 2, me.metric[2], true);
-      if (minc > sub_thr && (best != 0 || (abs(px - mvx) + abs(py - mvy))))                            // :173-200
-        stage(c_ns[best][second_pos], c_ne[best][second_pos], 2, me.metric[2], false);
-      if (best > 0) { mvx += c_hp[best][0] / 2; mvy += c_hp[best][1] / 2; }
+  bool live = false, done = false;
+  int px = 0, py = 0, mvx = 0, mvy = 0, evals = 0, lam = 0, lam_q = 0, best = 0, second_pos = 0, p0 = 0;
+  long long minc = 0, second = BIG, sub_thr = 0;
+  if (tid < cnt) {
+    const jmb_epzs_req q = reqs[base + tid];
+    SubS &me_ = S[tid];
+    me_.nc = 0; me_.nsub = 0; me_.blocktype = 7;
+    if ((q.flags & JMB_EPZS_SUBPEL) && q.blocktype >= 1 && q.blocktype <= 7 && q.ref < nref) {      // (rejected requests were reported by the integer stage)
+      const jmb_epzs_res r0 = res[base + tid];
+      const bool gt0 = (q.flags & JMB_EPZS_REF_GT0_FRAME) != 0, skip = (q.flags & JMB_EPZS_SKIP_INT) != 0;
+      if ((r0.exit_code != 0 || skip) && (skip || !gt0 || 2 * r0.icost < 7 * r0.prev_sad)) {      // mv_search.c:964-976
+        live = true;
+        me_.pos_x = q.pos_x; me_.pos_y = q.pos_y; me_.blocktype = q.blocktype; me_.ref = q.ref; me_.t8 = (q.flags & JMB_EPZS_TEST8X8) != 0;
+        px = q.pred_x; py = q.pred_y; mvx = r0.imv_x; mvy = r0.imv_y; evals = r0.n_evals; minc = r0.icost;
+        lam = q.lambda[1]; lam_q = q.lambda[2];
+        sub_thr = q.subthres + 2ll * lam;
+        if (!skip && !me.start_hp) minc = BIG;
+      }
     }
-    if (lane == 0) { res[ri].mv_x = (int16_t)mvx; res[ri].mv_y = (int16_t)mvy; res[ri].cost = minc; res[ri].n_evals = evals; }
   }
+  const int max_pos2 = (!me.start_hp || !me.start_qp) ? max(1, me.search_pos2) : me.search_pos2;
+
+#pragma unroll 1
+  for (int st = 0; st < 4; st++) {
+    const int metric = me.metric[1 + (st >> 1)], div = 1 + (st >> 1);
+    const bool wide = !(st & 1);
+    if (tid < cnt) {      // directors: the candidates of this step
+      SubS &me_ = S[tid];
+      int p1 = 0;
+      p0 = 0;
+      if (live && !done) {
+        if (st == 0) { p0 = me.start_hp; p1 = min(5, max_pos2); }                                                       // me_epzs_sub.c:66-90
+        else if (st == 1) { if (me.search_pos2 >= 9 && (best != 0 || (abs(px - mvx) + abs(py - mvy)))) { p0 = c_ns[best][second_pos]; p1 = c_ne[best][second_pos]; } }   // :97-122
+        else if (st == 2) { p0 = me.start_qp; p1 = (minc < sub_thr) ? 1 : 5; }                                          // :135-170
+        else if (minc > sub_thr && (best != 0 || (abs(px - mvx) + abs(py - mvy)))) { p0 = c_ns[best][second_pos]; p1 = c_ne[best][second_pos]; }               // :173-200
+      }
+      const int nb = max(0, p1 - p0);
+      for (int c = 0; c < nb; c++) { me_.cand[c] = make_short2((short)(mvx + c_hp[p0 + c][0] / div), (short)(mvy + c_hp[p0 + c][1] / div)); sums[tid][c] = 0; }
+      me_.nc = (unsigned char)nb;
+      const int nn = (metric == JMB_SATD && me_.t8) ? 8 : 4;
+      me_.nn = (unsigned char)nn; me_.nsx = (unsigned char)(c_bsx[me_.blocktype] / nn);
+      me_.nsub = nb ? (unsigned char)(me_.nsx * (c_bsy[me_.blocktype] / nn)) : 0;
+    }
+    __syncthreads();
+    if (tid == 0) { int f = 0; for (int i = 0; i < cnt; i++) { s_first[i] = f; f += S[i].nsub; } s_first[cnt] = f; }
+    __syncthreads();
+    const int nitems = s_first[cnt];
+    for (int item = tid; item < nitems; item += ET) {
+      int lo = 0, hi = cnt - 1;
+      while (lo < hi) { const int m = (lo + hi + 1) >> 1; if (s_first[m] <= item) lo = m; else hi = m - 1; }
+      while (s_first[lo + 1] == s_first[lo]) lo--;
+      const SubS &q = S[lo];
+      const int sb = item - s_first[lo], nn = q.nn, sbx = sb % q.nsx, sby = sb / q.nsx, nc = q.nc;
+      const RefView rv{ref_planes[q.ref], plane_bytes, ref_pitch, w, h};
+      SrcBlk src;
+      load_src(src, cur, cur_pitch, q.pos_x + sbx * nn, q.pos_y + sby * nn, nn);
+      const int bqx = q.pos_x << 2, bqy = q.pos_y << 2;
+      if (nn == 4) {
+        for (int c = 0; c < nc; c++) {
+          unsigned rw[4];
+          load_ref4(rv, bqx + q.cand[c].x, bqy + q.cand[c].y, sbx, sby, metric, rw);
+          atomicAdd(&sums[lo][c], dist4(src, rw, metric));
+        }
+      } else {
+        for (int c = 0; c < nc; c++) atomicAdd(&sums[lo][c], subblock_dist(rv, src, bqx + q.cand[c].x, bqy + q.cand[c].y, sbx, sby, 8, metric));
+      }
+    }
+    __syncthreads();
+    if (tid < cnt && live && !done) {      // directors: JM's sequential selection on the complete distortions
+      const SubS &me_ = S[tid];
+      const int nb = me_.nc;
+      evals += nb;
+      for (int c = 0; c < nb; c++) {
+        const int pos = p0 + c;
+        long long mcost = mv_cost32(lam, me_.cand[c].x, me_.cand[c].y, px, py);
+        if (wide) {
+          if (mcost < second) {
+            mcost += (long long)sums[tid][c] << 5;
+            if (mcost < minc) { second = minc; second_pos = best; minc = mcost; best = pos; }
+            else if (mcost < second) { second = mcost; second_pos = pos; }
+          }
+        } else if (mcost < minc) {
+          mcost += (long long)sums[tid][c] << 5;
+          if (mcost < minc) { minc = mcost; best = pos; }
+        }
+      }
+      if (st == 0 && best == 0 && px == mvx && py == mvy && minc < sub_thr) done = true;                               // :92-95
+      if (st == 1 && !done) {
+        if (best) { mvx += c_hp[best][0]; mvy += c_hp[best][1]; }
+        second = BIG; best = 0;      // start_me_refinement_qp == 1 (checked by the host side); second_pos carries over as in JM
+        lam = lam_q;
+      }
+      if (st == 3 && best > 0) { mvx += c_hp[best][0] / 2; mvy += c_hp[best][1] / 2; }
+    }
+  }
+  if (tid < cnt && live) { res[base + tid].mv_x = (int16_t)mvx; res[base + tid].mv_y = (int16_t)mvy; res[base + tid].cost = minc; res[base + tid].n_evals = evals; }
 }
 
 // requests of a whole picture for jmb_epzs_search_frame
@@ -438,32 +458,34 @@ __global__ void k_epzs_pack(const jmb_epzs_res *__restrict__ res, int n, jmb_epz
 
 }  // namespace
 
+// listed: the most predictors any of the searches lists (all four segments)
 static int epzs_launch(jmb_ctx *ctx, const jmb_epzs_req *d_reqs, int n, const int16_t *d_cands, int n_cands, jmb_epzs_res *d_res, int max_range,
-                       bool any_subpel) {
+                       bool any_subpel, int listed) {
   const jmb_ref &r0 = ctx->refs[ctx->ref_list[0]];
   const uint8_t *tab[JMB_MAX_REFS];
   for (int i = 0; i < JMB_MAX_REFS; i++) tab[i] = i < ctx->nref ? ctx->refs[ctx->ref_list[i]].planes : nullptr;
   int rc = jmb_reserve_dev(ctx, &ctx->d_reftab, &ctx->d_reftab_cap, sizeof(tab)); if (rc) return rc;
   JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_reftab, tab, sizeof(tab), cudaMemcpyHostToDevice, ctx->stream));
-  if (!ctx->epzs_grid[0]) {      // persistent warps: as many CTAs as fit the device at once
-    int sms = 148, per_sm = 1;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    JMB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_epzs_int, EW * 32, 0));
-    ctx->epzs_grid[0] = sms * max(1, per_sm);
-    JMB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_epzs_sub, EW * 32, 0));
-    ctx->epzs_grid[1] = sms * max(1, per_sm);
+  // the predictor-phase set of a search: power-of-two slots, filled to 3/4 at most (start mv + every listed predictor)
+  int hslots = 64;
+  while (hslots - hslots / 4 < listed + 1) hslots *= 2;
+  const size_t dyn = (size_t)EG * hslots * sizeof(unsigned);
+  if (dyn > 160 * 1024) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_epzs_search: %d predictors per search", listed);
+  if ((int)dyn > ctx->epzs_grid[0]) {      // (epzs_grid[0]: the dynamic shared memory k_epzs_int is opted in for on this device)
+    JMB_CUDA(ctx, cudaFuncSetAttribute(k_epzs_int, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    ctx->epzs_grid[0] = (int)dyn;
   }
-  const int blocks = (n + EW - 1) / EW;
+  const int blocks = (n + EG - 1) / EG;
   jmb_time_begin(ctx, JMB_K_EPZS);
-  k_epzs_int<<<min(blocks, ctx->epzs_grid[0]), EW * 32, 0, ctx->stream>>>(d_reqs, n, (const short2 *)d_cands, n_cands, d_res, ctx->cur, ctx->cur_pitch,
-                                                                           (const uint8_t *const *)ctx->d_reftab, r0.plane_bytes, r0.pitch, ctx->cur_w,
-                                                                           ctx->cur_h, ctx->nref, max_range, ctx->d_err);
+  k_epzs_int<<<blocks, ET, dyn, ctx->stream>>>(d_reqs, n, (const short2 *)d_cands, n_cands, d_res, ctx->cur, ctx->cur_pitch,
+                                               (const uint8_t *const *)ctx->d_reftab, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, ctx->nref,
+                                               max_range, hslots, ctx->d_err);
   jmb_time_end(ctx, JMB_K_EPZS);
   JMB_LAUNCH_CHECK(ctx);
   if (any_subpel) {
     jmb_time_begin(ctx, JMB_K_REFINE);      // reported as "subpel_refine", like the refinement that follows the full search
-    k_epzs_sub<<<min(blocks, ctx->epzs_grid[1]), EW * 32, 0, ctx->stream>>>(d_reqs, n, d_res, ctx->cur, ctx->cur_pitch, (const uint8_t *const *)ctx->d_reftab,
-                                                                             r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, ctx->me, ctx->nref);
+    k_epzs_sub<<<blocks, ET, 0, ctx->stream>>>(d_reqs, n, d_res, ctx->cur, ctx->cur_pitch, (const uint8_t *const *)ctx->d_reftab, r0.plane_bytes,
+                                               r0.pitch, ctx->cur_w, ctx->cur_h, ctx->me, ctx->nref);
     jmb_time_end(ctx, JMB_K_REFINE);
     JMB_LAUNCH_CHECK(ctx);
   }
@@ -487,10 +509,13 @@ int jmb_epzs_search(jmb_ctx *ctx, const jmb_epzs_req *reqs, int n, const int16_t
   JMB_CUDA(ctx, cudaSetDevice(ctx->device));
   const bool host = jmb_is_host(loc);
   const jmb_epzs_req *d_reqs = reqs; const int16_t *d_cands = cands; jmb_epzs_res *d_res = res;
-  int max_range = 4 * JMB_MAX_SEARCH_RANGE;
+  int max_range = 4 * JMB_MAX_SEARCH_RANGE, listed = 190;      // device-resident requests: lists of up to 190 predictors (longer ones are reported, never cut)
   if (host) {
-    max_range = 1;
-    for (int i = 0; i < n; i++) max_range = max(max_range, (int)max(reqs[i].range_x, reqs[i].range_y));
+    max_range = 1; listed = 0;
+    for (int i = 0; i < n; i++) {
+      max_range = max(max_range, (int)max(reqs[i].range_x, reqs[i].range_y));
+      listed = max(listed, reqs[i].n_cand[0] + reqs[i].n_cand[1] + reqs[i].n_cand[2] + reqs[i].n_cand[3]);
+    }
     if (max_range > 4 * JMB_MAX_SEARCH_RANGE) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_epzs_search: search range %d quarter-pel", max_range);
     const size_t rb = (size_t)n * sizeof(jmb_epzs_req), cb = (size_t)max(1, n_cands) * 4, ob = (size_t)n * sizeof(jmb_epzs_res);
     rc = jmb_reserve_dev(ctx, &ctx->d_stage, &ctx->d_stage_cap, rb); if (rc) return rc;
@@ -500,7 +525,7 @@ int jmb_epzs_search(jmb_ctx *ctx, const jmb_epzs_req *reqs, int n, const int16_t
     if (n_cands) JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage2, cands, (size_t)n_cands * 4, cudaMemcpyHostToDevice, ctx->stream));
     d_reqs = (const jmb_epzs_req *)ctx->d_stage; d_cands = (const int16_t *)ctx->d_stage2; d_res = (jmb_epzs_res *)ctx->d_stage5;
   } else max_range = 4 * ctx->me.search_range;      // device-resident requests: ranges are checked on the device against the configured one
-  rc = epzs_launch(ctx, d_reqs, n, d_cands, n_cands, d_res, max_range, true); if (rc) return rc;
+  rc = epzs_launch(ctx, d_reqs, n, d_cands, n_cands, d_res, max_range, true, listed); if (rc) return rc;
   if (host) {
     JMB_CUDA(ctx, cudaMemcpyAsync(res, d_res, (size_t)n * sizeof(jmb_epzs_res), cudaMemcpyDeviceToHost, ctx->stream));
     if (loc == JMB_HOST) return jmb_check_device_errors(ctx);
@@ -550,7 +575,7 @@ int jmb_epzs_search_frame(jmb_ctx *ctx, const jmb_mb_mvpred *pred, const int16_t
   k_gen_epzs<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_pred, n_mb, mb_w, *fp, d_reqs);
   jmb_time_end(ctx, JMB_K_GEN);
   JMB_LAUNCH_CHECK(ctx);
-  rc = epzs_launch(ctx, d_reqs, n, d_shared, n_cands, d_eres, fp->range, (fp->flags & JMB_EPZS_SUBPEL) != 0); if (rc) return rc;
+  rc = epzs_launch(ctx, d_reqs, n, d_shared, n_cands, d_eres, fp->range, (fp->flags & JMB_EPZS_SUBPEL) != 0, fp->n_shared + (fp->window ? 8 * fp->window - 1 : 0)); if (rc) return rc;
   jmb_me_res8 *d_out = res;
   if (host && res) {
     rc = jmb_reserve_dev(ctx, &ctx->d_res8, &ctx->d_res8_cap, (size_t)n * sizeof(jmb_me_res8)); if (rc) return rc;
