@@ -1,15 +1,11 @@
 // k_epzs.cu -- EPZS (SearchMode 3) on the device: EPZS_integer_motion_estimation (lencod/src/me_epzs_int.c:42-426) and
-// EPZS_sub_pel_motion_estimation (lencod/src/me_epzs_sub.c:30-213), one warp per search.
+// EPZS_sub_pel_motion_estimation (lencod/src/me_epzs_sub.c:30-213), one CTA per 41 searches (a macroblock's partitions).
 //
 // EPZS is a short, data-dependent walk: check the start mv, stop early against the previous distortions, check an ordered
 // predictor list, walk a refinement pattern until its centre wins (optionally again from the second-best predictor), then a
 // two-step half-/quarter-pel pattern.  10-60 distortions per block instead of the 4225 of the full search.  What is
-// data-parallel in it are the distortions of one step: the warp evaluates the candidates of a step TOGETHER (a candidate's
-// rows are split over 32 / n lanes and reduced by shuffle), then lane 0 replays JM's sequential selection on the complete
-// distortions -- JM's early-terminated distortion returns the threshold it was given (mv_search.h:19-23), which can never win
-// a strict '<', so complete sums decide alike.  JM's visited map (EPZSMap, stamped with BlkCount) is a per-warp bitmap in
-// shared memory (a small hash set of the positions around the start mv; only the slots a search filled are cleared before the
-// next one).  Warps are persistent: each walks requests warp, warp + #warps, ...  The sub-pel stage is a second launch.
+// data-parallel in it are the distortions of one step -- and the 41 searches of a macroblock, which are independent once
+// their predictors are given: the CTA advances all of them round by round (see k_epzs_int).  The sub-pel stage is a second launch.
 #include "jmb_dist_dev.cuh"
 
 namespace {
@@ -18,7 +14,7 @@ constexpr int EG = 41;         // searches per CTA: consecutive requests (one ma
 constexpr int ET = 128;        // threads per CTA
 constexpr int CB = 32;         // candidates a search puts up per round
 #ifndef JMB_EPZS_SUB_MINB
-#define JMB_EPZS_SUB_MINB 4
+#define JMB_EPZS_SUB_MINB 8
 #endif
 #ifndef JMB_EPZS_INT_MINB
 #define JMB_EPZS_INT_MINB 6
@@ -50,7 +46,7 @@ __device__ __forceinline__ unsigned mv_cost32(int lam, int vx, int vy, int px, i
 
 enum { EPZS_ERR_FIELD = 512 };      // a request field out of range (reported through d_err like the JMB_REQERR_* codes)
 
-__device__ __forceinline__ int epzs_check(const jmb_epzs_req &q, int w, int h, int nref, int n_cands, int max_range, int hcap) {
+__device__ __forceinline__ int epzs_check(const jmb_epzs_req &q, int w, int h, int nref, int n_cands, int max_range) {
   if (q.blocktype < 1 || q.blocktype > 7) return JMB_REQERR_BLOCKTYPE;
   const int bsx = c_bsx[q.blocktype], bsy = c_bsy[q.blocktype];
   int e = 0;
@@ -61,10 +57,9 @@ __device__ __forceinline__ int epzs_check(const jmb_epzs_req &q, int w, int h, i
   if (q.stop < 0 || q.stop > lim || q.medthres < 0 || q.medthres > lim || q.prev_sad < 0 || q.prev_sad > lim || q.subthres < 0 ||
       q.subthres > lim || q.min_mcost < 0 || q.min_mcost > lim) e |= JMB_REQERR_MINCOST;
   const int tot = q.n_cand[0] + q.n_cand[1] + ((q.flags & JMB_EPZS_WINDOW_GEN) ? 0 : q.n_cand[2]) + q.n_cand[3];
-  const int listed = q.n_cand[0] + q.n_cand[1] + q.n_cand[2] + q.n_cand[3];
   if (q.pattern > 5 || q.pattern_dual > 5 || q.range_x < 1 || q.range_y < 1 || q.range_x > max_range || q.range_y > max_range ||
       q.cand_off < 0 || q.cand_off + tot > n_cands || ((q.flags & JMB_EPZS_TEST8X8) && q.blocktype > 4) ||
-      ((q.flags & JMB_EPZS_WINDOW_GEN) && q.n_cand[2] > 63) || (!(q.flags & JMB_EPZS_SKIP_INT) && listed + 1 > hcap)) e |= EPZS_ERR_FIELD;
+      ((q.flags & JMB_EPZS_WINDOW_GEN) && q.n_cand[2] > 63)) e |= EPZS_ERR_FIELD;
   return e;
 }
 
@@ -75,9 +70,12 @@ __device__ __forceinline__ int epzs_check(const jmb_epzs_req &q, int w, int h, i
 // 41 partitions are 112 of them), walking that search's candidates and adding mv cost + (SAD << 5) into tot[search][candidate]
 // -- and the directors read the totals.  JM's early-terminated distortion returns the bound it was given (mv_search.h:19-23),
 // which can never win a strict '<', so complete sums decide alike.
-// JM's visited map (EPZSMap) is needed for one thing only: a predictor list that repeats a position (or the start mv) must not
-// count it twice in the best / second-best pair -- a small hash set per search, filled while the list is read.  The pattern
-// walk needs none: a position met again costs at least the current minimum (which only falls), and only a strict '<' moves.
+// JM's visited map (EPZSMap) is not needed.  A position met again costs what it cost before, which is at least the current
+// minimum (the minimum only falls), and only a strict '<' moves the minimum: the pattern walk decides alike with or without
+// the map.  In the predictor list a repeated position could do one thing only -- enter the best / second-best pair a second
+// time, as the second best behind itself -- and that is the one case the merge below excludes (a candidate equal to the
+// current best is passed over; one that was second best, or neither, fails both '<' on its own).  Repeats cost a few
+// redundant distortions (n_evals counts them) and nothing else.
 struct IntS {
   short pos_x, pos_y, px, py;
   int lam, first;                 // first: index of the search's first 4x4 block among the CTA's
@@ -89,28 +87,24 @@ struct IntS {
 __global__ void __launch_bounds__(ET, JMB_EPZS_INT_MINB)
 k_epzs_int(const jmb_epzs_req *__restrict__ reqs, int n, const short2 *__restrict__ cands, int n_cands, jmb_epzs_res *__restrict__ res,
            const uint8_t *__restrict__ cur, int cur_pitch, const uint8_t *const *__restrict__ ref_planes, size_t plane_bytes, int ref_pitch,
-           int w, int h, int nref, int max_range, int hslots, int *__restrict__ err) {
+           int w, int h, int nref, int max_range, int *__restrict__ err) {
   __shared__ IntS S[EG];
-  __shared__ int tot[EG][CB];
+  __shared__ int tot[EG][CB + 1];      // (+1: the directors read their rows side by side)
   __shared__ int s_first[EG + 1];
-  extern __shared__ unsigned hset[];      // [EG][hslots]: positions (relative to the start mv) the predictor list has named, 0 = empty
   const int tid = threadIdx.x, base = blockIdx.x * EG, cnt = min(EG, n - base);
   const long long BIG = (long long)0x7fffffff << 5;      // DISTBLK_MAX
   enum { PH_START, PH_PRED, PH_PAT, PH_DONE };
   int phase = PH_DONE;
   // director state
-  int sx = 0, sy = 0, rx = 0, ry = 0, tx = 0, ty = 0, t2x = 0, t2y = 0, check_median = 0, exit_code = 0, evals = 0, seg = 0, i0 = 0, off = 0, nset = 0, full = 0;
+  int sx = 0, sy = 0, rx = 0, ry = 0, tx = 0, ty = 0, t2x = 0, t2y = 0, check_median = 0, exit_code = 0, evals = 0, seg = 0, i0 = 0, off = 0;
   int pat = 0, cx = 0, cy = 0, point = 0, total = 0, next_last = 0, pattern_stop = 0, dir = 0, pending = 0;
   unsigned flags = 0, ncw = 0, gtw = 0, jm_ref = 0, pats = 0;
   long long minc = 0, second = 0, prev = 0, med = 0, stop = 0, ld = 0, centre_cost = 0;
-  unsigned *const hs = hset + (size_t)tid * hslots;
-
-  for (int i = tid; i < cnt * hslots; i += ET) hset[i] = 0;
   if (tid < cnt) {
     const jmb_epzs_req q = reqs[base + tid];
     IntS &me_ = S[tid];
     me_.nc = 0; me_.first = 0; me_.lbx = 0; me_.blocktype = 7;
-    const int bad = epzs_check(q, w, h, nref, n_cands, max_range, hslots - hslots / 4);
+    const int bad = epzs_check(q, w, h, nref, n_cands, max_range);
     jmb_epzs_res o;
     o.mv_x = o.imv_x = q.start_x; o.mv_y = o.imv_y = q.start_y; o.cost = o.icost = q.min_mcost; o.prev_sad = q.prev_sad; o.exit_code = 0; o.n_evals = 0;
     if (bad) { jmb_req_report(err, bad, base + tid); res[base + tid] = o; }
@@ -136,24 +130,16 @@ k_epzs_int(const jmb_epzs_req *__restrict__ reqs, int n, const short2 *__restric
   __syncthreads();
   const int nblk = s_first[cnt];
   auto in_range = [&](int vx, int vy) { return abs(vx - sx) <= rx && abs(vy - sy) <= ry; };
-  // claims (dx, dy) in the search's set: true if it was not there
-  auto claim = [&](int dx, int dy) -> bool {
-    const unsigned k = (((unsigned)(dy + 2048) << 16) | (unsigned)(dx + 2048)) + 1u;
-    for (unsigned sl = (k * 2654435761u) >> 8;; sl++) {
-      sl &= (unsigned)hslots - 1u;
-      const unsigned v = hs[sl];
-      if (v == k) return false;
-      if (!v) { if (nset >= hslots - hslots / 4) { full = 1; return false; } hs[sl] = k; nset++; return true; }
-    }
-  };
+  // the search a 4x4 block belongs to: the last one whose first block is <= item (searches without blocks share a first index with
+  // the next one that has some).  The thread's first block is the same in every round (a macroblock has 112 of them).
+  auto owner_of = [&](int item) { int lo = 0, hi = cnt - 1; while (lo < hi) { const int m = (lo + hi + 1) >> 1; if (s_first[m] <= item) lo = m; else hi = m - 1; } return lo; };
+  const int lo0 = tid < nblk ? owner_of(tid) : 0;
 
   for (;;) {
     if (!__syncthreads_or(phase != PH_DONE)) break;
     // ---- everybody: the distortions of what was put up ----
     for (int item = tid; item < nblk; item += ET) {
-      int lo = 0, hi = cnt - 1;                        // last search whose first block is <= item (searches without blocks share a first index: skip them)
-      while (lo < hi) { const int m = (lo + hi + 1) >> 1; if (s_first[m] <= item) lo = m; else hi = m - 1; }
-      while (s_first[lo + 1] == s_first[lo]) lo--;
+      const int lo = item == tid ? lo0 : owner_of(item);
       const IntS &q = S[lo];
       const int nc = q.nc;
       if (!nc) continue;
@@ -167,8 +153,7 @@ k_epzs_int(const jmb_epzs_req *__restrict__ reqs, int n, const short2 *__restric
       for (int c = 0; c < nc; c++) {
         const short2 v = q.cand[c];
         const uint8_t *rp = umv(rv, bqy + v.y, bqx + v.x) + boff;      // computeSAD (me_distortion.c:349): the PARTITION origin is clamped
-        unsigned d = __vsadu4(s0, ld4(rp)) + __vsadu4(s1, ld4(rp + ref_pitch)) + __vsadu4(s2, ld4(rp + 2 * (size_t)ref_pitch)) + __vsadu4(s3, ld4(rp + 3 * (size_t)ref_pitch));
-        d <<= 5;
+        unsigned d = (__vsadu4(s0, ld4(rp)) + __vsadu4(s1, ld4(rp + ref_pitch)) + __vsadu4(s2, ld4(rp + 2 * (size_t)ref_pitch)) + __vsadu4(s3, ld4(rp + 3 * (size_t)ref_pitch))) << 5;
         if (blk == 0) d += mv_cost32(q.lam, v.x, v.y, q.px, q.py);
         atomicAdd(&tot[lo][c], (int)d);
       }
@@ -190,7 +175,6 @@ k_epzs_int(const jmb_epzs_req *__restrict__ reqs, int n, const short2 *__restric
           else if (minc < (stop >> 1)) { if (jm_ref == 0 || prev > minc) prev = minc; exit_code = 2; phase = PH_DONE; } // :135-150
           else {
             second = BIG; centre_cost = minc;      // JM runs the predictor generators (and their gates) before it checks any predictor
-            claim(0, 0);
             seg = 0; i0 = 0; have = 0; phase = PH_PRED;
           }
         } else if (phase == PH_PRED) {
@@ -198,6 +182,7 @@ k_epzs_int(const jmb_epzs_req *__restrict__ reqs, int n, const short2 *__restric
           for (int c = 0; c < have; c++) {
             const long long v = (unsigned)tot[tid][c];
             const short2 m = me_.cand[c];
+            if (m.x == tx && m.y == ty) continue;      // the current best named again (see above)
             if (v < minc) { second = minc; t2x = tx; t2y = ty; minc = v; tx = m.x; ty = m.y; check_median = 1; }
             else if (v < second) { second = v; t2x = m.x; t2y = m.y; check_median = 1; }
           }
@@ -214,7 +199,7 @@ k_epzs_int(const jmb_epzs_req *__restrict__ reqs, int n, const short2 *__restric
                 const int rings = (ns + 8) >> 3, spc = rx >> (rings - 1 - (i >> 3));
                 v = make_short2((short)(sx + c_ring[i & 7][0] * spc), (short)(sy + c_ring[i & 7][1] * spc));
               } else v = cands[off + i];
-              if (in_range(v.x, v.y) && claim(v.x - sx, v.y - sy)) me_.cand[k++] = v;
+              if (in_range(v.x, v.y)) me_.cand[k++] = v;
             }
             i0 += nb;
           }
@@ -277,7 +262,6 @@ k_epzs_int(const jmb_epzs_req *__restrict__ reqs, int n, const short2 *__restric
       }
       if (phase == PH_DONE) {
         if (!exit_code) { if (jm_ref == 0 || prev > minc) prev = minc; exit_code = 5; }                                  // :409-410
-        if (full) jmb_req_report(err, EPZS_ERR_FIELD, base + tid);      // (more positions than the set holds: never silently wrong)
         jmb_epzs_res o;
         o.mv_x = o.imv_x = (int16_t)tx; o.mv_y = o.imv_y = (int16_t)ty;
         o.cost = o.icost = minc; o.prev_sad = prev; o.exit_code = exit_code; o.n_evals = evals;
@@ -295,6 +279,7 @@ struct SubS {
   short pos_x, pos_y;
   int first;
   unsigned char blocktype, ref, t8, nc, nsub, nn, nsx, pad_;
+  short nitems, pad2_;
   short2 cand[5];
 };
 
@@ -303,7 +288,6 @@ k_epzs_sub(const jmb_epzs_req *__restrict__ reqs, int n, jmb_epzs_res *__restric
            const uint8_t *const *__restrict__ ref_planes, size_t plane_bytes, int ref_pitch, int w, int h, jmb_me_config me, int nref) {
   __shared__ SubS S[EG];
   __shared__ int sums[EG][5];
-  __shared__ int s_first[EG + 1];
   const int tid = threadIdx.x, base = blockIdx.x * EG, cnt = min(EG, n - base);
   const long long BIG = (long long)0x7fffffff << 5;
   bool live = false, done = false;
@@ -312,7 +296,7 @@ k_epzs_sub(const jmb_epzs_req *__restrict__ reqs, int n, jmb_epzs_res *__restric
   if (tid < cnt) {
     const jmb_epzs_req q = reqs[base + tid];
     SubS &me_ = S[tid];
-    me_.nc = 0; me_.nsub = 0; me_.blocktype = 7;
+    me_.nc = 0; me_.nsub = 0; me_.nitems = 0; me_.blocktype = 7;
     if ((q.flags & JMB_EPZS_SUBPEL) && q.blocktype >= 1 && q.blocktype <= 7 && q.ref < nref) {      // (rejected requests were reported by the integer stage)
       const jmb_epzs_res r0 = res[base + tid];
       const bool gt0 = (q.flags & JMB_EPZS_REF_GT0_FRAME) != 0, skip = (q.flags & JMB_EPZS_SKIP_INT) != 0;
@@ -348,17 +332,19 @@ k_epzs_sub(const jmb_epzs_req *__restrict__ reqs, int n, jmb_epzs_res *__restric
       const int nn = (metric == JMB_SATD && me_.t8) ? 8 : 4;
       me_.nn = (unsigned char)nn; me_.nsx = (unsigned char)(c_bsx[me_.blocktype] / nn);
       me_.nsub = nb ? (unsigned char)(me_.nsx * (c_bsy[me_.blocktype] / nn)) : 0;
+      me_.nitems = (short)(nn == 8 ? me_.nsub * nb : me_.nsub);
     }
     __syncthreads();
-    if (tid == 0) { int f = 0; for (int i = 0; i < cnt; i++) { s_first[i] = f; f += S[i].nsub; } s_first[cnt] = f; }
-    __syncthreads();
-    const int nitems = s_first[cnt];
-    for (int item = tid; item < nitems; item += ET) {
-      int lo = 0, hi = cnt - 1;
-      while (lo < hi) { const int m = (lo + hi + 1) >> 1; if (s_first[m] <= item) lo = m; else hi = m - 1; }
-      while (s_first[lo + 1] == s_first[lo]) lo--;
+    // work items: a 4x4 sub-block walks its search's candidates; an 8x8 one (a Hadamard of 64 differences) takes one candidate per
+    // item.  An item finds its search by adding up the searches' item counts (41 broadcast reads at most; a prefix array would cost
+    // a barrier more).
+    for (int item = tid;; item += ET) {
+      int lo = 0, f = 0;
+      for (; lo < cnt; lo++) { const int ni = S[lo].nitems; if (item < f + ni) break; f += ni; }
+      if (lo == cnt) break;
       const SubS &q = S[lo];
-      const int sb = item - s_first[lo], nn = q.nn, sbx = sb % q.nsx, sby = sb / q.nsx, nc = q.nc;
+      const int nn = q.nn, nc = q.nc, it = item - f, c8 = nn == 8 ? it / q.nsub : 0, sb = nn == 8 ? it - c8 * q.nsub : it;
+      const int sbx = sb % q.nsx, sby = sb / q.nsx;
       const RefView rv{ref_planes[q.ref], plane_bytes, ref_pitch, w, h};
       SrcBlk src;
       load_src(src, cur, cur_pitch, q.pos_x + sbx * nn, q.pos_y + sby * nn, nn);
@@ -369,9 +355,7 @@ k_epzs_sub(const jmb_epzs_req *__restrict__ reqs, int n, jmb_epzs_res *__restric
           load_ref4(rv, bqx + q.cand[c].x, bqy + q.cand[c].y, sbx, sby, metric, rw);
           atomicAdd(&sums[lo][c], dist4(src, rw, metric));
         }
-      } else {
-        for (int c = 0; c < nc; c++) atomicAdd(&sums[lo][c], subblock_dist(rv, src, bqx + q.cand[c].x, bqy + q.cand[c].y, sbx, sby, 8, metric));
-      }
+      } else atomicAdd(&sums[lo][c8], subblock_dist(rv, src, bqx + q.cand[c8].x, bqy + q.cand[c8].y, sbx, sby, 8, metric));
     }
     __syncthreads();
     if (tid < cnt && live && !done) {      // directors: JM's sequential selection on the complete distortions
@@ -458,28 +442,18 @@ __global__ void k_epzs_pack(const jmb_epzs_res *__restrict__ res, int n, jmb_epz
 
 }  // namespace
 
-// listed: the most predictors any of the searches lists (all four segments)
 static int epzs_launch(jmb_ctx *ctx, const jmb_epzs_req *d_reqs, int n, const int16_t *d_cands, int n_cands, jmb_epzs_res *d_res, int max_range,
-                       bool any_subpel, int listed) {
+                       bool any_subpel) {
   const jmb_ref &r0 = ctx->refs[ctx->ref_list[0]];
   const uint8_t *tab[JMB_MAX_REFS];
   for (int i = 0; i < JMB_MAX_REFS; i++) tab[i] = i < ctx->nref ? ctx->refs[ctx->ref_list[i]].planes : nullptr;
   int rc = jmb_reserve_dev(ctx, &ctx->d_reftab, &ctx->d_reftab_cap, sizeof(tab)); if (rc) return rc;
   JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_reftab, tab, sizeof(tab), cudaMemcpyHostToDevice, ctx->stream));
-  // the predictor-phase set of a search: power-of-two slots, filled to 3/4 at most (start mv + every listed predictor)
-  int hslots = 64;
-  while (hslots - hslots / 4 < listed + 1) hslots *= 2;
-  const size_t dyn = (size_t)EG * hslots * sizeof(unsigned);
-  if (dyn > 160 * 1024) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_epzs_search: %d predictors per search", listed);
-  if ((int)dyn > ctx->epzs_grid[0]) {      // (epzs_grid[0]: the dynamic shared memory k_epzs_int is opted in for on this device)
-    JMB_CUDA(ctx, cudaFuncSetAttribute(k_epzs_int, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    ctx->epzs_grid[0] = (int)dyn;
-  }
   const int blocks = (n + EG - 1) / EG;
   jmb_time_begin(ctx, JMB_K_EPZS);
-  k_epzs_int<<<blocks, ET, dyn, ctx->stream>>>(d_reqs, n, (const short2 *)d_cands, n_cands, d_res, ctx->cur, ctx->cur_pitch,
+  k_epzs_int<<<blocks, ET, 0, ctx->stream>>>(d_reqs, n, (const short2 *)d_cands, n_cands, d_res, ctx->cur, ctx->cur_pitch,
                                                (const uint8_t *const *)ctx->d_reftab, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, ctx->nref,
-                                               max_range, hslots, ctx->d_err);
+                                               max_range, ctx->d_err);
   jmb_time_end(ctx, JMB_K_EPZS);
   JMB_LAUNCH_CHECK(ctx);
   if (any_subpel) {
@@ -509,13 +483,10 @@ int jmb_epzs_search(jmb_ctx *ctx, const jmb_epzs_req *reqs, int n, const int16_t
   JMB_CUDA(ctx, cudaSetDevice(ctx->device));
   const bool host = jmb_is_host(loc);
   const jmb_epzs_req *d_reqs = reqs; const int16_t *d_cands = cands; jmb_epzs_res *d_res = res;
-  int max_range = 4 * JMB_MAX_SEARCH_RANGE, listed = 190;      // device-resident requests: lists of up to 190 predictors (longer ones are reported, never cut)
+  int max_range = 4 * JMB_MAX_SEARCH_RANGE;
   if (host) {
-    max_range = 1; listed = 0;
-    for (int i = 0; i < n; i++) {
-      max_range = max(max_range, (int)max(reqs[i].range_x, reqs[i].range_y));
-      listed = max(listed, reqs[i].n_cand[0] + reqs[i].n_cand[1] + reqs[i].n_cand[2] + reqs[i].n_cand[3]);
-    }
+    max_range = 1;
+    for (int i = 0; i < n; i++) max_range = max(max_range, (int)max(reqs[i].range_x, reqs[i].range_y));
     if (max_range > 4 * JMB_MAX_SEARCH_RANGE) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_epzs_search: search range %d quarter-pel", max_range);
     const size_t rb = (size_t)n * sizeof(jmb_epzs_req), cb = (size_t)max(1, n_cands) * 4, ob = (size_t)n * sizeof(jmb_epzs_res);
     rc = jmb_reserve_dev(ctx, &ctx->d_stage, &ctx->d_stage_cap, rb); if (rc) return rc;
@@ -525,7 +496,7 @@ int jmb_epzs_search(jmb_ctx *ctx, const jmb_epzs_req *reqs, int n, const int16_t
     if (n_cands) JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage2, cands, (size_t)n_cands * 4, cudaMemcpyHostToDevice, ctx->stream));
     d_reqs = (const jmb_epzs_req *)ctx->d_stage; d_cands = (const int16_t *)ctx->d_stage2; d_res = (jmb_epzs_res *)ctx->d_stage5;
   } else max_range = 4 * ctx->me.search_range;      // device-resident requests: ranges are checked on the device against the configured one
-  rc = epzs_launch(ctx, d_reqs, n, d_cands, n_cands, d_res, max_range, true, listed); if (rc) return rc;
+  rc = epzs_launch(ctx, d_reqs, n, d_cands, n_cands, d_res, max_range, true); if (rc) return rc;
   if (host) {
     JMB_CUDA(ctx, cudaMemcpyAsync(res, d_res, (size_t)n * sizeof(jmb_epzs_res), cudaMemcpyDeviceToHost, ctx->stream));
     if (loc == JMB_HOST) return jmb_check_device_errors(ctx);
@@ -575,7 +546,7 @@ int jmb_epzs_search_frame(jmb_ctx *ctx, const jmb_mb_mvpred *pred, const int16_t
   k_gen_epzs<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_pred, n_mb, mb_w, *fp, d_reqs);
   jmb_time_end(ctx, JMB_K_GEN);
   JMB_LAUNCH_CHECK(ctx);
-  rc = epzs_launch(ctx, d_reqs, n, d_shared, n_cands, d_eres, fp->range, (fp->flags & JMB_EPZS_SUBPEL) != 0, fp->n_shared + (fp->window ? 8 * fp->window - 1 : 0)); if (rc) return rc;
+  rc = epzs_launch(ctx, d_reqs, n, d_shared, n_cands, d_eres, fp->range, (fp->flags & JMB_EPZS_SUBPEL) != 0); if (rc) return rc;
   jmb_me_res8 *d_out = res;
   if (host && res) {
     rc = jmb_reserve_dev(ctx, &ctx->d_res8, &ctx->d_res8_cap, (size_t)n * sizeof(jmb_me_res8)); if (rc) return rc;
