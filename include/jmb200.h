@@ -303,6 +303,43 @@ int jmb_epzs_search_frame(jmb_ctx *ctx, const jmb_mb_mvpred *pred, const int16_t
 int jmb_mb_surfaces(jmb_ctx *ctx, int ref, int mb_x, int mb_y, int center_x, int center_y, int radius);
 int jmb_mb_search(jmb_ctx *ctx, const jmb_me_req *req, jmb_me_res *res);
 
+/* jmb_mb_chain: up to JMB_CHAIN_MAX searches of ONE macroblock and ONE reference over the resident surfaces in one synchronous
+ * call, where later searches take their motion-vector predictor from earlier ones -- what PartitionMotionSearch /
+ * SubPartitionMotionSearch do block after block (lencod/src/mv_search.c:1560-1850).  Per search the device does what
+ * BlockMotionSearch does (mv_search.c:858-1024): GetMVPredictor from the three neighbours (lcommon/src/mv_prediction.c:192-300,
+ * non-MBAFF; the caller resolves get_neighbors, macroblock.c, incl. the C -> D replacement) -> search centre (FULL: the
+ * predictor rounded to integer pels, :931-934, clipped to the mv range, :957; FAST_FULL: req.center) -> IntPelME -> SubPelME
+ * (JMB_REQ_SUBPEL) -> clip_mv_range (:981); the clipped mv is what later searches of the chain see at that position
+ * (set_me_parameters, mv_search.c:100).  A neighbour is either given (mv, ref_idx as they stand in enc_picture->mv_info) or
+ * names an earlier search of the same chain (dep); searches with different chain ids are independent and run side by side.
+ * req.pred_x/y (and, for FULL, req.center) are outputs here: the result echoes what the device derived, so that a caller who
+ * ran ahead of JM's own call sequence can check each answer against the predictor JM computes when it gets there.
+ * status: DONE; UNCOVERED = the search window leaves the resident surfaces (not searched; use jmb_me_search);
+ * SKIPPED = a search it depends on was not done. */
+#define JMB_CHAIN_MAX 16
+enum { JMB_CHAIN_DONE = 0, JMB_CHAIN_UNCOVERED = 1, JMB_CHAIN_SKIPPED = 2 };
+typedef struct jmb_chain_nb {      /* 8 bytes: one neighbour (A, B or C) of a block */
+  int16_t mv_x, mv_y;              /* mv_info[pos_y][pos_x].mv[list] */
+  int8_t ref_idx;                  /* mv_info[pos_y][pos_x].ref_idx[list] (for dep >= 0: the reference being searched) */
+  int8_t available;                /* PixelPos.available */
+  int8_t dep;                      /* -1, or the index (in this call) of the earlier search whose block covers the position */
+  int8_t pad_;
+} jmb_chain_nb;
+typedef struct jmb_chain_req {     /* 72 bytes */
+  jmb_me_req req;
+  jmb_chain_nb nb[3];              /* A (left), B (up), C (up-right, or D where JM substitutes it) */
+  int8_t jm_ref;                   /* ref_frame GetMVPredictor compares the neighbours' ref_idx with */
+  int8_t chain;                    /* chain id, 0 .. (number of chains - 1); the searches of a chain appear in order */
+  int8_t pad_[6];
+} jmb_chain_req;
+typedef struct jmb_chain_res {     /* 40 bytes */
+  jmb_me_res res;
+  int16_t pred_x, pred_y, center_x, center_y;
+  int32_t status, pad_;
+} jmb_chain_res;
+/* mv_limits = {MaxHmvR[4], MaxHmvR[5], MaxVmvR[4], MaxVmvR[5]} (quarter-pel); int_divide = JM_INT_DIVIDE (lencod/inc/defines.h) */
+int jmb_mb_chain(jmb_ctx *ctx, const jmb_chain_req *reqs, int n, const int32_t mv_limits[4], int int_divide, jmb_chain_res *res);
+
 /* BlockSAD surfaces of one macroblock exactly as setup_fast_full_search leaves them:
  * out[(blocktype*16 + slot) * max_pos + pos], blocktype 1..7, uint32 (distpel), spiral order.
  * (lencod/src/me_fullfast.c:59-81 allocation, :492-556, :196-260) */

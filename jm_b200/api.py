@@ -23,6 +23,10 @@ ME_REQ = np.dtype([("pos_x", "<i2"), ("pos_y", "<i2"), ("pred_x", "<i2"), ("pred
                    ("center_x", "<i2"), ("center_y", "<i2"), ("blocktype", "u1"), ("ref", "u1"),
                    ("mode", "u1"), ("flags", "u1"), ("lambda", "<i4", (3,)), ("pad_", "<i4"), ("min_mcost", "<i8")])
 ME_RES = np.dtype([("mv_x", "<i2"), ("mv_y", "<i2"), ("imv_x", "<i2"), ("imv_y", "<i2"), ("cost", "<i8"), ("icost", "<i8")])
+CHAIN_NB = np.dtype([("mv_x", "<i2"), ("mv_y", "<i2"), ("ref_idx", "i1"), ("available", "i1"), ("dep", "i1"), ("pad_", "i1")])
+CHAIN_REQ = np.dtype([("req", ME_REQ), ("nb", CHAIN_NB, (3,)), ("jm_ref", "i1"), ("chain", "i1"), ("pad_", "i1", (6,))])
+CHAIN_RES = np.dtype([("res", ME_RES), ("pred_x", "<i2"), ("pred_y", "<i2"), ("center_x", "<i2"), ("center_y", "<i2"), ("status", "<i4"), ("pad_", "<i4")])
+CHAIN_DONE, CHAIN_UNCOVERED, CHAIN_SKIPPED = range(3)
 MB_PRED = np.dtype([("mv", "<i2", (16, 2)), ("b8mode", "u1", (4,)), ("ref", "u1", (4,))])
 QUANT_DESC = np.dtype([("n", "<i4"), ("qp", "<i4"), ("is_cavlc", "<i4"), ("around", "<i4"), ("adapt_rnd_weight", "<i4"),
                        ("qparams", "<i4", (64, 3)), ("scan", "u1", (64, 2)), ("c_cost", "u1", (64,))])
@@ -121,6 +125,7 @@ def load_library():
     L.jmb_chroma_residual_coding.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp, vp, vp, i]
     L.jmb_mb_surfaces.argtypes = [vp, i, i, i, i, i, i]
     L.jmb_mb_search.argtypes = [vp, vp, vp]
+    L.jmb_mb_chain.argtypes = [vp, vp, i, vp, i, vp]
     L.jmb_epzs_search.argtypes = [vp, vp, i, vp, i, vp, i]
     L.jmb_epzs_search_frame.argtypes = [vp, vp, vp, i, vp, vp, i]
     L.jmb_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
@@ -437,6 +442,13 @@ class Context:
         res = np.zeros(1, ME_RES)
         self._ck(self.L.jmb_mb_search(self.h, _ptr(req), _ptr(res)))
         return res[0]
+
+    def mb_chain(self, reqs, mv_limits, int_divide=1):
+        reqs = np.ascontiguousarray(reqs, CHAIN_REQ)
+        res = np.zeros(len(reqs), CHAIN_RES)
+        lim = np.ascontiguousarray(mv_limits, np.int32)
+        self._ck(self.L.jmb_mb_chain(self.h, _ptr(reqs), len(reqs), _ptr(lim), int_divide, _ptr(res)))
+        return res
 
     def block_distortion(self, metric, n, diff, thres=None):
         diff = np.ascontiguousarray(diff, np.int16).reshape(-1, n * n)

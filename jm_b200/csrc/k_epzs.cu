@@ -278,8 +278,8 @@ k_epzs_int(const jmb_epzs_req *__restrict__ reqs, int n, const short2 *__restric
 struct SubS {
   short pos_x, pos_y;
   int first;
-  unsigned char blocktype, ref, t8, nc, nsub, nn, nsx, pad_;
-  short nitems, pad2_;
+  unsigned char blocktype, ref, t8, nc, nsub, nn, nsx, lsx;      // nsub = sub-blocks (a power of two), nsx per row = 1 << lsx
+  short nitems; unsigned char lsub, pad_;
   short2 cand[5];
 };
 
@@ -288,6 +288,7 @@ k_epzs_sub(const jmb_epzs_req *__restrict__ reqs, int n, jmb_epzs_res *__restric
            const uint8_t *const *__restrict__ ref_planes, size_t plane_bytes, int ref_pitch, int w, int h, jmb_me_config me, int nref) {
   __shared__ SubS S[EG];
   __shared__ int sums[EG][5];
+  __shared__ int s_pre[ET / 32][EG + 24];
   const int tid = threadIdx.x, base = blockIdx.x * EG, cnt = min(EG, n - base);
   const long long BIG = (long long)0x7fffffff << 5;
   bool live = false, done = false;
@@ -333,18 +334,33 @@ k_epzs_sub(const jmb_epzs_req *__restrict__ reqs, int n, jmb_epzs_res *__restric
       me_.nn = (unsigned char)nn; me_.nsx = (unsigned char)(c_bsx[me_.blocktype] / nn);
       me_.nsub = nb ? (unsigned char)(me_.nsx * (c_bsy[me_.blocktype] / nn)) : 0;
       me_.nitems = (short)(nn == 8 ? me_.nsub * nb : me_.nsub);
+      me_.lsx = (unsigned char)(me_.nsx >> 1); me_.lsub = (unsigned char)(31 - __clz(max(1, (int)me_.nsub)));      // nsx = 1, 2, 4
     }
     __syncthreads();
     // work items: a 4x4 sub-block walks its search's candidates; an 8x8 one (a Hadamard of 64 differences) takes one candidate per
-    // item.  An item finds its search by adding up the searches' item counts (41 broadcast reads at most; a prefix array would cost
-    // a barrier more).
-    for (int item = tid;; item += ET) {
-      int lo = 0, f = 0;
-      for (; lo < cnt; lo++) { const int ni = S[lo].nitems; if (item < f + ni) break; f += ni; }
-      if (lo == cnt) break;
+    // item.  Every warp adds up the searches' item counts for itself (two shuffle scans; a shared prefix array would cost a barrier
+    // more) and an item finds its search by bisection.
+    int *const pre = s_pre[tid >> 5];
+    {
+      const int lane = tid & 31;
+      int a = lane < cnt ? S[lane].nitems : 0, b = lane + 32 < cnt ? S[lane + 32].nitems : 0;
+#pragma unroll
+      for (int sh = 1; sh < 32; sh <<= 1) { const int u = __shfl_up_sync(0xffffffffu, a, sh); if (lane >= sh) a += u; }
+      const int t32 = __shfl_sync(0xffffffffu, a, 31);
+#pragma unroll
+      for (int sh = 1; sh < 16; sh <<= 1) { const int u = __shfl_up_sync(0xffffffffu, b, sh); if (lane >= sh) b += u; }
+      pre[lane + 1] = a;
+      if (lane + 33 <= EG) pre[lane + 33] = t32 + b;
+      if (lane == 0) pre[0] = 0;
+      __syncwarp();
+    }
+    const int nitems = pre[cnt];
+    for (int item = tid; item < nitems; item += ET) {
+      int lo = 0, hi = cnt - 1;                        // last search whose first item is <= item (searches without items share it with the next that has some)
+      while (lo < hi) { const int m = (lo + hi + 1) >> 1; if (pre[m] <= item) lo = m; else hi = m - 1; }
       const SubS &q = S[lo];
-      const int nn = q.nn, nc = q.nc, it = item - f, c8 = nn == 8 ? it / q.nsub : 0, sb = nn == 8 ? it - c8 * q.nsub : it;
-      const int sbx = sb % q.nsx, sby = sb / q.nsx;
+      const int nn = q.nn, nc = q.nc, it = item - pre[lo], c8 = nn == 8 ? it >> q.lsub : 0, sb = nn == 8 ? it & (q.nsub - 1) : it;
+      const int sbx = sb & (q.nsx - 1), sby = sb >> q.lsx;
       const RefView rv{ref_planes[q.ref], plane_bytes, ref_pitch, w, h};
       SrcBlk src;
       load_src(src, cur, cur_pitch, q.pos_x + sbx * nn, q.pos_y + sby * nn, nn);

@@ -640,18 +640,21 @@ struct SurfView { const unsigned short *p; int x0, y0, ncol, nrow; };      // su
 constexpr int AM_NT = 256;
 __constant__ signed char c_sp9[9][2] = {{0,0},{0,-1},{0,1},{-1,-1},{1,-1},{-1,0},{1,0},{-1,1},{1,1}};      // spiral_search[0..8], mv_search.c:410-442
 
-// One partition's search in ONE launch: arg-min over its resident SAD surface, then -- JMB_REQ_SUBPEL -- the half- /
-// quarter-pel refinement of sub_pel_motion_estimation (me_fullsearch.c:186-289, as k_subpel_refine does for whole pictures),
-// answer and completion flag written straight into host-mapped memory.
-__global__ void __launch_bounds__(AM_NT)
-k_mb_search(jmb_me_req r, int slot, SurfView sv, const uint8_t *__restrict__ cur, int cur_pitch, RefView rv, int w, int h, int R, int max_mvd_m1,
-            jmb_me_config me, jmb_me_res *__restrict__ mailbox, volatile int *flag, int seq) {
-  __shared__ unsigned long long wbest[AM_NT / 32];
-  __shared__ int sums[9];
-  __shared__ int s_mvx, s_mvy;
-  __shared__ long long s_min, s_icost;
+// One partition's search: arg-min over its resident SAD surface, then -- JMB_REQ_SUBPEL -- the half- / quarter-pel
+// refinement of sub_pel_motion_estimation (me_fullsearch.c:186-289, as k_subpel_refine does for whole pictures).
+// Called by all AM_NT threads of a CTA; the answer is returned in thread 0.
+struct MbSearchS {
+  unsigned long long wbest[AM_NT / 32];
+  int sums[9];
+  int mvx, mvy;
+  long long mn, icost;
+};
+
+__device__ __forceinline__ void mb_search_body(MbSearchS &S, const jmb_me_req &r, int slot, const SurfView &sv, const uint8_t *__restrict__ cur, int cur_pitch,
+                                               const RefView &rv, int w, int h, int R, int max_mvd_m1, const jmb_me_config &me, jmb_me_res &o) {
   const int tid = threadIdx.x;
   const long long DISTBLK_MAX = (long long)0x7fffffff << 5;
+  __syncthreads();      // (S may still be read by a previous call)
   if (!(r.flags & JMB_REQ_SKIP_INT)) {
     const bool ffs = r.mode == JMB_SEARCH_FAST_FULL;
     const int ox = ffs ? (r.pos_x & ~15) : r.pos_x, oy = ffs ? (r.pos_y & ~15) : r.pos_y;      // origin the clamp applies to
@@ -672,22 +675,22 @@ k_mb_search(jmb_me_req r, int slot, SurfView sv, const uint8_t *__restrict__ cur
     }
 #pragma unroll
     for (int sh = 16; sh; sh >>= 1) {
-      const unsigned long long o = ((unsigned long long)__shfl_xor_sync(0xffffffffu, (unsigned)(best >> 32), sh) << 32) | __shfl_xor_sync(0xffffffffu, (unsigned)best, sh);
-      best = min(best, o);
+      const unsigned long long o2 = ((unsigned long long)__shfl_xor_sync(0xffffffffu, (unsigned)(best >> 32), sh) << 32) | __shfl_xor_sync(0xffffffffu, (unsigned)best, sh);
+      best = min(best, o2);
     }
-    if ((tid & 31) == 0) wbest[tid >> 5] = best;
+    if ((tid & 31) == 0) S.wbest[tid >> 5] = best;
     __syncthreads();
     if (tid == 0) {
-      for (int i = 1; i < AM_NT / 32; i++) best = min(best, wbest[i]);
+      for (int i = 1; i < AM_NT / 32; i++) best = min(best, S.wbest[i]);
       int dx = 0, dy = 0;
       if (best != ((unsigned long long)r.min_mcost << IDX_BITS)) spiral_xy((int)(best & ((1u << IDX_BITS) - 1)), &dx, &dy);
-      s_mvx = 4 * (cx + dx); s_mvy = 4 * (cy + dy);
-      s_icost = (long long)(best >> IDX_BITS);
-      s_min = me.start_hp ? s_icost : DISTBLK_MAX;                    // BlockMotionSearch, mv_search.c:971-974
+      S.mvx = 4 * (cx + dx); S.mvy = 4 * (cy + dy);
+      S.icost = (long long)(best >> IDX_BITS);
+      S.mn = me.start_hp ? S.icost : DISTBLK_MAX;                    // BlockMotionSearch, mv_search.c:971-974
     }
-  } else if (tid == 0) { s_mvx = r.center_x; s_mvy = r.center_y; s_icost = s_min = r.min_mcost; }
+  } else if (tid == 0) { S.mvx = r.center_x; S.mvy = r.center_y; S.icost = S.mn = r.min_mcost; }
   __syncthreads();
-  const int imx = s_mvx, imy = s_mvy;
+  const int imx = S.mvx, imy = S.mvy;
   if (r.flags & JMB_REQ_SUBPEL) {
 #pragma unroll 1
     for (int stage = 0; stage < 2; stage++) {
@@ -696,18 +699,18 @@ k_mb_search(jmb_me_req r, int slot, SurfView sv, const uint8_t *__restrict__ cur
       const int pos1 = stage ? me.search_pos4 : (!me.start_hp ? max(1, me.search_pos2) : me.search_pos2);
       const int nn = (metric == JMB_SATD && (r.flags & JMB_REQ_TEST8X8)) ? 8 : 4;
       const int nsx = c_bsx[r.blocktype] / nn, nsub = nsx * (c_bsy[r.blocktype] / nn);
-      if (tid < 9) sums[tid] = 0;
+      if (tid < 9) S.sums[tid] = 0;
       __syncthreads();
-      const int mvx = s_mvx, mvy = s_mvy, ncand = pos1 - pos0;
+      const int mvx = S.mvx, mvy = S.mvy, ncand = pos1 - pos0;
       for (int it = tid; it < ncand * nsub; it += AM_NT) {
         const int c = it / nsub, sb = it - c * nsub, sbx = sb % nsx, sby = sb / nsx, pos = pos0 + c;
         SrcBlk src;
         load_src(src, cur, cur_pitch, r.pos_x + sbx * nn, r.pos_y + sby * nn, nn);
-        atomicAdd(&sums[pos], subblock_dist(rv, src, (r.pos_x << 2) + mvx + step * c_sp9[pos][0], (r.pos_y << 2) + mvy + step * c_sp9[pos][1], sbx, sby, nn, metric));
+        atomicAdd(&S.sums[pos], subblock_dist(rv, src, (r.pos_x << 2) + mvx + step * c_sp9[pos][0], (r.pos_y << 2) + mvy + step * c_sp9[pos][1], sbx, sby, nn, metric));
       }
       __syncthreads();
       if (tid == 0) {      // JM's sequential strict-'<' selection (me_fullsearch.c:221-289)
-        long long mn = s_min;
+        long long mn = S.mn;
         if (stage == 1 && !me.start_qp) mn = DISTBLK_MAX;
         const int lam = r.lambda[1 + stage];
         int best = 0;
@@ -715,25 +718,125 @@ k_mb_search(jmb_me_req r, int slot, SurfView sv, const uint8_t *__restrict__ cur
           const int cxq = mvx + step * c_sp9[pos][0], cyq = mvy + step * c_sp9[pos][1];
           long long mc = (long long)lam * (jmb_mvbits(cxq - r.pred_x) + jmb_mvbits(cyq - r.pred_y));
           if (mc >= mn) continue;
-          mc += (long long)sums[pos] << 5;
+          mc += (long long)S.sums[pos] << 5;
           if (mc < mn) { mn = mc; best = pos; }
         }
-        s_min = mn; s_mvx = mvx + step * c_sp9[best][0]; s_mvy = mvy + step * c_sp9[best][1];
+        S.mn = mn; S.mvx = mvx + step * c_sp9[best][0]; S.mvy = mvy + step * c_sp9[best][1];
       }
       __syncthreads();
     }
   }
   if (tid == 0) {
-    jmb_me_res o;
-    o.imv_x = (int16_t)imx; o.imv_y = (int16_t)imy; o.icost = s_icost;
-    if (r.flags & JMB_REQ_SUBPEL) { o.mv_x = (int16_t)s_mvx; o.mv_y = (int16_t)s_mvy; o.cost = s_min; }
-    else { o.mv_x = o.imv_x; o.mv_y = o.imv_y; o.cost = s_icost; }
+    o.imv_x = (int16_t)imx; o.imv_y = (int16_t)imy; o.icost = S.icost;
+    if (r.flags & JMB_REQ_SUBPEL) { o.mv_x = (int16_t)S.mvx; o.mv_y = (int16_t)S.mvy; o.cost = S.mn; }
+    else { o.mv_x = o.imv_x; o.mv_y = o.imv_y; o.cost = S.icost; }
+  }
+}
+
+// one search in one launch, answer and completion flag written straight into host-mapped memory
+__global__ void __launch_bounds__(AM_NT)
+k_mb_search(jmb_me_req r, int slot, SurfView sv, const uint8_t *__restrict__ cur, int cur_pitch, RefView rv, int w, int h, int R, int max_mvd_m1,
+            jmb_me_config me, jmb_me_res *__restrict__ mailbox, volatile int *flag, int seq) {
+  __shared__ MbSearchS S;
+  jmb_me_res o;
+  mb_search_body(S, r, slot, sv, cur, cur_pitch, rv, w, h, R, max_mvd_m1, me, o);
+  if (threadIdx.x == 0) {
     *mailbox = o;
     __threadfence_system();
     *flag = seq;
   }
 }
 
+// ---- chains: what PartitionMotionSearch / SubPartitionMotionSearch do block after block (mv_search.c:1560-1850) -----------
+// A search of a chain takes its predictor from neighbours some of which are EARLIER searches of the same chain (the upper 16x8
+// block for the lower one, the 4x4 blocks of a quadrant for each other): GetMVPredictor (lcommon/src/mv_prediction.c:192-300,
+// non-MBAFF) -> search centre (mv_search.c:925-957) -> IntPelME -> SubPelME -> clip_mv_range (:981) -> set_me_parameters (the
+// final mv is what later blocks see).  One CTA per chain runs its searches in order; chains of one call run side by side.
+struct ChainArgs { jmb_chain_req q[JMB_CHAIN_MAX]; int n, nchains, mv_lim[4], int_divide; };
+
+__device__ __forceinline__ int median3(int a, int b, int c) { return max(min(a, b), min(max(a, b), c)); }
+
+__global__ void __launch_bounds__(AM_NT)
+k_mb_chain(const __grid_constant__ ChainArgs A, SurfView sv, const uint8_t *__restrict__ cur, int cur_pitch, RefView rv, int w, int h, int R, int max_mvd_m1,
+           jmb_me_config me, jmb_chain_res *__restrict__ mailbox, volatile int *flag, int seq, unsigned *__restrict__ done_count) {
+  __shared__ MbSearchS S;
+  __shared__ jmb_me_req cur_req;
+  __shared__ int s_status;
+  __shared__ short fin[JMB_CHAIN_MAX][2];      // final (clipped) mv of the searches done so far
+  __shared__ signed char fin_ok[JMB_CHAIN_MAX];
+  const int tid = threadIdx.x, chain = blockIdx.x;
+  for (int i = 0; i < A.n; i++) {
+    const jmb_chain_req &cq = A.q[i];
+    if (cq.chain != chain) continue;
+    if (tid == 0) {
+      int st = 0, ax[3], ay[3], rf[3], av[3];
+      for (int k = 0; k < 3; k++) {
+        const jmb_chain_nb &nb = cq.nb[k];
+        av[k] = nb.available; rf[k] = nb.available ? nb.ref_idx : -1; ax[k] = nb.mv_x; ay[k] = nb.mv_y;
+        if (nb.available && nb.dep >= 0) {
+          if (nb.dep >= i || A.q[nb.dep].chain != chain || !fin_ok[nb.dep]) st = JMB_CHAIN_SKIPPED;
+          else { ax[k] = fin[nb.dep][0]; ay[k] = fin[nb.dep][1]; }
+        }
+        if (!nb.available) ax[k] = ay[k] = 0;
+      }
+      // GetMotionVectorPredictorNormal (mv_prediction.c:192-300)
+      const int ref = cq.jm_ref, bsx = c_bsx[cq.req.blocktype], bsy = c_bsy[cq.req.blocktype], mbx = cq.req.pos_x & 15, mby = cq.req.pos_y & 15;
+      int type = 0;      // 0 median, 1 L, 2 U, 3 UR
+      if (rf[0] == ref && rf[1] != ref && rf[2] != ref) type = 1;
+      else if (rf[0] != ref && rf[1] == ref && rf[2] != ref) type = 2;
+      else if (rf[0] != ref && rf[1] != ref && rf[2] == ref) type = 3;
+      if (bsx == 8 && bsy == 16) { if (mbx == 0) { if (rf[0] == ref) type = 1; } else if (rf[2] == ref) type = 3; }
+      else if (bsx == 16 && bsy == 8) { if (mby == 0) { if (rf[1] == ref) type = 2; } else if (rf[0] == ref) type = 1; }
+      int px, py;
+      if (type == 0) {
+        if (!(av[1] || av[2])) { px = ax[0]; py = ay[0]; }
+        else { px = median3(ax[0], ax[1], ax[2]); py = median3(ay[0], ay[1], ay[2]); }
+      } else { px = ax[type - 1]; py = ay[type - 1]; }
+      jmb_me_req r = cq.req;
+      r.pred_x = (int16_t)px; r.pred_y = (int16_t)py;
+      if (r.mode == JMB_SEARCH_FULL) {      // mv_search.c:931-932 (JM_INT_DIVIDE), :957
+        r.center_x = (int16_t)jmb_clip(A.mv_lim[0], A.mv_lim[1], A.int_divide ? ((px + 2) >> 2) * 4 : (px / 4) * 4);
+        r.center_y = (int16_t)jmb_clip(A.mv_lim[2], A.mv_lim[3], A.int_divide ? ((py + 2) >> 2) * 4 : (py / 4) * 4);
+      }
+      if (!st) {      // every position the search reads (after UMVLine4X's clamp) must lie inside the resident surfaces
+        const bool ffs = r.mode == JMB_SEARCH_FAST_FULL;
+        const int ox = ffs ? (r.pos_x & ~15) : r.pos_x, oy = ffs ? (r.pos_y & ~15) : r.pos_y;
+        const int dlo_x = -JMB_PAD_X - ox, dhi_x = (w + JMB_PAD_X - 1 - 16) - ox, dlo_y = -JMB_PAD_Y - oy, dhi_y = (h + JMB_PAD_Y - 1 - 16) - oy;
+        const int cx = r.center_x >> 2, cy = r.center_y >> 2;
+        const int lx = jmb_clip(dlo_x, dhi_x, cx - R), hx = jmb_clip(dlo_x, dhi_x, cx + R), ly = jmb_clip(dlo_y, dhi_y, cy - R), hy = jmb_clip(dlo_y, dhi_y, cy + R);
+        if (lx < sv.x0 || hx >= sv.x0 + sv.ncol || ly < sv.y0 || hy >= sv.y0 + sv.nrow || ((r.center_x | r.center_y) & 3)) st = JMB_CHAIN_UNCOVERED;
+      }
+      cur_req = r; s_status = st;
+      fin_ok[i] = 0;
+    }
+    __syncthreads();
+    const int st = s_status;
+    jmb_me_res o;
+    if (!st) {
+      const jmb_me_req r = cur_req;
+      const int t = r.blocktype, bx = (r.pos_x & 15) >> 2, by = (r.pos_y & 15) >> 2;      // canonical slot of the partition (order of c_part)
+      const int base = t == 1 ? 0 : t == 2 ? 1 : t == 3 ? 3 : t == 4 ? 5 : t == 5 ? 9 : t == 6 ? 17 : 25;
+      const int w4 = c_bsx[t] >> 2, h4 = c_bsy[t] >> 2;
+      mb_search_body(S, r, base + (by / h4) * (4 / w4) + bx / w4, sv, cur, cur_pitch, rv, w, h, R, max_mvd_m1, me, o);
+    }
+    if (tid == 0) {
+      jmb_chain_res cr;
+      memset(&cr, 0, sizeof(cr));
+      cr.status = st; cr.pred_x = cur_req.pred_x; cr.pred_y = cur_req.pred_y; cr.center_x = cur_req.center_x; cr.center_y = cur_req.center_y;
+      if (!st) {
+        cr.res = o;
+        fin[i][0] = (short)jmb_clip(A.mv_lim[0], A.mv_lim[1], o.mv_x); fin[i][1] = (short)jmb_clip(A.mv_lim[2], A.mv_lim[3], o.mv_y);      // mv_search.c:981
+        fin_ok[i] = 1;
+      }
+      mailbox[i] = cr;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    __threadfence_system();
+    if (atomicAdd(done_count, 1u) == (unsigned)A.nchains - 1u) { *done_count = 0; __threadfence_system(); *flag = seq; }
+  }
+}
 
 }  // namespace
 
@@ -995,8 +1098,10 @@ int jmb_mb_surfaces(jmb_ctx *ctx, int ref, int mb_x, int mb_y, int center_x, int
 
 static int mailbox_init(jmb_ctx *ctx) {
   if (ctx->mbox) return 0;
-  JMB_CUDA(ctx, cudaHostAlloc(&ctx->mbox, 256, cudaHostAllocMapped));
-  memset(ctx->mbox, 0, 256);
+  JMB_CUDA(ctx, cudaHostAlloc(&ctx->mbox, 1024, cudaHostAllocMapped));      // one answer at 0, the flag at 128, chain answers from 256
+  memset(ctx->mbox, 0, 1024);
+  JMB_CUDA(ctx, cudaMalloc(&ctx->d_one, 16));
+  JMB_CUDA(ctx, cudaMemset(ctx->d_one, 0, 16));
   JMB_CUDA(ctx, cudaHostGetDevicePointer(&ctx->d_mbox, ctx->mbox, 0));
   return 0;
 }
@@ -1051,6 +1156,52 @@ int jmb_mb_search(jmb_ctx *ctx, const jmb_me_req *req, jmb_me_res *res) {
   JMB_LAUNCH_CHECK(ctx);
   rc = mailbox_wait(ctx, seq); if (rc) return rc;
   *res = *(const jmb_me_res *)ctx->mbox;
+  return JMB_OK;
+}
+
+int jmb_mb_chain(jmb_ctx *ctx, const jmb_chain_req *reqs, int n, const int32_t mv_limits[4], int int_divide, jmb_chain_res *res) {
+  static_assert(sizeof(jmb_chain_req) == 72 && sizeof(jmb_chain_res) == 40 && 256 + JMB_CHAIN_MAX * sizeof(jmb_chain_res) <= 1024, "chain mailbox layout");
+  if (!reqs || !res || !mv_limits || n < 1 || n > JMB_CHAIN_MAX) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_mb_chain: %d requests (1..%d)", n, JMB_CHAIN_MAX);
+  if (!ctx->cur || ctx->nref == 0) return jmb_fail(ctx, JMB_ERR_STATE, "jmb_mb_chain: call jmb_pic_begin first");
+  if (ctx->me.metric[0] != JMB_SAD) return jmb_fail(ctx, JMB_ERR_UNSUPPORTED, "jmb_mb_chain: the surfaces are SAD surfaces (MEDistortionFPel = SAD)");
+  if (mv_limits[0] > mv_limits[1] || mv_limits[2] > mv_limits[3] || mv_limits[0] < -32768 || mv_limits[1] > 32767 || mv_limits[2] < -32768 || mv_limits[3] > 32767)
+    return jmb_fail(ctx, JMB_ERR_ARG, "jmb_mb_chain: mv range x %d..%d y %d..%d", mv_limits[0], mv_limits[1], mv_limits[2], mv_limits[3]);
+  ChainArgs A;
+  memset(&A, 0, sizeof(A));
+  int nchains = 0;
+  for (int i = 0; i < n; i++) {
+    const jmb_chain_req &q = reqs[i];
+    int rc = validate_req(ctx, q.req, i); if (rc) return rc;
+    if (q.req.flags & JMB_REQ_SKIP_INT) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_mb_chain: request %d: JMB_REQ_SKIP_INT has no place in a chain", i);
+    if ((q.req.flags & JMB_REQ_TEST8X8) && q.req.blocktype > 4) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_mb_chain: request %d: JMB_REQ_TEST8X8 needs blocktype <= 4", i);
+    if (q.req.ref != reqs[0].req.ref || (q.req.pos_x & ~15) != (reqs[0].req.pos_x & ~15) || (q.req.pos_y & ~15) != (reqs[0].req.pos_y & ~15))
+      return jmb_fail(ctx, JMB_ERR_ARG, "jmb_mb_chain: request %d belongs to another macroblock / reference than request 0", i);
+    if (q.chain < 0 || q.chain >= JMB_CHAIN_MAX) return jmb_fail(ctx, JMB_ERR_ARG, "jmb_mb_chain: request %d: chain %d", i, q.chain);
+    for (int k = 0; k < 3; k++)
+      if (q.nb[k].available && q.nb[k].dep >= 0 && (q.nb[k].dep >= i || reqs[q.nb[k].dep].chain != q.chain))
+        return jmb_fail(ctx, JMB_ERR_ARG, "jmb_mb_chain: request %d depends on %d, which is not an earlier search of its chain", i, q.nb[k].dep);
+    nchains = nchains > q.chain + 1 ? nchains : q.chain + 1;
+    A.q[i] = q;
+  }
+  A.n = n; A.nchains = nchains; A.int_divide = int_divide;
+  for (int k = 0; k < 4; k++) A.mv_lim[k] = mv_limits[k];
+  JMB_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = mailbox_init(ctx); if (rc) return rc;
+  const jmb_me_req &r0 = reqs[0].req;
+  const jmb_ctx::Surf &sf = ctx->surf[r0.ref];
+  if (!sf.valid || sf.pic_serial != ctx->pic_serial || sf.mb_x != (r0.pos_x & ~15) || sf.mb_y != (r0.pos_y & ~15))
+    return jmb_fail(ctx, JMB_ERR_STATE, "jmb_mb_chain: no surfaces resident for macroblock (%d,%d) reference %d", r0.pos_x & ~15, r0.pos_y & ~15, r0.ref);
+  SurfView sv{(const unsigned short *)sf.buf, sf.x0, sf.y0, sf.n, sf.n};
+  const jmb_ref &rr = ctx->refs[ctx->ref_list[r0.ref]];
+  RefView rv{rr.planes, rr.plane_bytes, rr.pitch, rr.w, rr.h};
+  const int seq = ++ctx->mbox_seq;
+  jmb_time_begin(ctx, JMB_K_ARGMIN);
+  k_mb_chain<<<nchains, AM_NT, 0, ctx->stream>>>(A, sv, ctx->cur, ctx->cur_pitch, rv, ctx->cur_w, ctx->cur_h, ctx->me.search_range, ctx->me.max_mvd - 1, ctx->me,
+                                                 (jmb_chain_res *)((char *)ctx->d_mbox + 256), (volatile int *)((char *)ctx->d_mbox + 128), seq, (unsigned *)ctx->d_one);
+  jmb_time_end(ctx, JMB_K_ARGMIN);
+  JMB_LAUNCH_CHECK(ctx);
+  rc = mailbox_wait(ctx, seq); if (rc) return rc;
+  memcpy(res, (const char *)ctx->mbox + 256, (size_t)n * sizeof(jmb_chain_res));
   return JMB_OK;
 }
 

@@ -112,6 +112,7 @@ distblk __real_computeSATD(StorablePicture *, MEBlock *, distblk, MotionVector *
 
 
 enum { FAM_PLANES = 1, FAM_ME = 2, FAM_SUBPEL = 4, FAM_TQ = 8, FAM_DIST = 16 };
+enum { AHEAD_N = 8 * JMB_CHAIN_MAX };      /* answers kept ahead of JM: a call's worth for each of several references */
 
 static struct
 {
@@ -134,6 +135,11 @@ static struct
   /* the sub-pel refinement computed speculatively with the integer search of the same block (one device call instead of two) */
   struct { int valid, pos_x, pos_y, blocktype, list, ref_idx, test8x8, lambda_h, lambda_q; MotionVector pred, imv, mv; distblk min_in, cost; } spec;
   unsigned long    spec_hits, surf_builds;
+  /* answers the device gave AHEAD of JM's call sequence (jmb_mb_chain): each is handed out only when JM arrives at that block
+   * with exactly the predictor, centre, bound and lambda the device assumed */
+  struct { int valid, pos_x, pos_y, blocktype, list, ref_idx, test8x8, lambda, mode, R; unsigned long pic; MotionVector pred, center; jmb_me_res res; } ahead[AHEAD_N];
+  int              chains_off;        /* JMB_SHIM_CHAIN=0: one device call per search (A/B of the run-ahead) */
+  unsigned long    chain_calls, chain_hits, chain_stale;
 } S;
 
 /* JM's convention for fatal conditions is error(text, code) -> message on stderr, exit(code) (lencod/src/lencod.c).
@@ -163,9 +169,9 @@ static void report(void)
   if (S.init == 1 && S.verify)
     fprintf(stderr, "[jmb shim] luma_residual_coding verified on %lu macroblock codings (levels, cbp, cbp_blk, reconstruction); chroma_residual_coding verified on %lu\n", S.verified, chroma_verified);
   if (S.init == 1 && getenv("JMB_SHIM_VERBOSE"))
-    fprintf(stderr, "[jmb shim] planes %lu  full %lu  fastfull %lu  subpel %lu  fwd4 %lu  fwd8 %lu  quant4 %lu  quant8 %lu  dist %lu  kernel launches %llu  bipred/weighted distortions %lu  subpel served by the integer search's call %lu  surface builds %lu\n",
+    fprintf(stderr, "[jmb shim] planes %lu  full %lu  fastfull %lu  subpel %lu  fwd4 %lu  fwd8 %lu  quant4 %lu  quant8 %lu  dist %lu  kernel launches %llu  bipred/weighted distortions %lu  subpel served by the integer search's call %lu  surface builds %lu  chain calls %lu  searches answered ahead %lu  (discarded %lu)\n",
             S.calls[0], S.calls[1], S.calls[2], S.calls[3], S.calls[4], S.calls[5], S.calls[6], S.calls[7], S.calls[8],
-            (unsigned long long)jmb_launch_count(S.ctx), S.calls[9], S.spec_hits, S.surf_builds);
+            (unsigned long long)jmb_launch_count(S.ctx), S.calls[9], S.spec_hits, S.surf_builds, S.chain_calls, S.chain_hits, S.chain_stale);
 }
 
 static int shim_on(int family)
@@ -186,6 +192,7 @@ static int shim_on(int family)
       }
       S.init = 1;
       S.verify = getenv("JMB_SHIM_VERIFY") != NULL;
+      S.chains_off = getenv("JMB_SHIM_CHAIN") && !strcmp(getenv("JMB_SHIM_CHAIN"), "0");
       if (off)
       {
         if (strstr(off, "planes")) S.off |= FAM_PLANES;
@@ -346,6 +353,21 @@ static void fill_request(jmb_me_req *q, MEBlock *mv_block, MotionVector *pred_mv
   q->min_mcost = min_mcost;
 }
 
+/* the sub-pel refinement that came with an integer search's answer, kept for the SubPelME call that follows */
+static void note_spec(Macroblock *currMB, MotionVector *pred_mv, MEBlock *mv_block, int lambda_factor, int spec, const jmb_me_res *r)
+{
+  VideoParameters *p_Vid = currMB->p_Vid;
+  S.spec.valid = spec;
+  S.spec.pos_x = mv_block->pos_x; S.spec.pos_y = mv_block->pos_y; S.spec.blocktype = mv_block->blocktype;
+  S.spec.list = mv_block->list; S.spec.ref_idx = mv_block->ref_idx; S.spec.test8x8 = mv_block->test8x8;
+  S.spec.lambda_h = S.spec.lambda_q = lambda_factor;
+  S.spec.pred = *pred_mv;
+  S.spec.imv.mv_x = r->imv_x; S.spec.imv.mv_y = r->imv_y;
+  S.spec.mv.mv_x = r->mv_x;   S.spec.mv.mv_y = r->mv_y;
+  S.spec.min_in = p_Vid->start_me_refinement_hp ? (distblk)r->icost : DISTBLK_MAX;      /* what BlockMotionSearch hands to SubPelME */
+  S.spec.cost = (distblk)r->cost;
+}
+
 /* One partition's search + (speculatively) its sub-pel refinement in ONE device call over the macroblock's resident surfaces.
  * BlockMotionSearch calls SubPelME right after IntPelME with the same block, predictor and -- in every configuration JM
  * ships -- the same lambda at all three levels (mv_search.c:960-976); the refinement is therefore computed along with the
@@ -364,16 +386,128 @@ static int mb_search(Macroblock *currMB, MotionVector *pred_mv, MEBlock *mv_bloc
   q.lambda[0] = q.lambda[1] = q.lambda[2] = lambda_factor;
   rc = jmb_mb_search(S.ctx, &q, r);
   if (rc) return rc;
-  S.spec.valid = spec;
-  S.spec.pos_x = mv_block->pos_x; S.spec.pos_y = mv_block->pos_y; S.spec.blocktype = mv_block->blocktype;
-  S.spec.list = mv_block->list; S.spec.ref_idx = mv_block->ref_idx; S.spec.test8x8 = mv_block->test8x8;
-  S.spec.lambda_h = S.spec.lambda_q = lambda_factor;
-  S.spec.pred = *pred_mv;
-  S.spec.imv.mv_x = r->imv_x; S.spec.imv.mv_y = r->imv_y;
-  S.spec.mv.mv_x = r->mv_x;   S.spec.mv.mv_y = r->mv_y;
-  S.spec.min_in = p_Vid->start_me_refinement_hp ? (distblk)r->icost : DISTBLK_MAX;      /* what BlockMotionSearch hands to SubPelME */
-  S.spec.cost = (distblk)r->cost;
+  note_spec(currMB, pred_mv, mv_block, lambda_factor, spec, r);
   return 0;
+}
+
+/* ---- running ahead of JM's call sequence --------------------------------------------------------------------------------
+ * JM searches the partitions of a macroblock one BlockMotionSearch at a time because each block's predictor is the median of
+ * its neighbours' vectors, and some neighbours are blocks searched just before (mv_search.c:1560-1850).  Nothing else ties
+ * them together, so at the FIRST search of a region -- the 16x16 block (modes 1-3 follow), or the 8x8 block of a quadrant
+ * (its sub-modes 5-7 follow) -- the shim describes all searches of the region to the device in ONE call (jmb_mb_chain):
+ * geometry, and per block the three neighbours as JM's own get_neighbors finds them, either by value (mv_info as it stands)
+ * or by naming the earlier search of the call that will have written that position.  The device derives predictor and centre
+ * as BlockMotionSearch does and searches block after block.  When JM arrives at a later block, the stored answer is used only
+ * if JM's own predictor, centre, bound, lambda and range are what the device assumed (the assumption that can fail: with
+ * several references JM may settle the first block of a 16x8 / 8x16 pair on another reference); otherwise it is discarded
+ * and the block is searched by a call of its own.  Either way every number JM sees is the one it would have computed. */
+static const struct { int type, x, y, chain; } CHAIN_WHOLE[5] = {{1, 0, 0, 0}, {2, 0, 0, 1}, {2, 0, 8, 1}, {3, 0, 0, 2}, {3, 8, 0, 2}};
+static const struct { int type, x, y, chain; } CHAIN_QUAD[9] = {{4, 0, 0, 0}, {5, 0, 0, 1}, {5, 0, 4, 1}, {6, 0, 0, 2}, {6, 4, 0, 2},
+                                                                {7, 0, 0, 3}, {7, 4, 0, 3}, {7, 0, 4, 3}, {7, 4, 4, 3}};
+static const int CHAIN_BSX[8] = {0, 16, 16, 8, 8, 8, 4, 4}, CHAIN_BSY[8] = {0, 16, 8, 16, 8, 4, 8, 4};
+
+static int ahead_take(Macroblock *currMB, MotionVector *pred_mv, MEBlock *mv_block, distblk min_mcost, int lambda_factor, int mode, int R,
+                      int center_x, int center_y, jmb_me_res *r)
+{
+  int i;
+  for (i = 0; i < AHEAD_N; i++)
+    if (S.ahead[i].valid && S.ahead[i].pos_x == mv_block->pos_x && S.ahead[i].pos_y == mv_block->pos_y && S.ahead[i].blocktype == mv_block->blocktype &&
+        S.ahead[i].list == mv_block->list && S.ahead[i].ref_idx == mv_block->ref_idx)
+    {
+      S.ahead[i].valid = 0;
+      if (S.ahead[i].pic == S.pic_count && S.ahead[i].test8x8 == mv_block->test8x8 && S.ahead[i].lambda == lambda_factor && S.ahead[i].mode == mode &&
+          S.ahead[i].R == R && min_mcost == DISTBLK_MAX && S.ahead[i].pred.mv_x == pred_mv->mv_x && S.ahead[i].pred.mv_y == pred_mv->mv_y &&
+          S.ahead[i].center.mv_x == center_x && S.ahead[i].center.mv_y == center_y)
+      {
+        *r = S.ahead[i].res;
+        S.chain_hits++;
+        note_spec(currMB, pred_mv, mv_block, lambda_factor, !currMB->p_Inp->DisableSubpelME[currMB->p_Vid->view_id], r);
+        return 1;
+      }
+      S.chain_stale++;
+    }
+  return 0;
+}
+
+/* the region that starts with this block, in one device call; 1 = the block's own answer is in *r */
+static int ahead_run(Macroblock *currMB, MotionVector *pred_mv, MEBlock *mv_block, int lambda_factor, int mode, int R, int ri,
+                     int center_x, int center_y, jmb_me_res *r)
+{
+  VideoParameters *p_Vid = currMB->p_Vid;
+  InputParameters *p_Inp = currMB->p_Inp;
+  Slice *currSlice = currMB->p_Slice;
+  PicMotionParams **mv_info = p_Vid->enc_picture->mv_info;
+  jmb_chain_req q[JMB_CHAIN_MAX];
+  jmb_chain_res o[JMB_CHAIN_MAX];
+  int32_t lim[4];
+  int n, i, j, k, rc, list = mv_block->list, spec = !p_Inp->DisableSubpelME[p_Vid->view_id];
+  int mbx = mv_block->pos_x & ~15, mby = mv_block->pos_y & ~15, qx = mv_block->pos_x & 15, qy = mv_block->pos_y & 15;
+  if (S.chains_off || currSlice->mb_aff_frame_flag || p_Inp->DisableMEPrediction || !p_Inp->rdopt || currSlice->rdoq_motion_copy == 1) return 0;
+  if (mv_block->blocktype == 1) n = 5;
+  else if (mv_block->blocktype == 4) n = 9;
+  else return 0;
+  memset(q, 0, sizeof(q));
+  for (i = 0; i < n; i++)
+  {
+    int type = n == 5 ? CHAIN_WHOLE[i].type : CHAIN_QUAD[i].type;
+    int x = n == 5 ? CHAIN_WHOLE[i].x : qx + CHAIN_QUAD[i].x, y = n == 5 ? CHAIN_WHOLE[i].y : qy + CHAIN_QUAD[i].y;
+    PixelPos block[4];
+    q[i].req.pos_x = (int16_t)(mbx + x); q[i].req.pos_y = (int16_t)(mby + y);
+    q[i].req.blocktype = (uint8_t)type; q[i].req.ref = (uint8_t)ri; q[i].req.mode = (uint8_t)mode;
+    q[i].req.flags = (uint8_t)(spec ? (JMB_REQ_SUBPEL | ((p_Inp->Transform8x8Mode && type <= 4) ? JMB_REQ_TEST8X8 : 0)) : 0);      /* mv_search.c:1630,1769 */
+    q[i].req.lambda[0] = q[i].req.lambda[1] = q[i].req.lambda[2] = lambda_factor;
+    q[i].req.min_mcost = DISTBLK_MAX;
+    q[i].req.center_x = (int16_t)center_x; q[i].req.center_y = (int16_t)center_y;      /* FAST_FULL: one centre per macroblock and reference; FULL: derived */
+    q[i].jm_ref = (int8_t)mv_block->ref_idx;
+    q[i].chain = (int8_t)(n == 5 ? CHAIN_WHOLE[i].chain : CHAIN_QUAD[i].chain);
+    get_neighbors(currMB, block, x, y, CHAIN_BSX[type]);
+    for (k = 0; k < 3; k++)
+    {
+      jmb_chain_nb *nb = &q[i].nb[k];
+      nb->available = (int8_t)(block[k].available != 0);
+      nb->dep = -1;
+      if (!block[k].available) continue;
+      for (j = 0; j < i; j++)      /* a position inside an earlier block of the same chain: that search's vector will stand there */
+        if (q[j].chain == q[i].chain && block[k].pos_x * 4 >= q[j].req.pos_x && block[k].pos_x * 4 < q[j].req.pos_x + CHAIN_BSX[q[j].req.blocktype] &&
+            block[k].pos_y * 4 >= q[j].req.pos_y && block[k].pos_y * 4 < q[j].req.pos_y + CHAIN_BSY[q[j].req.blocktype])
+          nb->dep = (int8_t)j;
+      if (nb->dep >= 0) nb->ref_idx = (int8_t)mv_block->ref_idx;
+      else
+      {
+        nb->ref_idx = (int8_t)mv_info[block[k].pos_y][block[k].pos_x].ref_idx[list];
+        nb->mv_x = mv_info[block[k].pos_y][block[k].pos_x].mv[list].mv_x;
+        nb->mv_y = mv_info[block[k].pos_y][block[k].pos_x].mv[list].mv_y;
+      }
+    }
+  }
+  lim[0] = p_Vid->MaxHmvR[4]; lim[1] = p_Vid->MaxHmvR[5]; lim[2] = p_Vid->MaxVmvR[4]; lim[3] = p_Vid->MaxVmvR[5];      /* clip_mv_range(.., Q_PEL), conformance.c:640 */
+  rc = jmb_mb_chain(S.ctx, q, n, lim, JM_INT_DIVIDE, o);
+  if (rc) jmb_die("jmb_mb_chain", rc);
+  S.chain_calls++;
+  /* what is still waiting for this list and reference (or for another macroblock / picture) will not be asked for any more */
+  for (i = 0; i < AHEAD_N; i++)
+    if (S.ahead[i].valid && ((S.ahead[i].list == list && S.ahead[i].ref_idx == mv_block->ref_idx) || S.ahead[i].pic != S.pic_count ||
+                             (S.ahead[i].pos_x & ~15) != mbx || (S.ahead[i].pos_y & ~15) != mby))
+    { S.ahead[i].valid = 0; S.chain_stale++; }
+  for (i = 1, j = 0; i < n; i++)
+    if (o[i].status == JMB_CHAIN_DONE)
+    {
+      while (j < AHEAD_N && S.ahead[j].valid) j++;
+      if (j == AHEAD_N) break;
+      S.ahead[j].valid = 1; S.ahead[j].pos_x = q[i].req.pos_x; S.ahead[j].pos_y = q[i].req.pos_y; S.ahead[j].blocktype = q[i].req.blocktype;
+      S.ahead[j].list = list; S.ahead[j].ref_idx = mv_block->ref_idx; S.ahead[j].test8x8 = (q[i].req.flags & JMB_REQ_TEST8X8) != 0;
+      S.ahead[j].lambda = lambda_factor; S.ahead[j].mode = mode; S.ahead[j].R = R; S.ahead[j].pic = S.pic_count;
+      S.ahead[j].pred.mv_x = o[i].pred_x; S.ahead[j].pred.mv_y = o[i].pred_y;
+      S.ahead[j].center.mv_x = o[i].center_x; S.ahead[j].center.mv_y = o[i].center_y;
+      S.ahead[j].res = o[i].res;
+    }
+  /* the block JM asked for: the device must have derived JM's own predictor and centre for it */
+  if (o[0].status != JMB_CHAIN_DONE || o[0].pred_x != pred_mv->mv_x || o[0].pred_y != pred_mv->mv_y || o[0].center_x != center_x || o[0].center_y != center_y ||
+      ((q[0].req.flags & JMB_REQ_TEST8X8) != 0) != (mv_block->test8x8 != 0))
+    return 0;
+  *r = o[0].res;
+  note_spec(currMB, pred_mv, mv_block, lambda_factor, spec, r);
+  return 1;
 }
 
 /* stands behind full_search_motion_estimation (lencod/src/me_fullsearch.c:39) = currMB->IntPelME for SearchMode -1.
@@ -398,6 +532,11 @@ distblk __wrap_full_search_motion_estimation(Macroblock *currMB, MotionVector *p
   ri = ref_index(currMB, mv_block);
   mbx = mv_block->pos_x & ~15; mby = mv_block->pos_y & ~15;
   E = imin(8, (91 - (2 * R + 1)) / 2);
+  if (E >= 0 && ahead_take(currMB, pred_mv, mv_block, min_mcost, lambda_factor, JMB_SEARCH_FULL, R, mv->mv_x, mv->mv_y, &r))
+  { /* searched ahead of this call, with exactly this predictor and centre */
+    mv->mv_x = r.imv_x; mv->mv_y = r.imv_y;
+    return (distblk)r.icost;
+  }
   if (E >= 0)
     for (pass = 0; pass < 2; pass++)
     {
@@ -408,6 +547,8 @@ distblk __wrap_full_search_motion_estimation(Macroblock *currMB, MotionVector *p
         S.surf[ri].valid = 1; S.surf[ri].pic = S.pic_count; S.surf[ri].mb_x = mbx; S.surf[ri].mb_y = mby;
         S.surf_builds++;
       }
+      if (min_mcost == DISTBLK_MAX && ahead_run(currMB, pred_mv, mv_block, lambda_factor, JMB_SEARCH_FULL, R, ri, mv->mv_x, mv->mv_y, &r))
+      { mv->mv_x = r.imv_x; mv->mv_y = r.imv_y; return (distblk)r.icost; }
       rc = mb_search(currMB, pred_mv, mv_block, min_mcost, lambda_factor, JMB_SEARCH_FULL, ri, mv->mv_x, mv->mv_y, &r);
       if (!rc) { mv->mv_x = r.imv_x; mv->mv_y = r.imv_y; return (distblk)r.icost; }
       if (rc != JMB_ERR_STATE) jmb_die("jmb_mb_search(full)", rc);      /* JMB_ERR_STATE: window not covered -> fresh surfaces */
@@ -482,6 +623,15 @@ distblk __wrap_fast_full_search_motion_estimation(Macroblock *currMB, MotionVect
   S.calls[2]++;
   if (!ff->search_setup_done[list][ref]) currMB->p_SetupFastFullPelSearch(currMB, mv_block, list);
   configure(currMB, mv_block, imax(mv_block->searchRange.max_x, mv_block->searchRange.max_y) >> 2);
+  if (ahead_take(currMB, pred_mv, mv_block, min_mcost, lambda_factor, JMB_SEARCH_FAST_FULL, S.cfg.search_range,
+                 ff->search_center[list][ref].mv_x, ff->search_center[list][ref].mv_y, &r) ||
+      (min_mcost == DISTBLK_MAX && ahead_run(currMB, pred_mv, mv_block, lambda_factor, JMB_SEARCH_FAST_FULL, S.cfg.search_range, ref_index(currMB, mv_block),
+                                             ff->search_center[list][ref].mv_x, ff->search_center[list][ref].mv_y, &r)))
+  {
+    mv_block->mv[list].mv_x = r.imv_x;
+    mv_block->mv[list].mv_y = r.imv_y;
+    return (distblk)r.icost;
+  }
   rc = mb_search(currMB, pred_mv, mv_block, min_mcost, lambda_factor, JMB_SEARCH_FAST_FULL, ref_index(currMB, mv_block),
                  ff->search_center[list][ref].mv_x, ff->search_center[list][ref].mv_y, &r);
   if (rc == JMB_ERR_STATE)

@@ -455,3 +455,38 @@ def jmref_run_mbs(ref, mb_xy, preds, lam3, qp, qparams, scan, c_cost, do_tq=True
                     np.ascontiguousarray(c_cost, np.uint8), int(do_tq), mv, cost,
                     lev.ctypes.data if lev is not None else None, secs)
     return mv, cost, lev, secs
+
+
+def mv_predictor(nb, ref_frame, mb_x, mb_y, bsx, bsy):
+    """GetMotionVectorPredictorNormal (lcommon/src/mv_prediction.c:192-300) restated: nb = three (available, ref_idx, mv_x, mv_y)
+    for the neighbours A (left), B (up), C (up-right, or D where get_neighbors substitutes it); pinned against the real function
+    by tests/test_oracle_vs_ref.py::test_mv_predictor_matches_jm."""
+    rf = [n[1] if n[0] else -1 for n in nb]
+    mv = [(n[2], n[3]) if n[0] else (0, 0) for n in nb]
+    same = [r == ref_frame for r in rf]
+    kind = "median"
+    if same == [True, False, False]: kind = 0
+    elif same == [False, True, False]: kind = 1
+    elif same == [False, False, True]: kind = 2
+    if (bsx, bsy) == (8, 16):
+        if mb_x == 0:
+            if same[0]: kind = 0
+        elif same[2]: kind = 2
+    elif (bsx, bsy) == (16, 8):
+        if mb_y == 0:
+            if same[1]: kind = 1
+        elif same[0]: kind = 0
+    if kind == "median":
+        if not (nb[1][0] or nb[2][0]):
+            return mv[0]
+        return tuple(sorted(c)[1] for c in zip(*mv))
+    return mv[kind]
+
+
+def jmref_mv_predictor(nb, ref_frame, mb_x, mb_y, bsx, bsy):
+    """The same through JM's own function (oracle/_ref/libjmref.so)."""
+    L = C.CDLL(REF_SO)
+    L.jmref_mv_predictor.argtypes = [_i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i16p]
+    out = np.zeros(2, np.int16)
+    L.jmref_mv_predictor(np.ascontiguousarray(nb, np.int32).reshape(-1), ref_frame, mb_x, mb_y, bsx, bsy, out)
+    return int(out[0]), int(out[1])

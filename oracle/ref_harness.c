@@ -18,6 +18,7 @@
  *   forward4x4 / forward8x8              lcommon/src/transform.c:20,353
  *   quant_4x4_normal/_around             lencod/src/quant4x4_normal.c:39, quant4x4_around.c:40
  *   quant_8x8_normal/_around, quant_8x8cavlc_normal/_around   lencod/src/quant8x8_*.c
+ *   GetMotionVectorPredictorNormal       lcommon/src/mv_prediction.c:192 (through init_motion_vector_prediction, :306)
  */
 #include <stdint.h>
 #include <string.h>
@@ -36,6 +37,7 @@
 #include "quant8x8.h"
 #include "quantChroma.h"
 #include "refbuf.h"
+#include "mv_prediction.h"
 
 typedef struct jmref_ctx
 {
@@ -601,4 +603,29 @@ void jmref_run_mbs(void *h, int n_mb, const int16_t *mb_xy, const int16_t *preds
     }
   }
   secs[0] = t_me; secs[1] = t_tq;
+}
+
+/* JM's own median / directional motion-vector predictor (GetMotionVectorPredictorNormal, static in mv_prediction.c, reached
+ * through the function pointer init_motion_vector_prediction installs) on three caller-described neighbours A, B, C:
+ * nb[k] = {available, ref_idx, mv_x, mv_y}. */
+void jmref_mv_predictor(const int *nb, int ref_frame, int mb_x, int mb_y, int bsx, int bsy, int16_t *out)
+{
+  Macroblock mb;
+  PicMotionParams row[3], *rows[1];
+  PixelPos block[4];
+  MotionVector pmv;
+  int k;
+  memset(&mb, 0, sizeof(mb)); memset(row, 0, sizeof(row)); memset(block, 0, sizeof(block));
+  rows[0] = row;
+  for (k = 0; k < 3; k++)
+  {
+    block[k].available = nb[4 * k];
+    block[k].pos_x = (short)k; block[k].pos_y = 0;
+    row[k].ref_idx[LIST_0] = (char)nb[4 * k + 1];
+    row[k].mv[LIST_0].mv_x = (short)nb[4 * k + 2];
+    row[k].mv[LIST_0].mv_y = (short)nb[4 * k + 3];
+  }
+  init_motion_vector_prediction(&mb, 0);
+  mb.GetMVPredictor(&mb, block, &pmv, (short)ref_frame, rows, LIST_0, mb_x, mb_y, bsx, bsy);
+  out[0] = pmv.mv_x; out[1] = pmv.mv_y;
 }

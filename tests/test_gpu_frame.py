@@ -291,3 +291,90 @@ def test_mb_surfaces_and_per_partition_argmin(ctx, mode):
     q["center_x"] = c0[0]
     with pytest.raises(api.JMBError, match="no surfaces resident"):
         ctx.mb_search(q)
+
+
+def _chain_layouts():
+    """The two calls the shim makes per macroblock region: modes 1-3 of the macroblock; the four sub-modes of one 8x8 quadrant.
+    Entries: (blocktype, x, y, chain, deps) with deps = {neighbour index: index of the earlier search that covers it}."""
+    whole = [(1, 0, 0, 0, {}), (2, 0, 0, 1, {}), (2, 0, 8, 1, {1: 1}), (3, 0, 0, 2, {}), (3, 8, 0, 2, {0: 3})]
+    def quad(qx, qy):
+        return [(4, qx, qy, 0, {}),
+                (5, qx, qy, 1, {}), (5, qx, qy + 4, 1, {1: 1}),
+                (6, qx, qy, 2, {}), (6, qx + 4, qy, 2, {0: 3}),
+                (7, qx, qy, 3, {}), (7, qx + 4, qy, 3, {0: 5}), (7, qx, qy + 4, 3, {1: 5, 2: 6}), (7, qx + 4, qy + 4, 3, {0: 7, 1: 6, 2: 5})]
+    return [whole, quad(0, 0), quad(8, 0), quad(0, 8), quad(8, 8)]
+
+
+@pytest.mark.parametrize("mode", [api.SEARCH_FULL, api.SEARCH_FAST_FULL])
+def test_mb_chain_runs_ahead_like_jm_block_after_block(ctx, mode):
+    """jmb_mb_chain: the searches of a macroblock whose predictors depend on each other (the lower 16x8 block on the upper one,
+    the 4x4 blocks of a quadrant on each other) in one call.  Expected = JM's sequence done one leaf call at a time: predictor
+    from the neighbours (oracle.pyoracle.mv_predictor, pinned to JM's GetMVPredictor) -> centre -> jmb_me_search (oracle-checked
+    in tests/test_gpu_parity.py) -> clip -> visible to the next block."""
+    from oracle import pyoracle as po
+    w, h, R, E = 96, 80, 12, 6
+    f = synth.luma_frames(w, h, 2, seed=47, motion=(-2, 3))
+    ctx.configure(search_range=R)
+    ctx.ref_put(0, f[0]); ctx.pic_begin(f[1], [0])
+    rng = np.random.default_rng(48)
+    lim = (-60, 68, -52, 44)      # (multiples of 4: an integer-pel centre stays one after the clip)
+    n_done = n_unc = 0
+    for mb in [(0, 0), (80, 64), (32, 32), (48, 16), (16, 48)]:
+        base = rng.integers(-24, 25, 2)
+        c0 = (((int(base[0]) + 2) >> 2) * 4, ((int(base[1]) + 2) >> 2) * 4)
+        c0 = (min(max(c0[0], lim[0]), lim[1]) // 4 * 4, min(max(c0[1], lim[2]), lim[3]) // 4 * 4)
+        ctx.mb_surfaces(0, mb, c0, R + E)
+        for layout in _chain_layouts():
+            reqs = np.zeros(len(layout), api.CHAIN_REQ)
+            lam = int(rng.integers(1, 200))
+            for i, (t, x, y, chain, deps) in enumerate(layout):
+                q = reqs[i]
+                q["req"]["blocktype"] = t; q["req"]["pos_x"] = mb[0] + x; q["req"]["pos_y"] = mb[1] + y
+                q["req"]["mode"] = mode; q["req"]["flags"] = api.REQ_SUBPEL; q["req"]["lambda"] = lam; q["req"]["min_mcost"] = BIG
+                if mode == api.SEARCH_FAST_FULL:
+                    q["req"]["center_x"], q["req"]["center_y"] = c0
+                q["jm_ref"] = 0; q["chain"] = chain
+                for k in range(3):
+                    nb = q["nb"][k]
+                    if k in deps:
+                        nb["available"] = 1; nb["ref_idx"] = 0; nb["dep"] = deps[k]
+                    else:
+                        nb["dep"] = -1
+                        nb["available"] = rng.random() < 0.8
+                        nb["ref_idx"] = int(rng.choice([-1, 0, 0, 0, 1]))
+                        far = rng.random() < 0.1       # now and then a neighbour that pulls the window off the resident surfaces
+                        nb["mv_x"], nb["mv_y"] = base + rng.integers(-6, 7, 2) + (60 if far else 0)
+            got = ctx.mb_chain(reqs, lim)
+            fin = {}
+            for i, (t, x, y, chain, deps) in enumerate(layout):
+                q = reqs[i]; bsx, bsy = api.BLOCK_SIZE[t]
+                nbs, skipped = [], False
+                for k in range(3):
+                    nb = q["nb"][k]
+                    if nb["dep"] >= 0:
+                        if int(nb["dep"]) not in fin:
+                            skipped = True
+                        nbs.append((1, 0) + fin.get(int(nb["dep"]), (0, 0)))
+                    else:
+                        nbs.append((int(nb["available"]), int(nb["ref_idx"]), int(nb["mv_x"]), int(nb["mv_y"])))
+                if skipped:
+                    assert got[i]["status"] == api.CHAIN_SKIPPED, (mb, i, got[i])
+                    continue
+                px, py = po.mv_predictor(nbs, 0, x, y, bsx, bsy)
+                assert (got[i]["pred_x"], got[i]["pred_y"]) == (px, py), (mb, i, nbs, got[i])
+                lq = np.zeros(1, api.ME_REQ); lq[0] = q["req"]
+                lq["pred_x"] = px; lq["pred_y"] = py
+                if mode == api.SEARCH_FULL:
+                    lq["center_x"] = min(max(((px + 2) >> 2) * 4, lim[0]), lim[1]); lq["center_y"] = min(max(((py + 2) >> 2) * 4, lim[2]), lim[3])
+                assert (got[i]["center_x"], got[i]["center_y"]) == (lq["center_x"][0], lq["center_y"][0])
+                if got[i]["status"] == api.CHAIN_UNCOVERED:
+                    with pytest.raises(api.JMBError, match="not covered"):
+                        ctx.mb_search(lq)
+                    n_unc += 1
+                    continue
+                assert got[i]["status"] == api.CHAIN_DONE
+                want = ctx.me_search(lq)[0]
+                assert got[i]["res"] == want, (mb, i, lq, got[i], want)
+                fin[i] = (min(max(int(want["mv_x"]), lim[0]), lim[1]), min(max(int(want["mv_y"]), lim[2]), lim[3]))
+                n_done += 1
+    assert n_done > 150 and (n_unc > 0 or mode == api.SEARCH_FAST_FULL), (n_done, n_unc)

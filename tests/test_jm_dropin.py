@@ -255,3 +255,12 @@ def test_searches_run_on_resident_surfaces_with_device_argmin(tmp_path, name):
     served = int(line.split("served by the integer search's call")[1].split()[0]); builds = int(line.split("surface builds")[1].split()[0])
     searches = int(line.split("full")[1].split()[0]) + int(line.split("fastfull")[1].split()[0])
     assert builds > 0 and served > 0.9 * searches, line
+    # ... and most searches were answered AHEAD of JM's call (jmb_mb_chain: the searches of a macroblock region in one device call,
+    # each answer handed out only if JM arrives with the predictor and centre the device derived)
+    calls = int(line.split("chain calls")[1].split()[0]); ahead = int(line.split("searches answered ahead")[1].split()[0])
+    assert calls > 0 and ahead + calls > 0.5 * searches, line
+    # the same with the run-ahead switched off: one device call per search, the same bitstream
+    r3 = _encode(JMB, tmp_path, "gpu1", w, h, frames, CONFIGS[name], env={"JMB_SHIM_VERBOSE": "1", "JMB_SHIM_CHAIN": "0"})
+    assert r3.returncode == 0, r3.stderr[-500:]
+    _same_outputs(tmp_path, "ref", "gpu1")
+    assert "chain calls 0 " in [l for l in r3.stderr.splitlines() if l.startswith("[jmb shim]")][0]

@@ -294,3 +294,23 @@ def test_hadamards(oracle, have_ref):
         for _ in range(200):
             v = rng.integers(-30000, 30001, size=per)
             assert np.array_equal(oracle.hadamard(kind, v), ref.hadamard(kind, v)), kind
+
+
+def test_mv_predictor_matches_jm():
+    """oracle.pyoracle.mv_predictor (what the chain kernel k_mb_chain computes on the device, and what tests/test_gpu_frame.py
+    checks it against) vs JM's own GetMotionVectorPredictorNormal: every availability pattern, reference match pattern and
+    block shape / position that selects a directional rule."""
+    rng = np.random.default_rng(7)
+    shapes = [(16, 16, 0, 0), (16, 8, 0, 0), (16, 8, 0, 8), (8, 16, 0, 0), (8, 16, 8, 0), (8, 8, 8, 8), (8, 4, 0, 4), (4, 8, 4, 0), (4, 4, 12, 12)]
+    n = 0
+    for avail in range(8):
+        for refs in range(27):
+            for (bsx, bsy, mbx, mby) in shapes:
+                nb = []
+                for k in range(3):
+                    r = (refs // 3 ** k) % 3 - 1          # -1 (intra), 0, 1
+                    nb.append(((avail >> k) & 1, r, int(rng.integers(-300, 300)), int(rng.integers(-300, 300))))
+                for ref_frame in (0, 1):
+                    assert po.mv_predictor(nb, ref_frame, mbx, mby, bsx, bsy) == po.jmref_mv_predictor(nb, ref_frame, mbx, mby, bsx, bsy), (nb, ref_frame, bsx, bsy, mbx, mby)
+                    n += 1
+    assert n == 8 * 27 * 9 * 2
