@@ -496,6 +496,31 @@ int jmb_luma_residual_coding(jmb_ctx *ctx, const jmb_mb_pred *pred, int first_mb
 int jmb_pred_from_results(jmb_ctx *ctx, const jmb_me_res *res, int n_mb, int mode, jmb_mb_pred *pred, int loc);
 
 /* ---- measurement: CUDA events recorded on the context's stream around every kernel launch ----- */
+/* ---- deblocking: DeblockFrame (lencod/src/loopFilter.c:63-299) with the non-MBAFF strength and edge functions of
+ * lencod/src/loop_filter_normal.c (GetStrengthVer :53, GetStrengthHor :182, EdgeLoopLumaVer :310, EdgeLoopLumaHor :447,
+ * EdgeLoopChromaVer :585, EdgeLoopChromaHor :677), frame pictures, 8-bit, 4:0:0 / 4:2:0 / 4:2:2.  The picture is filtered IN
+ * PLACE, macroblock after macroblock in raster order as the standard has it (a macroblock's left edge reads samples its left
+ * neighbour's horizontal edges have already changed); the device walks the macroblocks as a wavefront x + 2y with the same
+ * result.  Per macroblock the caller gives what DeblockMb and the strength functions read: */
+#define JMB_DB_T8X8     1          /* Macroblock.luma_transform_size_8x8_flag */
+#define JMB_DB_CBP      2          /* Macroblock.cbp != 0 */
+#define JMB_DB_AVAIL_A  4          /* Macroblock.mbAvailA / mbAvailB: only read with DFDisableIdc 2 (no filtering across slice boundaries) */
+#define JMB_DB_AVAIL_B  8
+typedef struct jmb_db_mb {         /* 176 bytes */
+  uint8_t  mb_type;                /* Macroblock.mb_type: 0 PSKIP / BSKIP_DIRECT, 1 P16x16, 2 P16x8, 3 P8x16, 8 P8x8, 9 I4MB, 10 I16MB, 13 I8MB, 14 IPCM */
+  uint8_t  flags;                  /* JMB_DB_* */
+  int8_t   qp, qpc[2];             /* Macroblock.qp, qpc[0..1] (0 for IPCM, loopFilter.c:40-47) */
+  int8_t   df_disable_idc, df_alpha_c0_offset, df_beta_offset;      /* DFDisableIdc, DFAlphaC0Offset, DFBetaOffset */
+  uint32_t cbp_blk;                /* low 16 bits of Macroblock.cbp_blk: the coded luma 4x4 blocks, raster order */
+  uint32_t pad_;
+  int16_t  mv[2][16][2];           /* enc_picture->mv_info[][].mv[list] of the sixteen 4x4 blocks (raster order), quarter-pel */
+  int8_t   ref_id[2][16];          /* which picture mv_info[][].ref_pic[list] is: -1 = none (ref_idx -1), else an id equal exactly for equal pictures */
+} jmb_db_mb;
+/* luma / cb / cr: u8 planes of width x height (chroma: width/2 x height/2 or height); cb = cr = NULL with yuv_format 0.
+ * slice_type: JM's (0 P, 1 B, 2 I); SP / SI slices and MBAFF / field pictures are refused.  mbs: width/16 * height/16 entries, raster order. */
+int jmb_deblock_picture(jmb_ctx *ctx, uint8_t *luma, int pitch, uint8_t *cb, uint8_t *cr, int pitch_c, int width, int height, int yuv_format,
+                        int slice_type, int direct_8x8_inference, const jmb_db_mb *mbs, int loc);
+
 /* kernel names: subpel_planes, pack_cur, int_search, subpel_refine, dist, ffs_surfaces, forward,
  * quant_blocks, mc_tq, pred_from_results, gen_requests, epzs, chroma, deblock, argmin */
 int jmb_timing_enable(jmb_ctx *ctx, int on);      /* also clears the accumulated samples */

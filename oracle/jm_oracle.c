@@ -971,3 +971,131 @@ int jmo_chroma_rc(const uint8_t *src, const uint8_t *pred, int yuv, int qp_ac, i
       recon[y * 8 + x] = any ? (uint8_t)iclip(0, 255, ((rres[y][x] + 32) >> 6) + pred[y * 8 + x]) : pred[y * 8 + x];
   return cr_cbp;
 }
+
+/* ---- deblocking: DeblockFrame (lencod/src/loopFilter.c:63-299) + loop_filter_normal.c, non-MBAFF frame pictures, 8 bit -------
+ * Sequential restatement, macroblock after macroblock in raster order; pinned against JM's own DeblockFrame by
+ * tests/test_oracle_vs_ref.py::test_deblock_matches_jm (oracle/ref_harness.c::jmref_deblock). */
+static const unsigned char DB_ALPHA[52] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,4,4,5,6,7,8,9,10,12,13,15,17,20,22,25,28,32,36,40,45,50,56,63,71,80,90,101,113,127,144,162,182,203,226,255,255};
+static const unsigned char DB_BETA[52] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,2,2,2,3,3,3,3,4,4,4,6,6,7,7,8,8,9,9,10,10,11,11,12,12,13,13,14,14,15,15,16,16,17,17,18,18};
+static const unsigned char DB_CLIP[52][3] = {      /* CLIP_TAB[indexA][1..3] (loop_filter.h:36-45); [4] equals [3] and is never reached with strength < 4 */
+  {0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},
+  {0,0,1},{0,0,1},{0,0,1},{0,0,1},{0,1,1},{0,1,1},{1,1,1},{1,1,1},{1,1,1},{1,1,1},{1,1,2},{1,1,2},{1,1,2},{1,1,2},{1,2,3},{1,2,3},{2,2,3},
+  {2,2,4},{2,3,4},{2,3,4},{3,3,5},{3,4,6},{3,4,6},{4,5,7},{4,5,8},{4,6,9},{5,7,10},{6,8,11},{6,8,13},{7,10,14},{8,11,16},{9,12,18},{10,13,20},
+  {11,15,23},{13,17,25}};
+
+static int db_intra(int t) { return t == 9 || t == 10 || t == 13 || t == 14; }
+static int db_mvdiff(const int16_t *a, const int16_t *b) { return (abs(a[0] - b[0]) >= 4) | (abs(a[1] - b[1]) >= 4); }      /* compare_mvs, mvlimit 4 (frame) */
+
+/* strength of the 4-sample segment k of edge `edge` (0..3) in direction dir (0 vertical edge, 1 horizontal); Q = this macroblock,
+ * P = the macroblock on the other side (Q itself for inner edges): GetStrengthVer / GetStrengthHor */
+static int db_strength(int dir, int edge, int k, const jmo_db_mb *Q, const jmo_db_mb *P)
+{
+  if (db_intra(Q->mb_type) || db_intra(P->mb_type)) return edge == 0 ? 4 : 3;
+  int bq = dir ? edge * 4 + k : k * 4 + edge;                                       /* 4x4 block of Q at the edge */
+  int bp = edge ? (dir ? bq - 4 : bq - 1) : (dir ? 12 + k : k * 4 + 3);             /* the block across it */
+  if (((Q->cbp_blk >> bq) & 1) || ((P->cbp_blk >> bp) & 1)) return 2;
+  if (edge && (Q->mb_type == 1 || Q->mb_type == (dir ? 3 : 2))) return 0;
+  int p0 = Q->ref_id[0][bq], p1 = Q->ref_id[1][bq], q0 = P->ref_id[0][bp], q1 = P->ref_id[1][bp];      /* (JM names the Q-side block "p": symmetric) */
+  if (!((p0 == q0 && p1 == q1) || (p0 == q1 && p1 == q0))) return 1;
+  const int16_t *mp0 = Q->mv[0][bq], *mp1 = Q->mv[1][bq], *mq0 = P->mv[0][bp], *mq1 = P->mv[1][bp];
+  if (p0 != p1) return p0 == q0 ? (db_mvdiff(mp0, mq0) | db_mvdiff(mp1, mq1)) : (db_mvdiff(mp0, mq1) | db_mvdiff(mp1, mq0));
+  return (db_mvdiff(mp0, mq0) | db_mvdiff(mp1, mq1)) && (db_mvdiff(mp0, mq1) | db_mvdiff(mp1, mq0));
+}
+
+static int db_clip(int lo, int hi, int v) { return v < lo ? lo : v > hi ? hi : v; }
+
+/* one line of samples across a luma edge: q points at q0, `st` steps away from the edge on the q side */
+static void db_luma_line(uint8_t *q, int st, int bs, int alpha, int beta, int c0)
+{
+  uint8_t *p = q - st;
+  int L0 = p[0], R0 = q[0], L1 = p[-st], R1 = q[st];
+  if (abs(R0 - L0) >= alpha || abs(R0 - R1) >= beta || abs(L0 - L1) >= beta) return;
+  int L2 = p[-2 * st], R2 = q[2 * st];
+  if (bs == 4) {
+    int RL0 = L0 + R0, small_gap = abs(R0 - L0) < ((alpha >> 2) + 2);
+    int aq = (abs(R0 - R2) < beta) & small_gap, ap = (abs(L0 - L2) < beta) & small_gap;
+    if (ap) { int L3 = p[-3 * st]; p[0] = (uint8_t)((R1 + ((L1 + RL0) << 1) + L2 + 4) >> 3); p[-st] = (uint8_t)((L2 + L1 + RL0 + 2) >> 2); p[-2 * st] = (uint8_t)((((L3 + L2) << 1) + L2 + L1 + RL0 + 4) >> 3); }
+    else p[0] = (uint8_t)(((L1 << 1) + L0 + R1 + 2) >> 2);
+    if (aq) { int R3 = q[3 * st]; q[0] = (uint8_t)((L1 + ((R1 + RL0) << 1) + R2 + 4) >> 3); q[st] = (uint8_t)((R2 + R0 + L0 + R1 + 2) >> 2); q[2 * st] = (uint8_t)((((R3 + R2) << 1) + R2 + R1 + RL0 + 4) >> 3); }
+    else q[0] = (uint8_t)(((R1 << 1) + R0 + L1 + 2) >> 2);
+  } else {
+    int RL0 = (L0 + R0 + 1) >> 1, aq = abs(R0 - R2) < beta, ap = abs(L0 - L2) < beta, tc0 = c0 + ap + aq;
+    int dif = db_clip(-tc0, tc0, (((R0 - L0) << 2) + (L1 - R1) + 4) >> 3);
+    if (ap) p[-st] = (uint8_t)(L1 + db_clip(-c0, c0, (L2 + RL0 - (L1 << 1)) >> 1));
+    if (dif) { p[0] = (uint8_t)db_clip(0, 255, L0 + dif); q[0] = (uint8_t)db_clip(0, 255, R0 - dif); }
+    if (aq) q[st] = (uint8_t)(R1 + db_clip(-c0, c0, (R2 + RL0 - (R1 << 1)) >> 1));
+  }
+}
+
+static void db_chroma_line(uint8_t *q, int st, int bs, int alpha, int beta, int c0)
+{
+  uint8_t *p = q - st;
+  int L0 = p[0], R0 = q[0], L1 = p[-st], R1 = q[st];
+  if (abs(R0 - L0) >= alpha || abs(R0 - R1) >= beta || abs(L0 - L1) >= beta) return;
+  if (bs == 4) { p[0] = (uint8_t)(((L1 << 1) + L0 + R1 + 2) >> 2); q[0] = (uint8_t)(((R1 << 1) + R0 + L1 + 2) >> 2); }
+  else {
+    int tc0 = c0 + 1, dif = db_clip(-tc0, tc0, (((R0 - L0) << 2) + (L1 - R1) + 4) >> 3);
+    if (dif) { p[0] = (uint8_t)db_clip(0, 255, L0 + dif); q[0] = (uint8_t)db_clip(0, 255, R0 - dif); }
+  }
+}
+
+void jmo_deblock(uint8_t *luma, int pitch, uint8_t *cb, uint8_t *cr, int pitch_c, int w, int h, int yuv, int slice_type, int direct8x8inf,
+                 const jmo_db_mb *mbs)
+{
+  /* chroma_edge[dir][edge][yuv_format] and pelnum_cr (loop_filter.h:47-58), for 4:2:0 (1) and 4:2:2 (2) */
+  static const int cedge[2][4][3] = {{{-4, 0, 0}, {-4, -4, -4}, {-4, 4, 4}, {-4, -4, -4}}, {{-4, 0, 0}, {-4, -4, 4}, {-4, 4, 8}, {-4, -4, 12}}};
+  static const int pelnum[2][3] = {{0, 8, 16}, {0, 8, 8}};
+  const int mbw = w / 16, mbh = h / 16;
+  for (int my = 0; my < mbh; my++)
+    for (int mx = 0; mx < mbw; mx++) {
+      const jmo_db_mb *Q = &mbs[my * mbw + mx];
+      if (Q->df_disable_idc == 1) continue;
+      const int t8 = Q->flags & 1, cbp = Q->flags & 2;
+      int edge0[2] = {mx != 0, my != 0};
+      if (Q->df_disable_idc == 2) { edge0[0] = (Q->flags & 4) != 0; edge0[1] = (Q->flags & 8) != 0; }
+      for (int dir = 0; dir < 2; dir++)
+        for (int edge = 0; edge < 4; edge++) {
+          const int luma_on = !(t8 && (edge & 1));
+          if (!cbp) {      /* loopFilter.c:153-164, :209-220 */
+            if (!luma_on && (dir == 0 || yuv == 1)) continue;
+            if (edge > 0 && (slice_type == 0 || slice_type == 1)) {
+              if ((Q->mb_type == 0 && slice_type == 0) || Q->mb_type == 1 || Q->mb_type == (dir ? 3 : 2)) continue;
+              if ((edge & 1) && (Q->mb_type == (dir ? 2 : 3) || (Q->mb_type == 0 && slice_type == 1 && direct8x8inf))) continue;
+            }
+          }
+          if (!(edge || edge0[dir])) continue;
+          const jmo_db_mb *P = edge ? Q : (dir ? Q - mbw : Q - 1);
+          int bs[4], any = 0;
+          for (int k = 0; k < 4; k++) { bs[k] = db_strength(dir, edge, k, Q, P); any |= bs[k]; }
+          if (!any) continue;
+          if (luma_on) {
+            const int qp = (P->qp + Q->qp + 1) >> 1, ia = db_clip(0, 51, qp + Q->df_alpha_c0_offset), ib = db_clip(0, 51, qp + Q->df_beta_offset);
+            const int alpha = DB_ALPHA[ia], beta = DB_BETA[ib];
+            if (alpha | beta)
+              for (int i = 0; i < 16; i++) {
+                const int s = bs[i >> 2];
+                if (!s) continue;
+                uint8_t *q = dir ? luma + (size_t)(my * 16 + edge * 4) * pitch + mx * 16 + i : luma + (size_t)(my * 16 + i) * pitch + mx * 16 + edge * 4;
+                db_luma_line(q, dir ? pitch : 1, s, alpha, beta, s < 4 ? DB_CLIP[ia][s - 1] : 0);
+              }
+          }
+          if (yuv == 1 || yuv == 2) {
+            const int ec = cedge[dir][edge][yuv];
+            if (ec < 0) continue;
+            const int n = pelnum[dir][yuv], cw = 8, chh = yuv == 1 ? 8 : 16;
+            for (int uv = 0; uv < 2; uv++) {
+              uint8_t *pl = uv ? cr : cb;
+              const int qp = (P->qpc[uv] + Q->qpc[uv] + 1) >> 1, ia = db_clip(0, 51, qp + Q->df_alpha_c0_offset), ib = db_clip(0, 51, qp + Q->df_beta_offset);
+              const int alpha = DB_ALPHA[ia], beta = DB_BETA[ib];
+              if (!(alpha | beta)) continue;
+              for (int i = 0; i < n; i++) {
+                const int s = bs[n == 8 ? i >> 1 : i >> 2];      /* Strength[(PelNum == 8) ? ((pel >> 1) << 2) + (pel & 1) : pel] */
+                if (!s) continue;
+                uint8_t *q = dir ? pl + (size_t)(my * chh + ec) * pitch_c + mx * cw + i : pl + (size_t)(my * chh + i) * pitch_c + mx * cw + ec;
+                db_chroma_line(q, dir ? pitch_c : 1, s, alpha, beta, s < 4 ? DB_CLIP[ia][s - 1] : 0);
+              }
+            }
+          }
+        }
+    }
+}

@@ -118,6 +118,16 @@ void jmo_epzs_batch(const jmo_ref *r, const uint16_t *cur, int cur_stride, const
 void jmo_mc_tq_modes_mb(const jmo_ref *r, const uint16_t *cur, int cur_stride, int mb_x, int mb_y, const int16_t *mv41, int n, int qp,
                         const int *qparams, const uint8_t *scan, const uint8_t *c_cost, int is_cavlc, unsigned mode_mask, int16_t *levels);
 
+/* deblocking of a whole picture in place (DeblockFrame, loopFilter.c:63); jmo_db_mb has the layout of jmb_db_mb (include/jmb200.h) */
+typedef struct jmo_db_mb {
+  uint8_t mb_type, flags; int8_t qp, qpc[2], df_disable_idc, df_alpha_c0_offset, df_beta_offset;
+  uint32_t cbp_blk, pad_;
+  int16_t mv[2][16][2];
+  int8_t ref_id[2][16];
+} jmo_db_mb;
+void jmo_deblock(uint8_t *luma, int pitch, uint8_t *cb, uint8_t *cr, int pitch_c, int w, int h, int yuv, int slice_type, int direct8x8inf,
+                 const jmo_db_mb *mbs);
+
 #ifdef __cplusplus
 }
 #endif

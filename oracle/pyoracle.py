@@ -490,3 +490,77 @@ def jmref_mv_predictor(nb, ref_frame, mb_x, mb_y, bsx, bsy):
     out = np.zeros(2, np.int16)
     L.jmref_mv_predictor(np.ascontiguousarray(nb, np.int32).reshape(-1), ref_frame, mb_x, mb_y, bsx, bsy, out)
     return int(out[0]), int(out[1])
+
+
+DB_MB = np.dtype([("mb_type", "u1"), ("flags", "u1"), ("qp", "i1"), ("qpc", "i1", (2,)), ("df_disable_idc", "i1"), ("df_alpha_c0_offset", "i1"),
+                  ("df_beta_offset", "i1"), ("cbp_blk", "<u4"), ("pad_", "<u4"), ("mv", "<i2", (2, 16, 2)), ("ref_id", "i1", (2, 16))])
+assert DB_MB.itemsize == 176
+DB_T8X8, DB_CBP, DB_AVAIL_A, DB_AVAIL_B = 1, 2, 4, 8
+
+
+def deblock(luma, cb, cr, yuv, slice_type, mbs, direct8x8inf=1):
+    """jmo_deblock (oracle/jm_oracle.c): DeblockFrame restated; returns the filtered planes."""
+    L = C.CDLL(ORACLE_SO)
+    luma = np.ascontiguousarray(luma, np.uint8).copy(); h, w = luma.shape
+    cb = np.ascontiguousarray(cb, np.uint8).copy() if yuv else None; cr = np.ascontiguousarray(cr, np.uint8).copy() if yuv else None
+    mbs = np.ascontiguousarray(mbs, DB_MB)
+    assert len(mbs) == (w // 16) * (h // 16)
+    L.jmo_deblock.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.jmo_deblock(luma.ctypes.data, w, cb.ctypes.data if yuv else None, cr.ctypes.data if yuv else None, w // 2, w, h, yuv, slice_type, direct8x8inf, mbs.ctypes.data)
+    return luma, cb, cr
+
+
+def jmref_deblock(luma, cb, cr, yuv, slice_type, mbs, direct8x8inf=1):
+    """The same through JM's own DeblockFrame (oracle/_ref/libjmref.so)."""
+    L = C.CDLL(REF_SO)
+    luma = np.ascontiguousarray(luma, np.uint8).copy(); h, w = luma.shape
+    cb = np.ascontiguousarray(cb, np.uint8).copy() if yuv else None; cr = np.ascontiguousarray(cr, np.uint8).copy() if yuv else None
+    mbs = np.ascontiguousarray(mbs, DB_MB)
+    L.jmref_deblock.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.jmref_deblock(luma.ctypes.data, cb.ctypes.data if yuv else None, cr.ctypes.data if yuv else None, w, h, yuv, slice_type, direct8x8inf, mbs.ctypes.data)
+    return luma, cb, cr
+
+
+def random_deblock_picture(rng, w, h, yuv, slice_type, intra_share=0.15, idc=0):
+    """A synthetic coded picture for the deblocking tests: blocky samples (so that edges are filtered), macroblock types, coded-block
+    flags, motion and references of every kind the strength rules tell apart, QPs on both sides of the filter's on/off threshold."""
+    mbw, mbh = w // 16, h // 16
+    base = rng.integers(40, 200, (h // 4, w // 4)).astype(np.int32)
+    luma = np.clip(np.kron(base, np.ones((4, 4), np.int32)) + rng.integers(-6, 7, (h, w)), 0, 255).astype(np.uint8)
+    hc = h // 2 if yuv == 1 else h
+    planes = []
+    for _ in range(2):
+        b = rng.integers(60, 190, ((hc + 3) // 4, w // 8)).astype(np.int32)
+        planes.append(np.clip(np.kron(b, np.ones((4, 4), np.int32))[:hc] + rng.integers(-4, 5, (hc, w // 2)), 0, 255).astype(np.uint8))
+    mbs = np.zeros(mbw * mbh, DB_MB)
+    inter = [0, 1, 2, 3, 8] 
+    for i, m in enumerate(mbs):
+        is_intra = slice_type == 2 or rng.random() < intra_share
+        m["mb_type"] = int(rng.choice([9, 10, 13, 14])) if is_intra else int(rng.choice(inter))
+        t8 = (m["mb_type"] == 13) or (m["mb_type"] in (1, 2, 3, 8) and rng.random() < 0.3)
+        coded = rng.random() < 0.6 and m["mb_type"] != 0
+        m["cbp_blk"] = int(rng.integers(0, 1 << 16)) if coded else 0
+        if coded and rng.random() < 0.2:
+            m["cbp_blk"] = 0            # cbp != 0 may come from chroma alone
+        m["flags"] = (DB_T8X8 if t8 else 0) | (DB_CBP if coded else 0) | (DB_AVAIL_A if (i % mbw and rng.random() < 0.8) else 0) | (DB_AVAIL_B if (i >= mbw and rng.random() < 0.8) else 0)
+        q = int(rng.choice([12, 20, 26, 30, 36, 44, 51])); m["qp"] = 0 if m["mb_type"] == 14 else q
+        m["qpc"] = (0, 0) if m["mb_type"] == 14 else (max(0, q - int(rng.integers(0, 6))), max(0, q - int(rng.integers(0, 6))))
+        m["df_disable_idc"] = idc if rng.random() < 0.95 else 1
+        m["df_alpha_c0_offset"] = int(rng.choice([0, 0, -4, 6])); m["df_beta_offset"] = int(rng.choice([0, 0, 2, -6]))
+        # motion: per partition of the type, references from a small pool; B pictures use both lists
+        t = int(m["mb_type"])
+        part = {0: (4, 4), 1: (4, 4), 2: (4, 2), 3: (2, 4)}.get(t)
+        for k in range(16):
+            bx, by = k % 4, k // 4
+            if part is None:
+                key = (bx // int(rng.choice([1, 2])), by // int(rng.choice([1, 2])), int(rng.integers(0, 3)))
+            else:
+                key = (bx // part[0], by // part[1], 0)
+            r2 = np.random.default_rng(hash((i, key, t)) & 0xffffffff)
+            for l in range(2):
+                use = (l == 0) if slice_type != 1 else (r2.random() < 0.7)
+                if is_intra:
+                    use = False
+                m["ref_id"][l][k] = int(r2.integers(0, 3)) if use else -1
+                m["mv"][l][k] = r2.integers(-9, 10, 2) if (use or r2.random() < 0.3) else (0, 0)
+    return luma, planes[0], planes[1], mbs

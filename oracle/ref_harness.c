@@ -629,3 +629,75 @@ void jmref_mv_predictor(const int *nb, int ref_frame, int mb_x, int mb_y, int bs
   mb.GetMVPredictor(&mb, block, &pmv, (short)ref_frame, rows, LIST_0, mb_x, mb_y, bsx, bsy);
   out[0] = pmv.mv_x; out[1] = pmv.mv_y;
 }
+
+/* JM's own DeblockFrame (lencod/src/loopFilter.c:63, non-MBAFF functions of loop_filter_normal.c) on a caller-described picture.
+ * mb = n records of 176 bytes in the layout of jmb_db_mb (include/jmb200.h); planes are 8-bit samples, filtered in place. */
+extern void DeblockFrame(VideoParameters *p_Vid, imgpel **imgY, imgpel ***imgUV);
+extern void get_mb_block_pos_normal(BlockPos *PicPos, int mb_addr, short *x, short *y);
+void jmref_deblock(uint8_t *luma, uint8_t *cb, uint8_t *cr, int w, int h, int yuv, int slice_type, int direct8x8inf, const uint8_t *mb)
+{
+  VideoParameters *p_Vid = (VideoParameters *)calloc(1, sizeof(VideoParameters));
+  seq_parameter_set_rbsp_t *sps = (seq_parameter_set_rbsp_t *)calloc(1, sizeof(*sps));
+  Slice *sl = (Slice *)calloc(1, sizeof(Slice));
+  StorablePicture *pic = (StorablePicture *)calloc(1, sizeof(StorablePicture));
+  const int mbw = w / 16, mbh = h / 16, n = mbw * mbh, wc = w / 2, hc = yuv == 1 ? h / 2 : h;
+  imgpel **imgY = NULL, **uvp[2] = {NULL, NULL}, ***imgUV = NULL;
+  int i, k, l, x, y;
+  p_Vid->PicSizeInMbs = n; p_Vid->PicWidthInMbs = mbw;
+  p_Vid->structure = FRAME; p_Vid->mb_aff_frame_flag = 0; p_Vid->P444_joined = 0;
+  p_Vid->yuv_format = yuv; sps->chroma_format_idc = yuv; sps->direct_8x8_inference_flag = direct8x8inf;
+  p_Vid->active_sps = sps;
+  p_Vid->mb_size[IS_LUMA][0] = p_Vid->mb_size[IS_LUMA][1] = 16;
+  p_Vid->mb_size[IS_CHROMA][0] = 8; p_Vid->mb_size[IS_CHROMA][1] = yuv == 1 ? 8 : 16;
+  p_Vid->width_padded = w; p_Vid->width_cr = wc; p_Vid->pad_size_uv_x = 0;
+  p_Vid->bitdepth_scale[IS_LUMA] = p_Vid->bitdepth_scale[IS_CHROMA] = 1;
+  p_Vid->max_pel_value_comp[0] = p_Vid->max_pel_value_comp[1] = p_Vid->max_pel_value_comp[2] = 255;
+  p_Vid->get_mb_block_pos = get_mb_block_pos_normal;
+  p_Vid->PicPos = (BlockPos *)calloc(n + 1, sizeof(BlockPos));
+  for (i = 0; i <= n; i++) { p_Vid->PicPos[i].x = (short)(i % mbw); p_Vid->PicPos[i].y = (short)(i / mbw); }
+  p_Vid->mb_data = (Macroblock *)calloc(n, sizeof(Macroblock));
+  p_Vid->enc_picture = pic;
+  pic->mv_info = (PicMotionParams **)calloc(h / 4, sizeof(PicMotionParams *));
+  pic->mv_info[0] = (PicMotionParams *)calloc((size_t)(h / 4) * (w / 4), sizeof(PicMotionParams));
+  for (y = 1; y < h / 4; y++) pic->mv_info[y] = pic->mv_info[0] + (size_t)y * (w / 4);
+  sl->slice_type = slice_type; sl->p_Vid = p_Vid;
+  for (i = 0; i < n; i++)
+  {
+    const uint8_t *r = mb + (size_t)i * 176;
+    Macroblock *m = &p_Vid->mb_data[i];
+    const int16_t *mv = (const int16_t *)(r + 16);
+    const int8_t *rid = (const int8_t *)(r + 144);
+    m->p_Vid = p_Vid; m->p_Slice = sl; m->mbAddrX = i;
+    m->mb_type = r[0];
+    m->luma_transform_size_8x8_flag = (r[1] & 1) != 0; m->cbp = (r[1] & 2) ? 1 : 0;
+    m->mbAvailA = (r[1] & 4) != 0; m->mbAvailB = (r[1] & 8) != 0;
+    m->qp = (int8_t)r[2]; m->qpc[0] = (int8_t)r[3]; m->qpc[1] = (int8_t)r[4];
+    m->DFDisableIdc = (int8_t)r[5]; m->DFAlphaC0Offset = (int8_t)r[6]; m->DFBetaOffset = (int8_t)r[7];
+    m->cbp_blk = *(const uint32_t *)(r + 8);
+    for (l = 0; l < 2; l++)
+      for (k = 0; k < 16; k++)
+      {
+        PicMotionParams *p = &pic->mv_info[(i / mbw) * 4 + k / 4][(i % mbw) * 4 + k % 4];
+        p->mv[l].mv_x = mv[(l * 16 + k) * 2]; p->mv[l].mv_y = mv[(l * 16 + k) * 2 + 1];
+        p->ref_idx[l] = (char)(rid[l * 16 + k] < 0 ? -1 : 0);
+        p->ref_pic[l] = rid[l * 16 + k] < 0 ? NULL : (StorablePicture *)(uintptr_t)(4096 + 64 * rid[l * 16 + k]);      /* only ever compared */
+      }
+  }
+  get_mem2Dpel(&imgY, h, w);
+  for (y = 0; y < h; y++) for (x = 0; x < w; x++) imgY[y][x] = luma[(size_t)y * w + x];
+  if (yuv)
+  {
+    get_mem2Dpel(&uvp[0], hc, wc); get_mem2Dpel(&uvp[1], hc, wc);
+    for (y = 0; y < hc; y++) for (x = 0; x < wc; x++) { uvp[0][y][x] = cb[(size_t)y * wc + x]; uvp[1][y][x] = cr[(size_t)y * wc + x]; }
+    imgUV = uvp;
+  }
+  DeblockFrame(p_Vid, imgY, imgUV);
+  for (y = 0; y < h; y++) for (x = 0; x < w; x++) luma[(size_t)y * w + x] = (uint8_t)imgY[y][x];
+  if (yuv)
+  {
+    for (y = 0; y < hc; y++) for (x = 0; x < wc; x++) { cb[(size_t)y * wc + x] = (uint8_t)uvp[0][y][x]; cr[(size_t)y * wc + x] = (uint8_t)uvp[1][y][x]; }
+    free_mem2Dpel(uvp[0]); free_mem2Dpel(uvp[1]);
+  }
+  free_mem2Dpel(imgY);
+  free(pic->mv_info[0]); free(pic->mv_info); free(pic); free(p_Vid->mb_data); free(p_Vid->PicPos); free(sl); free(sps); free(p_Vid);
+}

@@ -314,3 +314,21 @@ def test_mv_predictor_matches_jm():
                     assert po.mv_predictor(nb, ref_frame, mbx, mby, bsx, bsy) == po.jmref_mv_predictor(nb, ref_frame, mbx, mby, bsx, bsy), (nb, ref_frame, bsx, bsy, mbx, mby)
                     n += 1
     assert n == 8 * 27 * 9 * 2
+
+
+@pytest.mark.parametrize("yuv,slice_type,idc", [(1, 0, 0), (1, 1, 0), (2, 0, 0), (2, 1, 2), (0, 0, 0), (1, 2, 0), (1, 0, 2)])
+def test_deblock_matches_jm(yuv, slice_type, idc):
+    """jmo_deblock (the CPU restatement the GPU deblocking kernel is checked against) vs JM's own DeblockFrame on synthetic coded
+    pictures: P / B / I slices, 4:0:0 / 4:2:0 / 4:2:2, 8x8-transform macroblocks, skipped and coefficient-free macroblocks,
+    differing references and vectors on both lists, QPs around the filter threshold, filter offsets, DFDisableIdc 0 / 1 / 2."""
+    for seed in range(3):
+        rng = np.random.default_rng(100 * yuv + 10 * slice_type + seed)
+        w, h = 96, 64
+        luma, cb, cr, mbs = po.random_deblock_picture(rng, w, h, yuv, slice_type, idc=idc)
+        want = po.jmref_deblock(luma, cb, cr, yuv, slice_type, mbs)
+        got = po.deblock(luma, cb, cr, yuv, slice_type, mbs)
+        assert np.array_equal(got[0], want[0]), np.argwhere(got[0] != want[0])[:5]
+        assert (luma != want[0]).mean() > 0.05, "the picture must actually be filtered"
+        if yuv:
+            assert np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+            assert (cb != want[1]).mean() > 0.02
