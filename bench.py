@@ -435,16 +435,19 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     launch_ms = k_ms / max(1, k_n)
+    if wl.epzs:      # the search is two launches (integer stage, sub-pel stage): the roofline line is about both together
+        launch_ms = kernel_break["epzs"] + kernel_break["subpel_refine"]
     if wl.epzs:
         # k_epzs: algorithmic bytes = per search the source block once + one reference block per distortion evaluated (u8 samples)
         # + request tables in / results out; the evaluation counts come from the kernel's own n_evals on a sample of set 0
         alg_bytes, evals_per_search = wl.epzs_algorithmic_bytes()
         achieved = alg_bytes / (launch_ms / 1e3) / 1e9
-        out["roofline"] = {"bound": "hbm", "kernel": "k_epzs", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        out["roofline"] = {"bound": "hbm", "kernel": "k_epzs_int + k_epzs_sub", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                            "traffic": None, "peak_source": "measured" if peaks else "fallback", "algorithmic_bytes_per_launch": alg_bytes,
                            "launch_ms": launch_ms, "distortions_per_search": evals_per_search,
-                           "note": "EPZS evaluates ~10-60 scattered block distortions per search, each decided by the one before: the kernel is "
-                                   "bound by L2 latency and the serial walk, not by HBM bandwidth -- DESIGN.md 3"}
+                           "note": "EPZS evaluates ~10-60 scattered block distortions per search, each step decided by the one before: the "
+                                   "kernels are bound by instruction issue and the barriers between a macroblock's rounds, not by HBM "
+                                   "bandwidth -- DESIGN.md 3"}
     else:
         achieved = BYTES_PER_MB_REF * n_mb / (launch_ms / 1e3) / 1e9
         traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (tools/ncu_summary.py)
@@ -484,12 +487,59 @@ def run_ours(args):
         out["alu_roofline"] = {"bound": "alu-pipe", "achieved": alu_ops / (launch_ms / 1e3), "peak": alu_peak, "unit": "lane-ops/s",
                                "frac": alu_ops / (launch_ms / 1e3) / alu_peak,
                                "note": "minimum ALU-pipe instructions of the algorithm / launch time, vs 64 lanes/clk/SM x 148 SMs x SM clock"}
+    if rank == 0 and world == 1 and args.config == 2:
+        out["next_rows"] = {"deblock": deblock_line(ctx, api, torch, wl.W, wl.H, local, with_cpu=not args.no_cpu)}
+        try:      # the re-linked encoder against stock JM on this configuration (tools/dropin_1080p.py, measured on a B200 box, committed)
+            enc = json.load(open(os.path.join(ROOT, "profiles", "r02_dropin_1080p.json")))["1080p"]
+            out["encoder"] = {"source": "profiles/r02_dropin_1080p.json (tools/dropin_1080p.py): stock lencod vs the same JM objects re-linked with libjmb200 "
+                                        "(ME on the device, run-ahead chains), 1080p FullSearch +-32, 1 reference",
+                              "frames": enc["frames"], "stock_wall_s": enc["stock"]["wall_s"], "dropin_wall_s": enc["dropin_me"]["wall_s"],
+                              "stock_me_time": enc["stock"]["total_me_time"], "dropin_me_time": enc["dropin_me"]["total_me_time"],
+                              "bitstream_identical": enc["dropin_me"]["bitstream_identical"]}
+        except Exception:
+            pass
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(wl, ctx=ctx, api=api, budget_s=args.cpu_seconds)
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def deblock_line(ctx, api, torch, w, h, local, with_cpu=True, iters=20):
+    """The deblocking row measured on its own: DeblockFrame of one synthetic coded picture, device-resident planes and
+    macroblock records, CUDA events; the CPU restatement of the same picture beside it (and its result compared)."""
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(77)
+    luma, cb, cr, mbs = po.random_deblock_picture(rng, w, h, 1, 0)
+    dev = f"cuda:{local}"
+    pitch, pitch_c = (w + 127) // 128 * 128, (w // 2 + 127) // 128 * 128
+    def padded(a, p):
+        o = np.zeros((a.shape[0], p), np.uint8); o[:, :a.shape[1]] = a
+        return o
+    src = [torch.from_numpy(padded(a, p)).to(dev) for a, p in ((luma, pitch), (cb, pitch_c), (cr, pitch_c))]
+    d = [t.clone() for t in src]
+    d_mbs = torch.from_numpy(mbs.view(np.uint8).copy()).to(dev)
+    ctx.timing(True)
+    for it in range(iters + 2):
+        for a, b in zip(d, src):
+            a.copy_(b)
+        torch.cuda.synchronize()
+        if it == 2:
+            ctx.timing(True)
+        ctx.deblock_picture_dev(d[0].data_ptr(), pitch, d[1].data_ptr(), d[2].data_ptr(), pitch_c, w, h, 1, 0, d_mbs.data_ptr())
+        ctx.sync()
+    ms, n = ctx.timing_get("deblock")
+    ctx.timing(False)
+    n_mb = (w // 16) * (h // 16)
+    res = {"kernel": "k_deblock", "picture": f"{w}x{h} 4:2:0, P slice, synthetic coded picture", "gpu_ms_per_picture": ms / max(1, n),
+           "macroblocks_per_s": n_mb / (ms / max(1, n) / 1e3), "wavefront_steps": w // 16 + 2 * (h // 16 - 1),
+           "algorithmic_bytes": 2 * (w * h * 3 // 2) + n_mb * 176}
+    if with_cpu:
+        t0 = time.perf_counter(); want = po.deblock(luma, cb, cr, 1, 0, mbs); res["cpu_port_ms_per_picture"] = 1e3 * (time.perf_counter() - t0)
+        got = [t.cpu().numpy()[:, :a.shape[1]] for t, a in zip(d, (luma, cb, cr))]
+        res["gpu_matches_cpu"] = bool(all(np.array_equal(g, wv) for g, wv in zip(got, want)))
+    return res
 
 
 _JM = {}

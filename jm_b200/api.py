@@ -27,6 +27,9 @@ CHAIN_NB = np.dtype([("mv_x", "<i2"), ("mv_y", "<i2"), ("ref_idx", "i1"), ("avai
 CHAIN_REQ = np.dtype([("req", ME_REQ), ("nb", CHAIN_NB, (3,)), ("jm_ref", "i1"), ("chain", "i1"), ("pad_", "i1", (6,))])
 CHAIN_RES = np.dtype([("res", ME_RES), ("pred_x", "<i2"), ("pred_y", "<i2"), ("center_x", "<i2"), ("center_y", "<i2"), ("status", "<i4"), ("pad_", "<i4")])
 CHAIN_DONE, CHAIN_UNCOVERED, CHAIN_SKIPPED = range(3)
+DB_MB = np.dtype([("mb_type", "u1"), ("flags", "u1"), ("qp", "i1"), ("qpc", "i1", (2,)), ("df_disable_idc", "i1"), ("df_alpha_c0_offset", "i1"),
+                  ("df_beta_offset", "i1"), ("cbp_blk", "<u4"), ("pad_", "<u4"), ("mv", "<i2", (2, 16, 2)), ("ref_id", "i1", (2, 16))])      # jmb_db_mb, 176 bytes
+DB_T8X8, DB_CBP, DB_AVAIL_A, DB_AVAIL_B = 1, 2, 4, 8
 MB_PRED = np.dtype([("mv", "<i2", (16, 2)), ("b8mode", "u1", (4,)), ("ref", "u1", (4,))])
 QUANT_DESC = np.dtype([("n", "<i4"), ("qp", "<i4"), ("is_cavlc", "<i4"), ("around", "<i4"), ("adapt_rnd_weight", "<i4"),
                        ("qparams", "<i4", (64, 3)), ("scan", "u1", (64, 2)), ("c_cost", "u1", (64,))])
@@ -126,6 +129,7 @@ def load_library():
     L.jmb_mb_surfaces.argtypes = [vp, i, i, i, i, i, i]
     L.jmb_mb_search.argtypes = [vp, vp, vp]
     L.jmb_mb_chain.argtypes = [vp, vp, i, vp, i, vp]
+    L.jmb_deblock_picture.argtypes = [vp, vp, i, vp, vp, i, i, i, i, i, i, vp, i]
     L.jmb_epzs_search.argtypes = [vp, vp, i, vp, i, vp, i]
     L.jmb_epzs_search_frame.argtypes = [vp, vp, vp, i, vp, vp, i]
     L.jmb_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
@@ -449,6 +453,21 @@ class Context:
         lim = np.ascontiguousarray(mv_limits, np.int32)
         self._ck(self.L.jmb_mb_chain(self.h, _ptr(reqs), len(reqs), _ptr(lim), int_divide, _ptr(res)))
         return res
+
+    def deblock_picture(self, luma, cb, cr, yuv, slice_type, mbs, direct8x8inf=1):
+        """DeblockFrame on host planes (u8); returns the filtered planes."""
+        luma = np.ascontiguousarray(luma, np.uint8).copy(); h, w = luma.shape
+        cb = np.ascontiguousarray(cb, np.uint8).copy() if yuv else None; cr = np.ascontiguousarray(cr, np.uint8).copy() if yuv else None
+        mbs = np.ascontiguousarray(mbs, DB_MB)
+        if len(mbs) != (w // 16) * (h // 16):
+            raise ValueError("one jmb_db_mb per macroblock")
+        self._ck(self.L.jmb_deblock_picture(self.h, _ptr(luma), w, _ptr(cb) if yuv else None, _ptr(cr) if yuv else None, w // 2, w, h, yuv, slice_type,
+                                            direct8x8inf, _ptr(mbs), HOST))
+        return luma, cb, cr
+
+    def deblock_picture_dev(self, d_luma, pitch, d_cb, d_cr, pitch_c, w, h, yuv, slice_type, d_mbs, direct8x8inf=1):
+        """The same in place on device-resident planes / records (raw device pointers); only enqueues work."""
+        self._ck(self.L.jmb_deblock_picture(self.h, d_luma, pitch, d_cb, d_cr, pitch_c, w, h, yuv, slice_type, direct8x8inf, d_mbs, DEVICE))
 
     def block_distortion(self, metric, n, diff, thres=None):
         diff = np.ascontiguousarray(diff, np.int16).reshape(-1, n * n)

@@ -176,6 +176,7 @@ void jmb_destroy(jmb_ctx *ctx) {
   for (int i = 0; i < JMB_MAX_REFS; i++) if (ctx->surf[i].buf) cudaFree(ctx->surf[i].buf);
   if (ctx->mbox) cudaFreeHost(ctx->mbox);
   if (ctx->d_one) cudaFree(ctx->d_one);
+  if (ctx->d_db) cudaFree(ctx->d_db);
   if (ctx->d_mvpred) cudaFree(ctx->d_mvpred);
   if (ctx->d_res8) cudaFree(ctx->d_res8);
   if (ctx->d_heads) cudaFree(ctx->d_heads);

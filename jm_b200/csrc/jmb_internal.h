@@ -71,6 +71,8 @@ struct jmb_ctx {
   void *d_heads = nullptr; size_t d_heads_cap = 0;
   void *d_tokens = nullptr; size_t d_tokens_cap = 0;
   unsigned *d_tok_count = nullptr; unsigned *h_tok_count = nullptr;
+  // deblocking: ticket counter + per-macroblock completion flags (k_deblock), stamped with db_serial
+  void *d_db = nullptr; size_t d_db_cap = 0; int db_serial = 0;
   // peer buffers opened with jmb_peer_open (cudaIpcOpenMemHandle is expensive: one mapping per handle)
   struct Peer { unsigned char handle[JMB_IPC_HANDLE_BYTES]; void *mapped; };
   Peer peers[32]; int n_peers = 0;

@@ -106,12 +106,13 @@ void    __real_ihadamard2x2(int *, int *);
 distblk __real_EPZS_integer_motion_estimation(Macroblock *, MotionVector *, MEBlock *, distblk, int);
 distblk __real_EPZS_sub_pel_motion_estimation(Macroblock *, MotionVector *, MEBlock *, distblk, int *);
 void    __real_select_distortion(VideoParameters *p_Vid, InputParameters *p_Inp);
+void    __real_DeblockFrame(VideoParameters *p_Vid, imgpel **imgY, imgpel ***imgUV);
 distblk __real_computeSAD(StorablePicture *, MEBlock *, distblk, MotionVector *);
 distblk __real_computeSSE(StorablePicture *, MEBlock *, distblk, MotionVector *);
 distblk __real_computeSATD(StorablePicture *, MEBlock *, distblk, MotionVector *);
 
 
-enum { FAM_PLANES = 1, FAM_ME = 2, FAM_SUBPEL = 4, FAM_TQ = 8, FAM_DIST = 16 };
+enum { FAM_PLANES = 1, FAM_ME = 2, FAM_SUBPEL = 4, FAM_TQ = 8, FAM_DIST = 16, FAM_DEBLOCK = 32 };
 enum { AHEAD_N = 8 * JMB_CHAIN_MAX };      /* answers kept ahead of JM: a call's worth for each of several references */
 
 static struct
@@ -140,6 +141,7 @@ static struct
   struct { int valid, pos_x, pos_y, blocktype, list, ref_idx, test8x8, lambda, mode, R; unsigned long pic; MotionVector pred, center; jmb_me_res res; } ahead[AHEAD_N];
   int              chains_off;        /* JMB_SHIM_CHAIN=0: one device call per search (A/B of the run-ahead) */
   unsigned long    chain_calls, chain_hits, chain_stale;
+  unsigned long    deblocked, deblock_verified;
 } S;
 
 /* JM's convention for fatal conditions is error(text, code) -> message on stderr, exit(code) (lencod/src/lencod.c).
@@ -167,11 +169,11 @@ static unsigned long chroma_verified;
 static void report(void)
 {
   if (S.init == 1 && S.verify)
-    fprintf(stderr, "[jmb shim] luma_residual_coding verified on %lu macroblock codings (levels, cbp, cbp_blk, reconstruction); chroma_residual_coding verified on %lu\n", S.verified, chroma_verified);
+    fprintf(stderr, "[jmb shim] luma_residual_coding verified on %lu macroblock codings (levels, cbp, cbp_blk, reconstruction); chroma_residual_coding verified on %lu; DeblockFrame verified on %lu pictures (every sample)\n", S.verified, chroma_verified, S.deblock_verified);
   if (S.init == 1 && getenv("JMB_SHIM_VERBOSE"))
-    fprintf(stderr, "[jmb shim] planes %lu  full %lu  fastfull %lu  subpel %lu  fwd4 %lu  fwd8 %lu  quant4 %lu  quant8 %lu  dist %lu  kernel launches %llu  bipred/weighted distortions %lu  subpel served by the integer search's call %lu  surface builds %lu  chain calls %lu  searches answered ahead %lu  (discarded %lu)\n",
+    fprintf(stderr, "[jmb shim] planes %lu  full %lu  fastfull %lu  subpel %lu  fwd4 %lu  fwd8 %lu  quant4 %lu  quant8 %lu  dist %lu  kernel launches %llu  bipred/weighted distortions %lu  subpel served by the integer search's call %lu  surface builds %lu  chain calls %lu  searches answered ahead %lu  (discarded %lu)  pictures deblocked %lu (verified %lu)\n",
             S.calls[0], S.calls[1], S.calls[2], S.calls[3], S.calls[4], S.calls[5], S.calls[6], S.calls[7], S.calls[8],
-            (unsigned long long)jmb_launch_count(S.ctx), S.calls[9], S.spec_hits, S.surf_builds, S.chain_calls, S.chain_hits, S.chain_stale);
+            (unsigned long long)jmb_launch_count(S.ctx), S.calls[9], S.spec_hits, S.surf_builds, S.chain_calls, S.chain_hits, S.chain_stale, S.deblocked, S.deblock_verified);
 }
 
 static int shim_on(int family)
@@ -200,6 +202,7 @@ static int shim_on(int family)
         if (strstr(off, "subpel")) S.off |= FAM_SUBPEL;
         if (strstr(off, "tq"))     S.off |= FAM_TQ;
         if (strstr(off, "dist"))   S.off |= FAM_DIST;
+        if (strstr(off, "deblock")) S.off |= FAM_DEBLOCK;
       }
       atexit(report);
     }
@@ -1742,4 +1745,79 @@ int __wrap_quant_8x8cavlc_around(Macroblock *currMB, int **tblock, struct quant_
   if (!shim_on(FAM_TQ)) return __real_quant_8x8cavlc_around(currMB, tblock, q_method, cofAC);
   S.calls[7]++;
   return quant_nxn(currMB, tblock, q_method, 8, 1, 1, cofAC);
+}
+
+
+/* ---- deblocking: DeblockFrame (lencod/src/loopFilter.c:63), called once per coded picture (image.c:236) -----------------------
+ * The wrapper describes every macroblock as DeblockMb and the strength functions read it (jmb_db_mb), hands the reconstructed
+ * planes over as bytes, and takes them back filtered (jmb_deblock_picture: a wavefront of macroblocks on the device).  With
+ * JMB_SHIM_VERIFY the real DeblockFrame runs as well, on a copy, and every sample is compared. */
+void __wrap_DeblockFrame(VideoParameters *p_Vid, imgpel **imgY, imgpel ***imgUV)
+{
+  const int w = p_Vid->width, h = p_Vid->height, mbw = w / 16, mbh = h / 16, n = mbw * mbh;
+  const int yuv = imgUV ? p_Vid->yuv_format : 0, wc = w / 2, hc = p_Vid->yuv_format == YUV420 ? h / 2 : h;
+  PicMotionParams **mv_info = p_Vid->enc_picture->mv_info;
+  StorablePicture *pics[64];
+  int npics = 0, i, k, l, x, y, rc, slice_type;
+  jmb_db_mb *mbs;
+  uint8_t *pl[3], *chk[3] = {NULL, NULL, NULL};
+  if (!shim_on(FAM_DEBLOCK)) { __real_DeblockFrame(p_Vid, imgY, imgUV); return; }
+  if (p_Vid->mb_aff_frame_flag || p_Vid->structure != FRAME) unsupported("deblocking of field / MBAFF pictures");
+  if (p_Vid->P444_joined || p_Vid->yuv_format == YUV444) unsupported("deblocking of 4:4:4 pictures");
+  if (p_Vid->bitdepth_luma != 8 || (p_Vid->yuv_format != YUV400 && p_Vid->bitdepth_chroma != 8)) unsupported("deblocking at bit depths above 8");
+  if ((int)p_Vid->PicSizeInMbs != n) unsupported("deblocking: picture size is not a whole number of macroblocks");
+  slice_type = p_Vid->mb_data[0].p_Slice->slice_type;
+  if (slice_type != P_SLICE && slice_type != B_SLICE && slice_type != I_SLICE) unsupported("deblocking of SP / SI slices");
+  mbs = (jmb_db_mb *)calloc(n, sizeof(jmb_db_mb));
+  pl[0] = (uint8_t *)malloc((size_t)w * h); pl[1] = (uint8_t *)malloc((size_t)wc * hc + 1); pl[2] = (uint8_t *)malloc((size_t)wc * hc + 1);
+  if (!mbs || !pl[0] || !pl[1] || !pl[2]) no_mem_exit("libjmb200 shim: deblocking buffers");
+  for (i = 0; i < n; i++)
+  {
+    Macroblock *m = &p_Vid->mb_data[i];
+    jmb_db_mb *d = &mbs[i];
+    int ipcm = m->mb_type == IPCM;      /* init_Deblock (loopFilter.c:40-47) zeroes the QPs of IPCM macroblocks, for good */
+    if (ipcm) { m->qp = 0; m->qpc[0] = 0; m->qpc[1] = 0; }
+    if (m->p_Slice->slice_type != slice_type) unsupported("deblocking of a picture whose slices differ in type");
+    d->mb_type = (uint8_t)m->mb_type;
+    d->flags = (uint8_t)((m->luma_transform_size_8x8_flag ? JMB_DB_T8X8 : 0) | (m->cbp ? JMB_DB_CBP : 0) | (m->mbAvailA ? JMB_DB_AVAIL_A : 0) | (m->mbAvailB ? JMB_DB_AVAIL_B : 0));
+    d->qp = (int8_t)(ipcm ? 0 : m->qp); d->qpc[0] = (int8_t)(ipcm ? 0 : m->qpc[0]); d->qpc[1] = (int8_t)(ipcm ? 0 : m->qpc[1]);
+    d->df_disable_idc = (int8_t)m->DFDisableIdc; d->df_alpha_c0_offset = (int8_t)m->DFAlphaC0Offset; d->df_beta_offset = (int8_t)m->DFBetaOffset;
+    d->cbp_blk = (uint32_t)(m->cbp_blk & 0xffff);
+    for (k = 0; k < 16; k++)
+    {
+      PicMotionParams *p = &mv_info[(i / mbw) * 4 + k / 4][(i % mbw) * 4 + k % 4];
+      for (l = 0; l < 2; l++)
+      {
+        int id = -1;
+        if (p->ref_idx[l] != -1)
+        {
+          for (id = 0; id < npics && pics[id] != p->ref_pic[l]; id++) ;
+          if (id == npics) { if (npics == 64) unsupported("deblocking: more than 64 distinct reference pictures in one picture"); pics[npics++] = p->ref_pic[l]; }
+        }
+        d->ref_id[l][k] = (int8_t)id;
+        d->mv[l][k][0] = p->mv[l].mv_x; d->mv[l][k][1] = p->mv[l].mv_y;
+      }
+    }
+  }
+  for (y = 0; y < h; y++) for (x = 0; x < w; x++) pl[0][(size_t)y * w + x] = (uint8_t)imgY[y][x];
+  if (yuv) for (k = 0; k < 2; k++) for (y = 0; y < hc; y++) for (x = 0; x < wc; x++) pl[1 + k][(size_t)y * wc + x] = (uint8_t)imgUV[k][y][x];
+  rc = jmb_deblock_picture(S.ctx, pl[0], w, yuv ? pl[1] : NULL, yuv ? pl[2] : NULL, wc, w, h, yuv, slice_type, p_Vid->active_sps->direct_8x8_inference_flag, mbs, JMB_HOST);
+  if (rc) jmb_die("jmb_deblock_picture", rc);
+  if (S.verify)
+  { /* JM's own filter on JM's own planes; the device result must be the same sample for sample */
+    __real_DeblockFrame(p_Vid, imgY, imgUV);
+    for (y = 0; y < h; y++) for (x = 0; x < w; x++)
+      if (imgY[y][x] != pl[0][(size_t)y * w + x]) { snprintf(errortext, ET_SIZE, "libjmb200 shim: deblocked luma differs from JM's at (%d,%d): %d vs %d", x, y, pl[0][(size_t)y * w + x], imgY[y][x]); fatal(703); }
+    if (yuv) for (k = 0; k < 2; k++) for (y = 0; y < hc; y++) for (x = 0; x < wc; x++)
+      if (imgUV[k][y][x] != pl[1 + k][(size_t)y * wc + x]) { snprintf(errortext, ET_SIZE, "libjmb200 shim: deblocked chroma %d differs from JM's at (%d,%d)", k, x, y); fatal(703); }
+    S.deblock_verified++;
+  }
+  else
+  {
+    for (y = 0; y < h; y++) for (x = 0; x < w; x++) imgY[y][x] = pl[0][(size_t)y * w + x];
+    if (yuv) for (k = 0; k < 2; k++) for (y = 0; y < hc; y++) for (x = 0; x < wc; x++) imgUV[k][y][x] = pl[1 + k][(size_t)y * wc + x];
+  }
+  S.deblocked++;
+  (void)chk;
+  free(mbs); free(pl[0]); free(pl[1]); free(pl[2]);
 }

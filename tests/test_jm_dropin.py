@@ -185,7 +185,9 @@ def test_device_luma_residual_coding_matches_jm_in_the_live_encoder(tmp_path, na
     line = [l for l in r.stderr.splitlines() if "luma_residual_coding verified on" in l]
     assert line, r.stderr[-400:]
     assert int(line[0].split("verified on")[1].split()[0]) > 100, line[0]
-    assert int(line[0].split("chroma_residual_coding verified on")[1].split()[0]) > 100, line[0]      # 4:2:0 chroma: prediction, 2x2 DC path, AC, thresholds
+    assert int(line[0].split("chroma_residual_coding verified on")[1].split()[0].rstrip(";")) > 100, line[0]      # 4:2:0 chroma: prediction, 2x2 DC path, AC, thresholds
+    # ... and every coded picture was deblocked on the device (k_deblock) AND by JM's own DeblockFrame, sample for sample the same
+    assert int(line[0].split("DeblockFrame verified on")[1].split()[0]) == frames, line[0]
 
 
 @pytest.mark.gpu
@@ -200,7 +202,8 @@ def test_device_chroma_residual_coding_422_matches_jm_in_the_live_encoder(tmp_pa
     r = _encode(JMB, tmp_path, "v", w, h, frames, cfg, env={"JMB_SHIM_VERIFY": "1"})
     assert r.returncode == 0, r.stderr[-800:]
     line = [l for l in r.stderr.splitlines() if "chroma_residual_coding verified on" in l]
-    assert line and int(line[0].split("chroma_residual_coding verified on")[1].split()[0]) > 100, r.stderr[-400:]
+    assert line and int(line[0].split("chroma_residual_coding verified on")[1].split()[0].rstrip(";")) > 100, r.stderr[-400:]
+    assert int(line[0].split("DeblockFrame verified on")[1].split()[0]) == frames, line[0]      # 4:2:2 deblocking: sixteen chroma rows, four horizontal chroma edges
 
 
 FIXTURES = os.path.join(ROOT, "oracle", "_ref", "fixtures")

@@ -8,6 +8,6 @@ for cfg in "$@"; do
   out=tools/_bin/libjmb200_nt$1_b$2${3:+_$3}.so
   nt=$1; mb=$2; shift 2; [ $# -gt 0 ] && shift
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Iinclude -DJMB_IS_NT=$nt -DJMB_IS_MINB=$mb $@ \
-       -Xcompiler -fPIC -shared -cudart static -o $out jm_b200/csrc/jmb_context.cu jm_b200/csrc/k_subpel.cu jm_b200/csrc/k_search.cu jm_b200/csrc/k_refine.cu jm_b200/csrc/k_tq.cu jm_b200/csrc/k_epzs.cu jm_b200/csrc/k_chroma.cu
+       -Xcompiler -fPIC -shared -cudart static -o $out jm_b200/csrc/jmb_context.cu jm_b200/csrc/k_subpel.cu jm_b200/csrc/k_search.cu jm_b200/csrc/k_refine.cu jm_b200/csrc/k_tq.cu jm_b200/csrc/k_epzs.cu jm_b200/csrc/k_chroma.cu jm_b200/csrc/k_deblock.cu
   echo built $out
 done
