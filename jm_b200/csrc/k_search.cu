@@ -39,12 +39,18 @@ static_assert(WIN_ROWS == JMB_WIN_BOX_H && 15 + CW + 15 + 4 <= WIN_PITCH, "TMA b
 #endif
 constexpr int S1_COLS = JMB_S1_COLS, S1_RGS = JMB_S1_RGS, S1_ITEMS = S1_COLS * S1_RGS, S1_PITCH = 43;   // stage-1 neighbourhood
 constexpr int ADJ_PITCH = 44;      // words per column (>= NPART; 176 B keeps the 128-bit row reads conflict-free)
+#ifndef JMB_IS_PACKED
+#define JMB_IS_PACKED 1            // the sweep's gate on two partitions per register (see "packed gate" in k_int_search)
+#endif
+constexpr int PK_N = 19, PK_PITCH = 20;      // packed pairs of the 38 partitions of at most 8x16 samples (SAD < 2^15); words per table row
+constexpr unsigned PK_ADJ_MAX = 8191;        // mv-cost terms are capped (a smaller term only loosens the gate) so that no 16-bit field overflows
 constexpr int WQ_CAP = 192;          // per-warp queue of gate hits awaiting their exact evaluation
 constexpr int HS_PITCH = NPART + 1;   // u16 per thread: SADs of the partitions of a displacement that met the gate
 constexpr int S1_BYTES = S1_ITEMS * 4 * S1_PITCH * 2, SWEEP_BYTES = (NT / 32) * WQ_CAP * 8 + NT * HS_PITCH * 2;   // stage-1 sums and the sweep's queue / hit SADs share memory
 constexpr unsigned S1_NONE = 0x3fffffffu, S1_BAD = 0x40000000u;   // real costs stay far below (lambda <= 65535)
 constexpr int S1T_ROWS = S1_COLS + 4 * S1_RGS;      // exact mv-cost terms of the stage-1 columns and rows, per partition
-constexpr int INT_SEARCH_DYN_SMEM = (CW + CH / 4 + S1T_ROWS) * ADJ_PITCH * 4 + (S1_BYTES > SWEEP_BYTES ? S1_BYTES : SWEEP_BYTES);
+constexpr int PK_BYTES = JMB_IS_PACKED ? (CW + CH / 4) * PK_PITCH * 4 : 0;      // packed copies of the column / row-group gate tables
+constexpr int INT_SEARCH_DYN_SMEM = (CW + CH / 4 + S1T_ROWS) * ADJ_PITCH * 4 + (S1_BYTES > SWEEP_BYTES ? S1_BYTES : SWEEP_BYTES) + PK_BYTES;
 #ifndef JMB_IS_SMEM_PAD
 #define JMB_IS_SMEM_PAD 0      // tuning builds only: extra dynamic shared memory lowers the CTAs per SM (occupancy probe at 128 registers: 4 CTAs 0.72 ms, 3 CTAs 0.77, 2 CTAs 0.92)
 #endif
@@ -83,8 +89,26 @@ struct Grp {
   unsigned long long best[NPART];      // (cost << IDX_BITS) | spiral index of the current winner
   __align__(16) unsigned thr[NPART + 3];   // gate: a SAD can only win if sad < thr (see bound_of)
   __align__(16) int4 inner[NPART];     // displacements that stand for exactly one candidate: x0, x1, y0, y1 (inclusive)
+  __align__(16) unsigned thr2[PK_PITCH];   // packed gate: min(thr, 32767) of two partitions per word (c_pk_half tells which half)
+  int nbig;                            // active partitions among those whose thr is still above 32767 (the packed gate stands back until 0)
   int R, max_mvd_m1;
 };
+
+// Packed gate: the partitions of up to 8x16 samples in pairs (low half, high half), in the order the packed sums come out of
+// the sixteen 4x4 SADs: E_j = (a[4j], a[4j+2]), O_j = (a[4j+1], a[4j+3]), 8x4 rows E_j + O_j, 4x8 columns E_0 + E_1 ..., 8x8
+// pairs, the 8x16 pair.  c_pk_half[p] = 2 * word + half for partition p (the three larger partitions are compared as scalars).
+__constant__ signed char c_pk_half[NPART] = {
+  -1, -1, -1,                  // 16x16, 16x8 x 2: scalars
+  36, 37,                      // 8x16: word 18
+  32, 33, 34, 35,              // 8x8: words 16, 17
+  16, 17, 18, 19, 20, 21, 22, 23,      // 8x4 (9..16): words 8..11 = rows 0..3, (left, right)
+  24, 26, 25, 27, 28, 30, 29, 31,      // 4x8 (17..24): words 12 (s6[0], s6[2]), 13 (s6[1], s6[3]), 14 (s6[4], s6[6]), 15 (s6[5], s6[7])
+  0, 2, 1, 3, 4, 6, 5, 7, 8, 10, 9, 11, 12, 14, 13, 15};      // 4x4 (25..40): words 2j = E_j (a[4j], a[4j+2]), 2j+1 = O_j (a[4j+1], a[4j+3])
+
+__device__ __forceinline__ void pk_set_thr(Grp *g, int p, unsigned thr) {
+  const int h = c_pk_half[p];
+  if (h >= 0) ((volatile unsigned short *)g->thr2)[h] = (unsigned short)min(thr, 32767u);
+}
 
 // Largest SAD that can still win against the key `k`: a winner needs (sad << 5) + lambda * bits <= cost(k),
 // and every candidate pays at least 2 bits (mvbits >= 1 per component).  The gate is sad < bound.
@@ -124,7 +148,15 @@ __device__ __forceinline__ unsigned sad4(unsigned a, unsigned b, unsigned c) {
 }
 
 __device__ __forceinline__ void publish(Grp *g, int p, unsigned long long k) {
-  if (k < atomicMin(&g->best[p], k)) atomicMin(&g->thr[p], bound_of(k, g->rq[p].lam));
+  if (k < atomicMin(&g->best[p], k)) {
+    const unsigned b = bound_of(k, g->rq[p].lam), old = atomicMin(&g->thr[p], b);
+#if JMB_IS_PACKED
+    if (b < old) {      // the packed copy follows (a racing, older value there is merely looser); the first to bring thr under 2^15 counts it off
+      pk_set_thr(g, p, *(volatile unsigned *)&g->thr[p]);
+      if (old > 32767u && b <= 32767u && c_pk_half[p] >= 0) atomicSub(&g->nbig, 1);
+    }
+#endif
+  }
 }
 
 // Exact cost evaluation of the candidates that read the block(s) at displacement (Dx,Dy).  Reached only
@@ -278,6 +310,7 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
   unsigned long long (*const wq)[WQ_CAP] = (unsigned long long (*)[WQ_CAP])(s1y + 4 * S1_RGS * ADJ_PITCH);
   unsigned short *const S1 = (unsigned short *)wq;      // stage 1 is over (barrier) before the sweep touches wq / hitsad
   unsigned short (*const hitsad)[HS_PITCH] = (unsigned short (*)[HS_PITCH])(wq + NT / 32);
+  unsigned *const adjx2 = (unsigned *)((char *)wq + (S1_BYTES > SWEEP_BYTES ? S1_BYTES : SWEEP_BYTES)), *const adjy2 = adjx2 + CW * PK_PITCH;
 
   const int tid = threadIdx.x, g = blockIdx.x;
   if (tid < NT / 32) wq_n[tid] = 0;
@@ -285,6 +318,8 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
     sbox[0] = sbox[2] = 1 << 30; sbox[1] = sbox[3] = -(1 << 30); sbox[7] = 0; sbox[10] = NPART;
     mbar_init(&mbar, 1);
     G.R = R; G.max_mvd_m1 = max_mvd_m1; G.thr[NPART] = G.thr[NPART + 1] = G.thr[NPART + 2] = 0;
+    G.nbig = 0;
+    for (int i = 0; i < PK_PITCH; i++) G.thr2[i] = 0;
   }
   __syncthreads();
   if (tid < NPART) {
@@ -322,6 +357,10 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
     G.rq[tid] = q;
     G.best[tid] = q.active ? q.init : 0ull;
     G.thr[tid] = q.active ? bound_of(q.init, q.lam) : 0u;
+#if JMB_IS_PACKED
+    pk_set_thr(&G, tid, G.thr[tid]);
+    if (q.active && c_pk_half[tid] >= 0 && G.thr[tid] > 32767u) atomicAdd(&G.nbig, 1);
+#endif
     int4 in = make_int4(1, 0, 1, 0);
     if (q.active) in = make_int4(max(q.dlo_x + 1, q.cx - R), min(q.dhi_x - 1, q.cx + R), max(q.dlo_y + 1, q.cy - R), min(q.dhi_y - 1, q.cy + R));
     G.inner[tid] = in;
@@ -389,6 +428,9 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
             unsigned a = min(65535u, (lam * (unsigned)(jmb_mvbits(4 * Dx - q.px) - 1)) >> 5);
             if (Dx < in.x || Dx > in.y) a = 0;
             adjx[ic * ADJ_PITCH + p] = a;
+#if JMB_IS_PACKED
+            if (c_pk_half[p] >= 0) ((unsigned short *)adjx2)[ic * PK_PITCH * 2 + c_pk_half[p]] = (unsigned short)min(a, PK_ADJ_MAX);
+#endif
           }
           // the row term is monotone in |4 Dy - py|: of the (up to) 4 rows of an item the one nearest py / 4 has the minimum
           for (int rg = sub; rg < ((ch + 3) >> 2); rg += lanes_per_p) {
@@ -397,6 +439,9 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
             unsigned a = min(65535u, (lam * (unsigned)(jmb_mvbits(am) - 1)) >> 5);
             if (D0 < in.z || D1 > in.w) a = 0;
             adjy4[rg * ADJ_PITCH + p] = a;
+#if JMB_IS_PACKED
+            if (c_pk_half[p] >= 0) ((unsigned short *)adjy2)[rg * PK_PITCH * 2 + c_pk_half[p]] = (unsigned short)min(a, PK_ADJ_MAX);
+#endif
           }
           if (s1) {      // stage 1's exact terms; S1_BAD marks a column / row that is not a plain candidate of this partition
             for (int c = sub; c < ncol; c += lanes_per_p) {
@@ -465,6 +510,53 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
         const int row0 = rg * 4, xo = ic + xoff0;
         unsigned acc[4][16];
         sad_item(win, ssrc, row0, xo, acc);
+#if JMB_IS_PACKED
+        // Packed gate.  A partition meets the gate when sad + (column term + row-group term) - thr < 0.  For the 38 partitions of at
+        // most 8x16 samples that is done two per register: N = adjx2 + adjy2 - thr2 once per item, then per displacement the
+        // packed sums (8 multiply-adds to pair up the 4x4 SADs, 11 adds for the larger shapes instead of 22), one add of N each
+        // OR-ed into one word (LOP3 takes two at a time); a set sign bit in either half is a hit.  The words are
+        // plain integers lo + 65536 hi: a negative low field borrows 1 from the high one, which can only turn a high field
+        // negative when the low one already is a hit -- never the other way round.  Terms are capped at PK_ADJ_MAX and thr at
+        // 32767 so that no field wraps (a cap only loosens the gate); while some thr is still above 32767 (nbig) every
+        // displacement goes to the exact re-visit.  The three large partitions are compared as before.
+        int t0, t1, t2;
+        {
+          unsigned th[4];
+          asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(th[0]), "=r"(th[1]), "=r"(th[2]), "=r"(th[3]) : "r"((unsigned)__cvta_generic_to_shared(&G.thr[0])));
+          const uint4 v = *(const uint4 *)&adjx[ic * ADJ_PITCH], u = *(const uint4 *)&adjy4[rg * ADJ_PITCH];
+          t0 = (int)(th[0] - v.x - u.x); t1 = (int)(th[1] - v.y - u.y); t2 = (int)(th[2] - v.z - u.z);
+        }
+        unsigned N[PK_PITCH];
+#pragma unroll
+        for (int i = 0; i < PK_PITCH / 4; i++) {
+          unsigned th[4];
+          asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(th[0]), "=r"(th[1]), "=r"(th[2]), "=r"(th[3]) : "r"((unsigned)__cvta_generic_to_shared(&G.thr2[4 * i])));
+          const uint4 v = *(const uint4 *)&adjx2[ic * PK_PITCH + 4 * i], u = *(const uint4 *)&adjy2[rg * PK_PITCH + 4 * i];
+          N[4 * i] = v.x + u.x - th[0]; N[4 * i + 1] = v.y + u.y - th[1]; N[4 * i + 2] = v.z + u.z - th[2]; N[4 * i + 3] = v.w + u.w - th[3];
+        }
+        const bool big = *(volatile int *)&G.nbig != 0;
+        bool hit[4];
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+          hit[s] = false;
+          if (row0 + s < ch) {
+            const unsigned *a = acc[s];
+            unsigned w[PK_N];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { w[2 * j] = a[4 * j] + a[4 * j + 2] * 65536u; w[2 * j + 1] = a[4 * j + 1] + a[4 * j + 3] * 65536u; }
+#pragma unroll
+            for (int j = 0; j < 4; j++) w[8 + j] = w[2 * j] + w[2 * j + 1];                  // 8x4 rows
+            w[12] = w[0] + w[2]; w[13] = w[1] + w[3]; w[14] = w[4] + w[6]; w[15] = w[5] + w[7];   // 4x8 columns
+            w[16] = w[12] + w[13]; w[17] = w[14] + w[15];                                        // 8x8
+            w[18] = w[16] + w[17];                                                               // 8x16
+            const unsigned s2a = __dp2a_lo(w[16], 0x0101u, 0u), s2b = __dp2a_lo(w[17], 0x0101u, 0u);   // 16x8: the two halves of an 8x8 pair added up
+            unsigned m = w[0] + N[0];      // the sign bits of all halves OR-ed together (one LOP3 per two words)
+#pragma unroll
+            for (int i = 1; i < PK_N; i += 2) m |= (w[i] + N[i]) | (w[i + 1] + N[i + 1]);
+            hit[s] = big | ((m & 0x80008000u) != 0u) | ((int)(s2a + s2b) < t0) | ((int)s2a < t1) | ((int)s2b < t2);
+          }
+        }
+#else
         // gate: does any of the 4 x 41 partition SADs beat its current bound?
         unsigned t[NPART + 3];
 #pragma unroll
@@ -488,6 +580,7 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
           hit[s] = false;
           if (row0 + s < ch) for_each_partition(acc[s], [&](int p, unsigned v) { hit[s] |= (int)v < (int)t[p]; });
         }
+#endif
         // Re-visit of a displacement that met the gate: collect the partitions that did in a bit mask (straight-line,
         // no calls), then walk the set bits: one jump per hit to the few adds that re-sum that partition's SAD, one more
         // check with the row term of the mv cost, and only then the exact evaluation.  Cost is proportional to the number
@@ -497,9 +590,24 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
         for (int s = 0; s < 4; s++) {
           if (!hit[s]) continue;
           unsigned mlo = 0, mhi = 0;
+#if JMB_IS_PACKED
+          unsigned t[NPART + 3];      // the exact gate, partition by partition (the packed one above only says "look here")
+#pragma unroll
+          for (int i = 0; i < (NPART + 3) / 4; i++) {
+            asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(t[4 * i]), "=r"(t[4 * i + 1]), "=r"(t[4 * i + 2]), "=r"(t[4 * i + 3])
+                         : "r"((unsigned)__cvta_generic_to_shared(&G.thr[4 * i])));
+            const uint4 v = *(const uint4 *)&adjx[ic * ADJ_PITCH + 4 * i], u = *(const uint4 *)&adjy4[rg * ADJ_PITCH + 4 * i];
+            t[4 * i] -= v.x + u.x; t[4 * i + 1] -= v.y + u.y; t[4 * i + 2] -= v.z + u.z; t[4 * i + 3] -= v.w + u.w;
+          }
           for_each_partition(acc[s], [&](int p, unsigned v) {
             if ((int)v < (int)t[p]) { if (p < 32) mlo |= 1u << (p & 31); else mhi |= 1u << (p & 31); hitsad[tid][p] = (unsigned short)v; }
           });
+#else
+          for_each_partition(acc[s], [&](int p, unsigned v) {
+            if ((int)v < (int)t[p]) { if (p < 32) mlo |= 1u << (p & 31); else mhi |= 1u << (p & 31); hitsad[tid][p] = (unsigned short)v; }
+          });
+#endif
           const int Dy = cy0 + row0 + s;
           const unsigned *ax = adjx + ic * ADJ_PITCH;
           while (mlo | mhi) {
