@@ -5,11 +5,12 @@
 // in the result: the left edge of a macroblock reads samples its left neighbour's horizontal edges have changed, the top edge
 // reads samples the top-right neighbour's left edge has changed.  So macroblock (x, y) needs (x-1, y) and (x+1, y-1) finished
 // (the latter implies (x, y-1)) and nothing else: a wavefront x + 2y (JM's own JM_PARALLEL_DEBLOCK walks the same diagonals).
-// One warp per macroblock.  Warps take macroblock numbers from a ticket counter in raster order -- whatever a warp waits for
-// was handed out before it, to a warp that is running or done -- and wait on per-macroblock flags in global memory.
-// A warp copies its macroblock and the 4 samples left of / above it into shared memory, derives the 32 edge strengths (one per
+// One CTA of two warps per macroblock.  CTAs take macroblock numbers from a ticket counter in raster order -- whatever a CTA
+// waits for was handed out before it, to a CTA that is running or done -- and wait on per-macroblock flags in global memory.
+// A CTA copies its macroblock and the 4 samples left of / above it into shared memory, derives the 32 edge strengths (one per
 // lane: direction x edge x 4-sample segment), filters the vertical edges row-parallel and the horizontal ones column-parallel
-// there, and writes back what it may have changed.  Nobody else touches that area in between (see jmb_deblock_picture).
+// there (luma in one warp, chroma in the other), and writes back what it may have changed.  Nobody else touches that area in
+// between.
 #include "jmb_internal.h"
 
 namespace {
@@ -89,79 +90,89 @@ __device__ __forceinline__ void db_chroma_line(uint8_t *q, int st, int bs, int a
   }
 }
 
-__global__ void __launch_bounds__(32)
+// Two warps per macroblock: warp 0 filters luma, warp 1 the two chroma planes (independent data, the same strengths).
+// What does not depend on the neighbours -- the macroblock records, the macroblock's own samples (nobody filters into them before
+// its turn) and the 32 strengths -- is fetched and worked out BEFORE the wait; after it only the 4 columns left of and the
+// 4 rows above the macroblock are read.
+__global__ void __launch_bounds__(64)
 k_deblock(const DbArgs A) {
   __shared__ jmb_db_mb M[3];                        // this macroblock, its left and its upper neighbour
   __shared__ __align__(4) uint8_t L[20 * LP];       // luma rows -4..15
   __shared__ __align__(4) uint8_t C[2][20 * CP];    // chroma rows -4..15 (4:2:0 uses -4..7)
   __shared__ unsigned char sbs[32];                 // strength of [dir][edge][segment]; 0 where DeblockMb passes the edge over
-  const int lane = threadIdx.x;
-  int mb = 0;
-  if (lane == 0) mb = (int)atomicAdd(A.ticket, 1u);
-  mb = __shfl_sync(0xffffffffu, mb, 0);
-  const int x = mb % A.mbw, y = mb / A.mbw;
-  if (lane == 0) {      // (x-1, y) and (x+1, y-1) -- (x, y-1) in the last column -- must be through
-    if (x > 0) while (*(volatile int *)&A.done[mb - 1] != A.serial) __nanosleep(40);
-    if (y > 0) { const int dep = mb - A.mbw + (x < A.mbw - 1 ? 1 : 0); while (*(volatile int *)&A.done[dep] != A.serial) __nanosleep(40); }
-    __threadfence();
-  }
-  __syncwarp();
-  // macroblock records
+  __shared__ int s_mb;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) s_mb = (int)atomicAdd(A.ticket, 1u);
+  __syncthreads();
+  const int mb = s_mb, x = mb % A.mbw, y = mb / A.mbw;
+  const int chh = A.yuv == 1 ? 8 : 16;
+  // ---- before the wait ----
   {
     const unsigned *src[3] = {(const unsigned *)&A.mbs[mb], (const unsigned *)&A.mbs[x > 0 ? mb - 1 : mb], (const unsigned *)&A.mbs[y > 0 ? mb - A.mbw : mb]};
-    for (int i = lane; i < 3 * 44; i += 32) ((unsigned *)M)[i] = __ldg(src[i / 44] + i % 44);
+    for (int i = tid; i < 3 * 44; i += 64) ((unsigned *)M)[i] = __ldg(src[i / 44] + i % 44);
   }
-  // sample tiles: every read goes to L2 (another SM wrote the neighbours' samples)
-  const int chh = A.yuv == 1 ? 8 : 16;
-  for (int i = lane; i < 20 * 5; i += 32) {
-    const int r = i / 5 - 4, wd = i % 5 - 1;      // row -4..15, word -1..3 (columns -4..15)
-    unsigned v = 0;
-    if ((r >= 0 || y > 0) && (wd >= 0 || x > 0)) v = __ldcg((const unsigned *)(A.luma + (size_t)(y * 16 + r) * A.pitch + x * 16 + wd * 4));
-    *(unsigned *)&L[(r + 4) * LP + (wd + 1) * 4] = v;
-  }
-  if (A.yuv)
-    for (int i = lane; i < 2 * (chh + 4) * 3; i += 32) {
-      const int pl = i / ((chh + 4) * 3), j = i % ((chh + 4) * 3), r = j / 3 - 4, wd = j % 3 - 1;
-      unsigned v = 0;
-      if ((r >= 0 || y > 0) && (wd >= 0 || x > 0)) v = __ldcg((const unsigned *)((pl ? A.cr : A.cb) + (size_t)(y * chh + r) * A.pitch_c + x * 8 + wd * 4));
-      *(unsigned *)&C[pl][(r + 4) * CP + (wd + 1) * 4] = v;
+  if (warp == 0) {
+    for (int i = lane; i < 16 * 4; i += 32) {      // own luma samples: rows 0..15, words 0..3
+      const int r = i >> 2, wd = i & 3;
+      *(unsigned *)&L[(r + 4) * LP + (wd + 1) * 4] = __ldcg((const unsigned *)(A.luma + (size_t)(y * 16 + r) * A.pitch + x * 16 + wd * 4));
     }
-  __syncwarp();
+  } else if (A.yuv) {
+    for (int i = lane; i < 2 * chh * 2; i += 32) {      // own chroma samples: rows 0..chh-1, words 0..1 of both planes
+      const int pl = i / (chh * 2), j = i % (chh * 2), r = j >> 1, wd = j & 1;
+      *(unsigned *)&C[pl][(r + 4) * CP + (wd + 1) * 4] = __ldcg((const unsigned *)((pl ? A.cr : A.cb) + (size_t)(y * chh + r) * A.pitch_c + x * 8 + wd * 4));
+    }
+  }
+  __syncthreads();
   const jmb_db_mb &Q = M[0];
-  if (Q.df_disable_idc != 1) {
-    const bool t8 = Q.flags & JMB_DB_T8X8, cbp = Q.flags & JMB_DB_CBP;
-    {      // the 32 strengths, one per lane; DeblockMb's reasons to pass an edge over (loopFilter.c:150-166, :206-222) make it 0
-      const int dir = lane >> 4, edge = (lane >> 2) & 3, k = lane & 3;
-      bool on = edge ? true : (Q.df_disable_idc == 2 ? (Q.flags & (dir ? JMB_DB_AVAIL_B : JMB_DB_AVAIL_A)) != 0 : (dir ? y : x) != 0);
-      if (!cbp) {
-        const bool luma_on = !(t8 && (edge & 1));
-        if (!luma_on && (dir == 0 || A.yuv == 1)) on = false;
-        else if (edge > 0 && (A.slice_type == 0 || A.slice_type == 1)) {
-          if ((Q.mb_type == 0 && A.slice_type == 0) || Q.mb_type == 1 || Q.mb_type == (dir ? 3 : 2)) on = false;
-          else if ((edge & 1) && (Q.mb_type == (dir ? 2 : 3) || (Q.mb_type == 0 && A.slice_type == 1 && A.d8))) on = false;
-        }
+  const bool filter_on = Q.df_disable_idc != 1;
+  const bool t8 = Q.flags & JMB_DB_T8X8, cbp = Q.flags & JMB_DB_CBP;
+  if (warp == 0 && filter_on) {      // the 32 strengths, one per lane; DeblockMb's reasons to pass an edge over (loopFilter.c:150-166, :206-222) make it 0
+    const int dir = lane >> 4, edge = (lane >> 2) & 3, k = lane & 3;
+    bool on = edge ? true : (Q.df_disable_idc == 2 ? (Q.flags & (dir ? JMB_DB_AVAIL_B : JMB_DB_AVAIL_A)) != 0 : (dir ? y : x) != 0);
+    if (!cbp) {
+      const bool luma_on = !(t8 && (edge & 1));
+      if (!luma_on && (dir == 0 || A.yuv == 1)) on = false;
+      else if (edge > 0 && (A.slice_type == 0 || A.slice_type == 1)) {
+        if ((Q.mb_type == 0 && A.slice_type == 0) || Q.mb_type == 1 || Q.mb_type == (dir ? 3 : 2)) on = false;
+        else if ((edge & 1) && (Q.mb_type == (dir ? 2 : 3) || (Q.mb_type == 0 && A.slice_type == 1 && A.d8))) on = false;
       }
-      sbs[lane] = on ? (unsigned char)db_strength(dir, edge, k, Q, edge ? Q : M[1 + dir]) : 0;
+    }
+    sbs[lane] = on ? (unsigned char)db_strength(dir, edge, k, Q, edge ? Q : M[1 + dir]) : 0;
+  }
+  // ---- the wait: (x-1, y) and (x+1, y-1) -- (x, y-1) in the last column -- must be through ----
+  if (tid == 0) {
+    if (x > 0) while (*(volatile int *)&A.done[mb - 1] != A.serial) __nanosleep(20);
+    if (y > 0) { const int dep = mb - A.mbw + (x < A.mbw - 1 ? 1 : 0); while (*(volatile int *)&A.done[dep] != A.serial) __nanosleep(20); }
+    __threadfence();
+  }
+  __syncthreads();
+  if (filter_on) {
+    // the strips the neighbours have just finished: every read goes to L2 (another SM wrote them)
+    if (warp == 0) {
+      if (lane < 16) { if (x > 0) *(unsigned *)&L[(lane + 4) * LP] = __ldcg((const unsigned *)(A.luma + (size_t)(y * 16 + lane) * A.pitch + x * 16 - 4)); }
+      else if (y > 0) { const int r = (lane - 16) >> 2, wd = lane & 3; *(unsigned *)&L[r * LP + (wd + 1) * 4] = __ldcg((const unsigned *)(A.luma + (size_t)(y * 16 - 4 + r) * A.pitch + x * 16 + wd * 4)); }
+    } else if (A.yuv) {
+      if (x > 0) for (int i = lane; i < 2 * chh; i += 32) { const int pl = i / chh, r = i % chh; *(unsigned *)&C[pl][(r + 4) * CP] = __ldcg((const unsigned *)((pl ? A.cr : A.cb) + (size_t)(y * chh + r) * A.pitch_c + x * 8 - 4)); }
+      if (y > 0 && lane < 16) { const int pl = lane >> 3, r = (lane >> 1) & 3, wd = lane & 1; *(unsigned *)&C[pl][r * CP + (wd + 1) * 4] = __ldcg((const unsigned *)((pl ? A.cr : A.cb) + (size_t)(y * chh - 4 + r) * A.pitch_c + x * 8 + wd * 4)); }
     }
     __syncwarp();
     // chroma_edge[dir][edge][yuv_format] (loop_filter.h:47-56): where a luma edge's strengths are used in the chroma planes
     auto cedge = [&](int dir, int edge) { return edge == 0 ? 0 : edge == 2 ? (dir && A.yuv == 2 ? 8 : 4) : (dir && A.yuv == 2 ? edge * 4 : -4); };
 #pragma unroll 1
     for (int dir = 0; dir < 2; dir++) {
-      // luma: lane = the row (vertical edges) / the column (horizontal edges)
-      if (lane < 16)
-        for (int edge = 0; edge < 4; edge++) {
-          const int s = sbs[dir * 16 + edge * 4 + (lane >> 2)];
-          if (!s || (t8 && (edge & 1))) continue;
-          const jmb_db_mb &P = edge ? Q : M[1 + dir];
-          const int qp = (P.qp + Q.qp + 1) >> 1, ia = jmb_clip(0, 51, qp + Q.df_alpha_c0_offset), ib = jmb_clip(0, 51, qp + Q.df_beta_offset);
-          const int alpha = c_db_alpha[ia], beta = c_db_beta[ib];
-          if (!(alpha | beta)) continue;
-          uint8_t *q = dir ? &L[(4 + edge * 4) * LP + 4 + lane] : &L[(4 + lane) * LP + 4 + edge * 4];
-          db_luma_line(q, dir ? LP : 1, s, alpha, beta, s < 4 ? c_db_clip[ia][s - 1] : 0);
-        }
-      // chroma: vertical edges run over chh rows of each plane, horizontal ones over 8 columns
-      if (A.yuv) {
+      if (warp == 0) {      // luma: lane = the row (vertical edges) / the column (horizontal edges)
+        if (lane < 16)
+          for (int edge = 0; edge < 4; edge++) {
+            const int s = sbs[dir * 16 + edge * 4 + (lane >> 2)];
+            if (!s || (t8 && (edge & 1))) continue;
+            const jmb_db_mb &P = edge ? Q : M[1 + dir];
+            const int qp = (P.qp + Q.qp + 1) >> 1, ia = jmb_clip(0, 51, qp + Q.df_alpha_c0_offset), ib = jmb_clip(0, 51, qp + Q.df_beta_offset);
+            const int alpha = c_db_alpha[ia], beta = c_db_beta[ib];
+            if (!(alpha | beta)) continue;
+            uint8_t *q = dir ? &L[(4 + edge * 4) * LP + 4 + lane] : &L[(4 + lane) * LP + 4 + edge * 4];
+            db_luma_line(q, dir ? LP : 1, s, alpha, beta, s < 4 ? c_db_clip[ia][s - 1] : 0);
+          }
+      } else if (A.yuv) {      // chroma: vertical edges run over chh rows of each plane, horizontal ones over 8 columns
         const int n = dir ? 8 : chh;
         for (int i = lane; i < 2 * n; i += 32) {
           const int pl = i / n, j = i % n;
@@ -182,21 +193,23 @@ k_deblock(const DbArgs A) {
       __syncwarp();
     }
     // write back: the macroblock, the 4 columns left of it and the 4 rows above it (not the corner: nothing there was touched)
-    for (int i = lane; i < 20 * 5; i += 32) {
-      const int r = i / 5 - 4, wd = i % 5 - 1;
-      if ((r < 0 && wd < 0) || (r < 0 && y == 0) || (wd < 0 && x == 0)) continue;
-      __stcg((unsigned *)(A.luma + (size_t)(y * 16 + r) * A.pitch + x * 16 + wd * 4), *(const unsigned *)&L[(r + 4) * LP + (wd + 1) * 4]);
-    }
-    if (A.yuv)
+    if (warp == 0) {
+      for (int i = lane; i < 20 * 5; i += 32) {
+        const int r = i / 5 - 4, wd = i % 5 - 1;
+        if ((r < 0 && wd < 0) || (r < 0 && y == 0) || (wd < 0 && x == 0)) continue;
+        __stcg((unsigned *)(A.luma + (size_t)(y * 16 + r) * A.pitch + x * 16 + wd * 4), *(const unsigned *)&L[(r + 4) * LP + (wd + 1) * 4]);
+      }
+    } else if (A.yuv) {
       for (int i = lane; i < 2 * (chh + 4) * 3; i += 32) {
         const int pl = i / ((chh + 4) * 3), j = i % ((chh + 4) * 3), r = j / 3 - 4, wd = j % 3 - 1;
         if ((r < 0 && wd < 0) || (r < 0 && y == 0) || (wd < 0 && x == 0)) continue;
         __stcg((unsigned *)((pl ? A.cr : A.cb) + (size_t)(y * chh + r) * A.pitch_c + x * 8 + wd * 4), *(const unsigned *)&C[pl][(r + 4) * CP + (wd + 1) * 4]);
       }
+    }
   }
   __threadfence();
-  __syncwarp();
-  if (lane == 0) *(volatile int *)&A.done[mb] = A.serial;
+  __syncthreads();
+  if (tid == 0) *(volatile int *)&A.done[mb] = A.serial;
 }
 
 }  // namespace
@@ -246,7 +259,7 @@ extern "C" int jmb_deblock_picture(jmb_ctx *ctx, uint8_t *luma, int pitch, uint8
   A.ticket = (unsigned *)ctx->d_db; A.done = (int *)ctx->d_db + 1; A.serial = ++ctx->db_serial;
   A.mbw = mbw; A.mbh = mbh; A.yuv = yuv_format; A.slice_type = slice_type; A.d8 = direct_8x8_inference != 0;
   jmb_time_begin(ctx, JMB_K_DEBLOCK);
-  k_deblock<<<n, 32, 0, ctx->stream>>>(A);
+  k_deblock<<<n, 64, 0, ctx->stream>>>(A);
   jmb_time_end(ctx, JMB_K_DEBLOCK);
   JMB_LAUNCH_CHECK(ctx);
   if (host) {

@@ -710,7 +710,7 @@ __global__ void k_ffs_surfaces(const uint8_t *__restrict__ cur, int cur_pitch, c
 // (:618-689) / full_search_motion_estimation (me_fullsearch.c:39-103) do per partition: partition sums
 // (update_full_search_large_blocks :196-260, here on the fly), mv cost with the call's own predictor, arg-min with JM's
 // tie-break -- one small launch, answer through a host-mapped mailbox.
-constexpr int SF_NT = 192, SF_BH = 8, SF_PITCH = 96;      // surface kernel: threads, displacement rows per CTA, u16 per surface row
+constexpr int SF_NT = 96, SF_BH = 4, SF_PITCH = 96;      // surface kernel: threads, displacement rows per CTA, u16 per surface row
 static_assert(SF_PITCH >= CW, "a surface row holds one staging chunk of displacements");
 
 __global__ void __launch_bounds__(SF_NT)
@@ -745,7 +745,7 @@ k_mb_surfaces(const __grid_constant__ TMaps tm, int ref, int mbx, int mby, int x
 
 struct SurfView { const unsigned short *p; int x0, y0, ncol, nrow; };      // surfaces of displacements [x0, x0+ncol) x [y0, y0+nrow)
 
-constexpr int AM_NT = 256;
+constexpr int AM_NT = 512;
 __constant__ signed char c_sp9[9][2] = {{0,0},{0,-1},{0,1},{-1,-1},{1,-1},{-1,0},{1,0},{-1,1},{1,1}};      // spiral_search[0..8], mv_search.c:410-442
 
 // One partition's search: arg-min over its resident SAD surface, then -- JMB_REQ_SUBPEL -- the half- / quarter-pel
@@ -770,16 +770,22 @@ __device__ __forceinline__ void mb_search_body(MbSearchS &S, const jmb_me_req &r
     const int cx = r.center_x >> 2, cy = r.center_y >> 2, px = r.pred_x, py = r.pred_y, lam = r.lambda[0];
     const int side = 2 * R + 1;
     const unsigned short *surf = sv.p + (size_t)slot * sv.nrow * SF_PITCH;
+    // costs fit 32 bits (lambda <= 65535, mvbits <= 33 each, SAD < 2^16) unless nothing has been found yet; the spiral index
+    // (the tie-break) is only worked out for a candidate that reaches the thread's current best cost
     unsigned long long best = (unsigned long long)r.min_mcost << IDX_BITS;
+    unsigned bcost = (unsigned)min((unsigned long long)r.min_mcost, 0xffffffffull);
+    const unsigned side_rcp = 0xffffffffu / (unsigned)side + 1u;      // i / side == umulhi(i, side_rcp) for i, side < 2^16
     for (int i = tid; i < side * side; i += AM_NT) {
-      const int dyi = i / side, dxi = i - dyi * side;
+      const int dyi = (int)__umulhi((unsigned)i, side_rcp), dxi = i - dyi * side;
       const int dx = cx - R + dxi, dy = cy - R + dyi;                  // the candidate (integer pels)
       const int mx = 4 * dx - px, my = 4 * dy - py;
       if (ffs && max(abs(mx), abs(my)) >= max_mvd_m1) continue;       // me_fullfast.c:671
       const int Dx = jmb_clip(dlo_x, dhi_x, dx) - sv.x0, Dy = jmb_clip(dlo_y, dhi_y, dy) - sv.y0;   // where the block is read (UMVLine4X)
       const unsigned sad = surf[(size_t)Dy * SF_PITCH + Dx];
-      const unsigned long long cost = ((unsigned long long)sad << 5) + (unsigned long long)((long long)lam * (jmb_mvbits(mx) + jmb_mvbits(my)));
-      best = min(best, (cost << IDX_BITS) | (unsigned)jmb_spiral_index(dx - cx, dy - cy));
+      const unsigned cost = (sad << 5) + (unsigned)lam * (unsigned)(jmb_mvbits(mx) + jmb_mvbits(my));
+      if (cost > bcost) continue;
+      const unsigned long long k = ((unsigned long long)cost << IDX_BITS) | (unsigned)jmb_spiral_index(dx - cx, dy - cy);
+      if (k < best) { best = k; bcost = cost; }
     }
 #pragma unroll
     for (int sh = 16; sh; sh >>= 1) {
@@ -817,19 +823,20 @@ __device__ __forceinline__ void mb_search_body(MbSearchS &S, const jmb_me_req &r
         atomicAdd(&S.sums[pos], subblock_dist(rv, src, (r.pos_x << 2) + mvx + step * c_sp9[pos][0], (r.pos_y << 2) + mvy + step * c_sp9[pos][1], sbx, sby, nn, metric));
       }
       __syncthreads();
-      if (tid == 0) {      // JM's sequential strict-'<' selection (me_fullsearch.c:221-289)
+      if (tid < 32) {      // JM's sequential strict-'<' selection (me_fullsearch.c:221-289): the first of the cheapest candidates, if it beats the bound
         long long mn = S.mn;
         if (stage == 1 && !me.start_qp) mn = DISTBLK_MAX;
-        const int lam = r.lambda[1 + stage];
-        int best = 0;
-        for (int pos = pos0; pos < pos1; pos++) {
-          const int cxq = mvx + step * c_sp9[pos][0], cyq = mvy + step * c_sp9[pos][1];
-          long long mc = (long long)lam * (jmb_mvbits(cxq - r.pred_x) + jmb_mvbits(cyq - r.pred_y));
-          if (mc >= mn) continue;
-          mc += (long long)S.sums[pos] << 5;
-          if (mc < mn) { mn = mc; best = pos; }
+        unsigned key = 0xffffffffu;      // (cost << 4) | position: costs stay below 2^23
+        if (tid >= pos0 && tid < pos1) {
+          const int cxq = mvx + step * c_sp9[tid][0], cyq = mvy + step * c_sp9[tid][1];
+          key = (((unsigned)r.lambda[1 + stage] * (unsigned)(jmb_mvbits(cxq - r.pred_x) + jmb_mvbits(cyq - r.pred_y)) + ((unsigned)S.sums[tid] << 5)) << 4) | (unsigned)tid;
         }
-        S.mn = mn; S.mvx = mvx + step * c_sp9[best][0]; S.mvy = mvy + step * c_sp9[best][1];
+        key = __reduce_min_sync(0xffffffffu, key);
+        if (tid == 0) {
+          int best = 0;
+          if (key != 0xffffffffu && (long long)(key >> 4) < mn) { mn = key >> 4; best = (int)(key & 15); }
+          S.mn = mn; S.mvx = mvx + step * c_sp9[best][0]; S.mvy = mvy + step * c_sp9[best][1];
+        }
       }
       __syncthreads();
     }

@@ -378,3 +378,35 @@ def test_mb_chain_runs_ahead_like_jm_block_after_block(ctx, mode):
                 fin[i] = (min(max(int(want["mv_x"]), lim[0]), lim[1]), min(max(int(want["mv_y"]), lim[2]), lim[3]))
                 n_done += 1
     assert n_done > 150 and (n_unc > 0 or mode == api.SEARCH_FAST_FULL), (n_done, n_unc)
+
+
+def test_1080p_picture_step_matches_jm_on_a_sample(ctx):
+    """BASELINE config 2 at full size through the picture form (predictor table in, 8-byte results and (level, run) tokens out):
+    motion vectors, costs AND quantised levels of a sample of macroblocks against JM's OWN functions (oracle/_ref/libjmref.so:
+    full_search_motion_estimation, sub_pel_motion_estimation, forward4x4, quant_4x4_normal) -- the re-check bench.py's CPU leg does,
+    as a test."""
+    from oracle import pyoracle as po
+    from jm_b200 import h264_tables as T
+    import bench
+    if not po.ref_available():
+        pytest.skip("oracle/_ref/libjmref.so not built")
+    w, h, R, qp, lam = 1920, 1088, 32, 28, 187
+    n_mb = (w // 16) * (h // 16)
+    f = synth.luma_frames(w, h, 2, seed=4321, motion=(5, 3))
+    pred = bench.make_pred_table(api, 91, n_mb)
+    ctx.configure(search_range=R)
+    ctx.ref_put_u8(0, f[0].astype(np.uint8)); ctx.pic_begin_u8(f[1].astype(np.uint8), [0])
+    fp = api.frame_params([lam] * 3, mode=api.SEARCH_FULL, flags=api.REQ_SUBPEL)
+    g = ctx.me_search_frame_pred(pred, fp).reshape(n_mb, 41)
+    qd = api.quant_desc(4, qp, T.q_params(qp, 0, 4), T.SNGL_SCAN, T.COEFF_COST4x4[0], 1)
+    heads, tokens = ctx.mc_tq_modes_compact(None, qd, 0x7F, n_mb=n_mb, token_cap=7 * n_mb * 96)
+    idx = np.unique(np.concatenate([np.linspace(0, n_mb - 1, 40).astype(int), [0, w // 16 - 1, n_mb - w // 16, n_mb - 1]]))      # incl. the four corners
+    ref = po.JMRef(w, h, R)
+    ref.set_ref(f[0].astype(np.uint16)); ref.set_cur(f[1].astype(np.uint16))
+    mbw = w // 16
+    mb_xy = np.stack([(idx % mbw) * 16, (idx // mbw) * 16], 1)
+    mv, cost, lev, _ = po.jmref_run_mbs(ref, mb_xy, pred["pred"][idx], [lam] * 3, qp, T.q_params(qp, 0, 4), T.SNGL_SCAN, T.COEFF_COST4x4[0])
+    assert np.array_equal(g["mv_x"][idx], mv[:, :, 0]) and np.array_equal(g["mv_y"][idx], mv[:, :, 1])
+    assert np.array_equal(g["cost"][idx], cost)
+    assert np.array_equal(bench.expand_tokens(heads, tokens, idx, per=16), lev)
+    assert (lev != 0).sum() > 50
