@@ -327,7 +327,7 @@ def run_ours(args):
     # ---- end-to-end leg: K independent picture streams per GPU (K host threads, each its own context = its own CUDA stream,
     # reference slots and staging), pictures being independent units (closed-GOP shards) exactly like the ranks; the
     # single-stream figure (one thread, one context, strictly serial pictures) is reported beside it.
-    n_streams = args.e2e_streams if args.e2e_streams > 0 else max(1, min(3, (os.cpu_count() or 1) // world - 1))
+    n_streams = args.e2e_streams if args.e2e_streams > 0 else max(1, min(3, (os.cpu_count() or 1) // world))      # one host thread per picture stream
     e2e_ctx = [ctx] + [api.Context(local) for _ in range(n_streams - 1)]
     for c in e2e_ctx[1:]:
         c.configure(search_range=SEARCH_RANGE)

@@ -12,7 +12,7 @@ namespace {
 
 constexpr int EG = 41;         // searches per CTA: consecutive requests (one macroblock's 41 partitions in the picture form)
 constexpr int ET = 128;        // threads per CTA
-constexpr int CB = 32;         // candidates a search puts up per round
+constexpr int CB = 48;         // candidates a search puts up per round (a multiple of 4: IntS stays word-sized)
 #ifndef JMB_EPZS_SUB_MINB
 #define JMB_EPZS_SUB_MINB 8
 #endif
@@ -188,11 +188,11 @@ k_epzs_int(const jmb_epzs_req *__restrict__ reqs, int n, const short2 *__restric
           }
           have = 0;
           int k = 0;
-          while (k == 0 && seg < 4) {      // the next stretch of the list (:215-252): what is in range and new
+          while (seg < 4 && k < CB) {      // the next stretch of the list (:215-252), across its segments: what is in range
             const int ns = (ncw >> (8 * seg)) & 255, gate = (gtw >> (8 * seg)) & 255;
             const bool gen = seg == 2 && (flags & JMB_EPZS_WINDOW_GEN);
             if (i0 >= ns || !(gate == 0 || centre_cost > (long long)gate * stop)) { if (!gen) off += ns; seg++; i0 = 0; continue; }
-            const int nb = min(CB, ns - i0);
+            const int nb = min(CB - k, ns - i0);
             for (int i = i0; i < i0 + nb; i++) {
               short2 v;
               if (gen) {      // window predictors around the start mv: rings of size range >> k, k descending (EPZSWindowPredictorInit)

@@ -105,9 +105,18 @@ __constant__ signed char c_pk_half[NPART] = {
   24, 26, 25, 27, 28, 30, 29, 31,      // 4x8 (17..24): words 12 (s6[0], s6[2]), 13 (s6[1], s6[3]), 14 (s6[4], s6[6]), 15 (s6[5], s6[7])
   0, 2, 1, 3, 4, 6, 5, 7, 8, 10, 9, 11, 12, 14, 13, 15};      // 4x4 (25..40): words 2j = E_j (a[4j], a[4j+2]), 2j+1 = O_j (a[4j+1], a[4j+3])
 
+// lowers partition p's half of its packed word to min(thr, 32767) (never raises it: thr only falls)
 __device__ __forceinline__ void pk_set_thr(Grp *g, int p, unsigned thr) {
   const int h = c_pk_half[p];
-  if (h >= 0) ((volatile unsigned short *)g->thr2)[h] = (unsigned short)min(thr, 32767u);
+  if (h < 0) return;
+  const unsigned sh = (h & 1) * 16, val = min(thr, 32767u);
+  unsigned *w = &g->thr2[h >> 1], old = *(volatile unsigned *)w;
+  for (;;) {
+    if (((old >> sh) & 0xffffu) <= val) return;
+    const unsigned seen = atomicCAS(w, old, (old & ~(0xffffu << sh)) | (val << sh));
+    if (seen == old) return;
+    old = seen;
+  }
 }
 
 // Largest SAD that can still win against the key `k`: a winner needs (sad << 5) + lambda * bits <= cost(k),
@@ -151,7 +160,7 @@ __device__ __forceinline__ void publish(Grp *g, int p, unsigned long long k) {
   if (k < atomicMin(&g->best[p], k)) {
     const unsigned b = bound_of(k, g->rq[p].lam), old = atomicMin(&g->thr[p], b);
 #if JMB_IS_PACKED
-    if (b < old) {      // the packed copy follows (a racing, older value there is merely looser); the first to bring thr under 2^15 counts it off
+    if (b < old) {      // the packed copy follows; the first to bring thr under 2^15 counts it off
       pk_set_thr(g, p, *(volatile unsigned *)&g->thr[p]);
       if (old > 32767u && b <= 32767u && c_pk_half[p] >= 0) atomicSub(&g->nbig, 1);
     }
@@ -319,7 +328,7 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
     mbar_init(&mbar, 1);
     G.R = R; G.max_mvd_m1 = max_mvd_m1; G.thr[NPART] = G.thr[NPART + 1] = G.thr[NPART + 2] = 0;
     G.nbig = 0;
-    for (int i = 0; i < PK_PITCH; i++) G.thr2[i] = 0;
+    for (int i = 0; i < PK_PITCH; i++) G.thr2[i] = 0xffffffffu;      // (every partition lowers its half below; the spare word is never read)
   }
   __syncthreads();
   if (tid < NPART) {
