@@ -142,6 +142,8 @@ static struct
   int              chains_off;        /* JMB_SHIM_CHAIN=0: one device call per search (A/B of the run-ahead) */
   unsigned long    chain_calls, chain_hits, chain_stale;
   unsigned long    deblocked, deblock_verified;
+  int              rc_device;         /* JMB_SHIM_RC=device: luma_residual_coding of eligible inter macroblocks IS the device call (results written into JM's state) */
+  unsigned long    rc_written;
 } S;
 
 /* JM's convention for fatal conditions is error(text, code) -> message on stderr, exit(code) (lencod/src/lencod.c).
@@ -171,9 +173,9 @@ static void report(void)
   if (S.init == 1 && S.verify)
     fprintf(stderr, "[jmb shim] luma_residual_coding verified on %lu macroblock codings (levels, cbp, cbp_blk, reconstruction); chroma_residual_coding verified on %lu; DeblockFrame verified on %lu pictures (every sample)\n", S.verified, chroma_verified, S.deblock_verified);
   if (S.init == 1 && getenv("JMB_SHIM_VERBOSE"))
-    fprintf(stderr, "[jmb shim] planes %lu  full %lu  fastfull %lu  subpel %lu  fwd4 %lu  fwd8 %lu  quant4 %lu  quant8 %lu  dist %lu  kernel launches %llu  bipred/weighted distortions %lu  subpel served by the integer search's call %lu  surface builds %lu  chain calls %lu  searches answered ahead %lu  (discarded %lu)  pictures deblocked %lu (verified %lu)\n",
+    fprintf(stderr, "[jmb shim] planes %lu  full %lu  fastfull %lu  subpel %lu  fwd4 %lu  fwd8 %lu  quant4 %lu  quant8 %lu  dist %lu  kernel launches %llu  bipred/weighted distortions %lu  subpel served by the integer search's call %lu  surface builds %lu  chain calls %lu  searches answered ahead %lu  (discarded %lu)  pictures deblocked %lu (verified %lu)  luma_residual_coding answered by the device %lu\n",
             S.calls[0], S.calls[1], S.calls[2], S.calls[3], S.calls[4], S.calls[5], S.calls[6], S.calls[7], S.calls[8],
-            (unsigned long long)jmb_launch_count(S.ctx), S.calls[9], S.spec_hits, S.surf_builds, S.chain_calls, S.chain_hits, S.chain_stale, S.deblocked, S.deblock_verified);
+            (unsigned long long)jmb_launch_count(S.ctx), S.calls[9], S.spec_hits, S.surf_builds, S.chain_calls, S.chain_hits, S.chain_stale, S.deblocked, S.deblock_verified, S.rc_written);
 }
 
 static int shim_on(int family)
@@ -195,6 +197,7 @@ static int shim_on(int family)
       S.init = 1;
       S.verify = getenv("JMB_SHIM_VERIFY") != NULL;
       S.chains_off = getenv("JMB_SHIM_CHAIN") && !strcmp(getenv("JMB_SHIM_CHAIN"), "0");
+      S.rc_device = getenv("JMB_SHIM_RC") && !strcmp(getenv("JMB_SHIM_RC"), "device");
       if (off)
       {
         if (strstr(off, "planes")) S.off |= FAM_PLANES;
@@ -1401,11 +1404,24 @@ void __wrap_luma_residual_coding(Macroblock *currMB)
   int k, bx, by, i, j, rc, n, cavlc8, qp;
   uint8_t scan8[64][2];
 
-  __real_luma_residual_coding(currMB);
-  if (S.init != 1 || !S.verify || (S.off & FAM_TQ)) return;
-  if (currSlice->slice_type != P_SLICE || p_Vid->AdaptiveRounding || p_Vid->structure != FRAME || currSlice->mb_aff_frame_flag) return;
-  if (!(currMB->mb_type == P16x16 || currMB->mb_type == P16x8 || currMB->mb_type == P8x16 || currMB->mb_type == P8x8)) return;
-  if (currSlice->weighted_prediction || currSlice->NoResidueDirect == 1 || p_Vid->bitdepth_luma != 8) return;
+  /* JMB_SHIM_RC=device: for the macroblocks the device path covers (inter macroblocks of P slices, list-0 prediction, no
+   * adaptive rounding / weighted prediction / error-robust RDO) the device call REPLACES JM's function: its levels, cbp, cbp_blk and
+   * reconstruction are written into JM's state (cofAC, currMB, enc_picture) and JM's own code is not run.  Otherwise JM's function
+   * runs, and with JMB_SHIM_VERIFY the device result is compared with what it left. */
+  int write_back = 0, eligible = shim_on(FAM_TQ) || (S.init == 1 && S.rc_device);
+  if (eligible && (currSlice->slice_type != P_SLICE || p_Vid->AdaptiveRounding || p_Vid->structure != FRAME || currSlice->mb_aff_frame_flag)) eligible = 0;
+  if (eligible && !(currMB->mb_type == P16x16 || currMB->mb_type == P16x8 || currMB->mb_type == P8x16 || currMB->mb_type == P8x8)) eligible = 0;
+  if (eligible && (currSlice->weighted_prediction || currSlice->NoResidueDirect == 1 || p_Vid->bitdepth_luma != 8 || currMB->p_Inp->rdopt == 3)) eligible = 0;
+  if (eligible && currMB->p_Inp->UseRDOQuant) eligible = 0;
+  for (k = 0; eligible && k < 4; k++)
+  {
+    int mode = currMB->b8x8[k].mode;
+    if (currMB->b8x8[k].pdir != 0 || mode < 1 || mode > 7 || (currMB->luma_transform_size_8x8_flag && mode > 4) ||
+        p_Vid->enc_picture->mv_info[currMB->block_y + 2 * (k >> 1)][currMB->block_x + 2 * (k & 1)].ref_idx[LIST_0] < 0) eligible = 0;
+  }
+  write_back = eligible && S.rc_device;
+  if (!write_back) __real_luma_residual_coding(currMB);
+  if (S.init != 1 || !eligible || (!S.verify && !write_back)) return;
   n = currMB->luma_transform_size_8x8_flag ? 8 : 4;
   cavlc8 = (n == 8 && currSlice->symbol_mode == CAVLC);
   memset(&pred, 0, sizeof(pred));
@@ -1458,6 +1474,40 @@ void __wrap_luma_residual_coding(Macroblock *currMB)
   rc = jmb_luma_residual_coding(S.ctx, &pred, currMB->mbAddrX, 1, &d, levels, cost8, &cbp_blk, &cbp, recon, &sse, JMB_HOST);
   if (rc) jmb_die("jmb_luma_residual_coding", rc);
 
+  if (write_back)
+  { /* what luma_residual_coding leaves behind (macroblock.c:1182-1257, block.c:661-725): cbp / cbp_blk, the reconstruction, and per
+       transform block the (level, run) list in cofAC -- zero lists where thresholding cleared a quadrant */
+    currMB->cbp = (int)cbp;
+    currMB->cbp_blk = (int64)cbp_blk;
+    currSlice->cmp_cbp[1] = currSlice->cmp_cbp[2] = 0;
+    currSlice->cur_cbp_blk[1] = currSlice->cur_cbp_blk[2] = 0;
+    for (j = 0; j < 16; j++)
+      for (i = 0; i < 16; i++) p_Vid->enc_picture->imgY[currMB->pix_y + j][currMB->pix_x + i] = recon[j * 16 + i];
+    for (k = 0; k < 4; k++)
+    {
+      int lists = (n == 4 || cavlc8) ? 4 : 1, len = (n == 4 || cavlc8) ? 16 : 64, s, e;
+      if (cost8[k] == 0)
+      { /* the quadrant fell to reset_block (cost <= _LUMA_COEFF_COST_): JM clears its whole cofAC slab (macroblock.c:818) */
+        memset(currSlice->cofAC[k][0][0], 0, 4 * 2 * 65 * sizeof(int));
+        continue;
+      }
+      /* otherwise the lists stand as the quantiser wrote them -- also when the macroblock-level threshold then drops the cbp
+         (macroblock.c:1248-1255 leaves cofAC alone); like JM's quantisers, nothing is written behind the terminating level */
+      for (s = 0; s < lists; s++)
+      {
+        int *ACL = currSlice->cofAC[k][s][0], *ACR = currSlice->cofAC[k][s][1], run = 0, cnt = 0;
+        const int16_t *lv = (n == 4) ? &levels[((2 * (k >> 1) + (s >> 1)) * 4 + 2 * (k & 1) + (s & 1)) * 16] : &levels[k * 64 + s * 16];
+        for (e = 0; e < len; e++)
+        {
+          if (lv[e]) { ACL[cnt] = lv[e]; ACR[cnt] = run; cnt++; run = 0; }
+          else run++;
+        }
+        ACL[cnt] = 0;
+      }
+    }
+    S.rc_written++;
+    return;
+  }
   if ((currMB->cbp & 15) != (int)cbp) verify_mismatch(currMB, "cbp", currMB->cbp & 15, (int)cbp);
   if ((int)(currMB->cbp_blk & 0xffff) != (int)cbp_blk) verify_mismatch(currMB, "cbp_blk", (int)(currMB->cbp_blk & 0xffff), (int)cbp_blk);
   for (j = 0; j < 16; j++)

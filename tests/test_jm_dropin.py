@@ -192,6 +192,24 @@ def test_device_luma_residual_coding_matches_jm_in_the_live_encoder(tmp_path, na
 
 @pytest.mark.gpu
 @needs_bins
+@pytest.mark.parametrize("name", sorted(VERIFY_CONFIGS))
+def test_luma_residual_coding_answered_by_the_device_gives_the_same_bitstream(tmp_path, name):
+    """JMB_SHIM_RC=device: for inter macroblocks of P slices JM's luma_residual_coding is NOT run -- one device call per RD
+    candidate (jmb_luma_residual_coding: prediction .. transform .. quantisation .. reconstruction .. thresholding) and its
+    levels, cbp, cbp_blk and reconstruction written into JM's state (cofAC, currMB, enc_picture).  Mode decision, entropy coding
+    and everything after see exactly what JM's own function would have left: bitstream, reconstruction and trace are identical."""
+    w, h, frames = 96, 80, 3
+    _make_yuv(tmp_path / "input.yuv", w, h, frames, seed=19)
+    r1 = _encode(REF, tmp_path, "ref", w, h, frames, VERIFY_CONFIGS[name])
+    r2 = _encode(JMB, tmp_path, "gpu", w, h, frames, VERIFY_CONFIGS[name], env={"JMB_SHIM_RC": "device", "JMB_SHIM_VERBOSE": "1"})
+    assert r1.returncode == 0 and r2.returncode == 0, (r1.stderr[-500:], r2.stderr[-500:])
+    _same_outputs(tmp_path, "ref", "gpu")
+    line = [l for l in r2.stderr.splitlines() if l.startswith("[jmb shim]")][0]
+    assert int(line.split("luma_residual_coding answered by the device")[1].split()[0]) > 100, line
+
+
+@pytest.mark.gpu
+@needs_bins
 def test_device_chroma_residual_coding_422_matches_jm_in_the_live_encoder(tmp_path):
     """The same differential pin for 4:2:2 (BASELINE config 4's chroma): hadamard4x2 + quant_dc4x2 at qp + 3, eight AC blocks per
     component, 1/4-sample vertical chroma motion."""
