@@ -1810,7 +1810,7 @@ void __wrap_DeblockFrame(VideoParameters *p_Vid, imgpel **imgY, imgpel ***imgUV)
   StorablePicture *pics[64];
   int npics = 0, i, k, l, x, y, rc, slice_type;
   jmb_db_mb *mbs;
-  uint8_t *pl[3], *chk[3] = {NULL, NULL, NULL};
+  uint8_t *pl[3];
   if (!shim_on(FAM_DEBLOCK)) { __real_DeblockFrame(p_Vid, imgY, imgUV); return; }
   if (p_Vid->mb_aff_frame_flag || p_Vid->structure != FRAME) unsupported("deblocking of field / MBAFF pictures");
   if (p_Vid->P444_joined || p_Vid->yuv_format == YUV444) unsupported("deblocking of 4:4:4 pictures");
@@ -1868,6 +1868,5 @@ void __wrap_DeblockFrame(VideoParameters *p_Vid, imgpel **imgY, imgpel ***imgUV)
     if (yuv) for (k = 0; k < 2; k++) for (y = 0; y < hc; y++) for (x = 0; x < wc; x++) imgUV[k][y][x] = pl[1 + k][(size_t)y * wc + x];
   }
   S.deblocked++;
-  (void)chk;
   free(mbs); free(pl[0]); free(pl[1]); free(pl[2]);
 }

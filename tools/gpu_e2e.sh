@@ -1,3 +1,7 @@
 #!/bin/bash
-for k in ${@:-1 2 3 4}; do python bench.py --steps 60 --warmup 3 --no-cpu --e2e-streams $k 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('streams $k', 'value', round(d['value']), 'e2e', round(d['e2e']['value']), 'ms', round(d['e2e']['ms_per_step'],3), d['e2e']['host_ms_per_picture'])"; done
+# tools/gpu_e2e.sh -- end-to-end leg with 1..6 picture streams per GPU
+for k in 2 3 4 5 6; do
+  python bench.py --steps 60 --warmup 3 --no-cpu --no-worst --e2e-streams $k 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); e=d['e2e']; print('streams', $k, 'e2e', round(e['value']), 'ms', round(e['ms_per_step'],4), 'value', round(d['value']))"
+done
+nproc
