@@ -64,7 +64,6 @@ struct jmb_ctx {
   Surf surf[JMB_MAX_REFS];
   unsigned long pic_serial = 0, reftab_serial = 0, mb_calls = 0;      // pic_serial: bumped by every jmb_pic_begin / jmb_ref_put
   void *mbox = nullptr, *d_mbox = nullptr, *d_one = nullptr; int mbox_seq = 0;
-  int epzs_grid[2] = {0, 0};  // persistent grid sizes of k_epzs_int / k_epzs_sub on this context's device
   // picture form with device-generated requests / compact outputs
   void *d_mvpred = nullptr; size_t d_mvpred_cap = 0;
   void *d_res8 = nullptr; size_t d_res8_cap = 0;
