@@ -52,41 +52,44 @@ __device__ int db_strength(int dir, int edge, int k, const jmb_db_mb &Q, const j
   return (db_mvdiff(mp0, mq0) | db_mvdiff(mp1, mq1)) && (db_mvdiff(mp0, mq1) | db_mvdiff(mp1, mq0));
 }
 
-// EdgeLoopLumaVer / Hor (:310-575), one line of samples across the edge: q = q0, st = the step away from the edge
-__device__ __forceinline__ void db_luma_line(uint8_t *q, int st, int bs, int alpha, int beta, int c0) {
-  uint8_t *p = q - st;
-  const int L0 = p[0], R0 = q[0], L1 = p[-st], R1 = q[st];
-  if (abs(R0 - L0) >= alpha || abs(R0 - R1) >= beta || abs(L0 - L1) >= beta) return;
-  const int L2 = p[-2 * st], R2 = q[2 * st];
-  if (bs == 4) {
-    const int RL0 = L0 + R0, small_gap = abs(R0 - L0) < ((alpha >> 2) + 2);
-    const int aq = (abs(R0 - R2) < beta) & small_gap, ap = (abs(L0 - L2) < beta) & small_gap;
-    if (ap) {
-      const int L3 = p[-3 * st];
-      p[0] = (uint8_t)((R1 + ((L1 + RL0) << 1) + L2 + 4) >> 3); p[-st] = (uint8_t)((L2 + L1 + RL0 + 2) >> 2); p[-2 * st] = (uint8_t)((((L3 + L2) << 1) + L2 + L1 + RL0 + 4) >> 3);
-    } else p[0] = (uint8_t)(((L1 << 1) + L0 + R1 + 2) >> 2);
-    if (aq) {
-      const int R3 = q[3 * st];
-      q[0] = (uint8_t)((L1 + ((R1 + RL0) << 1) + R2 + 4) >> 3); q[st] = (uint8_t)((R2 + R0 + L0 + R1 + 2) >> 2); q[2 * st] = (uint8_t)((((R3 + R2) << 1) + R2 + R1 + RL0 + 4) >> 3);
-    } else q[0] = (uint8_t)(((R1 << 1) + R0 + L1 + 2) >> 2);
+// One line of samples across a luma edge in the standard's notation (H.264 8.7.2.3 / 8.7.2.4; JM: EdgeLoopLumaVer / Hor,
+// loop_filter_normal.c:310-575): q points at q0, `st` is the step away from the edge, p0 = q[-st].
+__device__ __forceinline__ void db_luma_line(uint8_t *q, int st, int bS, int alpha, int beta, int tc0) {
+  const int p0 = q[-st], q0 = q[0], p1 = q[-2 * st], q1 = q[st];
+  if (abs(p0 - q0) >= alpha || abs(p1 - p0) >= beta || abs(q1 - q0) >= beta) return;      // filterSamplesFlag
+  const int p2 = q[-3 * st], q2 = q[2 * st];
+  const bool ap = abs(p2 - p0) < beta, aq = abs(q2 - q0) < beta;
+  if (bS == 4) {
+    const bool strong = abs(p0 - q0) < (alpha >> 2) + 2;
+    if (ap && strong) {
+      const int p3 = q[-4 * st];
+      q[-st] = (uint8_t)((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
+      q[-2 * st] = (uint8_t)((p2 + p1 + p0 + q0 + 2) >> 2);
+      q[-3 * st] = (uint8_t)((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
+    } else q[-st] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
+    if (aq && strong) {
+      const int q3 = q[3 * st];
+      q[0] = (uint8_t)((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
+      q[st] = (uint8_t)((p0 + q0 + q1 + q2 + 2) >> 2);
+      q[2 * st] = (uint8_t)((2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3);
+    } else q[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
   } else {
-    const int RL0 = (L0 + R0 + 1) >> 1, aq = abs(R0 - R2) < beta, ap = abs(L0 - L2) < beta, tc0 = c0 + ap + aq;
-    const int dif = jmb_clip(-tc0, tc0, (((R0 - L0) << 2) + (L1 - R1) + 4) >> 3);
-    if (ap) p[-st] = (uint8_t)(L1 + jmb_clip(-c0, c0, (L2 + RL0 - (L1 << 1)) >> 1));
-    if (dif) { p[0] = (uint8_t)jmb_clip(0, 255, L0 + dif); q[0] = (uint8_t)jmb_clip(0, 255, R0 - dif); }
-    if (aq) q[st] = (uint8_t)(R1 + jmb_clip(-c0, c0, (R2 + RL0 - (R1 << 1)) >> 1));
+    const int tc = tc0 + ap + aq, avg = (p0 + q0 + 1) >> 1;
+    const int delta = jmb_clip(-tc, tc, (((q0 - p0) << 2) + (p1 - q1) + 4) >> 3);
+    if (ap) q[-2 * st] = (uint8_t)(p1 + jmb_clip(-tc0, tc0, (p2 + avg - 2 * p1) >> 1));
+    if (aq) q[st] = (uint8_t)(q1 + jmb_clip(-tc0, tc0, (q2 + avg - 2 * q1) >> 1));
+    if (delta) { q[-st] = (uint8_t)jmb_clip(0, 255, p0 + delta); q[0] = (uint8_t)jmb_clip(0, 255, q0 - delta); }
   }
 }
 
-// EdgeLoopChromaVer / Hor (:585-758)
-__device__ __forceinline__ void db_chroma_line(uint8_t *q, int st, int bs, int alpha, int beta, int c0) {
-  uint8_t *p = q - st;
-  const int L0 = p[0], R0 = q[0], L1 = p[-st], R1 = q[st];
-  if (abs(R0 - L0) >= alpha || abs(R0 - R1) >= beta || abs(L0 - L1) >= beta) return;
-  if (bs == 4) { p[0] = (uint8_t)(((L1 << 1) + L0 + R1 + 2) >> 2); q[0] = (uint8_t)(((R1 << 1) + R0 + L1 + 2) >> 2); }
+// the same for a chroma edge (chromaStyleFilteringFlag: only p0 and q0 change; JM: EdgeLoopChromaVer / Hor, :585-758)
+__device__ __forceinline__ void db_chroma_line(uint8_t *q, int st, int bS, int alpha, int beta, int tc0) {
+  const int p0 = q[-st], q0 = q[0], p1 = q[-2 * st], q1 = q[st];
+  if (abs(p0 - q0) >= alpha || abs(p1 - p0) >= beta || abs(q1 - q0) >= beta) return;
+  if (bS == 4) { q[-st] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2); q[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2); }
   else {
-    const int tc0 = c0 + 1, dif = jmb_clip(-tc0, tc0, (((R0 - L0) << 2) + (L1 - R1) + 4) >> 3);
-    if (dif) { p[0] = (uint8_t)jmb_clip(0, 255, L0 + dif); q[0] = (uint8_t)jmb_clip(0, 255, R0 - dif); }
+    const int tc = tc0 + 1, delta = jmb_clip(-tc, tc, (((q0 - p0) << 2) + (p1 - q1) + 4) >> 3);
+    if (delta) { q[-st] = (uint8_t)jmb_clip(0, 255, p0 + delta); q[0] = (uint8_t)jmb_clip(0, 255, q0 - delta); }
   }
 }
 

@@ -1004,38 +1004,46 @@ static int db_strength(int dir, int edge, int k, const jmo_db_mb *Q, const jmo_d
 
 static int db_clip(int lo, int hi, int v) { return v < lo ? lo : v > hi ? hi : v; }
 
-/* one line of samples across a luma edge: q points at q0, `st` steps away from the edge on the q side */
-static void db_luma_line(uint8_t *q, int st, int bs, int alpha, int beta, int c0)
+/* one line of samples across a luma edge, in the standard's notation (8.7.2.3 / 8.7.2.4; loop_filter_normal.c:310-575):
+ * q points at q0, `st` steps away from the edge, p0 = q[-st] */
+static void db_luma_line(uint8_t *q, int st, int bS, int alpha, int beta, int tc0)
 {
-  uint8_t *p = q - st;
-  int L0 = p[0], R0 = q[0], L1 = p[-st], R1 = q[st];
-  if (abs(R0 - L0) >= alpha || abs(R0 - R1) >= beta || abs(L0 - L1) >= beta) return;
-  int L2 = p[-2 * st], R2 = q[2 * st];
-  if (bs == 4) {
-    int RL0 = L0 + R0, small_gap = abs(R0 - L0) < ((alpha >> 2) + 2);
-    int aq = (abs(R0 - R2) < beta) & small_gap, ap = (abs(L0 - L2) < beta) & small_gap;
-    if (ap) { int L3 = p[-3 * st]; p[0] = (uint8_t)((R1 + ((L1 + RL0) << 1) + L2 + 4) >> 3); p[-st] = (uint8_t)((L2 + L1 + RL0 + 2) >> 2); p[-2 * st] = (uint8_t)((((L3 + L2) << 1) + L2 + L1 + RL0 + 4) >> 3); }
-    else p[0] = (uint8_t)(((L1 << 1) + L0 + R1 + 2) >> 2);
-    if (aq) { int R3 = q[3 * st]; q[0] = (uint8_t)((L1 + ((R1 + RL0) << 1) + R2 + 4) >> 3); q[st] = (uint8_t)((R2 + R0 + L0 + R1 + 2) >> 2); q[2 * st] = (uint8_t)((((R3 + R2) << 1) + R2 + R1 + RL0 + 4) >> 3); }
-    else q[0] = (uint8_t)(((R1 << 1) + R0 + L1 + 2) >> 2);
+  int p0 = q[-st], q0 = q[0], p1 = q[-2 * st], q1 = q[st];
+  if (abs(p0 - q0) >= alpha || abs(p1 - p0) >= beta || abs(q1 - q0) >= beta) return;
+  int p2 = q[-3 * st], q2 = q[2 * st];
+  int ap = abs(p2 - p0) < beta, aq = abs(q2 - q0) < beta;
+  if (bS == 4) {
+    int strong = abs(p0 - q0) < (alpha >> 2) + 2;
+    if (ap && strong) {
+      int p3 = q[-4 * st];
+      q[-st] = (uint8_t)((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
+      q[-2 * st] = (uint8_t)((p2 + p1 + p0 + q0 + 2) >> 2);
+      q[-3 * st] = (uint8_t)((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
+    } else q[-st] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
+    if (aq && strong) {
+      int q3 = q[3 * st];
+      q[0] = (uint8_t)((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
+      q[st] = (uint8_t)((p0 + q0 + q1 + q2 + 2) >> 2);
+      q[2 * st] = (uint8_t)((2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3);
+    } else q[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
   } else {
-    int RL0 = (L0 + R0 + 1) >> 1, aq = abs(R0 - R2) < beta, ap = abs(L0 - L2) < beta, tc0 = c0 + ap + aq;
-    int dif = db_clip(-tc0, tc0, (((R0 - L0) << 2) + (L1 - R1) + 4) >> 3);
-    if (ap) p[-st] = (uint8_t)(L1 + db_clip(-c0, c0, (L2 + RL0 - (L1 << 1)) >> 1));
-    if (dif) { p[0] = (uint8_t)db_clip(0, 255, L0 + dif); q[0] = (uint8_t)db_clip(0, 255, R0 - dif); }
-    if (aq) q[st] = (uint8_t)(R1 + db_clip(-c0, c0, (R2 + RL0 - (R1 << 1)) >> 1));
+    int tc = tc0 + ap + aq, avg = (p0 + q0 + 1) >> 1;
+    int delta = db_clip(-tc, tc, (((q0 - p0) << 2) + (p1 - q1) + 4) >> 3);
+    if (ap) q[-2 * st] = (uint8_t)(p1 + db_clip(-tc0, tc0, (p2 + avg - 2 * p1) >> 1));
+    if (aq) q[st] = (uint8_t)(q1 + db_clip(-tc0, tc0, (q2 + avg - 2 * q1) >> 1));
+    if (delta) { q[-st] = (uint8_t)db_clip(0, 255, p0 + delta); q[0] = (uint8_t)db_clip(0, 255, q0 - delta); }
   }
 }
 
-static void db_chroma_line(uint8_t *q, int st, int bs, int alpha, int beta, int c0)
+/* chroma: only p0 and q0 change (loop_filter_normal.c:585-758) */
+static void db_chroma_line(uint8_t *q, int st, int bS, int alpha, int beta, int tc0)
 {
-  uint8_t *p = q - st;
-  int L0 = p[0], R0 = q[0], L1 = p[-st], R1 = q[st];
-  if (abs(R0 - L0) >= alpha || abs(R0 - R1) >= beta || abs(L0 - L1) >= beta) return;
-  if (bs == 4) { p[0] = (uint8_t)(((L1 << 1) + L0 + R1 + 2) >> 2); q[0] = (uint8_t)(((R1 << 1) + R0 + L1 + 2) >> 2); }
+  int p0 = q[-st], q0 = q[0], p1 = q[-2 * st], q1 = q[st];
+  if (abs(p0 - q0) >= alpha || abs(p1 - p0) >= beta || abs(q1 - q0) >= beta) return;
+  if (bS == 4) { q[-st] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2); q[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2); }
   else {
-    int tc0 = c0 + 1, dif = db_clip(-tc0, tc0, (((R0 - L0) << 2) + (L1 - R1) + 4) >> 3);
-    if (dif) { p[0] = (uint8_t)db_clip(0, 255, L0 + dif); q[0] = (uint8_t)db_clip(0, 255, R0 - dif); }
+    int tc = tc0 + 1, delta = db_clip(-tc, tc, (((q0 - p0) << 2) + (p1 - q1) + 4) >> 3);
+    if (delta) { q[-st] = (uint8_t)db_clip(0, 255, p0 + delta); q[0] = (uint8_t)db_clip(0, 255, q0 - delta); }
   }
 }
 
