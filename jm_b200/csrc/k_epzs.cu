@@ -404,40 +404,49 @@ k_epzs_sub(const jmb_epzs_req *__restrict__ reqs, int n, jmb_epzs_res *__restric
   if (tid < cnt && live) { res[base + tid].mv_x = (int16_t)mvx; res[base + tid].mv_y = (int16_t)mvy; res[base + tid].cost = minc; res[base + tid].n_evals = evals; }
 }
 
-// requests of a whole picture for jmb_epzs_search_frame
-__global__ void k_gen_epzs(const jmb_mb_mvpred *__restrict__ pred, int n_mb, int mb_w, jmb_epzs_frame_params fp, jmb_epzs_req *__restrict__ reqs) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_mb * 41) return;
-  const int mb = t / 41, p = t - mb * 41;
-  // canonical partition order: type, then raster order inside the macroblock
-  const int type = p < 1 ? 1 : p < 3 ? 2 : p < 5 ? 3 : p < 9 ? 4 : p < 17 ? 5 : p < 25 ? 6 : 7;
-  const int first = type == 1 ? 0 : type == 2 ? 1 : type == 3 ? 3 : type == 4 ? 5 : type == 5 ? 9 : type == 6 ? 17 : 25;
-  const int bsx = c_bsx[type], bsy = c_bsy[type], k = p - first, per_row = 16 / bsx;
-  jmb_epzs_req q;
-  memset(&q, 0, sizeof(q));
-  q.pos_x = (int16_t)((mb % mb_w) * 16 + (k % per_row) * bsx); q.pos_y = (int16_t)((mb / mb_w) * 16 + (k / per_row) * bsy);
-  const int px = pred[mb].pred[p][0], py = pred[mb].pred[p][1];
-  q.pred_x = (int16_t)px; q.pred_y = (int16_t)py;
-  // EPZSSubPelGrid: the search starts at the predictor itself (mv_search.c:925-928), clipped to the mv range (:957)
-  q.start_x = (int16_t)jmb_clip(fp.mv_min_x, fp.mv_max_x, px); q.start_y = (int16_t)jmb_clip(fp.mv_min_y, fp.mv_max_y, py);
-  q.blocktype = (uint8_t)type; q.ref = q.jm_ref = (uint8_t)fp.ref;
-  q.flags = (uint8_t)((fp.flags & (JMB_EPZS_ADAPT_PATTERN | JMB_EPZS_DUAL | JMB_EPZS_SUBPEL | (type <= 4 ? JMB_EPZS_TEST8X8 : 0))) | (fp.window ? JMB_EPZS_WINDOW_GEN : 0));
-  q.pattern = (uint8_t)fp.pattern; q.pattern_dual = (uint8_t)fp.pattern_dual;
-  q.n_cand[0] = (uint8_t)fp.n_shared; q.n_cand[2] = (uint8_t)(fp.window ? 8 * fp.window - 1 : 0);
-  q.gate[2] = 3;                                                       // me_epzs_int.c:193-198
-  q.cand_off = mb * fp.n_shared;
-  q.lambda[0] = fp.lambda[0]; q.lambda[1] = fp.lambda[1]; q.lambda[2] = fp.lambda[2];
-  q.range_x = q.range_y = (int16_t)fp.range;
-  // EPZSDetermineStopCriterion (me_epzs_common.c:1874) with no neighbour distortion known (sadA = sadB = sadC = DISTBLK_MAX)
-  const long long ld = 2ll * fp.lambda[0], med = fp.medthres[type];
-  long long stop = (long long)0x7fffffff << 5;
-  stop = max(stop, (long long)fp.minthres[type]);
-  stop = min(stop, (long long)fp.maxthres[type] + ld);
-  stop = (8 * max(med + ld, stop) + med) >> 3;
-  q.stop = stop + ld; q.medthres = med; q.subthres = fp.subthres[type];
-  q.prev_sad = (long long)0x7fffffff << 5;
-  q.min_mcost = (long long)0x7fffffff << 5;
-  reqs[t] = q;
+// requests of a whole picture for jmb_epzs_search_frame (88-byte records staged in shared memory, written as 16-byte words)
+__global__ void __launch_bounds__(256)
+k_gen_epzs(const jmb_mb_mvpred *__restrict__ pred, int n_mb, int mb_w, jmb_epzs_frame_params fp, jmb_epzs_req *__restrict__ reqs) {
+  __shared__ __align__(16) jmb_epzs_req sq[256];
+  static_assert(sizeof(jmb_epzs_req) == 88, "staging copies 256 x 88 bytes as 1408 x 16");
+  const int t0 = blockIdx.x * 256, t = t0 + threadIdx.x, n = n_mb * 41;
+  if (t < n) {
+    const int mb = t / 41, p = t - mb * 41;
+    // canonical partition order: type, then raster order inside the macroblock
+    const int type = p < 1 ? 1 : p < 3 ? 2 : p < 5 ? 3 : p < 9 ? 4 : p < 17 ? 5 : p < 25 ? 6 : 7;
+    const int first = type == 1 ? 0 : type == 2 ? 1 : type == 3 ? 3 : type == 4 ? 5 : type == 5 ? 9 : type == 6 ? 17 : 25;
+    const int bsx = c_bsx[type], bsy = c_bsy[type], k = p - first, per_row = 16 / bsx;
+    jmb_epzs_req q;
+    memset(&q, 0, sizeof(q));
+    q.pos_x = (int16_t)((mb % mb_w) * 16 + (k % per_row) * bsx); q.pos_y = (int16_t)((mb / mb_w) * 16 + (k / per_row) * bsy);
+    const int px = pred[mb].pred[p][0], py = pred[mb].pred[p][1];
+    q.pred_x = (int16_t)px; q.pred_y = (int16_t)py;
+    // EPZSSubPelGrid: the search starts at the predictor itself (mv_search.c:925-928), clipped to the mv range (:957)
+    q.start_x = (int16_t)jmb_clip(fp.mv_min_x, fp.mv_max_x, px); q.start_y = (int16_t)jmb_clip(fp.mv_min_y, fp.mv_max_y, py);
+    q.blocktype = (uint8_t)type; q.ref = q.jm_ref = (uint8_t)fp.ref;
+    q.flags = (uint8_t)((fp.flags & (JMB_EPZS_ADAPT_PATTERN | JMB_EPZS_DUAL | JMB_EPZS_SUBPEL | (type <= 4 ? JMB_EPZS_TEST8X8 : 0))) | (fp.window ? JMB_EPZS_WINDOW_GEN : 0));
+    q.pattern = (uint8_t)fp.pattern; q.pattern_dual = (uint8_t)fp.pattern_dual;
+    q.n_cand[0] = (uint8_t)fp.n_shared; q.n_cand[2] = (uint8_t)(fp.window ? 8 * fp.window - 1 : 0);
+    q.gate[2] = 3;                                                       // me_epzs_int.c:193-198
+    q.cand_off = mb * fp.n_shared;
+    q.lambda[0] = fp.lambda[0]; q.lambda[1] = fp.lambda[1]; q.lambda[2] = fp.lambda[2];
+    q.range_x = q.range_y = (int16_t)fp.range;
+    // EPZSDetermineStopCriterion (me_epzs_common.c:1874) with no neighbour distortion known (sadA = sadB = sadC = DISTBLK_MAX)
+    const long long ld = 2ll * fp.lambda[0], med = fp.medthres[type];
+    long long stop = (long long)0x7fffffff << 5;
+    stop = max(stop, (long long)fp.minthres[type]);
+    stop = min(stop, (long long)fp.maxthres[type] + ld);
+    stop = (8 * max(med + ld, stop) + med) >> 3;
+    q.stop = stop + ld; q.medthres = med; q.subthres = fp.subthres[type];
+    q.prev_sad = (long long)0x7fffffff << 5;
+    q.min_mcost = (long long)0x7fffffff << 5;
+    sq[threadIdx.x] = q;
+  }
+  __syncthreads();
+  const int cnt = min(256, n - t0);
+  uint4 *dst = (uint4 *)(reqs + t0);
+  for (int i = threadIdx.x; i < cnt * 88 / 16; i += 256) dst[i] = ((const uint4 *)sq)[i];
+  for (int i = (cnt * 88 / 16) * 16 + threadIdx.x * 8; i < cnt * 88; i += 256 * 8) *(uint2 *)((char *)dst + i) = *(const uint2 *)((const char *)sq + i);
 }
 
 // 8-byte results (+ the final clip of the mv, mv_search.c:981) and the 24-byte form the residual coder reads

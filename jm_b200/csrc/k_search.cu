@@ -1095,36 +1095,54 @@ static int me_search_impl(jmb_ctx *ctx, const jmb_me_req *reqs, int n, jmb_me_re
 namespace {
 // Requests of a whole picture from the 41 predictors of every macroblock (jmb_me_search_frame_pred): block geometry from the
 // partition index, search centre and flags by the rules of BlockMotionSearch / setup_fast_full_search.
-__global__ void k_gen_requests(const jmb_mb_mvpred *__restrict__ pred, int n_mb, int mb_w, jmb_frame_params fp, int R, jmb_me_req *__restrict__ reqs) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_mb * NPART) return;
-  const int mb = t / NPART, p = t - mb * NPART;
-  const PartGeom pg = c_part[p];
-  const int px = pred[mb].pred[p][0], py = pred[mb].pred[p][1];
-  jmb_me_req q;
-  q.pos_x = (int16_t)((mb % mb_w) * 16 + pg.bx * 4); q.pos_y = (int16_t)((mb / mb_w) * 16 + pg.by * 4);
-  q.pred_x = (int16_t)px; q.pred_y = (int16_t)py;
-  if (fp.mode == JMB_SEARCH_FAST_FULL) {      // one centre per macroblock: the rounded 16x16 predictor (me_fullfast.c:309-327)
-    const int bx = pred[mb].pred[0][0], by = pred[mb].pred[0][1];
-    q.center_x = (int16_t)jmb_clip(fp.mv_min_x + 4 * R, fp.mv_max_x - 4 * R, ((bx + 2) >> 2) * 4);
-    q.center_y = (int16_t)jmb_clip(fp.mv_min_y + 4 * R, fp.mv_max_y - 4 * R, ((by + 2) >> 2) * 4);
-  } else {                                    // mv_search.c:931-932, clip_mv_range :957
-    q.center_x = (int16_t)jmb_clip(fp.mv_min_x, fp.mv_max_x, ((px + 2) >> 2) * 4);
-    q.center_y = (int16_t)jmb_clip(fp.mv_min_y, fp.mv_max_y, ((py + 2) >> 2) * 4);
+// (40-byte records: a block of 256 stages them in shared memory and writes 16-byte words, 640 per block, fully coalesced)
+__global__ void __launch_bounds__(256)
+k_gen_requests(const jmb_mb_mvpred *__restrict__ pred, int n_mb, int mb_w, jmb_frame_params fp, int R, jmb_me_req *__restrict__ reqs) {
+  __shared__ __align__(16) jmb_me_req sq[256];
+  static_assert(sizeof(jmb_me_req) == 40, "staging copies 256 x 40 bytes as 640 x 16");
+  const int t0 = blockIdx.x * 256, t = t0 + threadIdx.x, n = n_mb * NPART;
+  if (t < n) {
+    const int mb = t / NPART, p = t - mb * NPART;
+    const PartGeom pg = c_part[p];
+    const int px = pred[mb].pred[p][0], py = pred[mb].pred[p][1];
+    jmb_me_req q;
+    q.pos_x = (int16_t)((mb % mb_w) * 16 + pg.bx * 4); q.pos_y = (int16_t)((mb / mb_w) * 16 + pg.by * 4);
+    q.pred_x = (int16_t)px; q.pred_y = (int16_t)py;
+    if (fp.mode == JMB_SEARCH_FAST_FULL) {      // one centre per macroblock: the rounded 16x16 predictor (me_fullfast.c:309-327)
+      const int bx = pred[mb].pred[0][0], by = pred[mb].pred[0][1];
+      q.center_x = (int16_t)jmb_clip(fp.mv_min_x + 4 * R, fp.mv_max_x - 4 * R, ((bx + 2) >> 2) * 4);
+      q.center_y = (int16_t)jmb_clip(fp.mv_min_y + 4 * R, fp.mv_max_y - 4 * R, ((by + 2) >> 2) * 4);
+    } else {                                    // mv_search.c:931-932, clip_mv_range :957
+      q.center_x = (int16_t)jmb_clip(fp.mv_min_x, fp.mv_max_x, ((px + 2) >> 2) * 4);
+      q.center_y = (int16_t)jmb_clip(fp.mv_min_y, fp.mv_max_y, ((py + 2) >> 2) * 4);
+    }
+    q.blocktype = pg.type; q.ref = (uint8_t)fp.ref; q.mode = (uint8_t)fp.mode;
+    q.flags = (uint8_t)(fp.flags & (JMB_REQ_SUBPEL | (pg.type <= 4 ? JMB_REQ_TEST8X8 : 0)));
+    q.lambda[0] = fp.lambda[0]; q.lambda[1] = fp.lambda[1]; q.lambda[2] = fp.lambda[2];
+    q.reserved_ = 0;
+    q.min_mcost = (int64_t)0x7fffffff << 5;      // DISTBLK_MAX, lencod/inc/defines.h:136
+    sq[threadIdx.x] = q;
   }
-  q.blocktype = pg.type; q.ref = (uint8_t)fp.ref; q.mode = (uint8_t)fp.mode;
-  q.flags = (uint8_t)(fp.flags & (JMB_REQ_SUBPEL | (pg.type <= 4 ? JMB_REQ_TEST8X8 : 0)));
-  q.lambda[0] = fp.lambda[0]; q.lambda[1] = fp.lambda[1]; q.lambda[2] = fp.lambda[2];
-  q.reserved_ = 0;
-  q.min_mcost = (int64_t)0x7fffffff << 5;      // DISTBLK_MAX, lencod/inc/defines.h:136
-  reqs[t] = q;
+  __syncthreads();
+  const int cnt = min(256, n - t0);      // records of this block; 256 * 40 bytes start on a 16-byte boundary
+  uint4 *dst = (uint4 *)(reqs + t0);
+  for (int i = threadIdx.x; i < cnt * 40 / 16; i += 256) dst[i] = ((const uint4 *)sq)[i];
+  for (int i = (cnt * 40 / 16) * 16 + threadIdx.x * 8; i < cnt * 40; i += 256 * 8) *(uint2 *)((char *)dst + i) = *(const uint2 *)((const char *)sq + i);
 }
 
-// final clip of the mv (mv_search.c:981) applied to the resident results, and their 8-byte form
-__global__ void k_pack_results(jmb_me_res *__restrict__ res, int n, jmb_frame_params fp, jmb_me_res8 *__restrict__ out) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+// final clip of the mv (mv_search.c:981) applied to the resident results, and their 8-byte form (24-byte records read through
+// shared memory as 16-byte words)
+__global__ void __launch_bounds__(256)
+k_pack_results(jmb_me_res *__restrict__ res, int n, jmb_frame_params fp, jmb_me_res8 *__restrict__ out) {
+  __shared__ __align__(16) jmb_me_res sr[256];
+  static_assert(sizeof(jmb_me_res) == 24, "staging copies 256 x 24 bytes as 384 x 16");
+  const int t0 = blockIdx.x * 256, t = t0 + threadIdx.x, cnt = min(256, n - t0);
+  const uint4 *src = (const uint4 *)(res + t0);
+  for (int i = threadIdx.x; i < cnt * 24 / 16; i += 256) ((uint4 *)sr)[i] = src[i];
+  for (int i = (cnt * 24 / 16) * 16 + threadIdx.x * 8; i < cnt * 24; i += 256 * 8) *(uint2 *)((char *)sr + i) = *(const uint2 *)((const char *)src + i);
+  __syncthreads();
   if (t >= n) return;
-  jmb_me_res r = res[t];
+  const jmb_me_res r = sr[threadIdx.x];
   const int mx = jmb_clip(fp.mv_min_x, fp.mv_max_x, r.mv_x), my = jmb_clip(fp.mv_min_y, fp.mv_max_y, r.mv_y);
   if (mx != r.mv_x || my != r.mv_y) { res[t].mv_x = (int16_t)mx; res[t].mv_y = (int16_t)my; }
   if (out) {
