@@ -381,7 +381,7 @@ def run_ours(args):
     ctx.timing(False)
     ctx.sync()
     tokens_dev = int(wl.d_ntok.item())
-    worst_ms = None
+    worst_ms = worst_refine_ms = None
     if not args.scene_cut and not args.no_worst and not wl.epzs:
         # worst case of the search gate: the reference is an unrelated picture (nothing matches, every bound stays loose)
         f = synth.luma_frames(wl.W, wl.H, 1, seed=999)[0].astype(np.uint8)
@@ -395,6 +395,8 @@ def run_ours(args):
             ctx.me_search_frame_pred(ds["pred"].data_ptr(), wl.fp, wl.d_res8.data_ptr(), api.DEVICE, n_mb=n_mb)
         w_ms, w_n = ctx.timing_get("int_search")
         worst_ms = w_ms / max(1, w_n)
+        r_ms, r_n = ctx.timing_get("subpel_refine")      # nothing matches: every partition ends on its own mv, no sub-block is shared
+        worst_refine_ms = r_ms / max(1, r_n)
         ctx.timing(False)
     if world > 1:
         t = torch.tensor([ms], device=f"cuda:{local}"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
@@ -458,7 +460,7 @@ def run_ours(args):
         out["roofline"] = {"bound": "hbm", "kernel": "k_int_search", "achieved": achieved, "peak": peak, "unit": "GB/s",
                            "frac": achieved / peak, "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
                            "algorithmic_bytes_per_launch": BYTES_PER_MB_REF * n_mb, "launch_ms": launch_ms,
-                           "worst_case_launch_ms": worst_ms,
+                           "worst_case_launch_ms": worst_ms, "worst_case_subpel_refine_ms": worst_refine_ms,
                            "note": "search-window model of SURVEY 8(d): 13804 B per macroblock*reference; the kernel is ALU-pipe "
                                    "(VABSDIFF4/PRMT/ISETP) bound, not HBM bound -- DESIGN.md 3; traffic < algorithmic bytes because "
                                    "neighbouring windows hit L2"}

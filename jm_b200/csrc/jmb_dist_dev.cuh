@@ -12,11 +12,13 @@ __constant__ unsigned char c_bsy[8] = {16, 16, 8, 16, 8, 4, 8, 4};
 
 struct RefView { const uint8_t *planes; size_t plane_bytes; int pitch, w, h; };
 
-// pointer to the sample at quarter-pel position (qx,qy) after UMVLine4X's origin clamp
+// pointer to the sample at quarter-pel position (qx,qy) after UMVLine4X's origin clamp; the 16 planes of a reference span less
+// than 4 GB (jmb_launch_subpel refuses more), so the offset is formed in 32 bits
 __device__ __forceinline__ const uint8_t *umv(const RefView &rv, int qy, int qx) {
-  int iy = jmb_clip(-JMB_PAD_Y, rv.h + JMB_PAD_Y - 1 - 16, qy >> 2);
-  int ix = jmb_clip(-JMB_PAD_X, rv.w + JMB_PAD_X - 1 - 16, qx >> 2);
-  return rv.planes + (size_t)((qy & 3) * 4 + (qx & 3)) * rv.plane_bytes + (size_t)(iy + JMB_PAD_Y) * rv.pitch + (ix + JMB_PAD_X);
+  const int iy = jmb_clip(-JMB_PAD_Y, rv.h + JMB_PAD_Y - 1 - 16, qy >> 2);
+  const int ix = jmb_clip(-JMB_PAD_X, rv.w + JMB_PAD_X - 1 - 16, qx >> 2);
+  const unsigned off = (unsigned)((qy & 3) * 4 + (qx & 3)) * (unsigned)rv.plane_bytes + (unsigned)((iy + JMB_PAD_Y) * rv.pitch + ix + JMB_PAD_X);
+  return rv.planes + off;
 }
 
 __device__ __forceinline__ int hadamard4(const int *d) {   // d[16] row-major
@@ -71,6 +73,23 @@ __device__ __forceinline__ void ld8(const uint8_t *p, unsigned &lo, unsigned &hi
   lo = __byte_perm(w0, w1, sel); hi = __byte_perm(w1, w2, sel);
 }
 
+// The rows of a block inside a reference plane: the pitch is a multiple of 4 (jmb_ref_put rounds it up to 128), so every row
+// has the word alignment of the first one -- one selector, one word stride.
+struct RowsAt { const unsigned *a; unsigned sel; int pw; };
+__device__ __forceinline__ RowsAt rows_at(const uint8_t *p, int pitch) {
+  const unsigned sh = (unsigned)(size_t)p & 3u;
+  return RowsAt{(const unsigned *)(p - sh), 0x3210u + 0x1111u * sh, pitch >> 2};
+}
+__device__ __forceinline__ unsigned row4(const RowsAt &R, int y) {
+  const unsigned *q = R.a + y * R.pw;
+  return __byte_perm(__ldg(q), __ldg(q + 1), R.sel);
+}
+__device__ __forceinline__ void row8(const RowsAt &R, int y, unsigned &lo, unsigned &hi) {
+  const unsigned *q = R.a + y * R.pw;
+  const unsigned w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+  lo = __byte_perm(w0, w1, R.sel); hi = __byte_perm(w1, w2, R.sel);
+}
+
 // One sub-block of the source, kept in registers while the candidates of a refinement stage go by.
 struct SrcBlk { unsigned w[16]; };   // n = 4: w[0..3] = rows; n = 8: w[2y], w[2y+1] = row y
 
@@ -91,10 +110,11 @@ __device__ __forceinline__ void load_src(SrcBlk &s, const uint8_t *cur, int cur_
 // |u + v| + |u - v| = 2 max(|u|, |v|): the maxima add up to half the coefficient sum S, and JM's (S + 2) >> 2 is (M + 1) >> 1.
 __device__ __forceinline__ int hadamard8_packed(const SrcBlk &src, const uint8_t *ref, int pitch) {
   int p[8][4];
+  const RowsAt R = rows_at(ref, pitch);
 #pragma unroll
   for (int y = 0; y < 8; y++) {
     unsigned lo, hi;
-    ld8(ref + (size_t)y * pitch, lo, hi);
+    row8(R, y, lo, hi);
     const int d0 = (int)__byte_perm(src.w[2 * y], 0, 0x4140) - (int)__byte_perm(lo, 0, 0x4140), d1 = (int)__byte_perm(src.w[2 * y], 0, 0x4342) - (int)__byte_perm(lo, 0, 0x4342);
     const int d2 = (int)__byte_perm(src.w[2 * y + 1], 0, 0x4140) - (int)__byte_perm(hi, 0, 0x4140), d3 = (int)__byte_perm(src.w[2 * y + 1], 0, 0x4342) - (int)__byte_perm(hi, 0, 0x4342);
     const int a0 = d0 + d2, a1 = d1 + d3, a2 = d0 - d2, a3 = d1 - d3;
@@ -121,9 +141,10 @@ __device__ __forceinline__ int subblock_dist(const RefView &rv, const SrcBlk &sr
   else ref = umv(rv, cqy, cqx) + (size_t)(sby * n) * rv.pitch + sbx * n;                     // partition clamp
   if (n == 4) {
     int d[16];
+    const RowsAt R = rows_at(ref, rv.pitch);
 #pragma unroll
     for (int y = 0; y < 4; y++) {
-      const unsigned sv = src.w[y], rw = ld4(ref + (size_t)y * rv.pitch);
+      const unsigned sv = src.w[y], rw = row4(R, y);
 #pragma unroll
       for (int x = 0; x < 4; x++) d[y * 4 + x] = (int)((sv >> (8 * x)) & 255) - (int)((rw >> (8 * x)) & 255);
     }
@@ -141,8 +162,9 @@ __device__ __forceinline__ void load_ref4(const RefView &rv, int cqx, int cqy, i
   const uint8_t *ref;
   if (metric == JMB_SATD) ref = umv(rv, cqy + ((sby * 4) << 2), cqx + ((sbx * 4) << 2));   // per-sub-block clamp
   else ref = umv(rv, cqy, cqx) + (size_t)(sby * 4) * rv.pitch + sbx * 4;                     // partition clamp
+  const RowsAt R = rows_at(ref, rv.pitch);
 #pragma unroll
-  for (int y = 0; y < 4; y++) rw[y] = ld4(ref + (size_t)y * rv.pitch);
+  for (int y = 0; y < 4; y++) rw[y] = row4(R, y);
 }
 // HadamardSAD4x4 (me_distortion.c:175-258) on two samples per register: a pair (a, b) is carried as the INTEGER
 // a + 65536 * b, on which adds and subtracts act on both halves at once (no field ever overflows: |values| <= 4080).

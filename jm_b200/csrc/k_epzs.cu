@@ -153,7 +153,8 @@ k_epzs_int(const jmb_epzs_req *__restrict__ reqs, int n, const short2 *__restric
       for (int c = 0; c < nc; c++) {
         const short2 v = q.cand[c];
         const uint8_t *rp = umv(rv, bqy + v.y, bqx + v.x) + boff;      // computeSAD (me_distortion.c:349): the PARTITION origin is clamped
-        unsigned d = (__vsadu4(s0, ld4(rp)) + __vsadu4(s1, ld4(rp + ref_pitch)) + __vsadu4(s2, ld4(rp + 2 * (size_t)ref_pitch)) + __vsadu4(s3, ld4(rp + 3 * (size_t)ref_pitch))) << 5;
+        const RowsAt R = rows_at(rp, ref_pitch);
+        unsigned d = (__vsadu4(s0, row4(R, 0)) + __vsadu4(s1, row4(R, 1)) + __vsadu4(s2, row4(R, 2)) + __vsadu4(s3, row4(R, 3))) << 5;
         if (blk == 0) d += mv_cost32(q.lam, v.x, v.y, q.px, q.py);
         atomicAdd(&tot[lo][c], (int)d);
       }

@@ -28,14 +28,15 @@ constexpr int RT = 128, RQ = 41;
                             // hides them better than in-thread batching: (group, CTAs/SM) (3,4) 0.243 ms, (2,6) 0.194, (2,8) 0.176, (1,8) 0.1745
 #endif
 constexpr int RF_GROUP = JMB_RF_GROUP;
+constexpr int DD_MAX = RT, DD_T = 256;     // one item per thread and chunk; the sub-blocks of one macroblock's 41 searches (112) are one chunk
 
 struct RefineS {
   short pos_x, pos_y, pred_x, pred_y;
   int mvx, mvy;
   long long min_mcost;
   int lam_h, lam_q;
-  unsigned char blocktype, ref, flags, nsub, n, nsx;
-  int first;                  // index of the request's first work item
+  unsigned char blocktype, ref, flags, nsub, n, nsx, nsx_sh;
+  short first;                // index of the request's first work item
 };
 
 #ifndef JMB_RF_MINB
@@ -47,6 +48,10 @@ k_subpel_refine(const jmb_me_req *__restrict__ reqs, jmb_me_res *__restrict__ re
   __shared__ RefineS sr[RQ];
   __shared__ int sums[RQ][9];
   __shared__ int s_total;
+  __shared__ int4 dd_key[DD_MAX];                  // (sub-block position, mv, reference | size | request for SAD/SSE)
+  __shared__ int dd_val[DD_MAX][9];                // distortion of distinct sub-block x candidate
+  __shared__ int dd_table[DD_T], dd_nlead;
+  __shared__ short dd_info[DD_MAX], dd_lead[DD_MAX], dd_slot[DD_MAX], dd_list[DD_MAX];
   const int tid = threadIdx.x, base = blockIdx.x * RQ, cnt = min(RQ, n - base);
   const long long DISTBLK_MAX = (long long)0x7fffffff << 5;     // lencod/inc/defines.h:136
 
@@ -56,7 +61,7 @@ k_subpel_refine(const jmb_me_req *__restrict__ reqs, jmb_me_res *__restrict__ re
     q.pos_x = r.pos_x; q.pos_y = r.pos_y; q.pred_x = r.pred_x; q.pred_y = r.pred_y;
     q.lam_h = r.lambda[1]; q.lam_q = r.lambda[2];
     q.blocktype = r.blocktype; q.ref = r.ref; q.flags = r.flags;
-    q.nsub = 0; q.n = 4; q.nsx = 1; q.first = 0; q.mvx = q.mvy = 0; q.min_mcost = 0;
+    q.nsub = 0; q.n = 4; q.nsx = 1; q.nsx_sh = 0; q.first = 0; q.mvx = q.mvy = 0; q.min_mcost = 0;
     const int bad = jmb_req_check(r, w, h, nref);
     jmb_req_report(err, bad, base + tid);
     if (bad) q.flags = 0;
@@ -82,59 +87,110 @@ k_subpel_refine(const jmb_me_req *__restrict__ reqs, jmb_me_res *__restrict__ re
       q.nsub = 0;
       if (q.flags & JMB_REQ_SUBPEL) {
         const int nn = (metric == JMB_SATD && (q.flags & JMB_REQ_TEST8X8)) ? 8 : 4;
-        q.n = (unsigned char)nn; q.nsx = (unsigned char)(c_bsx[q.blocktype] / nn);
-        q.nsub = (unsigned char)(q.nsx * (c_bsy[q.blocktype] / nn));
+        const int nsx = c_bsx[q.blocktype] / nn;                     // 1, 2 or 4 sub-blocks across
+        q.n = (unsigned char)nn; q.nsx = (unsigned char)nsx; q.nsx_sh = (unsigned char)(nsx >> 1);
+        q.nsub = (unsigned char)(nsx * (c_bsy[q.blocktype] / nn));
+        if (stage == 1 && !me.start_qp) q.min_mcost = DISTBLK_MAX;
       }
     }
     for (int i = tid; i < cnt * 9; i += RT) (&sums[0][0])[i] = 0;
     __syncthreads();
-    if (tid < cnt) {      // exclusive prefix sum of the item counts, one request per thread
-      int first = 0;
-      for (int i = 0; i < tid; i++) first += sr[i].nsub;
-      sr[tid].first = first;
-      if (tid == cnt - 1) s_total = first + sr[tid].nsub;
+    if (tid < 32) {       // exclusive prefix sum of the item counts: warp 0 scans requests tid and tid + 32
+      static_assert(RQ <= 64, "the scan covers two requests per lane");
+      const int n0 = tid < cnt ? sr[tid].nsub : 0, n1 = tid + 32 < cnt ? sr[tid + 32].nsub : 0;
+      int s0 = n0, s1 = n1;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t0 = __shfl_up_sync(0xffffffffu, s0, d), t1 = __shfl_up_sync(0xffffffffu, s1, d);
+        if (tid >= d) { s0 += t0; s1 += t1; }
+      }
+      const int half = __shfl_sync(0xffffffffu, s0, 31);
+      if (tid < cnt) sr[tid].first = s0 - n0;
+      if (tid + 32 < cnt) sr[tid + 32].first = half + s1 - n1;
+      if (tid == 31) s_total = half + s1;
     }
     __syncthreads();
     const int total = s_total;
-    for (int item = tid; item < total; item += RT) {
-      int lo = 0, hi = cnt - 1;                        // last request whose first item is <= item
-      while (lo < hi) { const int m = (lo + hi + 1) >> 1; if (sr[m].first <= item) lo = m; else hi = m - 1; }
-      while (sr[lo].nsub == 0) lo--;                   // skip inactive requests that share the same first index
-      const RefineS &q = sr[lo];
-      const int sb = item - q.first, nn = q.n, sbx = sb % q.nsx, sby = sb / q.nsx;
-      RefView rv{ref_planes[q.ref], plane_bytes, ref_pitch, w, h};
-      SrcBlk src;
-      load_src(src, cur, cur_pitch, q.pos_x + sbx * nn, q.pos_y + sby * nn, nn);
-      const int bqx = (q.pos_x << 2) + q.mvx, bqy = (q.pos_y << 2) + q.mvy;
-      if (nn == 4) {
-        for (int pos = pos0; pos < pos1; pos += RF_GROUP) {       // RF_GROUP candidates' reference rows in flight at a time
-          unsigned rw[RF_GROUP][4];
-#pragma unroll
-          for (int k = 0; k < RF_GROUP; k++)
-            if (pos + k < pos1) load_ref4(rv, bqx + step * c_spiral9[pos + k][0], bqy + step * c_spiral9[pos + k][1], sbx, sby, metric, rw[k]);
-#pragma unroll
-          for (int k = 0; k < RF_GROUP; k++)
-            if (pos + k < pos1) atomicAdd(&sums[lo][pos + k], dist4(src, rw[k], metric));
+    // With SATD every 4x4 / 8x8 sub-block clamps its own origin (me_distortion.c:771,799), so the distortion of a sub-block at a
+    // candidate depends only on where the sub-block lies, the reference and the candidate's ABSOLUTE mv -- not on which partition
+    // it belongs to.  Partitions of one macroblock that left the integer search with the same mv (the common case in coherent
+    // motion) walk the same candidates: their sub-blocks share one evaluation.  (SAD / SSE clamp the partition origin: the
+    // request index joins the key and nothing is shared.)  The items go by in chunks of DD_MAX: a macroblock's 112 are one chunk.
+#pragma unroll 1
+    for (int c0 = 0; c0 < total; c0 += DD_MAX) {
+      const int nit = min(DD_MAX, total - c0);
+      for (int i = tid; i < DD_T; i += RT) dd_table[i] = -1;
+      if (tid == 0) dd_nlead = 0;
+      if (tid < cnt) {                                   // every request names its sub-blocks of this chunk
+        const RefineS &q = sr[tid];
+        const int nn = q.n, tail = q.ref | (nn << 8) | (metric != JMB_SATD ? (tid + 1) << 16 : 0);
+        for (int item = max((int)q.first, c0); item < min(q.first + q.nsub, c0 + DD_MAX); item++) {
+          const int sb = item - q.first, sbx = sb & (q.nsx - 1), sby = sb >> q.nsx_sh;
+          dd_key[item - c0] = make_int4((q.pos_x + sbx * nn) | ((q.pos_y + sby * nn) << 16), q.mvx, q.mvy, tail);
+          dd_info[item - c0] = (short)(tid | (sb << 8));
         }
-      } else {
-        for (int pos = pos0; pos < pos1; pos++)
-          atomicAdd(&sums[lo][pos], subblock_dist(rv, src, bqx + step * c_spiral9[pos][0], bqy + step * c_spiral9[pos][1], sbx, sby, 8, metric));
       }
+      __syncthreads();
+      if (tid < nit) {                                   // open addressing: the first claimant of a key evaluates it
+        const int4 k = dd_key[tid];
+        const unsigned hsh = ((unsigned)k.x * 0x9e3779b1u) ^ ((unsigned)k.y * 0x85ebca6bu) ^ ((unsigned)k.z * 0xc2b2ae35u) ^ ((unsigned)k.w * 0x27d4eb2fu);
+        int slot = (int)(hsh >> 16) & (DD_T - 1), lead;
+        for (;;) {
+          const int o = atomicCAS(&dd_table[slot], -1, tid);
+          if (o == -1) { lead = tid; break; }
+          const int4 ko = dd_key[o];
+          if (ko.x == k.x && ko.y == k.y && ko.z == k.z && ko.w == k.w) { lead = o; break; }
+          slot = (slot + 1) & (DD_T - 1);
+        }
+        dd_lead[tid] = (short)lead;
+        if (lead == tid) { const int idx = atomicAdd(&dd_nlead, 1); dd_list[idx] = (short)tid; dd_slot[tid] = (short)idx; }
+      }
+      __syncthreads();
+      // (distinct sub-block, candidate group) units: the fewer distinct sub-blocks, the finer the split over the threads
+      const int nl = dd_nlead, ncand = pos1 - pos0;
+      int G = ncand;
+      if (nl * ncand <= RT) G = 1; else if (nl * ((ncand + 1) >> 1) <= RT) G = 2; else if (nl * ((ncand + 3) >> 2) <= RT) G = 4;
+      const int groups = ncand > 0 ? (ncand + G - 1) / G : 0;
+      for (int u = tid; u < nl * groups; u += RT) {
+        const int idx = u / groups, g = u - idx * groups, info = dd_info[dd_list[idx]], lo = info & 0xff, sb = info >> 8;
+        const RefineS &q = sr[lo];
+        const int nn = q.n, sbx = sb & (q.nsx - 1), sby = sb >> q.nsx_sh;
+        RefView rv{ref_planes[q.ref], plane_bytes, ref_pitch, w, h};
+        SrcBlk src;
+        load_src(src, cur, cur_pitch, q.pos_x + sbx * nn, q.pos_y + sby * nn, nn);
+        const int bqx = (q.pos_x << 2) + q.mvx, bqy = (q.pos_y << 2) + q.mvy;
+        const int pa = pos0 + g * G, pb = min(pos1, pa + G);
+        if (nn == 4) {
+          for (int pos = pa; pos < pb; pos++) {
+            unsigned rw[4];
+            load_ref4(rv, bqx + step * c_spiral9[pos][0], bqy + step * c_spiral9[pos][1], sbx, sby, metric, rw);
+            dd_val[idx][pos] = dist4(src, rw, metric);
+          }
+        } else {
+          for (int pos = pa; pos < pb; pos++)
+            dd_val[idx][pos] = subblock_dist(rv, src, bqx + step * c_spiral9[pos][0], bqy + step * c_spiral9[pos][1], sbx, sby, 8, metric);
+        }
+      }
+      __syncthreads();
+      if (tid < nit) {
+        const int lo = dd_info[tid] & 0xff, idx = dd_slot[dd_lead[tid]];
+        for (int pos = pos0; pos < pos1; pos++) atomicAdd(&sums[lo][pos], dd_val[idx][pos]);
+      }
+      __syncthreads();
     }
-    __syncthreads();
     if (tid < cnt && (sr[tid].flags & JMB_REQ_SUBPEL)) {
+      // JM's sequential strict-'<' walk (me_fullsearch.c:221-289).  A candidate's cost fits 32 bits (lambda <= 65535 times at most
+      // 130 bits, plus a block distortion < 2^24 shifted by 5); an incumbent beyond that loses to any candidate.
       RefineS &q = sr[tid];
-      if (stage == 1 && !me.start_qp) q.min_mcost = DISTBLK_MAX;
-      const int lam = stage ? q.lam_q : q.lam_h;
-      int best = 0;
+      const unsigned lam = (unsigned)(stage ? q.lam_q : q.lam_h);
+      unsigned cur = q.min_mcost > 0xffffffffll ? 0xffffffffu : (unsigned)q.min_mcost;
+      int best = -1;
       for (int pos = pos0; pos < pos1; pos++) {
         const int cx = q.mvx + step * c_spiral9[pos][0], cy = q.mvy + step * c_spiral9[pos][1];
-        long long mc = (long long)lam * (jmb_mvbits(cx - q.pred_x) + jmb_mvbits(cy - q.pred_y));
-        if (mc >= q.min_mcost) continue;
-        mc += (long long)sums[tid][pos] << 5;
-        if (mc < q.min_mcost) { q.min_mcost = mc; best = pos; }
+        const unsigned mc = lam * (unsigned)(jmb_mvbits(cx - q.pred_x) + jmb_mvbits(cy - q.pred_y)) + ((unsigned)sums[tid][pos] << 5);
+        if (mc < cur) { cur = mc; best = pos; }
       }
-      q.mvx += step * c_spiral9[best][0]; q.mvy += step * c_spiral9[best][1];
+      if (best >= 0) { q.min_mcost = cur; q.mvx += step * c_spiral9[best][0]; q.mvy += step * c_spiral9[best][1]; }
     }
     __syncthreads();
   }

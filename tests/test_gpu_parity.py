@@ -23,18 +23,24 @@ def _frames(w, h, seed, motion=(3, -2), n=2):
     return synth.luma_frames(w, h, n, seed=seed, motion=motion)
 
 
-@pytest.mark.parametrize("w,h,seed", [(96, 64, 1), (176, 144, 2), (16, 16, 3), (400, 48, 4)])
+@pytest.mark.parametrize("w,h,seed", [(96, 64, 1), (176, 144, 2), (16, 16, 3), (400, 48, 4), (208, 128, 5), (1920, 1088, 6)])
 def test_subpel_planes(ctx, oracle, w, h, seed):
     f = _frames(w, h, seed)[0]
     if seed == 3:
         f = np.random.default_rng(3).choice([0, 255], size=(h, w)).astype(np.uint16)   # exercises the clips
-    ctx.ref_put(0, f)
+    if seed == 5:
+        f = np.random.default_rng(5).integers(0, 256, size=(h, w)).astype(np.uint16)   # white noise: every tap sign pattern
     r = oracle.ref_create(f)
     want = oracle.planes(r)
-    for fy in range(4):
-        for fx in range(4):
-            got = ctx.ref_plane(0, fy, fx, (h, w))
-            assert np.array_equal(got, want[fy, fx]), (fy, fx)
+    for upload in ("u16", "u8"):          # JM's imgpel samples and the byte upload take different staging paths
+        if upload == "u16":
+            ctx.ref_put(0, f)
+        else:
+            ctx.ref_put_u8(0, f.astype(np.uint8))
+        for fy in range(4):
+            for fx in range(4):
+                got = ctx.ref_plane(0, fy, fx, (h, w))
+                assert np.array_equal(got, want[fy, fx]), (upload, fy, fx)
     oracle.ref_destroy(r)
 
 
