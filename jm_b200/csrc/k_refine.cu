@@ -10,24 +10,23 @@
 //    candidates around the integer mv, then eight (or nine) quarter-pel candidates around the best
 //    half-pel one; J = lambda * mvbits + (D << 5); the first candidate in spiral order wins ties.
 //
-// One warp per search: the (candidate x sub-block) work items are spread over the 32 lanes, each
-// lane does whole 4x4 (or 8x8) Hadamards in registers, per-candidate sums are combined with
-// shared-memory atomics, lane 0 replays JM's sequential strict-'<' selection.
+// One CTA per 41 consecutive searches (a macroblock in the picture layout).  Work item = one 4x4 (or 8x8) sub-block of one
+// search; items whose distortions cannot differ (same sub-block, same mv, SATD's per-sub-block clamp) are found through a
+// shared-memory hash table and evaluated once, each Hadamard whole in one thread's registers; the values are added up per
+// search and one thread per search replays JM's sequential strict-'<' selection.
 #include "jmb_internal.h"
 #include "jmb_dist_dev.cuh"
 
 namespace {
 
-// Refinement of up to RQ consecutive requests per CTA (one macroblock's 41 searches in the frame layout).
-// Work item = one sub-block of one request; the thread keeps the source sub-block in registers and walks
-// the candidates of the stage, adding its share of every candidate's distortion to sums[request][candidate].
-// One thread per request then replays JM's sequential strict-'<' selection (me_fullsearch.c:221-289).
+// Refinement of up to RQ consecutive requests per CTA (one macroblock's 41 searches in the frame layout).  Per stage
+// (half-pel, quarter-pel): the requests name their sub-blocks, identical ones elect a leader (open addressing, atomicCAS), the
+// distinct (sub-block, candidate group) units are spread over the threads -- the source sub-block in registers, one candidate
+// after the other -- every item then adds its leader's values to sums[request][candidate], and one thread per request replays
+// JM's sequential strict-'<' selection (me_fullsearch.c:221-289).
 constexpr int RT = 128, RQ = 41;
-#ifndef JMB_RF_GROUP
-#define JMB_RF_GROUP 1      // candidates whose reference rows are in flight together; the kernel waits on L2 loads, and occupancy
-                            // hides them better than in-thread batching: (group, CTAs/SM) (3,4) 0.243 ms, (2,6) 0.194, (2,8) 0.176, (1,8) 0.1745
-#endif
-constexpr int RF_GROUP = JMB_RF_GROUP;
+// (round-1 A/B, kept for the record: batching the reference rows of several candidates in one thread lost to occupancy --
+// (candidates in flight, CTAs/SM) (3,4) 0.243 ms, (2,6) 0.194, (2,8) 0.176, (1,8) 0.1745)
 constexpr int DD_MAX = RT, DD_T = 256;     // one item per thread and chunk; the sub-blocks of one macroblock's 41 searches (112) are one chunk
 
 struct RefineS {
@@ -40,8 +39,8 @@ struct RefineS {
 };
 
 #ifndef JMB_RF_MINB
-#define JMB_RF_MINB 8
-#endif
+#define JMB_RF_MINB 10      // CTAs/SM (registers): 6 (80) 0.127 ms, 8 (64) 0.113, 10 (48) 0.106, 12 (40) 0.107 -- the phases are short and
+#endif                      // separated by barriers, so resident CTAs count for more than the 216 bytes of spills at 48 registers
 __global__ void __launch_bounds__(RT, JMB_RF_MINB)
 k_subpel_refine(const jmb_me_req *__restrict__ reqs, jmb_me_res *__restrict__ res, int n, const uint8_t *__restrict__ cur, int cur_pitch,
                 const uint8_t *const *__restrict__ ref_planes, size_t plane_bytes, int ref_pitch, int w, int h, jmb_me_config me, int nref, int *__restrict__ err) {

@@ -202,6 +202,46 @@ def test_subpel_only_requests(ctx, oracle):
     oracle.ref_destroy(r)
 
 
+@pytest.mark.parametrize("case", ["one_mb_same_centre", "duplicates", "six_chunks_of_16x16", "test8x8"])
+def test_subpel_shared_evaluations(ctx, oracle, case):
+    """The refinement evaluates sub-blocks that several searches of a CTA share only once (same position, same mv, SATD): the
+    extremes of that path -- a macroblock whose 41 partitions all stand on one mv, the same search listed several times, a CTA
+    whose 656 items take six chunks with nothing shared, and 8x8 sub-blocks -- against JM search by search."""
+    w, h = 96, 64
+    f = _frames(w, h, 31)
+    ctx.configure(search_range=8); ctx.ref_put(0, f[0]); ctx.pic_begin(f[1], [0])
+    r = oracle.ref_create(f[0])
+    rng = np.random.default_rng(31)
+    shapes = [(bt, bx, by) for bt in range(1, 8) for by in range(0, 16, api.BLOCK_SIZE[bt][1]) for bx in range(0, 16, api.BLOCK_SIZE[bt][0])]
+    assert len(shapes) == 41
+    if case == "six_chunks_of_16x16":
+        reqs = np.zeros(41, api.ME_REQ)
+        for i, q in enumerate(reqs):
+            q["blocktype"] = 1; q["pos_x"] = 16 * (i % 6); q["pos_y"] = 16 * ((i // 6) % 4)
+            q["center_x"], q["center_y"] = 4 * int(rng.integers(-6, 7)), 4 * int(rng.integers(-6, 7))
+    else:
+        reqs = np.zeros(82 if case == "duplicates" else 41, api.ME_REQ)
+        for i, q in enumerate(reqs):
+            bt, bx, by = shapes[i % 41] if case != "duplicates" else shapes[(i // 2) % 41]
+            q["blocktype"] = bt; q["pos_x"] = 32 + bx; q["pos_y"] = 16 + by
+            q["center_x"], q["center_y"] = 12, -8
+    reqs["pred_x"] = rng.integers(-9, 10, len(reqs)); reqs["pred_y"] = rng.integers(-9, 10, len(reqs))
+    reqs["mode"] = api.SEARCH_FULL
+    reqs["flags"] = api.REQ_SUBPEL | api.REQ_SKIP_INT
+    if case == "test8x8":
+        reqs["flags"][reqs["blocktype"] <= 4] |= api.REQ_TEST8X8          # as the picture form does (jm_b200/api.py)
+    reqs["lambda"] = rng.integers(1, 300, (len(reqs), 1))
+    reqs["min_mcost"] = BIG
+    res = ctx.me_search(reqs)
+    for q, o in zip(reqs, res):
+        t8 = 1 if (case == "test8x8" and int(q["blocktype"]) <= 4) else 0
+        mv, c = oracle.sub_pel(r, f[1], int(q["blocktype"]), (int(q["pos_x"]), int(q["pos_y"])), (int(q["pred_x"]), int(q["pred_y"])),
+                               (int(q["center_x"]), int(q["center_y"])), [int(x) for x in q["lambda"]], int(q["min_mcost"]),
+                               po.SATD, po.SATD, 0, 1, t8)
+        assert (int(o["mv_x"]), int(o["mv_y"])) == mv and int(o["cost"]) == c, (case, q)
+    oracle.ref_destroy(r)
+
+
 @pytest.mark.parametrize("metric", [api.SAD, api.SSE, api.SATD])
 def test_dist(ctx, oracle, metric):
     w, h = 96, 64
