@@ -105,6 +105,9 @@ class ClockSampler:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 2.0:      # nvidia-smi needs ~100 ms to deliver its first sample
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
@@ -127,6 +130,9 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         i0, i1 = getattr(self, "i0", 0), getattr(self, "i1", len(self.rows)) + 1      # samples taken DURING the timed region
         rows = self.rows[i0:i1] if i1 > i0 else self.rows
+        nearest = False
+        if not rows and self.rows:      # a timed region shorter than the 20 ms sampling period: the samples on either side of it
+            rows, nearest = self.rows[max(0, i0 - 1):i1 + 1], True
         for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
@@ -135,8 +141,11 @@ class ClockSampler:
                         reasons.add(n)
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm)}
+        if nearest:
+            out["note"] = "timed region shorter than the sampling period: nearest samples"
+        return out
 
 
 class Workload:
