@@ -259,7 +259,8 @@ __global__ void k_mc_tq(const jmb_mb_pred *__restrict__ pred, int n_mb, int mb_w
 // block of one (mode, macroblock); outputs are mode-major.
 // first request of partition mode m in a macroblock's 41 results, and the mode's partition size in 4x4 units
 // (constant memory: as local arrays indexed by the mode they lived on the stack, 24 stores + 3 loads per thread)
-__constant__ int c_mode_base[8] = {0, 0, 1, 3, 5, 9, 17, 25}, c_mode_w4[8] = {4, 4, 4, 2, 2, 2, 1, 1}, c_mode_h4[8] = {4, 4, 2, 4, 2, 1, 2, 1};
+__constant__ int c_mode_base[8] = {0, 0, 1, 3, 5, 9, 17, 25}, c_mode_w4[8] = {4, 4, 4, 2, 2, 2, 1, 1}, c_mode_h4[8] = {4, 4, 2, 4, 2, 1, 2, 1},
+               c_mode_lw4[8] = {2, 2, 2, 1, 1, 1, 0, 0}, c_mode_lh4[8] = {2, 2, 1, 2, 1, 0, 1, 0};      // log2 of the two above
 
 template <int N, int STD>
 __global__ void k_mc_tq_modes(const jmb_me_res *__restrict__ res, int n_mb, int mb_w, unsigned mode_mask, const jmb_quant_desc *__restrict__ qd,
@@ -310,9 +311,17 @@ __global__ void k_mc_tq_modes(const jmb_me_res *__restrict__ res, int n_mb, int 
 // all; the dense kernel spends most of its issue slots waiting for ~50 broadcast LDS of these per thread).
 // Token space is handed out per macroblock: the threads of a macroblock (16 or 4 adjacent lanes) count their nonzero
 // levels, scan the counts with shuffles, the first lane takes the macroblock's range with ONE atomicAdd.
+// bit mask of the scan positions of a block: 32 bits for a 4x4 block, 64 for an 8x8 one
+template <bool WIDE> struct MaskOf { typedef unsigned type; };
+template <> struct MaskOf<true> { typedef unsigned long long type; };
+__device__ __forceinline__ int popc_of(unsigned m) { return __popc(m); }
+__device__ __forceinline__ int popc_of(unsigned long long m) { return __popcll(m); }
+__device__ __forceinline__ int msb_of(unsigned m) { return 31 - __clz(m); }
+__device__ __forceinline__ int msb_of(unsigned long long m) { return 63 - __clzll(m); }
+
 template <int N, int STD>
 __global__ void __launch_bounds__(128)
-k_mc_tq_modes_c(const jmb_me_res *__restrict__ res, int n_mb, int mb_w, unsigned mode_mask, const __grid_constant__ jmb_quant_desc q,
+k_mc_tq_modes_c(const jmb_me_res *__restrict__ res, int n_mb, int mb_w, unsigned mb_w_rcp, unsigned mode_mask, const __grid_constant__ jmb_quant_desc q,
                 const uint8_t *__restrict__ cur, int cur_pitch, const uint8_t *__restrict__ ref_plane0, size_t plane_bytes, int ref_pitch,
                 int w, int h, jmb_tq_head *__restrict__ heads, jmb_tq_token *__restrict__ tokens, unsigned token_cap, unsigned *__restrict__ tok_count) {
   constexpr int PER_MB = (N == 4) ? 16 : 4, NN = N * N;
@@ -321,24 +330,29 @@ k_mc_tq_modes_c(const jmb_me_res *__restrict__ res, int n_mb, int mb_w, unsigned
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = t < n_mb * PER_MB;                       // whole macroblocks are live or dead together
   const int mb = live ? t / PER_MB : 0, b = t % PER_MB;
-  const int mbx = (mb % mb_w) * 16, mby = (mb / mb_w) * 16;
+  const int mbr = (int)__umulhi((unsigned)mb, mb_w_rcp), mbx = (mb - mbr * mb_w) * 16, mby = mbr * 16;      // mb / mb_w by its reciprocal (exact: see the launcher)
   const int bx4 = (N == 4) ? (b & 3) : (b & 1) * 2, by4 = (N == 4) ? (b >> 2) : (b >> 1) * 2;
   const int b8 = (by4 >> 1) * 2 + (bx4 >> 1);
   int ux4 = bx4, uy4 = by4;                                  // prediction unit (macroblock.c:946-971)
   if (mode < 5 || N == 8) { ux4 &= ~1; uy4 &= ~1; }
   if (mode == 1) { ux4 = 0; uy4 = 0; }
-  const jmb_me_res r = res[mb * 41 + c_mode_base[mode] + (uy4 / c_mode_h4[mode]) * (4 / c_mode_w4[mode]) + ux4 / c_mode_w4[mode]];
+  const int lw = c_mode_lw4[mode], lh = c_mode_lh4[mode];     // partitions are 1, 2 or 4 blocks wide / high: shifts, not divisions
+  const jmb_me_res r = res[mb * 41 + c_mode_base[mode] + ((uy4 >> lh) << (2 - lw)) + (ux4 >> lw)];
   const int qx = ((mbx + ux4 * 4) << 2) + r.mv_x, qy = ((mby + uy4 * 4) << 2) + r.mv_y;
   const int iy = jmb_clip(-JMB_PAD_Y, h + JMB_PAD_Y - 1 - 16, qy >> 2), ix = jmb_clip(-JMB_PAD_X, w + JMB_PAD_X - 1 - 16, qx >> 2);
   const uint8_t *rp = ref_plane0 + (size_t)((qy & 3) * 4 + (qx & 3)) * plane_bytes +
                       (size_t)(iy + JMB_PAD_Y + (by4 - uy4) * 4) * ref_pitch + (ix + JMB_PAD_X + (bx4 - ux4) * 4);
   const uint8_t *sp = cur + (size_t)(mby + by4 * 4) * cur_pitch + mbx + bx4 * 4;
   int rr[NN];
+  const unsigned rsh = (unsigned)(size_t)rp & 3u, rsel = 0x3210u + 0x1111u * rsh;      // the pitch is a multiple of 4: one alignment for all rows
+  const unsigned *const ra = (const unsigned *)(rp - rsh);
+  const int rpw = ref_pitch >> 2;
 #pragma unroll
   for (int y = 0; y < N; y++)
 #pragma unroll
     for (int x4 = 0; x4 < N; x4 += 4) {
-      const unsigned sv = *(const unsigned *)(sp + (size_t)y * cur_pitch + x4), pv = tq_ld4(rp + (size_t)y * ref_pitch + x4);
+      const unsigned *const rq = ra + y * rpw + (x4 >> 2);
+      const unsigned sv = *(const unsigned *)(sp + (size_t)y * cur_pitch + x4), pv = __byte_perm(__ldg(rq), __ldg(rq + 1), rsel);
 #pragma unroll
       for (int x = 0; x < 4; x++) rr[y * N + x4 + x] = (int)((sv >> (8 * x)) & 255) - (int)((pv >> (8 * x)) & 255);
     }
@@ -348,34 +362,71 @@ k_mc_tq_modes_c(const jmb_me_res *__restrict__ res, int n_mb, int mb_w, unsigned
   const int qp_per = q.qp / 6, q_bits = (N == 4 ? 15 : 16) + qp_per;
   const bool cavlc8 = (N == 8) && q.is_cavlc;
   const bool clip = (N == 4) ? (q.is_cavlc != 0) : cavlc8;
-  unsigned long long nzm = 0;                                // bit k: scan position k holds a nonzero level
+  // 4x4 blocks, first pass: which scan positions keep a nonzero level -- (|c| * Scale + Offset) >> q_bits != 0 is one multiply-add
+  // and a compare; at the usual quantiser steps nearly all positions drop out here.  Second pass, only for the survivors: the level,
+  // its clip, and JM's coefficient cost with the run since the previous survivor of the same list.
+  typedef typename MaskOf<(NN > 32)>::type mask_t;
+  mask_t nzm = 0;                                            // bit k: scan position k holds a nonzero level
   int lv[NN];
   int cost = 0;
-  {
-    int run[4] = {0, 0, 0, 0};
+  if (N == 4) {
+    const int q_one = 1 << q_bits;
 #pragma unroll
     for (int k = 0; k < NN; k++) {
       int i, j;
       if (STD) { i = (N == 4) ? STD_SCAN4[k][0] : (STD == 2 ? STD_SCAN8_CAVLC[k][0] : STD_SCAN8[k][0]);
                  j = (N == 4) ? STD_SCAN4[k][1] : (STD == 2 ? STD_SCAN8_CAVLC[k][1] : STD_SCAN8[k][1]); }
       else { i = q.scan[k][0]; j = q.scan[k][1]; }
-      const int idx = j * N + i, s = cavlc8 ? (k >> 4) : 0;
-      const int c = STD ? rr[idx] : rr[idx];
-      int level = 0;
-      if (c != 0) {
-        level = (abs(c) * q.qparams[idx][1] + q.qparams[idx][0]) >> q_bits;
-        if (level != 0) {
+      const int idx = j * N + i, c = rr[idx];
+      lv[k] = 0;
+      if (c != 0 && abs(c) * q.qparams[idx][1] + q.qparams[idx][0] >= q_one) nzm |= (mask_t)1 << k;
+    }
+    if (nzm) {
+#pragma unroll
+      for (int k = 0; k < NN; k++) {
+        if ((nzm >> k) & 1) {
+          int i, j;
+          if (STD) { i = (N == 4) ? STD_SCAN4[k][0] : (STD == 2 ? STD_SCAN8_CAVLC[k][0] : STD_SCAN8[k][0]);
+                     j = (N == 4) ? STD_SCAN4[k][1] : (STD == 2 ? STD_SCAN8_CAVLC[k][1] : STD_SCAN8[k][1]); }
+          else { i = q.scan[k][0]; j = q.scan[k][1]; }
+          const int idx = j * N + i, c = rr[idx];
+          int level = (abs(c) * q.qparams[idx][1] + q.qparams[idx][0]) >> q_bits;
           if (clip) level = min(level, 2063);
-          cost += (level > 1) ? 999999 : q.c_cost[run[s]];
-          if (c < 0) level = -level;
-          nzm |= 1ull << k;
+          const int k0 = cavlc8 ? (k & ~15) : 0;
+          const mask_t before = nzm & (((mask_t)1 << k) - 1) & ~(((mask_t)1 << k0) - 1);      // earlier nonzero levels of the same list
+          const int run = before ? (k - 1 - msb_of(before)) : (k - k0);
+          cost += (level > 1) ? 999999 : q.c_cost[run];
+          lv[k] = c < 0 ? -level : level;
         }
       }
-      lv[k] = level;
-      if (level != 0) run[s] = 0; else run[s]++;
+    }
+  } else {      // 8x8: one pass, levels as they come -- with 64 positions and 64-bit masks the two-pass form is slower (0.071 -> 0.082 ms at 4K)
+    {
+      int run[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int k = 0; k < NN; k++) {
+        int i, j;
+        if (STD) { i = (N == 4) ? STD_SCAN4[k][0] : (STD == 2 ? STD_SCAN8_CAVLC[k][0] : STD_SCAN8[k][0]);
+                   j = (N == 4) ? STD_SCAN4[k][1] : (STD == 2 ? STD_SCAN8_CAVLC[k][1] : STD_SCAN8[k][1]); }
+        else { i = q.scan[k][0]; j = q.scan[k][1]; }
+        const int idx = j * N + i, s = cavlc8 ? (k >> 4) : 0;
+        const int c = STD ? rr[idx] : rr[idx];
+        int level = 0;
+        if (c != 0) {
+          level = (abs(c) * q.qparams[idx][1] + q.qparams[idx][0]) >> q_bits;
+          if (level != 0) {
+            if (clip) level = min(level, 2063);
+            cost += (level > 1) ? 999999 : q.c_cost[run[s]];
+            if (c < 0) level = -level;
+            nzm |= (mask_t)1 << k;
+          }
+        }
+        lv[k] = level;
+        if (level != 0) run[s] = 0; else run[s]++;
+      }
     }
   }
-  const int cnt = __popcll(nzm);
+  const int cnt = popc_of(nzm);
   // macroblock-wide exchange: cost per quadrant, coded-block bits, token range
   int c8 = cost;
   if (N == 4) { c8 += __shfl_xor_sync(0xffffffffu, c8, 1); c8 += __shfl_xor_sync(0xffffffffu, c8, 4); }
@@ -410,12 +461,12 @@ k_mc_tq_modes_c(const jmb_me_res *__restrict__ res, int n_mb, int mb_w, unsigned
     for (int k = 0; k < NN; k++) {
       if ((nzm >> k) & 1) {
         const int s = cavlc8 ? (k >> 4) : 0, k0 = cavlc8 ? (k & ~15) : 0;
-        const unsigned long long before = nzm & ((1ull << k) - 1) & ~((1ull << k0) - 1);     // earlier nonzero levels of the same list
-        const int run = before ? (k - 1 - (63 - __clzll(before))) : (k - k0);
+        const mask_t before = nzm & (((mask_t)1 << k) - 1) & ~(((mask_t)1 << k0) - 1);     // earlier nonzero levels of the same list
+        const int run = before ? (k - 1 - msb_of(before)) : (k - k0);
         jmb_tq_token tk;
         tk.level = (int16_t)lv[k]; tk.run = (uint8_t)run;
         tk.blk = (uint8_t)((N == 4) ? b : (cavlc8 ? b8 * 4 + s : b8));
-        o[__popcll(nzm & ((1ull << k) - 1))] = tk;
+        o[popc_of(nzm & (((mask_t)1 << k) - 1))] = tk;
       }
     }
   }
@@ -1078,7 +1129,10 @@ int jmb_mc_tq_modes_compact(jmb_ctx *ctx, const jmb_me_res *res, int n_mb, unsig
   for (int m = 0; m < 7; m++)      // modes outside the mask: empty heads
     if (!((mode_mask >> m) & 1)) JMB_CUDA(ctx, cudaMemsetAsync(d_heads + (size_t)m * n_mb, 0, (size_t)n_mb * sizeof(jmb_tq_head), ctx->stream));
   jmb_time_begin(ctx, JMB_K_MC_TQ);
-#define JMB_MTQC(NN, STD, GRID) k_mc_tq_modes_c<NN, STD><<<GRID, 128, 0, ctx->stream>>>(d_res, n_mb, mb_w, mode_mask, *q, ctx->cur, ctx->cur_pitch, \
+  // mb / mb_w inside the kernel is a multiply by ceil(2^32 / mb_w): exact while n_mb * mb_w < 2^32 (an 8K picture: 2^26)
+  if ((unsigned long long)n_mb * (unsigned long long)mb_w >= (1ull << 32)) return jmb_fail(ctx, JMB_ERR_UNSUPPORTED, "jmb_mc_tq_modes_compact: %d macroblocks in rows of %d", n_mb, mb_w);
+  const unsigned mb_w_rcp = (unsigned)(((1ull << 32) + (unsigned)mb_w - 1) / (unsigned)mb_w);
+#define JMB_MTQC(NN, STD, GRID) k_mc_tq_modes_c<NN, STD><<<GRID, 128, 0, ctx->stream>>>(d_res, n_mb, mb_w, mb_w_rcp, mode_mask, *q, ctx->cur, ctx->cur_pitch, \
         r0.planes, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_heads, d_tok, token_cap, d_cnt)
   {
     const int kind = std_scan_kind(q);
