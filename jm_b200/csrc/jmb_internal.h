@@ -70,6 +70,10 @@ struct jmb_ctx {
   void *d_heads = nullptr; size_t d_heads_cap = 0;
   void *d_tokens = nullptr; size_t d_tokens_cap = 0;
   unsigned *d_tok_count = nullptr; unsigned *h_tok_count = nullptr;
+  // picture form in flight (jmb_me_search_frame_pred): what the search / refinement kernels form their requests from, and where
+  // the refinement kernel leaves the 8-byte results (k_search.cu sets them around its launches)
+  const jmb_mb_mvpred *gen_pred = nullptr; jmb_frame_params gen_fp; int gen_R = 0, gen_mb_w = 0;
+  jmb_me_res8 *pack_out = nullptr; bool pack_on = false;
   // deblocking: ticket counter + per-macroblock completion flags (k_deblock), stamped with db_serial
   void *d_db = nullptr; size_t d_db_cap = 0; int db_serial = 0;
   // peer buffers opened with jmb_peer_open (cudaIpcOpenMemHandle is expensive: one mapping per handle)
@@ -142,6 +146,42 @@ __device__ __forceinline__ int jmb_req_check(const jmb_me_req &r, int w, int h, 
 }
 __device__ __forceinline__ void jmb_req_report(int *err, int code, int index) {
   if (code) { atomicOr(&err[0], code); err[1] = index; }
+}
+
+// ---- picture form: the requests of jmb_me_search_frame_pred are never written to memory ------------------------------------
+// The search and refinement kernels form the request of (macroblock, partition in canonical order) from the predictor
+// table and the slice's parameters where they would read it; gen.pred == nullptr means "requests come from memory".
+struct jmb_frame_gen { const jmb_mb_mvpred *pred; jmb_frame_params fp; int R, mb_w; };
+// The refinement kernel's last step for the picture form: final clip of the mv (mv_search.c:981) and the 8-byte results.
+struct jmb_pack_out { jmb_me_res8 *out; int on; };
+
+__device__ __forceinline__ jmb_me_req jmb_frame_request(const jmb_frame_gen &g, int mb, int p) {      // partition p (0..40) of macroblock mb
+  // canonical partition order: by type, then raster order of the partitions inside the macroblock
+  const int type = p < 1 ? 1 : p < 3 ? 2 : p < 5 ? 3 : p < 9 ? 4 : p < 17 ? 5 : p < 25 ? 6 : 7;
+  const int first = type == 1 ? 0 : type == 2 ? 1 : type == 3 ? 3 : type == 4 ? 5 : type == 5 ? 9 : type == 6 ? 17 : 25;
+  const int lx = (type <= 2) ? 0 : (type <= 5 ? 1 : 2);      // 1, 2 or 4 partitions across: 16, 8 or 4 samples wide
+  const int bsy = (type == 1 || type == 3) ? 16 : ((type == 2 || type == 4 || type == 6) ? 8 : 4);
+  const int k = p - first, row = k >> lx, col = k & ((1 << lx) - 1);
+  const int mby = mb / g.mb_w, mbx = mb - mby * g.mb_w;
+  const jmb_frame_params &fp = g.fp;
+  const int px = g.pred[mb].pred[p][0], py = g.pred[mb].pred[p][1];
+  jmb_me_req q;
+  q.pos_x = (int16_t)(mbx * 16 + col * (16 >> lx)); q.pos_y = (int16_t)(mby * 16 + row * bsy);
+  q.pred_x = (int16_t)px; q.pred_y = (int16_t)py;
+  if (fp.mode == JMB_SEARCH_FAST_FULL) {      // one centre per macroblock: the rounded 16x16 predictor (me_fullfast.c:309-327)
+    const int bx = g.pred[mb].pred[0][0], by = g.pred[mb].pred[0][1];
+    q.center_x = (int16_t)jmb_clip(fp.mv_min_x + 4 * g.R, fp.mv_max_x - 4 * g.R, ((bx + 2) >> 2) * 4);
+    q.center_y = (int16_t)jmb_clip(fp.mv_min_y + 4 * g.R, fp.mv_max_y - 4 * g.R, ((by + 2) >> 2) * 4);
+  } else {                                    // mv_search.c:931-932, clip_mv_range :957
+    q.center_x = (int16_t)jmb_clip(fp.mv_min_x, fp.mv_max_x, ((px + 2) >> 2) * 4);
+    q.center_y = (int16_t)jmb_clip(fp.mv_min_y, fp.mv_max_y, ((py + 2) >> 2) * 4);
+  }
+  q.blocktype = (uint8_t)type; q.ref = (uint8_t)fp.ref; q.mode = (uint8_t)fp.mode;
+  q.flags = (uint8_t)(fp.flags & (JMB_REQ_SUBPEL | (type <= 4 ? JMB_REQ_TEST8X8 : 0)));
+  q.lambda[0] = fp.lambda[0]; q.lambda[1] = fp.lambda[1]; q.lambda[2] = fp.lambda[2];
+  q.reserved_ = 0;
+  q.min_mcost = (int64_t)0x7fffffff << 5;      // DISTBLK_MAX, lencod/inc/defines.h:136
+  return q;
 }
 
 // kernels (defined in k_*.cu), launched through these host wrappers

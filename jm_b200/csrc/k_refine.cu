@@ -25,6 +25,7 @@ namespace {
 // after the other -- every item then adds its leader's values to sums[request][candidate], and one thread per request replays
 // JM's sequential strict-'<' selection (me_fullsearch.c:221-289).
 constexpr int RT = 128, RQ = 41;
+static_assert(RQ == 41, "the picture form takes CTA b for macroblock b and thread t for its partition t");
 // (round-1 A/B, kept for the record: batching the reference rows of several candidates in one thread lost to occupancy --
 // (candidates in flight, CTAs/SM) (3,4) 0.243 ms, (2,6) 0.194, (2,8) 0.176, (1,8) 0.1745)
 constexpr int DD_MAX = RT, DD_T = 256;     // one item per thread and chunk; the sub-blocks of one macroblock's 41 searches (112) are one chunk
@@ -43,7 +44,8 @@ struct RefineS {
 #endif                      // separated by barriers, so resident CTAs count for more than the 216 bytes of spills at 48 registers
 __global__ void __launch_bounds__(RT, JMB_RF_MINB)
 k_subpel_refine(const jmb_me_req *__restrict__ reqs, jmb_me_res *__restrict__ res, int n, const uint8_t *__restrict__ cur, int cur_pitch,
-                const uint8_t *const *__restrict__ ref_planes, size_t plane_bytes, int ref_pitch, int w, int h, jmb_me_config me, int nref, int *__restrict__ err) {
+                const uint8_t *const *__restrict__ ref_planes, size_t plane_bytes, int ref_pitch, int w, int h, jmb_me_config me, int nref, int *__restrict__ err,
+                const jmb_frame_gen gen, const jmb_pack_out pack) {
   __shared__ RefineS sr[RQ];
   __shared__ int sums[RQ][9];
   __shared__ int s_total;
@@ -55,7 +57,7 @@ k_subpel_refine(const jmb_me_req *__restrict__ reqs, jmb_me_res *__restrict__ re
   const long long DISTBLK_MAX = (long long)0x7fffffff << 5;     // lencod/inc/defines.h:136
 
   if (tid < cnt) {
-    const jmb_me_req r = reqs[base + tid];
+    const jmb_me_req r = gen.pred ? jmb_frame_request(gen, blockIdx.x, tid) : reqs[base + tid];      // picture form: CTA = macroblock (RQ = 41)
     RefineS q;
     q.pos_x = r.pos_x; q.pos_y = r.pos_y; q.pred_x = r.pred_x; q.pred_y = r.pred_y;
     q.lam_h = r.lambda[1]; q.lam_q = r.lambda[2];
@@ -193,8 +195,20 @@ k_subpel_refine(const jmb_me_req *__restrict__ reqs, jmb_me_res *__restrict__ re
     }
     __syncthreads();
   }
-  if (tid < cnt && (sr[tid].flags & JMB_REQ_SUBPEL)) {
-    res[base + tid].mv_x = (int16_t)sr[tid].mvx; res[base + tid].mv_y = (int16_t)sr[tid].mvy; res[base + tid].cost = sr[tid].min_mcost;
+  if (tid < cnt) {
+    jmb_me_res *const o = res + base + tid;
+    int mvx, mvy; long long cost;
+    if (sr[tid].flags & JMB_REQ_SUBPEL) { mvx = sr[tid].mvx; mvy = sr[tid].mvy; cost = sr[tid].min_mcost; o->cost = cost; }
+    else { if (!pack.on) return; mvx = o->mv_x; mvy = o->mv_y; cost = o->cost; }      // not refined: the integer stage's answer stands
+    if (pack.on) {      // picture form: the final clip of the mv (mv_search.c:981) and the 8-byte result, as k_pack_results does
+      mvx = jmb_clip(gen.fp.mv_min_x, gen.fp.mv_max_x, mvx); mvy = jmb_clip(gen.fp.mv_min_y, gen.fp.mv_max_y, mvy);
+      if (pack.out) {
+        jmb_me_res8 o8;
+        o8.mv_x = (int16_t)mvx; o8.mv_y = (int16_t)mvy; o8.cost = cost > 0x7fffffffLL ? 0x7fffffff : (int32_t)cost;
+        pack.out[base + tid] = o8;
+      }
+    }
+    o->mv_x = (int16_t)mvx; o->mv_y = (int16_t)mvy;
   }
 }
 
@@ -305,8 +319,11 @@ __global__ void k_block_dist(const int16_t *__restrict__ diff, int nblk, int n, 
 int jmb_launch_refine(jmb_ctx *ctx, const jmb_me_req *d_reqs, jmb_me_res *d_res, int n, const uint8_t *const *d_ref_planes) {
   const jmb_ref &r0 = ctx->refs[ctx->ref_list[0]];
   jmb_time_begin(ctx, JMB_K_REFINE);
+  jmb_frame_gen gen; memset(&gen, 0, sizeof(gen));
+  if (ctx->gen_pred) { gen.pred = ctx->gen_pred; gen.fp = ctx->gen_fp; gen.R = ctx->gen_R; gen.mb_w = ctx->gen_mb_w; }
+  jmb_pack_out pack; pack.out = ctx->pack_out; pack.on = ctx->pack_on ? 1 : 0;
   k_subpel_refine<<<(n + RQ - 1) / RQ, RT, 0, ctx->stream>>>(d_reqs, d_res, n, ctx->cur, ctx->cur_pitch, d_ref_planes, r0.plane_bytes,
-                                                        r0.pitch, ctx->cur_w, ctx->cur_h, ctx->me, ctx->nref, ctx->d_err);
+                                                        r0.pitch, ctx->cur_w, ctx->cur_h, ctx->me, ctx->nref, ctx->d_err, gen, pack);
   jmb_time_end(ctx, JMB_K_REFINE);
   JMB_LAUNCH_CHECK(ctx);
   return JMB_OK;

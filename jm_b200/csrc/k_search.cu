@@ -304,7 +304,8 @@ __device__ __forceinline__ void sad_item(const uint8_t *win, const unsigned *ssr
 #endif
 __global__ void __launch_bounds__(NT, JMB_IS_MINB)
 k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups, jmb_me_res *__restrict__ res,
-             const __grid_constant__ TMaps tm, int w, int h, int R, int max_mvd_m1, int nref, int fpel_metric, int *__restrict__ err) {
+             const __grid_constant__ TMaps tm, int w, int h, int R, int max_mvd_m1, int nref, int fpel_metric, int *__restrict__ err,
+             const jmb_frame_gen gen) {
   __shared__ Grp G;
   __shared__ __align__(128) uint8_t win[WIN_ROWS * WIN_PITCH];   // TMA destination: the search window tile
   __shared__ __align__(128) unsigned ssrc[16 * 4];               // TMA destination: the 16x16 source macroblock
@@ -335,9 +336,9 @@ k_int_search(const jmb_me_req *__restrict__ reqs, const int *__restrict__ groups
     int ri = groups ? groups[g * NPART + tid] : g * NPART + tid;
     ReqS q; q.active = 0; q.req = ri;
     if (ri >= 0) {
-      jmb_me_req r = reqs[ri];
+      jmb_me_req r = gen.pred ? jmb_frame_request(gen, g, tid) : reqs[ri];      // picture form: formed here, never in memory
       int bad = jmb_req_check(r, w, h, nref);
-      if (!bad && !groups) {      // frame layout: request k of a group must be partition k of one macroblock and reference
+      if (!bad && !groups && !gen.pred) {      // frame layout: request k of a group must be partition k of one macroblock and reference
         const PartGeom pg = c_part[tid];
         const jmb_me_req r0 = reqs[g * NPART];
         if (r.blocktype != pg.type || (r.pos_x & 15) != pg.bx * 4 || (r.pos_y & 15) != pg.by * 4 || ((r.pos_x ^ r0.pos_x) & ~15) ||
@@ -1016,8 +1017,10 @@ static int me_search_launch(jmb_ctx *ctx, const jmb_me_req *d_reqs, const int *d
   memset(&tm, 0, sizeof(tm));
   tm.cur = ctx->tmap_cur;
   for (int i = 0; i < ctx->nref; i++) tm.ref[i] = ctx->refs[ctx->ref_list[i]].tmap_int;
+  jmb_frame_gen gen; memset(&gen, 0, sizeof(gen));
+  if (ctx->gen_pred) { gen.pred = ctx->gen_pred; gen.fp = ctx->gen_fp; gen.R = ctx->gen_R; gen.mb_w = ctx->gen_mb_w; }
   k_int_search<<<n_groups, NT, INT_SEARCH_DYN_SMEM + JMB_IS_SMEM_PAD, ctx->stream>>>(d_reqs, d_groups, d_res, tm, ctx->cur_w, ctx->cur_h, ctx->me.search_range,
-                                                                  ctx->me.max_mvd - 1, ctx->nref, ctx->me.metric[0], ctx->d_err);
+                                                                  ctx->me.max_mvd - 1, ctx->nref, ctx->me.metric[0], ctx->d_err, gen);
   jmb_time_end(ctx, JMB_K_INT_SEARCH);
   JMB_LAUNCH_CHECK(ctx);
   if (any_subpel) { int rc = jmb_launch_refine(ctx, d_reqs, d_res, n, d_tab); if (rc) return rc; }
@@ -1096,40 +1099,6 @@ namespace {
 // Requests of a whole picture from the 41 predictors of every macroblock (jmb_me_search_frame_pred): block geometry from the
 // partition index, search centre and flags by the rules of BlockMotionSearch / setup_fast_full_search.
 // (40-byte records: a block of 256 stages them in shared memory and writes 16-byte words, 640 per block, fully coalesced)
-__global__ void __launch_bounds__(256)
-k_gen_requests(const jmb_mb_mvpred *__restrict__ pred, int n_mb, int mb_w, jmb_frame_params fp, int R, jmb_me_req *__restrict__ reqs) {
-  __shared__ __align__(16) jmb_me_req sq[256];
-  static_assert(sizeof(jmb_me_req) == 40, "staging copies 256 x 40 bytes as 640 x 16");
-  const int t0 = blockIdx.x * 256, t = t0 + threadIdx.x, n = n_mb * NPART;
-  if (t < n) {
-    const int mb = t / NPART, p = t - mb * NPART;
-    const PartGeom pg = c_part[p];
-    const int px = pred[mb].pred[p][0], py = pred[mb].pred[p][1];
-    jmb_me_req q;
-    q.pos_x = (int16_t)((mb % mb_w) * 16 + pg.bx * 4); q.pos_y = (int16_t)((mb / mb_w) * 16 + pg.by * 4);
-    q.pred_x = (int16_t)px; q.pred_y = (int16_t)py;
-    if (fp.mode == JMB_SEARCH_FAST_FULL) {      // one centre per macroblock: the rounded 16x16 predictor (me_fullfast.c:309-327)
-      const int bx = pred[mb].pred[0][0], by = pred[mb].pred[0][1];
-      q.center_x = (int16_t)jmb_clip(fp.mv_min_x + 4 * R, fp.mv_max_x - 4 * R, ((bx + 2) >> 2) * 4);
-      q.center_y = (int16_t)jmb_clip(fp.mv_min_y + 4 * R, fp.mv_max_y - 4 * R, ((by + 2) >> 2) * 4);
-    } else {                                    // mv_search.c:931-932, clip_mv_range :957
-      q.center_x = (int16_t)jmb_clip(fp.mv_min_x, fp.mv_max_x, ((px + 2) >> 2) * 4);
-      q.center_y = (int16_t)jmb_clip(fp.mv_min_y, fp.mv_max_y, ((py + 2) >> 2) * 4);
-    }
-    q.blocktype = pg.type; q.ref = (uint8_t)fp.ref; q.mode = (uint8_t)fp.mode;
-    q.flags = (uint8_t)(fp.flags & (JMB_REQ_SUBPEL | (pg.type <= 4 ? JMB_REQ_TEST8X8 : 0)));
-    q.lambda[0] = fp.lambda[0]; q.lambda[1] = fp.lambda[1]; q.lambda[2] = fp.lambda[2];
-    q.reserved_ = 0;
-    q.min_mcost = (int64_t)0x7fffffff << 5;      // DISTBLK_MAX, lencod/inc/defines.h:136
-    sq[threadIdx.x] = q;
-  }
-  __syncthreads();
-  const int cnt = min(256, n - t0);      // records of this block; 256 * 40 bytes start on a 16-byte boundary
-  uint4 *dst = (uint4 *)(reqs + t0);
-  for (int i = threadIdx.x; i < cnt * 40 / 16; i += 256) dst[i] = ((const uint4 *)sq)[i];
-  for (int i = (cnt * 40 / 16) * 16 + threadIdx.x * 8; i < cnt * 40; i += 256 * 8) *(uint2 *)((char *)dst + i) = *(const uint2 *)((const char *)sq + i);
-}
-
 // final clip of the mv (mv_search.c:981) applied to the resident results, and their 8-byte form (24-byte records read through
 // shared memory as 16-byte words)
 __global__ void __launch_bounds__(256)
@@ -1189,25 +1158,29 @@ int jmb_me_search_frame_pred(jmb_ctx *ctx, const jmb_mb_mvpred *pred, int n_mb, 
     JMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_mvpred, pred, (size_t)n_mb * sizeof(jmb_mb_mvpred), cudaMemcpyHostToDevice, ctx->stream));
     d_pred = (const jmb_mb_mvpred *)ctx->d_mvpred;
   }
-  rc = jmb_reserve_dev(ctx, &ctx->d_stage, &ctx->d_stage_cap, (size_t)n * sizeof(jmb_me_req)); if (rc) return rc;
   rc = jmb_reserve_dev(ctx, &ctx->d_res_keep, &ctx->d_res_keep_cap, (size_t)n * sizeof(jmb_me_res)); if (rc) return rc;
   const uint8_t *const *d_tab = nullptr;
   rc = upload_ref_table(ctx, &d_tab, 0); if (rc) return rc;
-  jmb_me_req *d_reqs = (jmb_me_req *)ctx->d_stage; jmb_me_res *d_res = (jmb_me_res *)ctx->d_res_keep;
-  jmb_time_begin(ctx, JMB_K_GEN);
-  k_gen_requests<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_pred, n_mb, mb_w, *fp, R, d_reqs);
-  jmb_time_end(ctx, JMB_K_GEN);
-  JMB_LAUNCH_CHECK(ctx);
-  rc = me_search_launch(ctx, d_reqs, nullptr, n_mb, n, d_res, (fp->flags & JMB_REQ_SUBPEL) != 0, d_tab); if (rc) return rc;
+  jmb_me_res *d_res = (jmb_me_res *)ctx->d_res_keep;
   jmb_me_res8 *d_out = res;
   if (host && res) {
     rc = jmb_reserve_dev(ctx, &ctx->d_res8, &ctx->d_res8_cap, (size_t)n * sizeof(jmb_me_res8)); if (rc) return rc;
     d_out = (jmb_me_res8 *)ctx->d_res8;
   }
-  jmb_time_begin(ctx, JMB_K_GEN);
-  k_pack_results<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_res, n, *fp, d_out);
-  jmb_time_end(ctx, JMB_K_GEN);
-  JMB_LAUNCH_CHECK(ctx);
+  // The 41 requests of a macroblock are formed inside the kernels from its predictor record (jmb_frame_request): no request
+  // array, no generator launch.  With the sub-pel stage on, its kernel also clips the final mv and writes the 8-byte results.
+  const bool subpel = (fp->flags & JMB_REQ_SUBPEL) != 0;
+  ctx->gen_pred = d_pred; ctx->gen_fp = *fp; ctx->gen_R = R; ctx->gen_mb_w = mb_w;
+  ctx->pack_on = subpel; ctx->pack_out = d_out;
+  rc = me_search_launch(ctx, nullptr, nullptr, n_mb, n, d_res, subpel, d_tab);
+  ctx->gen_pred = nullptr; ctx->pack_on = false; ctx->pack_out = nullptr;
+  if (rc) return rc;
+  if (!subpel) {
+    jmb_time_begin(ctx, JMB_K_GEN);
+    k_pack_results<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_res, n, *fp, d_out);
+    jmb_time_end(ctx, JMB_K_GEN);
+    JMB_LAUNCH_CHECK(ctx);
+  }
   if (host) {
     if (res) JMB_CUDA(ctx, cudaMemcpyAsync(res, d_out, (size_t)n * sizeof(jmb_me_res8), cudaMemcpyDeviceToHost, ctx->stream));
     if (loc == JMB_HOST) return jmb_check_device_errors(ctx);

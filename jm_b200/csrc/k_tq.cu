@@ -311,6 +311,9 @@ __global__ void k_mc_tq_modes(const jmb_me_res *__restrict__ res, int n_mb, int 
 // all; the dense kernel spends most of its issue slots waiting for ~50 broadcast LDS of these per thread).
 // Token space is handed out per macroblock: the threads of a macroblock (16 or 4 adjacent lanes) count their nonzero
 // levels, scan the counts with shuffles, the first lane takes the macroblock's range with ONE atomicAdd.
+// per position of a 4x4 block the smallest |coefficient| that quantises to a nonzero level (tq_thresholds)
+struct TqThr { int ok; int t[16]; };
+
 // bit mask of the scan positions of a block: 32 bits for a 4x4 block, 64 for an 8x8 one
 template <bool WIDE> struct MaskOf { typedef unsigned type; };
 template <> struct MaskOf<true> { typedef unsigned long long type; };
@@ -322,6 +325,7 @@ __device__ __forceinline__ int msb_of(unsigned long long m) { return 63 - __clzl
 template <int N, int STD>
 __global__ void __launch_bounds__(128)
 k_mc_tq_modes_c(const jmb_me_res *__restrict__ res, int n_mb, int mb_w, unsigned mb_w_rcp, unsigned mode_mask, const __grid_constant__ jmb_quant_desc q,
+                const __grid_constant__ TqThr thr,
                 const uint8_t *__restrict__ cur, int cur_pitch, const uint8_t *__restrict__ ref_plane0, size_t plane_bytes, int ref_pitch,
                 int w, int h, jmb_tq_head *__restrict__ heads, jmb_tq_token *__restrict__ tokens, unsigned token_cap, unsigned *__restrict__ tok_count) {
   constexpr int PER_MB = (N == 4) ? 16 : 4, NN = N * N;
@@ -369,17 +373,24 @@ k_mc_tq_modes_c(const jmb_me_res *__restrict__ res, int n_mb, int mb_w, unsigned
   mask_t nzm = 0;                                            // bit k: scan position k holds a nonzero level
   int lv[NN];
   int cost = 0;
-  if (N == 4) {
+  if constexpr (N == 4) {
+    // thr.t[idx] = the smallest |c| >= 1 whose level is not 0 (worked out on the host); the multiply-add form for descriptors
+    // whose parameters leave the range where that is the same thing
     const int q_one = 1 << q_bits;
+    if (thr.ok) {
 #pragma unroll
-    for (int k = 0; k < NN; k++) {
-      int i, j;
-      if (STD) { i = (N == 4) ? STD_SCAN4[k][0] : (STD == 2 ? STD_SCAN8_CAVLC[k][0] : STD_SCAN8[k][0]);
-                 j = (N == 4) ? STD_SCAN4[k][1] : (STD == 2 ? STD_SCAN8_CAVLC[k][1] : STD_SCAN8[k][1]); }
-      else { i = q.scan[k][0]; j = q.scan[k][1]; }
-      const int idx = j * N + i, c = rr[idx];
-      lv[k] = 0;
-      if (c != 0 && abs(c) * q.qparams[idx][1] + q.qparams[idx][0] >= q_one) nzm |= (mask_t)1 << k;
+      for (int k = 0; k < NN; k++) {
+        const int idx = STD ? STD_SCAN4[k][1] * N + STD_SCAN4[k][0] : q.scan[k][1] * N + q.scan[k][0];
+        lv[k] = 0;
+        if (abs(rr[idx]) >= thr.t[idx]) nzm |= (mask_t)1 << k;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < NN; k++) {
+        const int idx = STD ? STD_SCAN4[k][1] * N + STD_SCAN4[k][0] : q.scan[k][1] * N + q.scan[k][0], c = rr[idx];
+        lv[k] = 0;
+        if (c != 0 && abs(c) * q.qparams[idx][1] + q.qparams[idx][0] >= q_one) nzm |= (mask_t)1 << k;
+      }
     }
     if (nzm) {
 #pragma unroll
@@ -679,6 +690,28 @@ static int check_qdesc(jmb_ctx *ctx, const jmb_quant_desc *q) {
 
 // 1 / 2 when the descriptor's scan is the standard zig-zag / the standard 8x8 CAVLC interleave (compile-time scan
 // kernels), else 0 (table-driven kernels)
+// level = (|c| * Scale + Offset) >> q_bits is nonzero from some |c| on: that |c| per position of a 4x4 block.  Only claimed (ok)
+// where the kernel's 32-bit arithmetic is exact for every coefficient a 4x4 residual can produce (|c| <= 255 * 36).
+static TqThr tq_thresholds(const jmb_quant_desc *q) {
+  TqThr o;
+  memset(&o, 0, sizeof(o));
+  if (q->n != 4) return o;
+  const int q_bits = 15 + q->qp / 6;
+  if (q_bits < 0 || q_bits > 30) return o;
+  const long long one = 1ll << q_bits;
+  for (int i = 0; i < 16; i++) {
+    const long long off = q->qparams[i][0], sc = q->qparams[i][1];
+    if (off < 0 || sc < 0 || 9180 * sc + off > 0x7fffffffll) return o;
+    long long t;
+    if (off >= one) t = 1;
+    else if (sc == 0) t = 0x7fffffff;
+    else t = (one - off + sc - 1) / sc;
+    o.t[i] = (int)(t < 1 ? 1 : (t > 0x7fffffff ? 0x7fffffff : t));
+  }
+  o.ok = 1;
+  return o;
+}
+
 static int std_scan_kind(const jmb_quant_desc *q) {
   static const unsigned char Z4[16][2] = {{0,0}, {1,0}, {0,1}, {0,2}, {1,1}, {2,0}, {3,0}, {2,1}, {1,2}, {0,3}, {1,3}, {2,2}, {3,1}, {3,2}, {2,3}, {3,3}};
   static const unsigned char Z8[64][2] = {{0,0}, {1,0}, {0,1}, {0,2}, {1,1}, {2,0}, {3,0}, {2,1}, {1,2}, {0,3}, {0,4}, {1,3}, {2,2}, {3,1}, {4,0}, {5,0}, {4,1}, {3,2}, {2,3}, {1,4}, {0,5}, {0,6}, {1,5}, {2,4}, {3,3}, {4,2}, {5,1}, {6,0}, {7,0}, {6,1}, {5,2}, {4,3}, {3,4}, {2,5}, {1,6}, {0,7}, {1,7}, {2,6}, {3,5}, {4,4}, {5,3}, {6,2}, {7,1}, {7,2}, {6,3}, {5,4}, {4,5}, {3,6}, {2,7}, {3,7}, {4,6}, {5,5}, {6,4}, {7,3}, {7,4}, {6,5}, {5,6}, {4,7}, {5,7}, {6,6}, {7,5}, {7,6}, {6,7}, {7,7}};
@@ -1132,7 +1165,8 @@ int jmb_mc_tq_modes_compact(jmb_ctx *ctx, const jmb_me_res *res, int n_mb, unsig
   // mb / mb_w inside the kernel is a multiply by ceil(2^32 / mb_w): exact while n_mb * mb_w < 2^32 (an 8K picture: 2^26)
   if ((unsigned long long)n_mb * (unsigned long long)mb_w >= (1ull << 32)) return jmb_fail(ctx, JMB_ERR_UNSUPPORTED, "jmb_mc_tq_modes_compact: %d macroblocks in rows of %d", n_mb, mb_w);
   const unsigned mb_w_rcp = (unsigned)(((1ull << 32) + (unsigned)mb_w - 1) / (unsigned)mb_w);
-#define JMB_MTQC(NN, STD, GRID) k_mc_tq_modes_c<NN, STD><<<GRID, 128, 0, ctx->stream>>>(d_res, n_mb, mb_w, mb_w_rcp, mode_mask, *q, ctx->cur, ctx->cur_pitch, \
+  const TqThr thr = tq_thresholds(q);
+#define JMB_MTQC(NN, STD, GRID) k_mc_tq_modes_c<NN, STD><<<GRID, 128, 0, ctx->stream>>>(d_res, n_mb, mb_w, mb_w_rcp, mode_mask, *q, thr, ctx->cur, ctx->cur_pitch, \
         r0.planes, r0.plane_bytes, r0.pitch, ctx->cur_w, ctx->cur_h, d_heads, d_tok, token_cap, d_cnt)
   {
     const int kind = std_scan_kind(q);
