@@ -522,7 +522,7 @@ int jmb_deblock_picture(jmb_ctx *ctx, uint8_t *luma, int pitch, uint8_t *cb, uin
                         int slice_type, int direct_8x8_inference, const jmb_db_mb *mbs, int loc);
 
 /* kernel names: subpel_planes, pack_cur, int_search, subpel_refine, dist, ffs_surfaces, forward,
- * quant_blocks, mc_tq, pred_from_results, gen_requests, epzs, chroma, deblock, argmin */
+ * quant_blocks, mc_tq, pred_from_results, gen_requests (EPZS request generation and result packing), epzs, chroma, deblock, argmin */
 int jmb_timing_enable(jmb_ctx *ctx, int on);      /* also clears the accumulated samples */
 int jmb_timing_get(jmb_ctx *ctx, const char *kernel, double *total_ms, int *launches);
 
